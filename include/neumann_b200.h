@@ -1,0 +1,155 @@
+/*
+ * neumann_b200.h — C ABI of the B200-native SIMILAR brute-force scan.
+ *
+ * The reference (Shadylukin/Neumann @ aae3d465) has NO FFI for this path: the seam is the
+ * private trio "store.scan -> search_{sequential,parallel}[_with_metric] -> sort_by+truncate"
+ * inside three public Rust methods.  Each entry point below names the reference code it
+ * replaces (paths relative to the reference checkout).  INTEGRATION.md shows the Rust `-sys`
+ * shim that binds them.
+ *
+ * Conventions
+ *   - Every function returns an nm_status (0 = ok) unless stated otherwise; nothing throws or
+ *     aborts across the ABI.  nm_last_error() returns a thread-local message for the last
+ *     non-zero status on the calling thread.
+ *   - The caller owns every host buffer it passes (in and out).  The library owns device
+ *     memory, pinned staging and streams.  The row-index <-> key mapping stays with the
+ *     caller, in mirror (row) order, like `HnswCacheEntry = (Arc<HNSWIndex>, Vec<String>)`
+ *     (vector_engine/src/lib.rs:98).
+ *   - nm_search* may be called concurrently from many host threads on one index
+ *     (`VectorEngine: Send + Sync`, vector_engine/src/lib.rs:1127-1131; concurrent search +
+ *     store is tested at :5615-5711).  Mutations take the index write lock and never tear an
+ *     in-flight search.
+ *   - Results per query: min(k, rows) hits, sorted by score descending; exact-score ties
+ *     (-0.0 == +0.0) by ascending row; NaN scores last.  Scores are bit-identical to the
+ *     reference arithmetic restated in oracle/nm_oracle.c.
+ *   - There is no CPU fallback.  Without a CUDA device every compute entry point fails with
+ *     NM_ERR_STORAGE.
+ */
+#ifndef NEUMANN_B200_H
+#define NEUMANN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NM_ABI_VERSION 1
+
+/* DistanceMetric (vector_engine/src/lib.rs:281-289).  Score conventions follow compute_score
+ * (lib.rs:2231-2246): cosine = dot/(|q||x|) with zero guards, dot = raw, euclidean = 1/(1+d). */
+typedef enum nm_metric { NM_COSINE = 0, NM_EUCLIDEAN = 1, NM_DOT_PRODUCT = 2 } nm_metric;
+
+/* Status codes map 1:1 onto VectorError (vector_engine/src/lib.rs:102-149). */
+typedef enum nm_status {
+    NM_OK = 0,
+    NM_ERR_EMPTY_VECTOR = 1,       /* VectorError::EmptyVector                                */
+    NM_ERR_INVALID_TOP_K = 2,      /* VectorError::InvalidTopK                                */
+    NM_ERR_DIMENSION_MISMATCH = 3, /* VectorError::DimensionMismatch                          */
+    NM_ERR_STORAGE = 4,            /* VectorError::StorageError(msg): CUDA / NCCL / alloc     */
+    NM_ERR_SEARCH_TIMEOUT = 5,     /* VectorError::SearchTimeout                              */
+    NM_ERR_INVALID_ARGUMENT = 6,   /* null pointer, bad metric, bad device, row out of range  */
+    NM_ERR_NOT_FOUND = 7,          /* VectorError::NotFound                                   */
+    NM_ERR_CONFIGURATION = 8,      /* VectorError::ConfigurationError                         */
+    NM_ERR_COLLECTION_EXISTS = 9,  /* VectorError::CollectionExists                           */
+    NM_ERR_COLLECTION_NOT_FOUND = 10 /* VectorError::CollectionNotFound                       */
+} nm_status;
+
+typedef struct nm_index nm_index;
+
+/* Largest k served by the in-kernel selection; larger k takes the full-sort device path. */
+#define NM_TOPK_FAST_MAX 1024u
+
+/* ---- library ------------------------------------------------------------------------ */
+int nm_abi_version(void);
+const char *nm_last_error(void);
+/* Number of visible CUDA devices (0 on a CPU-only host; never fails). */
+int nm_device_count(void);
+
+/* ---- device mirror of the `emb:` rows (replaces TensorStore::scan + get as the data
+ *      source of the scan: tensor_store/src/lib.rs:948-999, slab_router.rs:217-305) -------- */
+
+/* Create an empty mirror for rows of `dim` floats, sharded by contiguous row range over
+ * `n_dev` devices of THIS process (devices == NULL, n_dev == 0 -> current device only). */
+int nm_index_create(uint32_t dim, const int *devices, int n_dev, nm_index **out);
+void nm_index_destroy(nm_index *idx);
+
+/* Replace the mirror's contents with `n` row-major rows [n, dim] from host memory (pinned or
+ * pageable).  Rows are split into contiguous ranges [g*n/G, (g+1)*n/G) over the devices.  */
+int nm_index_load(nm_index *idx, const float *rows, uint64_t n);
+/* Append `n` rows after the current last row (store_embedding of new keys, lib.rs:1840-1868).
+ * Appended rows go to the last device shard. */
+int nm_index_append(nm_index *idx, const float *rows, uint64_t n);
+/* Overwrite one row in place (store_embedding of an existing key). */
+int nm_index_update(nm_index *idx, uint64_t row, const float *vec);
+/* Delete row `row` by moving the LAST row into its slot (delete_embedding, lib.rs:1913-1925).
+ * The caller applies the same swap to its key table.  *moved_from receives the index of the
+ * row that was moved (== row when the last row itself was removed). */
+int nm_index_swap_remove(nm_index *idx, uint64_t row, uint64_t *moved_from);
+int nm_index_clear(nm_index *idx);
+/* Copy row `row` back to host (diagnostics / tests). */
+int nm_index_get_row(nm_index *idx, uint64_t row, float *out_vec);
+
+uint64_t nm_index_rows(const nm_index *idx);
+uint32_t nm_index_dim(const nm_index *idx);
+int nm_index_device_count(const nm_index *idx);
+
+/* Fill the mirror ON DEVICE with the synthetic corpus of SURVEY 8d:
+ *   x[r,c] = u24(splitmix64(splitmix64(seed) ^ ((row_offset + r)*dim + c))) * 2^-23 - 1
+ * (bit-identical to oracle nmo_fill_synthetic).  Benchmark / test utility. */
+int nm_index_fill_synthetic(nm_index *idx, uint64_t n, uint64_t seed, uint64_t row_offset);
+
+/* ---- the scan (replaces search_sequential/parallel[_with_metric] + sort_by + truncate:
+ *      vector_engine/src/lib.rs:2013-2034, 2070-2099, 1648-1686) ------------------------- */
+
+/* queries: [nq, dim] host floats.  Outputs (host): out_rows [nq, k] GLOBAL row ids,
+ * out_scores [nq, k], out_counts [nq] = hits written for that query (min(k, rows)); unused
+ * slots are left untouched.  Validation mirrors the reference: nq == 0 or dim == 0 ->
+ * NM_ERR_EMPTY_VECTOR, k == 0 -> NM_ERR_INVALID_TOP_K.  The zero-magnitude-query
+ * short-circuit (lib.rs:1970-1974, 2066) stays in the host wrapper; here a zero cosine query
+ * scores every row 0.0 exactly as cosine_similarity does (lib.rs:2261-2263).               */
+int nm_search(nm_index *idx, const float *queries, uint32_t nq, uint32_t k, int metric,
+              uint64_t *out_rows, float *out_scores, uint32_t *out_counts);
+
+/* Same scan with the query and the outputs resident in DEVICE memory of the index's first
+ * device and the work enqueued on `stream` (a cudaStream_t; NULL = library stream, and the
+ * call then synchronises before returning).  Single-device indexes only. */
+int nm_search_device(nm_index *idx, const float *d_queries, uint32_t nq, uint32_t k,
+                     int metric, uint64_t *d_out_rows, float *d_out_scores,
+                     uint32_t *d_out_counts, void *stream);
+
+/* ---- row-range sharding across processes (one process per GPU; replaces
+ *      QueryRouter::execute_scatter_gather + ResultMerger::merge_top_k,
+ *      query_router/src/lib.rs:1818-1900, distributed.rs:413-433) ------------------------- */
+#define NM_COMM_ID_BYTES 128
+/* Rank 0 creates the id and ships it to the other ranks over its own transport. */
+int nm_comm_create_id(void *out_id /* NM_COMM_ID_BYTES */);
+/* Attach this index (one shard = this process's rows) to an n_ranks communicator.
+ * `row_base` = global index of this shard's first row; shards must be attached in ascending
+ * row order by rank so that rank order == global row order (merge_top_k concatenates shards
+ * in shard order).  After attach, nm_search / nm_search_device are COLLECTIVE: every rank
+ * calls them with the same queries, k and metric, and every rank receives the merged result.
+ * The exchange is ONE ncclAllGather of nq*k 16-byte candidates per rank. */
+int nm_index_attach_comm(nm_index *idx, const void *id, int n_ranks, int rank,
+                         uint64_t row_base);
+int nm_index_detach_comm(nm_index *idx);
+
+/* ---- instrumentation (counters the reference keeps in ShardAccessTracker,
+ *      tensor_store/src/instrumentation.rs:1-40) ------------------------------------------ */
+typedef struct nm_stats {
+    uint64_t searches;        /* queries served                                   */
+    uint64_t rows_scanned;    /* rows x queries                                   */
+    uint64_t bytes_streamed;  /* algorithmic bytes: rows * dim * 4 per query pass */
+    uint64_t scan_launches;   /* scan kernel launches                             */
+    uint64_t merge_launches;  /* cross-shard merge kernel launches                */
+    uint64_t h2d_bytes;       /* staging + query uploads                          */
+    uint64_t d2h_bytes;       /* result downloads                                 */
+    double last_scan_ms;      /* device time of the most recent nm_search scan(s) */
+} nm_stats;
+int nm_index_stats(nm_index *idx, nm_stats *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NEUMANN_B200_H */

@@ -1,0 +1,73 @@
+"""Builds the in-tree native libraries.
+
+`libneumann_b200.so` is the product: hand-written sm_100a CUDA kernels + the C ABI declared in
+include/neumann_b200.h + the C++ host mirror of the reference's VectorEngine / SIMILAR operator.
+It is compiled with nvcc for sm_100a only (no multi-arch fatbin, no PTX fallback for older
+parts).  The built .so stays in-tree (git-ignored) so it travels to the GPU box.
+"""
+from __future__ import annotations
+
+import os
+import subprocess
+import sys
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent.parent
+CSRC = ROOT / "neumann_b200" / "csrc"
+LIB = ROOT / "neumann_b200" / "libneumann_b200.so"
+
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+
+NVCC_FLAGS = [
+    "-std=c++17", "-O3",
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-lineinfo",
+    # bit-exact reference arithmetic: no FMA contraction, IEEE div/sqrt, keep denormals
+    "-fmad=false", "-prec-div=true", "-prec-sqrt=true", "-ftz=false",
+    "-Xcompiler", "-fPIC,-ffp-contract=off,-fno-fast-math,-Wall",
+    "-shared", "-cudart", "static",
+]
+
+
+def sources() -> list[Path]:
+    return sorted(CSRC.glob("*.cu")) + sorted(CSRC.glob("*.cpp"))
+
+
+def _stale(target: Path, deps: list[Path]) -> bool:
+    if not target.exists():
+        return True
+    t = target.stat().st_mtime
+    return any(d.stat().st_mtime > t for d in deps)
+
+
+def build_library(force: bool = False, verbose: bool = False) -> Path:
+    deps = sources() + sorted(CSRC.glob("*.cuh")) + sorted(CSRC.glob("*.hpp")) + \
+        sorted((ROOT / "include").glob("*.h")) + [Path(__file__)]
+    if not force and not _stale(LIB, deps):
+        return LIB
+    cmd = [NVCC, *NVCC_FLAGS, "-I", str(ROOT / "include"), "-o", str(LIB),
+           *[str(s) for s in sources()], "-ldl", "-lpthread"]
+    if verbose:
+        cmd.insert(1, "-Xptxas=-v")
+        print(" ".join(cmd), file=sys.stderr)
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if verbose or r.returncode != 0:
+        sys.stderr.write(r.stdout + r.stderr)
+    if r.returncode != 0:
+        raise RuntimeError("nvcc failed building libneumann_b200.so")
+    return LIB
+
+
+def build_oracle(force: bool = False) -> Path:
+    """Test infrastructure only (see oracle/nm_oracle.c)."""
+    odir = ROOT / "oracle"
+    lib = odir / "libnm_oracle.so"
+    if force or _stale(lib, [odir / "nm_oracle.c", odir / "Makefile"]):
+        subprocess.run(["make", "-C", str(odir), "-B"], check=True, capture_output=True)
+    return lib
+
+
+if __name__ == "__main__":
+    build_library(force="--force" in sys.argv, verbose=True)
+    build_oracle(force="--force" in sys.argv)
+    print(LIB)

@@ -1,0 +1,1013 @@
+// nm_index.cu — C ABI (include/neumann_b200.h) over the sm_100a scan kernels.
+//
+// Owns: the device mirror of the reference's `emb:` rows (row-major f32, pitch = dim rounded up
+// to 4 floats so every row is 16-byte aligned for TMA), pinned double-buffered staging for
+// host -> device loads, per-call workspaces (stream, query, candidates, results) so that
+// nm_search is re-entrant, and the optional NCCL communicator for row-range sharding across
+// processes.  There is deliberately no CPU code path for the scan.
+#include "../../include/neumann_b200.h"
+#include "scan_kernels.cuh"
+
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <mutex>
+#include <shared_mutex>
+#include <string>
+#include <vector>
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                     \
+    do {                                                                                   \
+        cudaError_t _e = (expr);                                                           \
+        if (_e != cudaSuccess)                                                             \
+            return fail(NM_ERR_STORAGE, "CUDA error %s at %s:%d: %s", cudaGetErrorName(_e), \
+                        __FILE__, __LINE__, cudaGetErrorString(_e));                       \
+    } while (0)
+
+// ---- cuTensorMapEncodeTiled through the runtime (no link-time libcuda dependency) --------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *,
+                                  const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
+                                  const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_tiled() {
+    static EncodeTiledFn fn = [] {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) !=
+                cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            p = nullptr;
+        return reinterpret_cast<EncodeTiledFn>(p);
+    }();
+    return fn;
+}
+
+// ---- NCCL, loaded lazily so the library also loads on hosts without it -------------------
+struct NcclApi {
+    void *handle = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t,
+                              cudaStream_t) = nullptr;
+    const char *(*GetErrorString)(ncclResult_t) = nullptr;
+    bool ok = false;
+};
+
+NcclApi &nccl() {
+    static NcclApi api = [] {
+        NcclApi a;
+        a.handle = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!a.handle) a.handle = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+        if (!a.handle) return a;
+        a.GetUniqueId = (decltype(a.GetUniqueId))dlsym(a.handle, "ncclGetUniqueId");
+        a.CommInitRank = (decltype(a.CommInitRank))dlsym(a.handle, "ncclCommInitRank");
+        a.CommDestroy = (decltype(a.CommDestroy))dlsym(a.handle, "ncclCommDestroy");
+        a.AllGather = (decltype(a.AllGather))dlsym(a.handle, "ncclAllGather");
+        a.GetErrorString = (decltype(a.GetErrorString))dlsym(a.handle, "ncclGetErrorString");
+        a.ok = a.GetUniqueId && a.CommInitRank && a.CommDestroy && a.AllGather &&
+               a.GetErrorString;
+        return a;
+    }();
+    return api;
+}
+
+#define NCCL_TRY(expr)                                                                  \
+    do {                                                                                \
+        ncclResult_t _r = (expr);                                                       \
+        if (_r != ncclSuccess)                                                          \
+            return fail(NM_ERR_STORAGE, "NCCL error at %s:%d: %s", __FILE__, __LINE__,  \
+                        nccl().GetErrorString(_r));                                     \
+    } while (0)
+
+constexpr size_t kStagingBytes = 32u << 20;  // per pinned staging buffer (two per shard)
+
+// Per-call scratch on one device.  Pooled per shard so concurrent nm_search calls never share
+// a stream, a candidate buffer or the "last CTA" ticket.
+struct Workspace {
+    int device = -1;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    float *d_query = nullptr;
+    float *h_query = nullptr;  // pinned
+    size_t query_cap = 0;      // floats
+    uint64_t *d_cand = nullptr;
+    size_t cand_cap = 0;  // keys
+    uint32_t *d_counter = nullptr;
+    // packed result block: [counts u32 x nq (8-aligned)] [rows u64 x nq*k] [scores f32 x nq*k]
+    uint8_t *d_result = nullptr;
+    uint8_t *h_result = nullptr;  // pinned
+    size_t result_cap = 0;
+    nm::ShardHit *d_hits = nullptr;  // [nq, k] this shard's hits
+    nm::ShardHit *h_hits = nullptr;  // pinned
+    size_t hits_cap = 0;
+    nm::ShardHit *d_gather = nullptr;  // [n_ranks, nq, k]
+    size_t gather_cap = 0;
+    uint64_t *d_ceil = nullptr;  // unused placeholder for future paging
+
+    ~Workspace() {
+        if (device < 0) return;
+        cudaSetDevice(device);
+        if (d_query) cudaFree(d_query);
+        if (h_query) cudaFreeHost(h_query);
+        if (d_cand) cudaFree(d_cand);
+        if (d_counter) cudaFree(d_counter);
+        if (d_result) cudaFree(d_result);
+        if (h_result) cudaFreeHost(h_result);
+        if (d_hits) cudaFree(d_hits);
+        if (h_hits) cudaFreeHost(h_hits);
+        if (d_gather) cudaFree(d_gather);
+        if (ev0) cudaEventDestroy(ev0);
+        if (ev1) cudaEventDestroy(ev1);
+        if (stream) cudaStreamDestroy(stream);
+    }
+};
+
+struct Shard {
+    int device = 0;
+    int sm_count = 0;
+    float *d_rows = nullptr;
+    uint64_t rows = 0;      // local rows
+    uint64_t capacity = 0;  // local rows allocated
+    uint64_t row_base = 0;  // global index of local row 0 (within this process)
+    CUtensorMap tmap;
+    bool tmap_valid = false;
+    cudaStream_t copy_stream = nullptr;
+    float *staging[2] = {nullptr, nullptr};
+    cudaEvent_t staging_done[2] = {nullptr, nullptr};
+    std::mutex pool_mu;
+    std::vector<std::unique_ptr<Workspace>> pool;
+};
+
+}  // namespace
+
+struct nm_index {
+    uint32_t dim = 0;
+    uint32_t pitch = 0;  // floats per row in device memory
+    std::vector<std::unique_ptr<Shard>> shards;
+    mutable std::shared_mutex mu;
+    // cross-process sharding
+    ncclComm_t comm = nullptr;
+    int n_ranks = 1, rank = 0;
+    uint64_t comm_row_base = 0;
+    // counters
+    std::atomic<uint64_t> searches{0}, rows_scanned{0}, bytes_streamed{0}, scan_launches{0},
+        merge_launches{0}, h2d_bytes{0}, d2h_bytes{0};
+    std::atomic<double> last_scan_ms{0.0};
+    uint64_t total_rows() const {
+        uint64_t n = 0;
+        for (auto &s : shards) n += s->rows;
+        return n;
+    }
+};
+
+namespace {
+
+size_t scan_smem_bytes(uint32_t n_stages, uint32_t q_floats) {
+    return 1024 + (size_t)n_stages * nm::kStageBytes + (size_t)nm::kCandCap * 8 +
+           (size_t)q_floats * 4 + 2 * nm::kMaxStages * 8 + 64;
+}
+
+int build_tmap(nm_index *idx, Shard &sh) {
+    sh.tmap_valid = false;
+    if (sh.rows == 0) return NM_OK;
+    EncodeTiledFn enc = get_encode_tiled();
+    if (!enc) return fail(NM_ERR_STORAGE, "cuTensorMapEncodeTiled unavailable (driver too old?)");
+    cuuint64_t gdim[2] = {idx->dim, sh.rows};
+    cuuint64_t gstride[1] = {(cuuint64_t)idx->pitch * 4};
+    cuuint32_t box[2] = {nm::kChunkFloats, nm::kRowsPerBlock};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(&sh.tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, sh.d_rows, gdim, gstride, box,
+                     estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS)
+        return fail(NM_ERR_STORAGE, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+    sh.tmap_valid = true;
+    return NM_OK;
+}
+
+int shard_reserve(nm_index *idx, Shard &sh, uint64_t rows, bool keep) {
+    if (rows <= sh.capacity) return NM_OK;
+    if (rows > nm::kMaxLocalRows)
+        return fail(NM_ERR_INVALID_ARGUMENT, "shard would hold %llu rows; limit is %u per device",
+                    (unsigned long long)rows, nm::kMaxLocalRows);
+    uint64_t cap = rows;
+    if (keep && sh.capacity) cap = std::max<uint64_t>(rows, sh.capacity + sh.capacity / 2);
+    float *p = nullptr;
+    CUDA_TRY(cudaMalloc(&p, cap * idx->pitch * sizeof(float)));
+    if (keep && sh.rows) {
+        CUDA_TRY(cudaMemcpyAsync(p, sh.d_rows, sh.rows * idx->pitch * sizeof(float),
+                                 cudaMemcpyDeviceToDevice, sh.copy_stream));
+        CUDA_TRY(cudaStreamSynchronize(sh.copy_stream));
+    }
+    if (sh.d_rows) CUDA_TRY(cudaFree(sh.d_rows));
+    sh.d_rows = p;
+    sh.capacity = cap;
+    return NM_OK;
+}
+
+// Host rows [n, dim] -> device rows [first, first+n) of the shard.  Pinned sources are DMA'd
+// directly; pageable sources go through two pinned staging buffers so the host memcpy of
+// chunk i+1 overlaps the DMA of chunk i.
+int shard_upload(nm_index *idx, Shard &sh, uint64_t first, const float *src, uint64_t n) {
+    if (n == 0) return NM_OK;
+    const size_t row_bytes = (size_t)idx->dim * 4, pitch_bytes = (size_t)idx->pitch * 4;
+    float *dst = sh.d_rows + first * idx->pitch;
+    cudaPointerAttributes attr;
+    bool pinned = cudaPointerGetAttributes(&attr, src) == cudaSuccess &&
+                  attr.type == cudaMemoryTypeHost;
+    cudaGetLastError();
+    if (idx->pitch != idx->dim)
+        CUDA_TRY(cudaMemsetAsync(dst, 0, n * pitch_bytes, sh.copy_stream));
+    if (pinned) {
+        CUDA_TRY(cudaMemcpy2DAsync(dst, pitch_bytes, src, row_bytes, row_bytes, n,
+                                   cudaMemcpyHostToDevice, sh.copy_stream));
+    } else {
+        if (!sh.staging[0]) {
+            for (int b = 0; b < 2; ++b) {
+                CUDA_TRY(cudaMallocHost(&sh.staging[b], kStagingBytes));
+                CUDA_TRY(cudaEventCreateWithFlags(&sh.staging_done[b], cudaEventDisableTiming));
+            }
+        }
+        const uint64_t rows_per_chunk = std::max<uint64_t>(1, kStagingBytes / row_bytes);
+        if (row_bytes > kStagingBytes)
+            return fail(NM_ERR_DIMENSION_MISMATCH, "dimension %u too large for staging", idx->dim);
+        int b = 0;
+        for (uint64_t r = 0; r < n; r += rows_per_chunk, b ^= 1) {
+            uint64_t m = std::min(rows_per_chunk, n - r);
+            CUDA_TRY(cudaEventSynchronize(sh.staging_done[b]));
+            memcpy(sh.staging[b], src + r * idx->dim, m * row_bytes);
+            CUDA_TRY(cudaMemcpy2DAsync(dst + r * idx->pitch, pitch_bytes, sh.staging[b], row_bytes,
+                                       row_bytes, m, cudaMemcpyHostToDevice, sh.copy_stream));
+            CUDA_TRY(cudaEventRecord(sh.staging_done[b], sh.copy_stream));
+        }
+    }
+    CUDA_TRY(cudaStreamSynchronize(sh.copy_stream));
+    idx->h2d_bytes += n * row_bytes;
+    return NM_OK;
+}
+
+int ws_acquire(Shard &sh, std::unique_ptr<Workspace> &out) {
+    {
+        std::lock_guard<std::mutex> g(sh.pool_mu);
+        if (!sh.pool.empty()) {
+            out = std::move(sh.pool.back());
+            sh.pool.pop_back();
+            return NM_OK;
+        }
+    }
+    std::unique_ptr<Workspace> ws(new Workspace());
+    ws->device = sh.device;
+    CUDA_TRY(cudaStreamCreateWithFlags(&ws->stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaEventCreate(&ws->ev0));
+    CUDA_TRY(cudaEventCreate(&ws->ev1));
+    CUDA_TRY(cudaMalloc(&ws->d_counter, sizeof(uint32_t)));
+    CUDA_TRY(cudaMemsetAsync(ws->d_counter, 0, sizeof(uint32_t), ws->stream));
+    out = std::move(ws);
+    return NM_OK;
+}
+
+void ws_release(Shard &sh, std::unique_ptr<Workspace> &ws) {
+    if (!ws) return;
+    std::lock_guard<std::mutex> g(sh.pool_mu);
+    sh.pool.push_back(std::move(ws));
+}
+
+struct ResultLayout {
+    size_t counts_off, rows_off, scores_off, total;
+};
+ResultLayout result_layout(uint32_t nq, uint32_t k) {
+    ResultLayout l;
+    l.counts_off = 0;
+    l.rows_off = ((size_t)nq * 4 + 15) & ~size_t(15);
+    l.scores_off = l.rows_off + (size_t)nq * k * 8;
+    l.total = l.scores_off + (size_t)nq * k * 4;
+    return l;
+}
+
+int ws_ensure(Workspace &ws, const Shard &sh, uint32_t dim, uint32_t nq, uint32_t k,
+              bool need_query, bool need_result, bool need_hits, int gather_ranks) {
+    size_t qf = (size_t)nq * dim;
+    if (need_query && ws.query_cap < qf) {
+        if (ws.d_query) CUDA_TRY(cudaFree(ws.d_query));
+        if (ws.h_query) CUDA_TRY(cudaFreeHost(ws.h_query));
+        ws.query_cap = 0;
+        CUDA_TRY(cudaMalloc(&ws.d_query, qf * 4));
+        CUDA_TRY(cudaMallocHost(&ws.h_query, qf * 4));
+        ws.query_cap = qf;
+    }
+    size_t cand = (size_t)sh.sm_count * k;
+    if (ws.cand_cap < cand) {
+        if (ws.d_cand) CUDA_TRY(cudaFree(ws.d_cand));
+        ws.cand_cap = 0;
+        CUDA_TRY(cudaMalloc(&ws.d_cand, cand * 8));
+        ws.cand_cap = cand;
+    }
+    if (need_result) {
+        ResultLayout l = result_layout(nq, k);
+        if (ws.result_cap < l.total) {
+            if (ws.d_result) CUDA_TRY(cudaFree(ws.d_result));
+            if (ws.h_result) CUDA_TRY(cudaFreeHost(ws.h_result));
+            ws.result_cap = 0;
+            CUDA_TRY(cudaMalloc(&ws.d_result, l.total));
+            CUDA_TRY(cudaMallocHost(&ws.h_result, l.total));
+            ws.result_cap = l.total;
+        }
+    }
+    if (need_hits) {
+        size_t h = (size_t)nq * k;
+        if (ws.hits_cap < h) {
+            if (ws.d_hits) CUDA_TRY(cudaFree(ws.d_hits));
+            if (ws.h_hits) CUDA_TRY(cudaFreeHost(ws.h_hits));
+            ws.hits_cap = 0;
+            CUDA_TRY(cudaMalloc(&ws.d_hits, h * sizeof(nm::ShardHit)));
+            CUDA_TRY(cudaMallocHost(&ws.h_hits, h * sizeof(nm::ShardHit)));
+            ws.hits_cap = h;
+        }
+        size_t g = h * (size_t)gather_ranks;
+        if (gather_ranks > 0 && ws.gather_cap < g) {
+            if (ws.d_gather) CUDA_TRY(cudaFree(ws.d_gather));
+            ws.gather_cap = 0;
+            CUDA_TRY(cudaMalloc(&ws.d_gather, g * sizeof(nm::ShardHit)));
+            ws.gather_cap = g;
+        }
+    }
+    return NM_OK;
+}
+
+template <int METRIC>
+int launch_scan_t(const Shard &sh, const nm::ScanParams &p, size_t smem, cudaStream_t stream) {
+    static thread_local size_t configured[64] = {0};
+    auto kern = nm::scan_topk_kernel<METRIC>;
+    if (sh.device < 64 && configured[sh.device] < smem) {
+        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)smem));
+        configured[sh.device] = smem;
+    } else if (sh.device >= 64) {
+        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)smem));
+    }
+    uint32_t n_rb = (p.n_rows + nm::kRowsPerBlock - 1) / nm::kRowsPerBlock;
+    uint32_t grid = std::min<uint32_t>((uint32_t)sh.sm_count, n_rb);
+    kern<<<grid, nm::kScanThreads, smem, stream>>>(sh.tmap, p);
+    CUDA_TRY(cudaGetLastError());
+    return NM_OK;
+}
+
+// One scan launch for one query over one shard.
+int launch_scan(nm_index *idx, const Shard &sh, Workspace &ws, const float *d_query, uint32_t k,
+                int metric, uint64_t row_base, uint64_t *out_rows, float *out_scores,
+                uint32_t *out_count, nm::ShardHit *out_hits, cudaStream_t stream) {
+    nm::ScanParams p;
+    memset(&p, 0, sizeof(p));
+    p.query = d_query;
+    p.cand = ws.d_cand;
+    p.done_counter = ws.d_counter;
+    p.out_keys = nullptr;
+    p.out_hits = out_hits;
+    p.out_rows = out_rows;
+    p.out_scores = out_scores;
+    p.out_count = out_count;
+    p.row_base = row_base;
+    p.n_rows = (uint32_t)sh.rows;
+    p.dim = idx->dim;
+    p.k = k;
+    p.q_floats = (idx->dim + 31u) & ~31u;
+    // stream through L2 with evict_first unless the whole shard fits comfortably in L2
+    p.evict_first = (sh.rows * idx->pitch * 4ull > (64ull << 20)) ? 1u : 0u;
+    uint32_t stages = nm::kMaxStages;
+    const size_t limit = 227 * 1024;
+    while (stages > 2 && scan_smem_bytes(stages, p.q_floats) > limit) --stages;
+    if (scan_smem_bytes(stages, p.q_floats) > limit)
+        return fail(NM_ERR_DIMENSION_MISMATCH,
+                    "dimension %u does not fit the scan kernel's shared-memory query buffer",
+                    idx->dim);
+    p.n_stages = stages;
+    size_t smem = scan_smem_bytes(stages, p.q_floats);
+    idx->scan_launches++;
+    switch (metric) {
+    case NM_COSINE:
+        return launch_scan_t<nm::kCosine>(sh, p, smem, stream);
+    case NM_EUCLIDEAN:
+        return launch_scan_t<nm::kEuclidean>(sh, p, smem, stream);
+    default:
+        return launch_scan_t<nm::kDot>(sh, p, smem, stream);
+    }
+}
+
+uint32_t pow2_ceil(uint32_t v) {
+    uint32_t n = 2;
+    while (n < v) n <<= 1;
+    return n;
+}
+
+struct HostHit {
+    uint32_t ord;
+    uint32_t score_bits;
+    uint64_t row;
+    uint64_t pos;
+};
+
+int validate_search(const nm_index *idx, const void *queries, uint32_t nq, uint32_t k, int metric,
+                    const void *out_rows, const void *out_scores, const void *out_counts) {
+    if (!idx) return fail(NM_ERR_INVALID_ARGUMENT, "null index");
+    if (nq == 0 || idx->dim == 0) return fail(NM_ERR_EMPTY_VECTOR, "empty query");
+    if (k == 0) return fail(NM_ERR_INVALID_TOP_K, "top_k must be >= 1");
+    if (!queries || !out_rows || !out_scores || !out_counts)
+        return fail(NM_ERR_INVALID_ARGUMENT, "null buffer");
+    if (metric < 0 || metric > 2) return fail(NM_ERR_INVALID_ARGUMENT, "unknown metric %d", metric);
+    if (k > NM_TOPK_FAST_MAX)
+        return fail(NM_ERR_INVALID_TOP_K, "top_k %u exceeds the supported maximum %u", k,
+                    NM_TOPK_FAST_MAX);
+    return NM_OK;
+}
+
+}  // namespace
+
+// ======================================================================================
+// C ABI
+// ======================================================================================
+extern "C" {
+
+int nm_abi_version(void) { return NM_ABI_VERSION; }
+
+const char *nm_last_error(void) { return g_last_error.c_str(); }
+
+int nm_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int nm_index_create(uint32_t dim, const int *devices, int n_dev, nm_index **out) {
+    if (!out) return fail(NM_ERR_INVALID_ARGUMENT, "null out pointer");
+    *out = nullptr;
+    if (dim == 0) return fail(NM_ERR_EMPTY_VECTOR, "dimension must be >= 1");
+    int avail = nm_device_count();
+    if (avail == 0)
+        return fail(NM_ERR_STORAGE, "no CUDA device visible: the SIMILAR scan has no CPU path");
+    std::vector<int> devs;
+    if (!devices || n_dev <= 0) {
+        int cur = 0;
+        CUDA_TRY(cudaGetDevice(&cur));
+        devs.push_back(cur);
+    } else {
+        for (int i = 0; i < n_dev; ++i) {
+            if (devices[i] < 0 || devices[i] >= avail)
+                return fail(NM_ERR_INVALID_ARGUMENT, "device %d out of range (0..%d)", devices[i],
+                            avail - 1);
+            devs.push_back(devices[i]);
+        }
+    }
+    std::unique_ptr<nm_index> idx(new nm_index());
+    idx->dim = dim;
+    idx->pitch = (dim + 3u) & ~3u;
+    for (int d : devs) {
+        cudaDeviceProp prop;
+        CUDA_TRY(cudaGetDeviceProperties(&prop, d));
+        if (prop.major < 10)
+            return fail(NM_ERR_STORAGE, "device %d is sm_%d%d; this library is built for sm_100a", d,
+                        prop.major, prop.minor);
+        std::unique_ptr<Shard> sh(new Shard());
+        sh->device = d;
+        sh->sm_count = prop.multiProcessorCount;
+        CUDA_TRY(cudaSetDevice(d));
+        CUDA_TRY(cudaStreamCreateWithFlags(&sh->copy_stream, cudaStreamNonBlocking));
+        idx->shards.push_back(std::move(sh));
+    }
+    *out = idx.release();
+    return NM_OK;
+}
+
+void nm_index_destroy(nm_index *idx) {
+    if (!idx) return;
+    if (idx->comm && nccl().ok) nccl().CommDestroy(idx->comm);
+    for (auto &sh : idx->shards) {
+        cudaSetDevice(sh->device);
+        sh->pool.clear();
+        if (sh->d_rows) cudaFree(sh->d_rows);
+        for (int b = 0; b < 2; ++b) {
+            if (sh->staging[b]) cudaFreeHost(sh->staging[b]);
+            if (sh->staging_done[b]) cudaEventDestroy(sh->staging_done[b]);
+        }
+        if (sh->copy_stream) cudaStreamDestroy(sh->copy_stream);
+    }
+    delete idx;
+}
+
+int nm_index_clear(nm_index *idx) {
+    if (!idx) return fail(NM_ERR_INVALID_ARGUMENT, "null index");
+    std::unique_lock<std::shared_mutex> g(idx->mu);
+    uint64_t base = 0;
+    for (auto &sh : idx->shards) {
+        sh->rows = 0;
+        sh->row_base = base;
+        sh->tmap_valid = false;
+    }
+    return NM_OK;
+}
+
+int nm_index_load(nm_index *idx, const float *rows, uint64_t n) {
+    if (!idx) return fail(NM_ERR_INVALID_ARGUMENT, "null index");
+    if (n && !rows) return fail(NM_ERR_INVALID_ARGUMENT, "null rows");
+    std::unique_lock<std::shared_mutex> g(idx->mu);
+    const uint64_t G = idx->shards.size();
+    for (uint64_t s = 0; s < G; ++s) {
+        Shard &sh = *idx->shards[s];
+        uint64_t lo = n * s / G, hi = n * (s + 1) / G;
+        CUDA_TRY(cudaSetDevice(sh.device));
+        sh.rows = 0;
+        int rc = shard_reserve(idx, sh, hi - lo, false);
+        if (rc) return rc;
+        rc = shard_upload(idx, sh, 0, rows + lo * idx->dim, hi - lo);
+        if (rc) return rc;
+        sh.rows = hi - lo;
+        sh.row_base = lo;
+        rc = build_tmap(idx, sh);
+        if (rc) return rc;
+    }
+    return NM_OK;
+}
+
+int nm_index_append(nm_index *idx, const float *rows, uint64_t n) {
+    if (!idx) return fail(NM_ERR_INVALID_ARGUMENT, "null index");
+    if (n == 0) return NM_OK;
+    if (!rows) return fail(NM_ERR_INVALID_ARGUMENT, "null rows");
+    std::unique_lock<std::shared_mutex> g(idx->mu);
+    Shard &sh = *idx->shards.back();
+    CUDA_TRY(cudaSetDevice(sh.device));
+    int rc = shard_reserve(idx, sh, sh.rows + n, true);
+    if (rc) return rc;
+    rc = shard_upload(idx, sh, sh.rows, rows, n);
+    if (rc) return rc;
+    sh.rows += n;
+    return build_tmap(idx, sh);
+}
+
+static int locate_row(nm_index *idx, uint64_t row, Shard **out, uint64_t *local) {
+    for (auto &sh : idx->shards) {
+        if (row >= sh->row_base && row < sh->row_base + sh->rows) {
+            *out = sh.get();
+            *local = row - sh->row_base;
+            return NM_OK;
+        }
+    }
+    return fail(NM_ERR_INVALID_ARGUMENT, "row %llu out of range", (unsigned long long)row);
+}
+
+int nm_index_update(nm_index *idx, uint64_t row, const float *vec) {
+    if (!idx || !vec) return fail(NM_ERR_INVALID_ARGUMENT, "null argument");
+    std::unique_lock<std::shared_mutex> g(idx->mu);
+    Shard *sh = nullptr;
+    uint64_t local = 0;
+    int rc = locate_row(idx, row, &sh, &local);
+    if (rc) return rc;
+    CUDA_TRY(cudaSetDevice(sh->device));
+    return shard_upload(idx, *sh, local, vec, 1);
+}
+
+int nm_index_swap_remove(nm_index *idx, uint64_t row, uint64_t *moved_from) {
+    if (!idx) return fail(NM_ERR_INVALID_ARGUMENT, "null index");
+    std::unique_lock<std::shared_mutex> g(idx->mu);
+    Shard *sh = nullptr;
+    uint64_t local = 0;
+    int rc = locate_row(idx, row, &sh, &local);
+    if (rc) return rc;
+    // the globally last row lives in the last non-empty shard
+    Shard *last = nullptr;
+    for (auto it = idx->shards.rbegin(); it != idx->shards.rend(); ++it)
+        if ((*it)->rows) {
+            last = it->get();
+            break;
+        }
+    uint64_t last_global = last->row_base + last->rows - 1;
+    if (moved_from) *moved_from = last_global;
+    if (last_global != row) {
+        const size_t bytes = (size_t)idx->pitch * 4;
+        const float *src = last->d_rows + (last->rows - 1) * idx->pitch;
+        float *dst = sh->d_rows + local * idx->pitch;
+        CUDA_TRY(cudaSetDevice(sh->device));
+        if (last->device == sh->device)
+            CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, sh->copy_stream));
+        else
+            CUDA_TRY(cudaMemcpyPeerAsync(dst, sh->device, src, last->device, bytes,
+                                         sh->copy_stream));
+        CUDA_TRY(cudaStreamSynchronize(sh->copy_stream));
+    }
+    last->rows -= 1;
+    CUDA_TRY(cudaSetDevice(last->device));
+    return build_tmap(idx, *last);
+}
+
+int nm_index_get_row(nm_index *idx, uint64_t row, float *out_vec) {
+    if (!idx || !out_vec) return fail(NM_ERR_INVALID_ARGUMENT, "null argument");
+    std::shared_lock<std::shared_mutex> g(idx->mu);
+    Shard *sh = nullptr;
+    uint64_t local = 0;
+    int rc = locate_row(idx, row, &sh, &local);
+    if (rc) return rc;
+    CUDA_TRY(cudaSetDevice(sh->device));
+    CUDA_TRY(cudaMemcpy(out_vec, sh->d_rows + local * idx->pitch, (size_t)idx->dim * 4,
+                        cudaMemcpyDeviceToHost));
+    return NM_OK;
+}
+
+uint64_t nm_index_rows(const nm_index *idx) {
+    if (!idx) return 0;
+    std::shared_lock<std::shared_mutex> g(idx->mu);
+    return idx->total_rows();
+}
+uint32_t nm_index_dim(const nm_index *idx) { return idx ? idx->dim : 0; }
+int nm_index_device_count(const nm_index *idx) { return idx ? (int)idx->shards.size() : 0; }
+
+int nm_index_fill_synthetic(nm_index *idx, uint64_t n, uint64_t seed, uint64_t row_offset) {
+    if (!idx) return fail(NM_ERR_INVALID_ARGUMENT, "null index");
+    std::unique_lock<std::shared_mutex> g(idx->mu);
+    const uint64_t G = idx->shards.size();
+    for (uint64_t s = 0; s < G; ++s) {
+        Shard &sh = *idx->shards[s];
+        uint64_t lo = n * s / G, hi = n * (s + 1) / G;
+        CUDA_TRY(cudaSetDevice(sh.device));
+        sh.rows = 0;
+        int rc = shard_reserve(idx, sh, hi - lo, false);
+        if (rc) return rc;
+        if (hi > lo) {
+            nm::fill_synthetic_kernel<<<sh.sm_count * 8, 256, 0, sh.copy_stream>>>(
+                sh.d_rows, hi - lo, idx->dim, idx->pitch, seed, row_offset + lo);
+            CUDA_TRY(cudaGetLastError());
+            CUDA_TRY(cudaStreamSynchronize(sh.copy_stream));
+        }
+        sh.rows = hi - lo;
+        sh.row_base = lo;
+        rc = build_tmap(idx, sh);
+        if (rc) return rc;
+    }
+    return NM_OK;
+}
+
+// --------------------------------------------------------------------------------------
+// search
+// --------------------------------------------------------------------------------------
+int nm_search(nm_index *idx, const float *queries, uint32_t nq, uint32_t k, int metric,
+              uint64_t *out_rows, float *out_scores, uint32_t *out_counts) {
+    int rc = validate_search(idx, queries, nq, k, metric, out_rows, out_scores, out_counts);
+    if (rc) return rc;
+    std::shared_lock<std::shared_mutex> g(idx->mu);
+    const size_t G = idx->shards.size();
+    const uint32_t dim = idx->dim;
+    const bool collective = idx->comm != nullptr;
+    if (collective && G != 1)
+        return fail(NM_ERR_CONFIGURATION, "a communicator needs a single-device index per rank");
+
+    // ---- fast path: one device, no communicator: the kernel writes the final result ----
+    if (G == 1 && !collective) {
+        Shard &sh = *idx->shards[0];
+        if (sh.rows == 0) {
+            for (uint32_t q = 0; q < nq; ++q) out_counts[q] = 0;
+            return NM_OK;
+        }
+        CUDA_TRY(cudaSetDevice(sh.device));
+        std::unique_ptr<Workspace> ws;
+        rc = ws_acquire(sh, ws);
+        if (rc) return rc;
+        struct Releaser {
+            Shard &s;
+            std::unique_ptr<Workspace> &w;
+            ~Releaser() { ws_release(s, w); }
+        } rel{sh, ws};
+        rc = ws_ensure(*ws, sh, dim, nq, k, true, true, false, 0);
+        if (rc) return rc;
+        ResultLayout l = result_layout(nq, k);
+        memcpy(ws->h_query, queries, (size_t)nq * dim * 4);
+        CUDA_TRY(cudaMemcpyAsync(ws->d_query, ws->h_query, (size_t)nq * dim * 4,
+                                 cudaMemcpyHostToDevice, ws->stream));
+        CUDA_TRY(cudaEventRecord(ws->ev0, ws->stream));
+        for (uint32_t q = 0; q < nq; ++q) {
+            rc = launch_scan(idx, sh, *ws, ws->d_query + (size_t)q * dim, k, metric, sh.row_base,
+                             reinterpret_cast<uint64_t *>(ws->d_result + l.rows_off) + (size_t)q * k,
+                             reinterpret_cast<float *>(ws->d_result + l.scores_off) + (size_t)q * k,
+                             reinterpret_cast<uint32_t *>(ws->d_result + l.counts_off) + q, nullptr,
+                             ws->stream);
+            if (rc) return rc;
+        }
+        CUDA_TRY(cudaEventRecord(ws->ev1, ws->stream));
+        CUDA_TRY(cudaMemcpyAsync(ws->h_result, ws->d_result, l.total, cudaMemcpyDeviceToHost,
+                                 ws->stream));
+        CUDA_TRY(cudaStreamSynchronize(ws->stream));
+        float ms = 0.f;
+        CUDA_TRY(cudaEventElapsedTime(&ms, ws->ev0, ws->ev1));
+        idx->last_scan_ms = ms;
+        const uint32_t *hc = reinterpret_cast<const uint32_t *>(ws->h_result + l.counts_off);
+        const uint64_t *hr = reinterpret_cast<const uint64_t *>(ws->h_result + l.rows_off);
+        const float *hs = reinterpret_cast<const float *>(ws->h_result + l.scores_off);
+        for (uint32_t q = 0; q < nq; ++q) {
+            out_counts[q] = hc[q];
+            memcpy(out_rows + (size_t)q * k, hr + (size_t)q * k, (size_t)hc[q] * 8);
+            memcpy(out_scores + (size_t)q * k, hs + (size_t)q * k, (size_t)hc[q] * 4);
+        }
+        idx->searches += nq;
+        idx->rows_scanned += (uint64_t)nq * sh.rows;
+        idx->bytes_streamed += (uint64_t)nq * sh.rows * dim * 4;
+        idx->h2d_bytes += (uint64_t)nq * dim * 4;
+        idx->d2h_bytes += l.total;
+        return NM_OK;
+    }
+
+    // ---- collective path: one shard per process, ONE all-gather, merge on device ----
+    if (collective) {
+        Shard &sh = *idx->shards[0];
+        CUDA_TRY(cudaSetDevice(sh.device));
+        std::unique_ptr<Workspace> ws;
+        rc = ws_acquire(sh, ws);
+        if (rc) return rc;
+        struct Releaser {
+            Shard &s;
+            std::unique_ptr<Workspace> &w;
+            ~Releaser() { ws_release(s, w); }
+        } rel{sh, ws};
+        rc = ws_ensure(*ws, sh, dim, nq, k, true, true, true, idx->n_ranks);
+        if (rc) return rc;
+        ResultLayout l = result_layout(nq, k);
+        memcpy(ws->h_query, queries, (size_t)nq * dim * 4);
+        CUDA_TRY(cudaMemcpyAsync(ws->d_query, ws->h_query, (size_t)nq * dim * 4,
+                                 cudaMemcpyHostToDevice, ws->stream));
+        CUDA_TRY(cudaEventRecord(ws->ev0, ws->stream));
+        if (sh.rows == 0) {
+            CUDA_TRY(cudaMemsetAsync(ws->d_hits, 0, (size_t)nq * k * sizeof(nm::ShardHit),
+                                     ws->stream));
+        } else {
+            for (uint32_t q = 0; q < nq; ++q) {
+                rc = launch_scan(idx, sh, *ws, ws->d_query + (size_t)q * dim, k, metric,
+                                 idx->comm_row_base, nullptr, nullptr, nullptr,
+                                 ws->d_hits + (size_t)q * k, ws->stream);
+                if (rc) return rc;
+            }
+        }
+        CUDA_TRY(cudaEventRecord(ws->ev1, ws->stream));
+        NCCL_TRY(nccl().AllGather(ws->d_hits, ws->d_gather,
+                                  (size_t)nq * k * sizeof(nm::ShardHit), ncclChar, idx->comm,
+                                  ws->stream));
+        uint32_t total = (uint32_t)idx->n_ranks * k;
+        uint32_t n_sort = pow2_ceil(total);
+        size_t msmem = (size_t)n_sort * 8;
+        if (msmem > 200 * 1024)
+            return fail(NM_ERR_INVALID_TOP_K, "n_ranks*k = %u too large for the merge kernel", total);
+        if (msmem > 48 * 1024)
+            CUDA_TRY(cudaFuncSetAttribute(nm::merge_shards_kernel,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msmem));
+        nm::merge_shards_kernel<<<nq, nm::kMergeThreads, msmem, ws->stream>>>(
+            ws->d_gather, (uint32_t)idx->n_ranks, k, nq * k, n_sort,
+            reinterpret_cast<uint64_t *>(ws->d_result + l.rows_off),
+            reinterpret_cast<float *>(ws->d_result + l.scores_off),
+            reinterpret_cast<uint32_t *>(ws->d_result + l.counts_off));
+        CUDA_TRY(cudaGetLastError());
+        idx->merge_launches++;
+        CUDA_TRY(cudaMemcpyAsync(ws->h_result, ws->d_result, l.total, cudaMemcpyDeviceToHost,
+                                 ws->stream));
+        CUDA_TRY(cudaStreamSynchronize(ws->stream));
+        float ms = 0.f;
+        CUDA_TRY(cudaEventElapsedTime(&ms, ws->ev0, ws->ev1));
+        idx->last_scan_ms = ms;
+        const uint32_t *hc = reinterpret_cast<const uint32_t *>(ws->h_result + l.counts_off);
+        const uint64_t *hr = reinterpret_cast<const uint64_t *>(ws->h_result + l.rows_off);
+        const float *hs = reinterpret_cast<const float *>(ws->h_result + l.scores_off);
+        for (uint32_t q = 0; q < nq; ++q) {
+            out_counts[q] = hc[q];
+            memcpy(out_rows + (size_t)q * k, hr + (size_t)q * k, (size_t)hc[q] * 8);
+            memcpy(out_scores + (size_t)q * k, hs + (size_t)q * k, (size_t)hc[q] * 4);
+        }
+        idx->searches += nq;
+        idx->rows_scanned += (uint64_t)nq * sh.rows;
+        idx->bytes_streamed += (uint64_t)nq * sh.rows * dim * 4;
+        idx->h2d_bytes += (uint64_t)nq * dim * 4;
+        idx->d2h_bytes += l.total;
+        return NM_OK;
+    }
+
+    // ---- several devices in this process: scan each shard, merge the per-shard top-k on
+    //      the host (G*k hits), exactly ResultMerger::merge_top_k -------------------------
+    std::vector<std::unique_ptr<Workspace>> wss(G);
+    struct ReleaseAll {
+        nm_index *idx;
+        std::vector<std::unique_ptr<Workspace>> &w;
+        ~ReleaseAll() {
+            for (size_t s = 0; s < w.size(); ++s) ws_release(*idx->shards[s], w[s]);
+        }
+    } rel{idx, wss};
+    for (size_t s = 0; s < G; ++s) {
+        Shard &sh = *idx->shards[s];
+        CUDA_TRY(cudaSetDevice(sh.device));
+        rc = ws_acquire(sh, wss[s]);
+        if (rc) return rc;
+        Workspace &ws = *wss[s];
+        rc = ws_ensure(ws, sh, dim, nq, k, true, false, true, 0);
+        if (rc) return rc;
+        memcpy(ws.h_query, queries, (size_t)nq * dim * 4);
+        CUDA_TRY(cudaMemcpyAsync(ws.d_query, ws.h_query, (size_t)nq * dim * 4,
+                                 cudaMemcpyHostToDevice, ws.stream));
+        CUDA_TRY(cudaEventRecord(ws.ev0, ws.stream));
+        if (sh.rows == 0) {
+            CUDA_TRY(cudaMemsetAsync(ws.d_hits, 0, (size_t)nq * k * sizeof(nm::ShardHit), ws.stream));
+        } else {
+            for (uint32_t q = 0; q < nq; ++q) {
+                rc = launch_scan(idx, sh, ws, ws.d_query + (size_t)q * dim, k, metric, sh.row_base,
+                                 nullptr, nullptr, nullptr, ws.d_hits + (size_t)q * k, ws.stream);
+                if (rc) return rc;
+            }
+        }
+        CUDA_TRY(cudaEventRecord(ws.ev1, ws.stream));
+        CUDA_TRY(cudaMemcpyAsync(ws.h_hits, ws.d_hits, (size_t)nq * k * sizeof(nm::ShardHit),
+                                 cudaMemcpyDeviceToHost, ws.stream));
+    }
+    float max_ms = 0.f;
+    for (size_t s = 0; s < G; ++s) {
+        CUDA_TRY(cudaSetDevice(idx->shards[s]->device));
+        CUDA_TRY(cudaStreamSynchronize(wss[s]->stream));
+        float ms = 0.f;
+        CUDA_TRY(cudaEventElapsedTime(&ms, wss[s]->ev0, wss[s]->ev1));
+        max_ms = std::max(max_ms, ms);
+    }
+    idx->last_scan_ms = max_ms;
+    std::vector<HostHit> all;
+    for (uint32_t q = 0; q < nq; ++q) {
+        all.clear();
+        for (size_t s = 0; s < G; ++s) {
+            const nm::ShardHit *h = wss[s]->h_hits + (size_t)q * k;
+            for (uint32_t i = 0; i < k; ++i) {
+                if (h[i].ord == 0 && h[i].score_bits == 0) continue;
+                all.push_back(HostHit{h[i].ord, h[i].score_bits, h[i].global_row, all.size()});
+            }
+        }
+        std::stable_sort(all.begin(), all.end(),
+                         [](const HostHit &a, const HostHit &b) { return a.ord > b.ord; });
+        uint32_t m = (uint32_t)std::min<size_t>(k, all.size());
+        out_counts[q] = m;
+        for (uint32_t i = 0; i < m; ++i) {
+            out_rows[(size_t)q * k + i] = all[i].row;
+            memcpy(&out_scores[(size_t)q * k + i], &all[i].score_bits, 4);
+        }
+    }
+    uint64_t rows = idx->total_rows();
+    idx->searches += nq;
+    idx->rows_scanned += (uint64_t)nq * rows;
+    idx->bytes_streamed += (uint64_t)nq * rows * dim * 4;
+    idx->h2d_bytes += (uint64_t)nq * dim * 4 * G;
+    idx->d2h_bytes += (uint64_t)nq * k * sizeof(nm::ShardHit) * G;
+    return NM_OK;
+}
+
+int nm_search_device(nm_index *idx, const float *d_queries, uint32_t nq, uint32_t k, int metric,
+                     uint64_t *d_out_rows, float *d_out_scores, uint32_t *d_out_counts,
+                     void *stream_v) {
+    int rc = validate_search(idx, d_queries, nq, k, metric, d_out_rows, d_out_scores, d_out_counts);
+    if (rc) return rc;
+    std::shared_lock<std::shared_mutex> g(idx->mu);
+    if (idx->shards.size() != 1)
+        return fail(NM_ERR_CONFIGURATION, "nm_search_device needs a single-device index");
+    Shard &sh = *idx->shards[0];
+    const uint32_t dim = idx->dim;
+    const bool collective = idx->comm != nullptr;
+    CUDA_TRY(cudaSetDevice(sh.device));
+    std::unique_ptr<Workspace> ws;
+    rc = ws_acquire(sh, ws);
+    if (rc) return rc;
+    struct Releaser {
+        Shard &s;
+        std::unique_ptr<Workspace> &w;
+        ~Releaser() { ws_release(s, w); }
+    } rel{sh, ws};
+    cudaStream_t stream = stream_v ? (cudaStream_t)stream_v : ws->stream;
+    rc = ws_ensure(*ws, sh, dim, nq, k, false, false, collective, collective ? idx->n_ranks : 0);
+    if (rc) return rc;
+    if (!collective) {
+        if (sh.rows == 0) {
+            CUDA_TRY(cudaMemsetAsync(d_out_counts, 0, (size_t)nq * 4, stream));
+        } else {
+            for (uint32_t q = 0; q < nq; ++q) {
+                rc = launch_scan(idx, sh, *ws, d_queries + (size_t)q * dim, k, metric, sh.row_base,
+                                 d_out_rows + (size_t)q * k, d_out_scores + (size_t)q * k,
+                                 d_out_counts + q, nullptr, stream);
+                if (rc) return rc;
+            }
+        }
+    } else {
+        if (sh.rows == 0) {
+            CUDA_TRY(cudaMemsetAsync(ws->d_hits, 0, (size_t)nq * k * sizeof(nm::ShardHit), stream));
+        } else {
+            for (uint32_t q = 0; q < nq; ++q) {
+                rc = launch_scan(idx, sh, *ws, d_queries + (size_t)q * dim, k, metric,
+                                 idx->comm_row_base, nullptr, nullptr, nullptr,
+                                 ws->d_hits + (size_t)q * k, stream);
+                if (rc) return rc;
+            }
+        }
+        NCCL_TRY(nccl().AllGather(ws->d_hits, ws->d_gather,
+                                  (size_t)nq * k * sizeof(nm::ShardHit), ncclChar, idx->comm,
+                                  stream));
+        uint32_t total = (uint32_t)idx->n_ranks * k;
+        uint32_t n_sort = pow2_ceil(total);
+        size_t msmem = (size_t)n_sort * 8;
+        if (msmem > 200 * 1024)
+            return fail(NM_ERR_INVALID_TOP_K, "n_ranks*k = %u too large for the merge kernel", total);
+        if (msmem > 48 * 1024)
+            CUDA_TRY(cudaFuncSetAttribute(nm::merge_shards_kernel,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msmem));
+        nm::merge_shards_kernel<<<nq, nm::kMergeThreads, msmem, stream>>>(
+            ws->d_gather, (uint32_t)idx->n_ranks, k, nq * k, n_sort, d_out_rows, d_out_scores,
+            d_out_counts);
+        CUDA_TRY(cudaGetLastError());
+        idx->merge_launches++;
+    }
+    // The workspace (candidates, ticket, hits) is in use until the stream drains.  With a
+    // caller stream we must not hand it to another thread early, so wait here; the wait is
+    // on the device work only (no copies).
+    CUDA_TRY(cudaStreamSynchronize(stream));
+    idx->searches += nq;
+    idx->rows_scanned += (uint64_t)nq * sh.rows;
+    idx->bytes_streamed += (uint64_t)nq * sh.rows * dim * 4;
+    return NM_OK;
+}
+
+// --------------------------------------------------------------------------------------
+// communicator
+// --------------------------------------------------------------------------------------
+int nm_comm_create_id(void *out_id) {
+    if (!out_id) return fail(NM_ERR_INVALID_ARGUMENT, "null id buffer");
+    if (!nccl().ok) return fail(NM_ERR_STORAGE, "libnccl.so.2 could not be loaded");
+    static_assert(sizeof(ncclUniqueId) == NM_COMM_ID_BYTES, "ncclUniqueId size");
+    ncclUniqueId id;
+    NCCL_TRY(nccl().GetUniqueId(&id));
+    memcpy(out_id, &id, sizeof(id));
+    return NM_OK;
+}
+
+int nm_index_attach_comm(nm_index *idx, const void *id, int n_ranks, int rank, uint64_t row_base) {
+    if (!idx || !id) return fail(NM_ERR_INVALID_ARGUMENT, "null argument");
+    if (n_ranks < 1 || rank < 0 || rank >= n_ranks)
+        return fail(NM_ERR_INVALID_ARGUMENT, "bad rank %d of %d", rank, n_ranks);
+    if (!nccl().ok) return fail(NM_ERR_STORAGE, "libnccl.so.2 could not be loaded");
+    std::unique_lock<std::shared_mutex> g(idx->mu);
+    if (idx->shards.size() != 1)
+        return fail(NM_ERR_CONFIGURATION, "a communicator needs a single-device index per rank");
+    if (idx->comm) return fail(NM_ERR_CONFIGURATION, "communicator already attached");
+    CUDA_TRY(cudaSetDevice(idx->shards[0]->device));
+    ncclUniqueId uid;
+    memcpy(&uid, id, sizeof(uid));
+    NCCL_TRY(nccl().CommInitRank(&idx->comm, n_ranks, uid, rank));
+    idx->n_ranks = n_ranks;
+    idx->rank = rank;
+    idx->comm_row_base = row_base;
+    return NM_OK;
+}
+
+int nm_index_detach_comm(nm_index *idx) {
+    if (!idx) return fail(NM_ERR_INVALID_ARGUMENT, "null index");
+    std::unique_lock<std::shared_mutex> g(idx->mu);
+    if (idx->comm) {
+        NCCL_TRY(nccl().CommDestroy(idx->comm));
+        idx->comm = nullptr;
+    }
+    idx->n_ranks = 1;
+    idx->rank = 0;
+    idx->comm_row_base = 0;
+    return NM_OK;
+}
+
+int nm_index_stats(nm_index *idx, nm_stats *out) {
+    if (!idx || !out) return fail(NM_ERR_INVALID_ARGUMENT, "null argument");
+    out->searches = idx->searches;
+    out->rows_scanned = idx->rows_scanned;
+    out->bytes_streamed = idx->bytes_streamed;
+    out->scan_launches = idx->scan_launches;
+    out->merge_launches = idx->merge_launches;
+    out->h2d_bytes = idx->h2d_bytes;
+    out->d2h_bytes = idx->d2h_bytes;
+    out->last_scan_ms = idx->last_scan_ms;
+    return NM_OK;
+}
+
+}  // extern "C"

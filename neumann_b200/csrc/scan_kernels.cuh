@@ -1,0 +1,620 @@
+// scan_kernels.cuh — sm_100a kernels of the SIMILAR brute-force scan.
+//
+// What the kernels compute is the reference's per-row score followed by "sort all, keep k":
+//   simd::dot_product / sum_of_squares  tensor_store/src/hnsw.rs:168-222  (8-lane f32x8 tree)
+//   cosine_similarity                   vector_engine/src/lib.rs:2257-2266
+//   euclidean_distance (scalar fold)    vector_engine/src/lib.rs:2249-2253
+//   compute_score                       vector_engine/src/lib.rs:2231-2246
+//   sort_by(desc) + truncate(k)         vector_engine/src/lib.rs:2027-2034
+// The arithmetic reproduces the reference's summation ORDER so scores are bit-identical:
+// every multiply and add is a separate IEEE-754 round-to-nearest op (__fmul_rn/__fadd_rn are
+// never contracted into FMA), lane j of the f32x8 accumulator owns elements i = j (mod 8) in
+// ascending i, lanes are folded 0..7 left to right from 0.0, the dim%8 tail is added after.
+//
+// Data movement: the corpus is row-major f32 [rows, pitch] in HBM.  A persistent CTA per SM
+// walks row blocks of 256 rows; one producer thread streams [256 rows x 32 floats] boxes
+// (128 B per row, SWIZZLE_128B) with TMA into a ring of shared-memory stages guarded by
+// full/empty mbarriers; 256 consumer threads own one row each and keep that row's lane
+// accumulators in registers across the dim/32 boxes of the block.  With the 128 B swizzle the
+// eight 16-byte units of a row are XOR-permuted by (row & 7), so the LDS.128 of a quarter
+// warp (8 consecutive rows, same logical unit) hits 8 distinct bank groups: conflict-free.
+//
+// Selection: scores become 64-bit keys (order-preserving score bits | inverted row), so
+// "better" is plain unsigned >.  Each CTA keeps a candidate buffer with a running k-th-best
+// threshold, pruned by an in-smem bitonic sort when full; CTAs publish their k best and the
+// last CTA to finish merges all lists and writes the result (no second launch).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace nm {
+
+constexpr int kRowsPerBlock = 256;                  // rows per row block == consumer threads
+constexpr int kConsumerWarps = kRowsPerBlock / 32;  // 8
+constexpr int kScanThreads = kRowsPerBlock + 32;    // + 1 producer warp
+constexpr int kChunkFloats = 32;                    // floats per box row (128 B)
+constexpr int kStageBytes = kRowsPerBlock * 128;    // 32 KiB per stage
+constexpr int kMaxStages = 6;
+constexpr int kCandCap = 2048;                      // candidate buffer entries (u64)
+constexpr int kMaxFastK = 1024;                     // kCandCap - kMaxFastK >= kRowsPerBlock
+constexpr uint32_t kMaxLocalRows = 0x7ffffffeu;     // local row ids are 31 bit
+
+enum Metric : int { kCosine = 0, kEuclidean = 1, kDot = 2 };
+
+// ---------------------------------------------------------------------------------------
+// keys
+// ---------------------------------------------------------------------------------------
+// [63:32] order-preserving score (NaN -> 0 = worst, -0.0 folded onto +0.0)
+// [31:1]  0x7fffffff - local_row  (lower row wins ties)
+// [0]     1 iff the score bits were -0.0 (restored on decode; never decides an order because
+//         rows are unique)
+__host__ __device__ __forceinline__ uint32_t score_to_ord(uint32_t u) {
+    if ((u & 0x7fffffffu) > 0x7f800000u) return 0u;
+    if (u == 0x80000000u) u = 0u;
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__host__ __device__ __forceinline__ uint32_t ord_to_score_bits(uint32_t o) {
+    if (o == 0u) return 0x7fc00000u;  // canonical NaN
+    return (o & 0x80000000u) ? (o ^ 0x80000000u) : ~o;
+}
+__host__ __device__ __forceinline__ uint64_t make_key(uint32_t score_bits, uint32_t local_row) {
+    uint32_t negzero = (score_bits == 0x80000000u) ? 1u : 0u;
+    return ((uint64_t)score_to_ord(score_bits) << 32) |
+           ((uint64_t)(0x7fffffffu - local_row) << 1) | negzero;
+}
+__host__ __device__ __forceinline__ uint32_t key_local_row(uint64_t key) {
+    return 0x7fffffffu - (uint32_t)((key >> 1) & 0x7fffffffu);
+}
+__host__ __device__ __forceinline__ uint32_t key_score_bits(uint64_t key) {
+    if (key & 1ull) return 0x80000000u;
+    return ord_to_score_bits((uint32_t)(key >> 32));
+}
+
+// Candidate record exchanged between shards (one ncclAllGather of these).
+struct alignas(16) ShardHit {
+    uint64_t global_row;
+    uint32_t ord;         // score_to_ord(score_bits); 0 with valid==0 marks an empty slot
+    uint32_t score_bits;  // exact score bits (keeps -0.0)
+};
+
+#ifdef __CUDACC__
+// ---------------------------------------------------------------------------------------
+// PTX helpers (mbarrier, TMA, named barriers)
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_mbar_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t addr = smem_u32(bar);
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra.uni WAIT_DONE;\n\t"
+        "bra.uni WAIT_LOOP;\n\t"
+        "WAIT_DONE:\n\t"
+        "}\n" ::"r"(addr),
+        "r"(parity)
+        : "memory");
+}
+// 2D tiled TMA load global -> shared, completion counted in bytes on `bar`.
+__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *tmap, int32_t x,
+                                            int32_t y, uint64_t *bar, uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
+        ".L2::cache_hint [%0], [%1, {%2, %3}], [%4], %5;" ::"r"(smem_u32(dst)),
+        "l"(tmap), "r"(x), "r"(y), "r"(smem_u32(bar)), "l"(policy)
+        : "memory");
+}
+__device__ __forceinline__ uint64_t policy_evict_first() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t policy_evict_normal() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+// Named barrier 1 = the 256 consumer threads (the producer warp never joins it).
+__device__ __forceinline__ void consumer_sync() {
+    asm volatile("bar.sync 1, %0;" ::"n"(kRowsPerBlock) : "memory");
+}
+// Barrier + population count of `pred` over the 256 consumer threads; uniform result.
+__device__ __forceinline__ uint32_t consumer_sync_popc(bool pred) {
+    uint32_t total;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.u32 p, %1, 0;\n\t"
+        "bar.red.popc.u32 %0, 1, %2, p;\n\t"
+        "}\n"
+        : "=r"(total)
+        : "r"((uint32_t)pred), "n"(kRowsPerBlock)
+        : "memory");
+    return total;
+}
+
+// ---------------------------------------------------------------------------------------
+// candidate buffer (shared memory, consumer threads only)
+// ---------------------------------------------------------------------------------------
+struct TopKState {
+    uint64_t *buf;       // kCandCap keys
+    uint32_t *cnt_smem;  // append cursor
+    uint64_t *thr_smem;  // k-th best key after the last prune (0 = none yet)
+    uint32_t count;      // uniform copy of *cnt_smem
+    uint32_t k;
+};
+
+// Bitonic sort, descending, of buf[0..n) (n = power of two) by the 256 consumer threads.
+__device__ __forceinline__ void bitonic_sort_desc(uint64_t *buf, uint32_t n, uint32_t t) {
+    for (uint32_t size = 2; size <= n; size <<= 1) {
+        for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
+            for (uint32_t i = t; i < (n >> 1); i += kRowsPerBlock) {
+                uint32_t lo = ((i & ~(stride - 1)) << 1) | (i & (stride - 1));
+                uint32_t hi = lo + stride;
+                bool desc = ((lo & size) == 0);
+                uint64_t a = buf[lo], b = buf[hi];
+                bool swap = desc ? (a < b) : (a > b);
+                if (swap) {
+                    buf[lo] = b;
+                    buf[hi] = a;
+                }
+            }
+            consumer_sync();
+        }
+    }
+}
+
+// Sort the buffer, keep the k best, refresh the threshold.  Called by all consumer threads
+// with uniform state; contains barriers.
+__device__ __forceinline__ void topk_prune(TopKState &st, uint32_t t) {
+    uint32_t n = 2;
+    while (n < st.count) n <<= 1;
+    for (uint32_t i = st.count + t; i < n; i += kRowsPerBlock) st.buf[i] = 0ull;
+    consumer_sync();
+    bitonic_sort_desc(st.buf, n, t);
+    uint32_t kept = st.count < st.k ? st.count : st.k;
+    if (t == 0) {
+        *st.cnt_smem = kept;
+        *st.thr_smem = (st.count >= st.k) ? st.buf[st.k - 1] : 0ull;
+    }
+    st.count = kept;
+    consumer_sync();
+}
+
+// Offer one key per consumer thread (key == 0 -> nothing to offer).
+__device__ __forceinline__ void topk_offer(TopKState &st, uint64_t key, uint32_t t) {
+    bool cand = key > *st.thr_smem;
+    uint32_t total = consumer_sync_popc(cand);
+    if (st.count + total > (uint32_t)kCandCap) {
+        topk_prune(st, t);
+        cand = key > *st.thr_smem;
+        total = consumer_sync_popc(cand);
+    }
+    uint32_t ballot = __ballot_sync(0xffffffffu, cand);
+    if (ballot) {
+        uint32_t lane = t & 31;
+        uint32_t leader = __ffs(ballot) - 1;
+        uint32_t base = 0;
+        if (lane == leader) base = atomicAdd(st.cnt_smem, (uint32_t)__popc(ballot));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (cand) st.buf[base + __popc(ballot & ((1u << lane) - 1u))] = key;
+    }
+    st.count += total;
+}
+
+// ---------------------------------------------------------------------------------------
+// per-row accumulation
+// ---------------------------------------------------------------------------------------
+template <int METRIC>
+struct RowAcc {
+    float d[8];  // dot lanes   (cosine, dot)  | d[0] = running L2 sum (euclidean)
+    float s[8];  // sumsq lanes (cosine)
+    __device__ __forceinline__ void reset() {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            d[j] = 0.0f;
+            s[j] = 0.0f;
+        }
+    }
+    // one float4 of the row (elements 4u..4u+3 of the current 32-float chunk), with the
+    // matching float4 of the query.  `half` = u & 1 selects lanes 0-3 or 4-7.
+    template <int HALF>
+    __device__ __forceinline__ void step(const float4 v, const float4 q) {
+        if (METRIC == kEuclidean) {
+            float t0 = __fsub_rn(q.x, v.x);
+            d[0] = __fadd_rn(d[0], __fmul_rn(t0, t0));
+            float t1 = __fsub_rn(q.y, v.y);
+            d[0] = __fadd_rn(d[0], __fmul_rn(t1, t1));
+            float t2 = __fsub_rn(q.z, v.z);
+            d[0] = __fadd_rn(d[0], __fmul_rn(t2, t2));
+            float t3 = __fsub_rn(q.w, v.w);
+            d[0] = __fadd_rn(d[0], __fmul_rn(t3, t3));
+        } else {
+            constexpr int L = HALF * 4;
+            d[L + 0] = __fadd_rn(d[L + 0], __fmul_rn(q.x, v.x));
+            d[L + 1] = __fadd_rn(d[L + 1], __fmul_rn(q.y, v.y));
+            d[L + 2] = __fadd_rn(d[L + 2], __fmul_rn(q.z, v.z));
+            d[L + 3] = __fadd_rn(d[L + 3], __fmul_rn(q.w, v.w));
+            if (METRIC == kCosine) {
+                s[L + 0] = __fadd_rn(s[L + 0], __fmul_rn(v.x, v.x));
+                s[L + 1] = __fadd_rn(s[L + 1], __fmul_rn(v.y, v.y));
+                s[L + 2] = __fadd_rn(s[L + 2], __fmul_rn(v.z, v.z));
+                s[L + 3] = __fadd_rn(s[L + 3], __fmul_rn(v.w, v.w));
+            }
+        }
+    }
+};
+
+__device__ __forceinline__ float fold_lanes(const float *l) {
+    float r = 0.0f;  // arr.iter().sum(): left fold from 0.0 (hnsw.rs:184)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) r = __fadd_rn(r, l[j]);
+    return r;
+}
+
+struct ScanParams {
+    const float *query;      // [dim] device
+    uint64_t *cand;          // [grid, k] per-CTA best keys (workspace)
+    uint32_t *done_counter;  // ticket for "last CTA merges"; left at 0 on exit
+    uint64_t *out_keys;      // [k] merged local keys, descending, 0 padded (may be null)
+    ShardHit *out_hits;      // [k] merged hits with global rows (may be null)
+    uint64_t *out_rows;      // [k] global rows (may be null)
+    float *out_scores;       // [k] (may be null)
+    uint32_t *out_count;     // [1] (may be null)
+    uint64_t row_base;       // global index of local row 0
+    uint32_t n_rows;         // local rows
+    uint32_t dim;
+    uint32_t k;
+    uint32_t n_stages;
+    uint32_t q_floats;       // dim rounded up to a multiple of 32
+    uint32_t evict_first;    // 1: stream the corpus through L2 with evict_first
+};
+
+// Read element `col` (0..31) of row t in a swizzled stage.
+__device__ __forceinline__ float stage_elem(const uint8_t *stage, uint32_t t, uint32_t col) {
+    uint32_t unit = (col >> 2) ^ (t & 7u);
+    return *reinterpret_cast<const float *>(stage + t * 128u + (unit << 4) + ((col & 3u) << 2));
+}
+
+template <int METRIC>
+__global__ void __launch_bounds__(kScanThreads, 1)
+scan_topk_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    // carve-up: stages | candidate buffer | query | barriers + scalars
+    // (offset arithmetic, not an integer round-trip, so the compiler keeps the shared state space)
+    uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t *stages = smem;
+    uint64_t *cand_buf = reinterpret_cast<uint64_t *>(stages + p.n_stages * kStageBytes);
+    float *q_s = reinterpret_cast<float *>(cand_buf + kCandCap);
+    uint64_t *full_bar = reinterpret_cast<uint64_t *>(q_s + p.q_floats);
+    uint64_t *empty_bar = full_bar + kMaxStages;
+    uint64_t *thr_s = empty_bar + kMaxStages;
+    uint32_t *cnt_s = reinterpret_cast<uint32_t *>(thr_s + 1);
+    float *qmag_s = reinterpret_cast<float *>(cnt_s + 1);
+    uint32_t *ticket_s = cnt_s + 2;
+
+    const uint32_t tid = threadIdx.x;
+    const uint32_t warp = tid >> 5;
+    const uint32_t n_stages = p.n_stages;
+    const uint32_t n_rb = (p.n_rows + kRowsPerBlock - 1) / kRowsPerBlock;
+    const uint32_t n_kc_full = p.dim / kChunkFloats;
+    const uint32_t rem_cols = p.dim % kChunkFloats;
+    const uint32_t n_kc = n_kc_full + (rem_cols ? 1u : 0u);
+
+    if (tid == 0) {
+        for (uint32_t s = 0; s < n_stages; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], kConsumerWarps);
+        }
+        *thr_s = 0ull;
+        *cnt_s = 0u;
+        fence_mbar_init();
+    }
+    __syncthreads();
+
+    if (warp == kConsumerWarps) {
+        // ===================== TMA producer =====================
+        if (tid == kRowsPerBlock) {
+            const uint64_t policy = p.evict_first ? policy_evict_first() : policy_evict_normal();
+            uint32_t stage = 0, phase = 0;
+            for (uint32_t rb = blockIdx.x; rb < n_rb; rb += gridDim.x) {
+                for (uint32_t kc = 0; kc < n_kc; ++kc) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1u);
+                    mbar_arrive_expect_tx(&full_bar[stage], kStageBytes);
+                    tma_load_2d(stages + stage * kStageBytes, &tmap, (int32_t)(kc * kChunkFloats),
+                                (int32_t)(rb * kRowsPerBlock), &full_bar[stage], policy);
+                    if (++stage == n_stages) {
+                        stage = 0;
+                        phase ^= 1u;
+                    }
+                }
+            }
+        }
+        return;
+    }
+
+    // ===================== consumers: one row per thread =====================
+    const uint32_t t = tid;
+    const uint32_t lane = t & 31u;
+    // query -> shared (zero padded to a multiple of 32 floats)
+    for (uint32_t i = t; i < p.q_floats; i += kRowsPerBlock)
+        q_s[i] = (i < p.dim) ? __ldg(p.query + i) : 0.0f;
+    consumer_sync();
+    float qmag = 0.0f;
+    if (METRIC == kCosine) {
+        // |q| with the same lane tree (simd::magnitude, hnsw.rs:198-229): lanes 0..7 of warp 0
+        // each own one f32x8 lane, lane 0 folds them in order and adds the tail.
+        if (warp == 0) {
+            float acc = 0.0f;
+            const uint32_t chunks = p.dim / 8u;
+            if (lane < 8u) {
+                for (uint32_t c = 0; c < chunks; ++c) {
+                    float v = q_s[c * 8u + lane];
+                    acc = __fadd_rn(acc, __fmul_rn(v, v));
+                }
+            }
+            float r = 0.0f;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) r = __fadd_rn(r, __shfl_sync(0xffffffffu, acc, j));
+            if (lane == 0) {
+                for (uint32_t i = chunks * 8u; i < p.dim; ++i) {
+                    float v = q_s[i];
+                    r = __fadd_rn(r, __fmul_rn(v, v));
+                }
+                *qmag_s = __fsqrt_rn(r);
+            }
+        }
+        consumer_sync();
+        qmag = *qmag_s;
+    }
+
+    TopKState st;
+    st.buf = cand_buf;
+    st.cnt_smem = cnt_s;
+    st.thr_smem = thr_s;
+    st.count = 0;
+    st.k = p.k;
+
+    const uint32_t swz = t & 7u;
+    uint32_t stage = 0, phase = 0;
+    RowAcc<METRIC> acc;
+
+    for (uint32_t rb = blockIdx.x; rb < n_rb; rb += gridDim.x) {
+        acc.reset();
+        for (uint32_t kc = 0; kc < n_kc_full; ++kc) {
+            mbar_wait(&full_bar[stage], phase);
+            const uint8_t *srow = stages + stage * kStageBytes + t * 128u;
+            const float4 *qv = reinterpret_cast<const float4 *>(q_s) + kc * 8u;
+#pragma unroll
+            for (int u = 0; u < 8; u += 2) {
+                float4 v0 = *reinterpret_cast<const float4 *>(srow + (((uint32_t)u ^ swz) << 4));
+                float4 v1 =
+                    *reinterpret_cast<const float4 *>(srow + (((uint32_t)(u + 1) ^ swz) << 4));
+                float4 q0 = qv[u], q1 = qv[u + 1];
+                acc.template step<0>(v0, q0);
+                acc.template step<1>(v1, q1);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty_bar[stage]);
+            if (++stage == n_stages) {
+                stage = 0;
+                phase ^= 1u;
+            }
+        }
+        float dot, ssq = 0.0f;
+        if (rem_cols) {
+            // last, partial chunk: whole f32x8 groups first, then fold, then the scalar tail
+            mbar_wait(&full_bar[stage], phase);
+            const uint8_t *sbase = stages + stage * kStageBytes;
+            const float *qt = q_s + n_kc_full * kChunkFloats;
+            const uint32_t groups = rem_cols / 8u;
+            if (METRIC == kEuclidean) {
+                for (uint32_t c = 0; c < rem_cols; ++c) {
+                    float df = __fsub_rn(qt[c], stage_elem(sbase, t, c));
+                    acc.d[0] = __fadd_rn(acc.d[0], __fmul_rn(df, df));
+                }
+                dot = acc.d[0];
+            } else {
+                for (uint32_t g = 0; g < groups; ++g) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        float v = stage_elem(sbase, t, g * 8u + j);
+                        acc.d[j] = __fadd_rn(acc.d[j], __fmul_rn(qt[g * 8u + j], v));
+                        if (METRIC == kCosine) acc.s[j] = __fadd_rn(acc.s[j], __fmul_rn(v, v));
+                    }
+                }
+                dot = fold_lanes(acc.d);
+                if (METRIC == kCosine) ssq = fold_lanes(acc.s);
+                for (uint32_t c = groups * 8u; c < rem_cols; ++c) {
+                    float v = stage_elem(sbase, t, c);
+                    dot = __fadd_rn(dot, __fmul_rn(qt[c], v));
+                    if (METRIC == kCosine) ssq = __fadd_rn(ssq, __fmul_rn(v, v));
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty_bar[stage]);
+            if (++stage == n_stages) {
+                stage = 0;
+                phase ^= 1u;
+            }
+        } else {
+            if (METRIC == kEuclidean) {
+                dot = acc.d[0];
+            } else {
+                dot = fold_lanes(acc.d);
+                if (METRIC == kCosine) ssq = fold_lanes(acc.s);
+            }
+        }
+        float score;
+        if (METRIC == kCosine) {
+            float rmag = __fsqrt_rn(ssq);
+            score = (qmag == 0.0f || rmag == 0.0f) ? 0.0f
+                                                   : __fdiv_rn(dot, __fmul_rn(qmag, rmag));
+        } else if (METRIC == kEuclidean) {
+            score = __fdiv_rn(1.0f, __fadd_rn(1.0f, __fsqrt_rn(dot)));
+        } else {
+            score = dot;
+        }
+        const uint32_t row = rb * kRowsPerBlock + t;
+        const uint64_t key = (row < p.n_rows) ? make_key(__float_as_uint(score), row) : 0ull;
+        topk_offer(st, key, t);
+    }
+
+    // ---- publish this CTA's k best, last CTA merges everything ----
+    topk_prune(st, t);
+    uint64_t *my_cand = p.cand + (uint64_t)blockIdx.x * p.k;
+    for (uint32_t i = t; i < p.k; i += kRowsPerBlock) my_cand[i] = (i < st.count) ? st.buf[i] : 0ull;
+    __threadfence();
+    consumer_sync();
+    if (t == 0) *ticket_s = atomicAdd(p.done_counter, 1u);
+    consumer_sync();
+    if (*ticket_s != gridDim.x - 1) return;
+    __threadfence();
+
+    // st holds this CTA's own best (already in buf[0..count)); stream in the other CTAs' lists
+    const uint64_t total = (uint64_t)gridDim.x * p.k;
+    const volatile uint64_t *all = p.cand;
+    for (uint64_t base = 0; base < total; base += kRowsPerBlock) {
+        uint64_t i = base + t;
+        uint64_t key = 0ull;
+        if (i < total && (i / p.k) != blockIdx.x) key = all[i];
+        topk_offer(st, key, t);
+    }
+    topk_prune(st, t);
+    for (uint32_t i = t; i < p.k; i += kRowsPerBlock) {
+        uint64_t key = (i < st.count) ? st.buf[i] : 0ull;
+        if (p.out_keys) p.out_keys[i] = key;
+        uint64_t grow = p.row_base + key_local_row(key);
+        uint32_t sb = key_score_bits(key);
+        if (p.out_hits) {
+            ShardHit h;
+            h.global_row = key ? grow : 0ull;
+            h.ord = key ? (uint32_t)(key >> 32) : 0u;
+            h.score_bits = key ? sb : 0u;
+            // an empty slot is {0,0,0}; a real NaN hit has ord 0 too but is told apart by
+            // score_bits != 0
+            p.out_hits[i] = h;
+        }
+        if (i < st.count) {
+            if (p.out_rows) p.out_rows[i] = grow;
+            if (p.out_scores) p.out_scores[i] = __uint_as_float(sb);
+        }
+    }
+    if (t == 0) {
+        if (p.out_count) *p.out_count = st.count;
+        *p.done_counter = 0u;
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// cross-shard merge (ResultMerger::merge_top_k, query_router/src/distributed.rs:413-433):
+// concat shard lists in shard order, stable sort by score desc, truncate k.  hits is
+// [n_shards, k] as gathered; one CTA per query.
+// ---------------------------------------------------------------------------------------
+constexpr int kMergeThreads = 256;
+__global__ void __launch_bounds__(kMergeThreads)
+merge_shards_kernel(const ShardHit *hits, uint32_t n_shards, uint32_t k, uint32_t hits_stride_q,
+                    uint32_t n_sort, uint64_t *out_rows, float *out_scores,
+                    uint32_t *out_counts) {
+    extern __shared__ __align__(16) uint8_t merge_smem[];
+    uint64_t *keys = reinterpret_cast<uint64_t *>(merge_smem);
+    const uint32_t q = blockIdx.x;
+    const uint32_t t = threadIdx.x;
+    const uint32_t total = n_shards * k;
+    // gathered layout: [shard][query][k]
+    auto hit_at = [&](uint32_t pos) -> const ShardHit & {
+        uint32_t s = pos / k, i = pos % k;
+        return hits[(uint64_t)s * hits_stride_q + (uint64_t)q * k + i];
+    };
+    for (uint32_t i = t; i < n_sort; i += kMergeThreads) {
+        uint64_t key = 0ull;
+        if (i < total) {
+            const ShardHit &h = hit_at(i);
+            bool valid = (h.ord != 0u) || (h.score_bits != 0u);
+            // position in the concatenation breaks ties == stable sort; +1 keeps NaN hits > 0
+            if (valid) key = ((uint64_t)h.ord << 32) | (uint64_t)(0xffffffffu - i);
+        }
+        keys[i] = key;
+    }
+    __syncthreads();
+    for (uint32_t size = 2; size <= n_sort; size <<= 1) {
+        for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
+            for (uint32_t i = t; i < (n_sort >> 1); i += kMergeThreads) {
+                uint32_t lo = ((i & ~(stride - 1)) << 1) | (i & (stride - 1));
+                uint32_t hi = lo + stride;
+                bool desc = ((lo & size) == 0);
+                uint64_t a = keys[lo], b = keys[hi];
+                bool swap = desc ? (a < b) : (a > b);
+                if (swap) {
+                    keys[lo] = b;
+                    keys[hi] = a;
+                }
+            }
+            __syncthreads();
+        }
+    }
+    uint32_t cnt = 0;
+    for (uint32_t i = t; i < k; i += kMergeThreads) {
+        uint64_t key = keys[i];
+        if (key != 0ull) {
+            const ShardHit &h = hit_at(0xffffffffu - (uint32_t)key);
+            out_rows[(uint64_t)q * k + i] = h.global_row;
+            out_scores[(uint64_t)q * k + i] = __uint_as_float(h.score_bits);
+        }
+    }
+    if (t == 0) {
+        // keys are sorted: count = first zero within k
+        uint32_t lim = k < n_sort ? k : n_sort;
+        while (cnt < lim && keys[cnt] != 0ull) ++cnt;
+        out_counts[q] = cnt;
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// synthetic corpus: bit-identical to oracle nmo_fill_synthetic
+// ---------------------------------------------------------------------------------------
+__host__ __device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
+    uint64_t z = x + 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+__host__ __device__ __forceinline__ float synth_value(uint64_t seed, uint64_t flat) {
+    uint32_t u24 = (uint32_t)(splitmix64(splitmix64(seed) ^ flat) >> 40);
+    return (float)u24 * 1.1920928955078125e-07f - 1.0f;  // 2^-23, both ops exact
+}
+
+__global__ void fill_synthetic_kernel(float *rows, uint64_t n, uint32_t dim, uint32_t pitch,
+                                      uint64_t seed, uint64_t global_row0) {
+    const uint64_t total = n * (uint64_t)pitch;
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < total;
+         i += (uint64_t)gridDim.x * blockDim.x) {
+        uint64_t r = i / pitch;
+        uint32_t c = (uint32_t)(i % pitch);
+        rows[i] = (c < dim) ? synth_value(seed, (global_row0 + r) * dim + c) : 0.0f;
+    }
+}
+#endif  // __CUDACC__
+
+}  // namespace nm
