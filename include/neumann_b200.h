@@ -113,8 +113,10 @@ int nm_search(nm_index *idx, const float *queries, uint32_t nq, uint32_t k, int 
               uint64_t *out_rows, float *out_scores, uint32_t *out_counts);
 
 /* Same scan with the query and the outputs resident in DEVICE memory of the index's first
- * device and the work enqueued on `stream` (a cudaStream_t; NULL = library stream, and the
- * call then synchronises before returning).  Single-device indexes only. */
+ * device and the work enqueued on `stream` (a cudaStream_t).  With a caller stream the call
+ * is fully ASYNCHRONOUS: it returns after enqueueing and the outputs are valid once the
+ * stream reaches that point.  NULL = library stream, and the call then synchronises before
+ * returning.  Single-device indexes only. */
 int nm_search_device(nm_index *idx, const float *d_queries, uint32_t nq, uint32_t k,
                      int metric, uint64_t *d_out_rows, float *d_out_scores,
                      uint32_t *d_out_counts, void *stream);
@@ -146,8 +148,14 @@ typedef struct nm_stats {
     uint64_t h2d_bytes;       /* staging + query uploads                          */
     uint64_t d2h_bytes;       /* result downloads                                 */
     double last_scan_ms;      /* device time of the most recent nm_search scan(s) */
+    double profiled_scan_ms;  /* sum of CUDA-event times around profiled scan launches    */
+    uint64_t profiled_scans;  /* number of nm_search_device calls folded into the sum     */
 } nm_stats;
 int nm_index_stats(nm_index *idx, nm_stats *out);
+/* When enabled, every asynchronous nm_search_device call brackets its scan launches (not the
+ * all-gather / merge) with CUDA events on the caller's stream; nm_index_stats waits for them
+ * and accumulates profiled_scan_ms / profiled_scans.  Used by bench.py for the roofline. */
+int nm_index_set_profiling(nm_index *idx, int enable);
 
 #ifdef __cplusplus
 }

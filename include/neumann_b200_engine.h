@@ -1,0 +1,79 @@
+/*
+ * neumann_b200_engine.h — C view of the C++ host mirror (neumann_b200/csrc/vector_engine.hpp,
+ * similar_router.hpp) so that non-C++ hosts and the Python test harness can drive the same
+ * VectorEngine / SIMILAR surface the reference exposes in Rust.  The drop-in BOUNDARY for a
+ * Rust host is include/neumann_b200.h; this header is the reference-facing API rebuilt on top
+ * of it.  Function names follow vector_engine/src/lib.rs method names.
+ */
+#ifndef NEUMANN_B200_ENGINE_H
+#define NEUMANN_B200_ENGINE_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct nm_engine nm_engine;
+typedef struct nm_results nm_results;
+
+/* VectorEngineConfig (vector_engine/src/lib.rs:626-663).  0 / negative = "None". */
+typedef struct nm_engine_config {
+    uint64_t default_dimension;  /* 0 = None */
+    float sparse_threshold;      /* default 0.5 */
+    uint64_t parallel_threshold; /* default 5000 */
+    int default_metric;          /* nm_metric */
+    uint64_t max_dimension;      /* 0 = None */
+    int64_t search_timeout_ms;   /* < 0 = None */
+    int n_devices;               /* 0 = current device */
+    int devices[8];
+} nm_engine_config;
+
+void nm_engine_config_default(nm_engine_config *cfg);
+/* VectorEngine::new / with_config (validates; NM_ERR_CONFIGURATION on a bad config). */
+int nm_engine_create(const nm_engine_config *cfg /* NULL = defaults */, nm_engine **out);
+void nm_engine_destroy(nm_engine *e);
+const char *nm_engine_last_error(void);
+
+int nm_engine_store_embedding(nm_engine *e, const char *key, const float *vec, size_t n);
+int nm_engine_get_embedding(nm_engine *e, const char *key, float *out, size_t cap, size_t *len);
+int nm_engine_delete_embedding(nm_engine *e, const char *key);
+int nm_engine_exists(nm_engine *e, const char *key);
+uint64_t nm_engine_count(nm_engine *e);
+
+int nm_engine_search_similar(nm_engine *e, const float *query, size_t n, size_t top_k,
+                             nm_results **out);
+int nm_engine_search_similar_with_metric(nm_engine *e, const float *query, size_t n, size_t top_k,
+                                         int metric, nm_results **out);
+int nm_engine_compute_similarity(const float *a, size_t na, const float *b, size_t nb,
+                                 float *out);
+
+int nm_engine_create_collection(nm_engine *e, const char *name, uint64_t dimension /*0=None*/,
+                                int metric);
+int nm_engine_delete_collection(nm_engine *e, const char *name);
+int nm_engine_collection_exists(nm_engine *e, const char *name);
+int nm_engine_store_in_collection(nm_engine *e, const char *collection, const char *key,
+                                  const float *vec, size_t n);
+int nm_engine_delete_from_collection(nm_engine *e, const char *collection, const char *key);
+uint64_t nm_engine_collection_count(nm_engine *e, const char *collection);
+int nm_engine_search_in_collection(nm_engine *e, const char *collection, const float *query,
+                                   size_t n, size_t top_k, nm_results **out);
+
+/* QueryRouter::execute (legacy string path) / execute_parsed (AST path), SIMILAR + EMBED only.
+ * *out is NULL for QueryResult::Empty. */
+int nm_engine_execute(nm_engine *e, const char *command, nm_results **out);
+int nm_engine_execute_parsed(nm_engine *e, const char *command, nm_results **out);
+
+/* Device mirror introspection: rows held on host / on device for dimension `dim`. */
+int nm_engine_mirror_rows(nm_engine *e, uint32_t dim, uint64_t *host_rows, uint64_t *device_rows);
+
+size_t nm_results_len(const nm_results *r);
+const char *nm_results_key(const nm_results *r, size_t i);
+float nm_results_score(const nm_results *r, size_t i);
+void nm_results_free(nm_results *r);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

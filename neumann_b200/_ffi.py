@@ -31,6 +31,7 @@ class NmStats(C.Structure):
         ("searches", C.c_uint64), ("rows_scanned", C.c_uint64), ("bytes_streamed", C.c_uint64),
         ("scan_launches", C.c_uint64), ("merge_launches", C.c_uint64),
         ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("last_scan_ms", C.c_double),
+        ("profiled_scan_ms", C.c_double), ("profiled_scans", C.c_uint64),
     ]
 
 
@@ -62,6 +63,7 @@ SIGNATURES = {
     "nm_index_attach_comm": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_uint64]),
     "nm_index_detach_comm": (C.c_int, [_vp]),
     "nm_index_stats": (C.c_int, [_vp, C.POINTER(NmStats)]),
+    "nm_index_set_profiling": (C.c_int, [_vp, C.c_int]),
 }
 
 _lib = None

@@ -1,0 +1,214 @@
+// engine_capi.cpp — extern "C" view of VectorEngine / QueryRouter (include/neumann_b200_engine.h).
+#include <cstring>
+#include <memory>
+#include <string>
+
+#include "../../include/neumann_b200.h"
+#include "../../include/neumann_b200_engine.h"
+#include "similar_router.hpp"
+#include "vector_engine.hpp"
+
+using namespace neumann;
+
+struct nm_engine {
+    std::unique_ptr<VectorEngine> engine;
+    std::unique_ptr<QueryRouter> router;
+};
+struct nm_results {
+    std::vector<SearchResult> hits;
+};
+
+namespace {
+thread_local std::string g_engine_error;
+int fail(const VectorError &e) {
+    g_engine_error = e.to_string();
+    return e.status();
+}
+int fail(int code, const std::string &msg) {
+    g_engine_error = msg;
+    return code;
+}
+int give(Result<std::vector<SearchResult>> r, nm_results **out) {
+    if (out) *out = nullptr;
+    if (r.is_err()) return fail(r.error());
+    if (out) {
+        auto *res = new nm_results();
+        res->hits = std::move(r.value());
+        *out = res;
+    }
+    return NM_OK;
+}
+int give(const RouterOutcome &o, nm_results **out) {
+    if (out) *out = nullptr;
+    if (!o.ok) return fail(o.error.status, o.error.message);
+    if (out && o.result.kind == QueryResult::Kind::Similar) {
+        auto *res = new nm_results();
+        for (auto &s : o.result.similar) res->hits.push_back(SearchResult{s.key, s.score});
+        *out = res;
+    }
+    return NM_OK;
+}
+}  // namespace
+
+extern "C" {
+
+void nm_engine_config_default(nm_engine_config *cfg) {
+    if (!cfg) return;
+    std::memset(cfg, 0, sizeof(*cfg));
+    cfg->sparse_threshold = 0.5f;
+    cfg->parallel_threshold = 5000;
+    cfg->default_metric = NM_COSINE;
+    cfg->search_timeout_ms = -1;
+}
+
+int nm_engine_create(const nm_engine_config *cfg, nm_engine **out) {
+    if (!out) return fail(NM_ERR_INVALID_ARGUMENT, "null out pointer");
+    *out = nullptr;
+    VectorEngineConfig c;
+    if (cfg) {
+        if (cfg->default_dimension) c.default_dimension = (size_t)cfg->default_dimension;
+        c.sparse_threshold = cfg->sparse_threshold;
+        c.parallel_threshold = (size_t)cfg->parallel_threshold;
+        c.default_metric = (DistanceMetric)cfg->default_metric;
+        if (cfg->max_dimension) c.max_dimension = (size_t)cfg->max_dimension;
+        if (cfg->search_timeout_ms >= 0)
+            c.search_timeout = std::chrono::milliseconds(cfg->search_timeout_ms);
+        for (int i = 0; i < cfg->n_devices && i < 8; ++i) c.devices.push_back(cfg->devices[i]);
+    }
+    auto r = VectorEngine::with_config(std::move(c));
+    if (r.is_err()) return fail(r.error());
+    auto *e = new nm_engine();
+    e->engine = std::move(r.value());
+    e->router.reset(new QueryRouter(*e->engine));
+    *out = e;
+    return NM_OK;
+}
+
+void nm_engine_destroy(nm_engine *e) { delete e; }
+const char *nm_engine_last_error(void) { return g_engine_error.c_str(); }
+
+int nm_engine_store_embedding(nm_engine *e, const char *key, const float *vec, size_t n) {
+    if (!e || !key) return fail(NM_ERR_INVALID_ARGUMENT, "null argument");
+    auto r = e->engine->store_embedding(key, std::vector<float>(vec, vec + n));
+    return r.is_err() ? fail(r.error()) : NM_OK;
+}
+
+int nm_engine_get_embedding(nm_engine *e, const char *key, float *out, size_t cap, size_t *len) {
+    if (!e || !key) return fail(NM_ERR_INVALID_ARGUMENT, "null argument");
+    auto r = e->engine->get_embedding(key);
+    if (r.is_err()) return fail(r.error());
+    if (len) *len = r.value().size();
+    if (out && cap >= r.value().size())
+        std::memcpy(out, r.value().data(), r.value().size() * sizeof(float));
+    return NM_OK;
+}
+
+int nm_engine_delete_embedding(nm_engine *e, const char *key) {
+    if (!e || !key) return fail(NM_ERR_INVALID_ARGUMENT, "null argument");
+    auto r = e->engine->delete_embedding(key);
+    return r.is_err() ? fail(r.error()) : NM_OK;
+}
+
+int nm_engine_exists(nm_engine *e, const char *key) { return e && key && e->engine->exists(key); }
+uint64_t nm_engine_count(nm_engine *e) { return e ? e->engine->count() : 0; }
+
+int nm_engine_search_similar(nm_engine *e, const float *query, size_t n, size_t top_k,
+                             nm_results **out) {
+    if (!e) return fail(NM_ERR_INVALID_ARGUMENT, "null engine");
+    std::vector<float> q(query, query + (query ? n : 0));
+    return give(e->engine->search_similar(q, top_k), out);
+}
+
+int nm_engine_search_similar_with_metric(nm_engine *e, const float *query, size_t n, size_t top_k,
+                                         int metric, nm_results **out) {
+    if (!e) return fail(NM_ERR_INVALID_ARGUMENT, "null engine");
+    if (metric < 0 || metric > 2) return fail(NM_ERR_INVALID_ARGUMENT, "unknown metric");
+    std::vector<float> q(query, query + (query ? n : 0));
+    return give(e->engine->search_similar_with_metric(q, top_k, (DistanceMetric)metric), out);
+}
+
+int nm_engine_compute_similarity(const float *a, size_t na, const float *b, size_t nb,
+                                 float *out) {
+    auto r = VectorEngine::compute_similarity(std::vector<float>(a, a + (a ? na : 0)),
+                                              std::vector<float>(b, b + (b ? nb : 0)));
+    if (r.is_err()) return fail(r.error());
+    if (out) *out = r.value();
+    return NM_OK;
+}
+
+int nm_engine_create_collection(nm_engine *e, const char *name, uint64_t dimension, int metric) {
+    if (!e || !name) return fail(NM_ERR_INVALID_ARGUMENT, "null argument");
+    VectorCollectionConfig c;
+    if (dimension) c.dimension = (size_t)dimension;
+    c.distance_metric = (DistanceMetric)metric;
+    auto r = e->engine->create_collection(name, c);
+    return r.is_err() ? fail(r.error()) : NM_OK;
+}
+
+int nm_engine_delete_collection(nm_engine *e, const char *name) {
+    if (!e || !name) return fail(NM_ERR_INVALID_ARGUMENT, "null argument");
+    auto r = e->engine->delete_collection(name);
+    return r.is_err() ? fail(r.error()) : NM_OK;
+}
+
+int nm_engine_collection_exists(nm_engine *e, const char *name) {
+    return e && name && e->engine->collection_exists(name);
+}
+
+int nm_engine_store_in_collection(nm_engine *e, const char *collection, const char *key,
+                                  const float *vec, size_t n) {
+    if (!e || !collection || !key) return fail(NM_ERR_INVALID_ARGUMENT, "null argument");
+    auto r = e->engine->store_in_collection(collection, key, std::vector<float>(vec, vec + n));
+    return r.is_err() ? fail(r.error()) : NM_OK;
+}
+
+int nm_engine_delete_from_collection(nm_engine *e, const char *collection, const char *key) {
+    if (!e || !collection || !key) return fail(NM_ERR_INVALID_ARGUMENT, "null argument");
+    auto r = e->engine->delete_from_collection(collection, key);
+    return r.is_err() ? fail(r.error()) : NM_OK;
+}
+
+uint64_t nm_engine_collection_count(nm_engine *e, const char *collection) {
+    return (e && collection) ? e->engine->collection_count(collection) : 0;
+}
+
+int nm_engine_search_in_collection(nm_engine *e, const char *collection, const float *query,
+                                   size_t n, size_t top_k, nm_results **out) {
+    if (!e || !collection) return fail(NM_ERR_INVALID_ARGUMENT, "null argument");
+    std::vector<float> q(query, query + (query ? n : 0));
+    return give(e->engine->search_in_collection(collection, q, top_k), out);
+}
+
+int nm_engine_execute(nm_engine *e, const char *command, nm_results **out) {
+    if (!e || !command) return fail(NM_ERR_INVALID_ARGUMENT, "null argument");
+    return give(e->router->execute(command), out);
+}
+
+int nm_engine_execute_parsed(nm_engine *e, const char *command, nm_results **out) {
+    if (!e || !command) return fail(NM_ERR_INVALID_ARGUMENT, "null argument");
+    return give(e->router->execute_parsed(command), out);
+}
+
+int nm_engine_mirror_rows(nm_engine *e, uint32_t dim, uint64_t *host_rows, uint64_t *device_rows) {
+    if (!e) return fail(NM_ERR_INVALID_ARGUMENT, "null engine");
+    for (auto &m : e->engine->mirror_info())
+        if (m.dim == dim) {
+            if (host_rows) *host_rows = m.host_rows;
+            if (device_rows) *device_rows = m.device_rows;
+            return NM_OK;
+        }
+    if (host_rows) *host_rows = 0;
+    if (device_rows) *device_rows = 0;
+    return NM_OK;
+}
+
+size_t nm_results_len(const nm_results *r) { return r ? r->hits.size() : 0; }
+const char *nm_results_key(const nm_results *r, size_t i) {
+    return (r && i < r->hits.size()) ? r->hits[i].key.c_str() : "";
+}
+float nm_results_score(const nm_results *r, size_t i) {
+    return (r && i < r->hits.size()) ? r->hits[i].score : 0.0f;
+}
+void nm_results_free(nm_results *r) { delete r; }
+
+}  // extern "C"

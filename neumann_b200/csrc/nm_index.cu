@@ -124,7 +124,10 @@ struct Workspace {
     size_t hits_cap = 0;
     nm::ShardHit *d_gather = nullptr;  // [n_ranks, nq, k]
     size_t gather_cap = 0;
-    uint64_t *d_ceil = nullptr;  // unused placeholder for future paging
+    // profiling ring (nm_index_set_profiling): event pairs around the scan launches of
+    // asynchronous nm_search_device calls, resolved lazily by nm_index_stats
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
+    size_t prof_used = 0;
 
     ~Workspace() {
         if (device < 0) return;
@@ -140,6 +143,10 @@ struct Workspace {
         if (d_gather) cudaFree(d_gather);
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
+        for (auto &pe : prof_events) {
+            cudaEventDestroy(pe.first);
+            cudaEventDestroy(pe.second);
+        }
         if (stream) cudaStreamDestroy(stream);
     }
 };
@@ -158,6 +165,9 @@ struct Shard {
     cudaEvent_t staging_done[2] = {nullptr, nullptr};
     std::mutex pool_mu;
     std::vector<std::unique_ptr<Workspace>> pool;
+    // Workspaces bound to a caller stream (nm_search_device): work on one stream is ordered,
+    // so the same scratch can be reused by consecutive asynchronous calls without a sync.
+    std::vector<std::pair<cudaStream_t, std::unique_ptr<Workspace>>> stream_ws;
 };
 
 }  // namespace
@@ -175,6 +185,9 @@ struct nm_index {
     std::atomic<uint64_t> searches{0}, rows_scanned{0}, bytes_streamed{0}, scan_launches{0},
         merge_launches{0}, h2d_bytes{0}, d2h_bytes{0};
     std::atomic<double> last_scan_ms{0.0};
+    std::atomic<int> profiling{0};
+    double profiled_scan_ms = 0.0;  // guarded by mu (exclusive) in nm_index_stats
+    uint64_t profiled_scans = 0;
     uint64_t total_rows() const {
         uint64_t n = 0;
         for (auto &s : shards) n += s->rows;
@@ -186,7 +199,7 @@ namespace {
 
 size_t scan_smem_bytes(uint32_t n_stages, uint32_t q_floats) {
     return 1024 + (size_t)n_stages * nm::kStageBytes + (size_t)nm::kCandCap * 8 +
-           (size_t)q_floats * 4 + 2 * nm::kMaxStages * 8 + 64;
+           (size_t)q_floats * 4 + 2 * nm::kMaxStages * 8 + 64 + nm::kMaxStages * 4;
 }
 
 int build_tmap(nm_index *idx, Shard &sh) {
@@ -282,8 +295,8 @@ int ws_acquire(Shard &sh, std::unique_ptr<Workspace> &out) {
     CUDA_TRY(cudaStreamCreateWithFlags(&ws->stream, cudaStreamNonBlocking));
     CUDA_TRY(cudaEventCreate(&ws->ev0));
     CUDA_TRY(cudaEventCreate(&ws->ev1));
-    CUDA_TRY(cudaMalloc(&ws->d_counter, sizeof(uint32_t)));
-    CUDA_TRY(cudaMemsetAsync(ws->d_counter, 0, sizeof(uint32_t), ws->stream));
+    CUDA_TRY(cudaMalloc(&ws->d_counter, 2 * sizeof(uint32_t)));
+    CUDA_TRY(cudaMemsetAsync(ws->d_counter, 0, 2 * sizeof(uint32_t), ws->stream));
     out = std::move(ws);
     return NM_OK;
 }
@@ -358,15 +371,18 @@ int ws_ensure(Workspace &ws, const Shard &sh, uint32_t dim, uint32_t nq, uint32_
 
 template <int METRIC>
 int launch_scan_t(const Shard &sh, const nm::ScanParams &p, size_t smem, cudaStream_t stream) {
-    static thread_local size_t configured[64] = {0};
+    // The dynamic-smem opt-in is a per-function, per-device attribute shared by all host
+    // threads: raise it once to the architectural maximum and never lower it.
+    static std::mutex mu;
+    static bool configured[64] = {false};
     auto kern = nm::scan_topk_kernel<METRIC>;
-    if (sh.device < 64 && configured[sh.device] < smem) {
-        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)smem));
-        configured[sh.device] = smem;
-    } else if (sh.device >= 64) {
-        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)smem));
+    {
+        std::lock_guard<std::mutex> g(mu);
+        if (sh.device >= 64 || !configured[sh.device]) {
+            CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          227 * 1024));
+            if (sh.device < 64) configured[sh.device] = true;
+        }
     }
     uint32_t n_rb = (p.n_rows + nm::kRowsPerBlock - 1) / nm::kRowsPerBlock;
     uint32_t grid = std::min<uint32_t>((uint32_t)sh.sm_count, n_rb);
@@ -509,6 +525,7 @@ void nm_index_destroy(nm_index *idx) {
     for (auto &sh : idx->shards) {
         cudaSetDevice(sh->device);
         sh->pool.clear();
+        sh->stream_ws.clear();
         if (sh->d_rows) cudaFree(sh->d_rows);
         for (int b = 0; b < 2; ++b) {
             if (sh->staging[b]) cudaFreeHost(sh->staging[b]);
@@ -778,7 +795,7 @@ int nm_search(nm_index *idx, const float *queries, uint32_t nq, uint32_t k, int 
             return fail(NM_ERR_INVALID_TOP_K, "n_ranks*k = %u too large for the merge kernel", total);
         if (msmem > 48 * 1024)
             CUDA_TRY(cudaFuncSetAttribute(nm::merge_shards_kernel,
-                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msmem));
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         nm::merge_shards_kernel<<<nq, nm::kMergeThreads, msmem, ws->stream>>>(
             ws->d_gather, (uint32_t)idx->n_ranks, k, nq * k, n_sort,
             reinterpret_cast<uint64_t *>(ws->d_result + l.rows_off),
@@ -892,17 +909,56 @@ int nm_search_device(nm_index *idx, const float *d_queries, uint32_t nq, uint32_
     const uint32_t dim = idx->dim;
     const bool collective = idx->comm != nullptr;
     CUDA_TRY(cudaSetDevice(sh.device));
-    std::unique_ptr<Workspace> ws;
-    rc = ws_acquire(sh, ws);
-    if (rc) return rc;
+    // Caller stream: use the workspace bound to that stream and return without synchronising
+    // (stream order protects the scratch).  NULL stream: pooled workspace + synchronise.
+    std::unique_ptr<Workspace> pooled;
+    Workspace *ws = nullptr;
+    cudaStream_t stream = nullptr;
+    if (stream_v) {
+        stream = (cudaStream_t)stream_v;
+        std::lock_guard<std::mutex> pg(sh.pool_mu);
+        for (auto &e : sh.stream_ws)
+            if (e.first == stream) ws = e.second.get();
+        if (!ws) {
+            std::unique_ptr<Workspace> nw(new Workspace());
+            nw->device = sh.device;
+            CUDA_TRY(cudaMalloc(&nw->d_counter, 2 * sizeof(uint32_t)));
+            CUDA_TRY(cudaMemsetAsync(nw->d_counter, 0, 2 * sizeof(uint32_t), stream));
+            ws = nw.get();
+            sh.stream_ws.emplace_back(stream, std::move(nw));
+        }
+    } else {
+        rc = ws_acquire(sh, pooled);
+        if (rc) return rc;
+        ws = pooled.get();
+        stream = ws->stream;
+    }
     struct Releaser {
         Shard &s;
         std::unique_ptr<Workspace> &w;
         ~Releaser() { ws_release(s, w); }
-    } rel{sh, ws};
-    cudaStream_t stream = stream_v ? (cudaStream_t)stream_v : ws->stream;
+    } rel{sh, pooled};
+    // growing a stream-bound workspace frees buffers earlier launches may still read
+    {
+        size_t need_cand = (size_t)sh.sm_count * k, need_hits = (size_t)nq * k;
+        bool grow = ws->cand_cap < need_cand ||
+                    (collective && (ws->hits_cap < need_hits ||
+                                    ws->gather_cap < need_hits * (size_t)idx->n_ranks));
+        if (grow && stream_v) CUDA_TRY(cudaStreamSynchronize(stream));
+    }
     rc = ws_ensure(*ws, sh, dim, nq, k, false, false, collective, collective ? idx->n_ranks : 0);
     if (rc) return rc;
+    std::pair<cudaEvent_t, cudaEvent_t> *prof = nullptr;
+    if (idx->profiling.load() && sh.rows) {
+        if (ws->prof_used == ws->prof_events.size()) {
+            cudaEvent_t a, b;
+            CUDA_TRY(cudaEventCreate(&a));
+            CUDA_TRY(cudaEventCreate(&b));
+            ws->prof_events.emplace_back(a, b);
+        }
+        prof = &ws->prof_events[ws->prof_used++];
+        CUDA_TRY(cudaEventRecord(prof->first, stream));
+    }
     if (!collective) {
         if (sh.rows == 0) {
             CUDA_TRY(cudaMemsetAsync(d_out_counts, 0, (size_t)nq * 4, stream));
@@ -914,6 +970,7 @@ int nm_search_device(nm_index *idx, const float *d_queries, uint32_t nq, uint32_
                 if (rc) return rc;
             }
         }
+        if (prof) CUDA_TRY(cudaEventRecord(prof->second, stream));
     } else {
         if (sh.rows == 0) {
             CUDA_TRY(cudaMemsetAsync(ws->d_hits, 0, (size_t)nq * k * sizeof(nm::ShardHit), stream));
@@ -925,6 +982,7 @@ int nm_search_device(nm_index *idx, const float *d_queries, uint32_t nq, uint32_
                 if (rc) return rc;
             }
         }
+        if (prof) CUDA_TRY(cudaEventRecord(prof->second, stream));
         NCCL_TRY(nccl().AllGather(ws->d_hits, ws->d_gather,
                                   (size_t)nq * k * sizeof(nm::ShardHit), ncclChar, idx->comm,
                                   stream));
@@ -935,20 +993,23 @@ int nm_search_device(nm_index *idx, const float *d_queries, uint32_t nq, uint32_
             return fail(NM_ERR_INVALID_TOP_K, "n_ranks*k = %u too large for the merge kernel", total);
         if (msmem > 48 * 1024)
             CUDA_TRY(cudaFuncSetAttribute(nm::merge_shards_kernel,
-                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msmem));
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         nm::merge_shards_kernel<<<nq, nm::kMergeThreads, msmem, stream>>>(
             ws->d_gather, (uint32_t)idx->n_ranks, k, nq * k, n_sort, d_out_rows, d_out_scores,
             d_out_counts);
         CUDA_TRY(cudaGetLastError());
         idx->merge_launches++;
     }
-    // The workspace (candidates, ticket, hits) is in use until the stream drains.  With a
-    // caller stream we must not hand it to another thread early, so wait here; the wait is
-    // on the device work only (no copies).
-    CUDA_TRY(cudaStreamSynchronize(stream));
+    if (!stream_v) CUDA_TRY(cudaStreamSynchronize(stream));
     idx->searches += nq;
     idx->rows_scanned += (uint64_t)nq * sh.rows;
     idx->bytes_streamed += (uint64_t)nq * sh.rows * dim * 4;
+    return NM_OK;
+}
+
+int nm_index_set_profiling(nm_index *idx, int enable) {
+    if (!idx) return fail(NM_ERR_INVALID_ARGUMENT, "null index");
+    idx->profiling = enable ? 1 : 0;
     return NM_OK;
 }
 
@@ -1007,6 +1068,33 @@ int nm_index_stats(nm_index *idx, nm_stats *out) {
     out->h2d_bytes = idx->h2d_bytes;
     out->d2h_bytes = idx->d2h_bytes;
     out->last_scan_ms = idx->last_scan_ms;
+    {
+        // fold finished profiling event pairs into the totals (waits for the streams)
+        std::unique_lock<std::shared_mutex> g(idx->mu);
+        for (auto &sh : idx->shards) {
+            cudaSetDevice(sh->device);
+            std::lock_guard<std::mutex> pg(sh->pool_mu);
+            std::vector<Workspace *> all_ws;
+            for (auto &e : sh->stream_ws) all_ws.push_back(e.second.get());
+            for (auto &w : sh->pool) all_ws.push_back(w.get());
+            for (Workspace *wsp : all_ws) {
+                Workspace &ws = *wsp;
+                for (size_t i = 0; i < ws.prof_used; ++i) {
+                    float ms = 0.f;
+                    if (cudaEventSynchronize(ws.prof_events[i].second) == cudaSuccess &&
+                        cudaEventElapsedTime(&ms, ws.prof_events[i].first,
+                                             ws.prof_events[i].second) == cudaSuccess) {
+                        idx->profiled_scan_ms += ms;
+                        idx->profiled_scans += 1;
+                    }
+                }
+                ws.prof_used = 0;
+            }
+        }
+        cudaGetLastError();
+        out->profiled_scan_ms = idx->profiled_scan_ms;
+        out->profiled_scans = idx->profiled_scans;
+    }
     return NM_OK;
 }
 

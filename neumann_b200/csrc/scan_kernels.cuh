@@ -276,7 +276,8 @@ __device__ __forceinline__ float fold_lanes(const float *l) {
 struct ScanParams {
     const float *query;      // [dim] device
     uint64_t *cand;          // [grid, k] per-CTA best keys (workspace)
-    uint32_t *done_counter;  // ticket for "last CTA merges"; left at 0 on exit
+    uint32_t *done_counter;  // [0] ticket for "last CTA merges", [1] dynamic row-block cursor;
+                             // both left at 0 on exit
     uint64_t *out_keys;      // [k] merged local keys, descending, 0 padded (may be null)
     ShardHit *out_hits;      // [k] merged hits with global rows (may be null)
     uint64_t *out_rows;      // [k] global rows (may be null)
@@ -313,6 +314,7 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
     uint32_t *cnt_s = reinterpret_cast<uint32_t *>(thr_s + 1);
     float *qmag_s = reinterpret_cast<float *>(cnt_s + 1);
     uint32_t *ticket_s = cnt_s + 2;
+    uint32_t *rb_ring = cnt_s + 3;  // row block carried by each stage (kMaxStages entries)
 
     const uint32_t tid = threadIdx.x;
     const uint32_t warp = tid >> 5;
@@ -335,12 +337,25 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
 
     if (warp == kConsumerWarps) {
         // ===================== TMA producer =====================
+        // Row blocks are handed out dynamically: the first one is blockIdx.x, every further
+        // one comes from a global cursor, so SMs that see more bandwidth simply take more
+        // blocks and all CTAs finish together.  The block id travels to the consumers in
+        // rb_ring[stage] (published by the mbarrier arrive); 0xffffffff ends the stream.
         if (tid == kRowsPerBlock) {
             const uint64_t policy = p.evict_first ? policy_evict_first() : policy_evict_normal();
             uint32_t stage = 0, phase = 0;
-            for (uint32_t rb = blockIdx.x; rb < n_rb; rb += gridDim.x) {
+            uint32_t rb = blockIdx.x;
+            for (;;) {
+                if (rb >= n_rb) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1u);
+                    rb_ring[stage] = 0xffffffffu;
+                    mbar_arrive(&full_bar[stage]);
+                    break;
+                }
+                const uint32_t next = atomicAdd(p.done_counter + 1, 1u) + gridDim.x;
                 for (uint32_t kc = 0; kc < n_kc; ++kc) {
                     mbar_wait(&empty_bar[stage], phase ^ 1u);
+                    if (kc == 0) rb_ring[stage] = rb;
                     mbar_arrive_expect_tx(&full_bar[stage], kStageBytes);
                     tma_load_2d(stages + stage * kStageBytes, &tmap, (int32_t)(kc * kChunkFloats),
                                 (int32_t)(rb * kRowsPerBlock), &full_bar[stage], policy);
@@ -349,6 +364,7 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
                         phase ^= 1u;
                     }
                 }
+                rb = next;
             }
         }
         return;
@@ -400,7 +416,11 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
     uint32_t stage = 0, phase = 0;
     RowAcc<METRIC> acc;
 
-    for (uint32_t rb = blockIdx.x; rb < n_rb; rb += gridDim.x) {
+    for (;;) {
+        // the first stage of a row block also carries the block id
+        mbar_wait(&full_bar[stage], phase);
+        const uint32_t rb = rb_ring[stage];
+        if (rb == 0xffffffffu) break;
         acc.reset();
         for (uint32_t kc = 0; kc < n_kc_full; ++kc) {
             mbar_wait(&full_bar[stage], phase);
@@ -523,7 +543,9 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
     }
     if (t == 0) {
         if (p.out_count) *p.out_count = st.count;
-        *p.done_counter = 0u;
+        // every CTA took its ticket after its producer's last cursor fetch: safe to reset
+        p.done_counter[0] = 0u;
+        p.done_counter[1] = 0u;
     }
 }
 

@@ -1,0 +1,56 @@
+// similar_router.hpp — the query_router SIMILAR operator surface (and the EMBED command that
+// feeds it), mirrored from query_router/src/lib.rs:
+//   execute            -> legacy string path   QR:1498-1538, execute_similar QR:6632-6665,
+//                         parse_similar_args QR:6903-6929, execute_embed QR:6617-6630
+//   execute_parsed     -> AST path             exec_similar QR:5316-5451 with the grammar of
+//                         neumann_parser/src/parser.rs:1853-1919
+// Everything else the router dispatches (SQL, graph, vault, blob, chain, CONNECTED TO, WHERE
+// filters) is out of scope and reported as an error, not silently ignored.
+#pragma once
+#include <string>
+#include <vector>
+
+#include "vector_engine.hpp"
+
+namespace neumann {
+
+// query_router/src/lib.rs:384-389
+struct SimilarResult {
+    std::string key;
+    float score;
+};
+
+// QueryResult (QR:265-266) restricted to what this operator returns.
+struct QueryResult {
+    enum class Kind { Empty, Similar } kind = Kind::Empty;
+    std::vector<SimilarResult> similar;
+};
+
+struct RouterError {
+    enum class Kind { ParseError, MissingArgument, InvalidArgument, UnknownCommand, VectorError }
+        kind = Kind::ParseError;
+    std::string message;
+    int status = 6;  // nm_status; VectorError keeps its own code
+};
+
+struct RouterOutcome {
+    bool ok = false;
+    QueryResult result;
+    RouterError error;
+};
+
+class QueryRouter {
+  public:
+    explicit QueryRouter(VectorEngine &engine) : vector_(engine) {}
+    VectorEngine &vector() { return vector_; }
+    // Legacy string commands: `EMBED <key> [v, ...]`, `SIMILAR <key|[v, ...]> [TOP k]`.
+    RouterOutcome execute(const std::string &command);
+    // AST grammar: `SIMILAR <'key'|ident|[v, ...]> [LIMIT k] [COSINE|EUCLIDEAN|DOT_PRODUCT]
+    // [INTO collection]`; `EMBED STORE 'key' [v, ...] [INTO collection]` and the legacy EMBED.
+    RouterOutcome execute_parsed(const std::string &command);
+
+  private:
+    VectorEngine &vector_;
+};
+
+}  // namespace neumann

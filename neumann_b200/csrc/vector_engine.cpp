@@ -1,0 +1,514 @@
+// vector_engine.cpp — see vector_engine.hpp.  Host-side key tables + device-mirror upkeep;
+// every scan goes to the GPU through nm_search.
+#include "vector_engine.hpp"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+#include "../../include/neumann_b200.h"
+
+namespace neumann {
+
+// --------------------------------------------------------------------------------------
+// errors
+// --------------------------------------------------------------------------------------
+int VectorError::status() const {
+    switch (kind) {
+    case ErrorKind::NotFound: return NM_ERR_NOT_FOUND;
+    case ErrorKind::DimensionMismatch: return NM_ERR_DIMENSION_MISMATCH;
+    case ErrorKind::EmptyVector: return NM_ERR_EMPTY_VECTOR;
+    case ErrorKind::InvalidTopK: return NM_ERR_INVALID_TOP_K;
+    case ErrorKind::StorageError: return NM_ERR_STORAGE;
+    case ErrorKind::ConfigurationError: return NM_ERR_CONFIGURATION;
+    case ErrorKind::CollectionExists: return NM_ERR_COLLECTION_EXISTS;
+    case ErrorKind::CollectionNotFound: return NM_ERR_COLLECTION_NOT_FOUND;
+    case ErrorKind::SearchTimeout: return NM_ERR_SEARCH_TIMEOUT;
+    default: return NM_ERR_INVALID_ARGUMENT;
+    }
+}
+
+// Display strings follow `impl Display for VectorError` (vector_engine/src/lib.rs:151-182).
+std::string VectorError::to_string() const {
+    switch (kind) {
+    case ErrorKind::NotFound: return "Embedding not found: " + message;
+    case ErrorKind::DimensionMismatch:
+        return "Dimension mismatch: expected " + std::to_string(expected) + ", got " +
+               std::to_string(got);
+    case ErrorKind::EmptyVector: return "Empty vector provided";
+    case ErrorKind::InvalidTopK: return "Invalid top_k value (must be > 0)";
+    case ErrorKind::StorageError: return "Storage error: " + message;
+    case ErrorKind::ConfigurationError: return "Configuration error: " + message;
+    case ErrorKind::CollectionExists: return "Collection already exists: " + message;
+    case ErrorKind::CollectionNotFound: return "Collection not found: " + message;
+    case ErrorKind::SearchTimeout:
+        return "search timeout: " + operation + " exceeded " + std::to_string(timeout_ms) + "ms";
+    default: return "Invalid argument: " + message;
+    }
+}
+
+namespace {
+VectorError err(ErrorKind k, std::string msg = {}) {
+    VectorError e;
+    e.kind = k;
+    e.message = std::move(msg);
+    return e;
+}
+VectorError dim_mismatch(size_t expected, size_t got) {
+    VectorError e;
+    e.kind = ErrorKind::DimensionMismatch;
+    e.expected = expected;
+    e.got = got;
+    return e;
+}
+VectorError storage_from_nm(int code) {
+    VectorError e;
+    e.kind = ErrorKind::StorageError;  // CUDA / NCCL failures surface as StorageError(msg)
+    e.message = std::string(nm_last_error()) + " (nm_status " + std::to_string(code) + ")";
+    return e;
+}
+}  // namespace
+
+// --------------------------------------------------------------------------------------
+// simd (tensor_store/src/hnsw.rs:168-229): 8 lane accumulators, separate mul and add, lanes
+// folded left to right from 0.0, scalar tail.  Built with -ffp-contract=off.
+// --------------------------------------------------------------------------------------
+namespace simd {
+float dot_product(const float *a, const float *b, size_t n) {
+    const size_t chunks = n / 8, rem = n % 8;
+    float l[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (size_t c = 0; c < chunks; ++c)
+        for (int j = 0; j < 8; ++j) {
+            float p = a[c * 8 + j] * b[c * 8 + j];
+            l[j] = l[j] + p;
+        }
+    float r = 0.0f;
+    for (int j = 0; j < 8; ++j) r = r + l[j];
+    for (size_t i = 0; i < rem; ++i) {
+        float p = a[chunks * 8 + i] * b[chunks * 8 + i];
+        r = r + p;
+    }
+    return r;
+}
+float sum_of_squares(const float *v, size_t n) { return dot_product(v, v, n); }
+float magnitude(const float *v, size_t n) { return std::sqrt(sum_of_squares(v, n)); }
+}  // namespace simd
+
+// --------------------------------------------------------------------------------------
+// config
+// --------------------------------------------------------------------------------------
+Result<Unit> VectorEngineConfig::validate() const {
+    if (sparse_threshold < 0.0f || sparse_threshold > 1.0f || std::isnan(sparse_threshold))
+        return err(ErrorKind::ConfigurationError, "sparse_threshold must be between 0.0 and 1.0");
+    if (parallel_threshold == 0)
+        return err(ErrorKind::ConfigurationError, "parallel_threshold must be greater than 0");
+    if (max_dimension && *max_dimension == 0)
+        return err(ErrorKind::ConfigurationError, "max_dimension must be greater than 0");
+    if (max_keys_per_scan && *max_keys_per_scan == 0)
+        return err(ErrorKind::ConfigurationError, "max_keys_per_scan must be greater than 0");
+    if (batch_parallel_threshold == 0)
+        return err(ErrorKind::ConfigurationError,
+                   "batch_parallel_threshold must be greater than 0");
+    return Unit{};
+}
+
+// --------------------------------------------------------------------------------------
+// storage: one Space per key namespace (`emb:` or `coll:{name}:emb:`), rows bucketed by
+// dimension because the scan only ever compares equal-length vectors (lib.rs:2126-2128).
+// --------------------------------------------------------------------------------------
+struct VectorEngine::Bucket {
+    uint32_t dim = 0;
+    std::vector<std::string> keys;  // row -> key (mirror order)
+    std::vector<float> rows;        // host copy, row-major
+    nm_index *mirror = nullptr;     // device mirror, created at the first search
+    uint64_t synced_rows = 0;       // rows [0, synced_rows) are on the device
+    std::mutex sync_mu;             // serialises lazy appends issued by concurrent searches
+    ~Bucket() {
+        if (mirror) nm_index_destroy(mirror);
+    }
+};
+
+struct VectorEngine::Space {
+    mutable std::shared_mutex mu;
+    std::unordered_map<std::string, std::pair<uint32_t, uint64_t>> where;  // key -> (dim, row)
+    std::map<uint32_t, std::unique_ptr<Bucket>> buckets;
+};
+
+VectorEngine::VectorEngine() : default_space_(new Space()) {}
+VectorEngine::VectorEngine(VectorEngineConfig config)
+    : config_(std::move(config)), default_space_(new Space()) {}
+VectorEngine::~VectorEngine() = default;
+
+Result<std::unique_ptr<VectorEngine>> VectorEngine::with_config(VectorEngineConfig config) {
+    auto v = config.validate();
+    if (v.is_err()) return v.error();
+    return std::unique_ptr<VectorEngine>(new VectorEngine(std::move(config)));
+}
+
+// lib.rs:1876-1885
+bool VectorEngine::should_use_sparse(const std::vector<float> &v) const {
+    if (v.empty()) return false;
+    size_t nnz = 0;
+    for (float x : v)
+        if (std::fabs(x) > 1e-6f) ++nnz;
+    float zero_ratio = 1.0f - ((float)nnz / (float)v.size());
+    return zero_ratio >= config_.sparse_threshold;
+}
+
+Result<Unit> VectorEngine::store_in_space(Space &sp, const std::string &key,
+                                          std::vector<float> vector) {
+    // Sparse storage round-trips through SparseVector::from_dense / to_dense
+    // (tensor_store/src/sparse_vector.rs:212-229, 400-406): entries == 0.0 are dropped and come
+    // back as +0.0, so -0.0 loses its sign; everything else (incl. NaN) is preserved.
+    if (should_use_sparse(vector))
+        for (float &x : vector)
+            if (x == 0.0f) x = 0.0f;
+    const uint32_t dim = (uint32_t)vector.size();
+    std::unique_lock<std::shared_mutex> g(sp.mu);
+    auto it = sp.where.find(key);
+    if (it != sp.where.end() && it->second.first != dim) {
+        g.unlock();
+        auto d = delete_in_space(sp, key);
+        if (d.is_err()) return d.error();
+        g.lock();
+        it = sp.where.end();
+    }
+    auto &slot = sp.buckets[dim];
+    if (!slot) {
+        slot.reset(new Bucket());
+        slot->dim = dim;
+    }
+    Bucket &b = *slot;
+    if (it != sp.where.end()) {
+        uint64_t row = it->second.second;
+        std::memcpy(&b.rows[row * dim], vector.data(), (size_t)dim * 4);
+        if (b.mirror && row < b.synced_rows) {
+            int rc = nm_index_update(b.mirror, row, vector.data());
+            if (rc) return storage_from_nm(rc);
+        }
+        return Unit{};
+    }
+    uint64_t row = b.keys.size();
+    b.keys.push_back(key);
+    b.rows.insert(b.rows.end(), vector.begin(), vector.end());
+    sp.where[key] = {dim, row};
+    return Unit{};  // the device append is deferred to the next search (batched)
+}
+
+Result<Unit> VectorEngine::delete_in_space(Space &sp, const std::string &key) {
+    std::unique_lock<std::shared_mutex> g(sp.mu);
+    auto it = sp.where.find(key);
+    if (it == sp.where.end()) return err(ErrorKind::NotFound, key);
+    const uint32_t dim = it->second.first;
+    const uint64_t row = it->second.second;
+    Bucket &b = *sp.buckets[dim];
+    const uint64_t last = b.keys.size() - 1;
+    if (b.mirror && row < b.synced_rows) {
+        // bring the device up to date so that "last row" means the same on both sides
+        if (b.synced_rows < b.keys.size()) {
+            int rc = nm_index_append(b.mirror, &b.rows[b.synced_rows * dim],
+                                     b.keys.size() - b.synced_rows);
+            if (rc) return storage_from_nm(rc);
+            b.synced_rows = b.keys.size();
+        }
+        uint64_t moved = 0;
+        int rc = nm_index_swap_remove(b.mirror, row, &moved);
+        if (rc) return storage_from_nm(rc);
+        b.synced_rows -= 1;
+    }
+    if (row != last) {
+        std::memcpy(&b.rows[row * dim], &b.rows[last * dim], (size_t)dim * 4);
+        b.keys[row] = std::move(b.keys[last]);
+        sp.where[b.keys[row]] = {dim, row};
+    }
+    b.keys.pop_back();
+    b.rows.resize(b.keys.size() * (size_t)dim);
+    sp.where.erase(key);
+    if (b.keys.empty()) sp.buckets.erase(dim);
+    return Unit{};
+}
+
+Result<std::vector<float>> VectorEngine::get_in_space(const Space &sp,
+                                                      const std::string &key) const {
+    std::shared_lock<std::shared_mutex> g(sp.mu);
+    auto it = sp.where.find(key);
+    if (it == sp.where.end()) return err(ErrorKind::NotFound, key);
+    const Bucket &b = *sp.buckets.at(it->second.first);
+    const float *p = &b.rows[it->second.second * (size_t)b.dim];
+    return std::vector<float>(p, p + b.dim);
+}
+
+// The seam of SURVEY 8b: "store.scan -> search_* -> sort_by -> truncate" becomes one nm_search.
+Result<std::vector<SearchResult>> VectorEngine::scan_space(
+    const Space &sp, const std::vector<float> &query, size_t top_k, DistanceMetric metric,
+    const char *operation, std::chrono::steady_clock::time_point start) const {
+    auto expired = [&]() {
+        if (!config_.search_timeout) return false;
+        return std::chrono::steady_clock::now() - start >= *config_.search_timeout;
+    };
+    auto timeout_err = [&]() {
+        VectorError e;
+        e.kind = ErrorKind::SearchTimeout;
+        e.operation = operation;
+        e.timeout_ms = (uint64_t)config_.search_timeout->count();
+        return e;
+    };
+    std::shared_lock<std::shared_mutex> g(sp.mu);
+    auto bit = sp.buckets.find((uint32_t)query.size());
+    // first deadline check: after the reference's store.scan (lib.rs:2005-2010)
+    if (expired()) return timeout_err();
+    if (bit == sp.buckets.end() || bit->second->keys.empty())
+        return std::vector<SearchResult>{};  // rows of other dimensions are skipped
+    Bucket &b = *bit->second;
+    {
+        std::lock_guard<std::mutex> sg(b.sync_mu);
+        if (!b.mirror) {
+            const int *devs = config_.devices.empty() ? nullptr : config_.devices.data();
+            int rc = nm_index_create(b.dim, devs, (int)config_.devices.size(), &b.mirror);
+            if (rc) return storage_from_nm(rc);
+        }
+        if (b.synced_rows < b.keys.size()) {
+            int rc = nm_index_append(b.mirror, &b.rows[b.synced_rows * (size_t)b.dim],
+                                     b.keys.size() - b.synced_rows);
+            if (rc) return storage_from_nm(rc);
+            b.synced_rows = b.keys.size();
+        }
+    }
+    // The device path serves k <= NM_TOPK_FAST_MAX per call; clamp to the row count first
+    // (truncate(top_k) on fewer rows returns them all, lib.rs:2034).
+    size_t k = std::min<size_t>(top_k, b.keys.size());
+    std::vector<uint64_t> rows(k);
+    std::vector<float> scores(k);
+    uint32_t count = 0;
+    int rc = nm_search(b.mirror, query.data(), 1, (uint32_t)k, (int)metric, rows.data(),
+                       scores.data(), &count);
+    if (rc) return storage_from_nm(rc);
+    // second deadline check: after scoring (lib.rs:2019-2024)
+    if (expired()) return timeout_err();
+    std::vector<SearchResult> out;
+    out.reserve(count);
+    for (uint32_t i = 0; i < count; ++i) out.push_back(SearchResult{b.keys[rows[i]], scores[i]});
+    return out;
+}
+
+// --------------------------------------------------------------------------------------
+// public API
+// --------------------------------------------------------------------------------------
+Result<Unit> VectorEngine::store_embedding(const std::string &key, std::vector<float> vector) {
+    if (vector.empty()) return err(ErrorKind::EmptyVector);
+    if (config_.max_dimension && vector.size() > *config_.max_dimension)
+        return dim_mismatch(*config_.max_dimension, vector.size());
+    return store_in_space(*default_space_, key, std::move(vector));
+}
+
+Result<std::vector<float>> VectorEngine::get_embedding(const std::string &key) const {
+    return get_in_space(*default_space_, key);
+}
+
+Result<Unit> VectorEngine::delete_embedding(const std::string &key) {
+    return delete_in_space(*default_space_, key);
+}
+
+bool VectorEngine::exists(const std::string &key) const {
+    std::shared_lock<std::shared_mutex> g(default_space_->mu);
+    return default_space_->where.count(key) != 0;
+}
+
+size_t VectorEngine::count() const {
+    std::shared_lock<std::shared_mutex> g(default_space_->mu);
+    return default_space_->where.size();
+}
+
+std::optional<size_t> VectorEngine::dimension() const {
+    std::shared_lock<std::shared_mutex> g(default_space_->mu);
+    if (default_space_->buckets.empty()) return std::nullopt;
+    return (size_t)default_space_->buckets.begin()->first;
+}
+
+Result<size_t> VectorEngine::batch_store_embeddings(
+    const std::vector<std::pair<std::string, std::vector<float>>> &items) {
+    for (size_t i = 0; i < items.size(); ++i) {
+        if (items[i].second.empty()) {
+            VectorError e = err(ErrorKind::InvalidArgument,
+                                "batch validation failed at index " + std::to_string(i) +
+                                    ": empty vector");
+            return e;
+        }
+        if (config_.max_dimension && items[i].second.size() > *config_.max_dimension)
+            return dim_mismatch(*config_.max_dimension, items[i].second.size());
+    }
+    for (auto &kv : items) {
+        auto r = store_embedding(kv.first, kv.second);
+        if (r.is_err()) return r.error();
+    }
+    return items.size();
+}
+
+Result<std::vector<SearchResult>> VectorEngine::search_similar(const std::vector<float> &query,
+                                                               size_t top_k) const {
+    auto start = std::chrono::steady_clock::now();
+    if (query.empty()) return err(ErrorKind::EmptyVector);
+    if (top_k == 0) return err(ErrorKind::InvalidTopK);
+    if (config_.max_dimension && query.size() > *config_.max_dimension)
+        return dim_mismatch(*config_.max_dimension, query.size());
+    float qmag = simd::magnitude(query.data(), query.size());
+    if (qmag == 0.0f) return std::vector<SearchResult>{};  // lib.rs:1970-1974
+    return scan_space(*default_space_, query, top_k, DistanceMetric::Cosine, "search_similar",
+                      start);
+}
+
+Result<std::vector<SearchResult>> VectorEngine::search_similar_with_metric(
+    const std::vector<float> &query, size_t top_k, DistanceMetric metric) const {
+    auto start = std::chrono::steady_clock::now();
+    if (query.empty()) return err(ErrorKind::EmptyVector);
+    if (top_k == 0) return err(ErrorKind::InvalidTopK);
+    float qmag = simd::magnitude(query.data(), query.size());
+    if (qmag == 0.0f && metric != DistanceMetric::Euclidean)  // lib.rs:2066
+        return std::vector<SearchResult>{};
+    return scan_space(*default_space_, query, top_k, metric, "search_similar_with_metric", start);
+}
+
+Result<float> VectorEngine::compute_similarity(const std::vector<float> &a,
+                                               const std::vector<float> &b) {
+    if (a.empty() || b.empty()) return err(ErrorKind::EmptyVector);
+    if (a.size() != b.size()) return dim_mismatch(a.size(), b.size());
+    float am = simd::magnitude(a.data(), a.size());
+    if (am == 0.0f) return 0.0f;
+    float dot = simd::dot_product(a.data(), b.data(), a.size());
+    float bm = simd::magnitude(b.data(), b.size());
+    if (am == 0.0f || bm == 0.0f) return 0.0f;
+    float den = am * bm;
+    return dot / den;
+}
+
+// ---- collections ----
+struct VectorEngine::CollectionEntry {
+    std::optional<VectorCollectionConfig> config;
+    std::unique_ptr<Space> space{new Space()};
+};
+
+VectorEngine::Space &VectorEngine::collection_space(const std::string &name) {
+    std::unique_lock<std::shared_mutex> g(collections_mu_);
+    auto &e = collections_[name];
+    if (!e) e.reset(new CollectionEntry());
+    return *e->space;
+}
+
+const VectorEngine::Space *VectorEngine::find_collection_space(const std::string &name) const {
+    std::shared_lock<std::shared_mutex> g(collections_mu_);
+    auto it = collections_.find(name);
+    return it == collections_.end() ? nullptr : it->second->space.get();
+}
+
+Result<Unit> VectorEngine::create_collection(const std::string &name,
+                                             VectorCollectionConfig config) {
+    std::unique_lock<std::shared_mutex> g(collections_mu_);
+    auto &e = collections_[name];
+    if (e && e->config) return err(ErrorKind::CollectionExists, name);
+    if (!e) e.reset(new CollectionEntry());
+    e->config = config;
+    return Unit{};
+}
+
+Result<Unit> VectorEngine::delete_collection(const std::string &name) {
+    std::unique_lock<std::shared_mutex> g(collections_mu_);
+    auto it = collections_.find(name);
+    if (it == collections_.end() || !it->second->config)
+        return err(ErrorKind::CollectionNotFound, name);
+    collections_.erase(it);  // drops the rows and the device mirror with it
+    return Unit{};
+}
+
+bool VectorEngine::collection_exists(const std::string &name) const {
+    std::shared_lock<std::shared_mutex> g(collections_mu_);
+    auto it = collections_.find(name);
+    return it != collections_.end() && it->second->config.has_value();
+}
+
+std::vector<std::string> VectorEngine::list_collections() const {
+    std::shared_lock<std::shared_mutex> g(collections_mu_);
+    std::vector<std::string> out;
+    for (auto &kv : collections_)
+        if (kv.second->config) out.push_back(kv.first);
+    return out;
+}
+
+Result<Unit> VectorEngine::store_in_collection(const std::string &collection,
+                                               const std::string &key,
+                                               std::vector<float> vector) {
+    if (vector.empty()) return err(ErrorKind::EmptyVector);
+    {
+        std::shared_lock<std::shared_mutex> g(collections_mu_);
+        auto it = collections_.find(collection);
+        if (it != collections_.end() && it->second->config && it->second->config->dimension &&
+            vector.size() != *it->second->config->dimension)
+            return dim_mismatch(*it->second->config->dimension, vector.size());
+    }
+    if (config_.max_dimension && vector.size() > *config_.max_dimension)
+        return dim_mismatch(*config_.max_dimension, vector.size());
+    return store_in_space(collection_space(collection), key, std::move(vector));
+}
+
+Result<std::vector<float>> VectorEngine::get_from_collection(const std::string &collection,
+                                                             const std::string &key) const {
+    const Space *sp = find_collection_space(collection);
+    if (!sp) return err(ErrorKind::NotFound, collection + ":" + key);
+    auto r = get_in_space(*sp, key);
+    if (r.is_err()) return err(ErrorKind::NotFound, collection + ":" + key);
+    return r;
+}
+
+Result<Unit> VectorEngine::delete_from_collection(const std::string &collection,
+                                                  const std::string &key) {
+    const Space *sp = find_collection_space(collection);
+    if (!sp) return err(ErrorKind::NotFound, collection + ":" + key);
+    auto r = delete_in_space(*const_cast<Space *>(sp), key);
+    if (r.is_err()) return err(ErrorKind::NotFound, collection + ":" + key);
+    return r;
+}
+
+size_t VectorEngine::collection_count(const std::string &collection) const {
+    const Space *sp = find_collection_space(collection);
+    if (!sp) return 0;
+    std::shared_lock<std::shared_mutex> g(sp->mu);
+    return sp->where.size();
+}
+
+// lib.rs:1585-1689
+Result<std::vector<SearchResult>> VectorEngine::search_in_collection(
+    const std::string &collection, const std::vector<float> &query, size_t top_k) const {
+    auto start = std::chrono::steady_clock::now();
+    if (query.empty()) return err(ErrorKind::EmptyVector);
+    if (top_k == 0) return err(ErrorKind::InvalidTopK);
+    DistanceMetric metric = DistanceMetric::Cosine;
+    const Space *sp = nullptr;
+    {
+        std::shared_lock<std::shared_mutex> g(collections_mu_);
+        auto it = collections_.find(collection);
+        if (it != collections_.end()) {
+            if (it->second->config) {
+                if (it->second->config->dimension &&
+                    query.size() != *it->second->config->dimension)
+                    return dim_mismatch(*it->second->config->dimension, query.size());
+                metric = it->second->config->distance_metric;
+            }
+            sp = it->second->space.get();
+        }
+    }
+    float qmag = simd::magnitude(query.data(), query.size());
+    if (qmag == 0.0f && metric == DistanceMetric::Cosine)  // lib.rs:1618-1620 (cosine only)
+        return std::vector<SearchResult>{};
+    if (!sp) return std::vector<SearchResult>{};
+    return scan_space(*sp, query, top_k, metric, "search_in_collection", start);
+}
+
+std::vector<VectorEngine::MirrorInfo> VectorEngine::mirror_info() const {
+    std::vector<MirrorInfo> out;
+    std::shared_lock<std::shared_mutex> g(default_space_->mu);
+    for (auto &kv : default_space_->buckets)
+        out.push_back(MirrorInfo{kv.first, (uint64_t)kv.second->keys.size(),
+                                 kv.second->mirror ? nm_index_rows(kv.second->mirror) : 0});
+    return out;
+}
+
+}  // namespace neumann

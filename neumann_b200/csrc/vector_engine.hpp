@@ -1,0 +1,182 @@
+// vector_engine.hpp — C++ host mirror of the reference's `vector_engine` crate, restricted to
+// the SIMILAR hot path and the store operations that feed it.  Same names, argument meaning
+// and error behaviour as the Rust API (vector_engine/src/lib.rs); the scan itself is delegated
+// to the device through the nm_* C ABI (include/neumann_b200.h).  There is no CPU scan here:
+// without a CUDA device the search methods return StorageError.
+//
+// Not mirrored (out of scope): HNSW/IVF wrappers, metadata filters, pagination,
+// persistence, entity embeddings.
+#pragma once
+#include <chrono>
+#include <cstdint>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <optional>
+#include <shared_mutex>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+struct nm_index;
+
+namespace neumann {
+
+// vector_engine/src/lib.rs:281-289
+enum class DistanceMetric : int { Cosine = 0, Euclidean = 1, DotProduct = 2 };
+
+// vector_engine/src/lib.rs:252-258
+struct SearchResult {
+    std::string key;
+    float score;
+};
+
+// vector_engine/src/lib.rs:102-149 (the variants this path can produce)
+enum class ErrorKind : int {
+    NotFound,
+    DimensionMismatch,
+    EmptyVector,
+    InvalidTopK,
+    StorageError,
+    ConfigurationError,
+    CollectionExists,
+    CollectionNotFound,
+    SearchTimeout,
+    InvalidArgument,
+};
+
+struct VectorError {
+    ErrorKind kind = ErrorKind::StorageError;
+    std::string message;       // NotFound(key) / StorageError(msg) / ConfigurationError(msg) / ...
+    size_t expected = 0, got = 0;  // DimensionMismatch
+    std::string operation;     // SearchTimeout
+    uint64_t timeout_ms = 0;   // SearchTimeout
+    int status() const;        // nm_status code
+    std::string to_string() const;
+};
+
+template <class T>
+class Result {
+  public:
+    Result(T v) : val_(std::move(v)) {}
+    Result(VectorError e) : err_(std::move(e)) {}
+    bool is_ok() const { return val_.has_value(); }
+    bool is_err() const { return !val_.has_value(); }
+    T &value() { return *val_; }
+    const T &value() const { return *val_; }
+    const VectorError &error() const { return *err_; }
+
+  private:
+    std::optional<T> val_;
+    std::optional<VectorError> err_;
+};
+struct Unit {};
+
+// vector_engine/src/lib.rs:626-663.  `devices` is the only addition: which GPUs hold the mirror.
+struct VectorEngineConfig {
+    std::optional<size_t> default_dimension;
+    float sparse_threshold = 0.5f;
+    size_t parallel_threshold = 5000;  // kept for API parity; the device scan has no such switch
+    DistanceMetric default_metric = DistanceMetric::Cosine;
+    std::optional<size_t> max_dimension;
+    std::optional<size_t> max_keys_per_scan;
+    size_t batch_parallel_threshold = 100;
+    std::optional<std::chrono::milliseconds> search_timeout;
+    std::vector<int> devices;  // empty = current device
+    Result<Unit> validate() const;  // lib.rs:771-826
+};
+
+// vector_engine/src/lib.rs:455-499
+struct VectorCollectionConfig {
+    std::optional<size_t> dimension;
+    DistanceMetric distance_metric = DistanceMetric::Cosine;
+    bool auto_index = false;          // kept for API parity (HNSW is out of scope)
+    size_t auto_index_threshold = 1000;
+};
+
+// The reference's f32 helpers this layer needs on the host (zero-query short-circuit,
+// compute_similarity).  Bit-identical restatement of tensor_store/src/hnsw.rs:168-229.
+namespace simd {
+float dot_product(const float *a, const float *b, size_t n);
+float sum_of_squares(const float *v, size_t n);
+float magnitude(const float *v, size_t n);
+}  // namespace simd
+
+class VectorEngine {
+  public:
+    VectorEngine();
+    explicit VectorEngine(VectorEngineConfig config);
+    static Result<std::unique_ptr<VectorEngine>> with_config(VectorEngineConfig config);
+    ~VectorEngine();
+    VectorEngine(const VectorEngine &) = delete;
+    VectorEngine &operator=(const VectorEngine &) = delete;
+
+    const VectorEngineConfig &config() const { return config_; }
+
+    // lib.rs:1840-1868 / 1896-1925 / 1929-1940
+    Result<Unit> store_embedding(const std::string &key, std::vector<float> vector);
+    Result<std::vector<float>> get_embedding(const std::string &key) const;
+    Result<Unit> delete_embedding(const std::string &key);
+    bool exists(const std::string &key) const;
+    size_t count() const;
+    std::optional<size_t> dimension() const;
+    // lib.rs:2865-2913 (validation first, then stores; returns number stored)
+    Result<size_t> batch_store_embeddings(
+        const std::vector<std::pair<std::string, std::vector<float>>> &items);
+
+    // lib.rs:1950-2037, 2049-2101
+    Result<std::vector<SearchResult>> search_similar(const std::vector<float> &query,
+                                                     size_t top_k) const;
+    Result<std::vector<SearchResult>> search_similar_with_metric(const std::vector<float> &query,
+                                                                 size_t top_k,
+                                                                 DistanceMetric metric) const;
+    // lib.rs:2277-2295
+    static Result<float> compute_similarity(const std::vector<float> &a,
+                                            const std::vector<float> &b);
+
+    // collections: lib.rs:1371-1470, 1475-1560, 1585-1689
+    Result<Unit> create_collection(const std::string &name, VectorCollectionConfig config);
+    Result<Unit> delete_collection(const std::string &name);
+    bool collection_exists(const std::string &name) const;
+    std::vector<std::string> list_collections() const;
+    Result<Unit> store_in_collection(const std::string &collection, const std::string &key,
+                                     std::vector<float> vector);
+    Result<std::vector<float>> get_from_collection(const std::string &collection,
+                                                   const std::string &key) const;
+    Result<Unit> delete_from_collection(const std::string &collection, const std::string &key);
+    size_t collection_count(const std::string &collection) const;
+    Result<std::vector<SearchResult>> search_in_collection(const std::string &collection,
+                                                           const std::vector<float> &query,
+                                                           size_t top_k) const;
+
+    // Device-mirror introspection (tests / metrics).
+    struct MirrorInfo {
+        uint32_t dim;
+        uint64_t host_rows, device_rows;
+    };
+    std::vector<MirrorInfo> mirror_info() const;
+
+  private:
+    struct Bucket;
+    struct Space;
+    VectorEngineConfig config_;
+    std::unique_ptr<Space> default_space_;
+    mutable std::shared_mutex collections_mu_;
+    // A collection's rows may exist without a config (store_in_collection does not require
+    // create_collection, lib.rs:1445-1500); `config` is set by create_collection only.
+    struct CollectionEntry;
+    std::map<std::string, std::unique_ptr<CollectionEntry>> collections_;
+    Space &collection_space(const std::string &name);              // creates on demand
+    const Space *find_collection_space(const std::string &name) const;
+
+    bool should_use_sparse(const std::vector<float> &v) const;  // lib.rs:1871-1886
+    Result<Unit> store_in_space(Space &sp, const std::string &key, std::vector<float> vector);
+    Result<Unit> delete_in_space(Space &sp, const std::string &key);
+    Result<std::vector<float>> get_in_space(const Space &sp, const std::string &key) const;
+    Result<std::vector<SearchResult>> scan_space(const Space &sp, const std::vector<float> &query,
+                                                 size_t top_k, DistanceMetric metric,
+                                                 const char *operation,
+                                                 std::chrono::steady_clock::time_point start) const;
+};
+
+}  // namespace neumann

@@ -1,0 +1,231 @@
+"""Python view of the C++ host mirror (VectorEngine / QueryRouter) through
+include/neumann_b200_engine.h.  Test + bench harness only: method names, argument meaning and
+error behaviour follow vector_engine/src/lib.rs so the parity tests read like the reference's.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import _ffi
+
+COSINE, EUCLIDEAN, DOT_PRODUCT = 0, 1, 2
+
+
+class NmEngineConfig(C.Structure):
+    _fields_ = [
+        ("default_dimension", C.c_uint64), ("sparse_threshold", C.c_float),
+        ("parallel_threshold", C.c_uint64), ("default_metric", C.c_int),
+        ("max_dimension", C.c_uint64), ("search_timeout_ms", C.c_int64),
+        ("n_devices", C.c_int), ("devices", C.c_int * 8),
+    ]
+
+
+_vp, _cp, _sz, _u64 = C.c_void_p, C.c_char_p, C.c_size_t, C.c_uint64
+_pvp = C.POINTER(C.c_void_p)
+ENGINE_SIGNATURES = {
+    "nm_engine_config_default": (None, [C.POINTER(NmEngineConfig)]),
+    "nm_engine_create": (C.c_int, [C.POINTER(NmEngineConfig), _pvp]),
+    "nm_engine_destroy": (None, [_vp]),
+    "nm_engine_last_error": (_cp, []),
+    "nm_engine_store_embedding": (C.c_int, [_vp, _cp, _vp, _sz]),
+    "nm_engine_get_embedding": (C.c_int, [_vp, _cp, _vp, _sz, C.POINTER(_sz)]),
+    "nm_engine_delete_embedding": (C.c_int, [_vp, _cp]),
+    "nm_engine_exists": (C.c_int, [_vp, _cp]),
+    "nm_engine_count": (_u64, [_vp]),
+    "nm_engine_search_similar": (C.c_int, [_vp, _vp, _sz, _sz, _pvp]),
+    "nm_engine_search_similar_with_metric": (C.c_int, [_vp, _vp, _sz, _sz, C.c_int, _pvp]),
+    "nm_engine_compute_similarity": (C.c_int, [_vp, _sz, _vp, _sz, C.POINTER(C.c_float)]),
+    "nm_engine_create_collection": (C.c_int, [_vp, _cp, _u64, C.c_int]),
+    "nm_engine_delete_collection": (C.c_int, [_vp, _cp]),
+    "nm_engine_collection_exists": (C.c_int, [_vp, _cp]),
+    "nm_engine_store_in_collection": (C.c_int, [_vp, _cp, _cp, _vp, _sz]),
+    "nm_engine_delete_from_collection": (C.c_int, [_vp, _cp, _cp]),
+    "nm_engine_collection_count": (_u64, [_vp, _cp]),
+    "nm_engine_search_in_collection": (C.c_int, [_vp, _cp, _vp, _sz, _sz, _pvp]),
+    "nm_engine_execute": (C.c_int, [_vp, _cp, _pvp]),
+    "nm_engine_execute_parsed": (C.c_int, [_vp, _cp, _pvp]),
+    "nm_engine_mirror_rows": (C.c_int, [_vp, C.c_uint32, C.POINTER(_u64), C.POINTER(_u64)]),
+    "nm_results_len": (_sz, [_vp]),
+    "nm_results_key": (_cp, [_vp, _sz]),
+    "nm_results_score": (C.c_float, [_vp, _sz]),
+    "nm_results_free": (None, [_vp]),
+}
+
+_bound = False
+
+
+def _lib():
+    global _bound
+    l = _ffi.lib()
+    if not _bound:
+        for name, (res, args) in ENGINE_SIGNATURES.items():
+            fn = getattr(l, name)
+            fn.restype, fn.argtypes = res, args
+        _bound = True
+    return l
+
+
+_KINDS = {1: "EmptyVector", 2: "InvalidTopK", 3: "DimensionMismatch", 4: "StorageError",
+          5: "SearchTimeout", 6: "InvalidArgument", 7: "NotFound", 8: "ConfigurationError",
+          9: "CollectionExists", 10: "CollectionNotFound"}
+
+
+class VectorError(Exception):
+    """VectorError (vector_engine/src/lib.rs:102-149); `.kind` is the variant name."""
+
+    def __init__(self, code: int, msg: str):
+        super().__init__(msg)
+        self.code = code
+        self.kind = _KINDS.get(code, "Unknown")
+
+
+def _check(code: int) -> None:
+    if code != 0:
+        raise VectorError(code, _lib().nm_engine_last_error().decode("utf-8", "replace"))
+
+
+@dataclass
+class SearchResult:
+    key: str
+    score: float
+
+
+def _f32(v) -> np.ndarray:
+    return np.ascontiguousarray(np.asarray(v, dtype=np.float32).reshape(-1))
+
+
+def _take(handle: C.c_void_p) -> list[SearchResult]:
+    l = _lib()
+    if not handle:
+        return []
+    try:
+        n = l.nm_results_len(handle)
+        return [SearchResult(l.nm_results_key(handle, i).decode(), float(np.float32(l.nm_results_score(handle, i))))
+                for i in range(n)]
+    finally:
+        l.nm_results_free(handle)
+
+
+class VectorEngine:
+    def __init__(self, *, sparse_threshold: float | None = None, parallel_threshold: int | None = None,
+                 max_dimension: int | None = None, search_timeout_ms: int | None = None,
+                 devices: list[int] | None = None):
+        l = _lib()
+        cfg = NmEngineConfig()
+        l.nm_engine_config_default(C.byref(cfg))
+        if sparse_threshold is not None:
+            cfg.sparse_threshold = sparse_threshold
+        if parallel_threshold is not None:
+            cfg.parallel_threshold = parallel_threshold
+        if max_dimension is not None:
+            cfg.max_dimension = max_dimension
+        if search_timeout_ms is not None:
+            cfg.search_timeout_ms = search_timeout_ms
+        if devices:
+            cfg.n_devices = len(devices)
+            for i, d in enumerate(devices[:8]):
+                cfg.devices[i] = d
+        self._h = C.c_void_p()
+        _check(l.nm_engine_create(C.byref(cfg), C.byref(self._h)))
+
+    def close(self):
+        if self._h:
+            _lib().nm_engine_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- store side ----
+    def store_embedding(self, key: str, vector) -> None:
+        v = _f32(vector)
+        _check(_lib().nm_engine_store_embedding(self._h, key.encode(), v.ctypes.data, v.size))
+
+    def get_embedding(self, key: str) -> np.ndarray:
+        n = C.c_size_t()
+        _check(_lib().nm_engine_get_embedding(self._h, key.encode(), None, 0, C.byref(n)))
+        out = np.empty(n.value, np.float32)
+        _check(_lib().nm_engine_get_embedding(self._h, key.encode(), out.ctypes.data, out.size, C.byref(n)))
+        return out
+
+    def delete_embedding(self, key: str) -> None:
+        _check(_lib().nm_engine_delete_embedding(self._h, key.encode()))
+
+    def exists(self, key: str) -> bool:
+        return bool(_lib().nm_engine_exists(self._h, key.encode()))
+
+    def count(self) -> int:
+        return int(_lib().nm_engine_count(self._h))
+
+    # ---- search side ----
+    def search_similar(self, query, top_k: int) -> list[SearchResult]:
+        q = _f32(query)
+        h = C.c_void_p()
+        _check(_lib().nm_engine_search_similar(self._h, q.ctypes.data, q.size, top_k, C.byref(h)))
+        return _take(h)
+
+    def search_similar_with_metric(self, query, top_k: int, metric: int) -> list[SearchResult]:
+        q = _f32(query)
+        h = C.c_void_p()
+        _check(_lib().nm_engine_search_similar_with_metric(self._h, q.ctypes.data, q.size, top_k,
+                                                           metric, C.byref(h)))
+        return _take(h)
+
+    @staticmethod
+    def compute_similarity(a, b) -> float:
+        a, b = _f32(a), _f32(b)
+        out = C.c_float()
+        _check(_lib().nm_engine_compute_similarity(a.ctypes.data, a.size, b.ctypes.data, b.size,
+                                                   C.byref(out)))
+        return float(np.float32(out.value))
+
+    # ---- collections ----
+    def create_collection(self, name: str, dimension: int | None = None, metric: int = COSINE):
+        _check(_lib().nm_engine_create_collection(self._h, name.encode(), dimension or 0, metric))
+
+    def delete_collection(self, name: str):
+        _check(_lib().nm_engine_delete_collection(self._h, name.encode()))
+
+    def collection_exists(self, name: str) -> bool:
+        return bool(_lib().nm_engine_collection_exists(self._h, name.encode()))
+
+    def store_in_collection(self, collection: str, key: str, vector):
+        v = _f32(vector)
+        _check(_lib().nm_engine_store_in_collection(self._h, collection.encode(), key.encode(),
+                                                    v.ctypes.data, v.size))
+
+    def delete_from_collection(self, collection: str, key: str):
+        _check(_lib().nm_engine_delete_from_collection(self._h, collection.encode(), key.encode()))
+
+    def collection_count(self, collection: str) -> int:
+        return int(_lib().nm_engine_collection_count(self._h, collection.encode()))
+
+    def search_in_collection(self, collection: str, query, top_k: int) -> list[SearchResult]:
+        q = _f32(query)
+        h = C.c_void_p()
+        _check(_lib().nm_engine_search_in_collection(self._h, collection.encode(), q.ctypes.data,
+                                                     q.size, top_k, C.byref(h)))
+        return _take(h)
+
+    # ---- router ----
+    def execute(self, command: str) -> list[SearchResult] | None:
+        """QueryRouter::execute (legacy string path).  None == QueryResult::Empty."""
+        h = C.c_void_p()
+        _check(_lib().nm_engine_execute(self._h, command.encode(), C.byref(h)))
+        return _take(h) if h else None
+
+    def execute_parsed(self, command: str) -> list[SearchResult] | None:
+        h = C.c_void_p()
+        _check(_lib().nm_engine_execute_parsed(self._h, command.encode(), C.byref(h)))
+        return _take(h) if h else None
+
+    def mirror_rows(self, dim: int) -> tuple[int, int]:
+        a, b = C.c_uint64(), C.c_uint64()
+        _check(_lib().nm_engine_mirror_rows(self._h, dim, C.byref(a), C.byref(b)))
+        return int(a.value), int(b.value)

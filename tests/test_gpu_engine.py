@@ -1,0 +1,199 @@
+"""The reference's own behavioural tests for the path, replayed through the C++ host mirror
+(VectorEngine / QueryRouter) with the scan on the GPU."""
+import json
+import threading
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+import oracle_ffi as o
+from neumann_b200 import engine as eng
+from test_oracle import check_search_kat, create_test_vector
+
+pytestmark = pytest.mark.gpu
+GOLD = Path(__file__).parent / "golden"
+KATS = json.loads((GOLD / "reference_kats.json").read_text())
+METRIC_ID = {"cosine": eng.COSINE, "euclidean": eng.EUCLIDEAN, "dot": eng.DOT_PRODUCT}
+
+
+@pytest.mark.parametrize("kat", KATS["search"], ids=lambda k: k["src"])
+def test_reference_search_kats_on_gpu(kat):
+    e = eng.VectorEngine()
+    for k, v in kat["store"].items():
+        e.store_embedding(k, v)
+    if kat["api"] == "search_similar":
+        res = e.search_similar(kat["query"], kat["k"])
+    else:
+        res = e.search_similar_with_metric(kat["query"], kat["k"], METRIC_ID[kat["metric"]])
+    check_search_kat(kat, [(r.key, r.score) for r in res])
+
+
+def test_store_10000_vectors_search():
+    # vector_engine/src/lib.rs:4256-4276
+    e = eng.VectorEngine()
+    for i in range(10000):
+        e.store_embedding(f"v{i}", create_test_vector(128, i))
+    assert e.count() == 10000
+    res = e.search_similar(create_test_vector(128, 5000), 5)
+    assert len(res) == 5 and res[0].key == "v5000" and abs(res[0].score - 1.0) < 1e-5
+    assert e.mirror_rows(128) == (10000, 10000)
+
+
+@pytest.mark.parametrize("dim,probe", [(768, 50), (1536, 75)])
+def test_high_dimensional(dim, probe):
+    e = eng.VectorEngine()
+    for i in range(100):
+        e.store_embedding(f"v{i}", create_test_vector(dim, i))
+    assert e.search_similar(create_test_vector(dim, probe), 5)[0].key == f"v{probe}"
+
+
+def test_example_vector_search():
+    ex = json.loads((GOLD / "example_vector_search.json").read_text())
+    e = eng.VectorEngine()
+    for k, v in ex["docs"].items():
+        e.store_embedding(k, v)
+    keys = list(ex["docs"])
+    rows = np.asarray([ex["docs"][k] for k in keys], np.float32)
+    for spec in ex["queries"].values():
+        res = e.search_similar(spec["vector"], 3)
+        assert {r.key for r in res[:len(spec["top_set"])]} == set(spec["top_set"])
+        er, es = o.search(rows, np.asarray(spec["vector"], np.float32), 3, "cosine")
+        assert [r.key for r in res] == [keys[int(i)] for i in er]
+        assert [np.float32(r.score).view(np.uint32) for r in res] == list(es.view(np.uint32))
+
+
+def test_search_with_metric_parallel_path():
+    # vector_engine/src/lib.rs:6583-6603
+    e = eng.VectorEngine(parallel_threshold=5)
+    for i in range(10):
+        e.store_embedding(f"vec_{i}", [float(i), 0.0, 0.0])
+    res = e.search_similar_with_metric([5.0, 0.0, 0.0], 3, eng.EUCLIDEAN)
+    assert len(res) == 3 and res[0].key == "vec_5" and res[0].score == 1.0
+    assert {res[1].key, res[2].key} == {"vec_4", "vec_6"} and res[1].score == 0.5
+
+
+def test_mirror_is_maintained_incrementally():
+    e = eng.VectorEngine()
+    rows = o.fill_synthetic(500, 32, 3)
+    for i in range(300):
+        e.store_embedding(f"k{i}", rows[i])
+    q = rows[10]
+    assert e.search_similar(q, 1)[0].key == "k10"
+    assert e.mirror_rows(32) == (300, 300)
+    for i in range(300, 500):
+        e.store_embedding(f"k{i}", rows[i])          # appended lazily at the next search
+    assert e.mirror_rows(32) == (500, 300)
+    assert e.search_similar(rows[400], 1)[0].key == "k400"
+    assert e.mirror_rows(32) == (500, 500)
+    e.store_embedding("k7", rows[400])               # overwrite in place -> exact tie with k400
+    res = e.search_similar(rows[400], 2)
+    assert {res[0].key, res[1].key} == {"k7", "k400"} and res[0].score == res[1].score
+    e.delete_embedding("k400")
+    res = e.search_similar(rows[400], 2)
+    assert res[0].key == "k7" and res[1].key != "k400"
+    assert e.mirror_rows(32) == (499, 499)
+    e.store_embedding("k8", [1.0, 2.0])              # key moves to another dimension bucket
+    assert e.mirror_rows(32)[0] == 498
+    assert e.search_similar([1.0, 2.0], 5)[0].key == "k8"
+
+
+def test_engine_results_match_oracle_order_and_bits():
+    e = eng.VectorEngine()
+    rows = o.fill_synthetic(3000, 48, 12)
+    for i in range(3000):
+        e.store_embedding(f"k{i}", rows[i])
+    q = o.fill_synthetic(1, 48, 13)[0]
+    for name, mid in METRIC_ID.items():
+        res = e.search_similar_with_metric(q, 25, mid)
+        er, es = o.search(rows, q, 25, name)
+        assert [r.key for r in res] == [f"k{int(i)}" for i in er]
+        assert [np.float32(r.score).view(np.uint32) for r in res] == list(es.view(np.uint32))
+
+
+def test_collections_on_gpu():
+    e = eng.VectorEngine()
+    e.create_collection("euc", dimension=2, metric=eng.EUCLIDEAN)
+    for k, v in {"origin": [0.0, 0.0], "unit": [1.0, 0.0], "far": [10.0, 0.0]}.items():
+        e.store_in_collection("euc", k, v)
+    e.store_embedding("outside", [0.0, 0.0])
+    res = e.search_in_collection("euc", [0.0, 0.0], 3)   # zero query is fine for Euclidean
+    assert [r.key for r in res] == ["origin", "unit", "far"]
+    assert res[0].score == 1.0 and res[1].score == 0.5
+    e.store_in_collection("cos", "a", [1.0, 0.0])
+    assert e.search_in_collection("cos", [0.0, 0.0], 3) == []  # cosine zero query -> empty
+    assert e.search_in_collection("cos", [2.0, 0.0], 3)[0].key == "a"
+    e.delete_from_collection("euc", "origin")
+    assert e.search_in_collection("euc", [0.0, 0.0], 3)[0].key == "unit"
+
+
+def test_router_similar_operator():
+    # query_router/src/lib.rs:7669-7685, 8051-8064, 8467-8474
+    e = eng.VectorEngine()
+    e.execute("EMBED doc1 [1.0, 0.0, 0.0]")
+    e.execute("EMBED doc2 [0.0, 1.0, 0.0]")
+    e.execute("EMBED doc3 [0.9, 0.1, 0.0]")
+    res = e.execute("SIMILAR doc1 TOP 2")
+    assert len(res) == 2 and res[0].key == "doc1" and res[1].key == "doc3"
+    assert len(e.execute("SIMILAR doc1")) == 3           # default k = 10
+    res = e.execute("SIMILAR [0.0, 1.0, 0.0] TOP 1")
+    assert len(res) == 1 and res[0].key == "doc2"
+    assert len(e.execute('SIMILAR "doc2" TOP 1')) == 1
+    # integration_tests/tests/distance_metrics.rs:39-140 (AST path, LIMIT + metric keyword)
+    e.execute("EMBED vec:1 1.0, 0.0, 0.0, 0.0")
+    e.execute("EMBED vec:2 0.9, 0.1, 0.0, 0.0")
+    e.execute("EMBED vec:3 0.0, 1.0, 0.0, 0.0")
+    res = e.execute_parsed("SIMILAR 'vec:1' LIMIT 3")
+    assert [r.key for r in res] == ["vec:1", "vec:2", "vec:3"]
+    res = e.execute_parsed("SIMILAR 'vec:1' LIMIT 3 EUCLIDEAN")
+    assert res[0].key == "vec:1" and res[0].score == 1.0
+    res = e.execute_parsed("SIMILAR [1.0, 0.0, 0.0, 0.0] LIMIT 2 DOT_PRODUCT")
+    assert [r.key for r in res] == ["vec:1", "vec:2"] and res[0].score == 1.0
+    e.execute_parsed("EMBED STORE 'c1' [0.0, 3.0] INTO things")
+    e.execute_parsed("EMBED STORE 'c2' [4.0, 0.0] INTO things")
+    res = e.execute_parsed("SIMILAR [1.0, 0.0] LIMIT 5 INTO things")
+    assert [r.key for r in res] == ["c2", "c1"]
+
+
+def test_search_timeout_is_reported():
+    e = eng.VectorEngine(search_timeout_ms=0)
+    e.store_embedding("a", [1.0, 0.0])
+    with pytest.raises(eng.VectorError) as ei:
+        e.search_similar([1.0, 0.0], 1)
+    assert ei.value.kind == "SearchTimeout" and "search_similar" in str(ei.value)
+
+
+def test_concurrent_search_and_store():
+    # vector_engine/src/lib.rs:5615-5711: searches from many threads while stores happen
+    e = eng.VectorEngine()
+    rows = o.fill_synthetic(4000, 64, 31)
+    for i in range(2000):
+        e.store_embedding(f"k{i}", rows[i])
+    errors = []
+
+    def searcher(tid):
+        try:
+            for j in range(40):
+                probe = (tid * 97 + j * 13) % 2000
+                res = e.search_similar(rows[probe], 3)
+                if res[0].key != f"k{probe}":
+                    errors.append((tid, j, res[0].key))
+        except Exception as ex:  # noqa: BLE001
+            errors.append(repr(ex))
+
+    def writer():
+        try:
+            for i in range(2000, 4000):
+                e.store_embedding(f"k{i}", rows[i])
+        except Exception as ex:  # noqa: BLE001
+            errors.append(repr(ex))
+
+    ts = [threading.Thread(target=searcher, args=(t,)) for t in range(6)] + \
+         [threading.Thread(target=writer)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    assert not errors, errors[:3]
+    assert e.count() == 4000
+    assert e.search_similar(rows[3999], 1)[0].key == "k3999"

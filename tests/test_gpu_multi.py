@@ -1,0 +1,89 @@
+"""Multi-GPU parity (skipped when fewer than 2 devices are visible): in-process row-range
+shards with the host-side merge, and one-process-per-GPU shards with the NCCL all-gather +
+device merge."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+import oracle_ffi as o
+from neumann_b200 import DeviceIndex, device_count
+
+pytestmark = pytest.mark.gpu
+
+
+def _need(n):
+    if device_count() < n:
+        pytest.skip(f"needs {n} GPUs, {device_count()} visible")
+
+
+@pytest.mark.parametrize("metric", ["cosine", "euclidean", "dot"])
+def test_in_process_two_device_shards(metric):
+    _need(2)
+    n, d = 30011, 72
+    rows = o.fill_synthetic(n, d, 0x5EED0001)
+    rows[5] = rows[29000]  # tie across shards
+    idx = DeviceIndex(d, devices=[0, 1])
+    idx.load(rows)
+    qs = np.stack([rows[29000], o.fill_synthetic(1, d, 3)[0]])
+    res = idx.search(qs, 20, metric)
+    for i in range(2):
+        er, es = o.search(rows, qs[i], 20, metric, threads=4)
+        assert np.array_equal(res[i][0], er)
+        assert np.array_equal(res[i][1].view(np.uint32), es.view(np.uint32))
+    idx.close()
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _nccl_worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+    from neumann_b200 import dist as nd
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank),
+                      WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        n, d, k = 200_003, 96, 16
+        idx = DeviceIndex(d, devices=[rank])
+        lo, hi = nd.attach_index(idx, n)
+        idx.fill_synthetic(hi - lo, 0x5EED0001, row_offset=lo)
+        qs = o.fill_synthetic(3, d, 0x5EED1001)
+        rows = o.fill_synthetic(n, d, 0x5EED0001)
+        for metric in ("cosine", "euclidean", "dot"):
+            res = idx.search(qs, k, metric)
+            for i in range(3):
+                er, es = o.search(rows, qs[i], k, metric, threads=4)
+                assert np.array_equal(res[i][0], er), (metric, i, res[i][0], er)
+                assert np.array_equal(res[i][1].view(np.uint32), es.view(np.uint32))
+        assert idx.stats().merge_launches == 3
+        idx.detach_comm()
+        idx.close()
+        q.put((rank, "ok"))
+    except Exception as e:  # noqa: BLE001
+        import traceback
+        q.put((rank, traceback.format_exc()))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_nccl_allgather_shards(world):
+    _need(world)
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_nccl_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=600) for _ in procs]
+    for p in procs:
+        p.join(timeout=120)
+    assert sorted(res) == [(r, "ok") for r in range(world)], res

@@ -1,0 +1,327 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI, against the CPU oracle on
+the same seeded inputs.  Bar: identical row ids in identical rank order and bit-identical
+scores (stronger than the 1e-5 relative the north star asks for)."""
+import numpy as np
+import pytest
+
+import oracle_ffi as o
+from neumann_b200 import DeviceIndex, NmError, _ffi
+
+pytestmark = pytest.mark.gpu
+
+METRICS = ["cosine", "euclidean", "dot"]
+
+
+def assert_same(got, exp, ctx=""):
+    gr, gs = got
+    er, es = exp
+    assert np.array_equal(gr, er), f"{ctx}: rows {gr[:8]} != {er[:8]}"
+    # NaN payloads are canonicalised on the device; compare NaN-ness there, bits elsewhere
+    nan = np.isnan(es)
+    assert np.array_equal(np.isnan(gs), nan), ctx
+    assert np.array_equal(gs.view(np.uint32)[~nan], es.view(np.uint32)[~nan]), f"{ctx}: score bits"
+
+
+def synth_index(n, dim, seed=0x5EED0001):
+    idx = DeviceIndex(dim)
+    idx.fill_synthetic(n, seed)
+    return idx, o.fill_synthetic(n, dim, seed)
+
+
+@pytest.mark.parametrize("metric", METRICS)
+@pytest.mark.parametrize("n,dim,k", [
+    (1, 1, 1), (3, 3, 3), (255, 8, 5), (256, 32, 5), (257, 33, 10), (300, 100, 7), (1000, 7, 4),
+    (1000, 128, 5), (5000, 768, 10), (4096, 1536, 100), (70000, 64, 100), (50000, 96, 1000),
+    (40000, 31, 1024), (2000, 4096, 10), (600, 5000, 3),
+])
+def test_parity_synthetic(metric, n, dim, k):
+    idx, rows = synth_index(n, dim)
+    for qi in range(2):
+        q = o.fill_synthetic(1, dim, 0x5EED1001 + qi)[0]
+        (got,) = idx.search(q, k, metric)
+        assert_same(got, o.search(rows, q, k, metric, threads=8), f"{metric} n={n} d={dim} k={k}")
+    idx.close()
+
+
+def test_parity_committed_golden_vectors():
+    """CUDA path vs tests/golden/oracle_vectors.npz (frozen oracle outputs)."""
+    from pathlib import Path
+    g = np.load(Path(__file__).parent / "golden" / "oracle_vectors.npz")
+    for name in METRICS:
+        n, dim, k = (int(x) for x in g[f"{name}_shape"])
+        idx = DeviceIndex(dim)
+        idx.fill_synthetic(n, int(g["seed_rows"]))
+        q = o.fill_synthetic(1, dim, int(g["seed_query"]))[0]
+        ((r, s),) = idx.search(q, k, name)
+        assert np.array_equal(r, g[f"{name}_rows"])
+        assert np.array_equal(s.view(np.uint32), g[f"{name}_score_bits"])
+        idx.close()
+
+
+def create_test_vector(dim, seed):
+    i = np.arange(dim)
+    x = (seed * 31 + i * 17).astype(np.float32)
+    return (np.sin((x * np.float32(0.0001)).astype(np.float32)).astype(np.float32)
+            * ((seed + i).astype(np.float32) * np.float32(0.001)).astype(np.float32)).astype(np.float32)
+
+
+def test_config1_store_10000_vectors_search():
+    # BASELINE config 1 / vector_engine/src/lib.rs:4256-4276: 10k x 128 cosine TOP 5
+    rows = np.stack([create_test_vector(128, i) for i in range(10000)])
+    idx = DeviceIndex(128)
+    idx.load(rows)
+    q = create_test_vector(128, 5000)
+    (got,) = idx.search(q, 5, "cosine")
+    assert got[0][0] == 5000 and abs(got[1][0] - 1.0) < 1e-5
+    assert_same(got, o.search(rows, q, 5, "cosine"))
+    idx.close()
+
+
+def test_reference_integer_pattern_corpus():
+    # vector_engine/src/lib.rs:6534-6545 (large_scale_million_vectors), scaled to 200k rows
+    n, d = 200_000, 128
+    flat = (np.arange(n * d, dtype=np.int64) % 1000).astype(np.float32) / np.float32(1000.0)
+    rows = flat.reshape(n, d)
+    q = (np.arange(d, dtype=np.float32) / np.float32(d)).astype(np.float32)
+    idx = DeviceIndex(d)
+    idx.load(rows)
+    for m in METRICS:
+        (got,) = idx.search(q, 10, m)
+        assert_same(got, o.search(rows, q, 10, m, threads=8), m)  # many exact ties (period 1000)
+    idx.close()
+
+
+@pytest.mark.parametrize("metric", METRICS)
+def test_exact_ties_break_by_row(metric):
+    base = o.fill_synthetic(3000, 64, 5)
+    rows = np.concatenate([base, base[:1500], base])  # every row duplicated 2-3 times
+    idx = DeviceIndex(64)
+    idx.load(rows)
+    q = base[17]
+    (got,) = idx.search(q, 50, metric)
+    assert_same(got, o.search(rows, q, 50, metric), metric)
+    assert list(got[0][:3]) == [17, 3017, 4517]
+    idx.close()
+
+
+def test_special_values_rank_like_the_oracle():
+    d = 16
+    rows = o.fill_synthetic(600, d, 9)
+    rows[5] = 0.0                      # zero-norm row: cosine 0.0 exactly
+    rows[6] = -0.0
+    rows[7, 3] = np.nan                # NaN score ranks last
+    rows[8, 0] = np.inf
+    rows[9] = 1e30                     # overflow to inf inside sum of squares
+    rows[10] = 1e-30                   # underflow to denormal/zero
+    rows[11] = np.float32(1.1754944e-38) / 2  # denormals are kept (no FTZ)
+    rows[12] = -rows[13]
+    idx = DeviceIndex(d)
+    idx.load(rows)
+    for m in METRICS:
+        for q in (o.fill_synthetic(1, d, 77)[0], np.full(d, 1e-30, np.float32), rows[11].copy()):
+            (got,) = idx.search(q, 600, m)
+            assert_same(got, o.search(rows, q, 600, m), m)
+    # zero query: cosine scores every row 0.0 (guard in cosine_similarity), order = row order
+    (got,) = idx.search(np.zeros(d, np.float32), 5, "cosine")
+    assert list(got[0]) == [0, 1, 2, 3, 4] and not got[1].any()
+    idx.close()
+
+
+def test_negative_zero_score_is_preserved():
+    rows = np.array([[1e-30, 0.0], [-1e-30, 0.0], [0.0, 1.0]], np.float32)
+    q = np.array([1e-30, 0.0], np.float32)   # products underflow to +0.0 / -0.0
+    idx = DeviceIndex(2)
+    idx.load(rows)
+    (got,) = idx.search(q, 3, "dot")
+    exp = o.search(rows, q, 3, "dot")
+    assert_same(got, exp)
+    assert np.array_equal(got[1].view(np.uint32), exp[1].view(np.uint32))
+    idx.close()
+
+
+@pytest.mark.parametrize("metric", METRICS)
+def test_adversarial_ascending_scores_exercise_pruning(metric):
+    """Scores increase with the row index, so every row beats the running threshold and the
+    candidate buffer is pruned over and over."""
+    n, d = 60000, 8
+    t = np.linspace(0.01, 1.5, n, dtype=np.float32)
+    rows = np.zeros((n, d), np.float32)
+    if metric == "euclidean":
+        rows[:, 0] = t[::-1]          # distance to q=0 shrinks with row
+        q = np.zeros(d, np.float32)
+    elif metric == "dot":
+        rows[:, 0] = t
+        q = np.eye(1, d, 0, dtype=np.float32)[0]
+    else:
+        rows[:, 0] = np.cos(t[::-1]); rows[:, 1] = np.sin(t[::-1])
+        q = np.eye(1, d, 0, dtype=np.float32)[0]
+    idx = DeviceIndex(d)
+    idx.load(rows)
+    for k in (1, 10, 1000):
+        (got,) = idx.search(q, k, metric)
+        assert_same(got, o.search(rows, q, k, metric, threads=8), f"{metric} k={k}")
+    idx.close()
+
+
+def test_k_edge_cases_and_errors():
+    idx, rows = synth_index(100, 24)
+    q = o.fill_synthetic(1, 24, 1)[0]
+    (got,) = idx.search(q, 1024, "cosine")          # k > n returns all rows, sorted
+    assert len(got[0]) == 100
+    assert_same(got, o.search(rows, q, 1024, "cosine"))
+    with pytest.raises(NmError) as ei:
+        idx.search(q, 0, "cosine")
+    assert ei.value.code == _ffi.NM_ERR_INVALID_TOP_K
+    with pytest.raises(NmError) as ei:
+        idx.search(np.zeros(25, np.float32), 3, "cosine")
+    assert ei.value.code == _ffi.NM_ERR_DIMENSION_MISMATCH
+    idx.clear()
+    assert idx.rows == 0
+    (got,) = idx.search(q, 5, "cosine")
+    assert len(got[0]) == 0
+    idx.close()
+
+
+def test_multi_query_batch_equals_single_queries():
+    idx, rows = synth_index(20000, 96)
+    qs = o.fill_synthetic(7, 96, 0xABC)
+    for m in METRICS:
+        res = idx.search(qs, 10, m)
+        assert len(res) == 7
+        for i in range(7):
+            assert_same(res[i], o.search(rows, qs[i], 10, m, threads=4), f"{m} q{i}")
+    idx.close()
+
+
+def test_mirror_mutations_load_append_update_swap_remove():
+    d = 40
+    host = o.fill_synthetic(5000, d, 21)
+    idx = DeviceIndex(d)
+    idx.load(host[:3000])
+    idx.append(host[3000:4000])
+    idx.append(host[4000:])
+    assert idx.rows == 5000
+    q = o.fill_synthetic(1, d, 22)[0]
+    (got,) = idx.search(q, 20, "cosine")
+    assert_same(got, o.search(host, q, 20, "cosine"))
+    # overwrite one row with the query itself -> becomes the top hit
+    host = host.copy()
+    host[1234] = q
+    idx.update(1234, q)
+    (got,) = idx.search(q, 20, "cosine")
+    assert got[0][0] == 1234
+    assert_same(got, o.search(host, q, 20, "cosine"))
+    assert np.array_equal(idx.get_row(1234), q)
+    # delete = move the last row into the hole; the caller mirrors the swap
+    moved = idx.swap_remove(1234)
+    assert moved == 4999
+    host[1234] = host[4999]
+    host = host[:4999]
+    assert idx.rows == 4999
+    for m in METRICS:
+        (got,) = idx.search(q, 20, m)
+        assert_same(got, o.search(host, q, 20, m), m)
+    assert idx.swap_remove(4998) == 4998  # removing the last row itself
+    (got,) = idx.search(q, 5, "dot")
+    assert_same(got, o.search(host[:4998], q, 5, "dot"))
+    idx.close()
+
+
+def test_load_from_pageable_memory_with_ragged_dim():
+    # dim % 4 != 0 -> padded device pitch; dim % 8 != 0 -> scalar tail in the lane tree
+    for d in (5, 13, 97, 770):
+        host = o.fill_synthetic(3000, d, d)
+        idx = DeviceIndex(d)
+        idx.load(host)
+        assert np.array_equal(idx.get_row(2999), host[2999])
+        q = o.fill_synthetic(1, d, 1000 + d)[0]
+        for m in METRICS:
+            (got,) = idx.search(q, 9, m)
+            assert_same(got, o.search(host, q, 9, m), f"d={d} {m}")
+        idx.close()
+
+
+def test_search_device_resident_buffers():
+    import torch
+    idx, rows = synth_index(30000, 128)
+    q = o.fill_synthetic(3, 128, 5)
+    dq = torch.from_numpy(q).cuda()
+    k = 10
+    d_rows = torch.zeros((3, k), dtype=torch.int64, device="cuda")
+    d_scores = torch.zeros((3, k), dtype=torch.float32, device="cuda")
+    d_counts = torch.zeros(3, dtype=torch.int32, device="cuda")
+    torch.cuda.synchronize()
+    idx.search_device(dq.data_ptr(), 3, k, "cosine", d_rows.data_ptr(), d_scores.data_ptr(),
+                      d_counts.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    for i in range(3):
+        er, es = o.search(rows, q[i], k, "cosine", threads=4)
+        assert int(d_counts[i]) == k
+        assert np.array_equal(d_rows[i].cpu().numpy().astype(np.uint64), er)
+        assert np.array_equal(d_scores[i].cpu().numpy().view(np.uint32), es.view(np.uint32))
+    idx.close()
+
+
+def test_stats_counters():
+    idx, _ = synth_index(1000, 64)
+    q = o.fill_synthetic(2, 64, 5)
+    idx.search(q, 3, "dot")
+    s = idx.stats()
+    assert s.searches == 2 and s.scan_launches == 2
+    assert s.rows_scanned == 2000 and s.bytes_streamed == 2 * 1000 * 64 * 4
+    assert s.last_scan_ms > 0
+    idx.close()
+
+
+# ---- BASELINE configs at (or near) full size -------------------------------------------------
+def test_config2_1m_x_768_cosine_top10_vs_oracle():
+    n, d = 1_000_000, 768
+    idx, rows = synth_index(n, d)
+    q = o.fill_synthetic(1, d, 0x5EED1001)[0]
+    (got,) = idx.search(q, 10, "cosine")
+    assert_same(got, o.search(rows, q, 10, "cosine", threads=16))
+    idx.close()
+
+
+def _full_size_properties(n, d, k, metric):
+    """Size-independent checks where the oracle cannot score the whole corpus in seconds:
+    (1) every returned score is bit-equal to the oracle's score of that very row (row fetched
+    back from the device), (2) results are sorted by the total order, (3) no row of a large
+    random sample beats the k-th hit, (4) a planted copy of the query becomes the top hit with
+    the oracle's self-score, (5) the search is idempotent."""
+    idx = DeviceIndex(d)
+    idx.fill_synthetic(n, 0x5EED0001)
+    q = o.fill_synthetic(1, d, 0x5EED1001)[0]
+    ((r, s),) = idx.search(q, k, metric)
+    assert len(r) == k
+    for i in range(0, k, max(1, k // 16)):
+        row = idx.get_row(int(r[i]))
+        assert np.array_equal(row, o.fill_synthetic(1, d, 0x5EED0001, row_offset=int(r[i]))[0])
+        assert o.compute_score(q, row, metric).view(np.uint32) == s[i].view(np.uint32)
+    import np_ref
+    ordk = np_ref.orderable(s).astype(np.int64)
+    assert all((ordk[i] > ordk[i + 1]) or (ordk[i] == ordk[i + 1] and r[i] < r[i + 1])
+               for i in range(k - 1))
+    rng = np.random.default_rng(0)
+    for start in rng.integers(0, n - 50_000, 4):
+        block = o.fill_synthetic(50_000, d, 0x5EED0001, row_offset=int(start))
+        sc = o.score_rows(block, q, metric)
+        better = np_ref.orderable(sc).astype(np.int64) > ordk[-1]
+        rows_better = set((np.nonzero(better)[0] + int(start)).tolist())
+        assert rows_better <= set(int(x) for x in r), "a sampled row beats the k-th hit"
+    plant = n - 12345
+    idx.update(plant, q)
+    ((r2, s2),) = idx.search(q, k, metric)
+    assert r2[0] == plant
+    assert s2[0].view(np.uint32) == o.compute_score(q, q, metric).view(np.uint32)
+    ((r3, s3),) = idx.search(q, k, metric)
+    assert np.array_equal(r2, r3) and np.array_equal(s2.view(np.uint32), s3.view(np.uint32))
+    idx.close()
+
+
+def test_config3_10m_x_768_cosine_top10_properties():
+    _full_size_properties(10_000_000, 768, 10, "cosine")
+
+
+def test_config4_shape_10m_x_1536_l2_top100_properties():
+    _full_size_properties(10_000_000, 1536, 100, "euclidean")
