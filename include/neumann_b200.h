@@ -58,7 +58,8 @@ typedef enum nm_status {
 
 typedef struct nm_index nm_index;
 
-/* Largest k served by the in-kernel selection; larger k takes the full-sort device path. */
+/* Largest k served by ONE scan pass; larger k is served exactly by ceil(k/1024) chained passes
+ * (each a full scan admitting only hits below the previous pass's last one). */
 #define NM_TOPK_FAST_MAX 1024u
 
 /* ---- library ------------------------------------------------------------------------ */
@@ -156,6 +157,9 @@ int nm_index_stats(nm_index *idx, nm_stats *out);
  * all-gather / merge) with CUDA events on the caller's stream; nm_index_stats waits for them
  * and accumulates profiled_scan_ms / profiled_scans.  Used by bench.py for the roofline. */
 int nm_index_set_profiling(nm_index *idx, int enable);
+/* Batches of >= 8 queries share one corpus pass (batch_kernels.cuh) by default; 0 forces one
+ * scan per query.  Results are bit-identical either way (tested); this is a tuning knob. */
+int nm_index_set_batching(nm_index *idx, int enable);
 
 #ifdef __cplusplus
 }

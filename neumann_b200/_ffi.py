@@ -64,6 +64,7 @@ SIGNATURES = {
     "nm_index_detach_comm": (C.c_int, [_vp]),
     "nm_index_stats": (C.c_int, [_vp, C.POINTER(NmStats)]),
     "nm_index_set_profiling": (C.c_int, [_vp, C.c_int]),
+    "nm_index_set_batching": (C.c_int, [_vp, C.c_int]),
 }
 
 _lib = None

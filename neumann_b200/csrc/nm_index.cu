@@ -7,6 +7,7 @@
 // processes.  There is deliberately no CPU code path for the scan.
 #include "../../include/neumann_b200.h"
 #include "scan_kernels.cuh"
+#include "batch_kernels.cuh"
 
 #include <dlfcn.h>
 #include <nccl.h>
@@ -115,6 +116,8 @@ struct Workspace {
     uint64_t *d_cand = nullptr;
     size_t cand_cap = 0;  // keys
     uint32_t *d_counter = nullptr;
+    uint64_t *d_pass_keys = nullptr;  // [k] merged keys of the chained passes (k > 1024)
+    size_t pass_keys_cap = 0;
     // packed result block: [counts u32 x nq (8-aligned)] [rows u64 x nq*k] [scores f32 x nq*k]
     uint8_t *d_result = nullptr;
     uint8_t *h_result = nullptr;  // pinned
@@ -124,6 +127,15 @@ struct Workspace {
     size_t hits_cap = 0;
     nm::ShardHit *d_gather = nullptr;  // [n_ranks, nq, k]
     size_t gather_cap = 0;
+    // batched-query path (batch_kernels.cuh)
+    float *d_qt = nullptr;         // [n_kc][32][QB] transposed query chunks
+    size_t qt_cap = 0;             // floats
+    float *d_qmag = nullptr;       // [64]
+    float *d_scores = nullptr;     // [QB][score_stride]
+    size_t scores_cap = 0;         // floats
+    uint64_t *d_bcand = nullptr;   // [QB][ctas_per_query][k]
+    size_t bcand_cap = 0;          // keys
+    uint32_t *d_bctl = nullptr;    // [0] cursor [1] done [2..2+64) tickets
     // profiling ring (nm_index_set_profiling): event pairs around the scan launches of
     // asynchronous nm_search_device calls, resolved lazily by nm_index_stats
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
@@ -136,6 +148,12 @@ struct Workspace {
         if (h_query) cudaFreeHost(h_query);
         if (d_cand) cudaFree(d_cand);
         if (d_counter) cudaFree(d_counter);
+        if (d_pass_keys) cudaFree(d_pass_keys);
+        if (d_qt) cudaFree(d_qt);
+        if (d_qmag) cudaFree(d_qmag);
+        if (d_scores) cudaFree(d_scores);
+        if (d_bcand) cudaFree(d_bcand);
+        if (d_bctl) cudaFree(d_bctl);
         if (d_result) cudaFree(d_result);
         if (h_result) cudaFreeHost(h_result);
         if (d_hits) cudaFree(d_hits);
@@ -186,6 +204,7 @@ struct nm_index {
         merge_launches{0}, h2d_bytes{0}, d2h_bytes{0};
     std::atomic<double> last_scan_ms{0.0};
     std::atomic<int> profiling{0};
+    std::atomic<int> batching{1};  // nm_index_set_batching: 0 forces one scan per query
     double profiled_scan_ms = 0.0;  // guarded by mu (exclusive) in nm_index_stats
     uint64_t profiled_scans = 0;
     uint64_t total_rows() const {
@@ -330,7 +349,7 @@ int ws_ensure(Workspace &ws, const Shard &sh, uint32_t dim, uint32_t nq, uint32_
         CUDA_TRY(cudaMallocHost(&ws.h_query, qf * 4));
         ws.query_cap = qf;
     }
-    size_t cand = (size_t)sh.sm_count * k;
+    size_t cand = (size_t)sh.sm_count * std::min<uint32_t>(k, nm::kMaxFastK);
     if (ws.cand_cap < cand) {
         if (ws.d_cand) CUDA_TRY(cudaFree(ws.d_cand));
         ws.cand_cap = 0;
@@ -391,7 +410,8 @@ int launch_scan_t(const Shard &sh, const nm::ScanParams &p, size_t smem, cudaStr
     return NM_OK;
 }
 
-// One scan launch for one query over one shard.
+// One query over one shard: a single launch for k <= 1024, otherwise ceil(k/1024) chained
+// passes, each admitting only keys below the previous pass's last key.
 int launch_scan(nm_index *idx, const Shard &sh, Workspace &ws, const float *d_query, uint32_t k,
                 int metric, uint64_t row_base, uint64_t *out_rows, float *out_scores,
                 uint32_t *out_count, nm::ShardHit *out_hits, cudaStream_t stream) {
@@ -400,15 +420,9 @@ int launch_scan(nm_index *idx, const Shard &sh, Workspace &ws, const float *d_qu
     p.query = d_query;
     p.cand = ws.d_cand;
     p.done_counter = ws.d_counter;
-    p.out_keys = nullptr;
-    p.out_hits = out_hits;
-    p.out_rows = out_rows;
-    p.out_scores = out_scores;
-    p.out_count = out_count;
     p.row_base = row_base;
     p.n_rows = (uint32_t)sh.rows;
     p.dim = idx->dim;
-    p.k = k;
     p.q_floats = (idx->dim + 31u) & ~31u;
     // stream through L2 with evict_first unless the whole shard fits comfortably in L2
     p.evict_first = (sh.rows * idx->pitch * 4ull > (64ull << 20)) ? 1u : 0u;
@@ -421,15 +435,213 @@ int launch_scan(nm_index *idx, const Shard &sh, Workspace &ws, const float *d_qu
                     idx->dim);
     p.n_stages = stages;
     size_t smem = scan_smem_bytes(stages, p.q_floats);
-    idx->scan_launches++;
-    switch (metric) {
-    case NM_COSINE:
-        return launch_scan_t<nm::kCosine>(sh, p, smem, stream);
-    case NM_EUCLIDEAN:
-        return launch_scan_t<nm::kEuclidean>(sh, p, smem, stream);
-    default:
-        return launch_scan_t<nm::kDot>(sh, p, smem, stream);
+    const bool chained = k > (uint32_t)nm::kMaxFastK;
+    if (chained) {
+        if (ws.pass_keys_cap < k) {
+            if (ws.d_pass_keys) {
+                CUDA_TRY(cudaStreamSynchronize(stream));
+                CUDA_TRY(cudaFree(ws.d_pass_keys));
+            }
+            ws.pass_keys_cap = 0;
+            CUDA_TRY(cudaMalloc(&ws.d_pass_keys, (size_t)k * 8));
+            ws.pass_keys_cap = k;
+        }
+        if (out_count) CUDA_TRY(cudaMemsetAsync(out_count, 0, 4, stream));
     }
+    // never ask for more hits than the shard has rows (slots past that stay empty)
+    const uint32_t k_need = (uint32_t)std::min<uint64_t>(k, sh.rows);
+    if (out_hits && k_need < k)
+        CUDA_TRY(cudaMemsetAsync(out_hits + k_need, 0, (size_t)(k - k_need) * sizeof(nm::ShardHit),
+                                 stream));
+    for (uint32_t done = 0; done < k_need; done += nm::kMaxFastK) {
+        const uint32_t kp = std::min<uint32_t>(nm::kMaxFastK, k_need - done);
+        p.k = kp;
+        p.out_keys = chained ? ws.d_pass_keys + done : nullptr;
+        p.out_hits = out_hits ? out_hits + done : nullptr;
+        p.out_rows = out_rows ? out_rows + done : nullptr;
+        p.out_scores = out_scores ? out_scores + done : nullptr;
+        p.out_count = out_count;
+        p.accumulate_count = chained ? 1u : 0u;
+        // the previous pass always has kMaxFastK slots; its last one is 0 when it ran dry
+        p.key_ceiling = done ? ws.d_pass_keys + done - 1 : nullptr;
+        idx->scan_launches++;
+        int rc;
+        switch (metric) {
+        case NM_COSINE: rc = launch_scan_t<nm::kCosine>(sh, p, smem, stream); break;
+        case NM_EUCLIDEAN: rc = launch_scan_t<nm::kEuclidean>(sh, p, smem, stream); break;
+        default: rc = launch_scan_t<nm::kDot>(sh, p, smem, stream); break;
+        }
+        if (rc) return rc;
+    }
+    return NM_OK;
+}
+
+
+// ---- batched-query path ----------------------------------------------------------------
+constexpr uint32_t kBatchMinQueries = 8;   // below this, nq single-query passes are cheaper
+constexpr int kBatchMaxQB = 64;
+
+template <int METRIC, int QB>
+int launch_score_batch_t(const Shard &sh, const nm::BatchScoreParams &p, cudaStream_t stream) {
+    static std::mutex mu;
+    static bool configured[64] = {false};
+    auto kern = nm::score_batch_kernel<METRIC, QB>;
+    {
+        std::lock_guard<std::mutex> g(mu);
+        if (sh.device >= 64 || !configured[sh.device]) {
+            CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          227 * 1024));
+            if (sh.device < 64) configured[sh.device] = true;
+        }
+    }
+    size_t smem = 1024 + (size_t)p.n_stages * nm::batch_stage_bytes<QB>() + 2 * nm::kMaxStages * 8 +
+                  nm::kMaxStages * 4 + QB * 4 + 64;
+    uint32_t n_rb = (p.n_rows + nm::kRowsPerBlock - 1) / nm::kRowsPerBlock;
+    uint32_t grid = std::min<uint32_t>((uint32_t)sh.sm_count, n_rb);
+    kern<<<grid, nm::kScanThreads, smem, stream>>>(sh.tmap, p);
+    CUDA_TRY(cudaGetLastError());
+    return NM_OK;
+}
+
+template <int QB>
+uint32_t batch_stages() {
+    uint32_t st = nm::kMaxStages;
+    while (st > 2 && 1024 + (size_t)st * nm::batch_stage_bytes<QB>() + 512 + QB * 4 > 227 * 1024) --st;
+    return st;
+}
+
+bool batch_eligible(const nm_index *idx, const Shard &sh, uint32_t nq, uint32_t k, int metric) {
+    if (nq < kBatchMinQueries || sh.rows == 0) return false;
+    if (std::min<uint64_t>(k, sh.rows) > (uint64_t)nm::kMaxFastK) return false;
+    // dot/cosine lanes need whole f32x8 groups; the scalar tail only exists on the 1-query path
+    if (metric != NM_EUCLIDEAN && (idx->dim % 8u) != 0) return false;
+    return true;
+}
+
+// All nq queries over one shard through the batched kernels.  Returns NM_OK, an error, or
+// -1 when the score matrix cannot be allocated (caller falls back to single-query passes).
+int scan_queries_batched(nm_index *idx, const Shard &sh, Workspace &ws, const float *d_queries,
+                         uint32_t nq, uint32_t k, int metric, uint64_t row_base,
+                         uint64_t *out_rows, float *out_scores, uint32_t *out_counts,
+                         nm::ShardHit *out_hits, cudaStream_t stream) {
+    const uint32_t dim = idx->dim;
+    const uint32_t n_kc = (dim + 31u) / 32u;
+    const uint32_t k_eff = (uint32_t)std::min<uint64_t>(k, sh.rows);
+    const uint32_t n_rb = ((uint32_t)sh.rows + nm::kRowsPerBlock - 1) / nm::kRowsPerBlock;
+    const uint64_t stride = ((uint64_t)sh.rows + 63u) & ~uint64_t(63);
+    const uint32_t qb_max = (metric == NM_EUCLIDEAN) ? (nq > 16 ? 64u : 16u) : 16u;
+    // scratch
+    if (!ws.d_bctl) {
+        CUDA_TRY(cudaMalloc(&ws.d_bctl, (2 + kBatchMaxQB) * sizeof(uint32_t)));
+        CUDA_TRY(cudaMemsetAsync(ws.d_bctl, 0, (2 + kBatchMaxQB) * sizeof(uint32_t), stream));
+        CUDA_TRY(cudaMalloc(&ws.d_qmag, kBatchMaxQB * sizeof(float)));
+    }
+    size_t need_qt = (size_t)n_kc * 32u * qb_max;
+    size_t need_scores = (size_t)qb_max * stride;
+    uint32_t ctas_per_q = std::max<uint32_t>(1u, std::min<uint32_t>(n_rb, (2u * sh.sm_count + qb_max - 1) / qb_max));
+    size_t need_cand = (size_t)qb_max * ctas_per_q * k_eff;
+    if (ws.qt_cap < need_qt || ws.scores_cap < need_scores || ws.bcand_cap < need_cand)
+        CUDA_TRY(cudaStreamSynchronize(stream));  // earlier launches may still read the old buffers
+    if (ws.qt_cap < need_qt) {
+        if (ws.d_qt) CUDA_TRY(cudaFree(ws.d_qt));
+        ws.qt_cap = 0;
+        CUDA_TRY(cudaMalloc(&ws.d_qt, need_qt * 4));
+        ws.qt_cap = need_qt;
+    }
+    if (ws.scores_cap < need_scores) {
+        if (ws.d_scores) CUDA_TRY(cudaFree(ws.d_scores));
+        ws.scores_cap = 0;
+        if (cudaMalloc(&ws.d_scores, need_scores * 4) != cudaSuccess) {
+            cudaGetLastError();
+            ws.d_scores = nullptr;
+            return -1;
+        }
+        ws.scores_cap = need_scores;
+    }
+    if (ws.bcand_cap < need_cand) {
+        if (ws.d_bcand) CUDA_TRY(cudaFree(ws.d_bcand));
+        ws.bcand_cap = 0;
+        CUDA_TRY(cudaMalloc(&ws.d_bcand, need_cand * 8));
+        ws.bcand_cap = need_cand;
+    }
+    if (out_hits && k_eff < k)
+        CUDA_TRY(cudaMemsetAsync(out_hits, 0, (size_t)nq * k * sizeof(nm::ShardHit), stream));
+
+    for (uint32_t q0 = 0; q0 < nq; q0 += qb_max) {
+        const uint32_t nqp = std::min<uint32_t>(qb_max, nq - q0);
+        const uint32_t qb = (qb_max == 64u && nqp <= 16u) ? 16u : qb_max;
+        nm::prepare_batch_kernel<<<std::max<uint32_t>(8u, (n_kc * 32u * qb + 255u) / 256u), 256, 0, stream>>>(
+            d_queries + (size_t)q0 * dim, nqp, dim, qb, n_kc, ws.d_qt, ws.d_qmag);
+        CUDA_TRY(cudaGetLastError());
+        nm::BatchScoreParams sp;
+        memset(&sp, 0, sizeof(sp));
+        sp.qt = ws.d_qt;
+        sp.qmag = ws.d_qmag;
+        sp.scores = ws.d_scores;
+        sp.cursor = ws.d_bctl;
+        sp.done = ws.d_bctl + 1;
+        sp.score_stride = stride;
+        sp.n_rows = (uint32_t)sh.rows;
+        sp.dim = dim;
+        sp.evict_first = (sh.rows * idx->pitch * 4ull > (64ull << 20)) ? 1u : 0u;
+        int rc;
+        if (metric == NM_EUCLIDEAN) {
+            if (qb == 64u) {
+                sp.n_stages = batch_stages<64>();
+                rc = launch_score_batch_t<nm::kEuclidean, 64>(sh, sp, stream);
+            } else {
+                sp.n_stages = batch_stages<16>();
+                rc = launch_score_batch_t<nm::kEuclidean, 16>(sh, sp, stream);
+            }
+        } else if (metric == NM_COSINE) {
+            sp.n_stages = batch_stages<16>();
+            rc = launch_score_batch_t<nm::kCosine, 16>(sh, sp, stream);
+        } else {
+            sp.n_stages = batch_stages<16>();
+            rc = launch_score_batch_t<nm::kDot, 16>(sh, sp, stream);
+        }
+        if (rc) return rc;
+        nm::BatchSelectParams bp;
+        memset(&bp, 0, sizeof(bp));
+        bp.scores = ws.d_scores;
+        bp.score_stride = stride;
+        bp.cand = ws.d_bcand;
+        bp.tickets = ws.d_bctl + 2;
+        bp.out_hits = out_hits ? out_hits + (size_t)q0 * k : nullptr;
+        bp.out_rows = out_rows ? out_rows + (size_t)q0 * k : nullptr;
+        bp.out_scores = out_scores ? out_scores + (size_t)q0 * k : nullptr;
+        bp.out_counts = out_counts ? out_counts + q0 : nullptr;
+        bp.row_base = row_base;
+        bp.out_stride = k;
+        bp.n_rows = (uint32_t)sh.rows;
+        bp.k = k_eff;
+        dim3 grid(ctas_per_q, nqp);
+        nm::select_batch_kernel<<<grid, nm::kRowsPerBlock, 0, stream>>>(bp);
+        CUDA_TRY(cudaGetLastError());
+        idx->scan_launches += 3;
+    }
+    return NM_OK;
+}
+
+// nq queries over one shard: batched kernels when that pays, else one (chained) scan per query.
+int scan_queries(nm_index *idx, const Shard &sh, Workspace &ws, const float *d_queries,
+                 uint32_t nq, uint32_t k, int metric, uint64_t row_base, uint64_t *out_rows,
+                 float *out_scores, uint32_t *out_counts, nm::ShardHit *out_hits,
+                 cudaStream_t stream) {
+    if (idx->batching.load() && batch_eligible(idx, sh, nq, k, metric)) {
+        int rc = scan_queries_batched(idx, sh, ws, d_queries, nq, k, metric, row_base, out_rows,
+                                      out_scores, out_counts, out_hits, stream);
+        if (rc != -1) return rc;
+    }
+    for (uint32_t q = 0; q < nq; ++q) {
+        int rc = launch_scan(idx, sh, ws, d_queries + (size_t)q * idx->dim, k, metric, row_base,
+                             out_rows ? out_rows + (size_t)q * k : nullptr,
+                             out_scores ? out_scores + (size_t)q * k : nullptr,
+                             out_counts ? out_counts + q : nullptr,
+                             out_hits ? out_hits + (size_t)q * k : nullptr, stream);
+        if (rc) return rc;
+    }
+    return NM_OK;
 }
 
 uint32_t pow2_ceil(uint32_t v) {
@@ -453,9 +665,6 @@ int validate_search(const nm_index *idx, const void *queries, uint32_t nq, uint3
     if (!queries || !out_rows || !out_scores || !out_counts)
         return fail(NM_ERR_INVALID_ARGUMENT, "null buffer");
     if (metric < 0 || metric > 2) return fail(NM_ERR_INVALID_ARGUMENT, "unknown metric %d", metric);
-    if (k > NM_TOPK_FAST_MAX)
-        return fail(NM_ERR_INVALID_TOP_K, "top_k %u exceeds the supported maximum %u", k,
-                    NM_TOPK_FAST_MAX);
     return NM_OK;
 }
 
@@ -723,14 +932,12 @@ int nm_search(nm_index *idx, const float *queries, uint32_t nq, uint32_t k, int 
         CUDA_TRY(cudaMemcpyAsync(ws->d_query, ws->h_query, (size_t)nq * dim * 4,
                                  cudaMemcpyHostToDevice, ws->stream));
         CUDA_TRY(cudaEventRecord(ws->ev0, ws->stream));
-        for (uint32_t q = 0; q < nq; ++q) {
-            rc = launch_scan(idx, sh, *ws, ws->d_query + (size_t)q * dim, k, metric, sh.row_base,
-                             reinterpret_cast<uint64_t *>(ws->d_result + l.rows_off) + (size_t)q * k,
-                             reinterpret_cast<float *>(ws->d_result + l.scores_off) + (size_t)q * k,
-                             reinterpret_cast<uint32_t *>(ws->d_result + l.counts_off) + q, nullptr,
-                             ws->stream);
-            if (rc) return rc;
-        }
+        rc = scan_queries(idx, sh, *ws, ws->d_query, nq, k, metric, sh.row_base,
+                          reinterpret_cast<uint64_t *>(ws->d_result + l.rows_off),
+                          reinterpret_cast<float *>(ws->d_result + l.scores_off),
+                          reinterpret_cast<uint32_t *>(ws->d_result + l.counts_off), nullptr,
+                          ws->stream);
+        if (rc) return rc;
         CUDA_TRY(cudaEventRecord(ws->ev1, ws->stream));
         CUDA_TRY(cudaMemcpyAsync(ws->h_result, ws->d_result, l.total, cudaMemcpyDeviceToHost,
                                  ws->stream));
@@ -777,12 +984,9 @@ int nm_search(nm_index *idx, const float *queries, uint32_t nq, uint32_t k, int 
             CUDA_TRY(cudaMemsetAsync(ws->d_hits, 0, (size_t)nq * k * sizeof(nm::ShardHit),
                                      ws->stream));
         } else {
-            for (uint32_t q = 0; q < nq; ++q) {
-                rc = launch_scan(idx, sh, *ws, ws->d_query + (size_t)q * dim, k, metric,
-                                 idx->comm_row_base, nullptr, nullptr, nullptr,
-                                 ws->d_hits + (size_t)q * k, ws->stream);
-                if (rc) return rc;
-            }
+            rc = scan_queries(idx, sh, *ws, ws->d_query, nq, k, metric, idx->comm_row_base,
+                              nullptr, nullptr, nullptr, ws->d_hits, ws->stream);
+            if (rc) return rc;
         }
         CUDA_TRY(cudaEventRecord(ws->ev1, ws->stream));
         NCCL_TRY(nccl().AllGather(ws->d_hits, ws->d_gather,
@@ -850,11 +1054,9 @@ int nm_search(nm_index *idx, const float *queries, uint32_t nq, uint32_t k, int 
         if (sh.rows == 0) {
             CUDA_TRY(cudaMemsetAsync(ws.d_hits, 0, (size_t)nq * k * sizeof(nm::ShardHit), ws.stream));
         } else {
-            for (uint32_t q = 0; q < nq; ++q) {
-                rc = launch_scan(idx, sh, ws, ws.d_query + (size_t)q * dim, k, metric, sh.row_base,
-                                 nullptr, nullptr, nullptr, ws.d_hits + (size_t)q * k, ws.stream);
-                if (rc) return rc;
-            }
+            rc = scan_queries(idx, sh, ws, ws.d_query, nq, k, metric, sh.row_base, nullptr, nullptr,
+                              nullptr, ws.d_hits, ws.stream);
+            if (rc) return rc;
         }
         CUDA_TRY(cudaEventRecord(ws.ev1, ws.stream));
         CUDA_TRY(cudaMemcpyAsync(ws.h_hits, ws.d_hits, (size_t)nq * k * sizeof(nm::ShardHit),
@@ -940,7 +1142,8 @@ int nm_search_device(nm_index *idx, const float *d_queries, uint32_t nq, uint32_
     } rel{sh, pooled};
     // growing a stream-bound workspace frees buffers earlier launches may still read
     {
-        size_t need_cand = (size_t)sh.sm_count * k, need_hits = (size_t)nq * k;
+        size_t need_cand = (size_t)sh.sm_count * std::min<uint32_t>(k, nm::kMaxFastK),
+               need_hits = (size_t)nq * k;
         bool grow = ws->cand_cap < need_cand ||
                     (collective && (ws->hits_cap < need_hits ||
                                     ws->gather_cap < need_hits * (size_t)idx->n_ranks));
@@ -963,24 +1166,18 @@ int nm_search_device(nm_index *idx, const float *d_queries, uint32_t nq, uint32_
         if (sh.rows == 0) {
             CUDA_TRY(cudaMemsetAsync(d_out_counts, 0, (size_t)nq * 4, stream));
         } else {
-            for (uint32_t q = 0; q < nq; ++q) {
-                rc = launch_scan(idx, sh, *ws, d_queries + (size_t)q * dim, k, metric, sh.row_base,
-                                 d_out_rows + (size_t)q * k, d_out_scores + (size_t)q * k,
-                                 d_out_counts + q, nullptr, stream);
-                if (rc) return rc;
-            }
+            rc = scan_queries(idx, sh, *ws, d_queries, nq, k, metric, sh.row_base, d_out_rows,
+                              d_out_scores, d_out_counts, nullptr, stream);
+            if (rc) return rc;
         }
         if (prof) CUDA_TRY(cudaEventRecord(prof->second, stream));
     } else {
         if (sh.rows == 0) {
             CUDA_TRY(cudaMemsetAsync(ws->d_hits, 0, (size_t)nq * k * sizeof(nm::ShardHit), stream));
         } else {
-            for (uint32_t q = 0; q < nq; ++q) {
-                rc = launch_scan(idx, sh, *ws, d_queries + (size_t)q * dim, k, metric,
-                                 idx->comm_row_base, nullptr, nullptr, nullptr,
-                                 ws->d_hits + (size_t)q * k, stream);
-                if (rc) return rc;
-            }
+            rc = scan_queries(idx, sh, *ws, d_queries, nq, k, metric, idx->comm_row_base, nullptr,
+                              nullptr, nullptr, ws->d_hits, stream);
+            if (rc) return rc;
         }
         if (prof) CUDA_TRY(cudaEventRecord(prof->second, stream));
         NCCL_TRY(nccl().AllGather(ws->d_hits, ws->d_gather,
@@ -1004,6 +1201,12 @@ int nm_search_device(nm_index *idx, const float *d_queries, uint32_t nq, uint32_
     idx->searches += nq;
     idx->rows_scanned += (uint64_t)nq * sh.rows;
     idx->bytes_streamed += (uint64_t)nq * sh.rows * dim * 4;
+    return NM_OK;
+}
+
+int nm_index_set_batching(nm_index *idx, int enable) {
+    if (!idx) return fail(NM_ERR_INVALID_ARGUMENT, "null index");
+    idx->batching = enable ? 1 : 0;
     return NM_OK;
 }
 

@@ -163,6 +163,7 @@ struct TopKState {
     uint64_t *thr_smem;  // k-th best key after the last prune (0 = none yet)
     uint32_t count;      // uniform copy of *cnt_smem
     uint32_t k;
+    uint32_t cap;        // entries of buf in use: small k prunes a smaller buffer (cheaper sort)
 };
 
 // Bitonic sort, descending, of buf[0..n) (n = power of two) by the 256 consumer threads.
@@ -206,7 +207,7 @@ __device__ __forceinline__ void topk_prune(TopKState &st, uint32_t t) {
 __device__ __forceinline__ void topk_offer(TopKState &st, uint64_t key, uint32_t t) {
     bool cand = key > *st.thr_smem;
     uint32_t total = consumer_sync_popc(cand);
-    if (st.count + total > (uint32_t)kCandCap) {
+    if (st.count + total > st.cap) {
         topk_prune(st, t);
         cand = key > *st.thr_smem;
         total = consumer_sync_popc(cand);
@@ -221,6 +222,165 @@ __device__ __forceinline__ void topk_offer(TopKState &st, uint64_t key, uint32_t
         if (cand) st.buf[base + __popc(ballot & ((1u << lane) - 1u))] = key;
     }
     st.count += total;
+}
+
+
+// ---------------------------------------------------------------------------------------
+// final merge of the per-CTA lists (last CTA only)
+// ---------------------------------------------------------------------------------------
+struct MergeScratch {
+    uint32_t *hist;  // 256 bins
+    uint32_t *sc;    // [0..1] prefix (lo,hi) [2] need [3] exact flag [4] cursor [8..16) warp totals
+};
+
+// Select the k best of `total` published keys (0 = empty slot) into st.buf[0..count), sorted
+// descending.  Small inputs are sorted directly; larger ones go through an MSB-first radix
+// select (8-bit digits, early exit as soon as a digit bin is wholly selected), so the cost is
+// a few passes over the L2-resident lists instead of hundreds of buffer prunes.  Loads are
+// issued kMergeTile at a time per thread so the passes are bandwidth-, not latency-bound.
+constexpr int kMergeTile = 8;
+__device__ __forceinline__ void merge_published(TopKState &st, uint32_t t, const uint64_t *all,
+                                                uint32_t total, uint32_t k,
+                                                const MergeScratch ms) {
+    const uint32_t lane = t & 31u, warp = t >> 5;
+    if (total <= 512u) {
+        for (uint32_t i = t; i < total; i += kRowsPerBlock) st.buf[i] = __ldcg(all + i);
+        st.count = total;
+        consumer_sync();
+        topk_prune(st, t);  // zeros sort to the end
+        const uint32_t kept = st.count;
+        uint32_t valid = 0;
+        for (uint32_t base = 0; base < kept; base += kRowsPerBlock) {
+            const uint32_t i = base + t;
+            valid += consumer_sync_popc(i < kept && st.buf[i] != 0ull);
+        }
+        st.count = valid;
+        return;
+    }
+    if (t < 8) ms.sc[t] = 0u;
+    uint64_t prefix = 0ull;
+    uint32_t need = 0, kk = 0;
+    int shift = 56;
+    for (;; shift -= 8) {
+        ms.hist[t] = 0u;
+        consumer_sync();
+        for (uint32_t base = 0; base < total; base += kRowsPerBlock * kMergeTile) {
+            uint64_t keys[kMergeTile];
+#pragma unroll
+            for (int j = 0; j < kMergeTile; ++j) {
+                const uint32_t i = base + j * kRowsPerBlock + t;
+                keys[j] = (i < total) ? __ldcg(all + i) : 0ull;
+            }
+#pragma unroll
+            for (int j = 0; j < kMergeTile; ++j) {
+                const uint64_t key = keys[j];
+                const bool in = key != 0ull && (shift == 56 || (key >> (shift + 8)) == prefix);
+                const uint32_t bin = in ? (uint32_t)(key >> shift) & 255u : 0xffffffffu;
+                const uint32_t peers = __match_any_sync(0xffffffffu, bin);
+                if (in && lane == (uint32_t)(__ffs(peers) - 1))
+                    atomicAdd(&ms.hist[bin], (uint32_t)__popc(peers));
+            }
+        }
+        consumer_sync();
+        // thread t owns bin t; suffix sums by warp scan: s = bins t..(end of this warp)
+        const uint32_t mine = ms.hist[t];
+        uint32_t sfx = mine;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const uint32_t v = __shfl_down_sync(0xffffffffu, sfx, off);
+            if (lane + off < 32u) sfx += v;
+        }
+        if (lane == 0) ms.sc[8 + warp] = sfx;  // warp totals
+        consumer_sync();
+        uint32_t above = sfx - mine;
+        for (uint32_t w = warp + 1; w < (uint32_t)kConsumerWarps; ++w) above += ms.sc[8 + w];
+        if (shift == 56) {
+            uint32_t valid = 0;
+            for (uint32_t w = 0; w < (uint32_t)kConsumerWarps; ++w) valid += ms.sc[8 + w];
+            kk = min(k, valid);
+            need = kk;
+        }
+        if (kk == 0) {
+            st.count = 0;
+            consumer_sync();
+            return;
+        }
+        if (above < need && need <= above + mine) {
+            const uint64_t np = (prefix << 8) | (uint64_t)t;
+            ms.sc[0] = (uint32_t)np;
+            ms.sc[1] = (uint32_t)(np >> 32);
+            ms.sc[2] = need - above;
+            ms.sc[3] = (mine == need - above) ? 1u : 0u;
+        }
+        consumer_sync();
+        prefix = ((uint64_t)ms.sc[1] << 32) | ms.sc[0];
+        need = ms.sc[2];
+        const bool exact = ms.sc[3] != 0u;
+        if (exact || shift == 0) break;
+    }
+    // everything with (key >> shift) >= prefix is selected: exactly kk keys
+    for (uint32_t base = 0; base < total; base += kRowsPerBlock * kMergeTile) {
+        uint64_t keys[kMergeTile];
+#pragma unroll
+        for (int j = 0; j < kMergeTile; ++j) {
+            const uint32_t i = base + j * kRowsPerBlock + t;
+            keys[j] = (i < total) ? __ldcg(all + i) : 0ull;
+        }
+#pragma unroll
+        for (int j = 0; j < kMergeTile; ++j) {
+            const uint64_t key = keys[j];
+            const bool sel = key != 0ull && (key >> shift) >= prefix;
+            const uint32_t ballot = __ballot_sync(0xffffffffu, sel);
+            if (ballot) {
+                const uint32_t leader = __ffs(ballot) - 1;
+                uint32_t pos = 0;
+                if (lane == leader) pos = atomicAdd(&ms.sc[4], (uint32_t)__popc(ballot));
+                pos = __shfl_sync(0xffffffffu, pos, leader);
+                if (sel) st.buf[pos + __popc(ballot & ((1u << lane) - 1u))] = key;
+            }
+        }
+    }
+    consumer_sync();
+    st.count = kk;
+    if (t == 0) *st.cnt_smem = kk;
+    consumer_sync();
+    topk_prune(st, t);
+}
+
+// Decode the merged keys in st.buf[0..count) into the caller's output buffers.
+struct TopKOutputs {
+    uint64_t *out_keys;   // [k] sorted local keys, 0 padded (may be null)
+    ShardHit *out_hits;   // [k] hits with global rows, {0,0,0} padded (may be null)
+    uint64_t *out_rows;   // [k] (may be null)
+    float *out_scores;    // [k] (may be null)
+    uint32_t *out_count;  // (may be null)
+    uint64_t row_base;
+    uint32_t accumulate_count;
+};
+__device__ __forceinline__ void write_outputs(const TopKState &st, uint32_t t, uint32_t k,
+                                              const TopKOutputs o) {
+    for (uint32_t i = t; i < k; i += kRowsPerBlock) {
+        const uint64_t key = (i < st.count) ? st.buf[i] : 0ull;
+        if (o.out_keys) o.out_keys[i] = key;
+        const uint64_t grow = o.row_base + key_local_row(key);
+        const uint32_t sb = key_score_bits(key);
+        if (o.out_hits) {
+            ShardHit h;
+            // an empty slot is {0,0,0}; a real NaN hit has ord 0 too but score_bits != 0
+            h.global_row = key ? grow : 0ull;
+            h.ord = key ? (uint32_t)(key >> 32) : 0u;
+            h.score_bits = key ? sb : 0u;
+            o.out_hits[i] = h;
+        }
+        if (i < st.count) {
+            if (o.out_rows) o.out_rows[i] = grow;
+            if (o.out_scores) o.out_scores[i] = __uint_as_float(sb);
+        }
+    }
+    if (t == 0 && o.out_count) {
+        if (o.accumulate_count) atomicAdd(o.out_count, st.count);
+        else *o.out_count = st.count;
+    }
 }
 
 // ---------------------------------------------------------------------------------------
@@ -290,6 +450,10 @@ struct ScanParams {
     uint32_t n_stages;
     uint32_t q_floats;       // dim rounded up to a multiple of 32
     uint32_t evict_first;    // 1: stream the corpus through L2 with evict_first
+    // k > kMaxFastK is served by repeated passes: pass p only admits keys strictly below the
+    // last key of pass p-1 (read from device memory, so passes chain without a host sync).
+    const uint64_t *key_ceiling;  // null = no ceiling; *key_ceiling == 0 = nothing left
+    uint32_t accumulate_count;    // 1: atomicAdd into *out_count instead of storing
 };
 
 // Read element `col` (0..31) of row t in a swizzled stage.
@@ -405,12 +569,17 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
         qmag = *qmag_s;
     }
 
+    const uint64_t ceiling = p.key_ceiling ? __ldg(p.key_ceiling) : ~0ull;
+
     TopKState st;
     st.buf = cand_buf;
     st.cnt_smem = cnt_s;
     st.thr_smem = thr_s;
     st.count = 0;
     st.k = p.k;
+    // capacity: >= k + one row block of offers, power of two, at most kCandCap
+    st.cap = 512u;
+    while (st.cap < p.k + (uint32_t)kRowsPerBlock) st.cap <<= 1;
 
     const uint32_t swz = t & 7u;
     uint32_t stage = 0, phase = 0;
@@ -497,7 +666,8 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
             score = dot;
         }
         const uint32_t row = rb * kRowsPerBlock + t;
-        const uint64_t key = (row < p.n_rows) ? make_key(__float_as_uint(score), row) : 0ull;
+        uint64_t key = (row < p.n_rows) ? make_key(__float_as_uint(score), row) : 0ull;
+        if (key >= ceiling) key = 0ull;
         topk_offer(st, key, t);
     }
 
@@ -512,37 +682,25 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
     if (*ticket_s != gridDim.x - 1) return;
     __threadfence();
 
-    // st holds this CTA's own best (already in buf[0..count)); stream in the other CTAs' lists
-    const uint64_t total = (uint64_t)gridDim.x * p.k;
-    const volatile uint64_t *all = p.cand;
-    for (uint64_t base = 0; base < total; base += kRowsPerBlock) {
-        uint64_t i = base + t;
-        uint64_t key = 0ull;
-        if (i < total && (i / p.k) != blockIdx.x) key = all[i];
-        topk_offer(st, key, t);
-    }
-    topk_prune(st, t);
-    for (uint32_t i = t; i < p.k; i += kRowsPerBlock) {
-        uint64_t key = (i < st.count) ? st.buf[i] : 0ull;
-        if (p.out_keys) p.out_keys[i] = key;
-        uint64_t grow = p.row_base + key_local_row(key);
-        uint32_t sb = key_score_bits(key);
-        if (p.out_hits) {
-            ShardHit h;
-            h.global_row = key ? grow : 0ull;
-            h.ord = key ? (uint32_t)(key >> 32) : 0u;
-            h.score_bits = key ? sb : 0u;
-            // an empty slot is {0,0,0}; a real NaN hit has ord 0 too but is told apart by
-            // score_bits != 0
-            p.out_hits[i] = h;
-        }
-        if (i < st.count) {
-            if (p.out_rows) p.out_rows[i] = grow;
-            if (p.out_scores) p.out_scores[i] = __uint_as_float(sb);
-        }
-    }
+    // all lists (this CTA's own included) are in p.cand: select the k best of grid*k keys
+    MergeScratch ms;
+    ms.hist = reinterpret_cast<uint32_t *>(stages);  // the stage ring is idle now
+    ms.sc = ms.hist + 256;
+    if (t == 0) *st.cnt_smem = 0u;
+    st.count = 0;
+    st.cap = kCandCap;
+    consumer_sync();
+    merge_published(st, t, p.cand, gridDim.x * p.k, p.k, ms);
+    TopKOutputs o;
+    o.out_keys = p.out_keys;
+    o.out_hits = p.out_hits;
+    o.out_rows = p.out_rows;
+    o.out_scores = p.out_scores;
+    o.out_count = p.out_count;
+    o.row_base = p.row_base;
+    o.accumulate_count = p.accumulate_count;
+    write_outputs(st, t, p.k, o);
     if (t == 0) {
-        if (p.out_count) *p.out_count = st.count;
         // every CTA took its ticket after its producer's last cursor fetch: safe to reset
         p.done_counter[0] = 0u;
         p.done_counter[1] = 0u;

@@ -114,6 +114,9 @@ class DeviceIndex:
     def detach_comm(self) -> None:
         check(_ffi.lib().nm_index_detach_comm(self._h))
 
+    def set_batching(self, enable: bool) -> None:
+        check(_ffi.lib().nm_index_set_batching(self._h, 1 if enable else 0))
+
     def set_profiling(self, enable: bool) -> None:
         check(_ffi.lib().nm_index_set_profiling(self._h, 1 if enable else 0))
 

@@ -182,6 +182,22 @@ def test_k_edge_cases_and_errors():
     idx.close()
 
 
+@pytest.mark.parametrize("metric", METRICS)
+def test_large_k_chained_passes(metric):
+    """k > 1024 is served by chained passes under a key ceiling; result must equal the
+    oracle's single sort, including across pass boundaries and exact ties."""
+    base = o.fill_synthetic(6000, 40, 61)
+    rows = np.concatenate([base, base[:3000]])      # ties straddle the pass boundaries
+    idx = DeviceIndex(40)
+    idx.load(rows)
+    q = o.fill_synthetic(1, 40, 62)[0]
+    for k in (1025, 2048, 3000, 9000, 20000):
+        (got,) = idx.search(q, k, metric)
+        assert len(got[0]) == min(k, 9000)
+        assert_same(got, o.search(rows, q, k, metric, threads=4), f"{metric} k={k}")
+    idx.close()
+
+
 def test_multi_query_batch_equals_single_queries():
     idx, rows = synth_index(20000, 96)
     qs = o.fill_synthetic(7, 96, 0xABC)
@@ -190,6 +206,40 @@ def test_multi_query_batch_equals_single_queries():
         assert len(res) == 7
         for i in range(7):
             assert_same(res[i], o.search(rows, qs[i], 10, m, threads=4), f"{m} q{i}")
+    idx.close()
+
+
+@pytest.mark.parametrize("metric", METRICS)
+@pytest.mark.parametrize("n,dim,nq,k", [
+    (3000, 64, 8, 5), (20000, 96, 17, 10), (5000, 768, 70, 10), (1000, 40, 256, 100),
+    (70000, 32, 33, 1000), (300, 24, 9, 1024), (9000, 100, 20, 7), (4000, 1536, 64, 100),
+    (2500, 13, 12, 4),
+])
+def test_batched_queries_share_one_pass(metric, n, dim, nq, k):
+    """nq >= 8 goes through score_batch_kernel + select_batch_kernel (BASELINE config 4 shape);
+    every (query, row) score and every per-query ranking must equal nq independent searches.
+    dim % 8 != 0 with dot/cosine and dim % 32 != 0 with Euclidean cover the routing rules."""
+    base = o.fill_synthetic(n, dim, 0x5EED0001)
+    rows = base.copy()
+    rows[n // 2:n // 2 + n // 10] = base[:n // 10]      # exact ties
+    idx = DeviceIndex(dim)
+    idx.load(rows)
+    qs = o.fill_synthetic(nq, dim, 0xBEEF)
+    qs[1] = rows[7]                                      # a query equal to a stored row
+    if metric != "euclidean":
+        qs[2] = 0.0                                      # zero query: cosine scores all 0.0
+    res = idx.search(qs, k, metric)
+    launches_batched = idx.stats().scan_launches
+    assert len(res) == nq
+    for i in range(nq):
+        assert_same(res[i], o.search(rows, qs[i], k, metric, threads=8), f"{metric} q{i}")
+    idx.set_batching(False)
+    res2 = idx.search(qs, k, metric)
+    for i in range(nq):
+        assert np.array_equal(res[i][0], res2[i][0])
+        assert np.array_equal(res[i][1].view(np.uint32), res2[i][1].view(np.uint32))
+    batched_expected = metric == "euclidean" or dim % 8 == 0
+    assert (launches_batched < nq) == batched_expected
     idx.close()
 
 
