@@ -318,7 +318,10 @@ def run_ours(a):
             "workload": workload_name(a, total_rows), "rows": total_rows, "rows_per_gpu": local_rows,
             "dim": a.dim, "k": k, "metric": a.metric, "distinct_queries": nq,
             "sharding": "single GPU" if world == 1 else
-                        f"{world} contiguous row-range shards, one ncclAllGather of k 16-byte hits per rank",
+                        f"{world} contiguous row-range shards; per rank ONE fused kernel: scan + exchange of "
+                        f"k 16-byte hits through NVLink peer memory (CUDA IPC mailboxes) + merge"
+                        + (" [peer exchange disabled: ncclAllGather + merge kernel]"
+                           if os.environ.get("NM_DISABLE_PEER_EXCHANGE") == "1" else ""),
             "l2": f"input {algo_bytes / 1e9:.2f} GB per GPU per step >> 126 MB L2: no flush needed",
             "generator": "u24(splitmix64(splitmix64(seed)^(r*dim+c)))*2^-23-1, on device",
         },

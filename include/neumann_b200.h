@@ -113,6 +113,15 @@ int nm_index_fill_synthetic(nm_index *idx, uint64_t n, uint64_t seed, uint64_t r
 int nm_search(nm_index *idx, const float *queries, uint32_t nq, uint32_t k, int metric,
               uint64_t *out_rows, float *out_scores, uint32_t *out_counts);
 
+/* Pre-filtered scan (replaces search_with_pre_filter, vector_engine/src/lib.rs:3514-3557:
+ * "filter first, then search the subset").  row_mask is a host bitmask over the mirror's rows,
+ * bit (r % 64) of word r / 64 set = row r is eligible; ceil(rows / 64) words.  Ineligible rows
+ * never rank, and 256-row blocks without any eligible row are not even read from HBM.
+ * Single-device indexes without a communicator. */
+int nm_search_masked(nm_index *idx, const float *queries, uint32_t nq, uint32_t k, int metric,
+                     const uint64_t *row_mask, uint64_t *out_rows, float *out_scores,
+                     uint32_t *out_counts);
+
 /* Same scan with the query and the outputs resident in DEVICE memory of the index's first
  * device and the work enqueued on `stream` (a cudaStream_t).  With a caller stream the call
  * is fully ASYNCHRONOUS: it returns after enqueueing and the outputs are valid once the

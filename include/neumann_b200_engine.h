@@ -60,6 +60,31 @@ uint64_t nm_engine_collection_count(nm_engine *e, const char *collection);
 int nm_engine_search_in_collection(nm_engine *e, const char *collection, const float *query,
                                    size_t n, size_t top_k, nm_results **out);
 
+/* Metadata + filtered search (vector_engine/src/lib.rs:3429-3557, 1698-1829).
+ * `metadata` is a typed wire string: fields separated by 0x1f, each  name 0x1e type 0x1e value
+ * with type one of i (int64) f (double) s (string) b ("0"/"1") n (null).
+ * `where_expr` uses the SIMILAR ... WHERE grammar (field op literal, AND / OR, parentheses)
+ * plus EXISTS(f), CONTAINS(f,'s'), STARTS_WITH(f,'s'), f IN (v, ...); "TRUE" matches all.
+ * strategy: 0 auto, 1 pre-filter (device scan under a row bitmask), 2 post-filter. */
+int nm_engine_store_embedding_with_metadata(nm_engine *e, const char *key, const float *vec,
+                                            size_t n, const char *metadata);
+int nm_engine_store_in_collection_with_metadata(nm_engine *e, const char *collection,
+                                                const char *key, const float *vec, size_t n,
+                                                const char *metadata);
+int nm_engine_search_similar_filtered(nm_engine *e, const float *query, size_t n, size_t top_k,
+                                      const char *where_expr, int strategy,
+                                      size_t oversample_factor, nm_results **out);
+int nm_engine_search_filtered_in_collection(nm_engine *e, const char *collection,
+                                            const float *query, size_t n, size_t top_k,
+                                            const char *where_expr, int strategy,
+                                            size_t oversample_factor, nm_results **out);
+int nm_engine_count_matching(nm_engine *e, const char *where_expr, uint64_t *out);
+/* PointsService::query post-processing (neumann_server/src/service/points.rs:449-485);
+ * score_threshold is ignored when has_threshold == 0. */
+int nm_engine_query_points(nm_engine *e, const char *collection, const float *vector, size_t n,
+                           size_t limit, size_t offset, int has_threshold, float score_threshold,
+                           nm_results **out);
+
 /* QueryRouter::execute (legacy string path) / execute_parsed (AST path), SIMILAR + EMBED only.
  * *out is NULL for QueryResult::Empty. */
 int nm_engine_execute(nm_engine *e, const char *command, nm_results **out);

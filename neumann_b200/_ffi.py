@@ -58,6 +58,7 @@ SIGNATURES = {
     "nm_index_device_count": (C.c_int, [_vp]),
     "nm_index_fill_synthetic": (C.c_int, [_vp, C.c_uint64, C.c_uint64, C.c_uint64]),
     "nm_search": (C.c_int, [_vp, _vp, C.c_uint32, C.c_uint32, C.c_int, _vp, _vp, _vp]),
+    "nm_search_masked": (C.c_int, [_vp, _vp, C.c_uint32, C.c_uint32, C.c_int, _vp, _vp, _vp, _vp]),
     "nm_search_device": (C.c_int, [_vp, _vp, C.c_uint32, C.c_uint32, C.c_int, _vp, _vp, _vp, _vp]),
     "nm_comm_create_id": (C.c_int, [_vp]),
     "nm_index_attach_comm": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_uint64]),

@@ -1,6 +1,8 @@
 // engine_capi.cpp — extern "C" view of VectorEngine / QueryRouter (include/neumann_b200_engine.h).
+#include <cctype>
 #include <cstring>
 #include <memory>
+#include <optional>
 #include <string>
 
 #include "../../include/neumann_b200.h"
@@ -177,6 +179,105 @@ int nm_engine_search_in_collection(nm_engine *e, const char *collection, const f
     if (!e || !collection) return fail(NM_ERR_INVALID_ARGUMENT, "null argument");
     std::vector<float> q(query, query + (query ? n : 0));
     return give(e->engine->search_in_collection(collection, q, top_k), out);
+}
+
+namespace {
+bool parse_filter_arg(const char *where_expr, FilterCondition *f) {
+    std::string text = where_expr ? where_expr : "";
+    std::string up;
+    for (char c : text)
+        if (!isspace((unsigned char)c)) up += (char)toupper((unsigned char)c);
+    if (up.empty() || up == "TRUE") {
+        *f = FilterCondition::always();
+        return true;
+    }
+    std::string why;
+    if (!parse_where(text, f, &why)) {
+        fail(NM_ERR_INVALID_ARGUMENT, "Parse error: " + why);
+        return false;
+    }
+    return true;
+}
+FilteredSearchConfig filter_config(int strategy, size_t oversample) {
+    FilteredSearchConfig c;
+    c.strategy = (FilterStrategy)strategy;
+    if (oversample) c.oversample_factor = oversample;
+    return c;
+}
+}  // namespace
+
+int nm_engine_store_embedding_with_metadata(nm_engine *e, const char *key, const float *vec,
+                                            size_t n, const char *metadata) {
+    if (!e || !key) return fail(NM_ERR_INVALID_ARGUMENT, "null argument");
+    Metadata m;
+    std::string why;
+    if (!parse_metadata_wire(metadata ? metadata : "", &m, &why))
+        return fail(NM_ERR_INVALID_ARGUMENT, why);
+    auto r = e->engine->store_embedding_with_metadata(key, std::vector<float>(vec, vec + n), std::move(m));
+    return r.is_err() ? fail(r.error()) : NM_OK;
+}
+
+int nm_engine_store_in_collection_with_metadata(nm_engine *e, const char *collection,
+                                                const char *key, const float *vec, size_t n,
+                                                const char *metadata) {
+    if (!e || !collection || !key) return fail(NM_ERR_INVALID_ARGUMENT, "null argument");
+    Metadata m;
+    std::string why;
+    if (!parse_metadata_wire(metadata ? metadata : "", &m, &why))
+        return fail(NM_ERR_INVALID_ARGUMENT, why);
+    auto r = e->engine->store_in_collection_with_metadata(collection, key,
+                                                          std::vector<float>(vec, vec + n), std::move(m));
+    return r.is_err() ? fail(r.error()) : NM_OK;
+}
+
+int nm_engine_search_similar_filtered(nm_engine *e, const float *query, size_t n, size_t top_k,
+                                      const char *where_expr, int strategy,
+                                      size_t oversample_factor, nm_results **out) {
+    if (!e) return fail(NM_ERR_INVALID_ARGUMENT, "null engine");
+    if (out) *out = nullptr;
+    FilterCondition f;
+    if (!parse_filter_arg(where_expr, &f)) return NM_ERR_INVALID_ARGUMENT;
+    std::vector<float> q(query, query + (query ? n : 0));
+    return give(e->engine->search_similar_filtered(q, top_k, f, filter_config(strategy, oversample_factor)), out);
+}
+
+int nm_engine_search_filtered_in_collection(nm_engine *e, const char *collection,
+                                            const float *query, size_t n, size_t top_k,
+                                            const char *where_expr, int strategy,
+                                            size_t oversample_factor, nm_results **out) {
+    if (!e || !collection) return fail(NM_ERR_INVALID_ARGUMENT, "null argument");
+    if (out) *out = nullptr;
+    FilterCondition f;
+    if (!parse_filter_arg(where_expr, &f)) return NM_ERR_INVALID_ARGUMENT;
+    std::vector<float> q(query, query + (query ? n : 0));
+    return give(e->engine->search_filtered_in_collection(collection, q, top_k, f,
+                                                         filter_config(strategy, oversample_factor)), out);
+}
+
+int nm_engine_count_matching(nm_engine *e, const char *where_expr, uint64_t *out) {
+    if (!e || !out) return fail(NM_ERR_INVALID_ARGUMENT, "null argument");
+    FilterCondition f;
+    if (!parse_filter_arg(where_expr, &f)) return NM_ERR_INVALID_ARGUMENT;
+    *out = e->engine->count_matching(f);
+    return NM_OK;
+}
+
+int nm_engine_query_points(nm_engine *e, const char *collection, const float *vector, size_t n,
+                           size_t limit, size_t offset, int has_threshold, float score_threshold,
+                           nm_results **out) {
+    if (!e || !collection) return fail(NM_ERR_INVALID_ARGUMENT, "null argument");
+    if (out) *out = nullptr;
+    std::vector<float> q(vector, vector + (vector ? n : 0));
+    std::optional<float> thr;
+    if (has_threshold) thr = score_threshold;
+    auto r = e->engine->query_points(collection, q, limit, offset, thr, false);
+    if (r.is_err()) return fail(r.error());
+    if (out) {
+        auto *res = new nm_results();
+        for (auto &p : r.value()) res->hits.push_back(SearchResult{p.id, p.score});
+        *out = res;
+    }
+    return NM_OK;
 }
 
 int nm_engine_execute(nm_engine *e, const char *command, nm_results **out) {

@@ -116,6 +116,8 @@ struct Workspace {
     uint64_t *d_cand = nullptr;
     size_t cand_cap = 0;  // keys
     uint32_t *d_counter = nullptr;
+    uint32_t *d_mask = nullptr;       // row bitmask of a pre-filtered search, padded to row blocks
+    size_t mask_cap = 0;              // u32 words
     uint64_t *d_pass_keys = nullptr;  // [k] merged keys of the chained passes (k > 1024)
     size_t pass_keys_cap = 0;
     // packed result block: [counts u32 x nq (8-aligned)] [rows u64 x nq*k] [scores f32 x nq*k]
@@ -148,6 +150,7 @@ struct Workspace {
         if (h_query) cudaFreeHost(h_query);
         if (d_cand) cudaFree(d_cand);
         if (d_counter) cudaFree(d_counter);
+        if (d_mask) cudaFree(d_mask);
         if (d_pass_keys) cudaFree(d_pass_keys);
         if (d_qt) cudaFree(d_qt);
         if (d_qmag) cudaFree(d_qmag);
@@ -199,6 +202,13 @@ struct nm_index {
     ncclComm_t comm = nullptr;
     int n_ranks = 1, rank = 0;
     uint64_t comm_row_base = 0;
+    std::mutex comm_mu;  // collective searches are issued one at a time, in call order
+    // peer-memory exchange (CUDA IPC): the fused single-query path writes hits straight into
+    // the peers' mailboxes; NCCL stays for the batched / k > 1024 paths and as a fallback
+    void *xchg_mem = nullptr;                    // local [flags 256 B | mailbox]
+    void *xchg_peer[nm::kMaxRanks] = {nullptr};  // mapped peer buffers (own rank = xchg_mem)
+    bool xchg_ok = false;
+    uint32_t xchg_seq = 0;
     // counters
     std::atomic<uint64_t> searches{0}, rows_scanned{0}, bytes_streamed{0}, scan_launches{0},
         merge_launches{0}, h2d_bytes{0}, d2h_bytes{0};
@@ -414,9 +424,12 @@ int launch_scan_t(const Shard &sh, const nm::ScanParams &p, size_t smem, cudaStr
 // passes, each admitting only keys below the previous pass's last key.
 int launch_scan(nm_index *idx, const Shard &sh, Workspace &ws, const float *d_query, uint32_t k,
                 int metric, uint64_t row_base, uint64_t *out_rows, float *out_scores,
-                uint32_t *out_count, nm::ShardHit *out_hits, cudaStream_t stream) {
+                uint32_t *out_count, nm::ShardHit *out_hits, cudaStream_t stream,
+                const nm::PeerXchg *xchg = nullptr, const uint32_t *d_row_mask = nullptr) {
     nm::ScanParams p;
     memset(&p, 0, sizeof(p));
+    if (xchg) p.xchg = *xchg;
+    p.row_mask = d_row_mask;
     p.query = d_query;
     p.cand = ws.d_cand;
     p.done_counter = ws.d_counter;
@@ -449,7 +462,8 @@ int launch_scan(nm_index *idx, const Shard &sh, Workspace &ws, const float *d_qu
         if (out_count) CUDA_TRY(cudaMemsetAsync(out_count, 0, 4, stream));
     }
     // never ask for more hits than the shard has rows (slots past that stay empty)
-    const uint32_t k_need = (uint32_t)std::min<uint64_t>(k, sh.rows);
+    // (the fused exchange needs the same k on every rank, whatever the local row count)
+    const uint32_t k_need = xchg ? k : (uint32_t)std::min<uint64_t>(k, sh.rows);
     if (out_hits && k_need < k)
         CUDA_TRY(cudaMemsetAsync(out_hits + k_need, 0, (size_t)(k - k_need) * sizeof(nm::ShardHit),
                                  stream));
@@ -644,6 +658,96 @@ int scan_queries(nm_index *idx, const Shard &sh, Workspace &ws, const float *d_q
     return NM_OK;
 }
 
+
+constexpr size_t kXchgFlagBytes = 256;
+size_t xchg_bytes(int n_ranks) {
+    return kXchgFlagBytes + (size_t)2 * n_ranks * nm::kMaxFastK * sizeof(nm::ShardHit);
+}
+
+nm::PeerXchg make_xchg(const nm_index *idx, uint32_t seq) {
+    nm::PeerXchg x;
+    memset(&x, 0, sizeof(x));
+    x.n_ranks = (uint32_t)idx->n_ranks;
+    x.rank = (uint32_t)idx->rank;
+    x.seq = seq;
+    x.kcap = nm::kMaxFastK;
+    for (int r = 0; r < idx->n_ranks; ++r) {
+        uint8_t *base = static_cast<uint8_t *>(idx->xchg_peer[r]);
+        x.flags[r] = reinterpret_cast<uint32_t *>(base);
+        x.mailbox[r] = reinterpret_cast<nm::ShardHit *>(base + kXchgFlagBytes);
+    }
+    return x;
+}
+
+// Map every rank's exchange buffer into this process.  Failure is not fatal: the index then
+// keeps using ncclAllGather + merge_shards_kernel.
+void setup_peer_exchange(nm_index *idx, cudaStream_t stream) {
+    idx->xchg_ok = false;
+    const char *off = getenv("NM_DISABLE_PEER_EXCHANGE");
+    if (off && off[0] == '1') return;
+    if (idx->n_ranks < 2 || idx->n_ranks > nm::kMaxRanks) return;
+    const int n = idx->n_ranks;
+    bool ok = true;
+    cudaIpcMemHandle_t mine;
+    cudaIpcMemHandle_t *d_handles = nullptr;
+    std::vector<cudaIpcMemHandle_t> all((size_t)n);
+    // every rank must reach the all-gather below, so failures only clear `ok`
+    if (cudaMalloc(&idx->xchg_mem, xchg_bytes(n)) != cudaSuccess) ok = false;
+    if (ok && cudaMemset(idx->xchg_mem, 0, xchg_bytes(n)) != cudaSuccess) ok = false;
+    memset(&mine, 0, sizeof(mine));
+    if (ok && cudaIpcGetMemHandle(&mine, idx->xchg_mem) != cudaSuccess) ok = false;
+    if (!ok) memset(&mine, 0, sizeof(mine));
+    if (cudaMalloc(&d_handles, sizeof(mine) * n) != cudaSuccess) {
+        cudaGetLastError();
+        return;  // cannot even exchange: peers time out in NCCL, nothing we can do here
+    }
+    cudaMemcpyAsync(d_handles + idx->rank, &mine, sizeof(mine), cudaMemcpyHostToDevice, stream);
+    ncclResult_t nr = nccl().AllGather(d_handles + idx->rank, d_handles, sizeof(mine), ncclChar,
+                                       idx->comm, stream);
+    cudaMemcpyAsync(all.data(), d_handles, sizeof(mine) * n, cudaMemcpyDeviceToHost, stream);
+    if (cudaStreamSynchronize(stream) != cudaSuccess || nr != ncclSuccess) ok = false;
+    cudaFree(d_handles);
+    cudaIpcMemHandle_t zero;
+    memset(&zero, 0, sizeof(zero));
+    for (int r = 0; r < n && ok; ++r)
+        if (memcmp(&all[r], &zero, sizeof(zero)) == 0) ok = false;  // some rank failed
+    for (int r = 0; r < n && ok; ++r) {
+        if (r == idx->rank) {
+            idx->xchg_peer[r] = idx->xchg_mem;
+        } else if (cudaIpcOpenMemHandle(&idx->xchg_peer[r], all[r],
+                                        cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+            idx->xchg_peer[r] = nullptr;
+            ok = false;
+        }
+    }
+    // agree on the outcome: everyone uses the exchange or nobody does
+    int *d_flag = nullptr;
+    std::vector<int> flags((size_t)n, 0);
+    int my = ok ? 1 : 0;
+    if (cudaMalloc(&d_flag, sizeof(int) * n) == cudaSuccess) {
+        cudaMemcpyAsync(d_flag + idx->rank, &my, sizeof(int), cudaMemcpyHostToDevice, stream);
+        nr = nccl().AllGather(d_flag + idx->rank, d_flag, sizeof(int), ncclChar, idx->comm, stream);
+        cudaMemcpyAsync(flags.data(), d_flag, sizeof(int) * n, cudaMemcpyDeviceToHost, stream);
+        if (cudaStreamSynchronize(stream) != cudaSuccess || nr != ncclSuccess) ok = false;
+        cudaFree(d_flag);
+        for (int r = 0; r < n; ++r) ok = ok && flags[r] == 1;
+    } else {
+        ok = false;
+    }
+    cudaGetLastError();
+    idx->xchg_ok = ok;
+    idx->xchg_seq = 0;
+}
+
+void teardown_peer_exchange(nm_index *idx) {
+    for (int r = 0; r < nm::kMaxRanks; ++r) {
+        if (idx->xchg_peer[r] && idx->xchg_peer[r] != idx->xchg_mem)
+            cudaIpcCloseMemHandle(idx->xchg_peer[r]);
+        idx->xchg_peer[r] = nullptr;
+    }
+    idx->xchg_ok = false;
+}
+
 uint32_t pow2_ceil(uint32_t v) {
     uint32_t n = 2;
     while (n < v) n <<= 1;
@@ -669,6 +773,37 @@ int validate_search(const nm_index *idx, const void *queries, uint32_t nq, uint3
 }
 
 }  // namespace
+
+
+// Rank-independent routing decision for collective searches (every rank must agree).
+bool collective_uses_fused_exchange(const nm_index *idx, uint32_t nq, uint32_t k, int metric) {
+    if (!idx->xchg_ok || k > (uint32_t)nm::kMaxFastK) return false;
+    const bool would_batch = idx->batching.load() && nq >= kBatchMinQueries &&
+                             (metric == NM_EUCLIDEAN || (idx->dim % 8u) == 0);
+    return !would_batch;
+}
+
+// One fused launch per query: scan + peer-memory exchange + merge, results written in place.
+int collective_fused(nm_index *idx, const Shard &sh, Workspace &ws, const float *d_queries,
+                     uint32_t nq, uint32_t k, int metric, uint64_t *out_rows, float *out_scores,
+                     uint32_t *out_counts, cudaStream_t stream) {
+    for (uint32_t q = 0; q < nq; ++q) {
+        nm::PeerXchg x = make_xchg(idx, ++idx->xchg_seq);
+        if (sh.rows == 0) {
+            nm::exchange_empty_shard_kernel<<<1, nm::kRowsPerBlock, 0, stream>>>(
+                x, k, ws.d_cand, out_rows + (size_t)q * k, out_scores + (size_t)q * k,
+                out_counts + q);
+            CUDA_TRY(cudaGetLastError());
+            idx->merge_launches++;
+        } else {
+            int rc = launch_scan(idx, sh, ws, d_queries + (size_t)q * idx->dim, k, metric,
+                                 idx->comm_row_base, out_rows + (size_t)q * k,
+                                 out_scores + (size_t)q * k, out_counts + q, nullptr, stream, &x);
+            if (rc) return rc;
+        }
+    }
+    return NM_OK;
+}
 
 // ======================================================================================
 // C ABI
@@ -730,7 +865,13 @@ int nm_index_create(uint32_t dim, const int *devices, int n_dev, nm_index **out)
 
 void nm_index_destroy(nm_index *idx) {
     if (!idx) return;
-    if (idx->comm && nccl().ok) nccl().CommDestroy(idx->comm);
+    if (idx->comm && nccl().ok) {
+        cudaSetDevice(idx->shards[0]->device);
+        cudaDeviceSynchronize();
+        teardown_peer_exchange(idx);
+        nccl().CommDestroy(idx->comm);
+        if (idx->xchg_mem) cudaFree(idx->xchg_mem);
+    }
     for (auto &sh : idx->shards) {
         cudaSetDevice(sh->device);
         sh->pool.clear();
@@ -898,8 +1039,9 @@ int nm_index_fill_synthetic(nm_index *idx, uint64_t n, uint64_t seed, uint64_t r
 // --------------------------------------------------------------------------------------
 // search
 // --------------------------------------------------------------------------------------
-int nm_search(nm_index *idx, const float *queries, uint32_t nq, uint32_t k, int metric,
-              uint64_t *out_rows, float *out_scores, uint32_t *out_counts) {
+static int search_impl(nm_index *idx, const float *queries, uint32_t nq, uint32_t k, int metric,
+                       const uint64_t *row_mask, uint64_t *out_rows, float *out_scores,
+                       uint32_t *out_counts) {
     int rc = validate_search(idx, queries, nq, k, metric, out_rows, out_scores, out_counts);
     if (rc) return rc;
     std::shared_lock<std::shared_mutex> g(idx->mu);
@@ -908,6 +1050,9 @@ int nm_search(nm_index *idx, const float *queries, uint32_t nq, uint32_t k, int 
     const bool collective = idx->comm != nullptr;
     if (collective && G != 1)
         return fail(NM_ERR_CONFIGURATION, "a communicator needs a single-device index per rank");
+    if (row_mask && (collective || G != 1))
+        return fail(NM_ERR_CONFIGURATION,
+                    "nm_search_masked needs a single-device index without a communicator");
 
     // ---- fast path: one device, no communicator: the kernel writes the final result ----
     if (G == 1 && !collective) {
@@ -931,13 +1076,38 @@ int nm_search(nm_index *idx, const float *queries, uint32_t nq, uint32_t k, int 
         memcpy(ws->h_query, queries, (size_t)nq * dim * 4);
         CUDA_TRY(cudaMemcpyAsync(ws->d_query, ws->h_query, (size_t)nq * dim * 4,
                                  cudaMemcpyHostToDevice, ws->stream));
+        uint64_t *r_rows = reinterpret_cast<uint64_t *>(ws->d_result + l.rows_off);
+        float *r_scores = reinterpret_cast<float *>(ws->d_result + l.scores_off);
+        uint32_t *r_counts = reinterpret_cast<uint32_t *>(ws->d_result + l.counts_off);
+        if (row_mask) {
+            // stage the bitmask (bit r of word r/64 == bit r%32 of u32 word r/32 on little
+            // endian hosts), padded with zeros to whole row blocks
+            const size_t words = (((size_t)sh.rows + 255) / 256) * 8;
+            const size_t src_bytes = (((size_t)sh.rows + 63) / 64) * 8;
+            if (ws->mask_cap < words) {
+                if (ws->d_mask) CUDA_TRY(cudaFree(ws->d_mask));
+                ws->mask_cap = 0;
+                CUDA_TRY(cudaMalloc(&ws->d_mask, words * 4));
+                ws->mask_cap = words;
+            }
+            CUDA_TRY(cudaMemsetAsync(ws->d_mask, 0, words * 4, ws->stream));
+            CUDA_TRY(cudaMemcpyAsync(ws->d_mask, row_mask, src_bytes, cudaMemcpyHostToDevice,
+                                     ws->stream));
+            idx->h2d_bytes += src_bytes;
+        }
         CUDA_TRY(cudaEventRecord(ws->ev0, ws->stream));
-        rc = scan_queries(idx, sh, *ws, ws->d_query, nq, k, metric, sh.row_base,
-                          reinterpret_cast<uint64_t *>(ws->d_result + l.rows_off),
-                          reinterpret_cast<float *>(ws->d_result + l.scores_off),
-                          reinterpret_cast<uint32_t *>(ws->d_result + l.counts_off), nullptr,
-                          ws->stream);
-        if (rc) return rc;
+        if (row_mask) {
+            for (uint32_t q = 0; q < nq; ++q) {
+                rc = launch_scan(idx, sh, *ws, ws->d_query + (size_t)q * dim, k, metric, sh.row_base,
+                                 r_rows + (size_t)q * k, r_scores + (size_t)q * k, r_counts + q,
+                                 nullptr, ws->stream, nullptr, ws->d_mask);
+                if (rc) return rc;
+            }
+        } else {
+            rc = scan_queries(idx, sh, *ws, ws->d_query, nq, k, metric, sh.row_base, r_rows, r_scores,
+                              r_counts, nullptr, ws->stream);
+            if (rc) return rc;
+        }
         CUDA_TRY(cudaEventRecord(ws->ev1, ws->stream));
         CUDA_TRY(cudaMemcpyAsync(ws->h_result, ws->d_result, l.total, cudaMemcpyDeviceToHost,
                                  ws->stream));
@@ -961,10 +1131,13 @@ int nm_search(nm_index *idx, const float *queries, uint32_t nq, uint32_t k, int 
         return NM_OK;
     }
 
-    // ---- collective path: one shard per process, ONE all-gather, merge on device ----
+    // ---- collective path: one shard per process.  Single queries: ONE fused launch (scan +
+    //      peer-memory exchange + merge).  Batches / k > 1024: scan, ONE ncclAllGather of the
+    //      per-shard hits, merge kernel. ----
     if (collective) {
         Shard &sh = *idx->shards[0];
         CUDA_TRY(cudaSetDevice(sh.device));
+        std::lock_guard<std::mutex> cg(idx->comm_mu);
         std::unique_ptr<Workspace> ws;
         rc = ws_acquire(sh, ws);
         if (rc) return rc;
@@ -976,37 +1149,46 @@ int nm_search(nm_index *idx, const float *queries, uint32_t nq, uint32_t k, int 
         rc = ws_ensure(*ws, sh, dim, nq, k, true, true, true, idx->n_ranks);
         if (rc) return rc;
         ResultLayout l = result_layout(nq, k);
+        uint64_t *r_rows = reinterpret_cast<uint64_t *>(ws->d_result + l.rows_off);
+        float *r_scores = reinterpret_cast<float *>(ws->d_result + l.scores_off);
+        uint32_t *r_counts = reinterpret_cast<uint32_t *>(ws->d_result + l.counts_off);
         memcpy(ws->h_query, queries, (size_t)nq * dim * 4);
         CUDA_TRY(cudaMemcpyAsync(ws->d_query, ws->h_query, (size_t)nq * dim * 4,
                                  cudaMemcpyHostToDevice, ws->stream));
         CUDA_TRY(cudaEventRecord(ws->ev0, ws->stream));
-        if (sh.rows == 0) {
-            CUDA_TRY(cudaMemsetAsync(ws->d_hits, 0, (size_t)nq * k * sizeof(nm::ShardHit),
-                                     ws->stream));
-        } else {
-            rc = scan_queries(idx, sh, *ws, ws->d_query, nq, k, metric, idx->comm_row_base,
-                              nullptr, nullptr, nullptr, ws->d_hits, ws->stream);
+        if (collective_uses_fused_exchange(idx, nq, k, metric)) {
+            rc = collective_fused(idx, sh, *ws, ws->d_query, nq, k, metric, r_rows, r_scores,
+                                  r_counts, ws->stream);
             if (rc) return rc;
+            CUDA_TRY(cudaEventRecord(ws->ev1, ws->stream));
+        } else {
+            if (sh.rows == 0) {
+                CUDA_TRY(cudaMemsetAsync(ws->d_hits, 0, (size_t)nq * k * sizeof(nm::ShardHit),
+                                         ws->stream));
+            } else {
+                rc = scan_queries(idx, sh, *ws, ws->d_query, nq, k, metric, idx->comm_row_base,
+                                  nullptr, nullptr, nullptr, ws->d_hits, ws->stream);
+                if (rc) return rc;
+            }
+            CUDA_TRY(cudaEventRecord(ws->ev1, ws->stream));
+            NCCL_TRY(nccl().AllGather(ws->d_hits, ws->d_gather,
+                                      (size_t)nq * k * sizeof(nm::ShardHit), ncclChar, idx->comm,
+                                      ws->stream));
+            uint32_t total = (uint32_t)idx->n_ranks * k;
+            uint32_t n_sort = pow2_ceil(total);
+            size_t msmem = (size_t)n_sort * 8;
+            if (msmem > 200 * 1024)
+                return fail(NM_ERR_INVALID_TOP_K, "n_ranks*k = %u too large for the merge kernel",
+                            total);
+            if (msmem > 48 * 1024)
+                CUDA_TRY(cudaFuncSetAttribute(nm::merge_shards_kernel,
+                                              cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              200 * 1024));
+            nm::merge_shards_kernel<<<nq, nm::kMergeThreads, msmem, ws->stream>>>(
+                ws->d_gather, (uint32_t)idx->n_ranks, k, nq * k, n_sort, r_rows, r_scores, r_counts);
+            CUDA_TRY(cudaGetLastError());
+            idx->merge_launches++;
         }
-        CUDA_TRY(cudaEventRecord(ws->ev1, ws->stream));
-        NCCL_TRY(nccl().AllGather(ws->d_hits, ws->d_gather,
-                                  (size_t)nq * k * sizeof(nm::ShardHit), ncclChar, idx->comm,
-                                  ws->stream));
-        uint32_t total = (uint32_t)idx->n_ranks * k;
-        uint32_t n_sort = pow2_ceil(total);
-        size_t msmem = (size_t)n_sort * 8;
-        if (msmem > 200 * 1024)
-            return fail(NM_ERR_INVALID_TOP_K, "n_ranks*k = %u too large for the merge kernel", total);
-        if (msmem > 48 * 1024)
-            CUDA_TRY(cudaFuncSetAttribute(nm::merge_shards_kernel,
-                                          cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        nm::merge_shards_kernel<<<nq, nm::kMergeThreads, msmem, ws->stream>>>(
-            ws->d_gather, (uint32_t)idx->n_ranks, k, nq * k, n_sort,
-            reinterpret_cast<uint64_t *>(ws->d_result + l.rows_off),
-            reinterpret_cast<float *>(ws->d_result + l.scores_off),
-            reinterpret_cast<uint32_t *>(ws->d_result + l.counts_off));
-        CUDA_TRY(cudaGetLastError());
-        idx->merge_launches++;
         CUDA_TRY(cudaMemcpyAsync(ws->h_result, ws->d_result, l.total, cudaMemcpyDeviceToHost,
                                  ws->stream));
         CUDA_TRY(cudaStreamSynchronize(ws->stream));
@@ -1017,6 +1199,8 @@ int nm_search(nm_index *idx, const float *queries, uint32_t nq, uint32_t k, int 
         const uint64_t *hr = reinterpret_cast<const uint64_t *>(ws->h_result + l.rows_off);
         const float *hs = reinterpret_cast<const float *>(ws->h_result + l.scores_off);
         for (uint32_t q = 0; q < nq; ++q) {
+            if (hc[q] == 0xffffffffu)
+                return fail(NM_ERR_STORAGE, "peer exchange timed out waiting for another rank");
             out_counts[q] = hc[q];
             memcpy(out_rows + (size_t)q * k, hr + (size_t)q * k, (size_t)hc[q] * 8);
             memcpy(out_scores + (size_t)q * k, hs + (size_t)q * k, (size_t)hc[q] * 4);
@@ -1099,6 +1283,18 @@ int nm_search(nm_index *idx, const float *queries, uint32_t nq, uint32_t k, int 
     return NM_OK;
 }
 
+int nm_search(nm_index *idx, const float *queries, uint32_t nq, uint32_t k, int metric,
+              uint64_t *out_rows, float *out_scores, uint32_t *out_counts) {
+    return search_impl(idx, queries, nq, k, metric, nullptr, out_rows, out_scores, out_counts);
+}
+
+int nm_search_masked(nm_index *idx, const float *queries, uint32_t nq, uint32_t k, int metric,
+                     const uint64_t *row_mask, uint64_t *out_rows, float *out_scores,
+                     uint32_t *out_counts) {
+    if (!row_mask) return fail(NM_ERR_INVALID_ARGUMENT, "null row mask");
+    return search_impl(idx, queries, nq, k, metric, row_mask, out_rows, out_scores, out_counts);
+}
+
 int nm_search_device(nm_index *idx, const float *d_queries, uint32_t nq, uint32_t k, int metric,
                      uint64_t *d_out_rows, float *d_out_scores, uint32_t *d_out_counts,
                      void *stream_v) {
@@ -1171,7 +1367,15 @@ int nm_search_device(nm_index *idx, const float *d_queries, uint32_t nq, uint32_
             if (rc) return rc;
         }
         if (prof) CUDA_TRY(cudaEventRecord(prof->second, stream));
+    } else if (collective_uses_fused_exchange(idx, nq, k, metric)) {
+        // (collective calls on one index must be issued in the same order on every rank)
+        std::lock_guard<std::mutex> cg(idx->comm_mu);
+        rc = collective_fused(idx, sh, *ws, d_queries, nq, k, metric, d_out_rows, d_out_scores,
+                              d_out_counts, stream);
+        if (rc) return rc;
+        if (prof) CUDA_TRY(cudaEventRecord(prof->second, stream));
     } else {
+        std::lock_guard<std::mutex> cg(idx->comm_mu);
         if (sh.rows == 0) {
             CUDA_TRY(cudaMemsetAsync(ws->d_hits, 0, (size_t)nq * k * sizeof(nm::ShardHit), stream));
         } else {
@@ -1245,6 +1449,7 @@ int nm_index_attach_comm(nm_index *idx, const void *id, int n_ranks, int rank, u
     idx->n_ranks = n_ranks;
     idx->rank = rank;
     idx->comm_row_base = row_base;
+    setup_peer_exchange(idx, idx->shards[0]->copy_stream);
     return NM_OK;
 }
 
@@ -1252,8 +1457,13 @@ int nm_index_detach_comm(nm_index *idx) {
     if (!idx) return fail(NM_ERR_INVALID_ARGUMENT, "null index");
     std::unique_lock<std::shared_mutex> g(idx->mu);
     if (idx->comm) {
-        NCCL_TRY(nccl().CommDestroy(idx->comm));
+        CUDA_TRY(cudaSetDevice(idx->shards[0]->device));
+        CUDA_TRY(cudaDeviceSynchronize());
+        teardown_peer_exchange(idx);
+        NCCL_TRY(nccl().CommDestroy(idx->comm));  // collective: every rank has unmapped by now
         idx->comm = nullptr;
+        if (idx->xchg_mem) cudaFree(idx->xchg_mem);
+        idx->xchg_mem = nullptr;
     }
     idx->n_ranks = 1;
     idx->rank = 0;

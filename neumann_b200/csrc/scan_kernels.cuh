@@ -78,6 +78,19 @@ struct alignas(16) ShardHit {
     uint32_t score_bits;  // exact score bits (keeps -0.0)
 };
 
+// Peer-memory exchange of per-shard hits (one process per GPU, buffers mapped with CUDA IPC).
+// mailbox[r] / flags[r] are rank r's buffers as seen from THIS process (own rank = local).
+//   mailbox layout: [2 slots][n_ranks writers][kcap] ShardHit     flags: [n_ranks] u32 sequence
+constexpr int kMaxRanks = 8;
+struct PeerXchg {
+    ShardHit *mailbox[kMaxRanks];
+    uint32_t *flags[kMaxRanks];
+    uint32_t n_ranks;  // <= 1: exchange disabled
+    uint32_t rank;
+    uint32_t seq;      // launch sequence number, identical on every rank, starts at 1
+    uint32_t kcap;     // ShardHit slots per (slot, writer)
+};
+
 #ifdef __CUDACC__
 // ---------------------------------------------------------------------------------------
 // PTX helpers (mbarrier, TMA, named barriers)
@@ -152,6 +165,15 @@ __device__ __forceinline__ uint32_t consumer_sync_popc(bool pred) {
         : "r"((uint32_t)pred), "n"(kRowsPerBlock)
         : "memory");
     return total;
+}
+
+__device__ __forceinline__ void st_release_sys(uint32_t *p, uint32_t v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t *p) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -383,6 +405,82 @@ __device__ __forceinline__ void write_outputs(const TopKState &st, uint32_t t, u
     }
 }
 
+
+// ---------------------------------------------------------------------------------------
+// fused cross-shard exchange + merge (replaces ncclAllGather + merge_shards_kernel on the
+// single-query path; semantics of ResultMerger::merge_top_k, distributed.rs:413-433).
+// Called by the 256 consumer threads of the LAST CTA with this shard's sorted top-k keys in
+// st.buf[0..count).  Writes this shard's hits into every rank's mailbox over NVLink, raises
+// this rank's sequence flag on every peer, waits for all peers' flags, then merges the
+// n_ranks*k gathered hits (concatenation position breaks ties == stable sort in shard order).
+// Returns false if a peer did not show up within ~4 s of spinning (count is then poisoned).
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ bool exchange_and_merge(TopKState &st, uint32_t t, const PeerXchg &x,
+                                                   uint64_t row_base, uint64_t *scratch_keys,
+                                                   const MergeScratch ms, uint64_t *out_rows,
+                                                   float *out_scores, uint32_t *out_count) {
+    const uint32_t k = st.k;
+    const uint32_t slot = x.seq & 1u;
+    // 1. my hits -> every rank's mailbox[slot][my rank]
+    for (uint32_t r = 0; r < x.n_ranks; ++r) {
+        ShardHit *dst = x.mailbox[r] + ((size_t)slot * x.n_ranks + x.rank) * x.kcap;
+        for (uint32_t i = t; i < k; i += kRowsPerBlock) {
+            const uint64_t key = (i < st.count) ? st.buf[i] : 0ull;
+            uint4 w;
+            const uint64_t grow = key ? row_base + key_local_row(key) : 0ull;
+            w.x = (uint32_t)grow;
+            w.y = (uint32_t)(grow >> 32);
+            w.z = key ? (uint32_t)(key >> 32) : 0u;   // ord
+            w.w = key ? key_score_bits(key) : 0u;     // exact score bits
+            *reinterpret_cast<uint4 *>(dst + i) = w;
+        }
+    }
+    __threadfence_system();
+    consumer_sync();
+    if (t < x.n_ranks) st_release_sys(x.flags[t] + x.rank, x.seq);
+    // 2. wait until every rank's hits for this sequence number have landed here
+    bool ok = true;
+    if (t < x.n_ranks) {
+        const long long t0 = clock64();
+        while ((int32_t)(ld_acquire_sys(x.flags[x.rank] + t) - x.seq) < 0) {
+            __nanosleep(64);
+            if (clock64() - t0 > 8000000000ll) {
+                ok = false;
+                break;
+            }
+        }
+    }
+    const uint32_t bad = consumer_sync_popc(!ok);
+    if (bad) {
+        if (t == 0 && out_count) *out_count = 0xffffffffu;
+        return false;
+    }
+    // 3. merge keys: (ord, position in the concatenation)
+    const ShardHit *mine = x.mailbox[x.rank] + (size_t)slot * x.n_ranks * x.kcap;
+    const uint32_t total = x.n_ranks * k;
+    for (uint32_t pos = t; pos < total; pos += kRowsPerBlock) {
+        const uint32_t r = pos / k, i = pos - r * k;
+        const uint4 w = __ldcg(reinterpret_cast<const uint4 *>(mine + (size_t)r * x.kcap + i));
+        const bool valid = (w.z != 0u) || (w.w != 0u);
+        scratch_keys[pos] = valid ? (((uint64_t)w.z << 32) | (uint64_t)(0xffffffffu - pos)) : 0ull;
+    }
+    __threadfence();
+    if (t == 0) *st.cnt_smem = 0u;
+    st.count = 0;
+    st.cap = kCandCap;
+    consumer_sync();
+    merge_published(st, t, scratch_keys, total, k, ms);
+    for (uint32_t i = t; i < st.count; i += kRowsPerBlock) {
+        const uint32_t pos = 0xffffffffu - (uint32_t)st.buf[i];
+        const uint32_t r = pos / k, j = pos - r * k;
+        const uint4 w = __ldcg(reinterpret_cast<const uint4 *>(mine + (size_t)r * x.kcap + j));
+        if (out_rows) out_rows[i] = ((uint64_t)w.y << 32) | w.x;
+        if (out_scores) out_scores[i] = __uint_as_float(w.w);
+    }
+    if (t == 0 && out_count) *out_count = st.count;
+    return true;
+}
+
 // ---------------------------------------------------------------------------------------
 // per-row accumulation
 // ---------------------------------------------------------------------------------------
@@ -454,6 +552,11 @@ struct ScanParams {
     // last key of pass p-1 (read from device memory, so passes chain without a host sync).
     const uint64_t *key_ceiling;  // null = no ceiling; *key_ceiling == 0 = nothing left
     uint32_t accumulate_count;    // 1: atomicAdd into *out_count instead of storing
+    PeerXchg xchg;                // n_ranks > 1: fused cross-shard exchange in the last CTA
+    // optional pre-filter (search_with_pre_filter, vector_engine/src/lib.rs:3514-3557): bit r
+    // set = row r takes part.  Padded to whole row blocks (8 words each).  Row blocks whose 8
+    // words are all zero are never loaded.
+    const uint32_t *row_mask;
 };
 
 // Read element `col` (0..31) of row t in a swizzled stage.
@@ -510,6 +613,15 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
             uint32_t stage = 0, phase = 0;
             uint32_t rb = blockIdx.x;
             for (;;) {
+                if (p.row_mask) {
+                    // pre-filter: skip row blocks without a single eligible row
+                    while (rb < n_rb) {
+                        const uint4 *m = reinterpret_cast<const uint4 *>(p.row_mask + rb * 8u);
+                        const uint4 a = __ldg(m), b = __ldg(m + 1);
+                        if ((a.x | a.y | a.z | a.w | b.x | b.y | b.z | b.w) != 0u) break;
+                        rb = atomicAdd(p.done_counter + 1, 1u) + gridDim.x;
+                    }
+                }
                 if (rb >= n_rb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1u);
                     rb_ring[stage] = 0xffffffffu;
@@ -668,6 +780,7 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
         const uint32_t row = rb * kRowsPerBlock + t;
         uint64_t key = (row < p.n_rows) ? make_key(__float_as_uint(score), row) : 0ull;
         if (key >= ceiling) key = 0ull;
+        if (p.row_mask && key && !((__ldg(p.row_mask + (row >> 5)) >> (row & 31u)) & 1u)) key = 0ull;
         topk_offer(st, key, t);
     }
 
@@ -691,6 +804,17 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
     st.cap = kCandCap;
     consumer_sync();
     merge_published(st, t, p.cand, gridDim.x * p.k, p.k, ms);
+    if (p.xchg.n_ranks > 1) {
+        // p.cand has room for gridDim.x * k >= n_ranks * k merge keys only if the grid is
+        // at least n_ranks CTAs; the host guarantees a scratch of max(grid, n_ranks) * k
+        exchange_and_merge(st, t, p.xchg, p.row_base, p.cand, ms, p.out_rows, p.out_scores,
+                           p.out_count);
+        if (t == 0) {
+            p.done_counter[0] = 0u;
+            p.done_counter[1] = 0u;
+        }
+        return;
+    }
     TopKOutputs o;
     o.out_keys = p.out_keys;
     o.out_hits = p.out_hits;
@@ -705,6 +829,33 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
         p.done_counter[0] = 0u;
         p.done_counter[1] = 0u;
     }
+}
+
+// A rank whose shard is empty still has to take part in the exchange.
+__global__ void __launch_bounds__(kRowsPerBlock)
+exchange_empty_shard_kernel(PeerXchg x, uint32_t k, uint64_t *scratch_keys, uint64_t *out_rows,
+                            float *out_scores, uint32_t *out_count) {
+    __shared__ __align__(16) uint64_t buf[kCandCap];
+    __shared__ uint64_t thr_s;
+    __shared__ uint32_t cnt_s;
+    __shared__ uint32_t hist[256 + 16];
+    const uint32_t t = threadIdx.x;
+    if (t == 0) {
+        thr_s = 0ull;
+        cnt_s = 0u;
+    }
+    __syncthreads();
+    TopKState st;
+    st.buf = buf;
+    st.cnt_smem = &cnt_s;
+    st.thr_smem = &thr_s;
+    st.count = 0;
+    st.k = k;
+    st.cap = kCandCap;
+    MergeScratch ms;
+    ms.hist = hist;
+    ms.sc = hist + 256;
+    exchange_and_merge(st, t, x, 0ull, scratch_keys, ms, out_rows, out_scores, out_count);
 }
 
 // ---------------------------------------------------------------------------------------

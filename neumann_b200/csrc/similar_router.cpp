@@ -225,6 +225,8 @@ RouterOutcome QueryRouter::execute_parsed(const std::string &command_in) {
     DistanceMetric metric = DistanceMetric::Cosine;
     std::string collection;
     bool has_collection = false;
+    FilterCondition filter;
+    bool has_filter = false;
     int stage = 0;  // 0 limit, 1 metric, 2 into, 3 done
     while (!tail.empty()) {
         std::string kw, r2;
@@ -233,9 +235,14 @@ RouterOutcome QueryRouter::execute_parsed(const std::string &command_in) {
         if (K == "CONNECTED")
             return fail(RouterError::Kind::ParseError,
                         "SIMILAR ... CONNECTED TO is a cross-engine query (out of scope here)");
-        if (K == "WHERE")
-            return fail(RouterError::Kind::ParseError,
-                        "SIMILAR ... WHERE (filtered search) is out of scope in this build");
+        if (K == "WHERE") {
+            // the rest of the statement is the filter expression (QR:5370-5375)
+            std::string why;
+            if (!parse_where(r2, &filter, &why)) return fail(RouterError::Kind::ParseError, why);
+            has_filter = true;
+            tail.clear();
+            break;
+        }
         if (K == "LIMIT" && stage <= 0) {
             std::string n;
             split_first(r2, &n, &tail);
@@ -266,10 +273,14 @@ RouterOutcome QueryRouter::execute_parsed(const std::string &command_in) {
         if (g.is_err()) return from_vector_error(g.error());
         q = g.value();
     }
-    // QR:5385-5447 (no filter): collection -> search_in_collection (its own metric),
-    // otherwise search_similar_with_metric.
-    auto r = has_collection ? vector_.search_in_collection(collection, q, top_k)
-                            : vector_.search_similar_with_metric(q, top_k, metric);
+    // QR:5385-5447: (collection, filter) -> search_filtered_in_collection; (collection) ->
+    // search_in_collection (its own metric); (filter) -> search_similar_filtered; otherwise
+    // search_similar_with_metric.
+    auto r = has_collection
+                 ? (has_filter ? vector_.search_filtered_in_collection(collection, q, top_k, filter)
+                               : vector_.search_in_collection(collection, q, top_k))
+                 : (has_filter ? vector_.search_similar_filtered(q, top_k, filter)
+                               : vector_.search_similar_with_metric(q, top_k, metric));
     if (r.is_err()) return from_vector_error(r.error());
     return ok_similar(r.value());
 }

@@ -120,6 +120,7 @@ struct VectorEngine::Bucket {
     uint32_t dim = 0;
     std::vector<std::string> keys;  // row -> key (mirror order)
     std::vector<float> rows;        // host copy, row-major
+    std::vector<Metadata> meta;     // row -> metadata fields (empty map when none were stored)
     nm_index *mirror = nullptr;     // device mirror, created at the first search
     uint64_t synced_rows = 0;       // rows [0, synced_rows) are on the device
     std::mutex sync_mu;             // serialises lazy appends issued by concurrent searches
@@ -156,7 +157,7 @@ bool VectorEngine::should_use_sparse(const std::vector<float> &v) const {
 }
 
 Result<Unit> VectorEngine::store_in_space(Space &sp, const std::string &key,
-                                          std::vector<float> vector) {
+                                          std::vector<float> vector, const Metadata *metadata) {
     // Sparse storage round-trips through SparseVector::from_dense / to_dense
     // (tensor_store/src/sparse_vector.rs:212-229, 400-406): entries == 0.0 are dropped and come
     // back as +0.0, so -0.0 loses its sign; everything else (incl. NaN) is preserved.
@@ -182,6 +183,8 @@ Result<Unit> VectorEngine::store_in_space(Space &sp, const std::string &key,
     if (it != sp.where.end()) {
         uint64_t row = it->second.second;
         std::memcpy(&b.rows[row * dim], vector.data(), (size_t)dim * 4);
+        // store.put replaces the whole TensorData: metadata of the old value is gone
+        b.meta[row] = metadata ? *metadata : Metadata{};
         if (b.mirror && row < b.synced_rows) {
             int rc = nm_index_update(b.mirror, row, vector.data());
             if (rc) return storage_from_nm(rc);
@@ -190,6 +193,7 @@ Result<Unit> VectorEngine::store_in_space(Space &sp, const std::string &key,
     }
     uint64_t row = b.keys.size();
     b.keys.push_back(key);
+    b.meta.push_back(metadata ? *metadata : Metadata{});
     b.rows.insert(b.rows.end(), vector.begin(), vector.end());
     sp.where[key] = {dim, row};
     return Unit{};  // the device append is deferred to the next search (batched)
@@ -219,9 +223,11 @@ Result<Unit> VectorEngine::delete_in_space(Space &sp, const std::string &key) {
     if (row != last) {
         std::memcpy(&b.rows[row * dim], &b.rows[last * dim], (size_t)dim * 4);
         b.keys[row] = std::move(b.keys[last]);
+        b.meta[row] = std::move(b.meta[last]);
         sp.where[b.keys[row]] = {dim, row};
     }
     b.keys.pop_back();
+    b.meta.pop_back();
     b.rows.resize(b.keys.size() * (size_t)dim);
     sp.where.erase(key);
     if (b.keys.empty()) sp.buckets.erase(dim);
@@ -241,7 +247,8 @@ Result<std::vector<float>> VectorEngine::get_in_space(const Space &sp,
 // The seam of SURVEY 8b: "store.scan -> search_* -> sort_by -> truncate" becomes one nm_search.
 Result<std::vector<SearchResult>> VectorEngine::scan_space(
     const Space &sp, const std::vector<float> &query, size_t top_k, DistanceMetric metric,
-    const char *operation, std::chrono::steady_clock::time_point start) const {
+    const char *operation, std::chrono::steady_clock::time_point start,
+    const FilterCondition *pre_filter) const {
     auto expired = [&]() {
         if (!config_.search_timeout) return false;
         return std::chrono::steady_clock::now() - start >= *config_.search_timeout;
@@ -260,6 +267,19 @@ Result<std::vector<SearchResult>> VectorEngine::scan_space(
     if (bit == sp.buckets.end() || bit->second->keys.empty())
         return std::vector<SearchResult>{};  // rows of other dimensions are skipped
     Bucket &b = *bit->second;
+    // "filter first, then search the subset" (lib.rs:3514-3557): the subset is a row bitmask;
+    // an empty subset never reaches the device
+    std::vector<uint64_t> mask;
+    if (pre_filter) {
+        mask.assign((b.keys.size() + 63) / 64, 0ull);
+        size_t eligible = 0;
+        for (size_t r = 0; r < b.keys.size(); ++r)
+            if (evaluate_filter(b.meta[r], *pre_filter)) {
+                mask[r >> 6] |= 1ull << (r & 63);
+                ++eligible;
+            }
+        if (eligible == 0) return std::vector<SearchResult>{};
+    }
     {
         std::lock_guard<std::mutex> sg(b.sync_mu);
         if (!b.mirror) {
@@ -280,8 +300,14 @@ Result<std::vector<SearchResult>> VectorEngine::scan_space(
     std::vector<uint64_t> rows(k);
     std::vector<float> scores(k);
     uint32_t count = 0;
-    int rc = nm_search(b.mirror, query.data(), 1, (uint32_t)k, (int)metric, rows.data(),
+    int rc;
+    if (pre_filter) {
+        rc = nm_search_masked(b.mirror, query.data(), 1, (uint32_t)k, (int)metric, mask.data(),
+                              rows.data(), scores.data(), &count);
+    } else {
+        rc = nm_search(b.mirror, query.data(), 1, (uint32_t)k, (int)metric, rows.data(),
                        scores.data(), &count);
+    }
     if (rc) return storage_from_nm(rc);
     // second deadline check: after scoring (lib.rs:2019-2024)
     if (expired()) return timeout_err();
@@ -500,6 +526,187 @@ Result<std::vector<SearchResult>> VectorEngine::search_in_collection(
         return std::vector<SearchResult>{};
     if (!sp) return std::vector<SearchResult>{};
     return scan_space(*sp, query, top_k, metric, "search_in_collection", start);
+}
+
+// ---- metadata + filtered search ----
+Result<Unit> VectorEngine::store_embedding_with_metadata(const std::string &key,
+                                                         std::vector<float> vector,
+                                                         Metadata metadata) {
+    if (vector.empty()) return err(ErrorKind::EmptyVector);
+    if (config_.max_dimension && vector.size() > *config_.max_dimension)
+        return dim_mismatch(*config_.max_dimension, vector.size());
+    return store_in_space(*default_space_, key, std::move(vector), &metadata);
+}
+
+Result<Metadata> VectorEngine::get_metadata(const std::string &key) const {
+    const Space &sp = *default_space_;
+    std::shared_lock<std::shared_mutex> g(sp.mu);
+    auto it = sp.where.find(key);
+    if (it == sp.where.end()) return err(ErrorKind::NotFound, key);
+    return sp.buckets.at(it->second.first)->meta[it->second.second];
+}
+
+Result<Unit> VectorEngine::store_in_collection_with_metadata(const std::string &collection,
+                                                             const std::string &key,
+                                                             std::vector<float> vector,
+                                                             Metadata metadata) {
+    if (vector.empty()) return err(ErrorKind::EmptyVector);
+    {
+        std::shared_lock<std::shared_mutex> g(collections_mu_);
+        auto it = collections_.find(collection);
+        if (it != collections_.end() && it->second->config && it->second->config->dimension &&
+            vector.size() != *it->second->config->dimension)
+            return dim_mismatch(*it->second->config->dimension, vector.size());
+    }
+    if (config_.max_dimension && vector.size() > *config_.max_dimension)
+        return dim_mismatch(*config_.max_dimension, vector.size());
+    return store_in_space(collection_space(collection), key, std::move(vector), &metadata);
+}
+
+namespace {
+// the reference samples the first min(100, n) keys of an (unordered) key listing
+template <class SpaceT>
+float sample_selectivity(const SpaceT &sp, const FilterCondition &f) {
+    size_t seen = 0, hit = 0;
+    for (auto &kv : sp.buckets)
+        for (size_t r = 0; r < kv.second->keys.size() && seen < 100; ++r, ++seen)
+            if (evaluate_filter(kv.second->meta[r], f)) ++hit;
+    return seen ? (float)hit / (float)seen : -1.0f;
+}
+}  // namespace
+
+Result<std::vector<SearchResult>> VectorEngine::filtered_in_space(
+    const Space *sp, const std::vector<float> &query, size_t top_k, DistanceMetric post_metric,
+    const FilterCondition &filter, const FilteredSearchConfig &cfg, const char *operation,
+    std::chrono::steady_clock::time_point start) const {
+    FilterStrategy strategy = cfg.strategy;
+    if (strategy == FilterStrategy::Auto) {
+        // choose_filter_strategy (lib.rs:3485-3511): True -> post; empty -> post; else sample
+        strategy = FilterStrategy::PostFilter;
+        if (filter.op != FilterCondition::Op::True && sp) {
+            std::shared_lock<std::shared_mutex> g(sp->mu);
+            float sel = sample_selectivity(*sp, filter);
+            if (sel >= 0.0f && sel < cfg.selectivity_threshold) strategy = FilterStrategy::PreFilter;
+        }
+    }
+    if (config_.search_timeout && std::chrono::steady_clock::now() - start >= *config_.search_timeout) {
+        VectorError e;
+        e.kind = ErrorKind::SearchTimeout;
+        e.operation = operation;
+        e.timeout_ms = (uint64_t)config_.search_timeout->count();
+        return e;
+    }
+    if (!sp) return std::vector<SearchResult>{};
+    if (strategy == FilterStrategy::PreFilter) {
+        // always cosine, zero query -> empty (lib.rs:3520-3523, 1775-1790)
+        if (simd::magnitude(query.data(), query.size()) == 0.0f) return std::vector<SearchResult>{};
+        return scan_space(*sp, query, top_k, DistanceMetric::Cosine, operation, start, &filter);
+    }
+    // post-filter: oversample, then filter, then take top_k (lib.rs:3560-3578, 1792-1812)
+    size_t oversample_k = top_k * cfg.oversample_factor;
+    if (cfg.oversample_factor != 0 && oversample_k / cfg.oversample_factor != top_k)
+        oversample_k = SIZE_MAX;  // saturating_mul
+    oversample_k = std::max(oversample_k, top_k);
+    if (post_metric == DistanceMetric::Cosine &&
+        simd::magnitude(query.data(), query.size()) == 0.0f)
+        return std::vector<SearchResult>{};
+    auto cand = scan_space(*sp, query, oversample_k, post_metric, operation, start);
+    if (cand.is_err()) return cand;
+    std::vector<SearchResult> out;
+    std::shared_lock<std::shared_mutex> g(sp->mu);
+    for (auto &r : cand.value()) {
+        auto it = sp->where.find(r.key);
+        if (it == sp->where.end()) continue;
+        if (evaluate_filter(sp->buckets.at(it->second.first)->meta[it->second.second], filter)) {
+            out.push_back(r);
+            if (out.size() == top_k) break;
+        }
+    }
+    return out;
+}
+
+Result<std::vector<SearchResult>> VectorEngine::search_similar_filtered(
+    const std::vector<float> &query, size_t top_k, const FilterCondition &filter,
+    std::optional<FilteredSearchConfig> config) const {
+    auto start = std::chrono::steady_clock::now();
+    if (query.empty()) return err(ErrorKind::EmptyVector);
+    if (top_k == 0) return err(ErrorKind::InvalidTopK);
+    if (config_.max_dimension && query.size() > *config_.max_dimension)
+        return dim_mismatch(*config_.max_dimension, query.size());
+    return filtered_in_space(default_space_.get(), query, top_k, DistanceMetric::Cosine, filter,
+                             config.value_or(FilteredSearchConfig{}), "search_similar_filtered",
+                             start);
+}
+
+Result<std::vector<SearchResult>> VectorEngine::search_filtered_in_collection(
+    const std::string &collection, const std::vector<float> &query, size_t top_k,
+    const FilterCondition &filter, std::optional<FilteredSearchConfig> config) const {
+    auto start = std::chrono::steady_clock::now();
+    if (query.empty()) return err(ErrorKind::EmptyVector);
+    if (top_k == 0) return err(ErrorKind::InvalidTopK);
+    DistanceMetric metric = DistanceMetric::Cosine;
+    const Space *sp = nullptr;
+    {
+        std::shared_lock<std::shared_mutex> g(collections_mu_);
+        auto it = collections_.find(collection);
+        if (it != collections_.end()) {
+            if (it->second->config) {
+                if (it->second->config->dimension &&
+                    query.size() != *it->second->config->dimension)
+                    return dim_mismatch(*it->second->config->dimension, query.size());
+                metric = it->second->config->distance_metric;
+            }
+            sp = it->second->space.get();
+        }
+    }
+    // zero query -> empty for every metric on this path (lib.rs:1729-1732)
+    if (simd::magnitude(query.data(), query.size()) == 0.0f) return std::vector<SearchResult>{};
+    return filtered_in_space(sp, query, top_k, metric, filter,
+                             config.value_or(FilteredSearchConfig{}),
+                             "search_filtered_in_collection", start);
+}
+
+float VectorEngine::estimate_filter_selectivity(const FilterCondition &filter) const {
+    std::shared_lock<std::shared_mutex> g(default_space_->mu);
+    float s = sample_selectivity(*default_space_, filter);
+    return s < 0.0f ? 0.0f : s;
+}
+
+size_t VectorEngine::count_matching(const FilterCondition &filter) const {
+    return list_keys_matching(filter).size();
+}
+
+std::vector<std::string> VectorEngine::list_keys_matching(const FilterCondition &filter) const {
+    std::vector<std::string> out;
+    std::shared_lock<std::shared_mutex> g(default_space_->mu);
+    for (auto &kv : default_space_->buckets)
+        for (size_t r = 0; r < kv.second->keys.size(); ++r)
+            if (evaluate_filter(kv.second->meta[r], filter)) out.push_back(kv.second->keys[r]);
+    return out;
+}
+
+// neumann_server/src/service/points.rs:449-485
+Result<std::vector<VectorEngine::ScoredPoint>> VectorEngine::query_points(
+    const std::string &collection, const std::vector<float> &vector, size_t limit, size_t offset,
+    std::optional<float> score_threshold, bool with_vector) const {
+    limit = std::max<size_t>(limit, 1);
+    size_t want = limit + offset;
+    if (want < limit) want = SIZE_MAX;  // saturating_add
+    auto items = search_in_collection(collection, vector, want);
+    if (items.is_err()) return items.error();
+    std::vector<ScoredPoint> out;
+    size_t taken = 0;
+    for (size_t i = offset; i < items.value().size() && taken < limit; ++i, ++taken) {
+        const SearchResult &it = items.value()[i];
+        if (score_threshold && it.score < *score_threshold) continue;
+        ScoredPoint p{it.key, it.score, {}};
+        if (with_vector) {
+            auto v = get_from_collection(collection, it.key);
+            if (v.is_ok()) p.vector = v.value();
+        }
+        out.push_back(std::move(p));
+    }
+    return out;
 }
 
 std::vector<VectorEngine::MirrorInfo> VectorEngine::mirror_info() const {

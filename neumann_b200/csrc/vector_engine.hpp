@@ -18,6 +18,8 @@
 #include <unordered_map>
 #include <vector>
 
+#include "filter.hpp"
+
 struct nm_index;
 
 namespace neumann {
@@ -130,6 +132,37 @@ class VectorEngine {
     Result<std::vector<SearchResult>> search_similar_with_metric(const std::vector<float> &query,
                                                                  size_t top_k,
                                                                  DistanceMetric metric) const;
+    // metadata + filtered search: lib.rs:2930-3010 (store/get metadata), :3429-3557
+    // (search_similar_filtered, pre/post filter), :1698-1829 (search_filtered_in_collection),
+    // :3690-3735 (selectivity / count / list).  Pre-filter = device scan under a row bitmask.
+    Result<Unit> store_embedding_with_metadata(const std::string &key, std::vector<float> vector,
+                                               Metadata metadata);
+    Result<Metadata> get_metadata(const std::string &key) const;
+    Result<std::vector<SearchResult>> search_similar_filtered(
+        const std::vector<float> &query, size_t top_k, const FilterCondition &filter,
+        std::optional<FilteredSearchConfig> config = std::nullopt) const;
+    Result<Unit> store_in_collection_with_metadata(const std::string &collection,
+                                                   const std::string &key, std::vector<float> vector,
+                                                   Metadata metadata);
+    Result<std::vector<SearchResult>> search_filtered_in_collection(
+        const std::string &collection, const std::vector<float> &query, size_t top_k,
+        const FilterCondition &filter, std::optional<FilteredSearchConfig> config = std::nullopt) const;
+    float estimate_filter_selectivity(const FilterCondition &filter) const;
+    size_t count_matching(const FilterCondition &filter) const;
+    std::vector<std::string> list_keys_matching(const FilterCondition &filter) const;
+
+    // gRPC PointsService::query post-processing (neumann_server/src/service/points.rs:449-485):
+    // search limit+offset, skip offset, take limit, drop hits below score_threshold.
+    struct ScoredPoint {
+        std::string id;
+        float score;
+        std::vector<float> vector;  // filled when with_vector
+    };
+    Result<std::vector<ScoredPoint>> query_points(const std::string &collection,
+                                                  const std::vector<float> &vector, size_t limit,
+                                                  size_t offset, std::optional<float> score_threshold,
+                                                  bool with_vector) const;
+
     // lib.rs:2277-2295
     static Result<float> compute_similarity(const std::vector<float> &a,
                                             const std::vector<float> &b);
@@ -170,13 +203,19 @@ class VectorEngine {
     const Space *find_collection_space(const std::string &name) const;
 
     bool should_use_sparse(const std::vector<float> &v) const;  // lib.rs:1871-1886
-    Result<Unit> store_in_space(Space &sp, const std::string &key, std::vector<float> vector);
+    Result<Unit> store_in_space(Space &sp, const std::string &key, std::vector<float> vector,
+                                const Metadata *metadata = nullptr);
+    Result<std::vector<SearchResult>> filtered_in_space(
+        const Space *sp, const std::vector<float> &query, size_t top_k, DistanceMetric post_metric,
+        const FilterCondition &filter, const FilteredSearchConfig &cfg, const char *operation,
+        std::chrono::steady_clock::time_point start) const;
     Result<Unit> delete_in_space(Space &sp, const std::string &key);
     Result<std::vector<float>> get_in_space(const Space &sp, const std::string &key) const;
     Result<std::vector<SearchResult>> scan_space(const Space &sp, const std::vector<float> &query,
                                                  size_t top_k, DistanceMetric metric,
                                                  const char *operation,
-                                                 std::chrono::steady_clock::time_point start) const;
+                                                 std::chrono::steady_clock::time_point start,
+                                                 const FilterCondition *pre_filter = nullptr) const;
 };
 
 }  // namespace neumann

@@ -12,6 +12,25 @@ import numpy as np
 from . import _ffi
 
 COSINE, EUCLIDEAN, DOT_PRODUCT = 0, 1, 2
+AUTO, PRE_FILTER, POST_FILTER = 0, 1, 2
+
+
+def encode_metadata(meta: dict | None) -> bytes:
+    """dict -> the typed wire string of include/neumann_b200_engine.h."""
+    recs = []
+    for name, v in (meta or {}).items():
+        if v is None:
+            t, val = "n", ""
+        elif isinstance(v, bool):
+            t, val = "b", "1" if v else "0"
+        elif isinstance(v, int):
+            t, val = "i", str(v)
+        elif isinstance(v, float):
+            t, val = "f", repr(v)
+        else:
+            t, val = "s", str(v)
+        recs.append(f"{name}\x1e{t}\x1e{val}")
+    return "\x1f".join(recs).encode()
 
 
 class NmEngineConfig(C.Structure):
@@ -45,6 +64,12 @@ ENGINE_SIGNATURES = {
     "nm_engine_delete_from_collection": (C.c_int, [_vp, _cp, _cp]),
     "nm_engine_collection_count": (_u64, [_vp, _cp]),
     "nm_engine_search_in_collection": (C.c_int, [_vp, _cp, _vp, _sz, _sz, _pvp]),
+    "nm_engine_store_embedding_with_metadata": (C.c_int, [_vp, _cp, _vp, _sz, _cp]),
+    "nm_engine_store_in_collection_with_metadata": (C.c_int, [_vp, _cp, _cp, _vp, _sz, _cp]),
+    "nm_engine_search_similar_filtered": (C.c_int, [_vp, _vp, _sz, _sz, _cp, C.c_int, _sz, _pvp]),
+    "nm_engine_search_filtered_in_collection": (C.c_int, [_vp, _cp, _vp, _sz, _sz, _cp, C.c_int, _sz, _pvp]),
+    "nm_engine_count_matching": (C.c_int, [_vp, _cp, C.POINTER(_u64)]),
+    "nm_engine_query_points": (C.c_int, [_vp, _cp, _vp, _sz, _sz, _sz, C.c_int, C.c_float, _pvp]),
     "nm_engine_execute": (C.c_int, [_vp, _cp, _pvp]),
     "nm_engine_execute_parsed": (C.c_int, [_vp, _cp, _pvp]),
     "nm_engine_mirror_rows": (C.c_int, [_vp, C.c_uint32, C.POINTER(_u64), C.POINTER(_u64)]),
@@ -211,6 +236,49 @@ class VectorEngine:
         h = C.c_void_p()
         _check(_lib().nm_engine_search_in_collection(self._h, collection.encode(), q.ctypes.data,
                                                      q.size, top_k, C.byref(h)))
+        return _take(h)
+
+    # ---- metadata + filtered search ----
+    def store_embedding_with_metadata(self, key: str, vector, metadata: dict) -> None:
+        v = _f32(vector)
+        _check(_lib().nm_engine_store_embedding_with_metadata(self._h, key.encode(), v.ctypes.data,
+                                                              v.size, encode_metadata(metadata)))
+
+    def store_in_collection_with_metadata(self, collection: str, key: str, vector, metadata: dict):
+        v = _f32(vector)
+        _check(_lib().nm_engine_store_in_collection_with_metadata(
+            self._h, collection.encode(), key.encode(), v.ctypes.data, v.size, encode_metadata(metadata)))
+
+    def search_similar_filtered(self, query, top_k: int, where: str, strategy: int = AUTO,
+                                oversample_factor: int = 0) -> list[SearchResult]:
+        q = _f32(query)
+        h = C.c_void_p()
+        _check(_lib().nm_engine_search_similar_filtered(self._h, q.ctypes.data, q.size, top_k,
+                                                        where.encode(), strategy, oversample_factor,
+                                                        C.byref(h)))
+        return _take(h)
+
+    def search_filtered_in_collection(self, collection: str, query, top_k: int, where: str,
+                                      strategy: int = AUTO, oversample_factor: int = 0):
+        q = _f32(query)
+        h = C.c_void_p()
+        _check(_lib().nm_engine_search_filtered_in_collection(
+            self._h, collection.encode(), q.ctypes.data, q.size, top_k, where.encode(), strategy,
+            oversample_factor, C.byref(h)))
+        return _take(h)
+
+    def count_matching(self, where: str) -> int:
+        n = C.c_uint64()
+        _check(_lib().nm_engine_count_matching(self._h, where.encode(), C.byref(n)))
+        return int(n.value)
+
+    def query_points(self, collection: str, vector, limit: int, offset: int = 0,
+                     score_threshold: float | None = None) -> list[SearchResult]:
+        q = _f32(vector)
+        h = C.c_void_p()
+        _check(_lib().nm_engine_query_points(self._h, collection.encode(), q.ctypes.data, q.size,
+                                             limit, offset, 0 if score_threshold is None else 1,
+                                             score_threshold or 0.0, C.byref(h)))
         return _take(h)
 
     # ---- router ----

@@ -102,6 +102,24 @@ class DeviceIndex:
                                    rows.ctypes.data, scores.ctypes.data, counts.ctypes.data))
         return [(rows[i, :counts[i]].copy(), scores[i, :counts[i]].copy()) for i in range(nq)]
 
+    def search_masked(self, queries: np.ndarray, k: int, metric, mask: np.ndarray):
+        """mask: bool array over rows (True = eligible).  -> like search()."""
+        q = np.ascontiguousarray(queries, dtype=np.float32)
+        if q.ndim == 1:
+            q = q.reshape(1, -1)
+        nq = q.shape[0]
+        bits = np.packbits(np.asarray(mask, dtype=bool), bitorder="little")
+        words = np.zeros((bits.size + 7) // 8 + 1, np.uint64)
+        words.view(np.uint8)[:bits.size] = bits
+        kk = max(int(k), 1)
+        rows = np.zeros((nq, kk), np.uint64)
+        scores = np.zeros((nq, kk), np.float32)
+        counts = np.zeros(nq, np.uint32)
+        check(_ffi.lib().nm_search_masked(self._h, q.ctypes.data, nq, int(k), _metric(metric),
+                                          words.ctypes.data, rows.ctypes.data, scores.ctypes.data,
+                                          counts.ctypes.data))
+        return [(rows[i, :counts[i]].copy(), scores[i, :counts[i]].copy()) for i in range(nq)]
+
     def search_device(self, d_queries_ptr: int, nq: int, k: int, metric, d_rows_ptr: int,
                       d_scores_ptr: int, d_counts_ptr: int, stream_ptr: int = 0) -> None:
         check(_ffi.lib().nm_search_device(self._h, d_queries_ptr, nq, k, _metric(metric),

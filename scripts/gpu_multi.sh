@@ -16,3 +16,13 @@ for n in 1 2 4 8; do
     tail -c 1500 gpurun_out/scale_$n.json; tail -5 gpurun_out/scale_$n.err
   fi
 done
+if [ $N -ge 8 ]; then
+  # A/B: same strong-scaling point through ncclAllGather + merge kernel instead of the fused exchange
+  NM_DISABLE_PEER_EXCHANGE=1 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29512 \
+      bench.py --gpus 8 --steps 100 --warmup 10 > gpurun_out/scale_8_nccl.json 2> gpurun_out/scale_8_nccl.err
+  tail -c 600 gpurun_out/scale_8_nccl.json
+  # BASELINE config 5: 80M x 768 over 8 GPUs (10M rows per GPU)
+  timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29513 \
+      bench.py --gpus 8 --steps 100 --warmup 10 --scaling weak > gpurun_out/weak_8.json 2> gpurun_out/weak_8.err
+  tail -c 1200 gpurun_out/weak_8.json; tail -3 gpurun_out/weak_8.err
+fi

@@ -197,3 +197,63 @@ def test_concurrent_search_and_store():
     assert not errors, errors[:3]
     assert e.count() == 4000
     assert e.search_similar(rows[3999], 1)[0].key == "k3999"
+
+
+# ---- filtered search (vector_engine/src/lib.rs:6968-7720) and PointsService::query ----------
+from test_filter_cpu import setup_filtered_search_engine  # noqa: E402
+
+
+@pytest.mark.parametrize("strategy", [eng.AUTO, eng.PRE_FILTER, eng.POST_FILTER])
+def test_search_filtered_reference_kats(strategy):
+    e = setup_filtered_search_engine()
+    q = [1.0, 1.0, 1.0]
+    r = e.search_similar_filtered(q, 10, "category = 'electronics'", strategy)
+    assert [x.key for x in r] == ["item0"]                       # :7004-7017
+    r = e.search_similar_filtered([1.0, 0.0, 0.0], 10, "price = 50", strategy)
+    assert [x.key for x in r] == ["item1"]                       # :7020-7030
+    assert len(e.search_similar_filtered(q, 10, "price > 30", strategy)) == 2
+    r = e.search_similar_filtered(q, 10, "price > 30 AND price < 80", strategy)
+    assert [x.key for x in r] == ["item1"]                       # :7083-7095
+    assert len(e.search_similar_filtered(q, 10, "TRUE", strategy)) == 3   # :7117
+    assert e.search_similar_filtered(q, 10, "price > 1000", strategy) == []  # :7322
+    assert len(e.search_similar_filtered(q, 1, "price > 30", strategy)) == 1  # respects top_k :7701
+
+
+def test_pre_filter_matches_oracle_on_subset_and_post_filter_oversamples():
+    e = eng.VectorEngine()
+    rows = o.fill_synthetic(5000, 32, 77)
+    for i in range(5000):
+        e.store_embedding_with_metadata(f"k{i}", rows[i], {"bucket": i % 50, "name": f"n{i:05d}"})
+    q = o.fill_synthetic(1, 32, 78)[0]
+    sub = np.nonzero(np.arange(5000) % 50 == 7)[0]
+    er, es = o.search(rows[sub], q, 10, "cosine")
+    r = e.search_similar_filtered(q, 10, "bucket = 7", eng.PRE_FILTER)
+    assert [x.key for x in r] == [f"k{int(sub[int(i)])}" for i in er]
+    assert [np.float32(x.score).view(np.uint32) for x in r] == list(es.view(np.uint32))
+    assert [x.key for x in e.search_similar_filtered(q, 10, "bucket = 7")] == [x.key for x in r]  # auto -> pre (2 % selective)
+    # post-filter: filter(top (k*oversample)) — approximate by design (lib.rs:3560-3578)
+    gr, _ = o.search(rows, q, 30, "cosine")
+    want = [f"k{int(i)}" for i in gr if int(i) % 2 == 0][:10]
+    r = e.search_similar_filtered(q, 10, "bucket IN (0,2,4,6,8,10,12,14,16,18,20,22,24,26,28,30,32,34,36,38,40,42,44,46,48)",
+                                  eng.POST_FILTER, oversample_factor=3)
+    assert [x.key for x in r] == want
+    r = e.execute_parsed("SIMILAR 'k7' LIMIT 3 WHERE bucket = 7 AND name >= 'n00007'")
+    assert r[0].key == "k7" and all(int(x.key[1:]) % 50 == 7 for x in r)
+
+
+def test_search_filtered_in_collection_and_query_points():
+    e = eng.VectorEngine()
+    e.create_collection("docs", dimension=3, metric=eng.COSINE)
+    for i in range(20):
+        e.store_in_collection_with_metadata("docs", f"d{i}", [1.0, float(i), 0.5], {"even": i % 2 == 0})
+    r = e.search_filtered_in_collection("docs", [1.0, 0.0, 0.5], 3, "even = true", eng.PRE_FILTER)
+    assert [x.key for x in r] == ["d0", "d2", "d4"]
+    r = e.execute_parsed("SIMILAR [1.0, 0.0, 0.5] LIMIT 2 INTO docs WHERE even = false")
+    assert [x.key for x in r] == ["d1", "d3"]
+    # points.rs:449-485: search(limit+offset) -> skip(offset) -> take(limit) -> threshold
+    full = e.search_in_collection("docs", [1.0, 0.0, 0.5], 20)
+    page = e.query_points("docs", [1.0, 0.0, 0.5], limit=5, offset=3)
+    assert [x.key for x in page] == [x.key for x in full[3:8]]
+    thr = full[5].score
+    page = e.query_points("docs", [1.0, 0.0, 0.5], limit=10, offset=0, score_threshold=thr)
+    assert [x.key for x in page] == [x.key for x in full[:10] if x.score >= thr]

@@ -62,7 +62,22 @@ def _nccl_worker(rank, world, port, q):
                 er, es = o.search(rows, qs[i], k, metric, threads=4)
                 assert np.array_equal(res[i][0], er), (metric, i, res[i][0], er)
                 assert np.array_equal(res[i][1].view(np.uint32), es.view(np.uint32))
-        assert idx.stats().merge_launches == 3
+        fused = os.environ.get("NM_DISABLE_PEER_EXCHANGE") != "1"
+        # single queries: fused scan+exchange+merge launches (no separate merge kernel);
+        # with the exchange disabled: one merge_shards_kernel per search call
+        assert idx.stats().merge_launches == (0 if fused else 3)
+        # a batch of 9 queries takes the batched kernels + ONE ncclAllGather + merge kernel
+        qb = o.fill_synthetic(9, d, 0xBA7C)
+        res = idx.search(qb, k, "euclidean")
+        for i in range(9):
+            er, es = o.search(rows, qb[i], k, "euclidean", threads=4)
+            assert np.array_equal(res[i][0], er), ("batched", i)
+            assert np.array_equal(res[i][1].view(np.uint32), es.view(np.uint32))
+        assert idx.stats().merge_launches == (1 if fused else 4)
+        # k larger than a shard (and than the fast limit): chained passes + NCCL path
+        res = idx.search(qs[:1], 1500, "cosine")
+        er, es = o.search(rows, qs[0], 1500, "cosine", threads=4)
+        assert np.array_equal(res[0][0], er) and np.array_equal(res[0][1].view(np.uint32), es.view(np.uint32))
         idx.detach_comm()
         idx.close()
         q.put((rank, "ok"))
@@ -71,6 +86,59 @@ def _nccl_worker(rank, world, port, q):
         q.put((rank, traceback.format_exc()))
     finally:
         dist.destroy_process_group()
+
+
+def _empty_shard_worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+    from neumann_b200 import dist as nd
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank),
+                      WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        # 3 rows over 2 ranks -> rank 0 holds 1 row, rank 1 holds 2; then rank 0 is emptied
+        d = 16
+        rows = o.fill_synthetic(2, d, 5, row_offset=0)
+        idx = DeviceIndex(d, devices=[rank])
+        nd.attach_index(idx, 2)      # bounds: rank0 [0,1) rank1 [1,2)
+        if rank == 1:
+            idx.load(rows[1:2])
+        res = idx.search(rows[1], 5, "cosine")      # rank 0's shard is EMPTY
+        assert list(res[0][0]) == [1] and abs(float(res[0][1][0]) - 1.0) < 1e-6
+        idx.detach_comm()
+        idx.close()
+        q.put((rank, "ok"))
+    except Exception:  # noqa: BLE001
+        import traceback
+        q.put((rank, traceback.format_exc()))
+    finally:
+        dist.destroy_process_group()
+
+
+def _spawn(target, world):
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=target, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=600) for _ in procs]
+    for p in procs:
+        p.join(timeout=120)
+    assert sorted(res) == [(r, "ok") for r in range(world)], res
+
+
+def test_collective_with_an_empty_shard():
+    _need(2)
+    _spawn(_empty_shard_worker, 2)
+
+
+def test_nccl_fallback_when_peer_exchange_disabled(monkeypatch):
+    _need(2)
+    monkeypatch.setenv("NM_DISABLE_PEER_EXCHANGE", "1")
+    _spawn(_nccl_worker, 2)
 
 
 @pytest.mark.parametrize("world", [2, 4, 8])

@@ -243,6 +243,34 @@ def test_batched_queries_share_one_pass(metric, n, dim, nq, k):
     idx.close()
 
 
+@pytest.mark.parametrize("metric", METRICS)
+def test_masked_search_equals_oracle_on_the_subset(metric):
+    """nm_search_masked == the oracle run on only the eligible rows (search_with_pre_filter,
+    vector_engine/src/lib.rs:3514-3557), for dense, sparse, clustered, single-row and empty
+    masks (clustered masks exercise the 'skip whole row blocks' path)."""
+    n, d, k = 40000, 48, 20
+    idx, rows = synth_index(n, d)
+    q = o.fill_synthetic(1, d, 0x5EED1001)[0]
+    rng = np.random.default_rng(3)
+    masks = {
+        "half": rng.random(n) < 0.5,
+        "one_percent": rng.random(n) < 0.01,
+        "clustered": (np.arange(n) // 1000) % 7 == 3,
+        "single": np.arange(n) == 31337,
+        "fewer_than_k": np.isin(np.arange(n), [5, 300, 39999]),
+        "all": np.ones(n, bool),
+    }
+    for name, m in masks.items():
+        sub = np.nonzero(m)[0]
+        er, es = o.search(rows[sub], q, k, metric, threads=4)
+        ((gr, gs),) = idx.search_masked(q, k, metric, m)
+        assert np.array_equal(gr, sub[er.astype(np.int64)].astype(np.uint64)), (name, gr[:5])
+        assert np.array_equal(gs.view(np.uint32), es.view(np.uint32)), name
+    ((gr, gs),) = idx.search_masked(q, k, metric, np.zeros(n, bool))
+    assert len(gr) == 0
+    idx.close()
+
+
 def test_mirror_mutations_load_append_update_swap_remove():
     d = 40
     host = o.fill_synthetic(5000, d, 21)
