@@ -46,6 +46,8 @@ def parse_args():
     ap.add_argument("--queries", type=int, default=16, help="distinct queries cycled over steps")
     ap.add_argument("--cpu-sample-rows", type=int, default=1_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-staging", action="store_true")
+    ap.add_argument("--staging-rows", type=int, default=500_000)
     return ap.parse_args()
 
 
@@ -309,6 +311,28 @@ def run_ours(a):
             dist.destroy_process_group()
         return
 
+    # ---- staging (reported, not part of the metric): host -> device load of a corpus slice
+    #      through nm_index_load, pinned (direct DMA) and pageable (double-buffered pinned
+    #      staging inside the library) ----
+    staging = None
+    if world == 1 and not a.no_staging:
+        try:
+            srows = min(a.staging_rows, local_rows)
+            host_pinned = torch.empty((srows, a.dim), dtype=torch.float32).pin_memory()
+            host_pinned.uniform_(-1, 1)
+            pageable = host_pinned.numpy().copy()
+            sidx = DeviceIndex(a.dim, devices=[local_rank])
+            sidx.load(host_pinned.numpy()[:1024])  # warm (allocations, staging buffers)
+            t0 = time.perf_counter(); sidx.load(host_pinned.numpy()); t_pin = time.perf_counter() - t0
+            t0 = time.perf_counter(); sidx.load(pageable); t_page = time.perf_counter() - t0
+            gb = srows * a.dim * 4 / 1e9
+            staging = {"rows": srows, "GB": gb, "pinned_GBps": gb / t_pin, "pageable_GBps": gb / t_page,
+                       "note": "nm_index_load wall time; pageable source goes through two 32 MiB "
+                               "pinned staging buffers (memcpy of chunk i+1 overlaps DMA of chunk i)"}
+            sidx.close()
+        except Exception as e:  # noqa: BLE001
+            staging = {"error": repr(e)}
+
     line = {
         "metric": METRIC_NAME, "value": value, "unit": "queries/s", "n_gpus": world,
         "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms_per_step,
@@ -345,6 +369,8 @@ def run_ours(a):
                 line["roofline"]["traffic"] = t.get("dram_bytes_per_launch")
         except Exception:  # noqa: BLE001
             pass
+    if staging is not None:
+        line["staging"] = staging
     if world == 1 and not a.no_cpu_baseline:
         base = cpu_reference_qps(a, total_rows, steps=5, warmup=1, budget_s=30.0)
         base.pop("_t_full_s")
