@@ -351,6 +351,31 @@ def test_stats_counters():
     idx.close()
 
 
+@pytest.mark.parametrize("metric", METRICS)
+def test_parity_gate_1000_queries_with_tie_stress(metric):
+    """SURVEY 8d parity gate: >= 1000 queries per metric on a corpus with 1 % duplicated rows
+    (exact ties); ids position by position, scores bit for bit.  1000 queries ride the batched
+    kernels, the first 40 are repeated through single-query scans."""
+    n, d, k = 120_000, 128, 10
+    rows = o.fill_synthetic(n, d, 0x5EED0001)
+    rng = np.random.default_rng(11)
+    dup = rng.choice(n, n // 100, replace=False)
+    rows[dup] = rows[(dup * 7 + 13) % n]
+    idx = DeviceIndex(d)
+    idx.load(rows)
+    qs = o.fill_synthetic(1000, d, 0x5EED1001)
+    qs[::50] = rows[dup[:20]]            # 20 queries that hit a tie group exactly
+    res = idx.search(qs, k, metric)
+    for i in range(1000):
+        assert_same(res[i], o.search(rows, qs[i], k, metric, threads=16), f"{metric} q{i}")
+    idx.set_batching(False)
+    res1 = idx.search(qs[:40], k, metric)
+    for i in range(40):
+        assert np.array_equal(res1[i][0], res[i][0])
+        assert np.array_equal(res1[i][1].view(np.uint32), res[i][1].view(np.uint32))
+    idx.close()
+
+
 # ---- BASELINE configs at (or near) full size -------------------------------------------------
 def test_config2_1m_x_768_cosine_top10_vs_oracle():
     n, d = 1_000_000, 768
@@ -403,3 +428,36 @@ def test_config3_10m_x_768_cosine_top10_properties():
 
 def test_config4_shape_10m_x_1536_l2_top100_properties():
     _full_size_properties(10_000_000, 1536, 100, "euclidean")
+
+
+def test_config4_batch_256_queries_full_size():
+    """BASELINE config 4 as stated: 10M x 1536, Euclidean, TOP 100, ONE batch of 256 queries
+    (batched kernels).  Checked through size-independent properties on a spread of queries:
+    returned scores re-derived by the oracle from the rows themselves, total-order sortedness,
+    no row of a sampled block beats the 100th hit, and equality with the single-query scan."""
+    import np_ref
+    n, d, k, nq = 10_000_000, 1536, 100, 256
+    idx = DeviceIndex(d)
+    idx.fill_synthetic(n, 0x5EED0001)
+    qs = o.fill_synthetic(nq, d, 0x5EED1001)
+    res = idx.search(qs, k, "euclidean")
+    assert idx.stats().scan_launches == 3 * 4           # 4 passes of 64 queries
+    block_start = 6_543_210
+    block = o.fill_synthetic(40_000, d, 0x5EED0001, row_offset=block_start)
+    for qi in (0, 63, 64, 200, 255):
+        r, s = res[qi]
+        assert len(r) == k
+        ordk = np_ref.orderable(s).astype(np.int64)
+        assert all((ordk[i] > ordk[i + 1]) or (ordk[i] == ordk[i + 1] and r[i] < r[i + 1])
+                   for i in range(k - 1))
+        for i in (0, 1, 50, 99):
+            row = o.fill_synthetic(1, d, 0x5EED0001, row_offset=int(r[i]))[0]
+            assert o.compute_score(qs[qi], row, "euclidean").view(np.uint32) == s[i].view(np.uint32)
+        sc = o.score_rows(block, qs[qi], "euclidean")
+        better = np.nonzero(np_ref.orderable(sc).astype(np.int64) > ordk[-1])[0] + block_start
+        assert set(better.tolist()) <= set(int(x) for x in r)
+    idx.set_batching(False)
+    (single,) = idx.search(qs[200], k, "euclidean")
+    assert np.array_equal(single[0], res[200][0])
+    assert np.array_equal(single[1].view(np.uint32), res[200][1].view(np.uint32))
+    idx.close()
