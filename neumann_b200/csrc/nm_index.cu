@@ -21,6 +21,7 @@
 #include <mutex>
 #include <shared_mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 namespace {
@@ -102,7 +103,28 @@ NcclApi &nccl() {
                         nccl().GetErrorString(_r));                                     \
     } while (0)
 
-constexpr size_t kStagingBytes = 32u << 20;  // per pinned staging buffer (two per shard)
+constexpr size_t kStagingBytes = 64u << 20;  // per pinned staging buffer (two per shard)
+
+// Pageable -> pinned staging copy, split over a few host threads (one core tops out near
+// 11 GB/s, well below what the DMA engine takes from pinned memory).
+void parallel_memcpy(void *dst, const void *src, size_t bytes) {
+    unsigned hw = std::thread::hardware_concurrency();
+    unsigned n = std::min<unsigned>(8u, hw ? hw : 1u);
+    if (bytes < (4u << 20) || n < 2) {
+        memcpy(dst, src, bytes);
+        return;
+    }
+    std::vector<std::thread> th;
+    const size_t per = ((bytes / n) + 4095) & ~size_t(4095);
+    for (unsigned i = 1; i < n; ++i) {
+        size_t off = per * i;
+        if (off >= bytes) break;
+        size_t len = std::min(per, bytes - off);
+        th.emplace_back([=] { memcpy((char *)dst + off, (const char *)src + off, len); });
+    }
+    memcpy(dst, src, std::min(per, bytes));
+    for (auto &t : th) t.join();
+}
 
 // Per-call scratch on one device.  Pooled per shard so concurrent nm_search calls never share
 // a stream, a candidate buffer or the "last CTA" ticket.
@@ -299,7 +321,7 @@ int shard_upload(nm_index *idx, Shard &sh, uint64_t first, const float *src, uin
         for (uint64_t r = 0; r < n; r += rows_per_chunk, b ^= 1) {
             uint64_t m = std::min(rows_per_chunk, n - r);
             CUDA_TRY(cudaEventSynchronize(sh.staging_done[b]));
-            memcpy(sh.staging[b], src + r * idx->dim, m * row_bytes);
+            parallel_memcpy(sh.staging[b], src + r * idx->dim, m * row_bytes);
             CUDA_TRY(cudaMemcpy2DAsync(dst + r * idx->pitch, pitch_bytes, sh.staging[b], row_bytes,
                                        row_bytes, m, cudaMemcpyHostToDevice, sh.copy_stream));
             CUDA_TRY(cudaEventRecord(sh.staging_done[b], sh.copy_stream));
@@ -524,8 +546,19 @@ uint32_t batch_stages() {
     return st;
 }
 
+// Stages the single-query kernel can afford once the whole query sits in shared memory.
+uint32_t single_query_stages(uint32_t dim) {
+    const uint32_t q_floats = (dim + 31u) & ~31u;
+    uint32_t stages = nm::kMaxStages;
+    while (stages > 0 && scan_smem_bytes(stages, q_floats) > 227 * 1024) --stages;
+    return stages;
+}
+
 bool batch_eligible(const nm_index *idx, const Shard &sh, uint32_t nq, uint32_t k, int metric) {
-    if (nq < kBatchMinQueries || sh.rows == 0) return false;
+    // very long vectors: the single-query kernel keeps the query in shared memory and runs out
+    // of stages; the batched kernels stream the query chunk by chunk, so they take over
+    const bool long_rows = single_query_stages(idx->dim) < 4;
+    if ((nq < kBatchMinQueries && !long_rows) || sh.rows == 0) return false;
     if (std::min<uint64_t>(k, sh.rows) > (uint64_t)nm::kMaxFastK) return false;
     // dot/cosine lanes need whole f32x8 groups; the scalar tail only exists on the 1-query path
     if (metric != NM_EUCLIDEAN && (idx->dim % 8u) != 0) return false;
@@ -642,7 +675,8 @@ int scan_queries(nm_index *idx, const Shard &sh, Workspace &ws, const float *d_q
                  uint32_t nq, uint32_t k, int metric, uint64_t row_base, uint64_t *out_rows,
                  float *out_scores, uint32_t *out_counts, nm::ShardHit *out_hits,
                  cudaStream_t stream) {
-    if (idx->batching.load() && batch_eligible(idx, sh, nq, k, metric)) {
+    if ((idx->batching.load() || single_query_stages(idx->dim) < 2) &&
+        batch_eligible(idx, sh, nq, k, metric)) {
         int rc = scan_queries_batched(idx, sh, ws, d_queries, nq, k, metric, row_base, out_rows,
                                       out_scores, out_counts, out_hits, stream);
         if (rc != -1) return rc;
@@ -775,10 +809,39 @@ int validate_search(const nm_index *idx, const void *queries, uint32_t nq, uint3
 }  // namespace
 
 
+// Packed result block device -> pinned host -> caller buffers; one D2H copy, one sync.
+int download_results(nm_index *idx, const Shard &sh, Workspace &ws, const ResultLayout &l,
+                     uint32_t nq, uint32_t k, uint64_t *out_rows, float *out_scores,
+                     uint32_t *out_counts) {
+    CUDA_TRY(cudaMemcpyAsync(ws.h_result, ws.d_result, l.total, cudaMemcpyDeviceToHost, ws.stream));
+    CUDA_TRY(cudaStreamSynchronize(ws.stream));
+    float ms = 0.f;
+    CUDA_TRY(cudaEventElapsedTime(&ms, ws.ev0, ws.ev1));
+    idx->last_scan_ms = ms;
+    const uint32_t *hc = reinterpret_cast<const uint32_t *>(ws.h_result + l.counts_off);
+    const uint64_t *hr = reinterpret_cast<const uint64_t *>(ws.h_result + l.rows_off);
+    const float *hs = reinterpret_cast<const float *>(ws.h_result + l.scores_off);
+    for (uint32_t q = 0; q < nq; ++q) {
+        if (hc[q] == 0xffffffffu)  // poisoned by the exchange watchdog
+            return fail(NM_ERR_STORAGE, "peer exchange timed out waiting for another rank");
+        out_counts[q] = hc[q];
+        memcpy(out_rows + (size_t)q * k, hr + (size_t)q * k, (size_t)hc[q] * 8);
+        memcpy(out_scores + (size_t)q * k, hs + (size_t)q * k, (size_t)hc[q] * 4);
+    }
+    idx->searches += nq;
+    idx->rows_scanned += (uint64_t)nq * sh.rows;
+    idx->bytes_streamed += (uint64_t)nq * sh.rows * idx->dim * 4;
+    idx->h2d_bytes += (uint64_t)nq * idx->dim * 4;
+    idx->d2h_bytes += l.total;
+    return NM_OK;
+}
+
 // Rank-independent routing decision for collective searches (every rank must agree).
 bool collective_uses_fused_exchange(const nm_index *idx, uint32_t nq, uint32_t k, int metric) {
     if (!idx->xchg_ok || k > (uint32_t)nm::kMaxFastK) return false;
-    const bool would_batch = idx->batching.load() && nq >= kBatchMinQueries &&
+    const bool long_rows = single_query_stages(idx->dim) < 4;
+    const bool would_batch = (idx->batching.load() || single_query_stages(idx->dim) < 2) &&
+                             (nq >= kBatchMinQueries || long_rows) &&
                              (metric == NM_EUCLIDEAN || (idx->dim % 8u) == 0);
     return !would_batch;
 }
@@ -874,6 +937,7 @@ void nm_index_destroy(nm_index *idx) {
     }
     for (auto &sh : idx->shards) {
         cudaSetDevice(sh->device);
+        cudaDeviceSynchronize();  // asynchronous nm_search_device work may still be in flight
         sh->pool.clear();
         sh->stream_ws.clear();
         if (sh->d_rows) cudaFree(sh->d_rows);
@@ -1109,26 +1173,7 @@ static int search_impl(nm_index *idx, const float *queries, uint32_t nq, uint32_
             if (rc) return rc;
         }
         CUDA_TRY(cudaEventRecord(ws->ev1, ws->stream));
-        CUDA_TRY(cudaMemcpyAsync(ws->h_result, ws->d_result, l.total, cudaMemcpyDeviceToHost,
-                                 ws->stream));
-        CUDA_TRY(cudaStreamSynchronize(ws->stream));
-        float ms = 0.f;
-        CUDA_TRY(cudaEventElapsedTime(&ms, ws->ev0, ws->ev1));
-        idx->last_scan_ms = ms;
-        const uint32_t *hc = reinterpret_cast<const uint32_t *>(ws->h_result + l.counts_off);
-        const uint64_t *hr = reinterpret_cast<const uint64_t *>(ws->h_result + l.rows_off);
-        const float *hs = reinterpret_cast<const float *>(ws->h_result + l.scores_off);
-        for (uint32_t q = 0; q < nq; ++q) {
-            out_counts[q] = hc[q];
-            memcpy(out_rows + (size_t)q * k, hr + (size_t)q * k, (size_t)hc[q] * 8);
-            memcpy(out_scores + (size_t)q * k, hs + (size_t)q * k, (size_t)hc[q] * 4);
-        }
-        idx->searches += nq;
-        idx->rows_scanned += (uint64_t)nq * sh.rows;
-        idx->bytes_streamed += (uint64_t)nq * sh.rows * dim * 4;
-        idx->h2d_bytes += (uint64_t)nq * dim * 4;
-        idx->d2h_bytes += l.total;
-        return NM_OK;
+        return download_results(idx, sh, *ws, l, nq, k, out_rows, out_scores, out_counts);
     }
 
     // ---- collective path: one shard per process.  Single queries: ONE fused launch (scan +
@@ -1189,28 +1234,7 @@ static int search_impl(nm_index *idx, const float *queries, uint32_t nq, uint32_
             CUDA_TRY(cudaGetLastError());
             idx->merge_launches++;
         }
-        CUDA_TRY(cudaMemcpyAsync(ws->h_result, ws->d_result, l.total, cudaMemcpyDeviceToHost,
-                                 ws->stream));
-        CUDA_TRY(cudaStreamSynchronize(ws->stream));
-        float ms = 0.f;
-        CUDA_TRY(cudaEventElapsedTime(&ms, ws->ev0, ws->ev1));
-        idx->last_scan_ms = ms;
-        const uint32_t *hc = reinterpret_cast<const uint32_t *>(ws->h_result + l.counts_off);
-        const uint64_t *hr = reinterpret_cast<const uint64_t *>(ws->h_result + l.rows_off);
-        const float *hs = reinterpret_cast<const float *>(ws->h_result + l.scores_off);
-        for (uint32_t q = 0; q < nq; ++q) {
-            if (hc[q] == 0xffffffffu)
-                return fail(NM_ERR_STORAGE, "peer exchange timed out waiting for another rank");
-            out_counts[q] = hc[q];
-            memcpy(out_rows + (size_t)q * k, hr + (size_t)q * k, (size_t)hc[q] * 8);
-            memcpy(out_scores + (size_t)q * k, hs + (size_t)q * k, (size_t)hc[q] * 4);
-        }
-        idx->searches += nq;
-        idx->rows_scanned += (uint64_t)nq * sh.rows;
-        idx->bytes_streamed += (uint64_t)nq * sh.rows * dim * 4;
-        idx->h2d_bytes += (uint64_t)nq * dim * 4;
-        idx->d2h_bytes += l.total;
-        return NM_OK;
+        return download_results(idx, sh, *ws, l, nq, k, out_rows, out_scores, out_counts);
     }
 
     // ---- several devices in this process: scan each shard, merge the per-shard top-k on

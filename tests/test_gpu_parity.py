@@ -163,6 +163,18 @@ def test_adversarial_ascending_scores_exercise_pruning(metric):
     idx.close()
 
 
+def test_very_long_rows_stream_the_query():
+    """dim = 40000: the query no longer fits next to the stage ring, so even a single query is
+    served by the batched kernels (query streamed chunk by chunk)."""
+    n, d = 300, 40000
+    idx, rows = synth_index(n, d)
+    q = o.fill_synthetic(1, d, 3)[0]
+    for m in METRICS:
+        (got,) = idx.search(q, 5, m)
+        assert_same(got, o.search(rows, q, 5, m), m)
+    idx.close()
+
+
 def test_k_edge_cases_and_errors():
     idx, rows = synth_index(100, 24)
     q = o.fill_synthetic(1, 24, 1)[0]
