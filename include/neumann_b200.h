@@ -160,12 +160,25 @@ typedef struct nm_stats {
     double last_scan_ms;      /* device time of the most recent nm_search scan(s) */
     double profiled_scan_ms;  /* sum of CUDA-event times around profiled scan launches    */
     uint64_t profiled_scans;  /* number of nm_search_device calls folded into the sum     */
+    uint64_t prefilter_queries;   /* queries served through the int8 pre-filter            */
+    uint64_t prefilter_fallbacks; /* of those, redone with the exact f32 scan              */
+    uint64_t prefilter_kept;      /* rows whose score interval reached the running bound   */
 } nm_stats;
 int nm_index_stats(nm_index *idx, nm_stats *out);
 /* When enabled, every asynchronous nm_search_device call brackets its scan launches (not the
  * all-gather / merge) with CUDA events on the caller's stream; nm_index_stats waits for them
  * and accumulates profiled_scan_ms / profiled_scans.  Used by bench.py for the roofline. */
 int nm_index_set_profiling(nm_index *idx, int enable);
+/* SURVEY 8f row 4 — quantised pre-filter with EXACT re-score (precedent:
+ * ScalarQuantizedVector, tensor_store/src/hnsw.rs:308-356).  mode 1 keeps an int8 copy of the
+ * mirror (+1 byte per element, +16 bytes per row); nm_search on a single-device index then
+ * scans the int8 copy with dp4a (4x fewer HBM bytes), brackets every row's reference score in
+ * a rigorous interval, and re-scores only the rows whose interval reaches the k-th best lower
+ * bound with the exact f32 arithmetic.  Results are bit-identical to mode 0 (tested); cosine
+ * and dot product, k <= 1024, fewer than 8 queries per call; anything else, a non-finite
+ * query or an overflowing candidate list falls back to the f32 scan.  It changes the bytes
+ * read per row, so it is OFF by default and benchmarked separately from the f32 roofline. */
+int nm_index_set_prefilter(nm_index *idx, int mode);
 /* Batches of >= 8 queries share one corpus pass (batch_kernels.cuh) by default; 0 forces one
  * scan per query.  Results are bit-identical either way (tested); this is a tuning knob. */
 int nm_index_set_batching(nm_index *idx, int enable);

@@ -32,6 +32,8 @@ class NmStats(C.Structure):
         ("scan_launches", C.c_uint64), ("merge_launches", C.c_uint64),
         ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("last_scan_ms", C.c_double),
         ("profiled_scan_ms", C.c_double), ("profiled_scans", C.c_uint64),
+        ("prefilter_queries", C.c_uint64), ("prefilter_fallbacks", C.c_uint64),
+        ("prefilter_kept", C.c_uint64),
     ]
 
 
@@ -66,6 +68,7 @@ SIGNATURES = {
     "nm_index_stats": (C.c_int, [_vp, C.POINTER(NmStats)]),
     "nm_index_set_profiling": (C.c_int, [_vp, C.c_int]),
     "nm_index_set_batching": (C.c_int, [_vp, C.c_int]),
+    "nm_index_set_prefilter": (C.c_int, [_vp, C.c_int]),
 }
 
 _lib = None

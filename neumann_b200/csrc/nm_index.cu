@@ -8,6 +8,7 @@
 #include "../../include/neumann_b200.h"
 #include "scan_kernels.cuh"
 #include "batch_kernels.cuh"
+#include "prefilter_kernels.cuh"
 
 #include <dlfcn.h>
 #include <nccl.h>
@@ -151,6 +152,12 @@ struct Workspace {
     size_t hits_cap = 0;
     nm::ShardHit *d_gather = nullptr;  // [n_ranks, nq, k]
     size_t gather_cap = 0;
+    // pre-filter path (prefilter_kernels.cuh)
+    nm::KeptEntry *d_kept = nullptr;
+    uint64_t *d_exact_keys = nullptr;
+    uint32_t *d_pf_ctl = nullptr;   // [nq][8]
+    uint32_t *h_pf_ctl = nullptr;   // pinned
+    size_t pf_ctl_cap = 0;          // queries
     // batched-query path (batch_kernels.cuh)
     float *d_qt = nullptr;         // [n_kc][32][QB] transposed query chunks
     size_t qt_cap = 0;             // floats
@@ -174,6 +181,10 @@ struct Workspace {
         if (d_counter) cudaFree(d_counter);
         if (d_mask) cudaFree(d_mask);
         if (d_pass_keys) cudaFree(d_pass_keys);
+        if (d_kept) cudaFree(d_kept);
+        if (d_exact_keys) cudaFree(d_exact_keys);
+        if (d_pf_ctl) cudaFree(d_pf_ctl);
+        if (h_pf_ctl) cudaFreeHost(h_pf_ctl);
         if (d_qt) cudaFree(d_qt);
         if (d_qmag) cudaFree(d_qmag);
         if (d_scores) cudaFree(d_scores);
@@ -203,6 +214,14 @@ struct Shard {
     uint64_t row_base = 0;  // global index of local row 0 (within this process)
     CUtensorMap tmap;
     bool tmap_valid = false;
+    // int8 pre-filter copy (prefilter_kernels.cuh): [capacity8, pitch8] bytes + 16 B per row
+    int8_t *d_q8 = nullptr;
+    nm::RowMeta *d_meta = nullptr;
+    uint32_t *d_q8_flag = nullptr;
+    uint64_t q8_capacity = 0;
+    uint64_t q8_rows = 0;  // rows [0, q8_rows) are quantised and current
+    CUtensorMap tmap8;
+    bool tmap8_valid = false;
     cudaStream_t copy_stream = nullptr;
     float *staging[2] = {nullptr, nullptr};
     cudaEvent_t staging_done[2] = {nullptr, nullptr};
@@ -236,6 +255,8 @@ struct nm_index {
         merge_launches{0}, h2d_bytes{0}, d2h_bytes{0};
     std::atomic<double> last_scan_ms{0.0};
     std::atomic<int> profiling{0};
+    std::atomic<int> prefilter{0};  // nm_index_set_prefilter: 1 = exact int8 pre-filter
+    std::atomic<uint64_t> pf_queries{0}, pf_fallbacks{0}, pf_kept{0};
     std::atomic<int> batching{1};  // nm_index_set_batching: 0 forces one scan per query
     double profiled_scan_ms = 0.0;  // guarded by mu (exclusive) in nm_index_stats
     uint64_t profiled_scans = 0;
@@ -269,6 +290,73 @@ int build_tmap(nm_index *idx, Shard &sh) {
         return fail(NM_ERR_STORAGE, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
     sh.tmap_valid = true;
     return NM_OK;
+}
+
+
+// ---- int8 pre-filter copy upkeep ---------------------------------------------------------
+uint32_t q8_pitch(uint32_t dim) { return (dim + 15u) & ~15u; }
+
+int build_tmap8(nm_index *idx, Shard &sh) {
+    sh.tmap8_valid = false;
+    if (sh.rows == 0 || !sh.d_q8) return NM_OK;
+    EncodeTiledFn enc = get_encode_tiled();
+    if (!enc) return fail(NM_ERR_STORAGE, "cuTensorMapEncodeTiled unavailable (driver too old?)");
+    cuuint64_t gdim[2] = {idx->dim, sh.rows};
+    cuuint64_t gstride[1] = {(cuuint64_t)q8_pitch(idx->dim)};
+    cuuint32_t box[2] = {128, nm::kRowsPerBlock};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(&sh.tmap8, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, sh.d_q8, gdim, gstride, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS)
+        return fail(NM_ERR_STORAGE, "cuTensorMapEncodeTiled (int8) failed with CUresult %d", (int)r);
+    sh.tmap8_valid = true;
+    return NM_OK;
+}
+
+// Bring the int8 copy of rows [first, first+n) up to date (call with the index write lock held,
+// after the f32 mirror holds the new data).  No-op while the pre-filter is off.
+int q8_refresh(nm_index *idx, Shard &sh, uint64_t first, uint64_t n) {
+    if (!idx->prefilter.load()) return NM_OK;
+    const uint32_t pitch8 = q8_pitch(idx->dim);
+    if (sh.rows > sh.q8_capacity) {
+        uint64_t cap = std::max<uint64_t>(sh.rows, sh.capacity);
+        int8_t *nq = nullptr;
+        nm::RowMeta *nmeta = nullptr;
+        CUDA_TRY(cudaMalloc(&nq, cap * pitch8));
+        CUDA_TRY(cudaMalloc(&nmeta, cap * sizeof(nm::RowMeta)));
+        if (sh.d_q8 && sh.q8_rows) {
+            CUDA_TRY(cudaMemcpyAsync(nq, sh.d_q8, sh.q8_rows * pitch8, cudaMemcpyDeviceToDevice,
+                                     sh.copy_stream));
+            CUDA_TRY(cudaMemcpyAsync(nmeta, sh.d_meta, sh.q8_rows * sizeof(nm::RowMeta),
+                                     cudaMemcpyDeviceToDevice, sh.copy_stream));
+            CUDA_TRY(cudaStreamSynchronize(sh.copy_stream));
+        }
+        if (sh.d_q8) CUDA_TRY(cudaFree(sh.d_q8));
+        if (sh.d_meta) CUDA_TRY(cudaFree(sh.d_meta));
+        sh.d_q8 = nq;
+        sh.d_meta = nmeta;
+        sh.q8_capacity = cap;
+    }
+    if (!sh.d_q8_flag) {
+        CUDA_TRY(cudaMalloc(&sh.d_q8_flag, sizeof(uint32_t)));
+        CUDA_TRY(cudaMemsetAsync(sh.d_q8_flag, 0, sizeof(uint32_t), sh.copy_stream));
+    }
+    // anything the copy has never seen is (re)quantised together with the requested range
+    if (sh.q8_rows < first) {
+        n += first - sh.q8_rows;
+        first = sh.q8_rows;
+    }
+    if (first + n > sh.rows) n = sh.rows > first ? sh.rows - first : 0;
+    if (n) {
+        uint32_t blocks = (uint32_t)std::min<uint64_t>((n + 7) / 8, (uint64_t)sh.sm_count * 16);
+        nm::quantize_rows_kernel<<<blocks, 256, 0, sh.copy_stream>>>(
+            sh.d_rows, idx->pitch, idx->dim, first, n, sh.d_q8, pitch8, sh.d_meta, sh.d_q8_flag);
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaStreamSynchronize(sh.copy_stream));
+    }
+    sh.q8_rows = sh.rows;
+    return build_tmap8(idx, sh);
 }
 
 int shard_reserve(nm_index *idx, Shard &sh, uint64_t rows, bool keep) {
@@ -670,6 +758,98 @@ int scan_queries_batched(nm_index *idx, const Shard &sh, Workspace &ws, const fl
     return NM_OK;
 }
 
+
+// ---- exact int8 pre-filter path (single shard, host-synchronous nm_search only) -----------
+size_t prefilter_smem_bytes(uint32_t n_stages, uint32_t q_words) {
+    return 1024 + (size_t)n_stages * nm::kStageBytes + (size_t)nm::kCandCap * 8 +
+           (size_t)q_words * 4 + 2 * nm::kMaxStages * 8 + 256 +
+           (size_t)nm::kKeptStage * sizeof(nm::KeptEntry);
+}
+
+bool prefilter_usable(const nm_index *idx, const Shard &sh, uint32_t nq, uint32_t k, int metric,
+                      const uint64_t *row_mask) {
+    if (!idx->prefilter.load() || row_mask || metric == NM_EUCLIDEAN) return false;
+    if (!sh.tmap8_valid || sh.q8_rows != sh.rows || sh.rows == 0) return false;
+    if (k > (uint32_t)nm::kMaxFastK || k > sh.rows) return false;
+    if (idx->batching.load() && nq >= kBatchMinQueries && (idx->dim % 8u) == 0) return false;
+    uint32_t q_words = ((idx->dim + 127u) / 128u) * 32u;
+    return prefilter_smem_bytes(3, q_words) <= 227 * 1024;
+}
+
+int ws_ensure_prefilter(Workspace &ws, uint32_t nq) {
+    if (!ws.d_kept) {
+        CUDA_TRY(cudaMalloc(&ws.d_kept, (size_t)nm::kKeptCap * sizeof(nm::KeptEntry)));
+        CUDA_TRY(cudaMalloc(&ws.d_exact_keys, (size_t)nm::kKeptCap * sizeof(uint64_t)));
+    }
+    if (ws.pf_ctl_cap < nq) {
+        if (ws.d_pf_ctl) CUDA_TRY(cudaFree(ws.d_pf_ctl));
+        if (ws.h_pf_ctl) CUDA_TRY(cudaFreeHost(ws.h_pf_ctl));
+        ws.pf_ctl_cap = 0;
+        CUDA_TRY(cudaMalloc(&ws.d_pf_ctl, (size_t)nq * 8 * sizeof(uint32_t)));
+        CUDA_TRY(cudaMallocHost(&ws.h_pf_ctl, (size_t)nq * 8 * sizeof(uint32_t)));
+        ws.pf_ctl_cap = nq;
+    }
+    return NM_OK;
+}
+
+// Two launches per query: int8 scan (intervals, kept list, k-th best lower bound), then exact
+// re-score + selection.  ctl block q keeps the status for the host to inspect afterwards.
+int launch_prefiltered(nm_index *idx, const Shard &sh, Workspace &ws, const float *d_query,
+                       uint32_t q, uint32_t k, int metric, uint64_t *out_rows, float *out_scores,
+                       uint32_t *out_count, cudaStream_t stream) {
+    static std::mutex mu;
+    static bool configured[64] = {false};
+    {
+        std::lock_guard<std::mutex> g(mu);
+        if (sh.device >= 64 || !configured[sh.device]) {
+            CUDA_TRY(cudaFuncSetAttribute(nm::prefilter_scan_kernel,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            if (sh.device < 64) configured[sh.device] = true;
+        }
+    }
+    uint32_t *ctl = ws.d_pf_ctl + (size_t)q * 8;
+    CUDA_TRY(cudaMemsetAsync(ctl, 0, 8 * sizeof(uint32_t), stream));
+    nm::PrefilterParams p;
+    memset(&p, 0, sizeof(p));
+    p.query = d_query;
+    p.meta = sh.d_meta;
+    p.cand = ws.d_cand;
+    p.ctl = ctl;
+    p.kept = ws.d_kept;
+    p.n_rows = (uint32_t)sh.rows;
+    p.dim = idx->dim;
+    p.k = k;
+    p.q_words = ((idx->dim + 127u) / 128u) * 32u;
+    p.metric = metric == NM_COSINE ? nm::kCosine : nm::kDot;
+    uint32_t stages = nm::kMaxStages;
+    while (stages > 3 && prefilter_smem_bytes(stages, p.q_words) > 227 * 1024) --stages;
+    p.n_stages = stages;
+    const uint32_t n_rb = ((uint32_t)sh.rows + nm::kRowsPerBlock - 1) / nm::kRowsPerBlock;
+    const uint32_t grid = std::min<uint32_t>((uint32_t)sh.sm_count, n_rb);
+    nm::prefilter_scan_kernel<<<grid, nm::kScanThreads, prefilter_smem_bytes(stages, p.q_words),
+                                stream>>>(sh.tmap8, p);
+    CUDA_TRY(cudaGetLastError());
+    nm::RescoreParams r;
+    memset(&r, 0, sizeof(r));
+    r.query = d_query;
+    r.rows = sh.d_rows;
+    r.pitch = idx->pitch;
+    r.dim = idx->dim;
+    r.kept = ws.d_kept;
+    r.ctl = ctl;
+    r.exact_keys = ws.d_exact_keys;
+    r.out_rows = out_rows;
+    r.out_scores = out_scores;
+    r.out_count = out_count;
+    r.row_base = sh.row_base;
+    r.k = k;
+    r.metric = p.metric;
+    nm::prefilter_rescore_kernel<<<(uint32_t)sh.sm_count, nm::kRowsPerBlock, 0, stream>>>(r);
+    CUDA_TRY(cudaGetLastError());
+    idx->scan_launches += 2;
+    return NM_OK;
+}
+
 // nq queries over one shard: batched kernels when that pays, else one (chained) scan per query.
 int scan_queries(nm_index *idx, const Shard &sh, Workspace &ws, const float *d_queries,
                  uint32_t nq, uint32_t k, int metric, uint64_t row_base, uint64_t *out_rows,
@@ -941,6 +1121,9 @@ void nm_index_destroy(nm_index *idx) {
         sh->pool.clear();
         sh->stream_ws.clear();
         if (sh->d_rows) cudaFree(sh->d_rows);
+        if (sh->d_q8) cudaFree(sh->d_q8);
+        if (sh->d_meta) cudaFree(sh->d_meta);
+        if (sh->d_q8_flag) cudaFree(sh->d_q8_flag);
         for (int b = 0; b < 2; ++b) {
             if (sh->staging[b]) cudaFreeHost(sh->staging[b]);
             if (sh->staging_done[b]) cudaEventDestroy(sh->staging_done[b]);
@@ -953,11 +1136,12 @@ void nm_index_destroy(nm_index *idx) {
 int nm_index_clear(nm_index *idx) {
     if (!idx) return fail(NM_ERR_INVALID_ARGUMENT, "null index");
     std::unique_lock<std::shared_mutex> g(idx->mu);
-    uint64_t base = 0;
     for (auto &sh : idx->shards) {
         sh->rows = 0;
-        sh->row_base = base;
+        sh->row_base = 0;
         sh->tmap_valid = false;
+        sh->q8_rows = 0;
+        sh->tmap8_valid = false;
     }
     return NM_OK;
 }
@@ -980,6 +1164,9 @@ int nm_index_load(nm_index *idx, const float *rows, uint64_t n) {
         sh.row_base = lo;
         rc = build_tmap(idx, sh);
         if (rc) return rc;
+        sh.q8_rows = 0;
+        rc = q8_refresh(idx, sh, 0, sh.rows);
+        if (rc) return rc;
     }
     return NM_OK;
 }
@@ -996,7 +1183,9 @@ int nm_index_append(nm_index *idx, const float *rows, uint64_t n) {
     rc = shard_upload(idx, sh, sh.rows, rows, n);
     if (rc) return rc;
     sh.rows += n;
-    return build_tmap(idx, sh);
+    rc = build_tmap(idx, sh);
+    if (rc) return rc;
+    return q8_refresh(idx, sh, sh.rows - n, n);
 }
 
 static int locate_row(nm_index *idx, uint64_t row, Shard **out, uint64_t *local) {
@@ -1018,7 +1207,9 @@ int nm_index_update(nm_index *idx, uint64_t row, const float *vec) {
     int rc = locate_row(idx, row, &sh, &local);
     if (rc) return rc;
     CUDA_TRY(cudaSetDevice(sh->device));
-    return shard_upload(idx, *sh, local, vec, 1);
+    rc = shard_upload(idx, *sh, local, vec, 1);
+    if (rc) return rc;
+    return q8_refresh(idx, *sh, local, 1);
 }
 
 int nm_index_swap_remove(nm_index *idx, uint64_t row, uint64_t *moved_from) {
@@ -1051,7 +1242,16 @@ int nm_index_swap_remove(nm_index *idx, uint64_t row, uint64_t *moved_from) {
     }
     last->rows -= 1;
     CUDA_TRY(cudaSetDevice(last->device));
-    return build_tmap(idx, *last);
+    rc = build_tmap(idx, *last);
+    if (rc) return rc;
+    last->q8_rows = std::min(last->q8_rows, last->rows);
+    rc = q8_refresh(idx, *last, last->rows, 0);
+    if (rc) return rc;
+    if (last_global != row) {
+        CUDA_TRY(cudaSetDevice(sh->device));
+        rc = q8_refresh(idx, *sh, local, 1);  // the moved row took this slot
+    }
+    return rc;
 }
 
 int nm_index_get_row(nm_index *idx, uint64_t row, float *out_vec) {
@@ -1095,6 +1295,9 @@ int nm_index_fill_synthetic(nm_index *idx, uint64_t n, uint64_t seed, uint64_t r
         sh.rows = hi - lo;
         sh.row_base = lo;
         rc = build_tmap(idx, sh);
+        if (rc) return rc;
+        sh.q8_rows = 0;
+        rc = q8_refresh(idx, sh, 0, sh.rows);
         if (rc) return rc;
     }
     return NM_OK;
@@ -1166,6 +1369,55 @@ static int search_impl(nm_index *idx, const float *queries, uint32_t nq, uint32_
                                  r_rows + (size_t)q * k, r_scores + (size_t)q * k, r_counts + q,
                                  nullptr, ws->stream, nullptr, ws->d_mask);
                 if (rc) return rc;
+            }
+        } else if (prefilter_usable(idx, sh, nq, k, metric, row_mask)) {
+            rc = ws_ensure_prefilter(*ws, nq);
+            if (rc) return rc;
+            for (uint32_t q = 0; q < nq; ++q) {
+                rc = launch_prefiltered(idx, sh, *ws, ws->d_query + (size_t)q * dim, q, k, metric,
+                                        r_rows + (size_t)q * k, r_scores + (size_t)q * k,
+                                        r_counts + q, ws->stream);
+                if (rc) return rc;
+            }
+            // status words come back with the results (one sync); queries whose candidate list
+            // overflowed (or whose query is not finite) are redone with the exact f32 scan
+            CUDA_TRY(cudaMemcpyAsync(ws->h_pf_ctl, ws->d_pf_ctl, (size_t)nq * 8 * sizeof(uint32_t),
+                                     cudaMemcpyDeviceToHost, ws->stream));
+            CUDA_TRY(cudaEventRecord(ws->ev1, ws->stream));
+            CUDA_TRY(cudaMemcpyAsync(ws->h_result, ws->d_result, l.total, cudaMemcpyDeviceToHost,
+                                     ws->stream));
+            CUDA_TRY(cudaStreamSynchronize(ws->stream));
+            idx->pf_queries += nq;
+            bool redo = false;
+            for (uint32_t q = 0; q < nq; ++q) {
+                idx->pf_kept += ws->h_pf_ctl[(size_t)q * 8 + 7];
+                if (ws->h_pf_ctl[(size_t)q * 8 + 3] == 0) continue;
+                idx->pf_fallbacks++;
+                redo = true;
+                rc = launch_scan(idx, sh, *ws, ws->d_query + (size_t)q * dim, k, metric, sh.row_base,
+                                 r_rows + (size_t)q * k, r_scores + (size_t)q * k, r_counts + q,
+                                 nullptr, ws->stream);
+                if (rc) return rc;
+            }
+            if (!redo) {
+                // results are already on the host: finish without a second copy
+                float ms = 0.f;
+                CUDA_TRY(cudaEventElapsedTime(&ms, ws->ev0, ws->ev1));
+                idx->last_scan_ms = ms;
+                const uint32_t *hc = reinterpret_cast<const uint32_t *>(ws->h_result + l.counts_off);
+                const uint64_t *hr = reinterpret_cast<const uint64_t *>(ws->h_result + l.rows_off);
+                const float *hs = reinterpret_cast<const float *>(ws->h_result + l.scores_off);
+                for (uint32_t q = 0; q < nq; ++q) {
+                    out_counts[q] = hc[q];
+                    memcpy(out_rows + (size_t)q * k, hr + (size_t)q * k, (size_t)hc[q] * 8);
+                    memcpy(out_scores + (size_t)q * k, hs + (size_t)q * k, (size_t)hc[q] * 4);
+                }
+                idx->searches += nq;
+                idx->rows_scanned += (uint64_t)nq * sh.rows;
+                idx->bytes_streamed += (uint64_t)nq * sh.rows * (q8_pitch(dim) + sizeof(nm::RowMeta));
+                idx->h2d_bytes += (uint64_t)nq * dim * 4;
+                idx->d2h_bytes += l.total + (uint64_t)nq * 32;
+                return NM_OK;
             }
         } else {
             rc = scan_queries(idx, sh, *ws, ws->d_query, nq, k, metric, sh.row_base, r_rows, r_scores,
@@ -1432,6 +1684,30 @@ int nm_search_device(nm_index *idx, const float *d_queries, uint32_t nq, uint32_
     return NM_OK;
 }
 
+int nm_index_set_prefilter(nm_index *idx, int mode) {
+    if (!idx) return fail(NM_ERR_INVALID_ARGUMENT, "null index");
+    if (mode != 0 && mode != 1) return fail(NM_ERR_INVALID_ARGUMENT, "unknown pre-filter mode %d", mode);
+    std::unique_lock<std::shared_mutex> g(idx->mu);
+    idx->prefilter = mode;
+    for (auto &shp : idx->shards) {
+        Shard &sh = *shp;
+        CUDA_TRY(cudaSetDevice(sh.device));
+        if (mode == 0) {
+            if (sh.d_q8) CUDA_TRY(cudaFree(sh.d_q8));
+            if (sh.d_meta) CUDA_TRY(cudaFree(sh.d_meta));
+            sh.d_q8 = nullptr;
+            sh.d_meta = nullptr;
+            sh.q8_capacity = sh.q8_rows = 0;
+            sh.tmap8_valid = false;
+        } else {
+            sh.q8_rows = 0;
+            int rc = q8_refresh(idx, sh, 0, sh.rows);
+            if (rc) return rc;
+        }
+    }
+    return NM_OK;
+}
+
 int nm_index_set_batching(nm_index *idx, int enable) {
     if (!idx) return fail(NM_ERR_INVALID_ARGUMENT, "null index");
     idx->batching = enable ? 1 : 0;
@@ -1505,6 +1781,9 @@ int nm_index_stats(nm_index *idx, nm_stats *out) {
     out->h2d_bytes = idx->h2d_bytes;
     out->d2h_bytes = idx->d2h_bytes;
     out->last_scan_ms = idx->last_scan_ms;
+    out->prefilter_queries = idx->pf_queries;
+    out->prefilter_fallbacks = idx->pf_fallbacks;
+    out->prefilter_kept = idx->pf_kept;
     {
         // fold finished profiling event pairs into the totals (waits for the streams)
         std::unique_lock<std::shared_mutex> g(idx->mu);

@@ -208,14 +208,58 @@ __device__ __forceinline__ void bitonic_sort_desc(uint64_t *buf, uint32_t n, uin
     }
 }
 
+// Bitonic sort, descending, of buf[0..64) by ONE warp in registers (two keys per lane): no
+// block barriers, ~20x cheaper than the block-wide network for the small buffers that the
+// eager threshold refresh of the pre-filter scan produces.
+__device__ __forceinline__ void warp_sort_desc_64(uint64_t *buf, uint32_t lane) {
+    uint64_t a = buf[lane], b = buf[lane + 32u];  // element indices: lane, lane + 32
+    // network over 64 elements; element e lives in (e < 32 ? a : b) of lane e & 31
+#pragma unroll
+    for (uint32_t size = 2; size <= 64u; size <<= 1) {
+#pragma unroll
+        for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
+            if (stride == 32u) {
+                // partners are (lane, lane+32): both in this lane; size == 64 -> descending
+                if (a < b) {
+                    uint64_t tmp = a;
+                    a = b;
+                    b = tmp;
+                }
+            } else {
+                const uint64_t pa = __shfl_xor_sync(0xffffffffu, a, stride);
+                const uint64_t pb = __shfl_xor_sync(0xffffffffu, b, stride);
+                const bool upper = (lane & stride) != 0;  // this lane holds the higher index
+                // direction of the block of `size` elements containing the element
+                const bool desc_a = ((lane & size) == 0);            // element index = lane
+                const bool desc_b = (((lane + 32u) & size) == 0);    // element index = lane + 32
+                // lower index keeps the larger key when descending
+                const bool take_max_a = (desc_a != upper);
+                const bool take_max_b = (desc_b != upper);
+                a = take_max_a ? (a > pa ? a : pa) : (a < pa ? a : pa);
+                b = take_max_b ? (b > pb ? b : pb) : (b < pb ? b : pb);
+            }
+        }
+    }
+    buf[lane] = a;
+    buf[lane + 32u] = b;
+}
+
 // Sort the buffer, keep the k best, refresh the threshold.  Called by all consumer threads
 // with uniform state; contains barriers.
 __device__ __forceinline__ void topk_prune(TopKState &st, uint32_t t) {
     uint32_t n = 2;
     while (n < st.count) n <<= 1;
-    for (uint32_t i = st.count + t; i < n; i += kRowsPerBlock) st.buf[i] = 0ull;
+    if (n <= 64u) {
+        n = 64u;
+        for (uint32_t i = st.count + t; i < n; i += kRowsPerBlock) st.buf[i] = 0ull;
+        consumer_sync();
+        if (t < 32u) warp_sort_desc_64(st.buf, t);
+    } else {
+        for (uint32_t i = st.count + t; i < n; i += kRowsPerBlock) st.buf[i] = 0ull;
+        consumer_sync();
+        bitonic_sort_desc(st.buf, n, t);
+    }
     consumer_sync();
-    bitonic_sort_desc(st.buf, n, t);
     uint32_t kept = st.count < st.k ? st.count : st.k;
     if (t == 0) {
         *st.cnt_smem = kept;

@@ -132,6 +132,10 @@ class DeviceIndex:
     def detach_comm(self) -> None:
         check(_ffi.lib().nm_index_detach_comm(self._h))
 
+    def set_prefilter(self, mode: int) -> None:
+        """0 = off (default), 1 = exact int8 pre-filter (see include/neumann_b200.h)."""
+        check(_ffi.lib().nm_index_set_prefilter(self._h, int(mode)))
+
     def set_batching(self, enable: bool) -> None:
         check(_ffi.lib().nm_index_set_batching(self._h, 1 if enable else 0))
 

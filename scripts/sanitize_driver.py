@@ -28,6 +28,11 @@ for (n, d) in [(3000, 100), (1500, 64), (700, 13)]:
         sub = np.nonzero(mask)[0]
         er, es = o.search(rows[sub], qs[1], 5, m)
         ok &= np.array_equal(g[0], sub[er.astype(np.int64)].astype(np.uint64))
+    idx.set_prefilter(1)                                   # int8 pre-filter kernels
+    for m in ("cosine", "dot"):
+        (g,) = idx.search(qs[4], 10, m)
+        ok &= same(g, o.search(rows, qs[4], 10, m))
+    idx.set_prefilter(0)
     idx.update(5, qs[3]); idx.swap_remove(7); idx.append(rows[:10])
     (g,) = idx.search(qs[3], 3, "cosine")
     ok &= g[0][0] == 5
