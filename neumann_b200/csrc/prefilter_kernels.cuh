@@ -12,7 +12,8 @@
 // bit-identical to nm_search without the pre-filter (tests/test_gpu_prefilter.py); if the
 // candidate list overflows, or anything is non-finite, the caller falls back to the f32 scan.
 //
-// Error model (all data finite).  Row r: x_i = s_r (xt_i + d_i), xt_i in [-127,127] integer,
+// Error model (all data finite, quantisation scales normal f32 numbers; rows that violate
+// either are flagged and always re-scored, a query that does falls back to the f32 scan).  Row r: x_i = s_r (xt_i + d_i), xt_i in [-127,127] integer,
 // |d_i| <= 0.5001 (rint + the rounding of the f32 division x_i / s_r).  Query likewise with
 // s_q, qt_i, |e_i| <= 0.5001.  With I = sum qt_i xt_i (exact in int32) and D* the real dot:
 //   |D* - s_q s_r I| <= s_q s_r B_r,   B_r = 0.5001 (Q1 + X1_r) + 0.2502 dim,
@@ -97,7 +98,13 @@ __global__ void quantize_rows_kernel(const float *__restrict__ rows, uint32_t pi
             mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
             bad |= __shfl_xor_sync(0xffffffffu, (int)bad, o) != 0;
         }
-        const float scale = bad ? 0.0f : __fdiv_rn(mx, 127.0f);
+        float scale = bad ? 0.0f : __fdiv_rn(mx, 127.0f);
+        // a denormal scale no longer satisfies |x/scale - rint| <= 0.5001: treat the row as
+        // "unknown" (always a candidate, exact re-score decides)
+        if (mx > 0.0f && scale < 1.17549435e-38f) {
+            bad = true;
+            scale = 0.0f;
+        }
         uint32_t x1 = 0;
         int8_t *out = q8 + r * pitch8;
         for (uint32_t w = lane; w * 4u < pitch8; w += 32u) {
@@ -285,6 +292,7 @@ prefilter_scan_kernel(const __grid_constant__ CUtensorMap tmap8, const Prefilter
         bad |= red_u[w] != 0u;
     }
     const float s_q = __fdiv_rn(mx, 127.0f);
+    if (mx > 0.0f && s_q < 1.17549435e-38f) bad = true;  // denormal scale: let the f32 scan decide
     consumer_sync();
     // quantise the query into packed int8 words (zero padded), Q1 = sum |qt|
     uint32_t q1 = 0;

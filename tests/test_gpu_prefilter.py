@@ -59,11 +59,14 @@ def test_prefilter_adversarial_data(metric):
     rows[4100:4200] *= np.float32(1e15)
     rows[5000:5050] = 0.0
     rows[6000:6100] = -rows[1000:1100]
+    rows[7000:7050] *= np.float32(1e-38)          # denormal elements: scale below FLT_MIN
+    rows[7050:7060] = np.float32(1e-45)
     idx = DeviceIndex(d)
     idx.load(rows)
     idx.set_prefilter(1)
     for kk in (1, k, 500):
-        check(idx, rows, [q, rows[3100], rows[4050], rows[4150], np.abs(q)], kk, metric, "adversarial")
+        check(idx, rows, [q, rows[3100], rows[4050], rows[4150], np.abs(q), rows[7010],
+                          q * np.float32(1e30)], kk, metric, "adversarial")
     idx.close()
 
 
