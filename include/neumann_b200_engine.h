@@ -85,6 +85,13 @@ int nm_engine_query_points(nm_engine *e, const char *collection, const float *ve
                            size_t limit, size_t offset, int has_threshold, float score_threshold,
                            nm_results **out);
 
+/* Unified entity mode (vector_engine/src/lib.rs:3060-3219): `_embedding` of entity keys. */
+int nm_engine_set_entity_embedding(nm_engine *e, const char *entity_key, const float *vec, size_t n);
+int nm_engine_remove_entity_embedding(nm_engine *e, const char *entity_key);
+int nm_engine_entity_has_embedding(nm_engine *e, const char *entity_key);
+int nm_engine_search_entities(nm_engine *e, const float *query, size_t n, size_t top_k,
+                              nm_results **out);
+
 /* QueryRouter::execute (legacy string path) / execute_parsed (AST path), SIMILAR + EMBED only.
  * *out is NULL for QueryResult::Empty. */
 int nm_engine_execute(nm_engine *e, const char *command, nm_results **out);

@@ -26,6 +26,7 @@ NVCC_FLAGS = [
     "-fmad=false", "-prec-div=true", "-prec-sqrt=true", "-ftz=false",
     "-Xcompiler", "-fPIC,-ffp-contract=off,-fno-fast-math,-Wall",
     "-shared", "-cudart", "static",
+    "--threads", "4",
 ]
 
 

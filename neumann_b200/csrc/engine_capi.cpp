@@ -280,6 +280,29 @@ int nm_engine_query_points(nm_engine *e, const char *collection, const float *ve
     return NM_OK;
 }
 
+int nm_engine_set_entity_embedding(nm_engine *e, const char *entity_key, const float *vec, size_t n) {
+    if (!e || !entity_key) return fail(NM_ERR_INVALID_ARGUMENT, "null argument");
+    auto r = e->engine->set_entity_embedding(entity_key, std::vector<float>(vec, vec + n));
+    return r.is_err() ? fail(r.error()) : NM_OK;
+}
+
+int nm_engine_remove_entity_embedding(nm_engine *e, const char *entity_key) {
+    if (!e || !entity_key) return fail(NM_ERR_INVALID_ARGUMENT, "null argument");
+    auto r = e->engine->remove_entity_embedding(entity_key);
+    return r.is_err() ? fail(r.error()) : NM_OK;
+}
+
+int nm_engine_entity_has_embedding(nm_engine *e, const char *entity_key) {
+    return e && entity_key && e->engine->entity_has_embedding(entity_key);
+}
+
+int nm_engine_search_entities(nm_engine *e, const float *query, size_t n, size_t top_k,
+                              nm_results **out) {
+    if (!e) return fail(NM_ERR_INVALID_ARGUMENT, "null engine");
+    std::vector<float> q(query, query + (query ? n : 0));
+    return give(e->engine->search_entities(q, top_k), out);
+}
+
 int nm_engine_execute(nm_engine *e, const char *command, nm_results **out) {
     if (!e || !command) return fail(NM_ERR_INVALID_ARGUMENT, "null argument");
     return give(e->router->execute(command), out);

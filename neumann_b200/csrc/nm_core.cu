@@ -1,0 +1,563 @@
+// nm_core.cu — the device mirror behind include/neumann_b200.h: lifecycle, pinned
+// double-buffered staging, mutations (append / update / swap-remove), upkeep of the optional
+// int8 copy, statistics.  Row-major f32, pitch = dim rounded up to 4 floats so every row is
+// 16-byte aligned for TMA.  There is deliberately no CPU code path for the scan.
+#include "nm_internal.hpp"
+
+#include <cstdarg>
+#include <cstdio>
+#include <thread>
+
+using namespace nmi;
+
+namespace nmi {
+
+static thread_local std::string g_last_error;
+
+int fail(int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+    return code;
+}
+const char *last_error() { return g_last_error.c_str(); }
+
+}  // namespace nmi
+
+namespace {
+
+// ---- cuTensorMapEncodeTiled through the runtime (no link-time libcuda dependency) --------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *,
+                                  const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
+                                  const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_tiled() {
+    static EncodeTiledFn fn = [] {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) !=
+                cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            p = nullptr;
+        return reinterpret_cast<EncodeTiledFn>(p);
+    }();
+    return fn;
+}
+
+constexpr size_t kStagingBytes = 64u << 20;  // per pinned staging buffer (two per shard)
+
+// Pageable -> pinned staging copy, split over a few host threads (one core tops out near
+// 11 GB/s, well below what the DMA engine takes from pinned memory).
+void parallel_memcpy(void *dst, const void *src, size_t bytes) {
+    unsigned hw = std::thread::hardware_concurrency();
+    unsigned n = std::min<unsigned>(8u, hw ? hw : 1u);
+    if (bytes < (4u << 20) || n < 2) {
+        memcpy(dst, src, bytes);
+        return;
+    }
+    std::vector<std::thread> th;
+    const size_t per = ((bytes / n) + 4095) & ~size_t(4095);
+    for (unsigned i = 1; i < n; ++i) {
+        size_t off = per * i;
+        if (off >= bytes) break;
+        size_t len = std::min(per, bytes - off);
+        th.emplace_back([=] { memcpy((char *)dst + off, (const char *)src + off, len); });
+    }
+    memcpy(dst, src, std::min(per, bytes));
+    for (auto &t : th) t.join();
+}
+
+}  // namespace
+
+namespace nmi {
+
+int build_tmap(nm_index *idx, Shard &sh) {
+    sh.tmap_valid = false;
+    if (sh.rows == 0) return NM_OK;
+    EncodeTiledFn enc = get_encode_tiled();
+    if (!enc) return fail(NM_ERR_STORAGE, "cuTensorMapEncodeTiled unavailable (driver too old?)");
+    cuuint64_t gdim[2] = {idx->dim, sh.rows};
+    cuuint64_t gstride[1] = {(cuuint64_t)idx->pitch * 4};
+    cuuint32_t box[2] = {nm::kChunkFloats, nm::kRowsPerBlock};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(&sh.tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, sh.d_rows, gdim, gstride, box,
+                     estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS)
+        return fail(NM_ERR_STORAGE, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+    sh.tmap_valid = true;
+    return NM_OK;
+}
+
+
+// ---- int8 pre-filter copy upkeep ---------------------------------------------------------
+uint32_t q8_pitch(uint32_t dim) { return (dim + 15u) & ~15u; }
+
+int build_tmap8(nm_index *idx, Shard &sh) {
+    sh.tmap8_valid = false;
+    if (sh.rows == 0 || !sh.d_q8) return NM_OK;
+    EncodeTiledFn enc = get_encode_tiled();
+    if (!enc) return fail(NM_ERR_STORAGE, "cuTensorMapEncodeTiled unavailable (driver too old?)");
+    cuuint64_t gdim[2] = {idx->dim, sh.rows};
+    cuuint64_t gstride[1] = {(cuuint64_t)q8_pitch(idx->dim)};
+    cuuint32_t box[2] = {128, nm::kRowsPerBlock};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(&sh.tmap8, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, sh.d_q8, gdim, gstride, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS)
+        return fail(NM_ERR_STORAGE, "cuTensorMapEncodeTiled (int8) failed with CUresult %d", (int)r);
+    sh.tmap8_valid = true;
+    return NM_OK;
+}
+
+// Bring the int8 copy of rows [first, first+n) up to date (call with the index write lock held,
+// after the f32 mirror holds the new data).  No-op while the pre-filter is off.
+int q8_refresh(nm_index *idx, Shard &sh, uint64_t first, uint64_t n) {
+    if (!idx->prefilter.load()) return NM_OK;
+    const uint32_t pitch8 = q8_pitch(idx->dim);
+    if (sh.rows > sh.q8_capacity) {
+        uint64_t cap = std::max<uint64_t>(sh.rows, sh.capacity);
+        int8_t *nq = nullptr;
+        nm::RowMeta *nmeta = nullptr;
+        CUDA_TRY(cudaMalloc(&nq, cap * pitch8));
+        CUDA_TRY(cudaMalloc(&nmeta, cap * sizeof(nm::RowMeta)));
+        if (sh.d_q8 && sh.q8_rows) {
+            CUDA_TRY(cudaMemcpyAsync(nq, sh.d_q8, sh.q8_rows * pitch8, cudaMemcpyDeviceToDevice,
+                                     sh.copy_stream));
+            CUDA_TRY(cudaMemcpyAsync(nmeta, sh.d_meta, sh.q8_rows * sizeof(nm::RowMeta),
+                                     cudaMemcpyDeviceToDevice, sh.copy_stream));
+            CUDA_TRY(cudaStreamSynchronize(sh.copy_stream));
+        }
+        if (sh.d_q8) CUDA_TRY(cudaFree(sh.d_q8));
+        if (sh.d_meta) CUDA_TRY(cudaFree(sh.d_meta));
+        sh.d_q8 = nq;
+        sh.d_meta = nmeta;
+        sh.q8_capacity = cap;
+    }
+    if (!sh.d_q8_flag) {
+        CUDA_TRY(cudaMalloc(&sh.d_q8_flag, sizeof(uint32_t)));
+        CUDA_TRY(cudaMemsetAsync(sh.d_q8_flag, 0, sizeof(uint32_t), sh.copy_stream));
+    }
+    // anything the copy has never seen is (re)quantised together with the requested range
+    if (sh.q8_rows < first) {
+        n += first - sh.q8_rows;
+        first = sh.q8_rows;
+    }
+    if (first + n > sh.rows) n = sh.rows > first ? sh.rows - first : 0;
+    if (n) {
+        int rc = launch_quantize(sh, sh.d_rows, idx->pitch, idx->dim, first, n, sh.d_q8, pitch8,
+                                 sh.d_meta, sh.d_q8_flag, sh.copy_stream);
+        if (rc) return rc;
+        CUDA_TRY(cudaStreamSynchronize(sh.copy_stream));
+    }
+    sh.q8_rows = sh.rows;
+    return build_tmap8(idx, sh);
+}
+
+}  // namespace nmi
+
+namespace {
+
+int shard_reserve(nm_index *idx, Shard &sh, uint64_t rows, bool keep) {
+    if (rows <= sh.capacity) return NM_OK;
+    if (rows > nm::kMaxLocalRows)
+        return fail(NM_ERR_INVALID_ARGUMENT, "shard would hold %llu rows; limit is %u per device",
+                    (unsigned long long)rows, nm::kMaxLocalRows);
+    uint64_t cap = rows;
+    if (keep && sh.capacity) cap = std::max<uint64_t>(rows, sh.capacity + sh.capacity / 2);
+    float *p = nullptr;
+    CUDA_TRY(cudaMalloc(&p, cap * idx->pitch * sizeof(float)));
+    if (keep && sh.rows) {
+        CUDA_TRY(cudaMemcpyAsync(p, sh.d_rows, sh.rows * idx->pitch * sizeof(float),
+                                 cudaMemcpyDeviceToDevice, sh.copy_stream));
+        CUDA_TRY(cudaStreamSynchronize(sh.copy_stream));
+    }
+    if (sh.d_rows) CUDA_TRY(cudaFree(sh.d_rows));
+    sh.d_rows = p;
+    sh.capacity = cap;
+    return NM_OK;
+}
+
+// Host rows [n, dim] -> device rows [first, first+n) of the shard.  Pinned sources are DMA'd
+// directly; pageable sources go through two pinned staging buffers so the host memcpy of
+// chunk i+1 overlaps the DMA of chunk i.
+int shard_upload(nm_index *idx, Shard &sh, uint64_t first, const float *src, uint64_t n) {
+    if (n == 0) return NM_OK;
+    const size_t row_bytes = (size_t)idx->dim * 4, pitch_bytes = (size_t)idx->pitch * 4;
+    float *dst = sh.d_rows + first * idx->pitch;
+    cudaPointerAttributes attr;
+    bool pinned = cudaPointerGetAttributes(&attr, src) == cudaSuccess &&
+                  attr.type == cudaMemoryTypeHost;
+    cudaGetLastError();
+    if (idx->pitch != idx->dim)
+        CUDA_TRY(cudaMemsetAsync(dst, 0, n * pitch_bytes, sh.copy_stream));
+    if (pinned) {
+        CUDA_TRY(cudaMemcpy2DAsync(dst, pitch_bytes, src, row_bytes, row_bytes, n,
+                                   cudaMemcpyHostToDevice, sh.copy_stream));
+    } else {
+        if (!sh.staging[0]) {
+            for (int b = 0; b < 2; ++b) {
+                CUDA_TRY(cudaMallocHost(&sh.staging[b], kStagingBytes));
+                CUDA_TRY(cudaEventCreateWithFlags(&sh.staging_done[b], cudaEventDisableTiming));
+            }
+        }
+        const uint64_t rows_per_chunk = std::max<uint64_t>(1, kStagingBytes / row_bytes);
+        if (row_bytes > kStagingBytes)
+            return fail(NM_ERR_DIMENSION_MISMATCH, "dimension %u too large for staging", idx->dim);
+        int b = 0;
+        for (uint64_t r = 0; r < n; r += rows_per_chunk, b ^= 1) {
+            uint64_t m = std::min(rows_per_chunk, n - r);
+            CUDA_TRY(cudaEventSynchronize(sh.staging_done[b]));
+            parallel_memcpy(sh.staging[b], src + r * idx->dim, m * row_bytes);
+            CUDA_TRY(cudaMemcpy2DAsync(dst + r * idx->pitch, pitch_bytes, sh.staging[b], row_bytes,
+                                       row_bytes, m, cudaMemcpyHostToDevice, sh.copy_stream));
+            CUDA_TRY(cudaEventRecord(sh.staging_done[b], sh.copy_stream));
+        }
+    }
+    CUDA_TRY(cudaStreamSynchronize(sh.copy_stream));
+    idx->h2d_bytes += n * row_bytes;
+    return NM_OK;
+}
+
+}  // namespace
+
+// ======================================================================================
+// C ABI: library, mirror lifecycle and mutations
+// ======================================================================================
+extern "C" {
+
+int nm_abi_version(void) { return NM_ABI_VERSION; }
+
+const char *nm_last_error(void) { return nmi::last_error(); }
+
+int nm_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int nm_index_create(uint32_t dim, const int *devices, int n_dev, nm_index **out) {
+    if (!out) return fail(NM_ERR_INVALID_ARGUMENT, "null out pointer");
+    *out = nullptr;
+    if (dim == 0) return fail(NM_ERR_EMPTY_VECTOR, "dimension must be >= 1");
+    int avail = nm_device_count();
+    if (avail == 0)
+        return fail(NM_ERR_STORAGE, "no CUDA device visible: the SIMILAR scan has no CPU path");
+    std::vector<int> devs;
+    if (!devices || n_dev <= 0) {
+        int cur = 0;
+        CUDA_TRY(cudaGetDevice(&cur));
+        devs.push_back(cur);
+    } else {
+        for (int i = 0; i < n_dev; ++i) {
+            if (devices[i] < 0 || devices[i] >= avail)
+                return fail(NM_ERR_INVALID_ARGUMENT, "device %d out of range (0..%d)", devices[i],
+                            avail - 1);
+            devs.push_back(devices[i]);
+        }
+    }
+    std::unique_ptr<nm_index> idx(new nm_index());
+    idx->dim = dim;
+    idx->pitch = (dim + 3u) & ~3u;
+    for (int d : devs) {
+        cudaDeviceProp prop;
+        CUDA_TRY(cudaGetDeviceProperties(&prop, d));
+        if (prop.major < 10)
+            return fail(NM_ERR_STORAGE, "device %d is sm_%d%d; this library is built for sm_100a", d,
+                        prop.major, prop.minor);
+        std::unique_ptr<Shard> sh(new Shard());
+        sh->device = d;
+        sh->sm_count = prop.multiProcessorCount;
+        CUDA_TRY(cudaSetDevice(d));
+        CUDA_TRY(cudaStreamCreateWithFlags(&sh->copy_stream, cudaStreamNonBlocking));
+        idx->shards.push_back(std::move(sh));
+    }
+    *out = idx.release();
+    return NM_OK;
+}
+
+void nm_index_destroy(nm_index *idx) {
+    if (!idx) return;
+    if (idx->comm && nccl().ok) {
+        cudaSetDevice(idx->shards[0]->device);
+        cudaDeviceSynchronize();
+        teardown_peer_exchange(idx);
+        nccl().CommDestroy(idx->comm);
+        if (idx->xchg_mem) cudaFree(idx->xchg_mem);
+    }
+    for (auto &sh : idx->shards) {
+        cudaSetDevice(sh->device);
+        cudaDeviceSynchronize();  // asynchronous nm_search_device work may still be in flight
+        sh->pool.clear();
+        sh->stream_ws.clear();
+        if (sh->d_rows) cudaFree(sh->d_rows);
+        if (sh->d_q8) cudaFree(sh->d_q8);
+        if (sh->d_meta) cudaFree(sh->d_meta);
+        if (sh->d_q8_flag) cudaFree(sh->d_q8_flag);
+        for (int b = 0; b < 2; ++b) {
+            if (sh->staging[b]) cudaFreeHost(sh->staging[b]);
+            if (sh->staging_done[b]) cudaEventDestroy(sh->staging_done[b]);
+        }
+        if (sh->copy_stream) cudaStreamDestroy(sh->copy_stream);
+    }
+    delete idx;
+}
+
+int nm_index_clear(nm_index *idx) {
+    if (!idx) return fail(NM_ERR_INVALID_ARGUMENT, "null index");
+    std::unique_lock<std::shared_mutex> g(idx->mu);
+    for (auto &sh : idx->shards) {
+        sh->rows = 0;
+        sh->row_base = 0;
+        sh->tmap_valid = false;
+        sh->q8_rows = 0;
+        sh->tmap8_valid = false;
+    }
+    return NM_OK;
+}
+
+int nm_index_load(nm_index *idx, const float *rows, uint64_t n) {
+    if (!idx) return fail(NM_ERR_INVALID_ARGUMENT, "null index");
+    if (n && !rows) return fail(NM_ERR_INVALID_ARGUMENT, "null rows");
+    std::unique_lock<std::shared_mutex> g(idx->mu);
+    const uint64_t G = idx->shards.size();
+    for (uint64_t s = 0; s < G; ++s) {
+        Shard &sh = *idx->shards[s];
+        uint64_t lo = n * s / G, hi = n * (s + 1) / G;
+        CUDA_TRY(cudaSetDevice(sh.device));
+        sh.rows = 0;
+        int rc = shard_reserve(idx, sh, hi - lo, false);
+        if (rc) return rc;
+        rc = shard_upload(idx, sh, 0, rows + lo * idx->dim, hi - lo);
+        if (rc) return rc;
+        sh.rows = hi - lo;
+        sh.row_base = lo;
+        rc = build_tmap(idx, sh);
+        if (rc) return rc;
+        sh.q8_rows = 0;
+        rc = q8_refresh(idx, sh, 0, sh.rows);
+        if (rc) return rc;
+    }
+    return NM_OK;
+}
+
+int nm_index_append(nm_index *idx, const float *rows, uint64_t n) {
+    if (!idx) return fail(NM_ERR_INVALID_ARGUMENT, "null index");
+    if (n == 0) return NM_OK;
+    if (!rows) return fail(NM_ERR_INVALID_ARGUMENT, "null rows");
+    std::unique_lock<std::shared_mutex> g(idx->mu);
+    Shard &sh = *idx->shards.back();
+    CUDA_TRY(cudaSetDevice(sh.device));
+    int rc = shard_reserve(idx, sh, sh.rows + n, true);
+    if (rc) return rc;
+    rc = shard_upload(idx, sh, sh.rows, rows, n);
+    if (rc) return rc;
+    sh.rows += n;
+    rc = build_tmap(idx, sh);
+    if (rc) return rc;
+    return q8_refresh(idx, sh, sh.rows - n, n);
+}
+
+static int locate_row(nm_index *idx, uint64_t row, Shard **out, uint64_t *local) {
+    for (auto &sh : idx->shards) {
+        if (row >= sh->row_base && row < sh->row_base + sh->rows) {
+            *out = sh.get();
+            *local = row - sh->row_base;
+            return NM_OK;
+        }
+    }
+    return fail(NM_ERR_INVALID_ARGUMENT, "row %llu out of range", (unsigned long long)row);
+}
+
+int nm_index_update(nm_index *idx, uint64_t row, const float *vec) {
+    if (!idx || !vec) return fail(NM_ERR_INVALID_ARGUMENT, "null argument");
+    std::unique_lock<std::shared_mutex> g(idx->mu);
+    Shard *sh = nullptr;
+    uint64_t local = 0;
+    int rc = locate_row(idx, row, &sh, &local);
+    if (rc) return rc;
+    CUDA_TRY(cudaSetDevice(sh->device));
+    rc = shard_upload(idx, *sh, local, vec, 1);
+    if (rc) return rc;
+    return q8_refresh(idx, *sh, local, 1);
+}
+
+int nm_index_swap_remove(nm_index *idx, uint64_t row, uint64_t *moved_from) {
+    if (!idx) return fail(NM_ERR_INVALID_ARGUMENT, "null index");
+    std::unique_lock<std::shared_mutex> g(idx->mu);
+    Shard *sh = nullptr;
+    uint64_t local = 0;
+    int rc = locate_row(idx, row, &sh, &local);
+    if (rc) return rc;
+    // the globally last row lives in the last non-empty shard
+    Shard *last = nullptr;
+    for (auto it = idx->shards.rbegin(); it != idx->shards.rend(); ++it)
+        if ((*it)->rows) {
+            last = it->get();
+            break;
+        }
+    uint64_t last_global = last->row_base + last->rows - 1;
+    if (moved_from) *moved_from = last_global;
+    if (last_global != row) {
+        const size_t bytes = (size_t)idx->pitch * 4;
+        const float *src = last->d_rows + (last->rows - 1) * idx->pitch;
+        float *dst = sh->d_rows + local * idx->pitch;
+        CUDA_TRY(cudaSetDevice(sh->device));
+        if (last->device == sh->device)
+            CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, sh->copy_stream));
+        else
+            CUDA_TRY(cudaMemcpyPeerAsync(dst, sh->device, src, last->device, bytes,
+                                         sh->copy_stream));
+        CUDA_TRY(cudaStreamSynchronize(sh->copy_stream));
+    }
+    last->rows -= 1;
+    CUDA_TRY(cudaSetDevice(last->device));
+    rc = build_tmap(idx, *last);
+    if (rc) return rc;
+    last->q8_rows = std::min(last->q8_rows, last->rows);
+    rc = q8_refresh(idx, *last, last->rows, 0);
+    if (rc) return rc;
+    if (last_global != row) {
+        CUDA_TRY(cudaSetDevice(sh->device));
+        rc = q8_refresh(idx, *sh, local, 1);  // the moved row took this slot
+    }
+    return rc;
+}
+
+int nm_index_get_row(nm_index *idx, uint64_t row, float *out_vec) {
+    if (!idx || !out_vec) return fail(NM_ERR_INVALID_ARGUMENT, "null argument");
+    std::shared_lock<std::shared_mutex> g(idx->mu);
+    Shard *sh = nullptr;
+    uint64_t local = 0;
+    int rc = locate_row(idx, row, &sh, &local);
+    if (rc) return rc;
+    CUDA_TRY(cudaSetDevice(sh->device));
+    CUDA_TRY(cudaMemcpy(out_vec, sh->d_rows + local * idx->pitch, (size_t)idx->dim * 4,
+                        cudaMemcpyDeviceToHost));
+    return NM_OK;
+}
+
+uint64_t nm_index_rows(const nm_index *idx) {
+    if (!idx) return 0;
+    std::shared_lock<std::shared_mutex> g(idx->mu);
+    return idx->total_rows();
+}
+uint32_t nm_index_dim(const nm_index *idx) { return idx ? idx->dim : 0; }
+int nm_index_device_count(const nm_index *idx) { return idx ? (int)idx->shards.size() : 0; }
+
+int nm_index_fill_synthetic(nm_index *idx, uint64_t n, uint64_t seed, uint64_t row_offset) {
+    if (!idx) return fail(NM_ERR_INVALID_ARGUMENT, "null index");
+    std::unique_lock<std::shared_mutex> g(idx->mu);
+    const uint64_t G = idx->shards.size();
+    for (uint64_t s = 0; s < G; ++s) {
+        Shard &sh = *idx->shards[s];
+        uint64_t lo = n * s / G, hi = n * (s + 1) / G;
+        CUDA_TRY(cudaSetDevice(sh.device));
+        sh.rows = 0;
+        int rc = shard_reserve(idx, sh, hi - lo, false);
+        if (rc) return rc;
+        if (hi > lo) {
+            rc = launch_fill_synthetic(sh, sh.d_rows, hi - lo, idx->dim, idx->pitch, seed,
+                                       row_offset + lo, sh.copy_stream);
+            if (rc) return rc;
+            CUDA_TRY(cudaStreamSynchronize(sh.copy_stream));
+        }
+        sh.rows = hi - lo;
+        sh.row_base = lo;
+        rc = build_tmap(idx, sh);
+        if (rc) return rc;
+        sh.q8_rows = 0;
+        rc = q8_refresh(idx, sh, 0, sh.rows);
+        if (rc) return rc;
+    }
+    return NM_OK;
+}
+
+int nm_index_set_prefilter(nm_index *idx, int mode) {
+    if (!idx) return fail(NM_ERR_INVALID_ARGUMENT, "null index");
+    if (mode != 0 && mode != 1) return fail(NM_ERR_INVALID_ARGUMENT, "unknown pre-filter mode %d", mode);
+    std::unique_lock<std::shared_mutex> g(idx->mu);
+    idx->prefilter = mode;
+    for (auto &shp : idx->shards) {
+        Shard &sh = *shp;
+        CUDA_TRY(cudaSetDevice(sh.device));
+        if (mode == 0) {
+            if (sh.d_q8) CUDA_TRY(cudaFree(sh.d_q8));
+            if (sh.d_meta) CUDA_TRY(cudaFree(sh.d_meta));
+            sh.d_q8 = nullptr;
+            sh.d_meta = nullptr;
+            sh.q8_capacity = sh.q8_rows = 0;
+            sh.tmap8_valid = false;
+        } else {
+            sh.q8_rows = 0;
+            int rc = q8_refresh(idx, sh, 0, sh.rows);
+            if (rc) return rc;
+        }
+    }
+    return NM_OK;
+}
+
+int nm_index_set_batching(nm_index *idx, int enable) {
+    if (!idx) return fail(NM_ERR_INVALID_ARGUMENT, "null index");
+    idx->batching = enable ? 1 : 0;
+    return NM_OK;
+}
+
+int nm_index_set_profiling(nm_index *idx, int enable) {
+    if (!idx) return fail(NM_ERR_INVALID_ARGUMENT, "null index");
+    idx->profiling = enable ? 1 : 0;
+    return NM_OK;
+}
+
+int nm_index_stats(nm_index *idx, nm_stats *out) {
+    if (!idx || !out) return fail(NM_ERR_INVALID_ARGUMENT, "null argument");
+    out->searches = idx->searches;
+    out->rows_scanned = idx->rows_scanned;
+    out->bytes_streamed = idx->bytes_streamed;
+    out->scan_launches = idx->scan_launches;
+    out->merge_launches = idx->merge_launches;
+    out->h2d_bytes = idx->h2d_bytes;
+    out->d2h_bytes = idx->d2h_bytes;
+    out->last_scan_ms = idx->last_scan_ms;
+    out->prefilter_queries = idx->pf_queries;
+    out->prefilter_fallbacks = idx->pf_fallbacks;
+    out->prefilter_kept = idx->pf_kept;
+    {
+        // fold finished profiling event pairs into the totals (waits for the streams)
+        std::unique_lock<std::shared_mutex> g(idx->mu);
+        for (auto &sh : idx->shards) {
+            cudaSetDevice(sh->device);
+            std::lock_guard<std::mutex> pg(sh->pool_mu);
+            std::vector<Workspace *> all_ws;
+            for (auto &e : sh->stream_ws) all_ws.push_back(e.second.get());
+            for (auto &w : sh->pool) all_ws.push_back(w.get());
+            for (Workspace *wsp : all_ws) {
+                Workspace &ws = *wsp;
+                for (size_t i = 0; i < ws.prof_used; ++i) {
+                    float ms = 0.f;
+                    if (cudaEventSynchronize(ws.prof_events[i].second) == cudaSuccess &&
+                        cudaEventElapsedTime(&ms, ws.prof_events[i].first,
+                                             ws.prof_events[i].second) == cudaSuccess) {
+                        idx->profiled_scan_ms += ms;
+                        idx->profiled_scans += 1;
+                    }
+                }
+                ws.prof_used = 0;
+            }
+        }
+        cudaGetLastError();
+        out->profiled_scan_ms = idx->profiled_scan_ms;
+        out->profiled_scans = idx->profiled_scans;
+    }
+    return NM_OK;
+}
+
+}  // extern "C"

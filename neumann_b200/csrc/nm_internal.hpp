@@ -1,0 +1,262 @@
+// nm_internal.hpp — shared declarations of the host-side translation units:
+//   nm_core.cu    mirror lifecycle, staging, mutations, int8 copy upkeep, statistics
+//   nm_launch.cu  every kernel launch (the only unit that includes the kernel headers)
+//   nm_search.cu  nm_search / nm_search_masked / nm_search_device and their routing
+//   nm_comm.cu    NCCL loader, communicator, CUDA-IPC peer exchange
+#pragma once
+#include "../../include/neumann_b200.h"
+#include "nm_types.hpp"
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <nccl.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cstdint>
+#include <cstring>
+#include <memory>
+#include <mutex>
+#include <shared_mutex>
+#include <string>
+#include <vector>
+
+namespace nmi {
+
+// thread-local last error + nm_status in one call
+int fail(int code, const char *fmt, ...);
+const char *last_error();
+
+#define CUDA_TRY(expr)                                                                          \
+    do {                                                                                        \
+        cudaError_t _e = (expr);                                                                \
+        if (_e != cudaSuccess)                                                                  \
+            return nmi::fail(NM_ERR_STORAGE, "CUDA error %s at %s:%d: %s", cudaGetErrorName(_e), \
+                             __FILE__, __LINE__, cudaGetErrorString(_e));                       \
+    } while (0)
+
+// ---- NCCL, loaded lazily so the library also loads on hosts without it -------------------
+struct NcclApi {
+    void *handle = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t,
+                              cudaStream_t) = nullptr;
+    const char *(*GetErrorString)(ncclResult_t) = nullptr;
+    bool ok = false;
+};
+
+NcclApi &nccl();
+
+#define NCCL_TRY(expr)                                                                       \
+    do {                                                                                     \
+        ncclResult_t _r = (expr);                                                            \
+        if (_r != ncclSuccess)                                                               \
+            return nmi::fail(NM_ERR_STORAGE, "NCCL error at %s:%d: %s", __FILE__, __LINE__,  \
+                             nmi::nccl().GetErrorString(_r));                                \
+    } while (0)
+
+// Per-call scratch on one device.  Pooled per shard so concurrent nm_search calls never share
+// a stream, a candidate buffer or the "last CTA" ticket.
+struct Workspace {
+    int device = -1;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    float *d_query = nullptr;
+    float *h_query = nullptr;  // pinned
+    size_t query_cap = 0;      // floats
+    uint64_t *d_cand = nullptr;
+    size_t cand_cap = 0;  // keys
+    uint32_t *d_counter = nullptr;
+    uint32_t *d_mask = nullptr;       // row bitmask of a pre-filtered search, padded to row blocks
+    size_t mask_cap = 0;              // u32 words
+    uint64_t *d_pass_keys = nullptr;  // [k] merged keys of the chained passes (k > 1024)
+    size_t pass_keys_cap = 0;
+    // packed result block: [counts u32 x nq (8-aligned)] [rows u64 x nq*k] [scores f32 x nq*k]
+    uint8_t *d_result = nullptr;
+    uint8_t *h_result = nullptr;  // pinned
+    size_t result_cap = 0;
+    nm::ShardHit *d_hits = nullptr;  // [nq, k] this shard's hits
+    nm::ShardHit *h_hits = nullptr;  // pinned
+    size_t hits_cap = 0;
+    nm::ShardHit *d_gather = nullptr;  // [n_ranks, nq, k]
+    size_t gather_cap = 0;
+    // pre-filter path (prefilter_kernels.cuh)
+    nm::KeptEntry *d_kept = nullptr;
+    uint64_t *d_exact_keys = nullptr;
+    uint32_t *d_pf_ctl = nullptr;   // [nq][8]
+    uint32_t *h_pf_ctl = nullptr;   // pinned
+    size_t pf_ctl_cap = 0;          // queries
+    // batched-query path (batch_kernels.cuh)
+    float *d_qt = nullptr;         // [n_kc][32][QB] transposed query chunks
+    size_t qt_cap = 0;             // floats
+    float *d_qmag = nullptr;       // [64]
+    float *d_scores = nullptr;     // [QB][score_stride]
+    size_t scores_cap = 0;         // floats
+    uint64_t *d_bcand = nullptr;   // [QB][ctas_per_query][k]
+    size_t bcand_cap = 0;          // keys
+    uint32_t *d_bctl = nullptr;    // [0] cursor [1] done [2..2+64) tickets
+    // profiling ring (nm_index_set_profiling): event pairs around the scan launches of
+    // asynchronous nm_search_device calls, resolved lazily by nm_index_stats
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
+    size_t prof_used = 0;
+
+    ~Workspace() {
+        if (device < 0) return;
+        cudaSetDevice(device);
+        if (d_query) cudaFree(d_query);
+        if (h_query) cudaFreeHost(h_query);
+        if (d_cand) cudaFree(d_cand);
+        if (d_counter) cudaFree(d_counter);
+        if (d_mask) cudaFree(d_mask);
+        if (d_pass_keys) cudaFree(d_pass_keys);
+        if (d_kept) cudaFree(d_kept);
+        if (d_exact_keys) cudaFree(d_exact_keys);
+        if (d_pf_ctl) cudaFree(d_pf_ctl);
+        if (h_pf_ctl) cudaFreeHost(h_pf_ctl);
+        if (d_qt) cudaFree(d_qt);
+        if (d_qmag) cudaFree(d_qmag);
+        if (d_scores) cudaFree(d_scores);
+        if (d_bcand) cudaFree(d_bcand);
+        if (d_bctl) cudaFree(d_bctl);
+        if (d_result) cudaFree(d_result);
+        if (h_result) cudaFreeHost(h_result);
+        if (d_hits) cudaFree(d_hits);
+        if (h_hits) cudaFreeHost(h_hits);
+        if (d_gather) cudaFree(d_gather);
+        if (ev0) cudaEventDestroy(ev0);
+        if (ev1) cudaEventDestroy(ev1);
+        for (auto &pe : prof_events) {
+            cudaEventDestroy(pe.first);
+            cudaEventDestroy(pe.second);
+        }
+        if (stream) cudaStreamDestroy(stream);
+    }
+};
+
+struct Shard {
+    int device = 0;
+    int sm_count = 0;
+    float *d_rows = nullptr;
+    uint64_t rows = 0;      // local rows
+    uint64_t capacity = 0;  // local rows allocated
+    uint64_t row_base = 0;  // global index of local row 0 (within this process)
+    CUtensorMap tmap;
+    bool tmap_valid = false;
+    // int8 pre-filter copy (prefilter_kernels.cuh): [capacity8, pitch8] bytes + 16 B per row
+    int8_t *d_q8 = nullptr;
+    nm::RowMeta *d_meta = nullptr;
+    uint32_t *d_q8_flag = nullptr;
+    uint64_t q8_capacity = 0;
+    uint64_t q8_rows = 0;  // rows [0, q8_rows) are quantised and current
+    CUtensorMap tmap8;
+    bool tmap8_valid = false;
+    cudaStream_t copy_stream = nullptr;
+    float *staging[2] = {nullptr, nullptr};
+    cudaEvent_t staging_done[2] = {nullptr, nullptr};
+    std::mutex pool_mu;
+    std::vector<std::unique_ptr<Workspace>> pool;
+    // Workspaces bound to a caller stream (nm_search_device): work on one stream is ordered,
+    // so the same scratch can be reused by consecutive asynchronous calls without a sync.
+    std::vector<std::pair<cudaStream_t, std::unique_ptr<Workspace>>> stream_ws;
+};
+
+}  // namespace nmi
+
+struct nm_index {
+    uint32_t dim = 0;
+    uint32_t pitch = 0;  // floats per row in device memory
+    std::vector<std::unique_ptr<nmi::Shard>> shards;
+    mutable std::shared_mutex mu;
+    // cross-process sharding
+    ncclComm_t comm = nullptr;
+    int n_ranks = 1, rank = 0;
+    uint64_t comm_row_base = 0;
+    std::mutex comm_mu;  // collective searches are issued one at a time, in call order
+    // peer-memory exchange (CUDA IPC): the fused single-query path writes hits straight into
+    // the peers' mailboxes; NCCL stays for the batched / k > 1024 paths and as a fallback
+    void *xchg_mem = nullptr;                    // local [flags 256 B | mailbox]
+    void *xchg_peer[nm::kMaxRanks] = {nullptr};  // mapped peer buffers (own rank = xchg_mem)
+    bool xchg_ok = false;
+    uint32_t xchg_seq = 0;
+    // counters
+    std::atomic<uint64_t> searches{0}, rows_scanned{0}, bytes_streamed{0}, scan_launches{0},
+        merge_launches{0}, h2d_bytes{0}, d2h_bytes{0};
+    std::atomic<double> last_scan_ms{0.0};
+    std::atomic<int> profiling{0};
+    std::atomic<int> prefilter{0};  // nm_index_set_prefilter: 1 = exact int8 pre-filter
+    std::atomic<uint64_t> pf_queries{0}, pf_fallbacks{0}, pf_kept{0};
+    std::atomic<int> batching{1};  // nm_index_set_batching: 0 forces one scan per query
+    double profiled_scan_ms = 0.0;  // guarded by mu (exclusive) in nm_index_stats
+    uint64_t profiled_scans = 0;
+    uint64_t total_rows() const {
+        uint64_t n = 0;
+        for (auto &s : shards) n += s->rows;
+        return n;
+    }
+};
+
+namespace nmi {
+
+constexpr uint32_t kBatchMinQueries = 8;  // below this, nq single-query passes are cheaper
+
+struct ResultLayout {
+    size_t counts_off, rows_off, scores_off, total;
+};
+inline ResultLayout result_layout(uint32_t nq, uint32_t k) {
+    ResultLayout l;
+    l.counts_off = 0;
+    l.rows_off = ((size_t)nq * 4 + 15) & ~size_t(15);
+    l.scores_off = l.rows_off + (size_t)nq * k * 8;
+    l.total = l.scores_off + (size_t)nq * k * 4;
+    return l;
+}
+inline uint32_t pow2_ceil(uint32_t v) {
+    uint32_t n = 2;
+    while (n < v) n <<= 1;
+    return n;
+}
+
+// ---- nm_core.cu ----
+int build_tmap(nm_index *idx, Shard &sh);
+int q8_refresh(nm_index *idx, Shard &sh, uint64_t first, uint64_t n);
+uint32_t q8_pitch(uint32_t dim);
+
+// ---- nm_launch.cu: workspaces + every kernel launch ----
+int ws_acquire(Shard &sh, std::unique_ptr<Workspace> &out);
+void ws_release(Shard &sh, std::unique_ptr<Workspace> &ws);
+int ws_ensure(Workspace &ws, const Shard &sh, uint32_t dim, uint32_t nq, uint32_t k, bool need_query,
+              bool need_result, bool need_hits, int gather_ranks);
+int ws_ensure_prefilter(Workspace &ws, uint32_t nq);
+uint32_t single_query_stages(uint32_t dim);
+bool batch_eligible(const nm_index *idx, const Shard &sh, uint32_t nq, uint32_t k, int metric);
+bool prefilter_usable(const nm_index *idx, const Shard &sh, uint32_t nq, uint32_t k, int metric,
+                      const uint64_t *row_mask);
+int launch_scan(nm_index *idx, const Shard &sh, Workspace &ws, const float *d_query, uint32_t k,
+                int metric, uint64_t row_base, uint64_t *out_rows, float *out_scores,
+                uint32_t *out_count, nm::ShardHit *out_hits, cudaStream_t stream,
+                const nm::PeerXchg *xchg = nullptr, const uint32_t *d_row_mask = nullptr);
+int scan_queries(nm_index *idx, const Shard &sh, Workspace &ws, const float *d_queries, uint32_t nq,
+                 uint32_t k, int metric, uint64_t row_base, uint64_t *out_rows, float *out_scores,
+                 uint32_t *out_counts, nm::ShardHit *out_hits, cudaStream_t stream);
+int launch_prefiltered(nm_index *idx, const Shard &sh, Workspace &ws, const float *d_query,
+                       uint32_t q, uint32_t k, int metric, uint64_t *out_rows, float *out_scores,
+                       uint32_t *out_count, cudaStream_t stream);
+int launch_merge_shards(nm_index *idx, const nm::ShardHit *d_gather, uint32_t nq, uint32_t k,
+                        uint64_t *out_rows, float *out_scores, uint32_t *out_counts,
+                        cudaStream_t stream);
+int launch_exchange_empty(const nm::PeerXchg &x, uint32_t k, uint64_t *scratch, uint64_t *out_rows,
+                          float *out_scores, uint32_t *out_count, cudaStream_t stream);
+int launch_fill_synthetic(const Shard &sh, float *rows, uint64_t n, uint32_t dim, uint32_t pitch,
+                          uint64_t seed, uint64_t global_row0, cudaStream_t stream);
+int launch_quantize(const Shard &sh, const float *rows, uint32_t pitch, uint32_t dim, uint64_t first,
+                    uint64_t n, int8_t *q8, uint32_t pitch8, nm::RowMeta *meta, uint32_t *flag,
+                    cudaStream_t stream);
+
+// ---- nm_comm.cu ----
+nm::PeerXchg make_xchg(const nm_index *idx, uint32_t seq);
+void setup_peer_exchange(nm_index *idx, cudaStream_t stream);
+void teardown_peer_exchange(nm_index *idx);
+
+}  // namespace nmi

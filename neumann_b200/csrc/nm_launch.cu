@@ -1,0 +1,500 @@
+// nm_launch.cu — per-call workspaces and EVERY kernel launch of the library.  This is the
+// only translation unit that includes the kernel headers (scan / batch / prefilter).
+#include "nm_internal.hpp"
+#include "scan_kernels.cuh"
+#include "batch_kernels.cuh"
+#include "prefilter_kernels.cuh"
+
+namespace nmi {
+
+size_t scan_smem_bytes(uint32_t n_stages, uint32_t q_floats) {
+    return 1024 + (size_t)n_stages * nm::kStageBytes + (size_t)nm::kCandCap * 8 +
+           (size_t)q_floats * 4 + 2 * nm::kMaxStages * 8 + 64 + nm::kMaxStages * 4;
+}
+
+int ws_acquire(Shard &sh, std::unique_ptr<Workspace> &out) {
+    {
+        std::lock_guard<std::mutex> g(sh.pool_mu);
+        if (!sh.pool.empty()) {
+            out = std::move(sh.pool.back());
+            sh.pool.pop_back();
+            return NM_OK;
+        }
+    }
+    std::unique_ptr<Workspace> ws(new Workspace());
+    ws->device = sh.device;
+    CUDA_TRY(cudaStreamCreateWithFlags(&ws->stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaEventCreate(&ws->ev0));
+    CUDA_TRY(cudaEventCreate(&ws->ev1));
+    CUDA_TRY(cudaMalloc(&ws->d_counter, 2 * sizeof(uint32_t)));
+    CUDA_TRY(cudaMemsetAsync(ws->d_counter, 0, 2 * sizeof(uint32_t), ws->stream));
+    out = std::move(ws);
+    return NM_OK;
+}
+
+void ws_release(Shard &sh, std::unique_ptr<Workspace> &ws) {
+    if (!ws) return;
+    std::lock_guard<std::mutex> g(sh.pool_mu);
+    sh.pool.push_back(std::move(ws));
+}
+
+int ws_ensure(Workspace &ws, const Shard &sh, uint32_t dim, uint32_t nq, uint32_t k,
+              bool need_query, bool need_result, bool need_hits, int gather_ranks) {
+    size_t qf = (size_t)nq * dim;
+    if (need_query && ws.query_cap < qf) {
+        if (ws.d_query) CUDA_TRY(cudaFree(ws.d_query));
+        if (ws.h_query) CUDA_TRY(cudaFreeHost(ws.h_query));
+        ws.query_cap = 0;
+        CUDA_TRY(cudaMalloc(&ws.d_query, qf * 4));
+        CUDA_TRY(cudaMallocHost(&ws.h_query, qf * 4));
+        ws.query_cap = qf;
+    }
+    size_t cand = (size_t)sh.sm_count * std::min<uint32_t>(k, nm::kMaxFastK);
+    if (ws.cand_cap < cand) {
+        if (ws.d_cand) CUDA_TRY(cudaFree(ws.d_cand));
+        ws.cand_cap = 0;
+        CUDA_TRY(cudaMalloc(&ws.d_cand, cand * 8));
+        ws.cand_cap = cand;
+    }
+    if (need_result) {
+        ResultLayout l = result_layout(nq, k);
+        if (ws.result_cap < l.total) {
+            if (ws.d_result) CUDA_TRY(cudaFree(ws.d_result));
+            if (ws.h_result) CUDA_TRY(cudaFreeHost(ws.h_result));
+            ws.result_cap = 0;
+            CUDA_TRY(cudaMalloc(&ws.d_result, l.total));
+            CUDA_TRY(cudaMallocHost(&ws.h_result, l.total));
+            ws.result_cap = l.total;
+        }
+    }
+    if (need_hits) {
+        size_t h = (size_t)nq * k;
+        if (ws.hits_cap < h) {
+            if (ws.d_hits) CUDA_TRY(cudaFree(ws.d_hits));
+            if (ws.h_hits) CUDA_TRY(cudaFreeHost(ws.h_hits));
+            ws.hits_cap = 0;
+            CUDA_TRY(cudaMalloc(&ws.d_hits, h * sizeof(nm::ShardHit)));
+            CUDA_TRY(cudaMallocHost(&ws.h_hits, h * sizeof(nm::ShardHit)));
+            ws.hits_cap = h;
+        }
+        size_t g = h * (size_t)gather_ranks;
+        if (gather_ranks > 0 && ws.gather_cap < g) {
+            if (ws.d_gather) CUDA_TRY(cudaFree(ws.d_gather));
+            ws.gather_cap = 0;
+            CUDA_TRY(cudaMalloc(&ws.d_gather, g * sizeof(nm::ShardHit)));
+            ws.gather_cap = g;
+        }
+    }
+    return NM_OK;
+}
+
+template <int METRIC>
+int launch_scan_t(const Shard &sh, const nm::ScanParams &p, size_t smem, cudaStream_t stream) {
+    // The dynamic-smem opt-in is a per-function, per-device attribute shared by all host
+    // threads: raise it once to the architectural maximum and never lower it.
+    static std::mutex mu;
+    static bool configured[64] = {false};
+    auto kern = nm::scan_topk_kernel<METRIC>;
+    {
+        std::lock_guard<std::mutex> g(mu);
+        if (sh.device >= 64 || !configured[sh.device]) {
+            CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          227 * 1024));
+            if (sh.device < 64) configured[sh.device] = true;
+        }
+    }
+    uint32_t n_rb = (p.n_rows + nm::kRowsPerBlock - 1) / nm::kRowsPerBlock;
+    uint32_t grid = std::min<uint32_t>((uint32_t)sh.sm_count, n_rb);
+    kern<<<grid, nm::kScanThreads, smem, stream>>>(sh.tmap, p);
+    CUDA_TRY(cudaGetLastError());
+    return NM_OK;
+}
+
+// One query over one shard: a single launch for k <= 1024, otherwise ceil(k/1024) chained
+// passes, each admitting only keys below the previous pass's last key.
+int launch_scan(nm_index *idx, const Shard &sh, Workspace &ws, const float *d_query, uint32_t k,
+                int metric, uint64_t row_base, uint64_t *out_rows, float *out_scores,
+                uint32_t *out_count, nm::ShardHit *out_hits, cudaStream_t stream,
+                const nm::PeerXchg *xchg, const uint32_t *d_row_mask) {
+    nm::ScanParams p;
+    memset(&p, 0, sizeof(p));
+    if (xchg) p.xchg = *xchg;
+    p.row_mask = d_row_mask;
+    p.query = d_query;
+    p.cand = ws.d_cand;
+    p.done_counter = ws.d_counter;
+    p.row_base = row_base;
+    p.n_rows = (uint32_t)sh.rows;
+    p.dim = idx->dim;
+    p.q_floats = (idx->dim + 31u) & ~31u;
+    // stream through L2 with evict_first unless the whole shard fits comfortably in L2
+    p.evict_first = (sh.rows * idx->pitch * 4ull > (64ull << 20)) ? 1u : 0u;
+    uint32_t stages = nm::kMaxStages;
+    const size_t limit = 227 * 1024;
+    while (stages > 2 && scan_smem_bytes(stages, p.q_floats) > limit) --stages;
+    if (scan_smem_bytes(stages, p.q_floats) > limit)
+        return fail(NM_ERR_DIMENSION_MISMATCH,
+                    "dimension %u does not fit the scan kernel's shared-memory query buffer",
+                    idx->dim);
+    p.n_stages = stages;
+    size_t smem = scan_smem_bytes(stages, p.q_floats);
+    const bool chained = k > (uint32_t)nm::kMaxFastK;
+    if (chained) {
+        if (ws.pass_keys_cap < k) {
+            if (ws.d_pass_keys) {
+                CUDA_TRY(cudaStreamSynchronize(stream));
+                CUDA_TRY(cudaFree(ws.d_pass_keys));
+            }
+            ws.pass_keys_cap = 0;
+            CUDA_TRY(cudaMalloc(&ws.d_pass_keys, (size_t)k * 8));
+            ws.pass_keys_cap = k;
+        }
+        if (out_count) CUDA_TRY(cudaMemsetAsync(out_count, 0, 4, stream));
+    }
+    // never ask for more hits than the shard has rows (slots past that stay empty)
+    // (the fused exchange needs the same k on every rank, whatever the local row count)
+    const uint32_t k_need = xchg ? k : (uint32_t)std::min<uint64_t>(k, sh.rows);
+    if (out_hits && k_need < k)
+        CUDA_TRY(cudaMemsetAsync(out_hits + k_need, 0, (size_t)(k - k_need) * sizeof(nm::ShardHit),
+                                 stream));
+    for (uint32_t done = 0; done < k_need; done += nm::kMaxFastK) {
+        const uint32_t kp = std::min<uint32_t>(nm::kMaxFastK, k_need - done);
+        p.k = kp;
+        p.out_keys = chained ? ws.d_pass_keys + done : nullptr;
+        p.out_hits = out_hits ? out_hits + done : nullptr;
+        p.out_rows = out_rows ? out_rows + done : nullptr;
+        p.out_scores = out_scores ? out_scores + done : nullptr;
+        p.out_count = out_count;
+        p.accumulate_count = chained ? 1u : 0u;
+        // the previous pass always has kMaxFastK slots; its last one is 0 when it ran dry
+        p.key_ceiling = done ? ws.d_pass_keys + done - 1 : nullptr;
+        idx->scan_launches++;
+        int rc;
+        switch (metric) {
+        case NM_COSINE: rc = launch_scan_t<nm::kCosine>(sh, p, smem, stream); break;
+        case NM_EUCLIDEAN: rc = launch_scan_t<nm::kEuclidean>(sh, p, smem, stream); break;
+        default: rc = launch_scan_t<nm::kDot>(sh, p, smem, stream); break;
+        }
+        if (rc) return rc;
+    }
+    return NM_OK;
+}
+
+
+// ---- batched-query path ----------------------------------------------------------------
+constexpr int kBatchMaxQB = 64;
+
+template <int METRIC, int QB>
+int launch_score_batch_t(const Shard &sh, const nm::BatchScoreParams &p, cudaStream_t stream) {
+    static std::mutex mu;
+    static bool configured[64] = {false};
+    auto kern = nm::score_batch_kernel<METRIC, QB>;
+    {
+        std::lock_guard<std::mutex> g(mu);
+        if (sh.device >= 64 || !configured[sh.device]) {
+            CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          227 * 1024));
+            if (sh.device < 64) configured[sh.device] = true;
+        }
+    }
+    size_t smem = 1024 + (size_t)p.n_stages * nm::batch_stage_bytes<QB>() + 2 * nm::kMaxStages * 8 +
+                  nm::kMaxStages * 4 + QB * 4 + 64;
+    uint32_t n_rb = (p.n_rows + nm::kRowsPerBlock - 1) / nm::kRowsPerBlock;
+    uint32_t grid = std::min<uint32_t>((uint32_t)sh.sm_count, n_rb);
+    kern<<<grid, nm::kScanThreads, smem, stream>>>(sh.tmap, p);
+    CUDA_TRY(cudaGetLastError());
+    return NM_OK;
+}
+
+template <int QB>
+uint32_t batch_stages() {
+    uint32_t st = nm::kMaxStages;
+    while (st > 2 && 1024 + (size_t)st * nm::batch_stage_bytes<QB>() + 512 + QB * 4 > 227 * 1024) --st;
+    return st;
+}
+
+// Stages the single-query kernel can afford once the whole query sits in shared memory.
+uint32_t single_query_stages(uint32_t dim) {
+    const uint32_t q_floats = (dim + 31u) & ~31u;
+    uint32_t stages = nm::kMaxStages;
+    while (stages > 0 && scan_smem_bytes(stages, q_floats) > 227 * 1024) --stages;
+    return stages;
+}
+
+bool batch_eligible(const nm_index *idx, const Shard &sh, uint32_t nq, uint32_t k, int metric) {
+    // very long vectors: the single-query kernel keeps the query in shared memory and runs out
+    // of stages; the batched kernels stream the query chunk by chunk, so they take over
+    const bool long_rows = single_query_stages(idx->dim) < 4;
+    if ((nq < kBatchMinQueries && !long_rows) || sh.rows == 0) return false;
+    if (std::min<uint64_t>(k, sh.rows) > (uint64_t)nm::kMaxFastK) return false;
+    // dot/cosine lanes need whole f32x8 groups; the scalar tail only exists on the 1-query path
+    if (metric != NM_EUCLIDEAN && (idx->dim % 8u) != 0) return false;
+    return true;
+}
+
+// All nq queries over one shard through the batched kernels.  Returns NM_OK, an error, or
+// -1 when the score matrix cannot be allocated (caller falls back to single-query passes).
+int scan_queries_batched(nm_index *idx, const Shard &sh, Workspace &ws, const float *d_queries,
+                         uint32_t nq, uint32_t k, int metric, uint64_t row_base,
+                         uint64_t *out_rows, float *out_scores, uint32_t *out_counts,
+                         nm::ShardHit *out_hits, cudaStream_t stream) {
+    const uint32_t dim = idx->dim;
+    const uint32_t n_kc = (dim + 31u) / 32u;
+    const uint32_t k_eff = (uint32_t)std::min<uint64_t>(k, sh.rows);
+    const uint32_t n_rb = ((uint32_t)sh.rows + nm::kRowsPerBlock - 1) / nm::kRowsPerBlock;
+    const uint64_t stride = ((uint64_t)sh.rows + 63u) & ~uint64_t(63);
+    const uint32_t qb_max = (metric == NM_EUCLIDEAN) ? (nq > 16 ? 64u : 16u) : 16u;
+    // scratch
+    if (!ws.d_bctl) {
+        CUDA_TRY(cudaMalloc(&ws.d_bctl, (2 + kBatchMaxQB) * sizeof(uint32_t)));
+        CUDA_TRY(cudaMemsetAsync(ws.d_bctl, 0, (2 + kBatchMaxQB) * sizeof(uint32_t), stream));
+        CUDA_TRY(cudaMalloc(&ws.d_qmag, kBatchMaxQB * sizeof(float)));
+    }
+    size_t need_qt = (size_t)n_kc * 32u * qb_max;
+    size_t need_scores = (size_t)qb_max * stride;
+    uint32_t ctas_per_q = std::max<uint32_t>(1u, std::min<uint32_t>(n_rb, (2u * sh.sm_count + qb_max - 1) / qb_max));
+    size_t need_cand = (size_t)qb_max * ctas_per_q * k_eff;
+    if (ws.qt_cap < need_qt || ws.scores_cap < need_scores || ws.bcand_cap < need_cand)
+        CUDA_TRY(cudaStreamSynchronize(stream));  // earlier launches may still read the old buffers
+    if (ws.qt_cap < need_qt) {
+        if (ws.d_qt) CUDA_TRY(cudaFree(ws.d_qt));
+        ws.qt_cap = 0;
+        CUDA_TRY(cudaMalloc(&ws.d_qt, need_qt * 4));
+        ws.qt_cap = need_qt;
+    }
+    if (ws.scores_cap < need_scores) {
+        if (ws.d_scores) CUDA_TRY(cudaFree(ws.d_scores));
+        ws.scores_cap = 0;
+        if (cudaMalloc(&ws.d_scores, need_scores * 4) != cudaSuccess) {
+            cudaGetLastError();
+            ws.d_scores = nullptr;
+            return -1;
+        }
+        ws.scores_cap = need_scores;
+    }
+    if (ws.bcand_cap < need_cand) {
+        if (ws.d_bcand) CUDA_TRY(cudaFree(ws.d_bcand));
+        ws.bcand_cap = 0;
+        CUDA_TRY(cudaMalloc(&ws.d_bcand, need_cand * 8));
+        ws.bcand_cap = need_cand;
+    }
+    if (out_hits && k_eff < k)
+        CUDA_TRY(cudaMemsetAsync(out_hits, 0, (size_t)nq * k * sizeof(nm::ShardHit), stream));
+
+    for (uint32_t q0 = 0; q0 < nq; q0 += qb_max) {
+        const uint32_t nqp = std::min<uint32_t>(qb_max, nq - q0);
+        const uint32_t qb = (qb_max == 64u && nqp <= 16u) ? 16u : qb_max;
+        nm::prepare_batch_kernel<<<std::max<uint32_t>(8u, (n_kc * 32u * qb + 255u) / 256u), 256, 0, stream>>>(
+            d_queries + (size_t)q0 * dim, nqp, dim, qb, n_kc, ws.d_qt, ws.d_qmag);
+        CUDA_TRY(cudaGetLastError());
+        nm::BatchScoreParams sp;
+        memset(&sp, 0, sizeof(sp));
+        sp.qt = ws.d_qt;
+        sp.qmag = ws.d_qmag;
+        sp.scores = ws.d_scores;
+        sp.cursor = ws.d_bctl;
+        sp.done = ws.d_bctl + 1;
+        sp.score_stride = stride;
+        sp.n_rows = (uint32_t)sh.rows;
+        sp.dim = dim;
+        sp.evict_first = (sh.rows * idx->pitch * 4ull > (64ull << 20)) ? 1u : 0u;
+        int rc;
+        if (metric == NM_EUCLIDEAN) {
+            if (qb == 64u) {
+                sp.n_stages = batch_stages<64>();
+                rc = launch_score_batch_t<nm::kEuclidean, 64>(sh, sp, stream);
+            } else {
+                sp.n_stages = batch_stages<16>();
+                rc = launch_score_batch_t<nm::kEuclidean, 16>(sh, sp, stream);
+            }
+        } else if (metric == NM_COSINE) {
+            sp.n_stages = batch_stages<16>();
+            rc = launch_score_batch_t<nm::kCosine, 16>(sh, sp, stream);
+        } else {
+            sp.n_stages = batch_stages<16>();
+            rc = launch_score_batch_t<nm::kDot, 16>(sh, sp, stream);
+        }
+        if (rc) return rc;
+        nm::BatchSelectParams bp;
+        memset(&bp, 0, sizeof(bp));
+        bp.scores = ws.d_scores;
+        bp.score_stride = stride;
+        bp.cand = ws.d_bcand;
+        bp.tickets = ws.d_bctl + 2;
+        bp.out_hits = out_hits ? out_hits + (size_t)q0 * k : nullptr;
+        bp.out_rows = out_rows ? out_rows + (size_t)q0 * k : nullptr;
+        bp.out_scores = out_scores ? out_scores + (size_t)q0 * k : nullptr;
+        bp.out_counts = out_counts ? out_counts + q0 : nullptr;
+        bp.row_base = row_base;
+        bp.out_stride = k;
+        bp.n_rows = (uint32_t)sh.rows;
+        bp.k = k_eff;
+        dim3 grid(ctas_per_q, nqp);
+        nm::select_batch_kernel<<<grid, nm::kRowsPerBlock, 0, stream>>>(bp);
+        CUDA_TRY(cudaGetLastError());
+        idx->scan_launches += 3;
+    }
+    return NM_OK;
+}
+
+
+// ---- exact int8 pre-filter path (single shard, host-synchronous nm_search only) -----------
+size_t prefilter_smem_bytes(uint32_t n_stages, uint32_t q_words) {
+    return 1024 + (size_t)n_stages * nm::kStageBytes + (size_t)nm::kCandCap * 8 +
+           (size_t)q_words * 4 + 2 * nm::kMaxStages * 8 + 256 +
+           (size_t)nm::kKeptStage * sizeof(nm::KeptEntry);
+}
+
+bool prefilter_usable(const nm_index *idx, const Shard &sh, uint32_t nq, uint32_t k, int metric,
+                      const uint64_t *row_mask) {
+    if (!idx->prefilter.load() || row_mask || metric == NM_EUCLIDEAN) return false;
+    if (!sh.tmap8_valid || sh.q8_rows != sh.rows || sh.rows == 0) return false;
+    if (k > (uint32_t)nm::kMaxFastK || k > sh.rows) return false;
+    if (idx->batching.load() && nq >= kBatchMinQueries && (idx->dim % 8u) == 0) return false;
+    uint32_t q_words = ((idx->dim + 127u) / 128u) * 32u;
+    return prefilter_smem_bytes(3, q_words) <= 227 * 1024;
+}
+
+int ws_ensure_prefilter(Workspace &ws, uint32_t nq) {
+    if (!ws.d_kept) {
+        CUDA_TRY(cudaMalloc(&ws.d_kept, (size_t)nm::kKeptCap * sizeof(nm::KeptEntry)));
+        CUDA_TRY(cudaMalloc(&ws.d_exact_keys, (size_t)nm::kKeptCap * sizeof(uint64_t)));
+    }
+    if (ws.pf_ctl_cap < nq) {
+        if (ws.d_pf_ctl) CUDA_TRY(cudaFree(ws.d_pf_ctl));
+        if (ws.h_pf_ctl) CUDA_TRY(cudaFreeHost(ws.h_pf_ctl));
+        ws.pf_ctl_cap = 0;
+        CUDA_TRY(cudaMalloc(&ws.d_pf_ctl, (size_t)nq * 8 * sizeof(uint32_t)));
+        CUDA_TRY(cudaMallocHost(&ws.h_pf_ctl, (size_t)nq * 8 * sizeof(uint32_t)));
+        ws.pf_ctl_cap = nq;
+    }
+    return NM_OK;
+}
+
+// Two launches per query: int8 scan (intervals, kept list, k-th best lower bound), then exact
+// re-score + selection.  ctl block q keeps the status for the host to inspect afterwards.
+int launch_prefiltered(nm_index *idx, const Shard &sh, Workspace &ws, const float *d_query,
+                       uint32_t q, uint32_t k, int metric, uint64_t *out_rows, float *out_scores,
+                       uint32_t *out_count, cudaStream_t stream) {
+    static std::mutex mu;
+    static bool configured[64] = {false};
+    {
+        std::lock_guard<std::mutex> g(mu);
+        if (sh.device >= 64 || !configured[sh.device]) {
+            CUDA_TRY(cudaFuncSetAttribute(nm::prefilter_scan_kernel,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            if (sh.device < 64) configured[sh.device] = true;
+        }
+    }
+    uint32_t *ctl = ws.d_pf_ctl + (size_t)q * 8;
+    CUDA_TRY(cudaMemsetAsync(ctl, 0, 8 * sizeof(uint32_t), stream));
+    nm::PrefilterParams p;
+    memset(&p, 0, sizeof(p));
+    p.query = d_query;
+    p.meta = sh.d_meta;
+    p.cand = ws.d_cand;
+    p.ctl = ctl;
+    p.kept = ws.d_kept;
+    p.n_rows = (uint32_t)sh.rows;
+    p.dim = idx->dim;
+    p.k = k;
+    p.q_words = ((idx->dim + 127u) / 128u) * 32u;
+    p.metric = metric == NM_COSINE ? nm::kCosine : nm::kDot;
+    uint32_t stages = nm::kMaxStages;
+    while (stages > 3 && prefilter_smem_bytes(stages, p.q_words) > 227 * 1024) --stages;
+    p.n_stages = stages;
+    const uint32_t n_rb = ((uint32_t)sh.rows + nm::kRowsPerBlock - 1) / nm::kRowsPerBlock;
+    const uint32_t grid = std::min<uint32_t>((uint32_t)sh.sm_count, n_rb);
+    nm::prefilter_scan_kernel<<<grid, nm::kScanThreads, prefilter_smem_bytes(stages, p.q_words),
+                                stream>>>(sh.tmap8, p);
+    CUDA_TRY(cudaGetLastError());
+    nm::RescoreParams r;
+    memset(&r, 0, sizeof(r));
+    r.query = d_query;
+    r.rows = sh.d_rows;
+    r.pitch = idx->pitch;
+    r.dim = idx->dim;
+    r.kept = ws.d_kept;
+    r.ctl = ctl;
+    r.exact_keys = ws.d_exact_keys;
+    r.out_rows = out_rows;
+    r.out_scores = out_scores;
+    r.out_count = out_count;
+    r.row_base = sh.row_base;
+    r.k = k;
+    r.metric = p.metric;
+    nm::prefilter_rescore_kernel<<<(uint32_t)sh.sm_count, nm::kRowsPerBlock, 0, stream>>>(r);
+    CUDA_TRY(cudaGetLastError());
+    idx->scan_launches += 2;
+    return NM_OK;
+}
+
+// nq queries over one shard: batched kernels when that pays, else one (chained) scan per query.
+int scan_queries(nm_index *idx, const Shard &sh, Workspace &ws, const float *d_queries,
+                 uint32_t nq, uint32_t k, int metric, uint64_t row_base, uint64_t *out_rows,
+                 float *out_scores, uint32_t *out_counts, nm::ShardHit *out_hits,
+                 cudaStream_t stream) {
+    if ((idx->batching.load() || single_query_stages(idx->dim) < 2) &&
+        batch_eligible(idx, sh, nq, k, metric)) {
+        int rc = scan_queries_batched(idx, sh, ws, d_queries, nq, k, metric, row_base, out_rows,
+                                      out_scores, out_counts, out_hits, stream);
+        if (rc != -1) return rc;
+    }
+    for (uint32_t q = 0; q < nq; ++q) {
+        int rc = launch_scan(idx, sh, ws, d_queries + (size_t)q * idx->dim, k, metric, row_base,
+                             out_rows ? out_rows + (size_t)q * k : nullptr,
+                             out_scores ? out_scores + (size_t)q * k : nullptr,
+                             out_counts ? out_counts + q : nullptr,
+                             out_hits ? out_hits + (size_t)q * k : nullptr, stream);
+        if (rc) return rc;
+    }
+    return NM_OK;
+}
+
+
+
+int launch_merge_shards(nm_index *idx, const nm::ShardHit *d_gather, uint32_t nq, uint32_t k,
+                        uint64_t *out_rows, float *out_scores, uint32_t *out_counts,
+                        cudaStream_t stream) {
+    const uint32_t total = (uint32_t)idx->n_ranks * k;
+    const uint32_t n_sort = pow2_ceil(total);
+    const size_t msmem = (size_t)n_sort * 8;
+    if (msmem > 200 * 1024)
+        return fail(NM_ERR_INVALID_TOP_K, "n_ranks*k = %u too large for the merge kernel", total);
+    if (msmem > 48 * 1024)
+        CUDA_TRY(cudaFuncSetAttribute(nm::merge_shards_kernel,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    nm::merge_shards_kernel<<<nq, nm::kMergeThreads, msmem, stream>>>(
+        d_gather, (uint32_t)idx->n_ranks, k, nq * k, n_sort, out_rows, out_scores, out_counts);
+    CUDA_TRY(cudaGetLastError());
+    idx->merge_launches++;
+    return NM_OK;
+}
+
+int launch_exchange_empty(const nm::PeerXchg &x, uint32_t k, uint64_t *scratch, uint64_t *out_rows,
+                          float *out_scores, uint32_t *out_count, cudaStream_t stream) {
+    nm::exchange_empty_shard_kernel<<<1, nm::kRowsPerBlock, 0, stream>>>(x, k, scratch, out_rows,
+                                                                         out_scores, out_count);
+    CUDA_TRY(cudaGetLastError());
+    return NM_OK;
+}
+
+int launch_fill_synthetic(const Shard &sh, float *rows, uint64_t n, uint32_t dim, uint32_t pitch,
+                          uint64_t seed, uint64_t global_row0, cudaStream_t stream) {
+    nm::fill_synthetic_kernel<<<sh.sm_count * 8, 256, 0, stream>>>(rows, n, dim, pitch, seed,
+                                                                   global_row0);
+    CUDA_TRY(cudaGetLastError());
+    return NM_OK;
+}
+
+int launch_quantize(const Shard &sh, const float *rows, uint32_t pitch, uint32_t dim, uint64_t first,
+                    uint64_t n, int8_t *q8, uint32_t pitch8, nm::RowMeta *meta, uint32_t *flag,
+                    cudaStream_t stream) {
+    uint32_t blocks = (uint32_t)std::min<uint64_t>((n + 7) / 8, (uint64_t)sh.sm_count * 16);
+    nm::quantize_rows_kernel<<<blocks, 256, 0, stream>>>(rows, pitch, dim, first, n, q8, pitch8, meta,
+                                                         flag);
+    CUDA_TRY(cudaGetLastError());
+    return NM_OK;
+}
+
+}  // namespace nmi

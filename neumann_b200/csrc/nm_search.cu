@@ -1,0 +1,448 @@
+// nm_search.cu — nm_search / nm_search_masked / nm_search_device: validation, routing between
+// the single-query scan, the batched kernels, the int8 pre-filter, the fused peer exchange and
+// the NCCL all-gather path, and the host-side merge of in-process multi-device indexes.
+#include "nm_internal.hpp"
+
+using namespace nmi;
+
+namespace {
+
+struct HostHit {
+    uint32_t ord;
+    uint32_t score_bits;
+    uint64_t row;
+    uint64_t pos;
+};
+
+int validate_search(const nm_index *idx, const void *queries, uint32_t nq, uint32_t k, int metric,
+                    const void *out_rows, const void *out_scores, const void *out_counts) {
+    if (!idx) return fail(NM_ERR_INVALID_ARGUMENT, "null index");
+    if (nq == 0 || idx->dim == 0) return fail(NM_ERR_EMPTY_VECTOR, "empty query");
+    if (k == 0) return fail(NM_ERR_INVALID_TOP_K, "top_k must be >= 1");
+    if (!queries || !out_rows || !out_scores || !out_counts)
+        return fail(NM_ERR_INVALID_ARGUMENT, "null buffer");
+    if (metric < 0 || metric > 2) return fail(NM_ERR_INVALID_ARGUMENT, "unknown metric %d", metric);
+    return NM_OK;
+}
+
+
+
+// Packed result block device -> pinned host -> caller buffers; one D2H copy, one sync.
+int download_results(nm_index *idx, const Shard &sh, Workspace &ws, const ResultLayout &l,
+                     uint32_t nq, uint32_t k, uint64_t *out_rows, float *out_scores,
+                     uint32_t *out_counts) {
+    CUDA_TRY(cudaMemcpyAsync(ws.h_result, ws.d_result, l.total, cudaMemcpyDeviceToHost, ws.stream));
+    CUDA_TRY(cudaStreamSynchronize(ws.stream));
+    float ms = 0.f;
+    CUDA_TRY(cudaEventElapsedTime(&ms, ws.ev0, ws.ev1));
+    idx->last_scan_ms = ms;
+    const uint32_t *hc = reinterpret_cast<const uint32_t *>(ws.h_result + l.counts_off);
+    const uint64_t *hr = reinterpret_cast<const uint64_t *>(ws.h_result + l.rows_off);
+    const float *hs = reinterpret_cast<const float *>(ws.h_result + l.scores_off);
+    for (uint32_t q = 0; q < nq; ++q) {
+        if (hc[q] == 0xffffffffu)  // poisoned by the exchange watchdog
+            return fail(NM_ERR_STORAGE, "peer exchange timed out waiting for another rank");
+        out_counts[q] = hc[q];
+        memcpy(out_rows + (size_t)q * k, hr + (size_t)q * k, (size_t)hc[q] * 8);
+        memcpy(out_scores + (size_t)q * k, hs + (size_t)q * k, (size_t)hc[q] * 4);
+    }
+    idx->searches += nq;
+    idx->rows_scanned += (uint64_t)nq * sh.rows;
+    idx->bytes_streamed += (uint64_t)nq * sh.rows * idx->dim * 4;
+    idx->h2d_bytes += (uint64_t)nq * idx->dim * 4;
+    idx->d2h_bytes += l.total;
+    return NM_OK;
+}
+
+// Rank-independent routing decision for collective searches (every rank must agree).
+bool collective_uses_fused_exchange(const nm_index *idx, uint32_t nq, uint32_t k, int metric) {
+    if (!idx->xchg_ok || k > (uint32_t)nm::kMaxFastK) return false;
+    const bool long_rows = single_query_stages(idx->dim) < 4;
+    const bool would_batch = (idx->batching.load() || single_query_stages(idx->dim) < 2) &&
+                             (nq >= kBatchMinQueries || long_rows) &&
+                             (metric == NM_EUCLIDEAN || (idx->dim % 8u) == 0);
+    return !would_batch;
+}
+
+// One fused launch per query: scan + peer-memory exchange + merge, results written in place.
+int collective_fused(nm_index *idx, const Shard &sh, Workspace &ws, const float *d_queries,
+                     uint32_t nq, uint32_t k, int metric, uint64_t *out_rows, float *out_scores,
+                     uint32_t *out_counts, cudaStream_t stream) {
+    for (uint32_t q = 0; q < nq; ++q) {
+        nm::PeerXchg x = make_xchg(idx, ++idx->xchg_seq);
+        if (sh.rows == 0) {
+            int rc = launch_exchange_empty(x, k, ws.d_cand, out_rows + (size_t)q * k,
+                                           out_scores + (size_t)q * k, out_counts + q, stream);
+            if (rc) return rc;
+            idx->merge_launches++;
+        } else {
+            int rc = launch_scan(idx, sh, ws, d_queries + (size_t)q * idx->dim, k, metric,
+                                 idx->comm_row_base, out_rows + (size_t)q * k,
+                                 out_scores + (size_t)q * k, out_counts + q, nullptr, stream, &x);
+            if (rc) return rc;
+        }
+    }
+    return NM_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+static int search_impl(nm_index *idx, const float *queries, uint32_t nq, uint32_t k, int metric,
+                       const uint64_t *row_mask, uint64_t *out_rows, float *out_scores,
+                       uint32_t *out_counts) {
+    int rc = validate_search(idx, queries, nq, k, metric, out_rows, out_scores, out_counts);
+    if (rc) return rc;
+    std::shared_lock<std::shared_mutex> g(idx->mu);
+    const size_t G = idx->shards.size();
+    const uint32_t dim = idx->dim;
+    const bool collective = idx->comm != nullptr;
+    if (collective && G != 1)
+        return fail(NM_ERR_CONFIGURATION, "a communicator needs a single-device index per rank");
+    if (row_mask && (collective || G != 1))
+        return fail(NM_ERR_CONFIGURATION,
+                    "nm_search_masked needs a single-device index without a communicator");
+
+    // ---- fast path: one device, no communicator: the kernel writes the final result ----
+    if (G == 1 && !collective) {
+        Shard &sh = *idx->shards[0];
+        if (sh.rows == 0) {
+            for (uint32_t q = 0; q < nq; ++q) out_counts[q] = 0;
+            return NM_OK;
+        }
+        CUDA_TRY(cudaSetDevice(sh.device));
+        std::unique_ptr<Workspace> ws;
+        rc = ws_acquire(sh, ws);
+        if (rc) return rc;
+        struct Releaser {
+            Shard &s;
+            std::unique_ptr<Workspace> &w;
+            ~Releaser() { ws_release(s, w); }
+        } rel{sh, ws};
+        rc = ws_ensure(*ws, sh, dim, nq, k, true, true, false, 0);
+        if (rc) return rc;
+        ResultLayout l = result_layout(nq, k);
+        memcpy(ws->h_query, queries, (size_t)nq * dim * 4);
+        CUDA_TRY(cudaMemcpyAsync(ws->d_query, ws->h_query, (size_t)nq * dim * 4,
+                                 cudaMemcpyHostToDevice, ws->stream));
+        uint64_t *r_rows = reinterpret_cast<uint64_t *>(ws->d_result + l.rows_off);
+        float *r_scores = reinterpret_cast<float *>(ws->d_result + l.scores_off);
+        uint32_t *r_counts = reinterpret_cast<uint32_t *>(ws->d_result + l.counts_off);
+        if (row_mask) {
+            // stage the bitmask (bit r of word r/64 == bit r%32 of u32 word r/32 on little
+            // endian hosts), padded with zeros to whole row blocks
+            const size_t words = (((size_t)sh.rows + 255) / 256) * 8;
+            const size_t src_bytes = (((size_t)sh.rows + 63) / 64) * 8;
+            if (ws->mask_cap < words) {
+                if (ws->d_mask) CUDA_TRY(cudaFree(ws->d_mask));
+                ws->mask_cap = 0;
+                CUDA_TRY(cudaMalloc(&ws->d_mask, words * 4));
+                ws->mask_cap = words;
+            }
+            CUDA_TRY(cudaMemsetAsync(ws->d_mask, 0, words * 4, ws->stream));
+            CUDA_TRY(cudaMemcpyAsync(ws->d_mask, row_mask, src_bytes, cudaMemcpyHostToDevice,
+                                     ws->stream));
+            idx->h2d_bytes += src_bytes;
+        }
+        CUDA_TRY(cudaEventRecord(ws->ev0, ws->stream));
+        if (row_mask) {
+            for (uint32_t q = 0; q < nq; ++q) {
+                rc = launch_scan(idx, sh, *ws, ws->d_query + (size_t)q * dim, k, metric, sh.row_base,
+                                 r_rows + (size_t)q * k, r_scores + (size_t)q * k, r_counts + q,
+                                 nullptr, ws->stream, nullptr, ws->d_mask);
+                if (rc) return rc;
+            }
+        } else if (prefilter_usable(idx, sh, nq, k, metric, row_mask)) {
+            rc = ws_ensure_prefilter(*ws, nq);
+            if (rc) return rc;
+            for (uint32_t q = 0; q < nq; ++q) {
+                rc = launch_prefiltered(idx, sh, *ws, ws->d_query + (size_t)q * dim, q, k, metric,
+                                        r_rows + (size_t)q * k, r_scores + (size_t)q * k,
+                                        r_counts + q, ws->stream);
+                if (rc) return rc;
+            }
+            // status words come back with the results (one sync); queries whose candidate list
+            // overflowed (or whose query is not finite) are redone with the exact f32 scan
+            CUDA_TRY(cudaMemcpyAsync(ws->h_pf_ctl, ws->d_pf_ctl, (size_t)nq * 8 * sizeof(uint32_t),
+                                     cudaMemcpyDeviceToHost, ws->stream));
+            CUDA_TRY(cudaEventRecord(ws->ev1, ws->stream));
+            CUDA_TRY(cudaMemcpyAsync(ws->h_result, ws->d_result, l.total, cudaMemcpyDeviceToHost,
+                                     ws->stream));
+            CUDA_TRY(cudaStreamSynchronize(ws->stream));
+            idx->pf_queries += nq;
+            bool redo = false;
+            for (uint32_t q = 0; q < nq; ++q) {
+                idx->pf_kept += ws->h_pf_ctl[(size_t)q * 8 + 7];
+                if (ws->h_pf_ctl[(size_t)q * 8 + 3] == 0) continue;
+                idx->pf_fallbacks++;
+                redo = true;
+                rc = launch_scan(idx, sh, *ws, ws->d_query + (size_t)q * dim, k, metric, sh.row_base,
+                                 r_rows + (size_t)q * k, r_scores + (size_t)q * k, r_counts + q,
+                                 nullptr, ws->stream);
+                if (rc) return rc;
+            }
+            if (!redo) {
+                // results are already on the host: finish without a second copy
+                float ms = 0.f;
+                CUDA_TRY(cudaEventElapsedTime(&ms, ws->ev0, ws->ev1));
+                idx->last_scan_ms = ms;
+                const uint32_t *hc = reinterpret_cast<const uint32_t *>(ws->h_result + l.counts_off);
+                const uint64_t *hr = reinterpret_cast<const uint64_t *>(ws->h_result + l.rows_off);
+                const float *hs = reinterpret_cast<const float *>(ws->h_result + l.scores_off);
+                for (uint32_t q = 0; q < nq; ++q) {
+                    out_counts[q] = hc[q];
+                    memcpy(out_rows + (size_t)q * k, hr + (size_t)q * k, (size_t)hc[q] * 8);
+                    memcpy(out_scores + (size_t)q * k, hs + (size_t)q * k, (size_t)hc[q] * 4);
+                }
+                idx->searches += nq;
+                idx->rows_scanned += (uint64_t)nq * sh.rows;
+                idx->bytes_streamed += (uint64_t)nq * sh.rows * (q8_pitch(dim) + sizeof(nm::RowMeta));
+                idx->h2d_bytes += (uint64_t)nq * dim * 4;
+                idx->d2h_bytes += l.total + (uint64_t)nq * 32;
+                return NM_OK;
+            }
+        } else {
+            rc = scan_queries(idx, sh, *ws, ws->d_query, nq, k, metric, sh.row_base, r_rows, r_scores,
+                              r_counts, nullptr, ws->stream);
+            if (rc) return rc;
+        }
+        CUDA_TRY(cudaEventRecord(ws->ev1, ws->stream));
+        return download_results(idx, sh, *ws, l, nq, k, out_rows, out_scores, out_counts);
+    }
+
+    // ---- collective path: one shard per process.  Single queries: ONE fused launch (scan +
+    //      peer-memory exchange + merge).  Batches / k > 1024: scan, ONE ncclAllGather of the
+    //      per-shard hits, merge kernel. ----
+    if (collective) {
+        Shard &sh = *idx->shards[0];
+        CUDA_TRY(cudaSetDevice(sh.device));
+        std::lock_guard<std::mutex> cg(idx->comm_mu);
+        std::unique_ptr<Workspace> ws;
+        rc = ws_acquire(sh, ws);
+        if (rc) return rc;
+        struct Releaser {
+            Shard &s;
+            std::unique_ptr<Workspace> &w;
+            ~Releaser() { ws_release(s, w); }
+        } rel{sh, ws};
+        rc = ws_ensure(*ws, sh, dim, nq, k, true, true, true, idx->n_ranks);
+        if (rc) return rc;
+        ResultLayout l = result_layout(nq, k);
+        uint64_t *r_rows = reinterpret_cast<uint64_t *>(ws->d_result + l.rows_off);
+        float *r_scores = reinterpret_cast<float *>(ws->d_result + l.scores_off);
+        uint32_t *r_counts = reinterpret_cast<uint32_t *>(ws->d_result + l.counts_off);
+        memcpy(ws->h_query, queries, (size_t)nq * dim * 4);
+        CUDA_TRY(cudaMemcpyAsync(ws->d_query, ws->h_query, (size_t)nq * dim * 4,
+                                 cudaMemcpyHostToDevice, ws->stream));
+        CUDA_TRY(cudaEventRecord(ws->ev0, ws->stream));
+        if (collective_uses_fused_exchange(idx, nq, k, metric)) {
+            rc = collective_fused(idx, sh, *ws, ws->d_query, nq, k, metric, r_rows, r_scores,
+                                  r_counts, ws->stream);
+            if (rc) return rc;
+            CUDA_TRY(cudaEventRecord(ws->ev1, ws->stream));
+        } else {
+            if (sh.rows == 0) {
+                CUDA_TRY(cudaMemsetAsync(ws->d_hits, 0, (size_t)nq * k * sizeof(nm::ShardHit),
+                                         ws->stream));
+            } else {
+                rc = scan_queries(idx, sh, *ws, ws->d_query, nq, k, metric, idx->comm_row_base,
+                                  nullptr, nullptr, nullptr, ws->d_hits, ws->stream);
+                if (rc) return rc;
+            }
+            CUDA_TRY(cudaEventRecord(ws->ev1, ws->stream));
+            NCCL_TRY(nccl().AllGather(ws->d_hits, ws->d_gather,
+                                      (size_t)nq * k * sizeof(nm::ShardHit), ncclChar, idx->comm,
+                                      ws->stream));
+            rc = launch_merge_shards(idx, ws->d_gather, nq, k, r_rows, r_scores, r_counts, ws->stream);
+            if (rc) return rc;
+        }
+        return download_results(idx, sh, *ws, l, nq, k, out_rows, out_scores, out_counts);
+    }
+
+    // ---- several devices in this process: scan each shard, merge the per-shard top-k on
+    //      the host (G*k hits), exactly ResultMerger::merge_top_k -------------------------
+    std::vector<std::unique_ptr<Workspace>> wss(G);
+    struct ReleaseAll {
+        nm_index *idx;
+        std::vector<std::unique_ptr<Workspace>> &w;
+        ~ReleaseAll() {
+            for (size_t s = 0; s < w.size(); ++s) ws_release(*idx->shards[s], w[s]);
+        }
+    } rel{idx, wss};
+    for (size_t s = 0; s < G; ++s) {
+        Shard &sh = *idx->shards[s];
+        CUDA_TRY(cudaSetDevice(sh.device));
+        rc = ws_acquire(sh, wss[s]);
+        if (rc) return rc;
+        Workspace &ws = *wss[s];
+        rc = ws_ensure(ws, sh, dim, nq, k, true, false, true, 0);
+        if (rc) return rc;
+        memcpy(ws.h_query, queries, (size_t)nq * dim * 4);
+        CUDA_TRY(cudaMemcpyAsync(ws.d_query, ws.h_query, (size_t)nq * dim * 4,
+                                 cudaMemcpyHostToDevice, ws.stream));
+        CUDA_TRY(cudaEventRecord(ws.ev0, ws.stream));
+        if (sh.rows == 0) {
+            CUDA_TRY(cudaMemsetAsync(ws.d_hits, 0, (size_t)nq * k * sizeof(nm::ShardHit), ws.stream));
+        } else {
+            rc = scan_queries(idx, sh, ws, ws.d_query, nq, k, metric, sh.row_base, nullptr, nullptr,
+                              nullptr, ws.d_hits, ws.stream);
+            if (rc) return rc;
+        }
+        CUDA_TRY(cudaEventRecord(ws.ev1, ws.stream));
+        CUDA_TRY(cudaMemcpyAsync(ws.h_hits, ws.d_hits, (size_t)nq * k * sizeof(nm::ShardHit),
+                                 cudaMemcpyDeviceToHost, ws.stream));
+    }
+    float max_ms = 0.f;
+    for (size_t s = 0; s < G; ++s) {
+        CUDA_TRY(cudaSetDevice(idx->shards[s]->device));
+        CUDA_TRY(cudaStreamSynchronize(wss[s]->stream));
+        float ms = 0.f;
+        CUDA_TRY(cudaEventElapsedTime(&ms, wss[s]->ev0, wss[s]->ev1));
+        max_ms = std::max(max_ms, ms);
+    }
+    idx->last_scan_ms = max_ms;
+    std::vector<HostHit> all;
+    for (uint32_t q = 0; q < nq; ++q) {
+        all.clear();
+        for (size_t s = 0; s < G; ++s) {
+            const nm::ShardHit *h = wss[s]->h_hits + (size_t)q * k;
+            for (uint32_t i = 0; i < k; ++i) {
+                if (h[i].ord == 0 && h[i].score_bits == 0) continue;
+                all.push_back(HostHit{h[i].ord, h[i].score_bits, h[i].global_row, all.size()});
+            }
+        }
+        std::stable_sort(all.begin(), all.end(),
+                         [](const HostHit &a, const HostHit &b) { return a.ord > b.ord; });
+        uint32_t m = (uint32_t)std::min<size_t>(k, all.size());
+        out_counts[q] = m;
+        for (uint32_t i = 0; i < m; ++i) {
+            out_rows[(size_t)q * k + i] = all[i].row;
+            memcpy(&out_scores[(size_t)q * k + i], &all[i].score_bits, 4);
+        }
+    }
+    uint64_t rows = idx->total_rows();
+    idx->searches += nq;
+    idx->rows_scanned += (uint64_t)nq * rows;
+    idx->bytes_streamed += (uint64_t)nq * rows * dim * 4;
+    idx->h2d_bytes += (uint64_t)nq * dim * 4 * G;
+    idx->d2h_bytes += (uint64_t)nq * k * sizeof(nm::ShardHit) * G;
+    return NM_OK;
+}
+
+int nm_search(nm_index *idx, const float *queries, uint32_t nq, uint32_t k, int metric,
+              uint64_t *out_rows, float *out_scores, uint32_t *out_counts) {
+    return search_impl(idx, queries, nq, k, metric, nullptr, out_rows, out_scores, out_counts);
+}
+
+int nm_search_masked(nm_index *idx, const float *queries, uint32_t nq, uint32_t k, int metric,
+                     const uint64_t *row_mask, uint64_t *out_rows, float *out_scores,
+                     uint32_t *out_counts) {
+    if (!row_mask) return fail(NM_ERR_INVALID_ARGUMENT, "null row mask");
+    return search_impl(idx, queries, nq, k, metric, row_mask, out_rows, out_scores, out_counts);
+}
+
+int nm_search_device(nm_index *idx, const float *d_queries, uint32_t nq, uint32_t k, int metric,
+                     uint64_t *d_out_rows, float *d_out_scores, uint32_t *d_out_counts,
+                     void *stream_v) {
+    int rc = validate_search(idx, d_queries, nq, k, metric, d_out_rows, d_out_scores, d_out_counts);
+    if (rc) return rc;
+    std::shared_lock<std::shared_mutex> g(idx->mu);
+    if (idx->shards.size() != 1)
+        return fail(NM_ERR_CONFIGURATION, "nm_search_device needs a single-device index");
+    Shard &sh = *idx->shards[0];
+    const uint32_t dim = idx->dim;
+    const bool collective = idx->comm != nullptr;
+    CUDA_TRY(cudaSetDevice(sh.device));
+    // Caller stream: use the workspace bound to that stream and return without synchronising
+    // (stream order protects the scratch).  NULL stream: pooled workspace + synchronise.
+    std::unique_ptr<Workspace> pooled;
+    Workspace *ws = nullptr;
+    cudaStream_t stream = nullptr;
+    if (stream_v) {
+        stream = (cudaStream_t)stream_v;
+        std::lock_guard<std::mutex> pg(sh.pool_mu);
+        for (auto &e : sh.stream_ws)
+            if (e.first == stream) ws = e.second.get();
+        if (!ws) {
+            std::unique_ptr<Workspace> nw(new Workspace());
+            nw->device = sh.device;
+            CUDA_TRY(cudaMalloc(&nw->d_counter, 2 * sizeof(uint32_t)));
+            CUDA_TRY(cudaMemsetAsync(nw->d_counter, 0, 2 * sizeof(uint32_t), stream));
+            ws = nw.get();
+            sh.stream_ws.emplace_back(stream, std::move(nw));
+        }
+    } else {
+        rc = ws_acquire(sh, pooled);
+        if (rc) return rc;
+        ws = pooled.get();
+        stream = ws->stream;
+    }
+    struct Releaser {
+        Shard &s;
+        std::unique_ptr<Workspace> &w;
+        ~Releaser() { ws_release(s, w); }
+    } rel{sh, pooled};
+    // growing a stream-bound workspace frees buffers earlier launches may still read
+    {
+        size_t need_cand = (size_t)sh.sm_count * std::min<uint32_t>(k, nm::kMaxFastK),
+               need_hits = (size_t)nq * k;
+        bool grow = ws->cand_cap < need_cand ||
+                    (collective && (ws->hits_cap < need_hits ||
+                                    ws->gather_cap < need_hits * (size_t)idx->n_ranks));
+        if (grow && stream_v) CUDA_TRY(cudaStreamSynchronize(stream));
+    }
+    rc = ws_ensure(*ws, sh, dim, nq, k, false, false, collective, collective ? idx->n_ranks : 0);
+    if (rc) return rc;
+    std::pair<cudaEvent_t, cudaEvent_t> *prof = nullptr;
+    if (idx->profiling.load() && sh.rows) {
+        if (ws->prof_used == ws->prof_events.size()) {
+            cudaEvent_t a, b;
+            CUDA_TRY(cudaEventCreate(&a));
+            CUDA_TRY(cudaEventCreate(&b));
+            ws->prof_events.emplace_back(a, b);
+        }
+        prof = &ws->prof_events[ws->prof_used++];
+        CUDA_TRY(cudaEventRecord(prof->first, stream));
+    }
+    if (!collective) {
+        if (sh.rows == 0) {
+            CUDA_TRY(cudaMemsetAsync(d_out_counts, 0, (size_t)nq * 4, stream));
+        } else {
+            rc = scan_queries(idx, sh, *ws, d_queries, nq, k, metric, sh.row_base, d_out_rows,
+                              d_out_scores, d_out_counts, nullptr, stream);
+            if (rc) return rc;
+        }
+        if (prof) CUDA_TRY(cudaEventRecord(prof->second, stream));
+    } else if (collective_uses_fused_exchange(idx, nq, k, metric)) {
+        // (collective calls on one index must be issued in the same order on every rank)
+        std::lock_guard<std::mutex> cg(idx->comm_mu);
+        rc = collective_fused(idx, sh, *ws, d_queries, nq, k, metric, d_out_rows, d_out_scores,
+                              d_out_counts, stream);
+        if (rc) return rc;
+        if (prof) CUDA_TRY(cudaEventRecord(prof->second, stream));
+    } else {
+        std::lock_guard<std::mutex> cg(idx->comm_mu);
+        if (sh.rows == 0) {
+            CUDA_TRY(cudaMemsetAsync(ws->d_hits, 0, (size_t)nq * k * sizeof(nm::ShardHit), stream));
+        } else {
+            rc = scan_queries(idx, sh, *ws, d_queries, nq, k, metric, idx->comm_row_base, nullptr,
+                              nullptr, nullptr, ws->d_hits, stream);
+            if (rc) return rc;
+        }
+        if (prof) CUDA_TRY(cudaEventRecord(prof->second, stream));
+        NCCL_TRY(nccl().AllGather(ws->d_hits, ws->d_gather,
+                                  (size_t)nq * k * sizeof(nm::ShardHit), ncclChar, idx->comm,
+                                  stream));
+        rc = launch_merge_shards(idx, ws->d_gather, nq, k, d_out_rows, d_out_scores, d_out_counts,
+                                 stream);
+        if (rc) return rc;
+    }
+    if (!stream_v) CUDA_TRY(cudaStreamSynchronize(stream));
+    idx->searches += nq;
+    idx->rows_scanned += (uint64_t)nq * sh.rows;
+    idx->bytes_streamed += (uint64_t)nq * sh.rows * dim * 4;
+    return NM_OK;
+}
+
+}  // extern "C"

@@ -26,20 +26,6 @@
 
 namespace nm {
 
-struct alignas(16) RowMeta {
-    float scale;      // s_r (0 for an all-zero row)
-    uint32_t x1;      // sum |xt_i|
-    float rmag;       // reference-arithmetic |x| (lane tree + sqrt): exact denominator input
-    uint32_t flags;   // bit 0: row has a non-finite element
-};
-
-constexpr uint32_t kKeptCap = 1u << 20;  // kept (row, ub) entries per query before fallback
-
-struct KeptEntry {
-    uint32_t row;
-    uint32_t ub_ord;
-};
-
 #ifdef __CUDACC__
 
 // exact reference arithmetic on one row straight from global memory (re-score path)

@@ -135,9 +135,9 @@ struct VectorEngine::Space {
     std::map<uint32_t, std::unique_ptr<Bucket>> buckets;
 };
 
-VectorEngine::VectorEngine() : default_space_(new Space()) {}
+VectorEngine::VectorEngine() : default_space_(new Space()), entity_space_(new Space()) {}
 VectorEngine::VectorEngine(VectorEngineConfig config)
-    : config_(std::move(config)), default_space_(new Space()) {}
+    : config_(std::move(config)), default_space_(new Space()), entity_space_(new Space()) {}
 VectorEngine::~VectorEngine() = default;
 
 Result<std::unique_ptr<VectorEngine>> VectorEngine::with_config(VectorEngineConfig config) {
@@ -683,6 +683,40 @@ std::vector<std::string> VectorEngine::list_keys_matching(const FilterCondition 
         for (size_t r = 0; r < kv.second->keys.size(); ++r)
             if (evaluate_filter(kv.second->meta[r], filter)) out.push_back(kv.second->keys[r]);
     return out;
+}
+
+// ---- unified entity mode (lib.rs:3060-3219) ----
+Result<Unit> VectorEngine::set_entity_embedding(const std::string &entity_key,
+                                                std::vector<float> vector) {
+    if (vector.empty()) return err(ErrorKind::EmptyVector);
+    if (config_.max_dimension && vector.size() > *config_.max_dimension)
+        return dim_mismatch(*config_.max_dimension, vector.size());
+    return store_in_space(*entity_space_, entity_key, std::move(vector));
+}
+
+Result<std::vector<float>> VectorEngine::get_entity_embedding(const std::string &entity_key) const {
+    return get_in_space(*entity_space_, entity_key);
+}
+
+bool VectorEngine::entity_has_embedding(const std::string &entity_key) const {
+    std::shared_lock<std::shared_mutex> g(entity_space_->mu);
+    return entity_space_->where.count(entity_key) != 0;
+}
+
+Result<Unit> VectorEngine::remove_entity_embedding(const std::string &entity_key) {
+    return delete_in_space(*entity_space_, entity_key);
+}
+
+Result<std::vector<SearchResult>> VectorEngine::search_entities(const std::vector<float> &query,
+                                                                size_t top_k) const {
+    auto start = std::chrono::steady_clock::now();
+    if (query.empty()) return err(ErrorKind::EmptyVector);
+    if (top_k == 0) return err(ErrorKind::InvalidTopK);
+    if (config_.max_dimension && query.size() > *config_.max_dimension)
+        return dim_mismatch(*config_.max_dimension, query.size());
+    if (simd::magnitude(query.data(), query.size()) == 0.0f) return std::vector<SearchResult>{};
+    return scan_space(*entity_space_, query, top_k, DistanceMetric::Cosine, "search_entities",
+                      start);
 }
 
 // neumann_server/src/service/points.rs:449-485

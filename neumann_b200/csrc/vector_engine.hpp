@@ -151,6 +151,16 @@ class VectorEngine {
     size_t count_matching(const FilterCondition &filter) const;
     std::vector<std::string> list_keys_matching(const FilterCondition &filter) const;
 
+    // unified entity mode: the `_embedding` field of arbitrary entity keys (lib.rs:3060-3219);
+    // search_entities is what tensor_unified's find_similar_connected calls
+    // (tensor_unified/src/lib.rs:913-914)
+    Result<Unit> set_entity_embedding(const std::string &entity_key, std::vector<float> vector);
+    Result<std::vector<float>> get_entity_embedding(const std::string &entity_key) const;
+    bool entity_has_embedding(const std::string &entity_key) const;
+    Result<Unit> remove_entity_embedding(const std::string &entity_key);
+    Result<std::vector<SearchResult>> search_entities(const std::vector<float> &query,
+                                                      size_t top_k) const;
+
     // gRPC PointsService::query post-processing (neumann_server/src/service/points.rs:449-485):
     // search limit+offset, skip offset, take limit, drop hits below score_threshold.
     struct ScoredPoint {
@@ -194,6 +204,7 @@ class VectorEngine {
     struct Space;
     VectorEngineConfig config_;
     std::unique_ptr<Space> default_space_;
+    std::unique_ptr<Space> entity_space_;
     mutable std::shared_mutex collections_mu_;
     // A collection's rows may exist without a config (store_in_collection does not require
     // create_collection, lib.rs:1445-1500); `config` is set by create_collection only.

@@ -70,6 +70,10 @@ ENGINE_SIGNATURES = {
     "nm_engine_search_filtered_in_collection": (C.c_int, [_vp, _cp, _vp, _sz, _sz, _cp, C.c_int, _sz, _pvp]),
     "nm_engine_count_matching": (C.c_int, [_vp, _cp, C.POINTER(_u64)]),
     "nm_engine_query_points": (C.c_int, [_vp, _cp, _vp, _sz, _sz, _sz, C.c_int, C.c_float, _pvp]),
+    "nm_engine_set_entity_embedding": (C.c_int, [_vp, _cp, _vp, _sz]),
+    "nm_engine_remove_entity_embedding": (C.c_int, [_vp, _cp]),
+    "nm_engine_entity_has_embedding": (C.c_int, [_vp, _cp]),
+    "nm_engine_search_entities": (C.c_int, [_vp, _vp, _sz, _sz, _pvp]),
     "nm_engine_execute": (C.c_int, [_vp, _cp, _pvp]),
     "nm_engine_execute_parsed": (C.c_int, [_vp, _cp, _pvp]),
     "nm_engine_mirror_rows": (C.c_int, [_vp, C.c_uint32, C.POINTER(_u64), C.POINTER(_u64)]),
@@ -279,6 +283,23 @@ class VectorEngine:
         _check(_lib().nm_engine_query_points(self._h, collection.encode(), q.ctypes.data, q.size,
                                              limit, offset, 0 if score_threshold is None else 1,
                                              score_threshold or 0.0, C.byref(h)))
+        return _take(h)
+
+    # ---- unified entity mode ----
+    def set_entity_embedding(self, entity_key: str, vector) -> None:
+        v = _f32(vector)
+        _check(_lib().nm_engine_set_entity_embedding(self._h, entity_key.encode(), v.ctypes.data, v.size))
+
+    def remove_entity_embedding(self, entity_key: str) -> None:
+        _check(_lib().nm_engine_remove_entity_embedding(self._h, entity_key.encode()))
+
+    def entity_has_embedding(self, entity_key: str) -> bool:
+        return bool(_lib().nm_engine_entity_has_embedding(self._h, entity_key.encode()))
+
+    def search_entities(self, query, top_k: int) -> list[SearchResult]:
+        q = _f32(query)
+        h = C.c_void_p()
+        _check(_lib().nm_engine_search_entities(self._h, q.ctypes.data, q.size, top_k, C.byref(h)))
         return _take(h)
 
     # ---- router ----

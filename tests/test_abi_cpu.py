@@ -232,3 +232,24 @@ def test_router_parsing_without_device():
         e.execute_parsed("SIMILAR 'doc1' CONNECTED TO 'n1' LIMIT 3")
     assert e.execute_parsed("EMBED STORE 'k9' [1.0, 2.0, 3.0] INTO c1") is None
     assert e.collection_count("c1") == 1
+
+
+def test_entity_embeddings_host_side():
+    # vector_engine/src/lib.rs:3060-3145
+    e = eng.VectorEngine()
+    e.set_entity_embedding("user:1", [1.0, 0.0])
+    e.set_entity_embedding("user:2", [0.0, 1.0])
+    assert e.entity_has_embedding("user:1") and not e.entity_has_embedding("user:9")
+    assert e.count() == 0                      # entity embeddings live outside the emb: space
+    e.remove_entity_embedding("user:1")
+    assert not e.entity_has_embedding("user:1")
+    with pytest.raises(eng.VectorError) as ei:
+        e.remove_entity_embedding("user:1")
+    assert ei.value.kind == "NotFound"
+    with pytest.raises(eng.VectorError) as ei:
+        e.set_entity_embedding("user:3", [])
+    assert ei.value.kind == "EmptyVector"
+    assert e.search_entities([0.0, 0.0], 3) == []
+    with pytest.raises(eng.VectorError) as ei:
+        e.search_entities([1.0, 0.0], 0)
+    assert ei.value.kind == "InvalidTopK"

@@ -257,3 +257,19 @@ def test_search_filtered_in_collection_and_query_points():
     thr = full[5].score
     page = e.query_points("docs", [1.0, 0.0, 0.5], limit=10, offset=0, score_threshold=thr)
     assert [x.key for x in page] == [x.key for x in full[:10] if x.score >= thr]
+
+
+def test_search_entities_on_gpu():
+    # vector_engine/src/lib.rs:3155-3219 (the call tensor_unified makes, :913-914)
+    e = eng.VectorEngine()
+    rows = o.fill_synthetic(800, 24, 5)
+    for i in range(800):
+        e.set_entity_embedding(f"user:{i}", rows[i])
+    e.store_embedding("not_an_entity", rows[3])          # different namespace: never returned
+    q = rows[77]
+    res = e.search_entities(q, 5)
+    er, es = o.search(rows, q, 5, "cosine")
+    assert [r.key for r in res] == [f"user:{int(i)}" for i in er]
+    assert [np.float32(r.score).view(np.uint32) for r in res] == list(es.view(np.uint32))
+    e.remove_entity_embedding("user:77")
+    assert e.search_entities(q, 1)[0].key != "user:77"
