@@ -190,33 +190,66 @@ score_batch_kernel(const __grid_constant__ CUtensorMap tmap, const BatchScorePar
             const uint8_t *srow = stages + stage * kStage + t * 128u;
             const float *qs = reinterpret_cast<const float *>(stages + stage * kStage + kStageBytes);
             // two float4 units (8 consecutive elements = one f32x8 group) per iteration
+            if (METRIC == kEuclidean) {
 #pragma unroll 1
-            for (uint32_t u = 0; u < 8; u += 2) {
-                const float4 v0 = *reinterpret_cast<const float4 *>(srow + ((u ^ swz) << 4));
-                const float4 v1 = *reinterpret_cast<const float4 *>(srow + (((u + 1) ^ swz) << 4));
-                const float xv[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
-                const float *qe = qs + (u * 4u) * QB;
+                for (uint32_t u = 0; u < 8; u += 2) {
+                    const float4 v0 = *reinterpret_cast<const float4 *>(srow + ((u ^ swz) << 4));
+                    const float4 v1 = *reinterpret_cast<const float4 *>(srow + (((u + 1) ^ swz) << 4));
+                    const float xv[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+                    const float *qe = qs + (u * 4u) * QB;
 #pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                    const float x = xv[e];
-                    if (METRIC == kCosine) ss[e] = __fadd_rn(ss[e], __fmul_rn(x, x));
-                    const float4 *qp = reinterpret_cast<const float4 *>(qe + e * QB);
+                    for (int e = 0; e < 8; ++e) {
+                        const float x = xv[e];
+                        const float4 *qp = reinterpret_cast<const float4 *>(qe + e * QB);
 #pragma unroll
-                    for (int g = 0; g < QB / 4; ++g) {
-                        const float4 qq = qp[g];  // queries 4g..4g+3 at this element (broadcast)
-                        if (METRIC == kEuclidean) {
+                        for (int g = 0; g < QB / 4; ++g) {
+                            const float4 qq = qp[g];  // queries 4g..4g+3 at this element (broadcast)
                             const float d0 = __fsub_rn(qq.x, x), d1 = __fsub_rn(qq.y, x);
                             const float d2 = __fsub_rn(qq.z, x), d3 = __fsub_rn(qq.w, x);
                             acc[4 * g + 0] = __fadd_rn(acc[4 * g + 0], __fmul_rn(d0, d0));
                             acc[4 * g + 1] = __fadd_rn(acc[4 * g + 1], __fmul_rn(d1, d1));
                             acc[4 * g + 2] = __fadd_rn(acc[4 * g + 2], __fmul_rn(d2, d2));
                             acc[4 * g + 3] = __fadd_rn(acc[4 * g + 3], __fmul_rn(d3, d3));
-                        } else {
+                        }
+                    }
+                }
+            } else {
+                // dot / cosine: the query values of element e+1 are fetched while element e is
+                // being accumulated (explicit double buffer: with 2 warps per scheduler the
+                // 29-cycle LDS latency is otherwise exposed, ncu short_scoreboard stalls)
+                constexpr int G = QB / 4;
+                float4 qn[G];
+                {
+                    const float4 *qp = reinterpret_cast<const float4 *>(qs);
+#pragma unroll
+                    for (int g = 0; g < G; ++g) qn[g] = qp[g];
+                }
+#pragma unroll 1
+                for (uint32_t u = 0; u < 8; u += 2) {
+                    const float4 v0 = *reinterpret_cast<const float4 *>(srow + ((u ^ swz) << 4));
+                    const float4 v1 = *reinterpret_cast<const float4 *>(srow + (((u + 1) ^ swz) << 4));
+                    const float xv[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+                    const float *qe = qs + (u * 4u) * QB;
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        const float x = xv[e];
+                        if (METRIC == kCosine) ss[e] = __fadd_rn(ss[e], __fmul_rn(x, x));
+                        float4 qc[G];
+#pragma unroll
+                        for (int g = 0; g < G; ++g) qc[g] = qn[g];
+                        // next element of this stage (the last one re-reads element 31: harmless)
+                        const uint32_t nxt = min(u * 4u + (uint32_t)e + 1u, 31u);
+                        const float4 *qp = reinterpret_cast<const float4 *>(qs + nxt * QB);
+                        (void)qe;
+#pragma unroll
+                        for (int g = 0; g < G; ++g) qn[g] = qp[g];
+#pragma unroll
+                        for (int g = 0; g < G; ++g) {
                             float *a = acc + e * QB + 4 * g;
-                            a[0] = __fadd_rn(a[0], __fmul_rn(qq.x, x));
-                            a[1] = __fadd_rn(a[1], __fmul_rn(qq.y, x));
-                            a[2] = __fadd_rn(a[2], __fmul_rn(qq.z, x));
-                            a[3] = __fadd_rn(a[3], __fmul_rn(qq.w, x));
+                            a[0] = __fadd_rn(a[0], __fmul_rn(qc[g].x, x));
+                            a[1] = __fadd_rn(a[1], __fmul_rn(qc[g].y, x));
+                            a[2] = __fadd_rn(a[2], __fmul_rn(qc[g].z, x));
+                            a[3] = __fadd_rn(a[3], __fmul_rn(qc[g].w, x));
                         }
                     }
                 }

@@ -3,9 +3,37 @@
 // the NCCL all-gather path, and the host-side merge of in-process multi-device indexes.
 #include "nm_internal.hpp"
 
+#include <cstdlib>
+
 using namespace nmi;
 
 namespace {
+
+// Wait for the results of one search.  cudaStreamSynchronize parks the calling thread and its
+// wake-up costs tens of microseconds once the wait is longer than the driver's spin window —
+// about 60 us per query on a 4 ms scan.  Default: poll cudaStreamQuery (one busy core for the
+// duration of the scan, the usual latency/CPU trade of a serving thread).  NM_WAIT=block
+// restores the blocking wait.
+int wait_stream(cudaStream_t stream) {
+    static const bool block = [] {
+        const char *m = getenv("NM_WAIT");
+        return m && strcmp(m, "block") == 0;
+    }();
+    if (block) {
+        CUDA_TRY(cudaStreamSynchronize(stream));
+        return NM_OK;
+    }
+    for (;;) {
+        cudaError_t e = cudaStreamQuery(stream);
+        if (e == cudaSuccess) return NM_OK;
+        if (e != cudaErrorNotReady)
+            return fail(NM_ERR_STORAGE, "CUDA error %s while waiting for a search: %s",
+                        cudaGetErrorName(e), cudaGetErrorString(e));
+#if defined(__x86_64__)
+        __builtin_ia32_pause();
+#endif
+    }
+}
 
 struct HostHit {
     uint32_t ord;
@@ -32,7 +60,10 @@ int download_results(nm_index *idx, const Shard &sh, Workspace &ws, const Result
                      uint32_t nq, uint32_t k, uint64_t *out_rows, float *out_scores,
                      uint32_t *out_counts) {
     CUDA_TRY(cudaMemcpyAsync(ws.h_result, ws.d_result, l.total, cudaMemcpyDeviceToHost, ws.stream));
-    CUDA_TRY(cudaStreamSynchronize(ws.stream));
+    {
+        int wrc = wait_stream(ws.stream);
+        if (wrc) return wrc;
+    }
     float ms = 0.f;
     CUDA_TRY(cudaEventElapsedTime(&ms, ws.ev0, ws.ev1));
     idx->last_scan_ms = ms;
@@ -169,7 +200,8 @@ static int search_impl(nm_index *idx, const float *queries, uint32_t nq, uint32_
             CUDA_TRY(cudaEventRecord(ws->ev1, ws->stream));
             CUDA_TRY(cudaMemcpyAsync(ws->h_result, ws->d_result, l.total, cudaMemcpyDeviceToHost,
                                      ws->stream));
-            CUDA_TRY(cudaStreamSynchronize(ws->stream));
+            rc = wait_stream(ws->stream);
+            if (rc) return rc;
             idx->pf_queries += nq;
             bool redo = false;
             for (uint32_t q = 0; q < nq; ++q) {
@@ -296,7 +328,8 @@ static int search_impl(nm_index *idx, const float *queries, uint32_t nq, uint32_
     float max_ms = 0.f;
     for (size_t s = 0; s < G; ++s) {
         CUDA_TRY(cudaSetDevice(idx->shards[s]->device));
-        CUDA_TRY(cudaStreamSynchronize(wss[s]->stream));
+        rc = wait_stream(wss[s]->stream);
+        if (rc) return rc;
         float ms = 0.f;
         CUDA_TRY(cudaEventElapsedTime(&ms, wss[s]->ev0, wss[s]->ev1));
         max_ms = std::max(max_ms, ms);
