@@ -163,6 +163,8 @@ typedef struct nm_stats {
     uint64_t prefilter_queries;   /* queries served through the int8 pre-filter            */
     uint64_t prefilter_fallbacks; /* of those, redone with the exact f32 scan              */
     uint64_t prefilter_kept;      /* rows whose score interval reached the running bound   */
+    uint64_t coalesced_batches;   /* leader rounds of the single-query coalescer           */
+    uint64_t coalesced_queries;   /* queries served by those rounds                        */
 } nm_stats;
 int nm_index_stats(nm_index *idx, nm_stats *out);
 /* When enabled, every asynchronous nm_search_device call brackets its scan launches (not the
@@ -175,11 +177,17 @@ int nm_index_set_profiling(nm_index *idx, int enable);
  * scans the int8 copy with dp4a (4x fewer HBM bytes), brackets every row's reference score in
  * a rigorous interval, and re-scores only the rows whose interval reaches the k-th best lower
  * bound with the exact f32 arithmetic.  Results are bit-identical to mode 0 (tested); cosine
- * and dot product, k <= 1024, fewer than 8 queries per call; anything else, a non-finite
+ * and dot product, k <= 1024, fewer than 4 queries per call; anything else, a non-finite
  * query or an overflowing candidate list falls back to the f32 scan.  It changes the bytes
  * read per row, so it is OFF by default and benchmarked separately from the f32 roofline. */
 int nm_index_set_prefilter(nm_index *idx, int mode);
-/* Batches of >= 8 queries share one corpus pass (batch_kernels.cuh) by default; 0 forces one
+/* Concurrent single-query nm_search calls (many host threads, the reference's serving pattern:
+ * stress_tests/tests/mixed_workload_stress.rs:291-307) are coalesced: calls that arrive while
+ * the GPU is busy ride the next corpus pass together, up to max_batch per pass (default 64;
+ * 1 disables).  No timers are involved, so a lone call is never delayed; results are
+ * bit-identical to isolated calls. */
+int nm_index_set_coalescing(nm_index *idx, int max_batch);
+/* Batches of >= 4 queries share one corpus pass (batch_kernels.cuh) by default; 0 forces one
  * scan per query.  Results are bit-identical either way (tested); this is a tuning knob. */
 int nm_index_set_batching(nm_index *idx, int enable);
 

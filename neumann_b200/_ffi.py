@@ -34,6 +34,7 @@ class NmStats(C.Structure):
         ("profiled_scan_ms", C.c_double), ("profiled_scans", C.c_uint64),
         ("prefilter_queries", C.c_uint64), ("prefilter_fallbacks", C.c_uint64),
         ("prefilter_kept", C.c_uint64),
+        ("coalesced_batches", C.c_uint64), ("coalesced_queries", C.c_uint64),
     ]
 
 
@@ -69,6 +70,7 @@ SIGNATURES = {
     "nm_index_set_profiling": (C.c_int, [_vp, C.c_int]),
     "nm_index_set_batching": (C.c_int, [_vp, C.c_int]),
     "nm_index_set_prefilter": (C.c_int, [_vp, C.c_int]),
+    "nm_index_set_coalescing": (C.c_int, [_vp, C.c_int]),
 }
 
 _lib = None

@@ -530,6 +530,8 @@ int nm_index_stats(nm_index *idx, nm_stats *out) {
     out->prefilter_queries = idx->pf_queries;
     out->prefilter_fallbacks = idx->pf_fallbacks;
     out->prefilter_kept = idx->pf_kept;
+    out->coalesced_batches = idx->co_batches;
+    out->coalesced_queries = idx->co_queries;
     {
         // fold finished profiling event pairs into the totals (waits for the streams)
         std::unique_lock<std::shared_mutex> g(idx->mu);

@@ -13,6 +13,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <condition_variable>
 #include <cstdint>
 #include <cstring>
 #include <memory>
@@ -188,6 +189,26 @@ struct nm_index {
     std::atomic<int> prefilter{0};  // nm_index_set_prefilter: 1 = exact int8 pre-filter
     std::atomic<uint64_t> pf_queries{0}, pf_fallbacks{0}, pf_kept{0};
     std::atomic<int> batching{1};  // nm_index_set_batching: 0 forces one scan per query
+    // Coalescing of concurrent single-query nm_search calls (nm_index_set_coalescing): while
+    // one batch is on the GPU, calls from other host threads queue up and ride the next corpus
+    // pass together (batched kernels).  No timers: an idle index serves a lone call at once.
+    std::atomic<int> coalesce_max{64};
+    struct PendingSearch {
+        const float *query;
+        uint32_t k;
+        int metric;
+        uint64_t *out_rows;
+        float *out_scores;
+        uint32_t *out_count;
+        int rc = 0;
+        std::string error;
+        bool done = false;
+    };
+    std::mutex co_mu;
+    std::condition_variable co_cv;
+    std::vector<PendingSearch *> co_pending;
+    bool co_leader = false;
+    std::atomic<uint64_t> co_batches{0}, co_queries{0};
     double profiled_scan_ms = 0.0;  // guarded by mu (exclusive) in nm_index_stats
     uint64_t profiled_scans = 0;
     uint64_t total_rows() const {
@@ -199,7 +220,7 @@ struct nm_index {
 
 namespace nmi {
 
-constexpr uint32_t kBatchMinQueries = 8;  // below this, nq single-query passes are cheaper
+constexpr uint32_t kBatchMinQueries = 4;  // below this, nq single-query passes are cheaper
 
 struct ResultLayout {
     size_t counts_off, rows_off, scores_off, total;

@@ -363,9 +363,93 @@ static int search_impl(nm_index *idx, const float *queries, uint32_t nq, uint32_
     return NM_OK;
 }
 
+// Single-query calls from concurrent host threads are coalesced: the first caller becomes the
+// leader and runs its query at once; callers arriving while the GPU is busy queue up, and the
+// next leader round takes every queued query with the same (k, metric) through ONE search_impl
+// call (>= 4 of them share a corpus pass in the batched kernels).  Results are bit-identical
+// to isolated calls (tests/test_gpu_engine.py::test_concurrent_searches_are_coalesced).
+static int search_coalesced(nm_index *idx, const float *query, uint32_t k, int metric,
+                            uint64_t *out_rows, float *out_scores, uint32_t *out_count) {
+    nm_index::PendingSearch me;
+    me.query = query;
+    me.k = k;
+    me.metric = metric;
+    me.out_rows = out_rows;
+    me.out_scores = out_scores;
+    me.out_count = out_count;
+    std::unique_lock<std::mutex> lk(idx->co_mu);
+    idx->co_pending.push_back(&me);
+    for (;;) {
+        if (me.done) break;
+        if (idx->co_leader) {  // someone else is driving: wait for my result or for my turn
+            idx->co_cv.wait(lk);
+            continue;
+        }
+        // become the leader for one round: everything queued with my (k, metric)
+        idx->co_leader = true;
+        std::vector<nm_index::PendingSearch *> batch;
+        const size_t cap = (size_t)std::max(1, idx->coalesce_max.load());
+        for (auto it = idx->co_pending.begin(); it != idx->co_pending.end() && batch.size() < cap;) {
+            if ((*it)->k == me.k && (*it)->metric == me.metric) {
+                batch.push_back(*it);
+                it = idx->co_pending.erase(it);
+            } else {
+                ++it;
+            }
+        }
+        lk.unlock();
+        const uint32_t nb = (uint32_t)batch.size();
+        const uint32_t dim = idx->dim;
+        int rc;
+        if (nb == 1) {
+            rc = search_impl(idx, batch[0]->query, 1, k, metric, nullptr, batch[0]->out_rows,
+                             batch[0]->out_scores, batch[0]->out_count);
+        } else {
+            std::vector<float> qs((size_t)nb * dim);
+            std::vector<uint64_t> rows((size_t)nb * k);
+            std::vector<float> scores((size_t)nb * k);
+            std::vector<uint32_t> counts(nb);
+            for (uint32_t i = 0; i < nb; ++i)
+                memcpy(&qs[(size_t)i * dim], batch[i]->query, (size_t)dim * 4);
+            rc = search_impl(idx, qs.data(), nb, k, metric, nullptr, rows.data(), scores.data(),
+                             counts.data());
+            if (rc == NM_OK)
+                for (uint32_t i = 0; i < nb; ++i) {
+                    *batch[i]->out_count = counts[i];
+                    memcpy(batch[i]->out_rows, &rows[(size_t)i * k], (size_t)counts[i] * 8);
+                    memcpy(batch[i]->out_scores, &scores[(size_t)i * k], (size_t)counts[i] * 4);
+                }
+        }
+        const std::string err = rc ? std::string(nmi::last_error()) : std::string();
+        idx->co_batches++;
+        idx->co_queries += nb;
+        lk.lock();
+        for (auto *r : batch) {
+            r->rc = rc;
+            r->error = err;
+            r->done = true;
+        }
+        idx->co_leader = false;
+        idx->co_cv.notify_all();
+    }
+    lk.unlock();
+    if (me.rc) return fail(me.rc, "%s", me.error.c_str());
+    return NM_OK;
+}
+
 int nm_search(nm_index *idx, const float *queries, uint32_t nq, uint32_t k, int metric,
               uint64_t *out_rows, float *out_scores, uint32_t *out_counts) {
+    if (idx && nq == 1 && idx->coalesce_max.load() > 1 && queries && out_rows && out_scores &&
+        out_counts && k > 0 && metric >= 0 && metric <= 2 && idx->comm == nullptr)
+        return search_coalesced(idx, queries, k, metric, out_rows, out_scores, out_counts);
     return search_impl(idx, queries, nq, k, metric, nullptr, out_rows, out_scores, out_counts);
+}
+
+int nm_index_set_coalescing(nm_index *idx, int max_batch) {
+    if (!idx) return fail(NM_ERR_INVALID_ARGUMENT, "null index");
+    if (max_batch < 1) return fail(NM_ERR_INVALID_ARGUMENT, "max_batch must be >= 1");
+    idx->coalesce_max = max_batch;
+    return NM_OK;
 }
 
 int nm_search_masked(nm_index *idx, const float *queries, uint32_t nq, uint32_t k, int metric,

@@ -136,6 +136,9 @@ class DeviceIndex:
         """0 = off (default), 1 = exact int8 pre-filter (see include/neumann_b200.h)."""
         check(_ffi.lib().nm_index_set_prefilter(self._h, int(mode)))
 
+    def set_coalescing(self, max_batch: int) -> None:
+        check(_ffi.lib().nm_index_set_coalescing(self._h, int(max_batch)))
+
     def set_batching(self, enable: bool) -> None:
         check(_ffi.lib().nm_index_set_batching(self._h, 1 if enable else 0))
 

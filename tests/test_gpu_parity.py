@@ -228,7 +228,7 @@ def test_multi_query_batch_equals_single_queries():
     (2500, 13, 12, 4),
 ])
 def test_batched_queries_share_one_pass(metric, n, dim, nq, k):
-    """nq >= 8 goes through score_batch_kernel + select_batch_kernel (BASELINE config 4 shape);
+    """nq >= 4 goes through score_batch_kernel + select_batch_kernel (BASELINE config 4 shape);
     every (query, row) score and every per-query ranking must equal nq independent searches.
     dim % 8 != 0 with dot/cosine and dim % 32 != 0 with Euclidean cover the routing rules."""
     base = o.fill_synthetic(n, dim, 0x5EED0001)
@@ -349,6 +349,44 @@ def test_search_device_resident_buffers():
         assert int(d_counts[i]) == k
         assert np.array_equal(d_rows[i].cpu().numpy().astype(np.uint64), er)
         assert np.array_equal(d_scores[i].cpu().numpy().view(np.uint32), es.view(np.uint32))
+    idx.close()
+
+
+def test_concurrent_single_queries_are_coalesced():
+    """16 host threads issue single-query nm_search calls at once (the reference's serving
+    pattern): calls queue behind the running scan and share corpus passes; every result must
+    equal the isolated search."""
+    import threading
+    n, d, k = 400_000, 128, 10
+    idx, rows = synth_index(n, d)
+    qs = o.fill_synthetic(16 * 12, d, 0xC0A1)
+    expected = [o.search(rows, q, k, "cosine", threads=16) for q in qs[:48]]
+    results = [None] * len(qs)
+    errors = []
+
+    def worker(tid):
+        try:
+            for j in range(12):
+                i = tid * 12 + j
+                (results[i],) = idx.search(qs[i], k, "cosine")
+        except Exception as e:  # noqa: BLE001
+            errors.append(repr(e))
+
+    ts = [threading.Thread(target=worker, args=(t,)) for t in range(16)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    assert not errors, errors[:2]
+    st = idx.stats()
+    assert st.coalesced_queries == len(qs)
+    assert st.coalesced_batches < st.coalesced_queries      # some calls really shared a pass
+    for i in range(48):
+        assert_same(results[i], expected[i], f"coalesced q{i}")
+    idx.set_coalescing(1)
+    (alone,) = idx.search(qs[5], k, "cosine")
+    assert_same(alone, expected[5])
+    assert idx.stats().coalesced_queries == len(qs)          # coalescer bypassed
     idx.close()
 
 
