@@ -177,7 +177,7 @@ int nm_index_set_profiling(nm_index *idx, int enable);
  * scans the int8 copy with dp4a (4x fewer HBM bytes), brackets every row's reference score in
  * a rigorous interval, and re-scores only the rows whose interval reaches the k-th best lower
  * bound with the exact f32 arithmetic.  Results are bit-identical to mode 0 (tested); cosine
- * and dot product, k <= 1024, fewer than 4 queries per call; anything else, a non-finite
+ * and dot product, k <= 1024, single-query calls; anything else, a non-finite
  * query or an overflowing candidate list falls back to the f32 scan.  It changes the bytes
  * read per row, so it is OFF by default and benchmarked separately from the f32 roofline. */
 int nm_index_set_prefilter(nm_index *idx, int mode);
@@ -187,7 +187,7 @@ int nm_index_set_prefilter(nm_index *idx, int mode);
  * 1 disables).  No timers are involved, so a lone call is never delayed; results are
  * bit-identical to isolated calls. */
 int nm_index_set_coalescing(nm_index *idx, int max_batch);
-/* Batches of >= 4 queries share one corpus pass (batch_kernels.cuh) by default; 0 forces one
+/* Batches of >= 2 queries share one corpus pass (batch_kernels.cuh) by default; 0 forces one
  * scan per query.  Results are bit-identical either way (tested); this is a tuning knob. */
 int nm_index_set_batching(nm_index *idx, int enable);
 

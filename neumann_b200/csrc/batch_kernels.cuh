@@ -96,8 +96,15 @@ struct BatchScoreParams {
     uint32_t evict_first;
 };
 
+// Stage stride: corpus box + query chunk, rounded up to 1 KiB because the next stage's corpus
+// box must start 1024-byte aligned for SWIZZLE_128B (QB = 4 has a 512-byte query chunk).
 template <int QB>
 __host__ __device__ constexpr int batch_stage_bytes() {
+    return kStageBytes + ((32 * QB * 4 + 1023) / 1024) * 1024;
+}
+// Bytes that actually land in a stage (what the mbarrier expects).
+template <int QB>
+__host__ __device__ constexpr int batch_stage_tx_bytes() {
     return kStageBytes + 32 * QB * 4;
 }
 
@@ -148,7 +155,7 @@ score_batch_kernel(const __grid_constant__ CUtensorMap tmap, const BatchScorePar
                     mbar_wait(&empty_bar[stage], phase ^ 1u);
                     if (kc == 0) rb_ring[stage] = rb;
                     uint8_t *sb = stages + stage * kStage;
-                    mbar_arrive_expect_tx(&full_bar[stage], kStage);
+                    mbar_arrive_expect_tx(&full_bar[stage], batch_stage_tx_bytes<QB>());
                     tma_load_2d(sb, &tmap, (int32_t)(kc * kChunkFloats),
                                 (int32_t)(rb * kRowsPerBlock), &full_bar[stage], policy);
                     bulk_load_1d(sb + kStageBytes, p.qt + (size_t)kc * 32u * QB, 32u * QB * 4u,

@@ -220,7 +220,7 @@ struct nm_index {
 
 namespace nmi {
 
-constexpr uint32_t kBatchMinQueries = 4;  // below this, nq single-query passes are cheaper
+constexpr uint32_t kBatchMinQueries = 2;  // from 2 queries on, sharing the corpus pass pays
 
 struct ResultLayout {
     size_t counts_off, rows_off, scores_off, total;

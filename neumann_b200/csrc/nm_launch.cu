@@ -243,7 +243,9 @@ int scan_queries_batched(nm_index *idx, const Shard &sh, Workspace &ws, const fl
     const uint32_t k_eff = (uint32_t)std::min<uint64_t>(k, sh.rows);
     const uint32_t n_rb = ((uint32_t)sh.rows + nm::kRowsPerBlock - 1) / nm::kRowsPerBlock;
     const uint64_t stride = ((uint64_t)sh.rows + 63u) & ~uint64_t(63);
-    const uint32_t qb_max = (metric == NM_EUCLIDEAN) ? (nq > 16 ? 64u : 16u) : 16u;
+    // queries per pass: 4 / 8 / 16 (HBM-bound up to ~8, then FP32-issue-bound), 64 for L2 only
+    auto round_qb = [](uint32_t v) { return v <= 4u ? 4u : (v <= 8u ? 8u : 16u); };
+    const uint32_t qb_max = (metric == NM_EUCLIDEAN && nq > 16) ? 64u : round_qb(nq);
     // scratch
     if (!ws.d_bctl) {
         CUDA_TRY(cudaMalloc(&ws.d_bctl, (2 + kBatchMaxQB) * sizeof(uint32_t)));
@@ -283,7 +285,7 @@ int scan_queries_batched(nm_index *idx, const Shard &sh, Workspace &ws, const fl
 
     for (uint32_t q0 = 0; q0 < nq; q0 += qb_max) {
         const uint32_t nqp = std::min<uint32_t>(qb_max, nq - q0);
-        const uint32_t qb = (qb_max == 64u && nqp <= 16u) ? 16u : qb_max;
+        const uint32_t qb = nqp > 16u ? 64u : round_qb(nqp);
         nm::prepare_batch_kernel<<<std::max<uint32_t>(8u, (n_kc * 32u * qb + 255u) / 256u), 256, 0, stream>>>(
             d_queries + (size_t)q0 * dim, nqp, dim, qb, n_kc, ws.d_qt, ws.d_qmag);
         CUDA_TRY(cudaGetLastError());
@@ -299,21 +301,27 @@ int scan_queries_batched(nm_index *idx, const Shard &sh, Workspace &ws, const fl
         sp.dim = dim;
         sp.evict_first = (sh.rows * idx->pitch * 4ull > (64ull << 20)) ? 1u : 0u;
         int rc;
+#define NM_SCORE_BATCH(METRIC_, QB_)                                          \
+    do {                                                                      \
+        sp.n_stages = batch_stages<QB_>();                                    \
+        rc = launch_score_batch_t<METRIC_, QB_>(sh, sp, stream);              \
+    } while (0)
+#define NM_SCORE_BATCH_SMALL(METRIC_)                                         \
+    do {                                                                      \
+        if (qb == 4u) NM_SCORE_BATCH(METRIC_, 4);                             \
+        else if (qb == 8u) NM_SCORE_BATCH(METRIC_, 8);                        \
+        else NM_SCORE_BATCH(METRIC_, 16);                                     \
+    } while (0)
         if (metric == NM_EUCLIDEAN) {
-            if (qb == 64u) {
-                sp.n_stages = batch_stages<64>();
-                rc = launch_score_batch_t<nm::kEuclidean, 64>(sh, sp, stream);
-            } else {
-                sp.n_stages = batch_stages<16>();
-                rc = launch_score_batch_t<nm::kEuclidean, 16>(sh, sp, stream);
-            }
+            if (qb == 64u) NM_SCORE_BATCH(nm::kEuclidean, 64);
+            else NM_SCORE_BATCH_SMALL(nm::kEuclidean);
         } else if (metric == NM_COSINE) {
-            sp.n_stages = batch_stages<16>();
-            rc = launch_score_batch_t<nm::kCosine, 16>(sh, sp, stream);
+            NM_SCORE_BATCH_SMALL(nm::kCosine);
         } else {
-            sp.n_stages = batch_stages<16>();
-            rc = launch_score_batch_t<nm::kDot, 16>(sh, sp, stream);
+            NM_SCORE_BATCH_SMALL(nm::kDot);
         }
+#undef NM_SCORE_BATCH_SMALL
+#undef NM_SCORE_BATCH
         if (rc) return rc;
         nm::BatchSelectParams bp;
         memset(&bp, 0, sizeof(bp));

@@ -366,7 +366,7 @@ static int search_impl(nm_index *idx, const float *queries, uint32_t nq, uint32_
 // Single-query calls from concurrent host threads are coalesced: the first caller becomes the
 // leader and runs its query at once; callers arriving while the GPU is busy queue up, and the
 // next leader round takes every queued query with the same (k, metric) through ONE search_impl
-// call (>= 4 of them share a corpus pass in the batched kernels).  Results are bit-identical
+// call (>= 2 of them share a corpus pass in the batched kernels).  Results are bit-identical
 // to isolated calls (tests/test_gpu_engine.py::test_concurrent_searches_are_coalesced).
 static int search_coalesced(nm_index *idx, const float *query, uint32_t k, int metric,
                             uint64_t *out_rows, float *out_scores, uint32_t *out_count) {

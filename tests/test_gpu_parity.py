@@ -223,12 +223,12 @@ def test_multi_query_batch_equals_single_queries():
 
 @pytest.mark.parametrize("metric", METRICS)
 @pytest.mark.parametrize("n,dim,nq,k", [
-    (3000, 64, 8, 5), (20000, 96, 17, 10), (5000, 768, 70, 10), (1000, 40, 256, 100),
+    (3000, 64, 2, 5), (6000, 64, 3, 5), (3000, 64, 8, 5), (20000, 96, 17, 10), (5000, 768, 70, 10), (1000, 40, 256, 100),
     (70000, 32, 33, 1000), (300, 24, 9, 1024), (9000, 100, 20, 7), (4000, 1536, 64, 100),
     (2500, 13, 12, 4),
 ])
 def test_batched_queries_share_one_pass(metric, n, dim, nq, k):
-    """nq >= 4 goes through score_batch_kernel + select_batch_kernel (BASELINE config 4 shape);
+    """nq >= 2 goes through score_batch_kernel + select_batch_kernel (BASELINE config 4 shape);
     every (query, row) score and every per-query ranking must equal nq independent searches.
     dim % 8 != 0 with dot/cosine and dim % 32 != 0 with Euclidean cover the routing rules."""
     base = o.fill_synthetic(n, dim, 0x5EED0001)
@@ -238,7 +238,7 @@ def test_batched_queries_share_one_pass(metric, n, dim, nq, k):
     idx.load(rows)
     qs = o.fill_synthetic(nq, dim, 0xBEEF)
     qs[1] = rows[7]                                      # a query equal to a stored row
-    if metric != "euclidean":
+    if metric != "euclidean" and nq > 2:
         qs[2] = 0.0                                      # zero query: cosine scores all 0.0
     res = idx.search(qs, k, metric)
     launches_batched = idx.stats().scan_launches
@@ -250,8 +250,11 @@ def test_batched_queries_share_one_pass(metric, n, dim, nq, k):
     for i in range(nq):
         assert np.array_equal(res[i][0], res2[i][0])
         assert np.array_equal(res[i][1].view(np.uint32), res2[i][1].view(np.uint32))
-    batched_expected = metric == "euclidean" or dim % 8 == 0
-    assert (launches_batched < nq) == batched_expected
+    if metric == "euclidean" or dim % 8 == 0:        # batched: prepare + score + select per pass
+        per_pass = 64 if (metric == "euclidean" and nq > 16) else 16
+        assert launches_batched == 3 * -(-nq // per_pass)
+    else:                                             # dot/cosine tail rule: one scan per query
+        assert launches_batched == nq
     idx.close()
 
 
@@ -393,6 +396,7 @@ def test_concurrent_single_queries_are_coalesced():
 def test_stats_counters():
     idx, _ = synth_index(1000, 64)
     q = o.fill_synthetic(2, 64, 5)
+    idx.set_batching(False)              # two queries would otherwise share one batched pass
     idx.search(q, 3, "dot")
     s = idx.stats()
     assert s.searches == 2 and s.scan_launches == 2
