@@ -165,6 +165,9 @@ typedef struct nm_stats {
     uint64_t prefilter_kept;      /* rows whose score interval reached the running bound   */
     uint64_t coalesced_batches;   /* leader rounds of the single-query coalescer           */
     uint64_t coalesced_queries;   /* queries served by those rounds                        */
+    uint64_t tc_queries;          /* queries served through the tensor-core batch pre-filter */
+    uint64_t tc_fallbacks;        /* of those, redone by the exact path                     */
+    uint64_t tc_survivors;        /* (row, query) pairs re-scored exactly                    */
 } nm_stats;
 int nm_index_stats(nm_index *idx, nm_stats *out);
 /* When enabled, every asynchronous nm_search_device call brackets its scan launches (not the
@@ -181,6 +184,22 @@ int nm_index_set_profiling(nm_index *idx, int enable);
  * query or an overflowing candidate list falls back to the f32 scan.  It changes the bytes
  * read per row, so it is OFF by default and benchmarked separately from the f32 roofline. */
 int nm_index_set_prefilter(nm_index *idx, int mode);
+/* Batches (nq >= 2) on an index with the pre-filter ON go through the tensor-core pre-filter
+ * (tc_prefilter_kernels.cuh): ONE pass over the int8 copy serves up to 256 queries as an exact
+ * s8 x s8 -> s32 GEMM on the tcgen05 tensor cores (accumulators in TMEM); every integer dot
+ * product is turned into a rigorous score interval (cosine, dot product AND the reference's
+ * scalar L2 chain), only entries whose interval reaches the query's running k-th best lower
+ * bound are kept, and those are re-scored from the f32 mirror with the reference arithmetic.
+ * Results are bit-identical to the exact batched kernels (tested); queries that are not
+ * finite or whose candidate list overflows are redone by the exact path.  Single-device
+ * indexes, >= 32768 rows, k <= 1024.  enable = 0 keeps batches on the exact kernels. */
+int nm_index_set_tensor_core(nm_index *idx, int enable);
+/* Diagnostics: the exact integer dot products the tensor-core pass computes,
+ * out[q * rows + r] = sum_i int8(row r)[i] * int8(query q)[i], for the first min(nq, 256)
+ * queries (host buffers).  Needs the pre-filter ON and a single-device index. */
+int nm_debug_tc_dots(nm_index *idx, const float *queries, uint32_t nq, int32_t *out);
+/* Diagnostics: the int8 copy of row `row` and its scale (x ~ scale * int8). */
+int nm_debug_q8_row(nm_index *idx, uint64_t row, int8_t *out_q8, float *out_scale);
 /* Concurrent single-query nm_search calls (many host threads, the reference's serving pattern:
  * stress_tests/tests/mixed_workload_stress.rs:291-307) are coalesced: calls that arrive while
  * the GPU is busy ride the next corpus pass together, up to max_batch per pass (default 64;

@@ -35,6 +35,7 @@ class NmStats(C.Structure):
         ("prefilter_queries", C.c_uint64), ("prefilter_fallbacks", C.c_uint64),
         ("prefilter_kept", C.c_uint64),
         ("coalesced_batches", C.c_uint64), ("coalesced_queries", C.c_uint64),
+        ("tc_queries", C.c_uint64), ("tc_fallbacks", C.c_uint64), ("tc_survivors", C.c_uint64),
     ]
 
 
@@ -71,6 +72,9 @@ SIGNATURES = {
     "nm_index_set_batching": (C.c_int, [_vp, C.c_int]),
     "nm_index_set_prefilter": (C.c_int, [_vp, C.c_int]),
     "nm_index_set_coalescing": (C.c_int, [_vp, C.c_int]),
+    "nm_index_set_tensor_core": (C.c_int, [_vp, C.c_int]),
+    "nm_debug_tc_dots": (C.c_int, [_vp, _vp, C.c_uint32, _vp]),
+    "nm_debug_q8_row": (C.c_int, [_vp, C.c_uint64, _vp, _f32p]),
 }
 
 _lib = None

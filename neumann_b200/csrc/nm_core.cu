@@ -111,7 +111,28 @@ int build_tmap8(nm_index *idx, Shard &sh) {
                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS)
         return fail(NM_ERR_STORAGE, "cuTensorMapEncodeTiled (int8) failed with CUresult %d", (int)r);
+    // the tensor-core batch pre-filter reads the same copy in [128 rows x 128 B] MMA tiles
+    int rc = encode_tmap_u8(&sh.tmap8_tc, sh.d_q8, idx->dim, sh.rows, q8_pitch(idx->dim), 128,
+                            nm::kTcTileRows);
+    if (rc) return rc;
     sh.tmap8_valid = true;
+    return NM_OK;
+}
+
+// 2-D uint8 tensor map [rows, inner] (row pitch in bytes), SWIZZLE_128B, zero fill out of bounds.
+int encode_tmap_u8(CUtensorMap *out, void *base, uint64_t inner, uint64_t rows, uint64_t pitch_bytes,
+                   uint32_t box_inner, uint32_t box_rows) {
+    EncodeTiledFn enc = get_encode_tiled();
+    if (!enc) return fail(NM_ERR_STORAGE, "cuTensorMapEncodeTiled unavailable (driver too old?)");
+    cuuint64_t gdim[2] = {inner, rows};
+    cuuint64_t gstride[1] = {pitch_bytes};
+    cuuint32_t box[2] = {box_inner, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, base, gdim, gstride, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS)
+        return fail(NM_ERR_STORAGE, "cuTensorMapEncodeTiled (u8) failed with CUresult %d", (int)r);
     return NM_OK;
 }
 
@@ -505,6 +526,27 @@ int nm_index_set_prefilter(nm_index *idx, int mode) {
     return NM_OK;
 }
 
+int nm_index_set_tensor_core(nm_index *idx, int enable) {
+    if (!idx) return fail(NM_ERR_INVALID_ARGUMENT, "null index");
+    idx->tensor_core = enable ? 1 : 0;
+    return NM_OK;
+}
+
+int nm_debug_q8_row(nm_index *idx, uint64_t row, int8_t *out_q8, float *out_scale) {
+    if (!idx || !out_q8 || !out_scale) return fail(NM_ERR_INVALID_ARGUMENT, "null argument");
+    std::shared_lock<std::shared_mutex> g(idx->mu);
+    if (idx->shards.size() != 1 || !idx->shards[0]->d_q8 || row >= idx->shards[0]->q8_rows)
+        return fail(NM_ERR_CONFIGURATION, "needs a single-device index with the pre-filter on");
+    Shard &sh = *idx->shards[0];
+    CUDA_TRY(cudaSetDevice(sh.device));
+    const uint32_t pitch8 = q8_pitch(idx->dim);
+    CUDA_TRY(cudaMemcpy(out_q8, sh.d_q8 + row * pitch8, idx->dim, cudaMemcpyDeviceToHost));
+    nm::RowMeta m;
+    CUDA_TRY(cudaMemcpy(&m, sh.d_meta + row, sizeof(m), cudaMemcpyDeviceToHost));
+    *out_scale = m.scale;
+    return NM_OK;
+}
+
 int nm_index_set_batching(nm_index *idx, int enable) {
     if (!idx) return fail(NM_ERR_INVALID_ARGUMENT, "null index");
     idx->batching = enable ? 1 : 0;
@@ -530,6 +572,9 @@ int nm_index_stats(nm_index *idx, nm_stats *out) {
     out->prefilter_queries = idx->pf_queries;
     out->prefilter_fallbacks = idx->pf_fallbacks;
     out->prefilter_kept = idx->pf_kept;
+    out->tc_queries = idx->tc_queries;
+    out->tc_fallbacks = idx->tc_fallbacks;
+    out->tc_survivors = idx->tc_survivors;
     out->coalesced_batches = idx->co_batches;
     out->coalesced_queries = idx->co_queries;
     {

@@ -89,6 +89,16 @@ struct Workspace {
     uint32_t *d_pf_ctl = nullptr;   // [nq][8]
     uint32_t *h_pf_ctl = nullptr;   // pinned
     size_t pf_ctl_cap = 0;          // queries
+    // tensor-core batch pre-filter (tc_prefilter_kernels.cuh)
+    int8_t *d_tc_q8 = nullptr;      // [256][pitch8] int8 queries of the current pass
+    size_t tc_q8_cap = 0;           // bytes
+    void *d_tc_qmeta = nullptr;     // [nq] nm::TcQueryMeta
+    void *h_tc_qmeta = nullptr;     // pinned
+    void *d_tc_coef = nullptr;      // [nq] float4
+    uint32_t *d_tc_kept_n = nullptr;  // [nq] + [1] statistics
+    size_t tc_nq_cap = 0;           // queries
+    void *d_tc_kept = nullptr;      // [256][kTcKeptCap] nm::TcKept
+    uint64_t *d_tc_keys = nullptr;  // [256][kTcKeptCap]
     // batched-query path (batch_kernels.cuh)
     float *d_qt = nullptr;         // [n_kc][32][QB] transposed query chunks
     size_t qt_cap = 0;             // floats
@@ -116,6 +126,13 @@ struct Workspace {
         if (d_exact_keys) cudaFree(d_exact_keys);
         if (d_pf_ctl) cudaFree(d_pf_ctl);
         if (h_pf_ctl) cudaFreeHost(h_pf_ctl);
+        if (d_tc_q8) cudaFree(d_tc_q8);
+        if (d_tc_qmeta) cudaFree(d_tc_qmeta);
+        if (h_tc_qmeta) cudaFreeHost(h_tc_qmeta);
+        if (d_tc_coef) cudaFree(d_tc_coef);
+        if (d_tc_kept_n) cudaFree(d_tc_kept_n);
+        if (d_tc_kept) cudaFree(d_tc_kept);
+        if (d_tc_keys) cudaFree(d_tc_keys);
         if (d_qt) cudaFree(d_qt);
         if (d_qmag) cudaFree(d_qmag);
         if (d_scores) cudaFree(d_scores);
@@ -152,6 +169,7 @@ struct Shard {
     uint64_t q8_capacity = 0;
     uint64_t q8_rows = 0;  // rows [0, q8_rows) are quantised and current
     CUtensorMap tmap8;
+    CUtensorMap tmap8_tc;  // same copy, [128 rows x 128 B] boxes (tensor-core batch pre-filter)
     bool tmap8_valid = false;
     cudaStream_t copy_stream = nullptr;
     float *staging[2] = {nullptr, nullptr};
@@ -187,6 +205,9 @@ struct nm_index {
     std::atomic<double> last_scan_ms{0.0};
     std::atomic<int> profiling{0};
     std::atomic<int> prefilter{0};  // nm_index_set_prefilter: 1 = exact int8 pre-filter
+    std::atomic<int> tensor_core{1};  // nm_index_set_tensor_core: batches of a pre-filtered index
+                                      // go through the tcgen05 int8 GEMM pre-filter
+    std::atomic<uint64_t> tc_queries{0}, tc_fallbacks{0}, tc_survivors{0};
     std::atomic<uint64_t> pf_queries{0}, pf_fallbacks{0}, pf_kept{0};
     std::atomic<int> batching{1};  // nm_index_set_batching: 0 forces one scan per query
     // Coalescing of concurrent single-query nm_search calls (nm_index_set_coalescing): while
@@ -242,6 +263,8 @@ inline uint32_t pow2_ceil(uint32_t v) {
 // ---- nm_core.cu ----
 int build_tmap(nm_index *idx, Shard &sh);
 int q8_refresh(nm_index *idx, Shard &sh, uint64_t first, uint64_t n);
+int encode_tmap_u8(CUtensorMap *out, void *base, uint64_t inner, uint64_t rows, uint64_t pitch_bytes,
+                   uint32_t box_inner, uint32_t box_rows);
 uint32_t q8_pitch(uint32_t dim);
 
 // ---- nm_launch.cu: workspaces + every kernel launch ----
@@ -264,6 +287,16 @@ int scan_queries(nm_index *idx, const Shard &sh, Workspace &ws, const float *d_q
 int launch_prefiltered(nm_index *idx, const Shard &sh, Workspace &ws, const float *d_query,
                        uint32_t q, uint32_t k, int metric, uint64_t *out_rows, float *out_scores,
                        uint32_t *out_count, cudaStream_t stream);
+bool tc_usable(const nm_index *idx, const Shard &sh, uint32_t nq, uint32_t k, int metric,
+               const uint64_t *row_mask);
+// nq queries through the tensor-core pre-filter; h_flags[q] != 0 afterwards (once the stream has
+// been waited for) means query q must be redone by the exact path.  *h_flags_out points into
+// pinned memory owned by the workspace.
+int scan_queries_tc(nm_index *idx, const Shard &sh, Workspace &ws, const float *d_queries,
+                    uint32_t nq, uint32_t k, int metric, uint64_t *out_rows, float *out_scores,
+                    uint32_t *out_counts, cudaStream_t stream, int *debug_dots = nullptr);
+uint32_t tc_query_flags(const Workspace &ws, uint32_t q);
+uint32_t tc_survivors(const Workspace &ws);
 int launch_merge_shards(nm_index *idx, const nm::ShardHit *d_gather, uint32_t nq, uint32_t k,
                         uint64_t *out_rows, float *out_scores, uint32_t *out_counts,
                         cudaStream_t stream);

@@ -4,6 +4,7 @@
 #include "scan_kernels.cuh"
 #include "batch_kernels.cuh"
 #include "prefilter_kernels.cuh"
+#include "tc_prefilter_kernels.cuh"
 
 namespace nmi {
 
@@ -435,6 +436,175 @@ int launch_prefiltered(nm_index *idx, const Shard &sh, Workspace &ws, const floa
     CUDA_TRY(cudaGetLastError());
     idx->scan_launches += 2;
     return NM_OK;
+}
+
+// ---- tensor-core batch pre-filter (tc_prefilter_kernels.cuh) ------------------------------
+constexpr uint32_t kTcMinRows = 2 * nm::kTcKeptCap;  // below this the exact kernels are cheaper
+
+bool tc_usable(const nm_index *idx, const Shard &sh, uint32_t nq, uint32_t k, int metric,
+               const uint64_t *row_mask) {
+    (void)metric;
+    if (!idx->prefilter.load() || !idx->tensor_core.load() || row_mask) return false;
+    if (nq < 2 || !sh.tmap8_valid || sh.q8_rows != sh.rows) return false;
+    if (sh.rows < kTcMinRows || k > (uint32_t)nm::kMaxFastK) return false;
+    if ((uint64_t)idx->dim * 16129ull >= 0x7fffffffull) return false;   // s32 accumulators
+    if ((size_t)idx->dim * 4 > 160 * 1024) return false;                // rescore keeps q in smem
+    return true;
+}
+
+static int ws_ensure_tc(Workspace &ws, uint32_t dim, uint32_t nq, cudaStream_t stream) {
+    const size_t q8_bytes = (size_t)nm::kTcMaxQ * q8_pitch(dim);
+    if (ws.tc_q8_cap < q8_bytes || ws.tc_nq_cap < nq) CUDA_TRY(cudaStreamSynchronize(stream));
+    if (ws.tc_q8_cap < q8_bytes) {
+        if (ws.d_tc_q8) CUDA_TRY(cudaFree(ws.d_tc_q8));
+        ws.tc_q8_cap = 0;
+        CUDA_TRY(cudaMalloc(&ws.d_tc_q8, q8_bytes));
+        ws.tc_q8_cap = q8_bytes;
+    }
+    if (ws.tc_nq_cap < nq) {
+        const size_t cap = std::max<size_t>(nq, nm::kTcMaxQ);
+        if (ws.d_tc_qmeta) CUDA_TRY(cudaFree(ws.d_tc_qmeta));
+        if (ws.h_tc_qmeta) CUDA_TRY(cudaFreeHost(ws.h_tc_qmeta));
+        if (ws.d_tc_coef) CUDA_TRY(cudaFree(ws.d_tc_coef));
+        if (ws.d_tc_kept_n) CUDA_TRY(cudaFree(ws.d_tc_kept_n));
+        ws.tc_nq_cap = 0;
+        ws.d_tc_qmeta = ws.h_tc_qmeta = ws.d_tc_coef = nullptr;
+        ws.d_tc_kept_n = nullptr;
+        CUDA_TRY(cudaMalloc(&ws.d_tc_qmeta, cap * sizeof(nm::TcQueryMeta)));
+        CUDA_TRY(cudaMallocHost(&ws.h_tc_qmeta, cap * sizeof(nm::TcQueryMeta) + 16));
+        CUDA_TRY(cudaMalloc(&ws.d_tc_coef, cap * sizeof(float4)));
+        CUDA_TRY(cudaMalloc(&ws.d_tc_kept_n, (cap + 4) * sizeof(uint32_t)));
+        ws.tc_nq_cap = cap;
+    }
+    if (!ws.d_tc_kept) {
+        CUDA_TRY(cudaMalloc(&ws.d_tc_kept, (size_t)nm::kTcMaxQ * nm::kTcKeptCap * sizeof(nm::TcKept)));
+        CUDA_TRY(cudaMalloc(&ws.d_tc_keys, (size_t)nm::kTcMaxQ * nm::kTcKeptCap * sizeof(uint64_t)));
+    }
+    return NM_OK;
+}
+
+// Phases: rows [0, 16Ki) keep everything, then ranges growing by `factor` (expected kept entries
+// per query and phase ~ k (factor - 1) on unordered data), a refine step after each.
+int scan_queries_tc(nm_index *idx, const Shard &sh, Workspace &ws, const float *d_queries,
+                    uint32_t nq, uint32_t k, int metric, uint64_t *out_rows, float *out_scores,
+                    uint32_t *out_counts, cudaStream_t stream, int *debug_dots) {
+    static std::mutex mu;
+    static bool configured[64] = {false};
+    {
+        std::lock_guard<std::mutex> g(mu);
+        if (sh.device >= 64 || !configured[sh.device]) {
+            CUDA_TRY(cudaFuncSetAttribute(nm::tc_gemm_filter_kernel,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            CUDA_TRY(cudaFuncSetAttribute(nm::tc_rescore_kernel,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+            if (sh.device < 64) configured[sh.device] = true;
+        }
+    }
+    static const bool screen = [] {
+        const char *e = getenv("NM_TC_SCREEN");
+        return !(e && e[0] == '0');
+    }();
+    const uint32_t dim = idx->dim, pitch8 = q8_pitch(dim);
+    const uint32_t rows = (uint32_t)sh.rows;
+    const uint32_t k_eff = std::min<uint32_t>(k, rows);
+    int rc = ws_ensure_tc(ws, dim, nq, stream);
+    if (rc) return rc;
+    auto *qmeta = static_cast<nm::TcQueryMeta *>(ws.d_tc_qmeta);
+    auto *coef = static_cast<float4 *>(ws.d_tc_coef);
+    auto *kept = static_cast<nm::TcKept *>(ws.d_tc_kept);
+    uint32_t *stats = ws.d_tc_kept_n + ws.tc_nq_cap;
+    CUDA_TRY(cudaMemsetAsync(stats, 0, 4 * sizeof(uint32_t), stream));
+    const uint32_t factor =
+        std::max<uint32_t>(2u, std::min<uint32_t>(16u, nm::kTcKeptCap / (4u * k_eff)));
+    const int kmetric = metric == NM_COSINE ? nm::kCosine
+                                            : (metric == NM_EUCLIDEAN ? nm::kEuclidean : nm::kDot);
+    for (uint32_t q0 = 0; q0 < nq; q0 += nm::kTcMaxQ) {
+        const uint32_t nqp = std::min<uint32_t>(nm::kTcMaxQ, nq - q0);
+        const uint32_t n_pad = (nqp + 15u) & ~15u;
+        nm::tc_prepare_queries_kernel<<<n_pad, 256, 0, stream>>>(
+            d_queries + (size_t)q0 * dim, nqp, dim, pitch8, ws.d_tc_q8, qmeta + q0, coef + q0,
+            ws.d_tc_kept_n + q0);
+        CUDA_TRY(cudaGetLastError());
+        CUtensorMap tmap_q;
+        rc = encode_tmap_u8(&tmap_q, ws.d_tc_q8, dim, n_pad, pitch8, 128, n_pad);
+        if (rc) return rc;
+        nm::TcGemmParams gp;
+        memset(&gp, 0, sizeof(gp));
+        gp.meta = sh.d_meta;
+        gp.qmeta = qmeta + q0;
+        gp.coef = coef + q0;
+        gp.kept = kept;
+        gp.kept_n = ws.d_tc_kept_n + q0;
+        gp.dump = debug_dots ? debug_dots + (size_t)q0 * rows : nullptr;
+        gp.dump_stride = rows;
+        gp.dim = dim;
+        gp.nq = nqp;
+        gp.n_pad = n_pad;
+        gp.evict_first = ((uint64_t)rows * pitch8 > (64ull << 20)) ? 1u : 0u;
+        gp.screen = screen ? 1u : 0u;
+        gp.metric = kmetric;
+        nm::TcRefineParams rp;
+        memset(&rp, 0, sizeof(rp));
+        rp.kept = kept;
+        rp.kept_n = ws.d_tc_kept_n + q0;
+        rp.qmeta = qmeta + q0;
+        rp.coef = coef + q0;
+        rp.dim = dim;
+        rp.k = k_eff;
+        rp.metric = kmetric;
+        uint64_t begin = 0, end = std::min<uint64_t>(rows, nm::kTcKeptCap);
+        while (begin < rows) {
+            gp.row_begin = (uint32_t)begin;
+            gp.row_end = (uint32_t)end;
+            const uint32_t n_tiles = (uint32_t)((end - begin + nm::kTcM - 1) / nm::kTcM);
+            const uint32_t grid = std::min<uint32_t>((uint32_t)sh.sm_count, n_tiles);
+            nm::tc_gemm_filter_kernel<<<grid, nm::kTcThreads, nm::tc_gemm_smem_bytes(), stream>>>(
+                sh.tmap8_tc, tmap_q, gp);
+            CUDA_TRY(cudaGetLastError());
+            nm::tc_refine_kernel<<<nqp, 256, 0, stream>>>(rp);
+            CUDA_TRY(cudaGetLastError());
+            idx->scan_launches += 2;
+            begin = end;
+            end = std::min<uint64_t>(rows, end * factor);
+        }
+        nm::TcRescoreParams sp;
+        memset(&sp, 0, sizeof(sp));
+        sp.queries = d_queries + (size_t)q0 * dim;
+        sp.rows = sh.d_rows;
+        sp.kept = kept;
+        sp.kept_n = ws.d_tc_kept_n + q0;
+        sp.qmeta = qmeta + q0;
+        sp.exact_keys = ws.d_tc_keys;
+        sp.out_rows = out_rows + (size_t)q0 * k;
+        sp.out_scores = out_scores + (size_t)q0 * k;
+        sp.out_counts = out_counts + q0;
+        sp.stats = stats;
+        sp.row_base = sh.row_base;
+        sp.pitch = idx->pitch;
+        sp.dim = dim;
+        sp.k = k_eff;
+        sp.out_stride = k;
+        sp.metric = kmetric;
+        nm::tc_rescore_kernel<<<nqp, nm::kRowsPerBlock, (size_t)dim * 4, stream>>>(sp);
+        CUDA_TRY(cudaGetLastError());
+        idx->scan_launches += 2;
+    }
+    // flags + statistics come back with the results
+    CUDA_TRY(cudaMemcpyAsync(ws.h_tc_qmeta, ws.d_tc_qmeta, (size_t)nq * sizeof(nm::TcQueryMeta),
+                             cudaMemcpyDeviceToHost, stream));
+    CUDA_TRY(cudaMemcpyAsync(static_cast<uint8_t *>(ws.h_tc_qmeta) +
+                                 ws.tc_nq_cap * sizeof(nm::TcQueryMeta),
+                             stats, 16, cudaMemcpyDeviceToHost, stream));
+    return NM_OK;
+}
+
+// after the stream has been waited for: which queries must be redone exactly
+uint32_t tc_query_flags(const Workspace &ws, uint32_t q) {
+    return static_cast<const nm::TcQueryMeta *>(ws.h_tc_qmeta)[q].flags;
+}
+uint32_t tc_survivors(const Workspace &ws) {
+    return *reinterpret_cast<const uint32_t *>(static_cast<const uint8_t *>(ws.h_tc_qmeta) +
+                                               ws.tc_nq_cap * sizeof(nm::TcQueryMeta));
 }
 
 // nq queries over one shard: batched kernels when that pays, else one (chained) scan per query.

@@ -184,6 +184,49 @@ static int search_impl(nm_index *idx, const float *queries, uint32_t nq, uint32_
                                  nullptr, ws->stream, nullptr, ws->d_mask);
                 if (rc) return rc;
             }
+        } else if (tc_usable(idx, sh, nq, k, metric, row_mask)) {
+            // tensor-core pre-filter: one int8 GEMM pass per 256 queries + exact re-score; the
+            // per-query flags come back with the results, flagged queries are redone exactly
+            rc = scan_queries_tc(idx, sh, *ws, ws->d_query, nq, k, metric, r_rows, r_scores,
+                                 r_counts, ws->stream);
+            if (rc) return rc;
+            CUDA_TRY(cudaEventRecord(ws->ev1, ws->stream));
+            CUDA_TRY(cudaMemcpyAsync(ws->h_result, ws->d_result, l.total, cudaMemcpyDeviceToHost,
+                                     ws->stream));
+            rc = wait_stream(ws->stream);
+            if (rc) return rc;
+            idx->tc_queries += nq;
+            idx->tc_survivors += tc_survivors(*ws);
+            bool redo = false;
+            for (uint32_t q = 0; q < nq; ++q) {
+                if (tc_query_flags(*ws, q) == 0) continue;
+                idx->tc_fallbacks++;
+                redo = true;
+                rc = launch_scan(idx, sh, *ws, ws->d_query + (size_t)q * dim, k, metric, sh.row_base,
+                                 r_rows + (size_t)q * k, r_scores + (size_t)q * k, r_counts + q,
+                                 nullptr, ws->stream);
+                if (rc) return rc;
+            }
+            if (!redo) {
+                float ms = 0.f;
+                CUDA_TRY(cudaEventElapsedTime(&ms, ws->ev0, ws->ev1));
+                idx->last_scan_ms = ms;
+                const uint32_t *hc = reinterpret_cast<const uint32_t *>(ws->h_result + l.counts_off);
+                const uint64_t *hr = reinterpret_cast<const uint64_t *>(ws->h_result + l.rows_off);
+                const float *hs = reinterpret_cast<const float *>(ws->h_result + l.scores_off);
+                for (uint32_t q = 0; q < nq; ++q) {
+                    out_counts[q] = hc[q];
+                    memcpy(out_rows + (size_t)q * k, hr + (size_t)q * k, (size_t)hc[q] * 8);
+                    memcpy(out_scores + (size_t)q * k, hs + (size_t)q * k, (size_t)hc[q] * 4);
+                }
+                idx->searches += nq;
+                idx->rows_scanned += (uint64_t)nq * sh.rows;
+                idx->bytes_streamed += (uint64_t)((nq + 255u) / 256u) * sh.rows *
+                                       (q8_pitch(dim) + sizeof(nm::RowMeta));
+                idx->h2d_bytes += (uint64_t)nq * dim * 4;
+                idx->d2h_bytes += l.total + (uint64_t)nq * 48;
+                return NM_OK;
+            }
         } else if (prefilter_usable(idx, sh, nq, k, metric, row_mask)) {
             rc = ws_ensure_prefilter(*ws, nq);
             if (rc) return rc;
@@ -443,6 +486,50 @@ int nm_search(nm_index *idx, const float *queries, uint32_t nq, uint32_t k, int 
         out_counts && k > 0 && metric >= 0 && metric <= 2 && idx->comm == nullptr)
         return search_coalesced(idx, queries, k, metric, out_rows, out_scores, out_counts);
     return search_impl(idx, queries, nq, k, metric, nullptr, out_rows, out_scores, out_counts);
+}
+
+int nm_debug_tc_dots(nm_index *idx, const float *queries, uint32_t nq, int32_t *out) {
+    if (!idx || !queries || !out || nq == 0) return fail(NM_ERR_INVALID_ARGUMENT, "null argument");
+    std::shared_lock<std::shared_mutex> g(idx->mu);
+    if (idx->shards.size() != 1 || idx->comm)
+        return fail(NM_ERR_CONFIGURATION, "nm_debug_tc_dots needs a single-device index");
+    Shard &sh = *idx->shards[0];
+    nq = std::min<uint32_t>(nq, 256u);
+    if (!sh.tmap8_valid || sh.q8_rows != sh.rows || sh.rows == 0)
+        return fail(NM_ERR_CONFIGURATION, "nm_debug_tc_dots needs the pre-filter on");
+    CUDA_TRY(cudaSetDevice(sh.device));
+    std::unique_ptr<Workspace> ws;
+    int rc = ws_acquire(sh, ws);
+    if (rc) return rc;
+    struct Releaser {
+        Shard &s;
+        std::unique_ptr<Workspace> &w;
+        ~Releaser() { ws_release(s, w); }
+    } rel{sh, ws};
+    const uint32_t k = 1;
+    rc = ws_ensure(*ws, sh, idx->dim, nq, k, true, true, false, 0);
+    if (rc) return rc;
+    ResultLayout l = result_layout(nq, k);
+    memcpy(ws->h_query, queries, (size_t)nq * idx->dim * 4);
+    CUDA_TRY(cudaMemcpyAsync(ws->d_query, ws->h_query, (size_t)nq * idx->dim * 4,
+                             cudaMemcpyHostToDevice, ws->stream));
+    int *d_dots = nullptr;
+    CUDA_TRY(cudaMalloc(&d_dots, (size_t)nq * sh.rows * 4));
+    rc = scan_queries_tc(idx, sh, *ws, ws->d_query, nq, k, NM_DOT_PRODUCT,
+                         reinterpret_cast<uint64_t *>(ws->d_result + l.rows_off),
+                         reinterpret_cast<float *>(ws->d_result + l.scores_off),
+                         reinterpret_cast<uint32_t *>(ws->d_result + l.counts_off), ws->stream,
+                         d_dots);
+    if (rc == NM_OK) {
+        cudaError_t e = cudaMemcpyAsync(out, d_dots, (size_t)nq * sh.rows * 4,
+                                        cudaMemcpyDeviceToHost, ws->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ws->stream);
+        if (e != cudaSuccess)
+            rc = fail(NM_ERR_STORAGE, "CUDA error %s in nm_debug_tc_dots: %s", cudaGetErrorName(e),
+                      cudaGetErrorString(e));
+    }
+    cudaFree(d_dots);
+    return rc;
 }
 
 int nm_index_set_coalescing(nm_index *idx, int max_batch) {

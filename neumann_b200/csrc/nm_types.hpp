@@ -46,6 +46,8 @@ struct alignas(16) RowMeta {
     uint32_t flags;   // bit 0: row has a non-finite element
 };
 
+constexpr uint32_t kTcTileRows = 128;  // corpus rows per tensor-core tile (tc_prefilter_kernels.cuh)
+
 constexpr uint32_t kKeptCap = 1u << 20;  // kept (row, ub) entries per query before fallback
 
 struct KeptEntry {

@@ -1,0 +1,797 @@
+// tc_prefilter_kernels.cuh — tensor-core pre-filter for BATCHES of queries (BASELINE config 4:
+// "10M x 1536 f32 L2 TOP 100, batch 256 queries"), with EXACT re-score.
+//
+// The reference has no batch API: a batch is nq independent
+// search_similar_with_metric calls (vector_engine/src/lib.rs:2049-2101), so every returned
+// (row, score) must still be the bit-exact result of compute_score (lib.rs:2231-2246).  The
+// exact batched kernels (batch_kernels.cuh) are FP32-issue bound: 3 non-fusable lane-ops per
+// (element, query).  This path gets the same answer from the int8 mirror copy
+// (prefilter_kernels.cuh) and the 5th-generation tensor cores:
+//
+//   tc_prepare_queries_kernel   per query: int8 quantisation (own scale), sum|qt|, |q|^2
+//                               bounds, reference-arithmetic |q|.
+//   tc_gemm_filter_kernel       persistent GEMM  I[row, q] = sum_i xt[row,i] * qt[q,i]  with
+//                               tcgen05.mma kind::i8 (s8 x s8 -> s32, EXACT): A = 128 corpus
+//                               rows x 128 B and B = up to 256 queries x 128 B per stage, both
+//                               K-major SWIZZLE_128B boxes staged by TMA; accumulators
+//                               [128 lanes x 256 columns] s32 in TMEM, double buffered (512
+//                               columns) so the epilogue of tile t overlaps the MMAs of t+1.
+//                               Warp roles: 0 = TMA producer, 1 = MMA issuer (one thread),
+//                               2..5 = epilogue (one TMEM lane quarter each).
+//                               The epilogue never writes the score matrix.  Each exact
+//                               integer dot product gives a rigorous interval [lb, ub] for
+//                               the reference score (same error model as the 1-query
+//                               pre-filter, extended to the scalar L2 chain); an entry is kept
+//                               only if ub can still reach the query's running threshold tau
+//                               (k-th best lb so far).  A 5-instruction f32 test with provable
+//                               slack screens every (row, query); the few that pass are
+//                               re-evaluated rigorously in double and appended to the query's
+//                               kept list.
+//   tc_refine_kernel            per query: radix-select the k-th best lb of the kept list ->
+//                               new tau, compact the list to ub >= tau, derive the screen
+//                               coefficients for the next phase.
+//   tc_rescore_kernel           per query: survivors are re-scored from the f32 mirror with
+//                               the reference arithmetic and selected exactly like the f32
+//                               scan (same keys, same tie rule).
+//
+// The corpus is walked in phases of geometrically growing row ranges (first 16 Ki rows: keep
+// everything; then x4..x16 each) with a refine step between phases, so tau tightens while only
+// ~k..16k entries per query and phase are kept.  Every row of the exact top-k has
+// ub >= score >= tau, so the result is bit-identical to the f32 scan; a query whose list
+// overflows or that is not finite is flagged and redone by the exact path.
+#pragma once
+#include "prefilter_kernels.cuh"
+
+namespace nm {
+
+constexpr uint32_t kTcM = 128;                             // corpus rows per tile == TMEM lanes
+constexpr uint32_t kTcKBytes = 128;                        // int8 elements per k-block
+constexpr uint32_t kTcMaxQ = 256;                          // queries per pass == UMMA N max
+constexpr uint32_t kTcStages = 4;
+constexpr uint32_t kTcABytes = kTcM * kTcKBytes;           // 16 KiB
+constexpr uint32_t kTcBBytesMax = kTcMaxQ * kTcKBytes;     // 32 KiB
+constexpr uint32_t kTcThreads = 192;
+constexpr uint32_t kTcKeptCap = 16384;                     // kept entries per query
+constexpr uint32_t kTcTmemCols = 512;                      // 2 accumulators x 256 columns
+
+constexpr uint32_t kTcFlagUnusable = 1u;   // query not finite / zero / denormal scale
+constexpr uint32_t kTcFlagOverflow = 2u;   // kept list overflowed
+
+struct TcKept {
+    uint32_t row;
+    uint32_t lb_ord;
+    uint32_t ub_ord;
+};
+
+struct alignas(16) TcQueryMeta {
+    double c_lo, c_hi;   // bounds on the real |q|^2
+    float s_q;           // quantisation scale
+    float qmag;          // reference lane-tree |q|
+    uint32_t q1;         // sum |qt_i|
+    uint32_t flags;      // kTcFlag*
+    uint32_t tau_ord;    // k-th best lower bound so far (0 = none yet)
+    uint32_t pad[3];
+};
+
+inline size_t tc_gemm_smem_bytes() {
+    return 1024 + (size_t)kTcStages * (kTcABytes + kTcBBytesMax) + (size_t)kTcMaxQ * 16 + 256;
+}
+
+#ifdef __CUDACC__
+
+// ---------------------------------------------------------------------------------------
+// PTX helpers: tcgen05 / TMEM
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ void tc_fence_before() {
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_after() {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+// mbarrier wait with a watchdog: a protocol bug traps (launch failure) instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait_wd(uint64_t *bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    long long t0 = 0;
+    for (uint32_t spins = 0;; ++spins) {
+        uint32_t done;
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}\n"
+            : "=r"(done)
+            : "r"(addr), "r"(parity)
+            : "memory");
+        if (done) return;
+        if (spins == 4096u) t0 = clock64();
+        if (spins > 4096u && (spins & 1023u) == 0u && clock64() - t0 > 6000000000ll) __trap();
+    }
+}
+// K-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout):
+// [0,14) start address >> 4, [16,30) leading byte offset >> 4 (1: unused for swizzled
+// K-major), [32,46) stride byte offset >> 4 (1024 B = 8 rows x 128 B), [46,48) version = 1,
+// [61,64) layout type = 2 (SWIZZLE_128B).
+__device__ __forceinline__ uint64_t tc_smem_desc(uint32_t saddr) {
+    return (uint64_t)((saddr >> 4) & 0x3fffu) | (1ull << 16) | (64ull << 32) | (1ull << 46) |
+           (2ull << 61);
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor): c_format S32 = 2 @4, a/b format
+// INT8 = 1 @7/@10, K-major A and B, N >> 3 @17, M >> 4 @24
+__device__ __forceinline__ uint32_t tc_idesc_i8(uint32_t m, uint32_t n) {
+    return (2u << 4) | (1u << 7) | (1u << 10) | ((n >> 3) << 17) | ((m >> 4) << 24);
+}
+__device__ __forceinline__ void tc_mma_i8(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc,
+                                          uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(d_tmem),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tc_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                     smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, int (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]),
+          "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]),
+          "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// ---------------------------------------------------------------------------------------
+// error model
+// ---------------------------------------------------------------------------------------
+// score of the reference's Euclidean metric from the f32 chain sum (lib.rs:2244, 2249-2253)
+__device__ __forceinline__ float tc_l2_score(float s) {
+    return __fdiv_rn(1.0f, __fadd_rn(1.0f, __fsqrt_rn(s)));
+}
+constexpr double kTcU = 5.9604644775390625e-08;  // 2^-24
+
+// bounds on the real |x|^2 of a row from its reference-arithmetic magnitude: rmag =
+// fl(sqrt(lane tree)), every term non-negative, so the tree is within (dim/8 + 16) u relative
+// and the sqrt / re-squaring add ~2u; 1e-37 covers products that underflowed.
+__device__ __forceinline__ void tc_row_sq_bounds(const RowMeta &m, uint32_t dim, double &a_lo,
+                                                 double &a_hi) {
+    const double a = (double)m.rmag * (double)m.rmag;
+    const double rel = ((double)(dim / 8u) + 24.0) * kTcU * 1.01;
+    a_lo = a * (1.0 - rel) - 1e-37;
+    a_hi = a * (1.0 + rel) + 1e-37;
+    if (a_lo < 0.0) a_lo = 0.0;
+}
+
+// Rigorous interval of the reference score of (row, query) from the exact integer dot I.
+// wild == the analysis does not apply (non-finite data, possible overflow): always a candidate.
+__device__ __forceinline__ void tc_interval(int metric, int I, const RowMeta &m,
+                                            const TcQueryMeta &qm, uint32_t dim, uint32_t &lb_ord,
+                                            uint32_t &ub_ord) {
+    bool wild = (m.flags & 1u) != 0u || (qm.flags & kTcFlagUnusable) != 0u;
+    const double g = 2.0 * ((double)dim + 16.0) * kTcU;
+    const double ss = (double)qm.s_q * (double)m.scale;
+    const double B = 0.5001 * ((double)qm.q1 + (double)m.x1) + 0.2502 * (double)dim;
+    const double Dt = ss * (double)I;
+    float lb, ub;
+    if (metric == kEuclidean) {
+        // real dot within ss*B of ss*I; real d^2 = |x|^2 + |q|^2 - 2 dot; the f32 chain of
+        // non-negative terms is within (dim + 4) u relative of the real d^2
+        const double E = ss * B * 1.000001 + 1e-37;
+        double a_lo, a_hi;
+        tc_row_sq_bounds(m, dim, a_lo, a_hi);
+        const double gc = ((double)dim + 4.0) * kTcU * 1.01;
+        double lo = a_lo + qm.c_lo - 2.0 * (Dt + E);
+        double hi = a_hi + qm.c_hi - 2.0 * (Dt - E);
+        lo = lo * (1.0 - gc) * (1.0 - 1e-12) - 1e-36;
+        hi = hi * (1.0 + gc) * (1.0 + 1e-12) + 1e-36;
+        if (!(hi < 1e37) || !(a_hi < 1e37) || !(qm.c_hi < 1e37)) wild = true;
+        const float slo = (lo > 0.0) ? __double2float_rd(lo) : 0.0f;
+        const float shi = (hi > 0.0) ? __double2float_ru(hi) : 0.0f;
+        ub = tc_l2_score(slo);
+        lb = tc_l2_score(shi);
+    } else {
+        const double S = 127.51 * (double)m.x1 + B;
+        const double E = (ss * (B + g * S)) * 1.000001 + 1e-37;
+        const float lo = __double2float_rd(Dt - E), hi = __double2float_ru(Dt + E);
+        if (!(ss * S < 1e37) || !(fabs(Dt) + E < 1e37)) wild = true;
+        if (metric == kCosine) {
+            if (qm.qmag == 0.0f || m.rmag == 0.0f) {
+                lb = ub = 0.0f;
+            } else {
+                const float den = __fmul_rn(qm.qmag, m.rmag);
+                lb = __fdiv_rn(lo, den);
+                ub = __fdiv_rn(hi, den);
+                if (!(den > 1.17549435e-38f) || !(den < 3.0e38f)) wild = true;
+            }
+        } else {
+            lb = lo;
+            ub = hi;
+        }
+    }
+    lb_ord = wild ? 0u : score_to_ord(__float_as_uint(lb));
+    ub_ord = wild ? 0xffffffffu : score_to_ord(__float_as_uint(ub));
+}
+
+// Screen coefficients.  The epilogue keeps (row, q) for the rigorous test unless
+//     float(I) + Br  <  alpha_r * w_q + beta_r * u_q + v_q          (all f32, fma)
+// Derivation per metric (ss = s_q s_r, B = cB (Q1 + X1) + cD dim):
+//   L2     ub >= tau  <=>  chain lower bound <= T (T = largest f32 s with score(s) >= tau)
+//          <=>  I + B >= (A_lo + C_lo - T') / (2 ss):  alpha = A_lo/(2 s_r), beta = 1/(2 s_r),
+//          w = 1/s_q, u = (C_lo - T')/s_q
+//   dot    ub >= tau  <=>  ss (I + B') >= tau-:        alpha = 0, beta = 1/s_r, u = tau-/s_q
+//   cosine ub >= tau  <=>  ss (I + B') >= tau- |q||x|: alpha = 0, beta = rmag/s_r,
+//          u = tau- qmag / s_q
+// v = -(query part of B), Br = row part of B.  Every per-query term is moved by 2^-16 of its
+// magnitude (and Br by 2^-20 + the I2F slack) in the direction that keeps MORE, which covers
+// the f32 roundings of the test (each <= 2^-24 of the sum of the term magnitudes) and the
+// 1.000001 factors of the rigorous formulas.  NaN (inf - inf, 0 * inf) compares false: kept.
+constexpr double kTcEpsQ = 1.52587890625e-05;      // 2^-16
+constexpr double kTcEpsR = 9.5367431640625e-07;    // 2^-20
+constexpr double kTcCB = 0.5001 * 1.000002;
+constexpr double kTcCD = 0.2502 * 1.000002;
+
+__device__ __forceinline__ float4 tc_pass_all(uint32_t tau_ord) {
+    return make_float4(0.0f, 0.0f, -INFINITY, __uint_as_float(tau_ord));
+}
+// unusable queries are redone by the exact path: keep nothing for them
+__device__ __forceinline__ float4 tc_pass_none() {
+    return make_float4(0.0f, 0.0f, INFINITY, __uint_as_float(0xffffffffu));
+}
+
+__device__ __forceinline__ float4 tc_make_coef(int metric, uint32_t tau_ord, const TcQueryMeta &qm,
+                                               uint32_t dim) {
+    if ((qm.flags & kTcFlagUnusable) || !(qm.s_q > 0.0f)) return tc_pass_none();
+    if (tau_ord == 0u) return tc_pass_all(tau_ord);
+    const float tau = __uint_as_float(ord_to_score_bits(tau_ord));
+    const double g = 2.0 * ((double)dim + 16.0) * kTcU;
+    const double sq = (double)qm.s_q;
+    double w = 0.0, u, v;
+    if (metric == kEuclidean) {
+        if (!(tau > 0.0f) || !(tc_l2_score(0.0f) >= tau)) return tc_pass_all(tau_ord);
+        // T = largest non-negative f32 s with score(s) >= tau (score is monotone non-increasing)
+        uint32_t lo_b = 0u, hi_b = 0x7f800000u;  // score(+inf) = 0 < tau
+        while (hi_b - lo_b > 1u) {
+            const uint32_t mid = lo_b + ((hi_b - lo_b) >> 1);
+            if (tc_l2_score(__uint_as_float(mid)) >= tau) lo_b = mid;
+            else hi_b = mid;
+        }
+        // keep while the (real) chain lower bound is below the next float above T
+        const double Tn = (double)__uint_as_float(lo_b + 1u);
+        if (!(Tn < 1e37)) return tc_pass_all(tau_ord);
+        const double gc = ((double)dim + 4.0) * kTcU * 1.01;
+        const double Tp = (Tn + 2e-36) / ((1.0 - gc) * (1.0 - 2e-12));
+        w = 1.0 / sq;
+        u = (qm.c_lo - Tp) / sq;
+        v = -(kTcCB * (double)qm.q1 + kTcCD * (double)dim);
+    } else {
+        // hi = RU(Dt + E) >= tau needs Dt + E > pred(tau)
+        double tp = (double)tau;
+        if (metric == kCosine) {
+            // the quotient rounds to >= tau only if hi/den >= tau - ulp; tiny |tau| (incl. 0,
+            // where a negative quotient may round to -0.0 == +0.0) gets an absolute margin
+            if (fabs(tp) < 1e-30) tp = fmin(tp, 0.0) - 1e-30;
+            tp *= (double)qm.qmag;
+        } else {
+            tp = (double)__uint_as_float(ord_to_score_bits(tau_ord - 1u));  // pred(tau)
+            if (!(fabs(tp) < 1e38)) return tc_pass_all(tau_ord);
+            tp -= 1e-37;
+        }
+        u = tp / sq;
+        v = -((1.0 + g) * 1.000002 * (0.5001 * (double)qm.q1 + 0.2502 * (double)dim));
+    }
+    w *= (1.0 - kTcEpsQ);
+    u -= kTcEpsQ * fabs(u);
+    v -= kTcEpsQ * fabs(v);
+    return make_float4(__double2float_rd(w), __double2float_rd(u), __double2float_rd(v),
+                       __uint_as_float(tau_ord));
+}
+
+// per-row screen coefficients (alpha, beta, Br)
+__device__ __forceinline__ void tc_row_coef(int metric, const RowMeta &m, uint32_t dim, float &alpha,
+                                            float &beta, float &br) {
+    const double g = 2.0 * ((double)dim + 16.0) * kTcU;
+    const double sr = (double)m.scale;
+    // tiny scales: the absolute slack terms (<= 4e-36 / (s_q s_r)) would no longer be covered
+    if ((m.flags & 1u) || !(m.scale >= 1e-15f) || !(m.rmag < 3.0e38f)) {
+        alpha = 0.0f;
+        beta = 0.0f;
+        br = INFINITY;  // always re-evaluated rigorously
+        return;
+    }
+    double cb;
+    if (metric == kEuclidean) {
+        double a_lo, a_hi;
+        tc_row_sq_bounds(m, dim, a_lo, a_hi);
+        alpha = __double2float_rd(a_lo / (2.0 * sr) * (1.0 - kTcEpsR));
+        beta = (float)(1.0 / (2.0 * sr));
+        cb = kTcCB;
+    } else {
+        alpha = 0.0f;
+        beta = (metric == kCosine) ? (float)((double)m.rmag / sr) : (float)(1.0 / sr);
+        cb = 1.000002 * (0.5001 * (1.0 + g) + 127.51 * g);
+    }
+    br = __double2float_ru(cb * (double)m.x1 * (1.0 + kTcEpsR) +
+                           kTcEpsR * (16129.0 * (double)dim + 1.0));
+}
+
+// ---------------------------------------------------------------------------------------
+// prepare: one CTA (256 threads) per query slot; slots >= nq are zero rows of the B operand
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+tc_prepare_queries_kernel(const float *__restrict__ queries, uint32_t nq, uint32_t dim,
+                          uint32_t pitch8, int8_t *q8, TcQueryMeta *qmeta, float4 *coef,
+                          uint32_t *kept_n) {
+    __shared__ float red_f[8];
+    __shared__ uint32_t red_u[8];
+    __shared__ double red_d[8];
+    __shared__ float qmag_s;
+    const uint32_t q = blockIdx.x, t = threadIdx.x, lane = t & 31u, warp = t >> 5;
+    uint32_t *out = reinterpret_cast<uint32_t *>(q8 + (size_t)q * pitch8);
+    if (q >= nq) {
+        for (uint32_t w = t; w * 4u < pitch8; w += 256u) out[w] = 0u;
+        return;
+    }
+    const float *v = queries + (size_t)q * dim;
+    float mx = 0.0f;
+    bool bad = false;
+    double c = 0.0;
+    for (uint32_t i = t; i < dim; i += 256u) {
+        const float x = __ldg(v + i);
+        bad |= !(fabsf(x) <= 3.4028234e38f);
+        mx = fmaxf(mx, fabsf(x));
+        c += (double)x * (double)x;
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        bad |= __shfl_xor_sync(0xffffffffu, (int)bad, o) != 0;
+        c += __shfl_xor_sync(0xffffffffu, c, o);
+    }
+    if (lane == 0) {
+        red_f[warp] = mx;
+        red_u[warp] = bad ? 1u : 0u;
+        red_d[warp] = c;
+    }
+    __syncthreads();
+    mx = 0.0f;
+    bad = false;
+    c = 0.0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+        mx = fmaxf(mx, red_f[w]);
+        bad |= red_u[w] != 0u;
+        c += red_d[w];
+    }
+    const float s_q = bad ? 0.0f : __fdiv_rn(mx, 127.0f);
+    if (!(s_q >= 1e-15f)) bad = true;  // zero / tiny scale: the exact path decides
+    __syncthreads();
+    uint32_t q1 = 0;
+    for (uint32_t w = t; w * 4u < pitch8; w += 256u) {
+        uint32_t packed = 0;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            const uint32_t i = w * 4u + b;
+            int x = 0;
+            if (i < dim && !bad) {
+                x = __float2int_rn(__fdiv_rn(__ldg(v + i), s_q));
+                x = max(-127, min(127, x));
+            }
+            q1 += (uint32_t)abs(x);
+            packed |= ((uint32_t)(uint8_t)(int8_t)x) << (8 * b);
+        }
+        out[w] = packed;
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) q1 += __shfl_xor_sync(0xffffffffu, q1, o);
+    if (lane == 0) red_u[warp] = q1;
+    // |q| with the reference lane tree (hnsw.rs:198-229), warp 0
+    if (warp == 0) {
+        float acc = 0.0f;
+        const uint32_t chunks = dim / 8u;
+        if (lane < 8u)
+            for (uint32_t cix = 0; cix < chunks; ++cix) {
+                const float x = __ldg(v + cix * 8u + lane);
+                acc = __fadd_rn(acc, __fmul_rn(x, x));
+            }
+        float r = 0.0f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) r = __fadd_rn(r, __shfl_sync(0xffffffffu, acc, j));
+        if (lane == 0) {
+            for (uint32_t i = chunks * 8u; i < dim; ++i) {
+                const float x = __ldg(v + i);
+                r = __fadd_rn(r, __fmul_rn(x, x));
+            }
+            qmag_s = __fsqrt_rn(r);
+        }
+    }
+    __syncthreads();
+    if (t == 0) {
+        q1 = 0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) q1 += red_u[w];
+        TcQueryMeta m;
+        m.c_lo = c * (1.0 - 1e-12) - 1e-40;
+        if (m.c_lo < 0.0) m.c_lo = 0.0;
+        m.c_hi = c * (1.0 + 1e-12) + 1e-40;
+        m.s_q = bad ? 0.0f : s_q;
+        m.qmag = qmag_s;
+        m.q1 = q1;
+        m.flags = bad ? kTcFlagUnusable : 0u;
+        m.tau_ord = 0u;
+        m.pad[0] = m.pad[1] = m.pad[2] = 0u;
+        qmeta[q] = m;
+        coef[q] = bad ? tc_pass_none() : tc_pass_all(0u);
+        kept_n[q] = 0u;
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// GEMM + filter
+// ---------------------------------------------------------------------------------------
+struct TcGemmParams {
+    const RowMeta *meta;        // [rows]
+    const TcQueryMeta *qmeta;   // [nq]
+    const float4 *coef;         // [nq] screen coefficients of this phase
+    TcKept *kept;               // [nq][kTcKeptCap]
+    uint32_t *kept_n;           // [nq]
+    int *dump;                  // debug: [nq][dump_stride] integer dot products (may be null)
+    uint64_t dump_stride;
+    uint32_t row_begin;         // multiple of kTcM
+    uint32_t row_end;           // exclusive, <= rows
+    uint32_t dim;
+    uint32_t nq;
+    uint32_t n_pad;             // nq rounded up to 16 (UMMA N)
+    uint32_t evict_first;
+    uint32_t screen;            // 0: skip the f32 screen (every entry evaluated rigorously; tests)
+    int metric;
+};
+
+// rigorous re-evaluation + append of the entries of one accumulator column that passed the
+// screen.  Warp-uniform call; `pass` is per lane.
+__device__ __noinline__ void tc_keep_column(const TcGemmParams &p, uint32_t q, int I, uint32_t row,
+                                            const RowMeta &m, uint32_t tau_ord, bool pass) {
+    const uint32_t lane = threadIdx.x & 31u;
+    uint32_t lb_ord = 0u, ub_ord = 0u;
+    if (pass) {
+        const TcQueryMeta qm = p.qmeta[q];
+        tc_interval(p.metric, I, m, qm, p.dim, lb_ord, ub_ord);
+        pass = ub_ord >= tau_ord && !(qm.flags & kTcFlagUnusable);
+    }
+    const uint32_t ballot = __ballot_sync(0xffffffffu, pass);
+    if (!ballot) return;
+    const uint32_t leader = __ffs(ballot) - 1;
+    uint32_t base = 0;
+    if (lane == leader) base = atomicAdd(p.kept_n + q, (uint32_t)__popc(ballot));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (pass) {
+        const uint32_t pos = base + __popc(ballot & ((1u << lane) - 1u));
+        if (pos < kTcKeptCap) {
+            TcKept e;
+            e.row = row;
+            e.lb_ord = lb_ord;
+            e.ub_ord = ub_ord;
+            p.kept[(size_t)q * kTcKeptCap + pos] = e;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kTcThreads, 1)
+tc_gemm_filter_kernel(const __grid_constant__ CUtensorMap tmap_a,
+                      const __grid_constant__ CUtensorMap tmap_q,
+                      const __grid_constant__ TcGemmParams p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t *st_a = smem;
+    uint8_t *st_b = smem + kTcStages * kTcABytes;
+    float4 *coef_s = reinterpret_cast<float4 *>(st_b + kTcStages * kTcBBytesMax);
+    uint64_t *full_bar = reinterpret_cast<uint64_t *>(coef_s + kTcMaxQ);
+    uint64_t *empty_bar = full_bar + kTcStages;
+    uint64_t *tfull_bar = empty_bar + kTcStages;   // [2] accumulator ready
+    uint64_t *tempty_bar = tfull_bar + 2;          // [2] accumulator drained
+    uint32_t *tmem_base_s = reinterpret_cast<uint32_t *>(tempty_bar + 2);
+
+    const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31u;
+    const uint32_t n_tiles = (p.row_end - p.row_begin + kTcM - 1) / kTcM;
+    const uint32_t n_kb = (p.dim + kTcKBytes - 1) / kTcKBytes;
+
+    if (tid == 0) {
+        for (uint32_t s = 0; s < kTcStages; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        for (uint32_t a = 0; a < 2; ++a) {
+            mbar_init(&tfull_bar[a], 1);
+            mbar_init(&tempty_bar[a], 4);
+        }
+        fence_mbar_init();
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                         smem_u32(tmem_base_s)),
+                     "r"(kTcTmemCols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    for (uint32_t i = tid; i < kTcMaxQ; i += kTcThreads)
+        coef_s[i] = (i < p.nq) ? p.coef[i] : make_float4(0.0f, 0.0f, INFINITY, 0.0f);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_base_s;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            const uint64_t pol_a = p.evict_first ? policy_evict_first() : policy_evict_normal();
+            const uint64_t pol_q = policy_evict_normal();
+            const uint32_t tx = kTcABytes + p.n_pad * kTcKBytes;
+            uint32_t stage = 0, phase = 0;
+            for (uint32_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+                const int32_t row0 = (int32_t)(p.row_begin + t * kTcM);
+                for (uint32_t kb = 0; kb < n_kb; ++kb) {
+                    mbar_wait_wd(&empty_bar[stage], phase ^ 1u);
+                    mbar_arrive_expect_tx(&full_bar[stage], tx);
+                    tma_load_2d(st_a + stage * kTcABytes, &tmap_a, (int32_t)(kb * kTcKBytes), row0,
+                                &full_bar[stage], pol_a);
+                    tma_load_2d(st_b + stage * kTcBBytesMax, &tmap_q, (int32_t)(kb * kTcKBytes), 0,
+                                &full_bar[stage], pol_q);
+                    if (++stage == kTcStages) {
+                        stage = 0;
+                        phase ^= 1u;
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ===== MMA issuer: one thread =====
+        if (lane == 0) {
+            const uint32_t idesc = tc_idesc_i8(kTcM, p.n_pad);
+            uint32_t stage = 0, phase = 0, it = 0;
+            for (uint32_t t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
+                const uint32_t acc = it & 1u, aph = (it >> 1) & 1u;
+                mbar_wait_wd(&tempty_bar[acc], aph ^ 1u);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * kTcMaxQ;
+                for (uint32_t kb = 0; kb < n_kb; ++kb) {
+                    mbar_wait_wd(&full_bar[stage], phase);
+                    tc_fence_after();
+                    const uint64_t adesc = tc_smem_desc(smem_u32(st_a + stage * kTcABytes));
+                    const uint64_t bdesc = tc_smem_desc(smem_u32(st_b + stage * kTcBBytesMax));
+#pragma unroll
+                    for (uint32_t ks = 0; ks < kTcKBytes / 32u; ++ks)  // UMMA K = 32 int8 = 32 B
+                        tc_mma_i8(d_tmem, adesc + 2ull * ks, bdesc + 2ull * ks, idesc,
+                                  (kb | ks) != 0u ? 1u : 0u);
+                    tc_commit(&empty_bar[stage]);  // frees the stage once these MMAs retire
+                    if (++stage == kTcStages) {
+                        stage = 0;
+                        phase ^= 1u;
+                    }
+                }
+                tc_commit(&tfull_bar[acc]);
+            }
+        }
+        __syncwarp();
+    } else {
+        // ===== epilogue: warp w owns TMEM lanes 32 (w % 4) .. +31 =====
+        const uint32_t qd = warp & 3u;
+        uint32_t it = 0;
+        for (uint32_t t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
+            const uint32_t acc = it & 1u, aph = (it >> 1) & 1u;
+            const uint32_t row = p.row_begin + t * kTcM + qd * 32u + lane;
+            const bool valid = row < p.row_end;
+            RowMeta m;
+            m.scale = 0.0f;
+            m.x1 = 0u;
+            m.rmag = 0.0f;
+            m.flags = 0u;
+            if (valid) {
+                const float4 raw = __ldg(reinterpret_cast<const float4 *>(p.meta + row));
+                m.scale = raw.x;
+                m.x1 = __float_as_uint(raw.y);
+                m.rmag = raw.z;
+                m.flags = __float_as_uint(raw.w);
+            }
+            float alpha, beta, br;
+            tc_row_coef(p.metric, m, p.dim, alpha, beta, br);
+            if (!p.screen) br = INFINITY;
+            mbar_wait_wd(&tfull_bar[acc], aph);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((qd * 32u) << 16) + acc * kTcMaxQ;
+            for (uint32_t c0 = 0; c0 < p.n_pad; c0 += 16u) {
+                int v[16];
+                tc_ld16(taddr + c0, v);
+#pragma unroll
+                for (uint32_t j = 0; j < 16u; ++j) {
+                    const uint32_t q = c0 + j;
+                    if (q < p.nq) {  // warp-uniform
+                        if (p.dump && valid) p.dump[(size_t)q * p.dump_stride + row] = v[j];
+                        const float4 cq = coef_s[q];
+                        const float lhs = __int2float_rn(v[j]) + br;
+                        const float rhs = fmaf(alpha, cq.x, fmaf(beta, cq.y, cq.z));
+                        const bool pass = valid && !(lhs < rhs);
+                        if (__any_sync(0xffffffffu, pass))
+                            tc_keep_column(p, q, v[j], row, m, __float_as_uint(cq.w), pass);
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                     "r"(kTcTmemCols)
+                     : "memory");
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// refine: per query, new tau = k-th best lower bound of the kept list; compact to ub >= tau
+// ---------------------------------------------------------------------------------------
+struct TcRefineParams {
+    TcKept *kept;
+    uint32_t *kept_n;
+    TcQueryMeta *qmeta;
+    float4 *coef;
+    uint32_t dim;
+    uint32_t k;
+    int metric;
+};
+
+__global__ void __launch_bounds__(256) tc_refine_kernel(const TcRefineParams p) {
+    __shared__ uint32_t hist[256];
+    __shared__ uint32_t sel_s[2];   // [0] prefix [1] need
+    __shared__ uint32_t warp_cnt[8];
+    __shared__ uint32_t out_pos_s;
+    const uint32_t q = blockIdx.x, t = threadIdx.x, lane = t & 31u, warp = t >> 5;
+    TcKept *list = p.kept + (size_t)q * kTcKeptCap;
+    const uint32_t n_raw = p.kept_n[q];
+    const uint32_t n = min(n_raw, kTcKeptCap);
+    uint32_t tau = p.qmeta[q].tau_ord;
+    if (n >= p.k) {
+        // MSB-first radix select of the k-th largest lb_ord
+        if (t == 0) {
+            sel_s[0] = 0u;
+            sel_s[1] = p.k;
+        }
+        for (int shift = 24; shift >= 0; shift -= 8) {
+            hist[t] = 0u;
+            __syncthreads();
+            const uint32_t prefix = sel_s[0];
+            for (uint32_t i = t; i < n; i += 256u) {
+                const uint32_t o = list[i].lb_ord;
+                if (shift == 24 || (o >> (shift + 8)) == prefix) atomicAdd(&hist[(o >> shift) & 255u], 1u);
+            }
+            __syncthreads();
+            if (t == 0) {
+                uint32_t need = sel_s[1], cum = 0;
+                int b = 255;
+                for (; b > 0; --b) {
+                    if (cum + hist[b] >= need) break;
+                    cum += hist[b];
+                }
+                sel_s[0] = (prefix << 8) | (uint32_t)b;
+                sel_s[1] = need - cum;
+            }
+            __syncthreads();
+        }
+        tau = max(tau, sel_s[0]);
+    }
+    // in-place stable compaction (writes never pass the chunk being read)
+    if (t == 0) out_pos_s = 0u;
+    __syncthreads();
+    for (uint32_t base = 0; base < n; base += 256u) {
+        const uint32_t i = base + t;
+        TcKept e;
+        e.row = e.lb_ord = e.ub_ord = 0u;
+        if (i < n) e = list[i];
+        const bool keep = i < n && e.ub_ord >= tau;
+        const uint32_t ballot = __ballot_sync(0xffffffffu, keep);
+        if (lane == 0) warp_cnt[warp] = __popc(ballot);
+        __syncthreads();
+        uint32_t off = out_pos_s;
+        for (uint32_t w = 0; w < warp; ++w) off += warp_cnt[w];
+        if (keep) list[off + __popc(ballot & ((1u << lane) - 1u))] = e;
+        __syncthreads();
+        if (t == 0) {
+            uint32_t tot = 0;
+            for (uint32_t w = 0; w < 8; ++w) tot += warp_cnt[w];
+            out_pos_s += tot;
+        }
+        __syncthreads();
+    }
+    if (t == 0) {
+        p.kept_n[q] = out_pos_s;
+        TcQueryMeta qm = p.qmeta[q];
+        if (n_raw > kTcKeptCap) qm.flags |= kTcFlagOverflow;
+        qm.tau_ord = tau;
+        p.qmeta[q] = qm;
+        p.coef[q] = tc_make_coef(p.metric, tau, qm, p.dim);
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// exact re-score of the survivors + final selection: one CTA per query
+// ---------------------------------------------------------------------------------------
+struct TcRescoreParams {
+    const float *queries;     // [nq][dim]
+    const float *rows;        // f32 mirror
+    const TcKept *kept;
+    const uint32_t *kept_n;
+    const TcQueryMeta *qmeta;
+    uint64_t *exact_keys;     // [nq][kTcKeptCap]
+    uint64_t *out_rows;       // [nq][out_stride]
+    float *out_scores;
+    uint32_t *out_counts;
+    uint32_t *stats;          // [0] total survivors re-scored (atomic)
+    uint64_t row_base;
+    uint32_t pitch;
+    uint32_t dim;
+    uint32_t k;
+    uint32_t out_stride;
+    int metric;
+};
+
+__global__ void __launch_bounds__(kRowsPerBlock) tc_rescore_kernel(const TcRescoreParams p) {
+    extern __shared__ __align__(16) float q_s[];  // [dim]
+    __shared__ __align__(16) uint64_t buf[kCandCap];
+    __shared__ uint64_t thr_s;
+    __shared__ uint32_t cnt_s;
+    __shared__ uint32_t hist[256 + 16];
+    const uint32_t q = blockIdx.x, t = threadIdx.x;
+    const float *qv = p.queries + (size_t)q * p.dim;
+    for (uint32_t i = t; i < p.dim; i += kRowsPerBlock) q_s[i] = __ldg(qv + i);
+    if (t == 0) {
+        thr_s = 0ull;
+        cnt_s = 0u;
+    }
+    __syncthreads();
+    const uint32_t n = min(p.kept_n[q], kTcKeptCap);
+    const float qmag = p.qmeta[q].qmag;
+    const TcKept *list = p.kept + (size_t)q * kTcKeptCap;
+    uint64_t *keys = p.exact_keys + (size_t)q * kTcKeptCap;
+    for (uint32_t i = t; i < n; i += kRowsPerBlock) {
+        const uint32_t row = list[i].row;
+        const float s = exact_score_row(q_s, p.rows + (size_t)row * p.pitch, p.dim, qmag, p.metric);
+        keys[i] = make_key(__float_as_uint(s), row);
+    }
+    __threadfence();
+    __syncthreads();
+    if (t == 0 && p.stats) atomicAdd(p.stats, n);
+    TopKState st;
+    st.buf = buf;
+    st.cnt_smem = &cnt_s;
+    st.thr_smem = &thr_s;
+    st.count = 0;
+    st.k = p.k;
+    st.cap = kCandCap;
+    MergeScratch ms;
+    ms.hist = hist;
+    ms.sc = hist + 256;
+    merge_published(st, t, keys, n, p.k, ms);
+    TopKOutputs o;
+    o.out_keys = nullptr;
+    o.out_hits = nullptr;
+    o.out_rows = p.out_rows + (size_t)q * p.out_stride;
+    o.out_scores = p.out_scores + (size_t)q * p.out_stride;
+    o.out_count = p.out_counts + q;
+    o.row_base = p.row_base;
+    o.accumulate_count = 0;
+    write_outputs(st, t, p.k, o);
+}
+
+#endif  // __CUDACC__
+}  // namespace nm

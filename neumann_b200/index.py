@@ -136,6 +136,24 @@ class DeviceIndex:
         """0 = off (default), 1 = exact int8 pre-filter (see include/neumann_b200.h)."""
         check(_ffi.lib().nm_index_set_prefilter(self._h, int(mode)))
 
+    def set_tensor_core(self, enable: bool) -> None:
+        """Batches on a pre-filtered index: tcgen05 int8 GEMM pre-filter (default on) or not."""
+        check(_ffi.lib().nm_index_set_tensor_core(self._h, 1 if enable else 0))
+
+    def debug_tc_dots(self, queries: np.ndarray) -> np.ndarray:
+        """Exact integer dot products of the tensor-core pass: int32 [nq, rows]."""
+        q = np.ascontiguousarray(queries, dtype=np.float32).reshape(-1, self.dim)
+        out = np.zeros((min(q.shape[0], 256), self.rows), np.int32)
+        check(_ffi.lib().nm_debug_tc_dots(self._h, q.ctypes.data, q.shape[0], out.ctypes.data))
+        return out
+
+    def debug_q8_row(self, row: int):
+        """(int8[dim], scale) of one row of the int8 copy."""
+        out = np.zeros(self.dim, np.int8)
+        scale = C.c_float()
+        check(_ffi.lib().nm_debug_q8_row(self._h, row, out.ctypes.data, C.byref(scale)))
+        return out, float(scale.value)
+
     def set_coalescing(self, max_batch: int) -> None:
         check(_ffi.lib().nm_index_set_coalescing(self._h, int(max_batch)))
 
