@@ -295,7 +295,8 @@ bool tc_usable(const nm_index *idx, const Shard &sh, uint32_t nq, uint32_t k, in
 int scan_queries_tc(nm_index *idx, const Shard &sh, Workspace &ws, const float *d_queries,
                     uint32_t nq, uint32_t k, int metric, uint64_t *out_rows, float *out_scores,
                     uint32_t *out_counts, cudaStream_t stream, int *debug_dots = nullptr);
-uint32_t tc_query_flags(const Workspace &ws, uint32_t q);
+uint32_t tc_query_flags(const Workspace &ws, uint32_t q, uint32_t rows);
+uint32_t tc_phases(const Workspace &ws);
 uint32_t tc_survivors(const Workspace &ws);
 int launch_merge_shards(nm_index *idx, const nm::ShardHit *d_gather, uint32_t nq, uint32_t k,
                         uint64_t *out_rows, float *out_scores, uint32_t *out_counts,

@@ -452,6 +452,24 @@ bool tc_usable(const nm_index *idx, const Shard &sh, uint32_t nq, uint32_t k, in
     return true;
 }
 
+// auxiliary words of the tensor-core path: [cap kept_n][cap kept_prev][4 stats][passes x TcCtl]
+struct TcAux {
+    uint32_t *kept_n, *kept_prev, *stats;
+    nm::TcCtl *ctl;
+    size_t tail_off, tail_bytes;  // stats + ctl: copied back with the results
+};
+static TcAux tc_aux(const Workspace &ws) {
+    TcAux a;
+    const size_t cap = ws.tc_nq_cap;
+    a.kept_n = ws.d_tc_kept_n;
+    a.kept_prev = ws.d_tc_kept_n + cap;
+    a.stats = ws.d_tc_kept_n + 2 * cap;
+    a.ctl = reinterpret_cast<nm::TcCtl *>(ws.d_tc_kept_n + 2 * cap + 8);
+    a.tail_off = (2 * cap) * sizeof(uint32_t);
+    a.tail_bytes = 8 * sizeof(uint32_t) + (cap / nm::kTcMaxQ + 1) * sizeof(nm::TcCtl);
+    return a;
+}
+
 static int ws_ensure_tc(Workspace &ws, uint32_t dim, uint32_t nq, cudaStream_t stream) {
     const size_t q8_bytes = (size_t)nm::kTcMaxQ * q8_pitch(dim);
     if (ws.tc_q8_cap < q8_bytes || ws.tc_nq_cap < nq) CUDA_TRY(cudaStreamSynchronize(stream));
@@ -462,7 +480,7 @@ static int ws_ensure_tc(Workspace &ws, uint32_t dim, uint32_t nq, cudaStream_t s
         ws.tc_q8_cap = q8_bytes;
     }
     if (ws.tc_nq_cap < nq) {
-        const size_t cap = std::max<size_t>(nq, nm::kTcMaxQ);
+        const size_t cap = (std::max<size_t>(nq, nm::kTcMaxQ) + nm::kTcMaxQ - 1) / nm::kTcMaxQ * nm::kTcMaxQ;
         if (ws.d_tc_qmeta) CUDA_TRY(cudaFree(ws.d_tc_qmeta));
         if (ws.h_tc_qmeta) CUDA_TRY(cudaFreeHost(ws.h_tc_qmeta));
         if (ws.d_tc_coef) CUDA_TRY(cudaFree(ws.d_tc_coef));
@@ -470,10 +488,11 @@ static int ws_ensure_tc(Workspace &ws, uint32_t dim, uint32_t nq, cudaStream_t s
         ws.tc_nq_cap = 0;
         ws.d_tc_qmeta = ws.h_tc_qmeta = ws.d_tc_coef = nullptr;
         ws.d_tc_kept_n = nullptr;
+        const size_t tail = 8 * sizeof(uint32_t) + (cap / nm::kTcMaxQ + 1) * sizeof(nm::TcCtl);
         CUDA_TRY(cudaMalloc(&ws.d_tc_qmeta, cap * sizeof(nm::TcQueryMeta)));
-        CUDA_TRY(cudaMallocHost(&ws.h_tc_qmeta, cap * sizeof(nm::TcQueryMeta) + 16));
+        CUDA_TRY(cudaMallocHost(&ws.h_tc_qmeta, cap * sizeof(nm::TcQueryMeta) + tail));
         CUDA_TRY(cudaMalloc(&ws.d_tc_coef, cap * sizeof(float4)));
-        CUDA_TRY(cudaMalloc(&ws.d_tc_kept_n, (cap + 4) * sizeof(uint32_t)));
+        CUDA_TRY(cudaMalloc(&ws.d_tc_kept_n, 2 * cap * sizeof(uint32_t) + tail));
         ws.tc_nq_cap = cap;
     }
     if (!ws.d_tc_kept) {
@@ -483,8 +502,11 @@ static int ws_ensure_tc(Workspace &ws, uint32_t dim, uint32_t nq, cudaStream_t s
     return NM_OK;
 }
 
-// Phases: rows [0, 16Ki) keep everything, then ranges growing by `factor` (expected kept entries
-// per query and phase ~ k (factor - 1) on unordered data), a refine step after each.
+// One pass per 256 queries: prepare, then kTcMaxPhases (gemm, refine) pairs whose row ranges
+// are chosen ON DEVICE (first 16 Ki rows keep everything; each refine sizes the next range
+// from the pass rate it saw; pairs past the end exit at once), then the exact re-score.
+constexpr uint32_t kTcMaxPhases = 12;
+
 int scan_queries_tc(nm_index *idx, const Shard &sh, Workspace &ws, const float *d_queries,
                     uint32_t nq, uint32_t k, int metric, uint64_t *out_rows, float *out_scores,
                     uint32_t *out_counts, cudaStream_t stream, int *debug_dots) {
@@ -512,18 +534,20 @@ int scan_queries_tc(nm_index *idx, const Shard &sh, Workspace &ws, const float *
     auto *qmeta = static_cast<nm::TcQueryMeta *>(ws.d_tc_qmeta);
     auto *coef = static_cast<float4 *>(ws.d_tc_coef);
     auto *kept = static_cast<nm::TcKept *>(ws.d_tc_kept);
-    uint32_t *stats = ws.d_tc_kept_n + ws.tc_nq_cap;
-    CUDA_TRY(cudaMemsetAsync(stats, 0, 4 * sizeof(uint32_t), stream));
-    const uint32_t factor =
-        std::max<uint32_t>(2u, std::min<uint32_t>(16u, nm::kTcKeptCap / (4u * k_eff)));
+    const TcAux aux = tc_aux(ws);
+    CUDA_TRY(cudaMemsetAsync(aux.stats, 0, 8 * sizeof(uint32_t), stream));
     const int kmetric = metric == NM_COSINE ? nm::kCosine
                                             : (metric == NM_EUCLIDEAN ? nm::kEuclidean : nm::kDot);
-    for (uint32_t q0 = 0; q0 < nq; q0 += nm::kTcMaxQ) {
+    const uint32_t max_tiles = (rows + nm::kTcM - 1) / nm::kTcM;
+    const uint32_t grid = std::min<uint32_t>((uint32_t)sh.sm_count, max_tiles);
+    uint32_t pass = 0;
+    for (uint32_t q0 = 0; q0 < nq; q0 += nm::kTcMaxQ, ++pass) {
         const uint32_t nqp = std::min<uint32_t>(nm::kTcMaxQ, nq - q0);
         const uint32_t n_pad = (nqp + 15u) & ~15u;
+        nm::TcCtl *ctl = aux.ctl + pass;
         nm::tc_prepare_queries_kernel<<<n_pad, 256, 0, stream>>>(
             d_queries + (size_t)q0 * dim, nqp, dim, pitch8, ws.d_tc_q8, qmeta + q0, coef + q0,
-            ws.d_tc_kept_n + q0);
+            aux.kept_n + q0, aux.kept_prev + q0, ctl, rows);
         CUDA_TRY(cudaGetLastError());
         CUtensorMap tmap_q;
         rc = encode_tmap_u8(&tmap_q, ws.d_tc_q8, dim, n_pad, pitch8, 128, n_pad);
@@ -534,51 +558,50 @@ int scan_queries_tc(nm_index *idx, const Shard &sh, Workspace &ws, const float *
         gp.qmeta = qmeta + q0;
         gp.coef = coef + q0;
         gp.kept = kept;
-        gp.kept_n = ws.d_tc_kept_n + q0;
+        gp.kept_n = aux.kept_n + q0;
         gp.dump = debug_dots ? debug_dots + (size_t)q0 * rows : nullptr;
         gp.dump_stride = rows;
+        gp.ctl = ctl;
+        gp.n_rows = rows;
         gp.dim = dim;
         gp.nq = nqp;
         gp.n_pad = n_pad;
         gp.evict_first = ((uint64_t)rows * pitch8 > (64ull << 20)) ? 1u : 0u;
         gp.screen = screen ? 1u : 0u;
+        gp.shift = 0;
+        while (((16129ull * dim) >> gp.shift) >= (1ull << 22) - 8) ++gp.shift;
         gp.metric = kmetric;
         nm::TcRefineParams rp;
         memset(&rp, 0, sizeof(rp));
         rp.kept = kept;
-        rp.kept_n = ws.d_tc_kept_n + q0;
+        rp.kept_n = aux.kept_n + q0;
+        rp.kept_prev = aux.kept_prev + q0;
         rp.qmeta = qmeta + q0;
         rp.coef = coef + q0;
+        rp.ctl = ctl;
+        rp.n_rows = rows;
         rp.dim = dim;
         rp.k = k_eff;
         rp.metric = kmetric;
-        uint64_t begin = 0, end = std::min<uint64_t>(rows, nm::kTcKeptCap);
-        while (begin < rows) {
-            gp.row_begin = (uint32_t)begin;
-            gp.row_end = (uint32_t)end;
-            const uint32_t n_tiles = (uint32_t)((end - begin + nm::kTcM - 1) / nm::kTcM);
-            const uint32_t grid = std::min<uint32_t>((uint32_t)sh.sm_count, n_tiles);
+        for (uint32_t ph = 0; ph < kTcMaxPhases; ++ph) {
             nm::tc_gemm_filter_kernel<<<grid, nm::kTcThreads, nm::tc_gemm_smem_bytes(), stream>>>(
                 sh.tmap8_tc, tmap_q, gp);
             CUDA_TRY(cudaGetLastError());
             nm::tc_refine_kernel<<<nqp, 256, 0, stream>>>(rp);
             CUDA_TRY(cudaGetLastError());
-            idx->scan_launches += 2;
-            begin = end;
-            end = std::min<uint64_t>(rows, end * factor);
         }
         nm::TcRescoreParams sp;
         memset(&sp, 0, sizeof(sp));
         sp.queries = d_queries + (size_t)q0 * dim;
         sp.rows = sh.d_rows;
         sp.kept = kept;
-        sp.kept_n = ws.d_tc_kept_n + q0;
+        sp.kept_n = aux.kept_n + q0;
         sp.qmeta = qmeta + q0;
         sp.exact_keys = ws.d_tc_keys;
         sp.out_rows = out_rows + (size_t)q0 * k;
         sp.out_scores = out_scores + (size_t)q0 * k;
         sp.out_counts = out_counts + q0;
-        sp.stats = stats;
+        sp.stats = aux.stats;
         sp.row_base = sh.row_base;
         sp.pitch = idx->pitch;
         sp.dim = dim;
@@ -587,24 +610,36 @@ int scan_queries_tc(nm_index *idx, const Shard &sh, Workspace &ws, const float *
         sp.metric = kmetric;
         nm::tc_rescore_kernel<<<nqp, nm::kRowsPerBlock, (size_t)dim * 4, stream>>>(sp);
         CUDA_TRY(cudaGetLastError());
-        idx->scan_launches += 2;
+        idx->scan_launches += 2 + 2 * kTcMaxPhases;
     }
-    // flags + statistics come back with the results
+    // flags, phase control and statistics come back with the results
     CUDA_TRY(cudaMemcpyAsync(ws.h_tc_qmeta, ws.d_tc_qmeta, (size_t)nq * sizeof(nm::TcQueryMeta),
                              cudaMemcpyDeviceToHost, stream));
     CUDA_TRY(cudaMemcpyAsync(static_cast<uint8_t *>(ws.h_tc_qmeta) +
                                  ws.tc_nq_cap * sizeof(nm::TcQueryMeta),
-                             stats, 16, cudaMemcpyDeviceToHost, stream));
+                             reinterpret_cast<const uint8_t *>(ws.d_tc_kept_n) + aux.tail_off,
+                             aux.tail_bytes, cudaMemcpyDeviceToHost, stream));
     return NM_OK;
 }
 
 // after the stream has been waited for: which queries must be redone exactly
-uint32_t tc_query_flags(const Workspace &ws, uint32_t q) {
-    return static_cast<const nm::TcQueryMeta *>(ws.h_tc_qmeta)[q].flags;
+// (a pass whose phases did not reach the end of the corpus flags all of its queries)
+uint32_t tc_query_flags(const Workspace &ws, uint32_t q, uint32_t rows) {
+    const uint8_t *tail = static_cast<const uint8_t *>(ws.h_tc_qmeta) +
+                          ws.tc_nq_cap * sizeof(nm::TcQueryMeta);
+    const nm::TcCtl *ctl = reinterpret_cast<const nm::TcCtl *>(tail + 8 * sizeof(uint32_t));
+    uint32_t f = static_cast<const nm::TcQueryMeta *>(ws.h_tc_qmeta)[q].flags;
+    if (ctl[q / nm::kTcMaxQ].row_begin < rows) f |= 4u;
+    return f;
 }
 uint32_t tc_survivors(const Workspace &ws) {
     return *reinterpret_cast<const uint32_t *>(static_cast<const uint8_t *>(ws.h_tc_qmeta) +
                                                ws.tc_nq_cap * sizeof(nm::TcQueryMeta));
+}
+uint32_t tc_phases(const Workspace &ws) {
+    const uint8_t *tail = static_cast<const uint8_t *>(ws.h_tc_qmeta) +
+                          ws.tc_nq_cap * sizeof(nm::TcQueryMeta);
+    return reinterpret_cast<const nm::TcCtl *>(tail + 8 * sizeof(uint32_t))[0].phases;
 }
 
 // nq queries over one shard: batched kernels when that pays, else one (chained) scan per query.

@@ -199,7 +199,7 @@ static int search_impl(nm_index *idx, const float *queries, uint32_t nq, uint32_
             idx->tc_survivors += tc_survivors(*ws);
             bool redo = false;
             for (uint32_t q = 0; q < nq; ++q) {
-                if (tc_query_flags(*ws, q) == 0) continue;
+                if (tc_query_flags(*ws, q, (uint32_t)sh.rows) == 0) continue;
                 idx->tc_fallbacks++;
                 redo = true;
                 rc = launch_scan(idx, sh, *ws, ws->d_query + (size_t)q * dim, k, metric, sh.row_base,

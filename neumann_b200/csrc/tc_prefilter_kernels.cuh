@@ -50,8 +50,10 @@ constexpr uint32_t kTcMaxQ = 256;                          // queries per pass =
 constexpr uint32_t kTcStages = 4;
 constexpr uint32_t kTcABytes = kTcM * kTcKBytes;           // 16 KiB
 constexpr uint32_t kTcBBytesMax = kTcMaxQ * kTcKBytes;     // 32 KiB
-constexpr uint32_t kTcThreads = 192;
-constexpr uint32_t kTcKeptCap = 16384;                     // kept entries per query
+constexpr uint32_t kTcEpilogueWarps = 8;                   // 2 per TMEM lane quarter
+constexpr uint32_t kTcThreads = 64 + 32 * kTcEpilogueWarps;  // + TMA warp + MMA warp
+constexpr uint32_t kTcKeptCap = 32768;                     // kept entries per query
+constexpr uint32_t kTcPhase0Rows = 4096;                   // first phase: keep everything
 constexpr uint32_t kTcTmemCols = 512;                      // 2 accumulators x 256 columns
 
 constexpr uint32_t kTcFlagUnusable = 1u;   // query not finite / zero / denormal scale
@@ -70,6 +72,18 @@ struct alignas(16) TcQueryMeta {
     uint32_t q1;         // sum |qt_i|
     uint32_t flags;      // kTcFlag*
     uint32_t tau_ord;    // k-th best lower bound so far (0 = none yet)
+    uint32_t pad[3];
+};
+
+// Phase control of one pass, device resident: the refine kernel sizes the next row range from
+// the pass rate it just observed, so the host enqueues a fixed number of (gemm, refine) pairs
+// without reading anything back; pairs past the end of the corpus exit at once.
+struct TcCtl {
+    uint32_t row_begin;   // current phase [row_begin, row_end)
+    uint32_t row_end;
+    uint32_t next_rows;   // atomicMin over queries: rows the next phase may cover
+    uint32_t ticket;
+    uint32_t phases;      // phases completed (statistics)
     uint32_t pad[3];
 };
 
@@ -137,7 +151,9 @@ __device__ __forceinline__ void tc_commit(uint64_t *bar) {
                      smem_u32(bar))
                  : "memory");
 }
-__device__ __forceinline__ void tc_ld16(uint32_t taddr, int (&v)[16]) {
+// TMEM -> registers: 16 consecutive columns of this thread's lane.  The load is asynchronous;
+// tc_ld_wait ties the registers to the wait so no consumer can be scheduled before it.
+__device__ __forceinline__ void tc_ld16_issue(uint32_t taddr, int (&v)[16]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
         "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
@@ -146,7 +162,14 @@ __device__ __forceinline__ void tc_ld16(uint32_t taddr, int (&v)[16]) {
           "=r"(v[14]), "=r"(v[15])
         : "r"(taddr)
         : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tc_ld_wait(int (&v)[16]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]),
+                   "+r"(v[6]), "+r"(v[7]), "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]),
+                   "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15])
+                 :
+                 : "memory");
 }
 
 // ---------------------------------------------------------------------------------------
@@ -328,13 +351,23 @@ __device__ __forceinline__ void tc_row_coef(int metric, const RowMeta &m, uint32
 __global__ void __launch_bounds__(256)
 tc_prepare_queries_kernel(const float *__restrict__ queries, uint32_t nq, uint32_t dim,
                           uint32_t pitch8, int8_t *q8, TcQueryMeta *qmeta, float4 *coef,
-                          uint32_t *kept_n) {
+                          uint32_t *kept_n, uint32_t *kept_prev, TcCtl *ctl, uint32_t n_rows) {
     __shared__ float red_f[8];
     __shared__ uint32_t red_u[8];
     __shared__ double red_d[8];
     __shared__ float qmag_s;
     const uint32_t q = blockIdx.x, t = threadIdx.x, lane = t & 31u, warp = t >> 5;
     uint32_t *out = reinterpret_cast<uint32_t *>(q8 + (size_t)q * pitch8);
+    if (q == 0 && t == 0) {
+        TcCtl c;
+        c.row_begin = 0u;
+        c.row_end = min(n_rows, kTcPhase0Rows);
+        c.next_rows = 0xffffffffu;
+        c.ticket = 0u;
+        c.phases = 0u;
+        c.pad[0] = c.pad[1] = c.pad[2] = 0u;
+        *ctl = c;
+    }
     if (q >= nq) {
         for (uint32_t w = t; w * 4u < pitch8; w += 256u) out[w] = 0u;
         return;
@@ -430,6 +463,7 @@ tc_prepare_queries_kernel(const float *__restrict__ queries, uint32_t nq, uint32
         qmeta[q] = m;
         coef[q] = bad ? tc_pass_none() : tc_pass_all(0u);
         kept_n[q] = 0u;
+        kept_prev[q] = 0u;
     }
 }
 
@@ -444,13 +478,14 @@ struct TcGemmParams {
     uint32_t *kept_n;           // [nq]
     int *dump;                  // debug: [nq][dump_stride] integer dot products (may be null)
     uint64_t dump_stride;
-    uint32_t row_begin;         // multiple of kTcM
-    uint32_t row_end;           // exclusive, <= rows
+    const TcCtl *ctl;           // row range of this phase
+    uint32_t n_rows;
     uint32_t dim;
     uint32_t nq;
     uint32_t n_pad;             // nq rounded up to 16 (UMMA N)
     uint32_t evict_first;
     uint32_t screen;            // 0: skip the f32 screen (every entry evaluated rigorously; tests)
+    uint32_t shift;             // the screen works on I >> shift (|I >> shift| < 2^22)
     int metric;
 };
 
@@ -499,7 +534,9 @@ tc_gemm_filter_kernel(const __grid_constant__ CUtensorMap tmap_a,
     uint32_t *tmem_base_s = reinterpret_cast<uint32_t *>(tempty_bar + 2);
 
     const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31u;
-    const uint32_t n_tiles = (p.row_end - p.row_begin + kTcM - 1) / kTcM;
+    const uint32_t row_begin = p.ctl->row_begin, row_end = min(p.ctl->row_end, p.n_rows);
+    if (row_begin >= row_end) return;  // past the end of the corpus: nothing to do (uniform)
+    const uint32_t n_tiles = (row_end - row_begin + kTcM - 1) / kTcM;
     const uint32_t n_kb = (p.dim + kTcKBytes - 1) / kTcKBytes;
 
     if (tid == 0) {
@@ -509,7 +546,7 @@ tc_gemm_filter_kernel(const __grid_constant__ CUtensorMap tmap_a,
         }
         for (uint32_t a = 0; a < 2; ++a) {
             mbar_init(&tfull_bar[a], 1);
-            mbar_init(&tempty_bar[a], 4);
+            mbar_init(&tempty_bar[a], kTcEpilogueWarps);
         }
         fence_mbar_init();
     }
@@ -520,8 +557,20 @@ tc_gemm_filter_kernel(const __grid_constant__ CUtensorMap tmap_a,
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    for (uint32_t i = tid; i < kTcMaxQ; i += kTcThreads)
-        coef_s[i] = (i < p.nq) ? p.coef[i] : make_float4(0.0f, 0.0f, INFINITY, 0.0f);
+    {
+        // the screen compares in units of 2^shift (exact power-of-two scaling)
+        const float sc = __uint_as_float((127u - p.shift) << 23);
+        for (uint32_t i = tid; i < kTcMaxQ; i += kTcThreads) {
+            float4 c = make_float4(0.0f, 0.0f, INFINITY, 0.0f);
+            if (i < p.nq) {
+                c = p.coef[i];
+                c.x *= sc;
+                c.y *= sc;
+                c.z *= sc;
+            }
+            coef_s[i] = c;
+        }
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -535,7 +584,7 @@ tc_gemm_filter_kernel(const __grid_constant__ CUtensorMap tmap_a,
             const uint32_t tx = kTcABytes + p.n_pad * kTcKBytes;
             uint32_t stage = 0, phase = 0;
             for (uint32_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-                const int32_t row0 = (int32_t)(p.row_begin + t * kTcM);
+                const int32_t row0 = (int32_t)(row_begin + t * kTcM);
                 for (uint32_t kb = 0; kb < n_kb; ++kb) {
                     mbar_wait_wd(&empty_bar[stage], phase ^ 1u);
                     mbar_arrive_expect_tx(&full_bar[stage], tx);
@@ -581,13 +630,19 @@ tc_gemm_filter_kernel(const __grid_constant__ CUtensorMap tmap_a,
         }
         __syncwarp();
     } else {
-        // ===== epilogue: warp w owns TMEM lanes 32 (w % 4) .. +31 =====
+        // ===== epilogue: warp w owns TMEM lanes 32 (w % 4) .. +31; the two warps of a lane
+        //       quarter split the query columns =====
         const uint32_t qd = warp & 3u;
+        const uint32_t half = (warp - 2u) >> 2;
+        const uint32_t n_chunks = p.n_pad / 16u;
+        const uint32_t ch_begin = half ? (n_chunks + 1u) / 2u : 0u;
+        const uint32_t ch_end = half ? n_chunks : (n_chunks + 1u) / 2u;
+        const float sc = __uint_as_float((127u - p.shift) << 23);
         uint32_t it = 0;
         for (uint32_t t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
             const uint32_t acc = it & 1u, aph = (it >> 1) & 1u;
-            const uint32_t row = p.row_begin + t * kTcM + qd * 32u + lane;
-            const bool valid = row < p.row_end;
+            const uint32_t row = row_begin + t * kTcM + qd * 32u + lane;
+            const bool valid = row < row_end;
             RowMeta m;
             m.scale = 0.0f;
             m.x1 = 0u;
@@ -603,23 +658,52 @@ tc_gemm_filter_kernel(const __grid_constant__ CUtensorMap tmap_a,
             float alpha, beta, br;
             tc_row_coef(p.metric, m, p.dim, alpha, beta, br);
             if (!p.screen) br = INFINITY;
+            // lhs = float(I >> shift) + br / 2^shift (+3: the floor of the shift and the two
+            // roundings below), with the int -> float conversion done by the 1.5 * 2^23 trick
+            const float brm = __fadd_ru(__fadd_ru(__fmul_ru(br, sc), 3.0f), -12582912.0f);
             mbar_wait_wd(&tfull_bar[acc], aph);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((qd * 32u) << 16) + acc * kTcMaxQ;
-            for (uint32_t c0 = 0; c0 < p.n_pad; c0 += 16u) {
-                int v[16];
-                tc_ld16(taddr + c0, v);
+            auto process = [&](int (&v)[16], uint32_t c0) {
+                uint32_t mask = 0u;
 #pragma unroll
                 for (uint32_t j = 0; j < 16u; ++j) {
-                    const uint32_t q = c0 + j;
-                    if (q < p.nq) {  // warp-uniform
-                        if (p.dump && valid) p.dump[(size_t)q * p.dump_stride + row] = v[j];
-                        const float4 cq = coef_s[q];
-                        const float lhs = __int2float_rn(v[j]) + br;
-                        const float rhs = fmaf(alpha, cq.x, fmaf(beta, cq.y, cq.z));
-                        const bool pass = valid && !(lhs < rhs);
-                        if (__any_sync(0xffffffffu, pass))
-                            tc_keep_column(p, q, v[j], row, m, __float_as_uint(cq.w), pass);
+                    const float4 cq = coef_s[c0 + j];
+                    const float lhs =
+                        __int_as_float(0x4B400000 + (v[j] >> p.shift)) + brm;
+                    const float rhs = fmaf(alpha, cq.x, fmaf(beta, cq.y, cq.z));
+                    if (!(lhs < rhs)) mask |= 1u << j;
+                }
+                const uint32_t left = p.nq - min(p.nq, c0);
+                mask &= left >= 16u ? 0xffffu : ((1u << left) - 1u);
+                if (!valid) mask = 0u;
+                if (p.dump && valid) {
+#pragma unroll
+                    for (uint32_t j = 0; j < 16u; ++j)
+                        if (c0 + j < p.nq) p.dump[(size_t)(c0 + j) * p.dump_stride + row] = v[j];
+                }
+                const uint32_t any = __reduce_or_sync(0xffffffffu, mask);
+                if (any) {
+#pragma unroll
+                    for (uint32_t j = 0; j < 16u; ++j)
+                        if (any & (1u << j))
+                            tc_keep_column(p, c0 + j, v[j], row, m,
+                                           __float_as_uint(coef_s[c0 + j].w), (mask >> j) & 1u);
+                }
+            };
+            if (ch_begin < ch_end) {
+                int va[16], vb[16];
+                tc_ld16_issue(taddr + ch_begin * 16u, va);
+                tc_ld_wait(va);
+                for (uint32_t ch = ch_begin; ch < ch_end; ch += 2u) {
+                    const bool has_b = ch + 1u < ch_end;
+                    if (has_b) tc_ld16_issue(taddr + (ch + 1u) * 16u, vb);
+                    process(va, ch * 16u);
+                    if (has_b) {
+                        tc_ld_wait(vb);
+                        if (ch + 2u < ch_end) tc_ld16_issue(taddr + (ch + 2u) * 16u, va);
+                        process(vb, (ch + 1u) * 16u);
+                        if (ch + 2u < ch_end) tc_ld_wait(va);
                     }
                 }
             }
@@ -644,8 +728,11 @@ tc_gemm_filter_kernel(const __grid_constant__ CUtensorMap tmap_a,
 struct TcRefineParams {
     TcKept *kept;
     uint32_t *kept_n;
+    uint32_t *kept_prev;   // [nq] list length after the previous refine
     TcQueryMeta *qmeta;
     float4 *coef;
+    TcCtl *ctl;
+    uint32_t n_rows;
     uint32_t dim;
     uint32_t k;
     int metric;
@@ -657,6 +744,8 @@ __global__ void __launch_bounds__(256) tc_refine_kernel(const TcRefineParams p) 
     __shared__ uint32_t warp_cnt[8];
     __shared__ uint32_t out_pos_s;
     const uint32_t q = blockIdx.x, t = threadIdx.x, lane = t & 31u, warp = t >> 5;
+    const uint32_t row_begin = p.ctl->row_begin, row_end = min(p.ctl->row_end, p.n_rows);
+    if (row_begin >= row_end) return;  // no phase ran before this launch
     TcKept *list = p.kept + (size_t)q * kTcKeptCap;
     const uint32_t n_raw = p.kept_n[q];
     const uint32_t n = min(n_raw, kTcKeptCap);
@@ -714,12 +803,41 @@ __global__ void __launch_bounds__(256) tc_refine_kernel(const TcRefineParams p) 
         __syncthreads();
     }
     if (t == 0) {
-        p.kept_n[q] = out_pos_s;
+        const uint32_t m = out_pos_s;
+        p.kept_n[q] = m;
         TcQueryMeta qm = p.qmeta[q];
         if (n_raw > kTcKeptCap) qm.flags |= kTcFlagOverflow;
         qm.tau_ord = tau;
         p.qmeta[q] = qm;
         p.coef[q] = tc_make_coef(p.metric, tau, qm, p.dim);
+        // rows the next phase may cover so that this query's list stays half empty even if the
+        // pass rate does not drop (it does: tau has just tightened)
+        const uint32_t prev = p.kept_prev[q];
+        p.kept_prev[q] = m;
+        if (!(qm.flags & (kTcFlagUnusable | kTcFlagOverflow))) {
+            const uint64_t added = n > prev ? n - prev : 1u;
+            const uint64_t room = (kTcKeptCap - m) / 2u;
+            const uint64_t allowed = room * (uint64_t)(row_end - row_begin) / added;
+            atomicMin(&p.ctl->next_rows, allowed < 0xfffffff0ull ? (uint32_t)allowed : 0xfffffff0u);
+        }
+        __threadfence();
+        if (atomicAdd(&p.ctl->ticket, 1u) == gridDim.x - 1) {
+            __threadfence();
+            unsigned long long span = *reinterpret_cast<volatile uint32_t *>(&p.ctl->next_rows);
+            // the first phase keeps everything, so its pass rate says nothing: grow 4x;
+            // afterwards at least 8 Ki rows and at most 15x what has been seen so far
+            if (row_begin == 0u) span = 4ull * row_end;
+            if (span < 8192ull) span = 8192ull;
+            if (span > 15ull * row_end) span = 15ull * row_end;
+            const unsigned long long nb = row_end;
+            unsigned long long ne = (nb + span + kTcM - 1) / kTcM * kTcM;
+            if (ne > p.n_rows) ne = p.n_rows;
+            p.ctl->row_begin = (uint32_t)nb;
+            p.ctl->row_end = (uint32_t)ne;
+            p.ctl->next_rows = 0xffffffffu;
+            p.ctl->ticket = 0u;
+            p.ctl->phases += 1u;
+        }
     }
 }
 
@@ -745,6 +863,58 @@ struct TcRescoreParams {
     int metric;
 };
 
+// One thread scores one survivor row with the reference arithmetic: 128-byte blocks of the row
+// are fetched as 8 independent float4 loads, the next block is in flight while the current one
+// is folded (the rows are scattered, so the loop is bound by HBM latency otherwise); the query
+// comes from shared memory as broadcast float4.  Same element order as scan_topk_kernel.
+template <int METRIC>
+__device__ __forceinline__ float tc_score_row(const float *q_s, const float *__restrict__ x,
+                                              uint32_t dim, float qmag) {
+    RowAcc<METRIC> acc;
+    acc.reset();
+    const uint32_t full = (dim / 8u) * 8u;  // elements in whole f32x8 groups
+    const uint32_t n4 = full / 4u;
+    const float4 *xv = reinterpret_cast<const float4 *>(x);
+    const float4 *qv = reinterpret_cast<const float4 *>(q_s);
+    constexpr uint32_t BLK = 8;
+    float4 cur[BLK], nxt[BLK];
+#pragma unroll
+    for (uint32_t j = 0; j < BLK; ++j)
+        cur[j] = (j < n4) ? __ldg(xv + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (uint32_t b = 0; b < n4; b += BLK) {
+#pragma unroll
+        for (uint32_t j = 0; j < BLK; ++j)
+            nxt[j] = (b + BLK + j < n4) ? __ldg(xv + b + BLK + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (uint32_t j = 0; j < BLK; ++j) {
+            if (b + j < n4) {
+                const float4 qq = qv[b + j];
+                if (j & 1u) acc.template step<1>(cur[j], qq);
+                else acc.template step<0>(cur[j], qq);
+            }
+        }
+#pragma unroll
+        for (uint32_t j = 0; j < BLK; ++j) cur[j] = nxt[j];
+    }
+    if (METRIC == kEuclidean) {
+        float sum = acc.d[0];
+        for (uint32_t i = full; i < dim; ++i) {
+            const float df = __fsub_rn(q_s[i], x[i]);
+            sum = __fadd_rn(sum, __fmul_rn(df, df));
+        }
+        return tc_l2_score(sum);
+    }
+    float dot = fold_lanes(acc.d), ssq = fold_lanes(acc.s);
+    for (uint32_t i = full; i < dim; ++i) {
+        const float xi = x[i];
+        dot = __fadd_rn(dot, __fmul_rn(q_s[i], xi));
+        if (METRIC == kCosine) ssq = __fadd_rn(ssq, __fmul_rn(xi, xi));
+    }
+    if (METRIC == kDot) return dot;
+    const float rmag = __fsqrt_rn(ssq);
+    return (qmag == 0.0f || rmag == 0.0f) ? 0.0f : __fdiv_rn(dot, __fmul_rn(qmag, rmag));
+}
+
 __global__ void __launch_bounds__(kRowsPerBlock) tc_rescore_kernel(const TcRescoreParams p) {
     extern __shared__ __align__(16) float q_s[];  // [dim]
     __shared__ __align__(16) uint64_t buf[kCandCap];
@@ -765,7 +935,11 @@ __global__ void __launch_bounds__(kRowsPerBlock) tc_rescore_kernel(const TcResco
     uint64_t *keys = p.exact_keys + (size_t)q * kTcKeptCap;
     for (uint32_t i = t; i < n; i += kRowsPerBlock) {
         const uint32_t row = list[i].row;
-        const float s = exact_score_row(q_s, p.rows + (size_t)row * p.pitch, p.dim, qmag, p.metric);
+        const float *x = p.rows + (size_t)row * p.pitch;
+        float s;
+        if (p.metric == kEuclidean) s = tc_score_row<kEuclidean>(q_s, x, p.dim, qmag);
+        else if (p.metric == kCosine) s = tc_score_row<kCosine>(q_s, x, p.dim, qmag);
+        else s = tc_score_row<kDot>(q_s, x, p.dim, qmag);
         keys[i] = make_key(__float_as_uint(s), row);
     }
     __threadfence();
