@@ -519,6 +519,8 @@ int scan_queries_tc(nm_index *idx, const Shard &sh, Workspace &ws, const float *
                                           cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
             CUDA_TRY(cudaFuncSetAttribute(nm::tc_rescore_kernel,
                                           cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+            CUDA_TRY(cudaFuncSetAttribute(nm::tc_refine_kernel,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
             if (sh.device < 64) configured[sh.device] = true;
         }
     }
@@ -569,7 +571,7 @@ int scan_queries_tc(nm_index *idx, const Shard &sh, Workspace &ws, const float *
         gp.evict_first = ((uint64_t)rows * pitch8 > (64ull << 20)) ? 1u : 0u;
         gp.screen = screen ? 1u : 0u;
         gp.shift = 0;
-        while (((16129ull * dim) >> gp.shift) >= (1ull << 22) - 8) ++gp.shift;
+        while (((16300ull * dim) >> gp.shift) >= (1ull << 22) - 64) ++gp.shift;
         gp.metric = kmetric;
         nm::TcRefineParams rp;
         memset(&rp, 0, sizeof(rp));
@@ -579,6 +581,9 @@ int scan_queries_tc(nm_index *idx, const Shard &sh, Workspace &ws, const float *
         rp.qmeta = qmeta + q0;
         rp.coef = coef + q0;
         rp.ctl = ctl;
+        rp.queries = d_queries + (size_t)q0 * dim;
+        rp.rows = sh.d_rows;
+        rp.pitch = idx->pitch;
         rp.n_rows = rows;
         rp.dim = dim;
         rp.k = k_eff;
@@ -587,7 +592,7 @@ int scan_queries_tc(nm_index *idx, const Shard &sh, Workspace &ws, const float *
             nm::tc_gemm_filter_kernel<<<grid, nm::kTcThreads, nm::tc_gemm_smem_bytes(), stream>>>(
                 sh.tmap8_tc, tmap_q, gp);
             CUDA_TRY(cudaGetLastError());
-            nm::tc_refine_kernel<<<nqp, 256, 0, stream>>>(rp);
+            nm::tc_refine_kernel<<<nqp, 256, (size_t)dim * 4, stream>>>(rp);
             CUDA_TRY(cudaGetLastError());
         }
         nm::TcRescoreParams sp;

@@ -50,10 +50,11 @@ constexpr uint32_t kTcMaxQ = 256;                          // queries per pass =
 constexpr uint32_t kTcStages = 4;
 constexpr uint32_t kTcABytes = kTcM * kTcKBytes;           // 16 KiB
 constexpr uint32_t kTcBBytesMax = kTcMaxQ * kTcKBytes;     // 32 KiB
-constexpr uint32_t kTcEpilogueWarps = 8;                   // 2 per TMEM lane quarter
+constexpr uint32_t kTcEpilogueWarps = 16;                  // 4 per TMEM lane quarter
+constexpr uint32_t kTcColParts = kTcEpilogueWarps / 4;     // they split the 16-query chunks
 constexpr uint32_t kTcThreads = 64 + 32 * kTcEpilogueWarps;  // + TMA warp + MMA warp
 constexpr uint32_t kTcKeptCap = 32768;                     // kept entries per query
-constexpr uint32_t kTcPhase0Rows = 4096;                   // first phase: keep everything
+constexpr uint32_t kTcPhase0Rows = 2048;                   // first phase: keep everything (>= k)
 constexpr uint32_t kTcTmemCols = 512;                      // 2 accumulators x 256 columns
 
 constexpr uint32_t kTcFlagUnusable = 1u;   // query not finite / zero / denormal scale
@@ -88,7 +89,8 @@ struct TcCtl {
 };
 
 inline size_t tc_gemm_smem_bytes() {
-    return 1024 + (size_t)kTcStages * (kTcABytes + kTcBBytesMax) + (size_t)kTcMaxQ * 16 + 256;
+    return 1024 + (size_t)kTcStages * (kTcABytes + kTcBBytesMax) + (size_t)kTcMaxQ * 16 + 256 +
+           (size_t)kTcMaxQ * sizeof(TcQueryMeta) + 256;
 }
 
 #ifdef __CUDACC__
@@ -118,6 +120,7 @@ __device__ __forceinline__ void mbar_wait_wd(uint64_t *bar, uint32_t parity) {
             : "r"(addr), "r"(parity)
             : "memory");
         if (done) return;
+        if (spins >= 8u) __nanosleep(40);
         if (spins == 4096u) t0 = clock64();
         if (spins > 4096u && (spins & 1023u) == 0u && clock64() - t0 > 6000000000ll) __trap();
     }
@@ -162,6 +165,12 @@ __device__ __forceinline__ void tc_ld16_issue(uint32_t taddr, int (&v)[16]) {
           "=r"(v[14]), "=r"(v[15])
         : "r"(taddr)
         : "memory");
+}
+__device__ __forceinline__ int tc_ld1(uint32_t taddr) {
+    int v;
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(v) : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" : "+r"(v) : : "memory");
+    return v;
 }
 __device__ __forceinline__ void tc_ld_wait(int (&v)[16]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;"
@@ -462,7 +471,7 @@ tc_prepare_queries_kernel(const float *__restrict__ queries, uint32_t nq, uint32
         m.pad[0] = m.pad[1] = m.pad[2] = 0u;
         qmeta[q] = m;
         coef[q] = bad ? tc_pass_none() : tc_pass_all(0u);
-        kept_n[q] = 0u;
+        kept_n[q] = bad ? 0u : min(n_rows, kTcPhase0Rows);  // phase 0 fills slots [0, rows)
         kept_prev[q] = 0u;
     }
 }
@@ -489,32 +498,26 @@ struct TcGemmParams {
     int metric;
 };
 
-// rigorous re-evaluation + append of the entries of one accumulator column that passed the
-// screen.  Warp-uniform call; `pass` is per lane.
-__device__ __noinline__ void tc_keep_column(const TcGemmParams &p, uint32_t q, int I, uint32_t row,
-                                            const RowMeta &m, uint32_t tau_ord, bool pass) {
-    const uint32_t lane = threadIdx.x & 31u;
-    uint32_t lb_ord = 0u, ub_ord = 0u;
-    if (pass) {
-        const TcQueryMeta qm = p.qmeta[q];
-        tc_interval(p.metric, I, m, qm, p.dim, lb_ord, ub_ord);
-        pass = ub_ord >= tau_ord && !(qm.flags & kTcFlagUnusable);
-    }
-    const uint32_t ballot = __ballot_sync(0xffffffffu, pass);
-    if (!ballot) return;
-    const uint32_t leader = __ffs(ballot) - 1;
-    uint32_t base = 0;
-    if (lane == leader) base = atomicAdd(p.kept_n + q, (uint32_t)__popc(ballot));
-    base = __shfl_sync(0xffffffffu, base, leader);
-    if (pass) {
-        const uint32_t pos = base + __popc(ballot & ((1u << lane) - 1u));
-        if (pos < kTcKeptCap) {
-            TcKept e;
-            e.row = row;
-            e.lb_ord = lb_ord;
-            e.ub_ord = ub_ord;
-            p.kept[(size_t)q * kTcKeptCap + pos] = e;
-        }
+// rigorous re-evaluation + append of ONE (row, query) entry that passed the screen.  Called
+// divergently: every lane walks its own hits, so the latencies of the list reservations of a
+// chunk overlap instead of queueing up column by column.
+__device__ __noinline__ void tc_keep_entry(const TcGemmParams &p, const TcQueryMeta *qmeta_s,
+                                           uint32_t q, int I, uint32_t row, const RowMeta &m,
+                                           uint32_t tau_ord, bool phase0) {
+    const TcQueryMeta &qm = qmeta_s[q];
+    if (qm.flags & kTcFlagUnusable) return;
+    uint32_t lb_ord, ub_ord;
+    tc_interval(p.metric, I, m, qm, p.dim, lb_ord, ub_ord);
+    if (ub_ord < tau_ord) return;
+    // the first phase keeps every row of [0, kTcPhase0Rows): slot == row, the list length was
+    // set by the prepare kernel, no reservation needed
+    const uint32_t pos = phase0 ? row : atomicAdd(p.kept_n + q, 1u);
+    if (pos < kTcKeptCap) {
+        TcKept e;
+        e.row = row;
+        e.lb_ord = lb_ord;
+        e.ub_ord = ub_ord;
+        p.kept[(size_t)q * kTcKeptCap + pos] = e;
     }
 }
 
@@ -527,7 +530,9 @@ tc_gemm_filter_kernel(const __grid_constant__ CUtensorMap tmap_a,
     uint8_t *st_a = smem;
     uint8_t *st_b = smem + kTcStages * kTcABytes;
     float4 *coef_s = reinterpret_cast<float4 *>(st_b + kTcStages * kTcBBytesMax);
-    uint64_t *full_bar = reinterpret_cast<uint64_t *>(coef_s + kTcMaxQ);
+    float4 *cmin_s = coef_s + kTcMaxQ;             // [16] per 16-query chunk: min w, min u, min v
+    TcQueryMeta *qmeta_s = reinterpret_cast<TcQueryMeta *>(cmin_s + kTcMaxQ / 16u);  // [256]
+    uint64_t *full_bar = reinterpret_cast<uint64_t *>(qmeta_s + kTcMaxQ);
     uint64_t *empty_bar = full_bar + kTcStages;
     uint64_t *tfull_bar = empty_bar + kTcStages;   // [2] accumulator ready
     uint64_t *tempty_bar = tfull_bar + 2;          // [2] accumulator drained
@@ -558,18 +563,34 @@ tc_gemm_filter_kernel(const __grid_constant__ CUtensorMap tmap_a,
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     {
-        // the screen compares in units of 2^shift (exact power-of-two scaling)
+        // the screen compares in units of 2^shift (exact power-of-two scaling) and with the
+        // int -> float conversion constant 1.5 * 2^23 folded into the query's additive term
         const float sc = __uint_as_float((127u - p.shift) << 23);
         for (uint32_t i = tid; i < kTcMaxQ; i += kTcThreads) {
-            float4 c = make_float4(0.0f, 0.0f, INFINITY, 0.0f);
+            float4 c = make_float4(0.0f, 0.0f, INFINITY, 0.0f);  // padding: never passes
             if (i < p.nq) {
                 c = p.coef[i];
                 c.x *= sc;
                 c.y *= sc;
-                c.z *= sc;
+                c.z = __double2float_rd((double)c.z * (double)sc + 12582912.0);
             }
             coef_s[i] = c;
         }
+        for (uint32_t i = tid; i < p.nq * (uint32_t)(sizeof(TcQueryMeta) / 16u); i += kTcThreads)
+            reinterpret_cast<uint4 *>(qmeta_s)[i] = reinterpret_cast<const uint4 *>(p.qmeta)[i];
+    }
+    __syncthreads();
+    if (tid < kTcMaxQ / 16u) {
+        // coarse screen of a whole 16-query chunk: alpha, beta >= 0, so the smallest threshold of
+        // the chunk is at least alpha min(w) + beta min(u) + min(v)
+        float4 mn = make_float4(INFINITY, INFINITY, INFINITY, 0.0f);
+        for (uint32_t j = 0; j < 16u && tid * 16u + j < p.nq; ++j) {
+            const float4 c = coef_s[tid * 16u + j];
+            mn.x = fminf(mn.x, c.x);
+            mn.y = fminf(mn.y, c.y);
+            mn.z = fminf(mn.z, c.z);
+        }
+        cmin_s[tid] = mn;
     }
     tc_fence_before();
     __syncthreads();
@@ -633,77 +654,110 @@ tc_gemm_filter_kernel(const __grid_constant__ CUtensorMap tmap_a,
         // ===== epilogue: warp w owns TMEM lanes 32 (w % 4) .. +31; the two warps of a lane
         //       quarter split the query columns =====
         const uint32_t qd = warp & 3u;
-        const uint32_t half = (warp - 2u) >> 2;
-        const uint32_t n_chunks = p.n_pad / 16u;
-        const uint32_t ch_begin = half ? (n_chunks + 1u) / 2u : 0u;
-        const uint32_t ch_end = half ? n_chunks : (n_chunks + 1u) / 2u;
+        const uint32_t part = (warp - 2u) >> 2;  // chunks part, part + kTcColParts, ...
+        const uint32_t n_chunks = (p.nq + 15u) / 16u;
         const float sc = __uint_as_float((127u - p.shift) << 23);
+        const int sh = (int)p.shift;
+        const bool phase0 = row_begin == 0u;
+        auto load_meta = [&](uint32_t r, bool ok) {
+            float4 raw = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            if (ok) raw = __ldg(reinterpret_cast<const float4 *>(p.meta + r));
+            return raw;
+        };
         uint32_t it = 0;
+        float4 raw_next = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        if (blockIdx.x < n_tiles) {
+            const uint32_t r0 = row_begin + blockIdx.x * kTcM + qd * 32u + lane;
+            raw_next = load_meta(r0, r0 < row_end);
+        }
         for (uint32_t t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
             const uint32_t acc = it & 1u, aph = (it >> 1) & 1u;
             const uint32_t row = row_begin + t * kTcM + qd * 32u + lane;
             const bool valid = row < row_end;
-            RowMeta m;
-            m.scale = 0.0f;
-            m.x1 = 0u;
-            m.rmag = 0.0f;
-            m.flags = 0u;
-            if (valid) {
-                const float4 raw = __ldg(reinterpret_cast<const float4 *>(p.meta + row));
-                m.scale = raw.x;
-                m.x1 = __float_as_uint(raw.y);
-                m.rmag = raw.z;
-                m.flags = __float_as_uint(raw.w);
+            const float4 raw = raw_next;
+            {   // next tile's row constants: in flight while this tile is screened
+                const uint32_t tn = t + gridDim.x;
+                const uint32_t rn = row_begin + tn * kTcM + qd * 32u + lane;
+                raw_next = load_meta(rn, tn < n_tiles && rn < row_end);
             }
+            RowMeta m;
+            m.scale = raw.x;
+            m.x1 = __float_as_uint(raw.y);
+            m.rmag = raw.z;
+            m.flags = __float_as_uint(raw.w);
             float alpha, beta, br;
             tc_row_coef(p.metric, m, p.dim, alpha, beta, br);
             if (!p.screen) br = INFINITY;
-            // lhs = float(I >> shift) + br / 2^shift (+3: the floor of the shift and the two
-            // roundings below), with the int -> float conversion done by the 1.5 * 2^23 trick
-            const float brm = __fadd_ru(__fadd_ru(__fmul_ru(br, sc), 3.0f), -12582912.0f);
-            mbar_wait_wd(&tfull_bar[acc], aph);
+            // lhs = float((I >> shift) + ceil(br / 2^shift) + 5) via the 1.5 * 2^23 bit trick (the
+            // 5 covers the floor of the shift and the roundings of the two fma below, whose
+            // results are near 1.26e7 where one ulp is 1); rows that must always be kept get
+            // a huge lhs
+            const float brs = __fmul_ru(br, sc);
+            const int add_r = (brs < 2000000.0f) ? 0x4B400000 + (__float2int_ru(brs) + 5) : 0x7f000000;
+            if (lane == 0) mbar_wait_wd(&tfull_bar[acc], aph);
+            __syncwarp();
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((qd * 32u) << 16) + acc * kTcMaxQ;
             auto process = [&](int (&v)[16], uint32_t c0) {
-                uint32_t mask = 0u;
+                // coarse: the largest dot product of the chunk against its smallest threshold
+                int mx = max(max(max(v[0], v[1]), max(v[2], v[3])), max(max(v[4], v[5]), max(v[6], v[7])));
+                mx = max(mx, max(max(max(v[8], v[9]), max(v[10], v[11])),
+                                 max(max(v[12], v[13]), max(v[14], v[15]))));
+                const float4 cm = cmin_s[c0 >> 4];
+                const float lhs_c = __int_as_float((mx >> sh) + add_r);
+                const float rhs_c = fmaf(alpha, cm.x, fmaf(beta, cm.y, cm.z));
+                if (!__any_sync(0xffffffffu, valid && !(lhs_c < rhs_c))) return;
+                // fine: every column against its own threshold
+                bool hit = false;
 #pragma unroll
                 for (uint32_t j = 0; j < 16u; ++j) {
                     const float4 cq = coef_s[c0 + j];
-                    const float lhs =
-                        __int_as_float(0x4B400000 + (v[j] >> p.shift)) + brm;
+                    const float lhs = __int_as_float((v[j] >> sh) + add_r);
                     const float rhs = fmaf(alpha, cq.x, fmaf(beta, cq.y, cq.z));
-                    if (!(lhs < rhs)) mask |= 1u << j;
+                    hit |= !(lhs < rhs);
                 }
-                const uint32_t left = p.nq - min(p.nq, c0);
-                mask &= left >= 16u ? 0xffffu : ((1u << left) - 1u);
-                if (!valid) mask = 0u;
-                if (p.dump && valid) {
+                if (hit && valid) {  // rare: rigorous evaluation of this lane's hits
+                    uint32_t mask = 0u;
+                    int tmp[16];
 #pragma unroll
-                    for (uint32_t j = 0; j < 16u; ++j)
-                        if (c0 + j < p.nq) p.dump[(size_t)(c0 + j) * p.dump_stride + row] = v[j];
-                }
-                const uint32_t any = __reduce_or_sync(0xffffffffu, mask);
-                if (any) {
-#pragma unroll
-                    for (uint32_t j = 0; j < 16u; ++j)
-                        if (any & (1u << j))
-                            tc_keep_column(p, c0 + j, v[j], row, m,
-                                           __float_as_uint(coef_s[c0 + j].w), (mask >> j) & 1u);
+                    for (uint32_t j = 0; j < 16u; ++j) {
+                        const float4 cq = coef_s[c0 + j];
+                        const float lhs = __int_as_float((v[j] >> sh) + add_r);
+                        const float rhs = fmaf(alpha, cq.x, fmaf(beta, cq.y, cq.z));
+                        if (!(lhs < rhs)) mask |= 1u << j;
+                        tmp[j] = v[j];
+                    }
+                    const uint32_t left = p.nq - c0;  // c0 < nq
+                    mask &= left >= 16u ? 0xffffu : ((1u << left) - 1u);
+                    while (mask) {
+                        const uint32_t j = __ffs(mask) - 1u;
+                        mask &= mask - 1u;
+                        tc_keep_entry(p, qmeta_s, c0 + j, tmp[j], row, m,
+                                      __float_as_uint(coef_s[c0 + j].w), phase0);
+                    }
                 }
             };
-            if (ch_begin < ch_end) {
+            if (p.dump) {  // diagnostics only (nm_debug_tc_dots)
+                for (uint32_t c = 0; c < p.nq; ++c) {
+                    const int I = tc_ld1(taddr + c);
+                    if (valid && ((c >> 4) % kTcColParts) == part)
+                        p.dump[(size_t)c * p.dump_stride + row] = I;
+                }
+            }
+            if (part < n_chunks) {
                 int va[16], vb[16];
-                tc_ld16_issue(taddr + ch_begin * 16u, va);
+                tc_ld16_issue(taddr + part * 16u, va);
                 tc_ld_wait(va);
-                for (uint32_t ch = ch_begin; ch < ch_end; ch += 2u) {
-                    const bool has_b = ch + 1u < ch_end;
-                    if (has_b) tc_ld16_issue(taddr + (ch + 1u) * 16u, vb);
+                for (uint32_t ch = part; ch < n_chunks; ch += 2u * kTcColParts) {
+                    const uint32_t chb = ch + kTcColParts, chn = ch + 2u * kTcColParts;
+                    const bool has_b = chb < n_chunks;
+                    if (has_b) tc_ld16_issue(taddr + chb * 16u, vb);
                     process(va, ch * 16u);
                     if (has_b) {
                         tc_ld_wait(vb);
-                        if (ch + 2u < ch_end) tc_ld16_issue(taddr + (ch + 2u) * 16u, va);
-                        process(vb, (ch + 1u) * 16u);
-                        if (ch + 2u < ch_end) tc_ld_wait(va);
+                        if (chn < n_chunks) tc_ld16_issue(taddr + chn * 16u, va);
+                        process(vb, chb * 16u);
+                        if (chn < n_chunks) tc_ld_wait(va);
                     }
                 }
             }
@@ -723,8 +777,14 @@ tc_gemm_filter_kernel(const __grid_constant__ CUtensorMap tmap_a,
 }
 
 // ---------------------------------------------------------------------------------------
-// refine: per query, new tau = k-th best lower bound of the kept list; compact to ub >= tau
+// refine: per query, tighten tau and compact the kept list
 // ---------------------------------------------------------------------------------------
+// tau must be a score that at least k rows reach.  The k-th best LOWER bound is one, but it
+// sits a whole interval width below the true k-th best score, which lets ~e^(lambda width)
+// times too many entries through the screen.  So the k entries with the best lower bounds are
+// re-scored exactly here (reference arithmetic, from the f32 mirror): the k-th best of their
+// exact scores is also reached by k rows and is, up to the quantisation noise, the true k-th
+// best score of the rows seen so far.  Re-scored entries keep lb = ub = exact score.
 struct TcRefineParams {
     TcKept *kept;
     uint32_t *kept_n;
@@ -732,17 +792,109 @@ struct TcRefineParams {
     TcQueryMeta *qmeta;
     float4 *coef;
     TcCtl *ctl;
+    const float *queries;  // [nq][dim]
+    const float *rows;     // f32 mirror
+    uint32_t pitch;
     uint32_t n_rows;
     uint32_t dim;
     uint32_t k;
     int metric;
 };
 
+constexpr uint32_t kTcTopCap = 2048;  // >= kMaxFastK; entries re-scored per refine at most
+
+// k-th largest of val(0..n) (n >= k >= 1), MSB-first radix select; all 256 threads call.
+template <class F>
+__device__ __forceinline__ uint32_t tc_radix_kth(F val, uint32_t n, uint32_t k, uint32_t *hist,
+                                                 uint32_t *sel_s, uint32_t t) {
+    if (t == 0) {
+        sel_s[0] = 0u;
+        sel_s[1] = k;
+    }
+    for (int shift = 24; shift >= 0; shift -= 8) {
+        hist[t] = 0u;
+        __syncthreads();
+        const uint32_t prefix = sel_s[0];
+        for (uint32_t i = t; i < n; i += 256u) {
+            const uint32_t o = val(i);
+            if (shift == 24 || (o >> (shift + 8)) == prefix) atomicAdd(&hist[(o >> shift) & 255u], 1u);
+        }
+        __syncthreads();
+        if (t == 0) {
+            uint32_t need = sel_s[1], cum = 0;
+            int b = 255;
+            for (; b > 0; --b) {
+                if (cum + hist[b] >= need) break;
+                cum += hist[b];
+            }
+            sel_s[0] = (prefix << 8) | (uint32_t)b;
+            sel_s[1] = need - cum;
+        }
+        __syncthreads();
+    }
+    return sel_s[0];
+}
+
+// One thread scores one survivor row with the reference arithmetic: 128-byte blocks of the row
+// are fetched as 8 independent float4 loads, the next block is in flight while the current one
+// is folded (the rows are scattered, so the loop is bound by HBM latency otherwise); the query
+// comes from shared memory as broadcast float4.  Same element order as scan_topk_kernel.
+template <int METRIC>
+__device__ __forceinline__ float tc_score_row(const float *q_s, const float *__restrict__ x,
+                                              uint32_t dim, float qmag) {
+    RowAcc<METRIC> acc;
+    acc.reset();
+    const uint32_t full = (dim / 8u) * 8u;  // elements in whole f32x8 groups
+    const uint32_t n4 = full / 4u;
+    const float4 *xv = reinterpret_cast<const float4 *>(x);
+    const float4 *qv = reinterpret_cast<const float4 *>(q_s);
+    constexpr uint32_t BLK = 8;
+    float4 cur[BLK], nxt[BLK];
+#pragma unroll
+    for (uint32_t j = 0; j < BLK; ++j)
+        cur[j] = (j < n4) ? __ldg(xv + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (uint32_t b = 0; b < n4; b += BLK) {
+#pragma unroll
+        for (uint32_t j = 0; j < BLK; ++j)
+            nxt[j] = (b + BLK + j < n4) ? __ldg(xv + b + BLK + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (uint32_t j = 0; j < BLK; ++j) {
+            if (b + j < n4) {
+                const float4 qq = qv[b + j];
+                if (j & 1u) acc.template step<1>(cur[j], qq);
+                else acc.template step<0>(cur[j], qq);
+            }
+        }
+#pragma unroll
+        for (uint32_t j = 0; j < BLK; ++j) cur[j] = nxt[j];
+    }
+    if (METRIC == kEuclidean) {
+        float sum = acc.d[0];
+        for (uint32_t i = full; i < dim; ++i) {
+            const float df = __fsub_rn(q_s[i], x[i]);
+            sum = __fadd_rn(sum, __fmul_rn(df, df));
+        }
+        return tc_l2_score(sum);
+    }
+    float dot = fold_lanes(acc.d), ssq = fold_lanes(acc.s);
+    for (uint32_t i = full; i < dim; ++i) {
+        const float xi = x[i];
+        dot = __fadd_rn(dot, __fmul_rn(q_s[i], xi));
+        if (METRIC == kCosine) ssq = __fadd_rn(ssq, __fmul_rn(xi, xi));
+    }
+    if (METRIC == kDot) return dot;
+    const float rmag = __fsqrt_rn(ssq);
+    return (qmag == 0.0f || rmag == 0.0f) ? 0.0f : __fdiv_rn(dot, __fmul_rn(qmag, rmag));
+}
+
 __global__ void __launch_bounds__(256) tc_refine_kernel(const TcRefineParams p) {
+    extern __shared__ __align__(16) float q_s[];  // [dim]
     __shared__ uint32_t hist[256];
-    __shared__ uint32_t sel_s[2];   // [0] prefix [1] need
+    __shared__ uint32_t sel_s[2];
     __shared__ uint32_t warp_cnt[8];
-    __shared__ uint32_t out_pos_s;
+    __shared__ uint32_t out_pos_s, top_n;
+    __shared__ uint32_t top_idx[kTcTopCap];
+    __shared__ uint32_t top_ord[kTcTopCap];
     const uint32_t q = blockIdx.x, t = threadIdx.x, lane = t & 31u, warp = t >> 5;
     const uint32_t row_begin = p.ctl->row_begin, row_end = min(p.ctl->row_end, p.n_rows);
     if (row_begin >= row_end) return;  // no phase ran before this launch
@@ -751,33 +903,43 @@ __global__ void __launch_bounds__(256) tc_refine_kernel(const TcRefineParams p) 
     const uint32_t n = min(n_raw, kTcKeptCap);
     uint32_t tau = p.qmeta[q].tau_ord;
     if (n >= p.k) {
-        // MSB-first radix select of the k-th largest lb_ord
-        if (t == 0) {
-            sel_s[0] = 0u;
-            sel_s[1] = p.k;
-        }
-        for (int shift = 24; shift >= 0; shift -= 8) {
-            hist[t] = 0u;
-            __syncthreads();
-            const uint32_t prefix = sel_s[0];
-            for (uint32_t i = t; i < n; i += 256u) {
-                const uint32_t o = list[i].lb_ord;
-                if (shift == 24 || (o >> (shift + 8)) == prefix) atomicAdd(&hist[(o >> shift) & 255u], 1u);
+        const uint32_t sel = tc_radix_kth([&](uint32_t i) { return list[i].lb_ord; }, n, p.k, hist,
+                                          sel_s, t);
+        tau = max(tau, sel);
+        // the entries with the k best lower bounds (ties may add a few)
+        if (t == 0) top_n = 0u;
+        const float *qv = p.queries + (size_t)q * p.dim;
+        for (uint32_t i = t; i < p.dim; i += 256u) q_s[i] = __ldg(qv + i);
+        __syncthreads();
+        for (uint32_t i = t; i < n; i += 256u) {
+            if (list[i].lb_ord >= sel) {
+                const uint32_t pos = atomicAdd(&top_n, 1u);
+                if (pos < kTcTopCap) top_idx[pos] = i;
             }
-            __syncthreads();
-            if (t == 0) {
-                uint32_t need = sel_s[1], cum = 0;
-                int b = 255;
-                for (; b > 0; --b) {
-                    if (cum + hist[b] >= need) break;
-                    cum += hist[b];
+        }
+        __syncthreads();
+        const uint32_t cnt = top_n;
+        if (cnt <= kTcTopCap) {
+            const float qmag = p.qmeta[q].qmag;
+            for (uint32_t j = t; j < cnt; j += 256u) {
+                const uint32_t i = top_idx[j];
+                TcKept e = list[i];
+                if (e.lb_ord != e.ub_ord) {
+                    const float *x = p.rows + (size_t)e.row * p.pitch;
+                    float sc;
+                    if (p.metric == kEuclidean) sc = tc_score_row<kEuclidean>(q_s, x, p.dim, qmag);
+                    else if (p.metric == kCosine) sc = tc_score_row<kCosine>(q_s, x, p.dim, qmag);
+                    else sc = tc_score_row<kDot>(q_s, x, p.dim, qmag);
+                    e.lb_ord = e.ub_ord = score_to_ord(__float_as_uint(sc));
+                    list[i] = e;
                 }
-                sel_s[0] = (prefix << 8) | (uint32_t)b;
-                sel_s[1] = need - cum;
+                top_ord[j] = e.lb_ord;
             }
             __syncthreads();
+            const uint32_t ex = tc_radix_kth([&](uint32_t i) { return top_ord[i]; }, cnt, p.k, hist,
+                                            sel_s, t);
+            tau = max(tau, ex);
         }
-        tau = max(tau, sel_s[0]);
     }
     // in-place stable compaction (writes never pass the chunk being read)
     if (t == 0) out_pos_s = 0u;
@@ -862,58 +1024,6 @@ struct TcRescoreParams {
     uint32_t out_stride;
     int metric;
 };
-
-// One thread scores one survivor row with the reference arithmetic: 128-byte blocks of the row
-// are fetched as 8 independent float4 loads, the next block is in flight while the current one
-// is folded (the rows are scattered, so the loop is bound by HBM latency otherwise); the query
-// comes from shared memory as broadcast float4.  Same element order as scan_topk_kernel.
-template <int METRIC>
-__device__ __forceinline__ float tc_score_row(const float *q_s, const float *__restrict__ x,
-                                              uint32_t dim, float qmag) {
-    RowAcc<METRIC> acc;
-    acc.reset();
-    const uint32_t full = (dim / 8u) * 8u;  // elements in whole f32x8 groups
-    const uint32_t n4 = full / 4u;
-    const float4 *xv = reinterpret_cast<const float4 *>(x);
-    const float4 *qv = reinterpret_cast<const float4 *>(q_s);
-    constexpr uint32_t BLK = 8;
-    float4 cur[BLK], nxt[BLK];
-#pragma unroll
-    for (uint32_t j = 0; j < BLK; ++j)
-        cur[j] = (j < n4) ? __ldg(xv + j) : make_float4(0.f, 0.f, 0.f, 0.f);
-    for (uint32_t b = 0; b < n4; b += BLK) {
-#pragma unroll
-        for (uint32_t j = 0; j < BLK; ++j)
-            nxt[j] = (b + BLK + j < n4) ? __ldg(xv + b + BLK + j) : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-        for (uint32_t j = 0; j < BLK; ++j) {
-            if (b + j < n4) {
-                const float4 qq = qv[b + j];
-                if (j & 1u) acc.template step<1>(cur[j], qq);
-                else acc.template step<0>(cur[j], qq);
-            }
-        }
-#pragma unroll
-        for (uint32_t j = 0; j < BLK; ++j) cur[j] = nxt[j];
-    }
-    if (METRIC == kEuclidean) {
-        float sum = acc.d[0];
-        for (uint32_t i = full; i < dim; ++i) {
-            const float df = __fsub_rn(q_s[i], x[i]);
-            sum = __fadd_rn(sum, __fmul_rn(df, df));
-        }
-        return tc_l2_score(sum);
-    }
-    float dot = fold_lanes(acc.d), ssq = fold_lanes(acc.s);
-    for (uint32_t i = full; i < dim; ++i) {
-        const float xi = x[i];
-        dot = __fadd_rn(dot, __fmul_rn(q_s[i], xi));
-        if (METRIC == kCosine) ssq = __fadd_rn(ssq, __fmul_rn(xi, xi));
-    }
-    if (METRIC == kDot) return dot;
-    const float rmag = __fsqrt_rn(ssq);
-    return (qmag == 0.0f || rmag == 0.0f) ? 0.0f : __fdiv_rn(dot, __fmul_rn(qmag, rmag));
-}
 
 __global__ void __launch_bounds__(kRowsPerBlock) tc_rescore_kernel(const TcRescoreParams p) {
     extern __shared__ __align__(16) float q_s[];  // [dim]
