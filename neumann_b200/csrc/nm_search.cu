@@ -197,15 +197,25 @@ static int search_impl(nm_index *idx, const float *queries, uint32_t nq, uint32_
             if (rc) return rc;
             idx->tc_queries += nq;
             idx->tc_survivors += tc_survivors(*ws);
-            bool redo = false;
-            for (uint32_t q = 0; q < nq; ++q) {
-                if (tc_query_flags(*ws, q, (uint32_t)sh.rows) == 0) continue;
-                idx->tc_fallbacks++;
-                redo = true;
-                rc = launch_scan(idx, sh, *ws, ws->d_query + (size_t)q * dim, k, metric, sh.row_base,
-                                 r_rows + (size_t)q * k, r_scores + (size_t)q * k, r_counts + q,
-                                 nullptr, ws->stream);
+            uint32_t n_redo = 0;
+            for (uint32_t q = 0; q < nq; ++q)
+                if (tc_query_flags(*ws, q, (uint32_t)sh.rows) != 0) ++n_redo;
+            idx->tc_fallbacks += n_redo;
+            const bool redo = n_redo != 0;
+            if (n_redo * 2 > nq) {
+                // most of the batch (e.g. a corpus ordered against the running threshold): the
+                // exact batched kernels redo all of it in shared corpus passes
+                rc = scan_queries(idx, sh, *ws, ws->d_query, nq, k, metric, sh.row_base, r_rows,
+                                  r_scores, r_counts, nullptr, ws->stream);
                 if (rc) return rc;
+            } else if (redo) {
+                for (uint32_t q = 0; q < nq; ++q) {
+                    if (tc_query_flags(*ws, q, (uint32_t)sh.rows) == 0) continue;
+                    rc = launch_scan(idx, sh, *ws, ws->d_query + (size_t)q * dim, k, metric,
+                                     sh.row_base, r_rows + (size_t)q * k, r_scores + (size_t)q * k,
+                                     r_counts + q, nullptr, ws->stream);
+                    if (rc) return rc;
+                }
             }
             if (!redo) {
                 float ms = 0.f;

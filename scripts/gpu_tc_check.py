@@ -70,6 +70,7 @@ if ok and stage in ("all", "search"):
     for metric in ("euclidean", "cosine", "dot"):
         ok &= check_search(100_000, 256, 16, 10, metric)
         ok &= check_search(300_000, 200, 37, 100, metric)
+        ok &= check_search(70_000, 131, 5, 7, metric)
     ok &= check_search(1_000_000, 768, 256, 10, "cosine", timing=True)
 if ok and stage in ("all", "big"):
     ok &= check_search(2_000_000, 1536, 256, 100, "euclidean", timing=True)

@@ -1,0 +1,252 @@
+"""Tensor-core batch pre-filter (tc_prefilter_kernels.cuh; BASELINE config 4 "batch 256 queries").
+
+A batch is nq independent search_similar_with_metric calls (vector_engine/src/lib.rs:2049-2101),
+so every query of a batch must return exactly what the exact f32 kernels return: same row ids
+in the same order, bit-identical scores.  Checked against the CPU oracle at sizes it finishes in
+seconds and against the exact batched kernels (nm_index_set_tensor_core(0)) at larger sizes;
+the tcgen05 integer GEMM itself is checked against numpy integer dot products."""
+import numpy as np
+import pytest
+
+import oracle_ffi as o
+from neumann_b200 import DeviceIndex
+from neumann_b200.synth import synth_rows
+
+pytestmark = pytest.mark.gpu
+
+METRICS = ["cosine", "euclidean", "dot"]
+
+
+def assert_same(got, exp, ctx=""):
+    assert np.array_equal(got[0], exp[0]), f"{ctx}: rows {got[0][:8]} != {exp[0][:8]}"
+    nan = np.isnan(exp[1])
+    assert np.array_equal(np.isnan(got[1]), nan), ctx
+    assert np.array_equal(got[1].view(np.uint32)[~nan], exp[1].view(np.uint32)[~nan]), ctx
+
+
+def tc_search(idx, qs, k, metric):
+    """-> results, tc queries served, fallbacks, survivors"""
+    s0 = idx.stats()
+    res = idx.search(qs, k, metric)
+    s1 = idx.stats()
+    return (res, s1.tc_queries - s0.tc_queries, s1.tc_fallbacks - s0.tc_fallbacks,
+            s1.tc_survivors - s0.tc_survivors)
+
+
+def quantise(q):
+    """The library's int8 quantisation of a query (tc_prepare_queries_kernel)."""
+    q = q.astype(np.float32)
+    s = np.float32(np.abs(q).max()) / np.float32(127.0)
+    return np.clip(np.rint(q / s), -127, 127).astype(np.int32)
+
+
+@pytest.mark.parametrize("n,dim,nq", [(70_000, 128, 16), (66_000, 200, 21), (70_000, 768, 256),
+                                      (65_600, 100, 3)])
+def test_tensor_core_dot_products_are_exact(n, dim, nq):
+    """tcgen05.mma kind::i8 over the TMA-staged SWIZZLE_128B tiles == integer dot products."""
+    idx = DeviceIndex(dim)
+    idx.fill_synthetic(n, 0x5EED0001)
+    idx.set_prefilter(1)
+    qs = synth_rows(nq, dim, 0x5EED1001)
+    dots = idx.debug_tc_dots(qs)
+    q8 = np.stack([quantise(q) for q in qs])
+    rng = np.random.default_rng(1)
+    rows = sorted(set([0, 1, 31, 32, 127, 128, 129, 2047, 2048, n - 1, n - 2, n // 2] +
+                      [int(r) for r in rng.integers(0, n, 150)]))
+    for r in rows:
+        x8, _ = idx.debug_q8_row(r)
+        assert np.array_equal(q8 @ x8.astype(np.int32), dots[:, r]), f"row {r}"
+    idx.close()
+
+
+@pytest.mark.parametrize("metric", METRICS)
+@pytest.mark.parametrize("n,dim,nq,k", [(70_000, 128, 16, 10), (100_000, 96, 37, 100),
+                                        (66_000, 131, 5, 7), (80_000, 768, 8, 1),
+                                        (120_000, 64, 2, 1000), (70_000, 1536, 4, 20)])
+def test_tc_batch_equals_oracle(metric, n, dim, nq, k):
+    rows = o.fill_synthetic(n, dim, 0x5EED0001)
+    idx = DeviceIndex(dim)
+    idx.load(rows)
+    idx.set_prefilter(1)
+    qs = o.fill_synthetic(nq, dim, 0x5EED1001)
+    qs[1] = rows[n // 3]                               # a query equal to a stored row
+    res, used, fell, _ = tc_search(idx, qs, k, metric)
+    assert used == nq and fell == 0
+    for i in range(nq):
+        assert_same(res[i], o.search(rows, qs[i], k, metric, threads=8), f"{metric} n={n} d={dim} q{i}")
+    idx.close()
+
+
+@pytest.mark.parametrize("metric", METRICS)
+def test_tc_batch_equals_exact_kernels_large(metric):
+    """300 queries (two passes of the 256-query GEMM) over 1M x 256 against the exact batched
+    kernels; the screen must also be a no-op for the result (NM_TC_SCREEN is exercised by
+    test_tc_adversarial_data through rows that bypass it)."""
+    n, dim, nq, k = 1_000_000, 256, 300, 50
+    idx = DeviceIndex(dim)
+    idx.fill_synthetic(n, 0x5EED0001)
+    qs = synth_rows(nq, dim, 0x5EED1001)
+    exact = idx.search(qs, k, metric)
+    idx.set_prefilter(1)
+    res, used, fell, surv = tc_search(idx, qs, k, metric)
+    assert used == nq and fell == 0
+    assert surv < nq * 40 * k, "the filter should keep a small multiple of k rows per query"
+    for i in range(nq):
+        assert_same(res[i], exact[i], f"{metric} q{i}")
+    idx.set_tensor_core(False)
+    res2, used2, _, _ = tc_search(idx, qs[:8], k, metric)
+    assert used2 == 0
+    for i in range(8):
+        assert_same(res2[i], exact[i], f"{metric} tensor core off q{i}")
+    idx.close()
+
+
+@pytest.mark.parametrize("metric", METRICS)
+def test_tc_adversarial_data(metric):
+    """Near-duplicates inside the quantisation error, exact ties, outlier elements (coarse int8
+    scale), tiny / huge / denormal magnitudes, zero rows, NaN and Inf rows, and queries that are
+    zero, huge, tiny or not finite (those are redone by the exact path)."""
+    n, d, k = 70_000, 96, 20
+    rng = np.random.default_rng(5)
+    rows = o.fill_synthetic(n, d, 21)
+    q = o.fill_synthetic(1, d, 22)[0]
+    rows[1000:1400] = q + rng.normal(0, 1e-4, (400, d)).astype(np.float32)
+    rows[2000:2100] = rows[1000]
+    rows[3000:3200, 0] = 1000.0
+    rows[4000:4100] *= np.float32(1e-20)
+    rows[4100:4200] *= np.float32(1e15)
+    rows[5000:5050] = 0.0
+    rows[6000:6100] = -rows[1000:1100]
+    rows[7000:7050] *= np.float32(1e-38)
+    rows[7050:7060] = np.float32(1e-45)
+    rows[8000, 3] = np.nan
+    rows[8001, 5] = np.inf
+    rows[8002, 7] = -np.inf
+    rows[8003] *= np.float32(3e38)                      # squares overflow in the reference too
+    idx = DeviceIndex(d)
+    idx.load(rows)
+    idx.set_prefilter(1)
+    qs = np.stack([q, rows[3100], rows[4050], rows[4150], np.abs(q), rows[7010],
+                   q * np.float32(1e30), np.zeros(d, np.float32), q * np.float32(1e-30),
+                   rows[5000] + np.float32(1.0)])
+    for kk in (1, k, 500):
+        res, used, fell, _ = tc_search(idx, qs, kk, metric)
+        assert used == len(qs)
+        for i in range(len(qs)):
+            assert_same(res[i], o.search(rows, qs[i], kk, metric, threads=8),
+                        f"adversarial {metric} k={kk} q{i}")
+    bad = qs.copy()
+    bad[2, 4] = np.nan
+    bad[5, 1] = np.inf
+    res, used, fell, _ = tc_search(idx, bad, k, metric)
+    assert fell >= 2
+    for i in range(len(bad)):
+        assert_same(res[i], o.search(rows, bad[i], k, metric, threads=8), f"non-finite {metric} q{i}")
+    idx.close()
+
+
+@pytest.mark.parametrize("metric", ["cosine", "euclidean"])
+def test_tc_sorted_corpus_falls_back_or_survives(metric):
+    """Rows ordered so that every new row beats everything before it: the worst case for the
+    running threshold (each phase keeps nearly all of its rows).  Whatever mix of tensor-core
+    results and exact fallbacks the library chooses, the answer must not change."""
+    n, d, k, nq = 200_000, 32, 10, 6
+    rng = np.random.default_rng(9)
+    qs = rng.normal(0, 1, (nq, d)).astype(np.float32)
+    t = np.linspace(0.0, 1.0, n, dtype=np.float32)[:, None]
+    noise = rng.normal(0, 1, (n, d)).astype(np.float32)
+    rows = (t * qs[0][None, :] + (1 - t) * noise).astype(np.float32)   # drifts towards query 0
+    idx = DeviceIndex(d)
+    idx.load(rows)
+    idx.set_prefilter(1)
+    res, used, fell, _ = tc_search(idx, qs, k, metric)
+    assert used == nq
+    for i in range(nq):
+        assert_same(res[i], o.search(rows, qs[i], k, metric, threads=8), f"sorted {metric} q{i}")
+    idx.close()
+
+
+def test_tc_many_ties_overflow_falls_back():
+    """Every row identical: every (row, query) interval reaches the threshold, the kept lists
+    overflow and the exact path must take over."""
+    n, d = 300_000, 16
+    rows = np.ones((n, d), np.float32)
+    idx = DeviceIndex(d)
+    idx.load(rows)
+    idx.set_prefilter(1)
+    qs = np.ones((3, d), np.float32)
+    qs[1] *= 2
+    res, used, fell, _ = tc_search(idx, qs, 10, "cosine")
+    assert used == 3 and fell == 3
+    for i in range(3):
+        assert np.array_equal(res[i][0], np.arange(10, dtype=np.uint64))
+    idx.close()
+
+
+def test_tc_follows_mutations_and_routing():
+    """The int8 copy follows append / update / swap-remove; small indexes, single queries and
+    masked searches stay on their own paths."""
+    n, d, k = 70_000, 64, 5
+    rows = o.fill_synthetic(n, d, 3)
+    idx = DeviceIndex(d)
+    idx.load(rows[:60_000])
+    idx.set_prefilter(1)
+    qs = o.fill_synthetic(4, d, 4)
+    _, used, _, _ = tc_search(idx, qs, k, "euclidean")
+    assert used == 0, "below the row threshold the exact kernels serve the batch"
+    idx.append(rows[60_000:])
+    res, used, fell, _ = tc_search(idx, qs, k, "euclidean")
+    assert used == 4 and fell == 0
+    for i in range(4):
+        assert_same(res[i], o.search(rows, qs[i], k, "euclidean", threads=8), f"append q{i}")
+    rows = rows.copy()
+    rows[123] = qs[2]
+    idx.update(123, qs[2])
+    moved = idx.swap_remove(77)
+    rows[77] = rows[moved]
+    rows = rows[:n - 1]
+    res, used, _, _ = tc_search(idx, qs, k, "cosine")
+    assert used == 4
+    for i in range(4):
+        assert_same(res[i], o.search(rows, qs[i], k, "cosine", threads=8), f"mutated q{i}")
+    assert res[2][0][0] == 123
+    _, used, _, _ = tc_search(idx, qs[0], k, "cosine")
+    assert used == 0, "single queries use the 1-query pre-filter"
+    idx.close()
+
+
+@pytest.mark.parametrize("n,dim,nq,k,metric", [(10_000_000, 1536, 256, 100, "euclidean")])
+def test_config4_full_size_properties(n, dim, nq, k, metric):
+    """BASELINE config 4 at full size through size-independent properties: scores re-derived by
+    the oracle from rows fetched back from the device, total-order sortedness, the k-th hit is
+    not beaten by sampled rows, planted neighbours are found, and the result is identical to
+    the exact batched kernels for a sample of the queries."""
+    idx = DeviceIndex(dim)
+    idx.fill_synthetic(n, 0x5EED0001)
+    qs = synth_rows(nq, dim, 0x5EED1001)
+    planted = [123_456, 9_999_999, 0]
+    for j, r in enumerate(planted):
+        qs[j] = idx.get_row(r) + np.float32(1e-3) * qs[j]
+    idx.set_prefilter(1)
+    res, used, fell, _ = tc_search(idx, qs, k, metric)
+    assert used == nq and fell == 0
+    rng = np.random.default_rng(2)
+    sample_rows = rng.integers(0, n, 64)
+    fetched = np.stack([idx.get_row(int(r)) for r in sample_rows])
+    for qi in list(range(len(planted))) + [17, 200, 255]:
+        r, s = res[qi]
+        assert len(r) == k and len(set(r.tolist())) == k
+        hit_rows = np.stack([idx.get_row(int(x)) for x in r[:12]])
+        exp = o.score_rows(hit_rows, qs[qi], metric)
+        assert np.array_equal(exp.view(np.uint32), s[:12].view(np.uint32))
+        keys = [(-float(sc), int(rw)) for sc, rw in zip(s, r)]
+        assert keys == sorted(keys)
+        assert (o.score_rows(fetched, qs[qi], metric) <= s[-1]).all() or \
+            set(sample_rows[o.score_rows(fetched, qs[qi], metric) > s[-1]]).issubset(set(r.tolist()))
+    for j, rw in enumerate(planted):
+        assert res[j][0][0] == rw
+    idx.set_tensor_core(False)
+    exact = idx.search(qs[:4], k, metric)
+    for i in range(4):
+        assert_same(res[i], exact[i], f"config 4 q{i}")
+    idx.close()
