@@ -421,6 +421,46 @@ def run_ours(a):
                 "note": "nm_index_set_prefilter(1): dp4a scan of an int8 copy with rigorous score "
                         "intervals + exact f32 re-score of the candidates; changes bytes/row, so it is "
                         "NOT the headline metric and NOT part of `value`/`e2e`/`roofline`"}
+            # ---- batches on the same int8 copy: the tcgen05 GEMM pre-filter (BASELINE config 4
+            #      is the L2 / 1536-dim variant of this; scripts/gpu_tc_bench.py runs that shape) ----
+            try:
+                from neumann_b200.synth import synth_rows
+                nqb = 256
+                qb = synth_rows(nqb, a.dim, 0x5EED2001)
+                idx.set_tensor_core(False)
+                exact = idx.search(qb[:16], a.k, a.metric)
+                t0 = time.perf_counter()
+                idx.search(qb, a.k, a.metric)
+                t_exact_batch = time.perf_counter() - t0
+                idx.set_tensor_core(True)
+                idx.search(qb, a.k, a.metric)
+                b0 = idx.stats()
+                ts = []
+                for _ in range(10):
+                    t0 = time.perf_counter()
+                    got = idx.search(qb, a.k, a.metric)
+                    ts.append(time.perf_counter() - t0)
+                b1 = idx.stats()
+                t_b = sorted(ts)[len(ts) // 2]
+                nb = int(b1.tc_queries - b0.tc_queries)
+                same = all(np.array_equal(g[0], e[0]) and
+                           np.array_equal(g[1].view(np.uint32), e[1].view(np.uint32))
+                           for g, e in zip(got[:16], exact))
+                line["batch_tc_int8"] = {
+                    "batch": nqb, "e2e_ms_per_batch": t_b * 1e3, "e2e_value": nqb / t_b,
+                    "unit": "queries/s", "device_ms_per_batch": float(b1.last_scan_ms),
+                    "exact_batched_kernels_ms_per_batch": t_exact_batch * 1e3,
+                    "speedup_vs_exact_batched_kernels": t_exact_batch / t_b,
+                    "speedup_vs_f32_e2e": (nqb / t_b) / e2e_qps,
+                    "identical_to_exact_kernels": bool(same),
+                    "rescored_rows_per_query": (b1.tc_survivors - b0.tc_survivors) / max(nb, 1),
+                    "fallbacks": int(b1.tc_fallbacks - b0.tc_fallbacks),
+                    "note": "256 queries per call through nm_search (host buffers): one tcgen05 "
+                            "kind::i8 GEMM pass over the int8 copy (accumulators in TMEM) + rigorous "
+                            "score intervals + exact f32 re-score; bit-identical to the exact batched "
+                            "kernels; NOT part of `value`/`e2e`/`roofline`"}
+            except Exception as e:  # noqa: BLE001
+                line["batch_tc_int8"] = {"error": repr(e)}
             idx.set_prefilter(0)
         except Exception as e:  # noqa: BLE001
             line["prefilter_int8"] = {"error": repr(e)}

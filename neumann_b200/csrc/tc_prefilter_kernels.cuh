@@ -47,15 +47,18 @@ namespace nm {
 constexpr uint32_t kTcM = 128;                             // corpus rows per tile == TMEM lanes
 constexpr uint32_t kTcKBytes = 128;                        // int8 elements per k-block
 constexpr uint32_t kTcMaxQ = 256;                          // queries per pass == UMMA N max
-constexpr uint32_t kTcStages = 4;
+constexpr uint32_t kTcStagesA = 6;                         // corpus tiles (from HBM: deep ring)
+constexpr uint32_t kTcStagesB = 3;                         // query tiles (L2 resident: short ring)
 constexpr uint32_t kTcABytes = kTcM * kTcKBytes;           // 16 KiB
 constexpr uint32_t kTcBBytesMax = kTcMaxQ * kTcKBytes;     // 32 KiB
 constexpr uint32_t kTcEpilogueWarps = 16;                  // 4 per TMEM lane quarter
 constexpr uint32_t kTcColParts = kTcEpilogueWarps / 4;     // they split the 16-query chunks
-constexpr uint32_t kTcThreads = 64 + 32 * kTcEpilogueWarps;  // + TMA warp + MMA warp
+constexpr uint32_t kTcRoleWarps = 3;                       // A producer, MMA issuer, B producer
+constexpr uint32_t kTcThreads = 32 * (kTcRoleWarps + kTcEpilogueWarps);
 constexpr uint32_t kTcKeptCap = 32768;                     // kept entries per query
 constexpr uint32_t kTcPhase0Rows = 2048;                   // first phase: keep everything (>= k)
 constexpr uint32_t kTcTmemCols = 512;                      // 2 accumulators x 256 columns
+constexpr uint32_t kTcPendCap = 48;                        // parked entries per epilogue warp and tile
 
 constexpr uint32_t kTcFlagUnusable = 1u;   // query not finite / zero / denormal scale
 constexpr uint32_t kTcFlagOverflow = 2u;   // kept list overflowed
@@ -89,8 +92,9 @@ struct TcCtl {
 };
 
 inline size_t tc_gemm_smem_bytes() {
-    return 1024 + (size_t)kTcStages * (kTcABytes + kTcBBytesMax) + (size_t)kTcMaxQ * 16 + 256 +
-           (size_t)kTcMaxQ * sizeof(TcQueryMeta) + 256;
+    return 1024 + (size_t)kTcStagesA * kTcABytes + (size_t)kTcStagesB * kTcBBytesMax +
+           (size_t)kTcMaxQ * 16 + 256 +
+           (size_t)kTcEpilogueWarps * (kTcPendCap * 24 + 4) + 256;
 }
 
 #ifdef __CUDACC__
@@ -104,11 +108,14 @@ __device__ __forceinline__ void tc_fence_before() {
 __device__ __forceinline__ void tc_fence_after() {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 }
-// mbarrier wait with a watchdog: a protocol bug traps (launch failure) instead of hanging the GPU
+// mbarrier wait with a watchdog: a protocol bug traps (launch failure) instead of hanging the
+// GPU.  SLEEP_NS > 0 backs off between polls so that a waiting role does not eat the issue
+// slots of the warps that share its scheduler.
+template <uint32_t SLEEP_NS>
 __device__ __forceinline__ void mbar_wait_wd(uint64_t *bar, uint32_t parity) {
     const uint32_t addr = smem_u32(bar);
     long long t0 = 0;
-    for (uint32_t spins = 0;; ++spins) {
+    for (uint32_t spins = 1;; ++spins) {
         uint32_t done;
         asm volatile(
             "{\n\t"
@@ -120,9 +127,11 @@ __device__ __forceinline__ void mbar_wait_wd(uint64_t *bar, uint32_t parity) {
             : "r"(addr), "r"(parity)
             : "memory");
         if (done) return;
-        if (spins >= 8u) __nanosleep(40);
-        if (spins == 4096u) t0 = clock64();
-        if (spins > 4096u && (spins & 1023u) == 0u && clock64() - t0 > 6000000000ll) __trap();
+        if (SLEEP_NS) __nanosleep(SLEEP_NS);
+        if ((spins & 1023u) == 0u) {
+            if (t0 == 0) t0 = clock64();
+            else if (clock64() - t0 > 6000000000ll) __trap();
+        }
     }
 }
 // K-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout):
@@ -498,13 +507,23 @@ struct TcGemmParams {
     int metric;
 };
 
+// An entry that passed the screen, parked until the accumulator has been handed back to the MMA
+// issuer: the rigorous evaluation (double precision, a list reservation in global memory) must
+// not sit between the TMEM reads of a tile and the release of its accumulator.
+struct TcPend {
+    int I;
+    uint32_t q_flags;   // query | row flags << 16
+    uint32_t row;
+    float scale;
+    uint32_t x1;
+    float rmag;
+};
 // rigorous re-evaluation + append of ONE (row, query) entry that passed the screen.  Called
 // divergently: every lane walks its own hits, so the latencies of the list reservations of a
 // chunk overlap instead of queueing up column by column.
-__device__ __noinline__ void tc_keep_entry(const TcGemmParams &p, const TcQueryMeta *qmeta_s,
-                                           uint32_t q, int I, uint32_t row, const RowMeta &m,
-                                           uint32_t tau_ord, bool phase0) {
-    const TcQueryMeta &qm = qmeta_s[q];
+__device__ __noinline__ void tc_keep_entry(const TcGemmParams &p, uint32_t q, int I, uint32_t row,
+                                           const RowMeta &m, uint32_t tau_ord, bool phase0) {
+    const TcQueryMeta qm = p.qmeta[q];
     if (qm.flags & kTcFlagUnusable) return;
     uint32_t lb_ord, ub_ord;
     tc_interval(p.metric, I, m, qm, p.dim, lb_ord, ub_ord);
@@ -528,13 +547,16 @@ tc_gemm_filter_kernel(const __grid_constant__ CUtensorMap tmap_a,
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t *st_a = smem;
-    uint8_t *st_b = smem + kTcStages * kTcABytes;
-    float4 *coef_s = reinterpret_cast<float4 *>(st_b + kTcStages * kTcBBytesMax);
+    uint8_t *st_b = smem + kTcStagesA * kTcABytes;
+    float4 *coef_s = reinterpret_cast<float4 *>(st_b + kTcStagesB * kTcBBytesMax);
     float4 *cmin_s = coef_s + kTcMaxQ;             // [16] per 16-query chunk: min w, min u, min v
-    TcQueryMeta *qmeta_s = reinterpret_cast<TcQueryMeta *>(cmin_s + kTcMaxQ / 16u);  // [256]
-    uint64_t *full_bar = reinterpret_cast<uint64_t *>(qmeta_s + kTcMaxQ);
-    uint64_t *empty_bar = full_bar + kTcStages;
-    uint64_t *tfull_bar = empty_bar + kTcStages;   // [2] accumulator ready
+    TcPend *pend_s = reinterpret_cast<TcPend *>(cmin_s + kTcMaxQ / 16u);  // [warps][kTcPendCap]
+    uint32_t *pend_cnt_s = reinterpret_cast<uint32_t *>(pend_s + kTcEpilogueWarps * kTcPendCap);
+    uint64_t *full_a = reinterpret_cast<uint64_t *>(pend_cnt_s + kTcEpilogueWarps);
+    uint64_t *empty_a = full_a + kTcStagesA;
+    uint64_t *full_b = empty_a + kTcStagesA;
+    uint64_t *empty_b = full_b + kTcStagesB;
+    uint64_t *tfull_bar = empty_b + kTcStagesB;    // [2] accumulator ready
     uint64_t *tempty_bar = tfull_bar + 2;          // [2] accumulator drained
     uint32_t *tmem_base_s = reinterpret_cast<uint32_t *>(tempty_bar + 2);
 
@@ -545,9 +567,13 @@ tc_gemm_filter_kernel(const __grid_constant__ CUtensorMap tmap_a,
     const uint32_t n_kb = (p.dim + kTcKBytes - 1) / kTcKBytes;
 
     if (tid == 0) {
-        for (uint32_t s = 0; s < kTcStages; ++s) {
-            mbar_init(&full_bar[s], 1);
-            mbar_init(&empty_bar[s], 1);
+        for (uint32_t s = 0; s < kTcStagesA; ++s) {
+            mbar_init(&full_a[s], 1);
+            mbar_init(&empty_a[s], 1);
+        }
+        for (uint32_t s = 0; s < kTcStagesB; ++s) {
+            mbar_init(&full_b[s], 1);
+            mbar_init(&empty_b[s], 1);
         }
         for (uint32_t a = 0; a < 2; ++a) {
             mbar_init(&tfull_bar[a], 1);
@@ -576,8 +602,7 @@ tc_gemm_filter_kernel(const __grid_constant__ CUtensorMap tmap_a,
             }
             coef_s[i] = c;
         }
-        for (uint32_t i = tid; i < p.nq * (uint32_t)(sizeof(TcQueryMeta) / 16u); i += kTcThreads)
-            reinterpret_cast<uint4 *>(qmeta_s)[i] = reinterpret_cast<const uint4 *>(p.qmeta)[i];
+        if (tid < kTcEpilogueWarps) pend_cnt_s[tid] = 0u;
     }
     __syncthreads();
     if (tid < kTcMaxQ / 16u) {
@@ -598,22 +623,40 @@ tc_gemm_filter_kernel(const __grid_constant__ CUtensorMap tmap_a,
     const uint32_t tmem_base = *tmem_base_s;
 
     if (warp == 0) {
-        // ===== TMA producer =====
+        // ===== TMA producer, corpus tiles: streams from HBM, runs up to kTcStagesA k-blocks
+        //       ahead (the bytes in flight per SM are what bounds the achieved HBM rate) =====
         if (lane == 0) {
             const uint64_t pol_a = p.evict_first ? policy_evict_first() : policy_evict_normal();
-            const uint64_t pol_q = policy_evict_normal();
-            const uint32_t tx = kTcABytes + p.n_pad * kTcKBytes;
             uint32_t stage = 0, phase = 0;
             for (uint32_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
                 const int32_t row0 = (int32_t)(row_begin + t * kTcM);
                 for (uint32_t kb = 0; kb < n_kb; ++kb) {
-                    mbar_wait_wd(&empty_bar[stage], phase ^ 1u);
-                    mbar_arrive_expect_tx(&full_bar[stage], tx);
+                    mbar_wait_wd<96>(&empty_a[stage], phase ^ 1u);
+                    mbar_arrive_expect_tx(&full_a[stage], kTcABytes);
                     tma_load_2d(st_a + stage * kTcABytes, &tmap_a, (int32_t)(kb * kTcKBytes), row0,
-                                &full_bar[stage], pol_a);
+                                &full_a[stage], pol_a);
+                    if (++stage == kTcStagesA) {
+                        stage = 0;
+                        phase ^= 1u;
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 2) {
+        // ===== TMA producer, query tiles: the same dim/128 boxes for every corpus tile, served
+        //       from L2 =====
+        if (lane == 0) {
+            const uint64_t pol_q = policy_evict_normal();
+            const uint32_t tx = p.n_pad * kTcKBytes;
+            uint32_t stage = 0, phase = 0;
+            for (uint32_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+                for (uint32_t kb = 0; kb < n_kb; ++kb) {
+                    mbar_wait_wd<96>(&empty_b[stage], phase ^ 1u);
+                    mbar_arrive_expect_tx(&full_b[stage], tx);
                     tma_load_2d(st_b + stage * kTcBBytesMax, &tmap_q, (int32_t)(kb * kTcKBytes), 0,
-                                &full_bar[stage], pol_q);
-                    if (++stage == kTcStages) {
+                                &full_b[stage], pol_q);
+                    if (++stage == kTcStagesB) {
                         stage = 0;
                         phase ^= 1u;
                     }
@@ -625,25 +668,31 @@ tc_gemm_filter_kernel(const __grid_constant__ CUtensorMap tmap_a,
         // ===== MMA issuer: one thread =====
         if (lane == 0) {
             const uint32_t idesc = tc_idesc_i8(kTcM, p.n_pad);
-            uint32_t stage = 0, phase = 0, it = 0;
+            uint32_t sa = 0, pa = 0, sb = 0, pb = 0, it = 0;
             for (uint32_t t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
                 const uint32_t acc = it & 1u, aph = (it >> 1) & 1u;
-                mbar_wait_wd(&tempty_bar[acc], aph ^ 1u);
+                mbar_wait_wd<32>(&tempty_bar[acc], aph ^ 1u);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * kTcMaxQ;
                 for (uint32_t kb = 0; kb < n_kb; ++kb) {
-                    mbar_wait_wd(&full_bar[stage], phase);
+                    mbar_wait_wd<0>(&full_b[sb], pb);
+                    mbar_wait_wd<0>(&full_a[sa], pa);
                     tc_fence_after();
-                    const uint64_t adesc = tc_smem_desc(smem_u32(st_a + stage * kTcABytes));
-                    const uint64_t bdesc = tc_smem_desc(smem_u32(st_b + stage * kTcBBytesMax));
+                    const uint64_t adesc = tc_smem_desc(smem_u32(st_a + sa * kTcABytes));
+                    const uint64_t bdesc = tc_smem_desc(smem_u32(st_b + sb * kTcBBytesMax));
 #pragma unroll
                     for (uint32_t ks = 0; ks < kTcKBytes / 32u; ++ks)  // UMMA K = 32 int8 = 32 B
                         tc_mma_i8(d_tmem, adesc + 2ull * ks, bdesc + 2ull * ks, idesc,
                                   (kb | ks) != 0u ? 1u : 0u);
-                    tc_commit(&empty_bar[stage]);  // frees the stage once these MMAs retire
-                    if (++stage == kTcStages) {
-                        stage = 0;
-                        phase ^= 1u;
+                    tc_commit(&empty_a[sa]);  // both stages are free once these MMAs retire
+                    tc_commit(&empty_b[sb]);
+                    if (++sa == kTcStagesA) {
+                        sa = 0;
+                        pa ^= 1u;
+                    }
+                    if (++sb == kTcStagesB) {
+                        sb = 0;
+                        pb ^= 1u;
                     }
                 }
                 tc_commit(&tfull_bar[acc]);
@@ -654,11 +703,13 @@ tc_gemm_filter_kernel(const __grid_constant__ CUtensorMap tmap_a,
         // ===== epilogue: warp w owns TMEM lanes 32 (w % 4) .. +31; the two warps of a lane
         //       quarter split the query columns =====
         const uint32_t qd = warp & 3u;
-        const uint32_t part = (warp - 2u) >> 2;  // chunks part, part + kTcColParts, ...
+        const uint32_t part = (warp - kTcRoleWarps) >> 2;  // chunks part, part + kTcColParts, ...
         const uint32_t n_chunks = (p.nq + 15u) / 16u;
         const float sc = __uint_as_float((127u - p.shift) << 23);
         const int sh = (int)p.shift;
         const bool phase0 = row_begin == 0u;
+        TcPend *pq = pend_s + (warp - kTcRoleWarps) * kTcPendCap;
+        uint32_t *pcnt = pend_cnt_s + (warp - kTcRoleWarps);
         auto load_meta = [&](uint32_t r, bool ok) {
             float4 raw = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
             if (ok) raw = __ldg(reinterpret_cast<const float4 *>(p.meta + r));
@@ -694,7 +745,7 @@ tc_gemm_filter_kernel(const __grid_constant__ CUtensorMap tmap_a,
             // a huge lhs
             const float brs = __fmul_ru(br, sc);
             const int add_r = (brs < 2000000.0f) ? 0x4B400000 + (__float2int_ru(brs) + 5) : 0x7f000000;
-            if (lane == 0) mbar_wait_wd(&tfull_bar[acc], aph);
+            if (lane == 0) mbar_wait_wd<64>(&tfull_bar[acc], aph);
             __syncwarp();
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((qd * 32u) << 16) + acc * kTcMaxQ;
@@ -732,8 +783,20 @@ tc_gemm_filter_kernel(const __grid_constant__ CUtensorMap tmap_a,
                     while (mask) {
                         const uint32_t j = __ffs(mask) - 1u;
                         mask &= mask - 1u;
-                        tc_keep_entry(p, qmeta_s, c0 + j, tmp[j], row, m,
-                                      __float_as_uint(coef_s[c0 + j].w), phase0);
+                        const uint32_t slot = atomicAdd(pcnt, 1u);
+                        if (slot < kTcPendCap) {
+                            TcPend e;
+                            e.I = tmp[j];
+                            e.q_flags = (c0 + j) | (m.flags << 16);
+                            e.row = row;
+                            e.scale = m.scale;
+                            e.x1 = m.x1;
+                            e.rmag = m.rmag;
+                            pq[slot] = e;
+                        } else {  // queue full (early phases keep most entries): evaluate now
+                            tc_keep_entry(p, c0 + j, tmp[j], row, m,
+                                          __float_as_uint(coef_s[c0 + j].w), phase0);
+                        }
                     }
                 }
             };
@@ -764,6 +827,21 @@ tc_gemm_filter_kernel(const __grid_constant__ CUtensorMap tmap_a,
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+            // the accumulator is back with the MMA issuer: now the parked entries, one per lane
+            const uint32_t n_pend = min(*pcnt, kTcPendCap);
+            for (uint32_t e = lane; e < n_pend; e += 32u) {
+                const TcPend pe = pq[e];
+                RowMeta rm;
+                rm.scale = pe.scale;
+                rm.x1 = pe.x1;
+                rm.rmag = pe.rmag;
+                rm.flags = pe.q_flags >> 16;
+                const uint32_t qq = pe.q_flags & 0xffffu;
+                tc_keep_entry(p, qq, pe.I, pe.row, rm, __float_as_uint(coef_s[qq].w), phase0);
+            }
+            __syncwarp();
+            if (lane == 0) *pcnt = 0u;
+            __syncwarp();
         }
     }
     tc_fence_before();
