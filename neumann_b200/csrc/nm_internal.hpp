@@ -99,6 +99,8 @@ struct Workspace {
     size_t tc_nq_cap = 0;           // queries
     void *d_tc_kept = nullptr;      // [256][kTcKeptCap] nm::TcKept
     uint64_t *d_tc_keys = nullptr;  // [256][kTcKeptCap]
+    uint32_t *d_tc_bucket = nullptr;  // row-bucket counters / cursors of the re-score ordering
+    void *d_tc_sorted = nullptr;      // [256 * kTcKeptCap] uint2 {row, query << 16 | slot}
     // batched-query path (batch_kernels.cuh)
     float *d_qt = nullptr;         // [n_kc][32][QB] transposed query chunks
     size_t qt_cap = 0;             // floats
@@ -133,6 +135,8 @@ struct Workspace {
         if (d_tc_kept_n) cudaFree(d_tc_kept_n);
         if (d_tc_kept) cudaFree(d_tc_kept);
         if (d_tc_keys) cudaFree(d_tc_keys);
+        if (d_tc_bucket) cudaFree(d_tc_bucket);
+        if (d_tc_sorted) cudaFree(d_tc_sorted);
         if (d_qt) cudaFree(d_qt);
         if (d_qmag) cudaFree(d_qmag);
         if (d_scores) cudaFree(d_scores);

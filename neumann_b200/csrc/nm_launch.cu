@@ -439,6 +439,7 @@ int launch_prefiltered(nm_index *idx, const Shard &sh, Workspace &ws, const floa
 }
 
 // ---- tensor-core batch pre-filter (tc_prefilter_kernels.cuh) ------------------------------
+constexpr uint32_t kTcSortBuckets = 65536;  // row buckets of the re-score ordering
 constexpr uint32_t kTcMinRows = 2 * nm::kTcKeptCap;  // below this the exact kernels are cheaper
 
 bool tc_usable(const nm_index *idx, const Shard &sh, uint32_t nq, uint32_t k, int metric,
@@ -496,6 +497,8 @@ static int ws_ensure_tc(Workspace &ws, uint32_t dim, uint32_t nq, cudaStream_t s
         ws.tc_nq_cap = cap;
     }
     if (!ws.d_tc_kept) {
+        CUDA_TRY(cudaMalloc(&ws.d_tc_bucket, (size_t)(kTcSortBuckets + 2) * sizeof(uint32_t)));
+        CUDA_TRY(cudaMalloc(&ws.d_tc_sorted, (size_t)nm::kTcMaxQ * nm::kTcKeptCap * sizeof(uint2)));
         CUDA_TRY(cudaMalloc(&ws.d_tc_kept, (size_t)nm::kTcMaxQ * nm::kTcKeptCap * sizeof(nm::TcKept)));
         CUDA_TRY(cudaMalloc(&ws.d_tc_keys, (size_t)nm::kTcMaxQ * nm::kTcKeptCap * sizeof(uint64_t)));
     }
@@ -613,8 +616,35 @@ int scan_queries_tc(nm_index *idx, const Shard &sh, Workspace &ws, const float *
         sp.k = k_eff;
         sp.out_stride = k;
         sp.metric = kmetric;
-        nm::tc_rescore_kernel<<<nqp, nm::kRowsPerBlock, (size_t)dim * 4, stream>>>(sp);
-        CUDA_TRY(cudaGetLastError());
+        if (dim % 4u == 0u && (size_t)nqp <= 0xffffu) {
+            // survivors of all queries, re-scored in corpus order (see tc_score_sorted_kernel)
+            nm::TcSortParams so;
+            memset(&so, 0, sizeof(so));
+            so.kept = kept;
+            so.kept_n = aux.kept_n + q0;
+            so.bucket = ws.d_tc_bucket;
+            so.sorted = static_cast<uint2 *>(ws.d_tc_sorted);
+            so.total = ws.d_tc_bucket + kTcSortBuckets + 1;
+            so.shift = 8;
+            while (((uint64_t)rows >> so.shift) + 1 > kTcSortBuckets) ++so.shift;
+            so.n_buckets = (uint32_t)(((uint64_t)rows >> so.shift) + 1);
+            CUDA_TRY(cudaMemsetAsync(so.bucket, 0, (size_t)(so.n_buckets + 1) * sizeof(uint32_t), stream));
+            nm::tc_sort_count_kernel<<<nqp, 256, 0, stream>>>(so);
+            CUDA_TRY(cudaGetLastError());
+            nm::tc_sort_scan_kernel<<<1, 1024, 0, stream>>>(so);
+            CUDA_TRY(cudaGetLastError());
+            nm::tc_sort_scatter_kernel<<<nqp, 256, 0, stream>>>(so);
+            CUDA_TRY(cudaGetLastError());
+            nm::tc_score_sorted_kernel<<<(uint32_t)sh.sm_count * 8u, 256, 0, stream>>>(sp, so.sorted,
+                                                                                      so.total);
+            CUDA_TRY(cudaGetLastError());
+            nm::tc_select_kernel<<<nqp, nm::kRowsPerBlock, 0, stream>>>(sp);
+            CUDA_TRY(cudaGetLastError());
+            idx->scan_launches += 4;
+        } else {
+            nm::tc_rescore_kernel<<<nqp, nm::kRowsPerBlock, (size_t)dim * 4, stream>>>(sp);
+            CUDA_TRY(cudaGetLastError());
+        }
         idx->scan_launches += 2 + 2 * kTcMaxPhases;
     }
     // flags, phase control and statistics come back with the results

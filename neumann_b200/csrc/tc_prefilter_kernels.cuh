@@ -1103,6 +1103,36 @@ struct TcRescoreParams {
     int metric;
 };
 
+// final selection of one query over its exact keys (all 256 threads of the CTA)
+__device__ __forceinline__ void tc_select_query(const TcRescoreParams &p, uint32_t q, uint32_t n,
+                                                uint64_t *buf, uint64_t *thr_s, uint32_t *cnt_s,
+                                                uint32_t *hist, uint32_t t) {
+    const uint64_t *keys = p.exact_keys + (size_t)q * kTcKeptCap;
+    if (t == 0 && p.stats) atomicAdd(p.stats, n);
+    TopKState st;
+    st.buf = buf;
+    st.cnt_smem = cnt_s;
+    st.thr_smem = thr_s;
+    st.count = 0;
+    st.k = p.k;
+    st.cap = kCandCap;
+    MergeScratch ms;
+    ms.hist = hist;
+    ms.sc = hist + 256;
+    merge_published(st, t, keys, n, p.k, ms);
+    TopKOutputs o;
+    o.out_keys = nullptr;
+    o.out_hits = nullptr;
+    o.out_rows = p.out_rows + (size_t)q * p.out_stride;
+    o.out_scores = p.out_scores + (size_t)q * p.out_stride;
+    o.out_count = p.out_counts + q;
+    o.row_base = p.row_base;
+    o.accumulate_count = 0;
+    write_outputs(st, t, p.k, o);
+}
+
+// Per-query re-score (query in shared memory, rows in list order).  Only used when the query
+// rows are not 16-byte aligned (dim % 4 != 0); see tc_score_sorted_kernel for the fast path.
 __global__ void __launch_bounds__(kRowsPerBlock) tc_rescore_kernel(const TcRescoreParams p) {
     extern __shared__ __align__(16) float q_s[];  // [dim]
     __shared__ __align__(16) uint64_t buf[kCandCap];
@@ -1132,27 +1162,98 @@ __global__ void __launch_bounds__(kRowsPerBlock) tc_rescore_kernel(const TcResco
     }
     __threadfence();
     __syncthreads();
-    if (t == 0 && p.stats) atomicAdd(p.stats, n);
-    TopKState st;
-    st.buf = buf;
-    st.cnt_smem = &cnt_s;
-    st.thr_smem = &thr_s;
-    st.count = 0;
-    st.k = p.k;
-    st.cap = kCandCap;
-    MergeScratch ms;
-    ms.hist = hist;
-    ms.sc = hist + 256;
-    merge_published(st, t, keys, n, p.k, ms);
-    TopKOutputs o;
-    o.out_keys = nullptr;
-    o.out_hits = nullptr;
-    o.out_rows = p.out_rows + (size_t)q * p.out_stride;
-    o.out_scores = p.out_scores + (size_t)q * p.out_stride;
-    o.out_count = p.out_counts + q;
-    o.row_base = p.row_base;
-    o.accumulate_count = 0;
-    write_outputs(st, t, p.k, o);
+    tc_select_query(p, q, n, buf, &thr_s, &cnt_s, hist, t);
+}
+
+// ---- fast path: survivors of ALL queries re-scored in corpus order --------------------------
+// The survivors of one query are spread over the whole mirror (tens of GB): co-resident threads
+// that each walk a different far-away row touch hundreds of pages per SM, and the gather runs
+// at ~1.2 TB/s (scripts/mb_gather.cu: address translation, not DRAM, is the limit).  Ordered by
+// row, neighbouring threads walk neighbouring rows and the same gather reaches ~4.3 TB/s.  So:
+// counting sort of the (row, query, slot) triples by row bucket, then one thread per sorted
+// entry (its query read through L1/L2), then the per-query selection.
+struct TcSortParams {
+    const TcKept *kept;
+    const uint32_t *kept_n;
+    uint32_t *bucket;      // [n_buckets + 1] counts, then cursors
+    uint2 *sorted;         // {row, query << 16 | slot}
+    uint32_t *total;       // [1]
+    uint32_t n_buckets;
+    uint32_t shift;        // bucket = row >> shift
+};
+
+__global__ void __launch_bounds__(256) tc_sort_count_kernel(const TcSortParams p) {
+    const uint32_t q = blockIdx.x;
+    const uint32_t n = min(p.kept_n[q], kTcKeptCap);
+    const TcKept *list = p.kept + (size_t)q * kTcKeptCap;
+    for (uint32_t i = threadIdx.x; i < n; i += 256u) atomicAdd(&p.bucket[list[i].row >> p.shift], 1u);
+}
+
+__global__ void __launch_bounds__(1024) tc_sort_scan_kernel(const TcSortParams p) {
+    __shared__ uint32_t part[1024];
+    const uint32_t t = threadIdx.x;
+    const uint32_t per = (p.n_buckets + 1023u) / 1024u;
+    const uint32_t lo = min(t * per, p.n_buckets), hi = min(lo + per, p.n_buckets);
+    uint32_t sum = 0;
+    for (uint32_t b = lo; b < hi; ++b) sum += p.bucket[b];
+    part[t] = sum;
+    __syncthreads();
+    for (uint32_t off = 1; off < 1024u; off <<= 1) {  // inclusive scan of the per-thread sums
+        const uint32_t v = t >= off ? part[t - off] : 0u;
+        __syncthreads();
+        part[t] += v;
+        __syncthreads();
+    }
+    uint32_t run = part[t] - sum;
+    for (uint32_t b = lo; b < hi; ++b) {
+        const uint32_t c = p.bucket[b];
+        p.bucket[b] = run;  // exclusive offset: the scatter kernel's cursor
+        run += c;
+    }
+    if (t == 1023u) *p.total = part[1023];
+}
+
+__global__ void __launch_bounds__(256) tc_sort_scatter_kernel(const TcSortParams p) {
+    const uint32_t q = blockIdx.x;
+    const uint32_t n = min(p.kept_n[q], kTcKeptCap);
+    const TcKept *list = p.kept + (size_t)q * kTcKeptCap;
+    for (uint32_t i = threadIdx.x; i < n; i += 256u) {
+        const uint32_t row = list[i].row;
+        const uint32_t pos = atomicAdd(&p.bucket[row >> p.shift], 1u);
+        p.sorted[pos] = make_uint2(row, (q << 16) | i);
+    }
+}
+
+__global__ void __launch_bounds__(256) tc_score_sorted_kernel(const TcRescoreParams p,
+                                                             const uint2 *__restrict__ sorted,
+                                                             const uint32_t *__restrict__ total) {
+    const uint32_t n = *total;
+    for (uint32_t e = blockIdx.x * 256u + threadIdx.x; e < n; e += gridDim.x * 256u) {
+        const uint2 ent = sorted[e];
+        const uint32_t row = ent.x, q = ent.y >> 16, i = ent.y & 0xffffu;
+        const float *x = p.rows + (size_t)row * p.pitch;
+        const float *qv = p.queries + (size_t)q * p.dim;  // 16-byte aligned: dim % 4 == 0
+        const float qmag = p.qmeta[q].qmag;
+        float s;
+        if (p.metric == kEuclidean) s = tc_score_row<kEuclidean>(qv, x, p.dim, qmag);
+        else if (p.metric == kCosine) s = tc_score_row<kCosine>(qv, x, p.dim, qmag);
+        else s = tc_score_row<kDot>(qv, x, p.dim, qmag);
+        p.exact_keys[(size_t)q * kTcKeptCap + i] = make_key(__float_as_uint(s), row);
+    }
+}
+
+__global__ void __launch_bounds__(kRowsPerBlock) tc_select_kernel(const TcRescoreParams p) {
+    __shared__ __align__(16) uint64_t buf[kCandCap];
+    __shared__ uint64_t thr_s;
+    __shared__ uint32_t cnt_s;
+    __shared__ uint32_t hist[256 + 16];
+    const uint32_t q = blockIdx.x, t = threadIdx.x;
+    if (t == 0) {
+        thr_s = 0ull;
+        cnt_s = 0u;
+    }
+    __syncthreads();
+    tc_select_query(p, q, min(p.kept_n[q], kTcKeptCap), buf, &thr_s, &cnt_s, hist, t);
 }
 
 #endif  // __CUDACC__
