@@ -518,7 +518,9 @@ int scan_queries_tc(nm_index *idx, const Shard &sh, Workspace &ws, const float *
     {
         std::lock_guard<std::mutex> g(mu);
         if (sh.device >= 64 || !configured[sh.device]) {
-            CUDA_TRY(cudaFuncSetAttribute(nm::tc_gemm_filter_kernel,
+            CUDA_TRY(cudaFuncSetAttribute(nm::tc_gemm_filter_kernel<1>,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            CUDA_TRY(cudaFuncSetAttribute(nm::tc_gemm_filter_kernel<2>,
                                           cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
             CUDA_TRY(cudaFuncSetAttribute(nm::tc_rescore_kernel,
                                           cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
@@ -543,19 +545,25 @@ int scan_queries_tc(nm_index *idx, const Shard &sh, Workspace &ws, const float *
     CUDA_TRY(cudaMemsetAsync(aux.stats, 0, 8 * sizeof(uint32_t), stream));
     const int kmetric = metric == NM_COSINE ? nm::kCosine
                                             : (metric == NM_EUCLIDEAN ? nm::kEuclidean : nm::kDot);
-    const uint32_t max_tiles = (rows + nm::kTcM - 1) / nm::kTcM;
-    const uint32_t grid = std::min<uint32_t>((uint32_t)sh.sm_count, max_tiles);
+    // cta_group::2 (pairs of CTAs on one 256-row super tile) unless NM_TC_PAIR=0
+    static const bool pair = [] {
+        const char *e = getenv("NM_TC_PAIR");
+        return !(e && e[0] == '0');
+    }();
+    const uint32_t ctas = pair ? 2u : 1u;
+    const uint32_t max_tiles = (rows + nm::kTcM * ctas - 1) / (nm::kTcM * ctas);
+    const uint32_t grid = ctas * std::min<uint32_t>((uint32_t)sh.sm_count / ctas, max_tiles);
     uint32_t pass = 0;
     for (uint32_t q0 = 0; q0 < nq; q0 += nm::kTcMaxQ, ++pass) {
         const uint32_t nqp = std::min<uint32_t>(nm::kTcMaxQ, nq - q0);
-        const uint32_t n_pad = (nqp + 15u) & ~15u;
+        const uint32_t n_pad = pair ? ((nqp + 31u) & ~31u) : ((nqp + 15u) & ~15u);  // UMMA N
         nm::TcCtl *ctl = aux.ctl + pass;
         nm::tc_prepare_queries_kernel<<<n_pad, 256, 0, stream>>>(
             d_queries + (size_t)q0 * dim, nqp, dim, pitch8, ws.d_tc_q8, qmeta + q0, coef + q0,
             aux.kept_n + q0, aux.kept_prev + q0, ctl, rows);
         CUDA_TRY(cudaGetLastError());
         CUtensorMap tmap_q;
-        rc = encode_tmap_u8(&tmap_q, ws.d_tc_q8, dim, n_pad, pitch8, 128, n_pad);
+        rc = encode_tmap_u8(&tmap_q, ws.d_tc_q8, dim, n_pad, pitch8, 128, n_pad / ctas);
         if (rc) return rc;
         nm::TcGemmParams gp;
         memset(&gp, 0, sizeof(gp));
@@ -592,8 +600,24 @@ int scan_queries_tc(nm_index *idx, const Shard &sh, Workspace &ws, const float *
         rp.k = k_eff;
         rp.metric = kmetric;
         for (uint32_t ph = 0; ph < kTcMaxPhases; ++ph) {
-            nm::tc_gemm_filter_kernel<<<grid, nm::kTcThreads, nm::tc_gemm_smem_bytes(), stream>>>(
-                sh.tmap8_tc, tmap_q, gp);
+            if (pair) {
+                cudaLaunchConfig_t cfg = {};
+                cfg.gridDim = dim3(grid);
+                cfg.blockDim = dim3(nm::kTcThreads);
+                cfg.dynamicSmemBytes = nm::tc_gemm_smem_bytes();
+                cfg.stream = stream;
+                cudaLaunchAttribute attr[1];
+                attr[0].id = cudaLaunchAttributeClusterDimension;
+                attr[0].val.clusterDim.x = 2;
+                attr[0].val.clusterDim.y = 1;
+                attr[0].val.clusterDim.z = 1;
+                cfg.attrs = attr;
+                cfg.numAttrs = 1;
+                CUDA_TRY(cudaLaunchKernelEx(&cfg, nm::tc_gemm_filter_kernel<2>, sh.tmap8_tc, tmap_q, gp));
+            } else {
+                nm::tc_gemm_filter_kernel<1><<<grid, nm::kTcThreads, nm::tc_gemm_smem_bytes(), stream>>>(
+                    sh.tmap8_tc, tmap_q, gp);
+            }
             CUDA_TRY(cudaGetLastError());
             nm::tc_refine_kernel<<<nqp, 256, (size_t)dim * 4, stream>>>(rp);
             CUDA_TRY(cudaGetLastError());

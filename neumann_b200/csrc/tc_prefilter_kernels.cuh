@@ -47,18 +47,25 @@ namespace nm {
 constexpr uint32_t kTcM = 128;                             // corpus rows per tile == TMEM lanes
 constexpr uint32_t kTcKBytes = 128;                        // int8 elements per k-block
 constexpr uint32_t kTcMaxQ = 256;                          // queries per pass == UMMA N max
-constexpr uint32_t kTcStagesA = 6;                         // corpus tiles (from HBM: deep ring)
-constexpr uint32_t kTcStagesB = 3;                         // query tiles (L2 resident: short ring)
+// One TMA ring; a stage = the corpus box + the query box of one k-block.  CTAS = 1: the CTA
+// stages all 256 queries (16 + 32 KiB, 4 stages).  CTAS = 2 (cta_group::2): the two CTAs of a
+// cluster each stage their own 128 corpus rows and HALF of the queries (16 + 16 KiB, 6 stages)
+// and one UMMA of M = 256 reads both halves, so the query bytes each SM pulls from L2 halve
+// and more k-blocks are in flight: the loop is bound by bytes in flight / memory latency.
+constexpr uint32_t kTcStages1 = 4;
+constexpr uint32_t kTcStages2 = 6;
+constexpr uint32_t kTcRingBytes = 192u * 1024u;
 constexpr uint32_t kTcABytes = kTcM * kTcKBytes;           // 16 KiB
 constexpr uint32_t kTcBBytesMax = kTcMaxQ * kTcKBytes;     // 32 KiB
 constexpr uint32_t kTcEpilogueWarps = 16;                  // 4 per TMEM lane quarter
 constexpr uint32_t kTcColParts = kTcEpilogueWarps / 4;     // they split the 16-query chunks
-constexpr uint32_t kTcRoleWarps = 3;                       // A producer, MMA issuer, B producer
+constexpr uint32_t kTcRoleWarps = 2;                       // TMA producer, MMA issuer
 constexpr uint32_t kTcThreads = 32 * (kTcRoleWarps + kTcEpilogueWarps);
 constexpr uint32_t kTcKeptCap = 32768;                     // kept entries per query
 constexpr uint32_t kTcPhase0Rows = 2048;                   // first phase: keep everything (>= k)
 constexpr uint32_t kTcTmemCols = 512;                      // 2 accumulators x 256 columns
-constexpr uint32_t kTcPendCap = 48;                        // parked entries per epilogue warp and tile
+constexpr uint32_t kTcPendCap = 48;                        // parked entries per epilogue warp
+constexpr uint32_t kTcPendDrain = 20;                      // drained once this many are parked
 
 constexpr uint32_t kTcFlagUnusable = 1u;   // query not finite / zero / denormal scale
 constexpr uint32_t kTcFlagOverflow = 2u;   // kept list overflowed
@@ -91,10 +98,19 @@ struct TcCtl {
     uint32_t pad[3];
 };
 
+// what the rigorous evaluation needs of a query: the first 32 bytes of TcQueryMeta, staged in
+// shared memory by the GEMM kernel
+struct alignas(16) TcQm {
+    double c_lo, c_hi;
+    float s_q;
+    float qmag;
+    uint32_t q1;
+    uint32_t flags;
+};
+
 inline size_t tc_gemm_smem_bytes() {
-    return 1024 + (size_t)kTcStagesA * kTcABytes + (size_t)kTcStagesB * kTcBBytesMax +
-           (size_t)kTcMaxQ * 16 + 256 +
-           (size_t)kTcEpilogueWarps * (kTcPendCap * 24 + 4) + 256;
+    return 1024 + (size_t)kTcRingBytes + (size_t)kTcMaxQ * 16 + 256 +
+           (size_t)kTcEpilogueWarps * (kTcPendCap * 24 + 4) + (size_t)kTcMaxQ * 32 + 256;
 }
 
 #ifdef __CUDACC__
@@ -134,6 +150,57 @@ __device__ __forceinline__ void mbar_wait_wd(uint64_t *bar, uint32_t parity) {
         }
     }
 }
+// ---- thread-block cluster helpers (cta_group::2) ----
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of the same shared-memory offset in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_shared(uint32_t saddr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr)
+                 : "memory");
+}
+// TMA load of a cta_group::2 pair: data lands in THIS CTA's shared memory, the bytes are
+// counted on the barrier at `bar_cluster_addr` (the leader CTA's)
+__device__ __forceinline__ void tma_load_2d_pair(void *dst, const CUtensorMap *tmap, int32_t x,
+                                                 int32_t y, uint32_t bar_cluster_addr,
+                                                 uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+        ".L2::cache_hint [%0], [%1, {%2, %3}], [%4], %5;" ::"r"(smem_u32(dst)),
+        "l"(tmap), "r"(x), "r"(y), "r"(bar_cluster_addr), "l"(policy)
+        : "memory");
+}
+__device__ __forceinline__ void tc_mma_i8_pair(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc,
+                                               uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(d_tmem),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// commit of the pair's MMAs: arrives on the barrier at this offset in BOTH CTAs
+__device__ __forceinline__ void tc_commit_pair(uint64_t *bar) {
+    asm volatile(
+        "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 "
+        "[%0], %1;" ::"r"(smem_u32(bar)),
+        "h"((uint16_t)3)
+        : "memory");
+}
+
 // K-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout):
 // [0,14) start address >> 4, [16,30) leading byte offset >> 4 (1: unused for swizzled
 // K-major), [32,46) stride byte offset >> 4 (1024 B = 8 rows x 128 B), [46,48) version = 1,
@@ -213,8 +280,9 @@ __device__ __forceinline__ void tc_row_sq_bounds(const RowMeta &m, uint32_t dim,
 
 // Rigorous interval of the reference score of (row, query) from the exact integer dot I.
 // wild == the analysis does not apply (non-finite data, possible overflow): always a candidate.
+template <class QM>
 __device__ __forceinline__ void tc_interval(int metric, int I, const RowMeta &m,
-                                            const TcQueryMeta &qm, uint32_t dim, uint32_t &lb_ord,
+                                            const QM &qm, uint32_t dim, uint32_t &lb_ord,
                                             uint32_t &ub_ord) {
     bool wild = (m.flags & 1u) != 0u || (qm.flags & kTcFlagUnusable) != 0u;
     const double g = 2.0 * ((double)dim + 16.0) * kTcU;
@@ -335,11 +403,25 @@ __device__ __forceinline__ float4 tc_make_coef(int metric, uint32_t tau_ord, con
                        __uint_as_float(tau_ord));
 }
 
-// per-row screen coefficients (alpha, beta, Br)
-__device__ __forceinline__ void tc_row_coef(int metric, const RowMeta &m, uint32_t dim, float &alpha,
-                                            float &beta, float &br) {
+// per-row screen coefficients (alpha, beta, Br), f32 with directed rounding (runs once per row
+// and tile in every epilogue thread).  rc: per-launch constants from tc_row_consts.
+struct TcRowConsts {
+    float one_minus_rel;   // 1 - rel of tc_row_sq_bounds, rounded down
+    float cb;              // row part of the interval half-width per unit of x1, rounded up
+    float addc;            // I2F / rounding slack, rounded up
+};
+__device__ __forceinline__ TcRowConsts tc_row_consts(int metric, uint32_t dim) {
     const double g = 2.0 * ((double)dim + 16.0) * kTcU;
-    const double sr = (double)m.scale;
+    const double rel = ((double)(dim / 8u) + 24.0) * kTcU * 1.01;
+    const double cb = (metric == kEuclidean) ? kTcCB : 1.000002 * (0.5001 * (1.0 + g) + 127.51 * g);
+    TcRowConsts rc;
+    rc.one_minus_rel = __double2float_rd(1.0 - rel);
+    rc.cb = __double2float_ru(cb * (1.0 + kTcEpsR));
+    rc.addc = __double2float_ru(kTcEpsR * (16129.0 * (double)dim + 1.0));
+    return rc;
+}
+__device__ __forceinline__ void tc_row_coef(int metric, const RowMeta &m, const TcRowConsts &rc,
+                                            float &alpha, float &beta, float &br) {
     // tiny scales: the absolute slack terms (<= 4e-36 / (s_q s_r)) would no longer be covered
     if ((m.flags & 1u) || !(m.scale >= 1e-15f) || !(m.rmag < 3.0e38f)) {
         alpha = 0.0f;
@@ -347,20 +429,18 @@ __device__ __forceinline__ void tc_row_coef(int metric, const RowMeta &m, uint32
         br = INFINITY;  // always re-evaluated rigorously
         return;
     }
-    double cb;
     if (metric == kEuclidean) {
-        double a_lo, a_hi;
-        tc_row_sq_bounds(m, dim, a_lo, a_hi);
-        alpha = __double2float_rd(a_lo / (2.0 * sr) * (1.0 - kTcEpsR));
-        beta = (float)(1.0 / (2.0 * sr));
-        cb = kTcCB;
+        // alpha <= A_lo / (2 s_r) with A_lo as in tc_row_sq_bounds: every step rounds down
+        float a_lo = __fmul_rd(__fmul_rd(m.rmag, m.rmag), rc.one_minus_rel);
+        a_lo = fmaxf(__fsub_rd(a_lo, 1e-37f), 0.0f);
+        const float two_s = __fmul_rn(2.0f, m.scale);  // exact
+        alpha = __fmul_rd(__fmul_rd(a_lo, __frcp_rd(two_s)), 0.99999904f);  // (1 - 2^-20)
+        beta = __frcp_rn(two_s);
     } else {
         alpha = 0.0f;
-        beta = (metric == kCosine) ? (float)((double)m.rmag / sr) : (float)(1.0 / sr);
-        cb = 1.000002 * (0.5001 * (1.0 + g) + 127.51 * g);
+        beta = (metric == kCosine) ? __fdiv_rn(m.rmag, m.scale) : __frcp_rn(m.scale);
     }
-    br = __double2float_ru(cb * (double)m.x1 * (1.0 + kTcEpsR) +
-                           kTcEpsR * (16129.0 * (double)dim + 1.0));
+    br = __fmaf_ru(rc.cb, __uint2float_ru(m.x1), rc.addc);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -521,9 +601,10 @@ struct TcPend {
 // rigorous re-evaluation + append of ONE (row, query) entry that passed the screen.  Called
 // divergently: every lane walks its own hits, so the latencies of the list reservations of a
 // chunk overlap instead of queueing up column by column.
-__device__ __noinline__ void tc_keep_entry(const TcGemmParams &p, uint32_t q, int I, uint32_t row,
-                                           const RowMeta &m, uint32_t tau_ord, bool phase0) {
-    const TcQueryMeta qm = p.qmeta[q];
+__device__ __noinline__ void tc_keep_entry(const TcGemmParams &p, const TcQm *qm_s, uint32_t q,
+                                           int I, uint32_t row, const RowMeta &m, uint32_t tau_ord,
+                                           bool phase0) {
+    const TcQm &qm = qm_s[q];
     if (qm.flags & kTcFlagUnusable) return;
     uint32_t lb_ord, ub_ord;
     tc_interval(p.metric, I, m, qm, p.dim, lb_ord, ub_ord);
@@ -540,53 +621,64 @@ __device__ __noinline__ void tc_keep_entry(const TcGemmParams &p, uint32_t q, in
     }
 }
 
+// CTAS = 1: one CTA per 128-row tile.  CTAS = 2: launched in clusters of two; the pair owns a
+// 256-row super tile (CTA r: rows r*128..), CTA 0 (the leader) issues the MMAs for both.
+template <int CTAS>
 __global__ void __launch_bounds__(kTcThreads, 1)
 tc_gemm_filter_kernel(const __grid_constant__ CUtensorMap tmap_a,
                       const __grid_constant__ CUtensorMap tmap_q,
                       const __grid_constant__ TcGemmParams p) {
+    constexpr uint32_t kStages = CTAS == 2 ? kTcStages2 : kTcStages1;
+    constexpr uint32_t kStageBytes = kTcRingBytes / kStages;       // 48 KiB / 32 KiB
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    uint8_t *st_a = smem;
-    uint8_t *st_b = smem + kTcStagesA * kTcABytes;
-    float4 *coef_s = reinterpret_cast<float4 *>(st_b + kTcStagesB * kTcBBytesMax);
+    uint8_t *ring = smem;                                          // stage: [A 16 KiB][B ...]
+    float4 *coef_s = reinterpret_cast<float4 *>(ring + kTcRingBytes);
     float4 *cmin_s = coef_s + kTcMaxQ;             // [16] per 16-query chunk: min w, min u, min v
     TcPend *pend_s = reinterpret_cast<TcPend *>(cmin_s + kTcMaxQ / 16u);  // [warps][kTcPendCap]
     uint32_t *pend_cnt_s = reinterpret_cast<uint32_t *>(pend_s + kTcEpilogueWarps * kTcPendCap);
-    uint64_t *full_a = reinterpret_cast<uint64_t *>(pend_cnt_s + kTcEpilogueWarps);
-    uint64_t *empty_a = full_a + kTcStagesA;
-    uint64_t *full_b = empty_a + kTcStagesA;
-    uint64_t *empty_b = full_b + kTcStagesB;
-    uint64_t *tfull_bar = empty_b + kTcStagesB;    // [2] accumulator ready
+    TcQm *qm_s = reinterpret_cast<TcQm *>(pend_cnt_s + kTcEpilogueWarps);  // [256]
+    uint64_t *full_bar = reinterpret_cast<uint64_t *>(qm_s + kTcMaxQ);
+    uint64_t *empty_bar = full_bar + kTcStages2;
+    uint64_t *tfull_bar = empty_bar + kTcStages2;  // [2] accumulator ready
     uint64_t *tempty_bar = tfull_bar + 2;          // [2] accumulator drained
     uint32_t *tmem_base_s = reinterpret_cast<uint32_t *>(tempty_bar + 2);
 
     const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31u;
     const uint32_t row_begin = p.ctl->row_begin, row_end = min(p.ctl->row_end, p.n_rows);
     if (row_begin >= row_end) return;  // past the end of the corpus: nothing to do (uniform)
-    const uint32_t n_tiles = (row_end - row_begin + kTcM - 1) / kTcM;
+    const uint32_t cr = CTAS == 2 ? cluster_ctarank() : 0u;        // rank in the pair
+    const uint32_t unit = blockIdx.x / CTAS, n_units = gridDim.x / CTAS;  // pair / CTA index
+    constexpr uint32_t kTileRows = kTcM * CTAS;
+    const uint32_t n_tiles = (row_end - row_begin + kTileRows - 1) / kTileRows;
     const uint32_t n_kb = (p.dim + kTcKBytes - 1) / kTcKBytes;
+    const uint32_t n_b = p.n_pad / CTAS;           // query rows this CTA stages per k-block
 
     if (tid == 0) {
-        for (uint32_t s = 0; s < kTcStagesA; ++s) {
-            mbar_init(&full_a[s], 1);
-            mbar_init(&empty_a[s], 1);
-        }
-        for (uint32_t s = 0; s < kTcStagesB; ++s) {
-            mbar_init(&full_b[s], 1);
-            mbar_init(&empty_b[s], 1);
+        for (uint32_t s = 0; s < kStages; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
         }
         for (uint32_t a = 0; a < 2; ++a) {
             mbar_init(&tfull_bar[a], 1);
-            mbar_init(&tempty_bar[a], kTcEpilogueWarps);
+            mbar_init(&tempty_bar[a], kTcEpilogueWarps * CTAS);  // the leader's collects both CTAs
         }
         fence_mbar_init();
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
-                         smem_u32(tmem_base_s)),
-                     "r"(kTcTmemCols)
-                     : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if (CTAS == 2) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                             smem_u32(tmem_base_s)),
+                         "r"(kTcTmemCols)
+                         : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                             smem_u32(tmem_base_s)),
+                         "r"(kTcTmemCols)
+                         : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
     }
     {
         // the screen compares in units of 2^shift (exact power-of-two scaling) and with the
@@ -603,6 +695,9 @@ tc_gemm_filter_kernel(const __grid_constant__ CUtensorMap tmap_a,
             coef_s[i] = c;
         }
         if (tid < kTcEpilogueWarps) pend_cnt_s[tid] = 0u;
+        for (uint32_t i = tid; i < p.nq * 2u; i += kTcThreads)  // first 32 bytes of each record
+            reinterpret_cast<uint4 *>(qm_s)[i] =
+                reinterpret_cast<const uint4 *>(p.qmeta + (i >> 1))[i & 1u];
     }
     __syncthreads();
     if (tid < kTcMaxQ / 16u) {
@@ -618,45 +713,40 @@ tc_gemm_filter_kernel(const __grid_constant__ CUtensorMap tmap_a,
         cmin_s[tid] = mn;
     }
     tc_fence_before();
-    __syncthreads();
+    if (CTAS == 2) cluster_sync_all();  // barriers initialised in both CTAs before any remote use
+    else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_base_s;
+    // the leader's barriers as seen from this CTA (identity for the leader / 1-CTA)
+    const uint32_t lead_full0 = CTAS == 2 ? mapa_shared(smem_u32(&full_bar[0]), 0u) : 0u;
+    const uint32_t lead_tempty0 = CTAS == 2 ? mapa_shared(smem_u32(&tempty_bar[0]), 0u) : 0u;
 
     if (warp == 0) {
-        // ===== TMA producer, corpus tiles: streams from HBM, runs up to kTcStagesA k-blocks
-        //       ahead (the bytes in flight per SM are what bounds the achieved HBM rate) =====
+        // ===== TMA producer: this CTA's corpus rows and its share of the queries =====
         if (lane == 0) {
             const uint64_t pol_a = p.evict_first ? policy_evict_first() : policy_evict_normal();
-            uint32_t stage = 0, phase = 0;
-            for (uint32_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-                const int32_t row0 = (int32_t)(row_begin + t * kTcM);
-                for (uint32_t kb = 0; kb < n_kb; ++kb) {
-                    mbar_wait_wd<96>(&empty_a[stage], phase ^ 1u);
-                    mbar_arrive_expect_tx(&full_a[stage], kTcABytes);
-                    tma_load_2d(st_a + stage * kTcABytes, &tmap_a, (int32_t)(kb * kTcKBytes), row0,
-                                &full_a[stage], pol_a);
-                    if (++stage == kTcStagesA) {
-                        stage = 0;
-                        phase ^= 1u;
-                    }
-                }
-            }
-        }
-        __syncwarp();
-    } else if (warp == 2) {
-        // ===== TMA producer, query tiles: the same dim/128 boxes for every corpus tile, served
-        //       from L2 =====
-        if (lane == 0) {
             const uint64_t pol_q = policy_evict_normal();
-            const uint32_t tx = p.n_pad * kTcKBytes;
+            const uint32_t tx = (kTcABytes + n_b * kTcKBytes) * CTAS;  // both CTAs' bytes
             uint32_t stage = 0, phase = 0;
-            for (uint32_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+            for (uint32_t t = unit; t < n_tiles; t += n_units) {
+                const int32_t row0 = (int32_t)(row_begin + t * kTileRows + cr * kTcM);
                 for (uint32_t kb = 0; kb < n_kb; ++kb) {
-                    mbar_wait_wd<96>(&empty_b[stage], phase ^ 1u);
-                    mbar_arrive_expect_tx(&full_b[stage], tx);
-                    tma_load_2d(st_b + stage * kTcBBytesMax, &tmap_q, (int32_t)(kb * kTcKBytes), 0,
-                                &full_b[stage], pol_q);
-                    if (++stage == kTcStagesB) {
+                    mbar_wait_wd<96>(&empty_bar[stage], phase ^ 1u);
+                    uint8_t *sa = ring + stage * kStageBytes;
+                    if (CTAS == 2) {
+                        if (cr == 0u) mbar_arrive_expect_tx(&full_bar[stage], tx);
+                        const uint32_t fb = lead_full0 + stage * 8u;
+                        tma_load_2d_pair(sa, &tmap_a, (int32_t)(kb * kTcKBytes), row0, fb, pol_a);
+                        tma_load_2d_pair(sa + kTcABytes, &tmap_q, (int32_t)(kb * kTcKBytes),
+                                         (int32_t)(cr * n_b), fb, pol_q);
+                    } else {
+                        mbar_arrive_expect_tx(&full_bar[stage], tx);
+                        tma_load_2d(sa, &tmap_a, (int32_t)(kb * kTcKBytes), row0, &full_bar[stage],
+                                    pol_a);
+                        tma_load_2d(sa + kTcABytes, &tmap_q, (int32_t)(kb * kTcKBytes), 0,
+                                    &full_bar[stage], pol_q);
+                    }
+                    if (++stage == kStages) {
                         stage = 0;
                         phase ^= 1u;
                     }
@@ -665,37 +755,40 @@ tc_gemm_filter_kernel(const __grid_constant__ CUtensorMap tmap_a,
         }
         __syncwarp();
     } else if (warp == 1) {
-        // ===== MMA issuer: one thread =====
-        if (lane == 0) {
-            const uint32_t idesc = tc_idesc_i8(kTcM, p.n_pad);
-            uint32_t sa = 0, pa = 0, sb = 0, pb = 0, it = 0;
-            for (uint32_t t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
+        // ===== MMA issuer: one thread (of the leader CTA) =====
+        if (lane == 0 && cr == 0u) {
+            const uint32_t idesc = tc_idesc_i8(kTcM * CTAS, p.n_pad);
+            uint32_t stage = 0, phase = 0, it = 0;
+            for (uint32_t t = unit; t < n_tiles; t += n_units, ++it) {
                 const uint32_t acc = it & 1u, aph = (it >> 1) & 1u;
                 mbar_wait_wd<32>(&tempty_bar[acc], aph ^ 1u);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * kTcMaxQ;
                 for (uint32_t kb = 0; kb < n_kb; ++kb) {
-                    mbar_wait_wd<0>(&full_b[sb], pb);
-                    mbar_wait_wd<0>(&full_a[sa], pa);
+                    mbar_wait_wd<0>(&full_bar[stage], phase);
                     tc_fence_after();
-                    const uint64_t adesc = tc_smem_desc(smem_u32(st_a + sa * kTcABytes));
-                    const uint64_t bdesc = tc_smem_desc(smem_u32(st_b + sb * kTcBBytesMax));
+                    const uint32_t sa = smem_u32(ring + stage * kStageBytes);
+                    const uint64_t adesc = tc_smem_desc(sa);
+                    const uint64_t bdesc = tc_smem_desc(sa + kTcABytes);
 #pragma unroll
-                    for (uint32_t ks = 0; ks < kTcKBytes / 32u; ++ks)  // UMMA K = 32 int8 = 32 B
-                        tc_mma_i8(d_tmem, adesc + 2ull * ks, bdesc + 2ull * ks, idesc,
-                                  (kb | ks) != 0u ? 1u : 0u);
-                    tc_commit(&empty_a[sa]);  // both stages are free once these MMAs retire
-                    tc_commit(&empty_b[sb]);
-                    if (++sa == kTcStagesA) {
-                        sa = 0;
-                        pa ^= 1u;
+                    for (uint32_t ks = 0; ks < kTcKBytes / 32u; ++ks) {  // UMMA K = 32 int8 = 32 B
+                        if (CTAS == 2)
+                            tc_mma_i8_pair(d_tmem, adesc + 2ull * ks, bdesc + 2ull * ks, idesc,
+                                           (kb | ks) != 0u ? 1u : 0u);
+                        else
+                            tc_mma_i8(d_tmem, adesc + 2ull * ks, bdesc + 2ull * ks, idesc,
+                                      (kb | ks) != 0u ? 1u : 0u);
                     }
-                    if (++sb == kTcStagesB) {
-                        sb = 0;
-                        pb ^= 1u;
+                    // frees the stage (in both CTAs) once these MMAs retire
+                    if (CTAS == 2) tc_commit_pair(&empty_bar[stage]);
+                    else tc_commit(&empty_bar[stage]);
+                    if (++stage == kStages) {
+                        stage = 0;
+                        phase ^= 1u;
                     }
                 }
-                tc_commit(&tfull_bar[acc]);
+                if (CTAS == 2) tc_commit_pair(&tfull_bar[acc]);
+                else tc_commit(&tfull_bar[acc]);
             }
         }
         __syncwarp();
@@ -708,6 +801,7 @@ tc_gemm_filter_kernel(const __grid_constant__ CUtensorMap tmap_a,
         const float sc = __uint_as_float((127u - p.shift) << 23);
         const int sh = (int)p.shift;
         const bool phase0 = row_begin == 0u;
+        const TcRowConsts rcst = tc_row_consts(p.metric, p.dim);
         TcPend *pq = pend_s + (warp - kTcRoleWarps) * kTcPendCap;
         uint32_t *pcnt = pend_cnt_s + (warp - kTcRoleWarps);
         auto load_meta = [&](uint32_t r, bool ok) {
@@ -715,20 +809,37 @@ tc_gemm_filter_kernel(const __grid_constant__ CUtensorMap tmap_a,
             if (ok) raw = __ldg(reinterpret_cast<const float4 *>(p.meta + r));
             return raw;
         };
+        auto drain = [&]() {  // warp-uniform
+            __syncwarp();
+            const uint32_t n_pend = min(*pcnt, kTcPendCap);
+            for (uint32_t e = lane; e < n_pend; e += 32u) {
+                const TcPend pe = pq[e];
+                RowMeta rm;
+                rm.scale = pe.scale;
+                rm.x1 = pe.x1;
+                rm.rmag = pe.rmag;
+                rm.flags = pe.q_flags >> 16;
+                const uint32_t qq = pe.q_flags & 0xffffu;
+                tc_keep_entry(p, qm_s, qq, pe.I, pe.row, rm, __float_as_uint(coef_s[qq].w), phase0);
+            }
+            __syncwarp();
+            if (lane == 0) *pcnt = 0u;
+            __syncwarp();
+        };
         uint32_t it = 0;
         float4 raw_next = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-        if (blockIdx.x < n_tiles) {
-            const uint32_t r0 = row_begin + blockIdx.x * kTcM + qd * 32u + lane;
+        if (unit < n_tiles) {
+            const uint32_t r0 = row_begin + unit * kTileRows + cr * kTcM + qd * 32u + lane;
             raw_next = load_meta(r0, r0 < row_end);
         }
-        for (uint32_t t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
+        for (uint32_t t = unit; t < n_tiles; t += n_units, ++it) {
             const uint32_t acc = it & 1u, aph = (it >> 1) & 1u;
-            const uint32_t row = row_begin + t * kTcM + qd * 32u + lane;
+            const uint32_t row = row_begin + t * kTileRows + cr * kTcM + qd * 32u + lane;
             const bool valid = row < row_end;
             const float4 raw = raw_next;
             {   // next tile's row constants: in flight while this tile is screened
-                const uint32_t tn = t + gridDim.x;
-                const uint32_t rn = row_begin + tn * kTcM + qd * 32u + lane;
+                const uint32_t tn = t + n_units;
+                const uint32_t rn = row_begin + tn * kTileRows + cr * kTcM + qd * 32u + lane;
                 raw_next = load_meta(rn, tn < n_tiles && rn < row_end);
             }
             RowMeta m;
@@ -737,7 +848,7 @@ tc_gemm_filter_kernel(const __grid_constant__ CUtensorMap tmap_a,
             m.rmag = raw.z;
             m.flags = __float_as_uint(raw.w);
             float alpha, beta, br;
-            tc_row_coef(p.metric, m, p.dim, alpha, beta, br);
+            tc_row_coef(p.metric, m, rcst, alpha, beta, br);
             if (!p.screen) br = INFINITY;
             // lhs = float((I >> shift) + ceil(br / 2^shift) + 5) via the 1.5 * 2^23 bit trick (the
             // 5 covers the floor of the shift and the roundings of the two fma below, whose
@@ -794,7 +905,7 @@ tc_gemm_filter_kernel(const __grid_constant__ CUtensorMap tmap_a,
                             e.rmag = m.rmag;
                             pq[slot] = e;
                         } else {  // queue full (early phases keep most entries): evaluate now
-                            tc_keep_entry(p, c0 + j, tmp[j], row, m,
+                            tc_keep_entry(p, qm_s, c0 + j, tmp[j], row, m,
                                           __float_as_uint(coef_s[c0 + j].w), phase0);
                         }
                     }
@@ -826,31 +937,30 @@ tc_gemm_filter_kernel(const __grid_constant__ CUtensorMap tmap_a,
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty_bar[acc]);
-            // the accumulator is back with the MMA issuer: now the parked entries, one per lane
-            const uint32_t n_pend = min(*pcnt, kTcPendCap);
-            for (uint32_t e = lane; e < n_pend; e += 32u) {
-                const TcPend pe = pq[e];
-                RowMeta rm;
-                rm.scale = pe.scale;
-                rm.x1 = pe.x1;
-                rm.rmag = pe.rmag;
-                rm.flags = pe.q_flags >> 16;
-                const uint32_t qq = pe.q_flags & 0xffffu;
-                tc_keep_entry(p, qq, pe.I, pe.row, rm, __float_as_uint(coef_s[qq].w), phase0);
+            if (lane == 0) {
+                if (CTAS == 2) mbar_arrive_cluster(lead_tempty0 + acc * 8u);
+                else mbar_arrive(&tempty_bar[acc]);
             }
-            __syncwarp();
-            if (lane == 0) *pcnt = 0u;
-            __syncwarp();
+            // the accumulator is back with the MMA issuer.  Parked entries are evaluated one per
+            // lane once enough of them have gathered (the latency of a batch -- query constants,
+            // double precision, a list reservation in global memory -- is the same for 1 or 32)
+            if (*pcnt >= kTcPendDrain) drain();
         }
+        drain();
     }
     tc_fence_before();
-    __syncthreads();
+    if (CTAS == 2) cluster_sync_all();  // no CTA may leave while its peer still signals it
+    else __syncthreads();
     tc_fence_after();
     if (warp == 1) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
-                     "r"(kTcTmemCols)
-                     : "memory");
+        if (CTAS == 2)
+            asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                         "r"(kTcTmemCols)
+                         : "memory");
+        else
+            asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                         "r"(kTcTmemCols)
+                         : "memory");
     }
 }
 
