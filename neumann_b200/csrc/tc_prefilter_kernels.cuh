@@ -167,8 +167,10 @@ __device__ __forceinline__ uint32_t mapa_shared(uint32_t saddr, uint32_t rank) {
     return r;
 }
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr)
-                 : "memory");
+    // (default .release at CTA scope, as CUTLASS's ClusterBarrier::arrive(cta_id): the TMEM reads
+    // are ordered by tcgen05.fence::before_thread_sync; a cluster-scope release costs a
+    // MEMBAR.GPU per arrive)
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // TMA load of a cta_group::2 pair: data lands in THIS CTA's shared memory, the bytes are
 // counted on the barrier at `bar_cluster_addr` (the leader CTA's)
@@ -661,7 +663,9 @@ tc_gemm_filter_kernel(const __grid_constant__ CUtensorMap tmap_a,
         }
         for (uint32_t a = 0; a < 2; ++a) {
             mbar_init(&tfull_bar[a], 1);
-            mbar_init(&tempty_bar[a], kTcEpilogueWarps * CTAS);  // the leader's collects both CTAs
+            // 1 CTA: one arrive per epilogue warp.  Pair: one per CTA on the leader's barrier (a
+            // remote arrive drags a MEMBAR.GPU along, so the warps first meet on a named barrier)
+            mbar_init(&tempty_bar[a], CTAS == 2 ? 2u : kTcEpilogueWarps);
         }
         fence_mbar_init();
     }
@@ -936,10 +940,12 @@ tc_gemm_filter_kernel(const __grid_constant__ CUtensorMap tmap_a,
                 }
             }
             tc_fence_before();
-            __syncwarp();
-            if (lane == 0) {
-                if (CTAS == 2) mbar_arrive_cluster(lead_tempty0 + acc * 8u);
-                else mbar_arrive(&tempty_bar[acc]);
+            if (CTAS == 2) {
+                asm volatile("bar.sync 2, %0;" ::"n"(32 * kTcEpilogueWarps) : "memory");
+                if (warp == kTcRoleWarps && lane == 0) mbar_arrive_cluster(lead_tempty0 + acc * 8u);
+            } else {
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty_bar[acc]);
             }
             // the accumulator is back with the MMA issuer.  Parked entries are evaluated one per
             // lane once enough of them have gathered (the latency of a batch -- query constants,
