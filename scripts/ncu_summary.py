@@ -26,6 +26,14 @@ want = [
  'smsp__pcsamp_warps_issue_stalled_misc', 'smsp__pcsamp_warps_issue_stalled_imc_miss',
  'smsp__pcsamp_warps_issue_stalled_tex_throttle', 'smsp__pcsamp_warps_issue_stalled_drain',
  'smsp__pcsamp_warps_issue_stalled_gmma', 'smsp__pcsamp_sample_buffers',
+ 'sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active',
+ 'sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed',
+ 'sm__inst_executed_pipe_tensor_subpipe_imma.avg.pct_of_peak_sustained_active',
+ 'sm__inst_executed_pipe_tmem.avg.pct_of_peak_sustained_active',
+ 'sm__inst_executed_pipe_tma.avg.pct_of_peak_sustained_active',
+ 'sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active',
+ 'dram__bytes_read.sum.per_second', 'l1tex__m_xbar2l1tex_read_bytes.sum',
+ 'launch__cluster_dim_x', 'launch__cluster_size',
 ]
 out = []
 for r in rows[2:]:
