@@ -998,9 +998,13 @@ struct TcRefineParams {
 constexpr uint32_t kTcTopCap = 2048;  // >= kMaxFastK; entries re-scored per refine at most
 
 // k-th largest of val(0..n) (n >= k >= 1), MSB-first radix select; all 256 threads call.
+// Thread t owns digit bin t; the bin holding the k-th largest is found with a parallel suffix
+// sum (warp shuffles + 8 warp totals), not a serial walk over the 256 bins.
 template <class F>
 __device__ __forceinline__ uint32_t tc_radix_kth(F val, uint32_t n, uint32_t k, uint32_t *hist,
                                                  uint32_t *sel_s, uint32_t t) {
+    __shared__ uint32_t wtot[8];
+    const uint32_t lane = t & 31u, warp = t >> 5;
     if (t == 0) {
         sel_s[0] = 0u;
         sel_s[1] = k;
@@ -1008,21 +1012,26 @@ __device__ __forceinline__ uint32_t tc_radix_kth(F val, uint32_t n, uint32_t k, 
     for (int shift = 24; shift >= 0; shift -= 8) {
         hist[t] = 0u;
         __syncthreads();
-        const uint32_t prefix = sel_s[0];
+        const uint32_t prefix = sel_s[0], need = sel_s[1];
         for (uint32_t i = t; i < n; i += 256u) {
             const uint32_t o = val(i);
             if (shift == 24 || (o >> (shift + 8)) == prefix) atomicAdd(&hist[(o >> shift) & 255u], 1u);
         }
         __syncthreads();
-        if (t == 0) {
-            uint32_t need = sel_s[1], cum = 0;
-            int b = 255;
-            for (; b > 0; --b) {
-                if (cum + hist[b] >= need) break;
-                cum += hist[b];
-            }
-            sel_s[0] = (prefix << 8) | (uint32_t)b;
-            sel_s[1] = need - cum;
+        const uint32_t mine = hist[t];
+        uint32_t sfx = mine;  // sum of bins t .. end of this warp
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const uint32_t v = __shfl_down_sync(0xffffffffu, sfx, off);
+            if (lane + off < 32u) sfx += v;
+        }
+        if (lane == 0) wtot[warp] = sfx;
+        __syncthreads();
+        for (uint32_t w = warp + 1; w < 8u; ++w) sfx += wtot[w];  // bins t .. 255
+        const uint32_t above = sfx - mine;                         // bins t+1 .. 255
+        if (above < need && need <= sfx) {                         // exactly one thread
+            sel_s[0] = (prefix << 8) | t;
+            sel_s[1] = need - above;
         }
         __syncthreads();
     }

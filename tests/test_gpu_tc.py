@@ -215,6 +215,38 @@ def test_tc_follows_mutations_and_routing():
     idx.close()
 
 
+def test_tc_concurrent_batches():
+    """Batches from several host threads at once (each call owns its workspace and stream; the
+    GEMM kernels of different calls cannot share an SM) return what sequential calls return."""
+    import threading
+    n, d, k = 200_000, 128, 10
+    idx = DeviceIndex(d)
+    idx.fill_synthetic(n, 0x5EED0001)
+    idx.set_prefilter(1)
+    batches = [synth_rows(24, d, 0x5EED3000 + t) for t in range(6)]
+    expect = [idx.search(b, k, "euclidean") for b in batches]
+    got = [None] * len(batches)
+    errs = []
+
+    def work(t):
+        try:
+            for _ in range(5):
+                got[t] = idx.search(batches[t], k, "euclidean")
+        except Exception as e:  # noqa: BLE001
+            errs.append(e)
+
+    th = [threading.Thread(target=work, args=(t,)) for t in range(len(batches))]
+    for x in th:
+        x.start()
+    for x in th:
+        x.join()
+    assert not errs, errs
+    for t in range(len(batches)):
+        for i in range(24):
+            assert_same(got[t][i], expect[t][i], f"thread {t} q{i}")
+    idx.close()
+
+
 @pytest.mark.parametrize("n,dim,nq,k,metric", [(10_000_000, 1536, 256, 100, "euclidean")])
 def test_config4_full_size_properties(n, dim, nq, k, metric):
     """BASELINE config 4 at full size through size-independent properties: scores re-derived by
