@@ -449,6 +449,8 @@ bool tc_usable(const nm_index *idx, const Shard &sh, uint32_t nq, uint32_t k, in
     if (nq < 2 || !sh.tmap8_valid || sh.q8_rows != sh.rows) return false;
     if (sh.rows < kTcMinRows || k > (uint32_t)nm::kMaxFastK) return false;
     if ((uint64_t)idx->dim * 16129ull >= 0x7fffffffull) return false;   // s32 accumulators
+    // dim % 4 != 0: the re-score keeps the (then unaligned) query in shared memory
+    if ((idx->dim % 4u) != 0u && (size_t)idx->dim * 4 > 160 * 1024) return false;
     if ((size_t)idx->dim * 4 > 160 * 1024) return false;                // rescore keeps q in smem
     return true;
 }

@@ -62,7 +62,9 @@ def test_tensor_core_dot_products_are_exact(n, dim, nq):
 @pytest.mark.parametrize("metric", METRICS)
 @pytest.mark.parametrize("n,dim,nq,k", [(70_000, 128, 16, 10), (100_000, 96, 37, 100),
                                         (66_000, 131, 5, 7), (80_000, 768, 8, 1),
-                                        (120_000, 64, 2, 1000), (70_000, 1536, 4, 20)])
+                                        (120_000, 64, 2, 1000), (70_000, 1536, 4, 20),
+                                        (70_000, 8, 3, 5), (66_000, 24, 9, 3), (66_000, 2052, 3, 4),
+                                        (66_000, 1, 2, 3)])
 def test_tc_batch_equals_oracle(metric, n, dim, nq, k):
     rows = o.fill_synthetic(n, dim, 0x5EED0001)
     idx = DeviceIndex(dim)
@@ -71,7 +73,8 @@ def test_tc_batch_equals_oracle(metric, n, dim, nq, k):
     qs = o.fill_synthetic(nq, dim, 0x5EED1001)
     qs[1] = rows[n // 3]                               # a query equal to a stored row
     res, used, fell, _ = tc_search(idx, qs, k, metric)
-    assert used == nq and fell == 0
+    assert used == nq
+    assert fell == 0 or dim == 1      # dim 1: every cosine is +-1, the tie flood falls back
     for i in range(nq):
         assert_same(res[i], o.search(rows, qs[i], k, metric, threads=8), f"{metric} n={n} d={dim} q{i}")
     idx.close()
