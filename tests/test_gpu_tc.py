@@ -218,6 +218,51 @@ def test_tc_follows_mutations_and_routing():
     idx.close()
 
 
+_SCREEN_AB = r"""
+import sys, json
+sys.path.insert(0, sys.argv[1])
+import numpy as np
+from neumann_b200 import DeviceIndex
+from neumann_b200.synth import synth_rows
+out = {}
+for metric in ("cosine", "euclidean", "dot"):
+    idx = DeviceIndex(160)
+    idx.fill_synthetic(400_000, 0x5EED0001)
+    idx.set_prefilter(1)
+    qs = synth_rows(48, 160, 0x5EED1001)
+    s0 = idx.stats()
+    res = idx.search(qs, 25, metric)
+    s1 = idx.stats()
+    out[metric] = {"survivors": int(s1.tc_survivors - s0.tc_survivors),
+                   "fallbacks": int(s1.tc_fallbacks - s0.tc_fallbacks),
+                   "rows": [r[0].tolist() for r in res],
+                   "scores": [r[1].view(np.uint32).tolist() for r in res]}
+    idx.close()
+print(json.dumps(out))
+"""
+
+
+def test_tc_screen_never_drops_a_keeper():
+    """The f32 screen of the GEMM epilogue must be a superset of the rigorous interval test.
+    With NM_TC_SCREEN=0 every (row, query) entry goes through the rigorous test; the screened
+    run must keep exactly the same entries: identical results AND identical survivor counts."""
+    import json, os, subprocess, sys
+    from pathlib import Path
+    root = str(Path(__file__).resolve().parent.parent)
+    runs = {}
+    for screen in ("1", "0"):
+        env = dict(os.environ, NM_TC_SCREEN=screen)
+        p = subprocess.run([sys.executable, "-c", _SCREEN_AB, root], env=env, capture_output=True,
+                           text=True, timeout=600)
+        assert p.returncode == 0, p.stderr[-2000:]
+        runs[screen] = json.loads(p.stdout.strip().splitlines()[-1])
+    for metric in ("cosine", "euclidean", "dot"):
+        a, b = runs["1"][metric], runs["0"][metric]
+        assert a["fallbacks"] == 0 and b["fallbacks"] == 0
+        assert a["rows"] == b["rows"] and a["scores"] == b["scores"], metric
+        assert a["survivors"] == b["survivors"], (metric, a["survivors"], b["survivors"])
+
+
 def test_tc_concurrent_batches():
     """Batches from several host threads at once (each call owns its workspace and stream; the
     GEMM kernels of different calls cannot share an SM) return what sequential calls return."""
