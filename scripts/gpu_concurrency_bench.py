@@ -11,10 +11,14 @@ from neumann_b200.synth import synth_rows
 n, d, k = 10_000_000, 768, 10
 idx = DeviceIndex(d); idx.fill_synthetic(n, 0x5EED0001)
 qs = synth_rows(256, d, 0x5EED1001)
+modes = [("f32", 64), ("f32", 1)]
+if len(sys.argv) > 1 and sys.argv[1] == "prefilter":
+    idx.set_prefilter(1)   # single calls: int8 dp4a pre-filter; coalesced rounds: tcgen05 pre-filter
+    modes = [("int8", 64), ("int8", 1)]
 for T in (1, 4, 16, 64):
-    for co in (64, 1):
+    for tag, co in modes:
         idx.set_coalescing(co)
-        per = max(8, 128 // T)
+        per = max(8, 256 // T)
         lat = []
         def worker(t):
             for j in range(per):
@@ -27,5 +31,5 @@ for T in (1, 4, 16, 64):
         for t in ts: t.start()
         for t in ts: t.join()
         dt = time.perf_counter() - t0
-        print(f"threads={T:3d} coalescing={'on ' if co > 1 else 'off'}: {T * per / dt:8.1f} QPS  "
+        print(f"[{tag}] threads={T:3d} coalescing={'on ' if co > 1 else 'off'}: {T * per / dt:8.1f} QPS  "
               f"latency p50 {np.median(lat) * 1e3:7.2f} ms p99 {np.percentile(lat, 99) * 1e3:7.2f} ms", flush=True)
