@@ -191,8 +191,10 @@ int nm_index_set_prefilter(nm_index *idx, int mode);
  * scalar L2 chain), only entries whose interval reaches the query's running k-th best lower
  * bound are kept, and those are re-scored from the f32 mirror with the reference arithmetic.
  * Results are bit-identical to the exact batched kernels (tested); queries that are not
- * finite or whose candidate list overflows are redone by the exact path.  Single-device
- * indexes, >= 32768 rows, k <= 1024.  enable = 0 keeps batches on the exact kernels. */
+ * finite or whose candidate list overflows are redone by the exact path.  Shards of >= 65536
+ * rows (single-device, in-process multi-device and collective indexes alike: a sharded index
+ * computes each shard's hits this way and merges them as usual), k <= 1024.  enable = 0 keeps
+ * batches on the exact kernels. */
 int nm_index_set_tensor_core(nm_index *idx, int enable);
 /* Diagnostics: the exact integer dot products the tensor-core pass computes,
  * out[q * rows + r] = sum_i int8(row r)[i] * int8(query q)[i], for the first min(nq, 256)

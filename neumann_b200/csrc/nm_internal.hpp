@@ -99,6 +99,8 @@ struct Workspace {
     size_t tc_nq_cap = 0;           // queries
     void *d_tc_kept = nullptr;      // [256][kTcKeptCap] nm::TcKept
     uint64_t *d_tc_keys = nullptr;  // [256][kTcKeptCap]
+    uint8_t *d_tc_out = nullptr;      // scratch result block of a sharded tensor-core pass
+    size_t tc_out_cap = 0;
     uint32_t *d_tc_bucket = nullptr;  // row-bucket counters / cursors of the re-score ordering
     void *d_tc_sorted = nullptr;      // [256 * kTcKeptCap] uint2 {row, query << 16 | slot}
     // batched-query path (batch_kernels.cuh)
@@ -135,6 +137,7 @@ struct Workspace {
         if (d_tc_kept_n) cudaFree(d_tc_kept_n);
         if (d_tc_kept) cudaFree(d_tc_kept);
         if (d_tc_keys) cudaFree(d_tc_keys);
+        if (d_tc_out) cudaFree(d_tc_out);
         if (d_tc_bucket) cudaFree(d_tc_bucket);
         if (d_tc_sorted) cudaFree(d_tc_sorted);
         if (d_qt) cudaFree(d_qt);
@@ -297,8 +300,15 @@ bool tc_usable(const nm_index *idx, const Shard &sh, uint32_t nq, uint32_t k, in
 // been waited for) means query q must be redone by the exact path.  *h_flags_out points into
 // pinned memory owned by the workspace.
 int scan_queries_tc(nm_index *idx, const Shard &sh, Workspace &ws, const float *d_queries,
-                    uint32_t nq, uint32_t k, int metric, uint64_t *out_rows, float *out_scores,
-                    uint32_t *out_counts, cudaStream_t stream, int *debug_dots = nullptr);
+                    uint32_t nq, uint32_t k, int metric, uint64_t row_base, uint64_t *out_rows,
+                    float *out_scores, uint32_t *out_counts, cudaStream_t stream,
+                    int *debug_dots = nullptr);
+int scan_queries_tc_hits_enqueue(nm_index *idx, const Shard &sh, Workspace &ws,
+                                 const float *d_queries, uint32_t nq, uint32_t k, int metric,
+                                 uint64_t row_base, nm::ShardHit *out_hits, cudaStream_t stream);
+int scan_queries_tc_hits_finish(nm_index *idx, const Shard &sh, Workspace &ws,
+                                const float *d_queries, uint32_t nq, uint32_t k, int metric,
+                                uint64_t row_base, nm::ShardHit *out_hits, cudaStream_t stream);
 uint32_t tc_query_flags(const Workspace &ws, uint32_t q, uint32_t rows);
 uint32_t tc_phases(const Workspace &ws);
 uint32_t tc_survivors(const Workspace &ws);

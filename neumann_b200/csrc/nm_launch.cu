@@ -513,8 +513,8 @@ static int ws_ensure_tc(Workspace &ws, uint32_t dim, uint32_t nq, cudaStream_t s
 constexpr uint32_t kTcMaxPhases = 12;
 
 int scan_queries_tc(nm_index *idx, const Shard &sh, Workspace &ws, const float *d_queries,
-                    uint32_t nq, uint32_t k, int metric, uint64_t *out_rows, float *out_scores,
-                    uint32_t *out_counts, cudaStream_t stream, int *debug_dots) {
+                    uint32_t nq, uint32_t k, int metric, uint64_t row_base, uint64_t *out_rows,
+                    float *out_scores, uint32_t *out_counts, cudaStream_t stream, int *debug_dots) {
     static std::mutex mu;
     static bool configured[64] = {false};
     {
@@ -636,7 +636,7 @@ int scan_queries_tc(nm_index *idx, const Shard &sh, Workspace &ws, const float *
         sp.out_scores = out_scores + (size_t)q0 * k;
         sp.out_counts = out_counts + q0;
         sp.stats = aux.stats;
-        sp.row_base = sh.row_base;
+        sp.row_base = row_base;
         sp.pitch = idx->pitch;
         sp.dim = dim;
         sp.k = k_eff;
@@ -701,6 +701,46 @@ uint32_t tc_phases(const Workspace &ws) {
     const uint8_t *tail = static_cast<const uint8_t *>(ws.h_tc_qmeta) +
                           ws.tc_nq_cap * sizeof(nm::TcQueryMeta);
     return reinterpret_cast<const nm::TcCtl *>(tail + 8 * sizeof(uint32_t))[0].phases;
+}
+
+// ---- the same for sharded indexes: this shard's hits as ShardHit[nq, k] (global rows) -------
+// Enqueue: tensor-core pass into scratch, pack to hits, flags to the host.  Finish (after the
+// caller has other shards in flight): wait, redo flagged queries with the exact scan.
+int scan_queries_tc_hits_enqueue(nm_index *idx, const Shard &sh, Workspace &ws,
+                                 const float *d_queries, uint32_t nq, uint32_t k, int metric,
+                                 uint64_t row_base, nm::ShardHit *out_hits, cudaStream_t stream) {
+    const ResultLayout l = result_layout(nq, k);
+    if (ws.tc_out_cap < l.total) {
+        CUDA_TRY(cudaStreamSynchronize(stream));
+        if (ws.d_tc_out) CUDA_TRY(cudaFree(ws.d_tc_out));
+        ws.tc_out_cap = 0;
+        CUDA_TRY(cudaMalloc(&ws.d_tc_out, l.total));
+        ws.tc_out_cap = l.total;
+    }
+    uint64_t *t_rows = reinterpret_cast<uint64_t *>(ws.d_tc_out + l.rows_off);
+    float *t_scores = reinterpret_cast<float *>(ws.d_tc_out + l.scores_off);
+    uint32_t *t_counts = reinterpret_cast<uint32_t *>(ws.d_tc_out + l.counts_off);
+    int rc = scan_queries_tc(idx, sh, ws, d_queries, nq, k, metric, row_base, t_rows, t_scores,
+                             t_counts, stream);
+    if (rc) return rc;
+    nm::tc_pack_hits_kernel<<<nq, 256, 0, stream>>>(t_rows, t_scores, t_counts, k, out_hits);
+    CUDA_TRY(cudaGetLastError());
+    return NM_OK;
+}
+
+int scan_queries_tc_hits_finish(nm_index *idx, const Shard &sh, Workspace &ws,
+                                const float *d_queries, uint32_t nq, uint32_t k, int metric,
+                                uint64_t row_base, nm::ShardHit *out_hits, cudaStream_t stream) {
+    CUDA_TRY(cudaStreamSynchronize(stream));
+    idx->tc_survivors += tc_survivors(ws);
+    for (uint32_t q = 0; q < nq; ++q) {
+        if (tc_query_flags(ws, q, (uint32_t)sh.rows) == 0) continue;
+        idx->tc_fallbacks++;
+        int rc = launch_scan(idx, sh, ws, d_queries + (size_t)q * idx->dim, k, metric, row_base,
+                             nullptr, nullptr, nullptr, out_hits + (size_t)q * k, stream);
+        if (rc) return rc;
+    }
+    return NM_OK;
 }
 
 // nq queries over one shard: batched kernels when that pays, else one (chained) scan per query.

@@ -187,8 +187,8 @@ static int search_impl(nm_index *idx, const float *queries, uint32_t nq, uint32_
         } else if (tc_usable(idx, sh, nq, k, metric, row_mask)) {
             // tensor-core pre-filter: one int8 GEMM pass per 256 queries + exact re-score; the
             // per-query flags come back with the results, flagged queries are redone exactly
-            rc = scan_queries_tc(idx, sh, *ws, ws->d_query, nq, k, metric, r_rows, r_scores,
-                                 r_counts, ws->stream);
+            rc = scan_queries_tc(idx, sh, *ws, ws->d_query, nq, k, metric, sh.row_base, r_rows,
+                                 r_scores, r_counts, ws->stream);
             if (rc) return rc;
             CUDA_TRY(cudaEventRecord(ws->ev1, ws->stream));
             CUDA_TRY(cudaMemcpyAsync(ws->h_result, ws->d_result, l.total, cudaMemcpyDeviceToHost,
@@ -330,6 +330,16 @@ static int search_impl(nm_index *idx, const float *queries, uint32_t nq, uint32_
             if (sh.rows == 0) {
                 CUDA_TRY(cudaMemsetAsync(ws->d_hits, 0, (size_t)nq * k * sizeof(nm::ShardHit),
                                          ws->stream));
+            } else if (tc_usable(idx, sh, nq, k, metric, nullptr)) {
+                // this shard's hits through the tensor-core pre-filter (a rank-local choice:
+                // the exchange format is the same)
+                rc = scan_queries_tc_hits_enqueue(idx, sh, *ws, ws->d_query, nq, k, metric,
+                                                  idx->comm_row_base, ws->d_hits, ws->stream);
+                if (rc) return rc;
+                rc = scan_queries_tc_hits_finish(idx, sh, *ws, ws->d_query, nq, k, metric,
+                                                 idx->comm_row_base, ws->d_hits, ws->stream);
+                if (rc) return rc;
+                idx->tc_queries += nq;
             } else {
                 rc = scan_queries(idx, sh, *ws, ws->d_query, nq, k, metric, idx->comm_row_base,
                                   nullptr, nullptr, nullptr, ws->d_hits, ws->stream);
@@ -348,6 +358,8 @@ static int search_impl(nm_index *idx, const float *queries, uint32_t nq, uint32_
     // ---- several devices in this process: scan each shard, merge the per-shard top-k on
     //      the host (G*k hits), exactly ResultMerger::merge_top_k -------------------------
     std::vector<std::unique_ptr<Workspace>> wss(G);
+    std::vector<char> tc_shard(G, 0);
+    bool any_tc = false;
     struct ReleaseAll {
         nm_index *idx;
         std::vector<std::unique_ptr<Workspace>> &w;
@@ -369,6 +381,13 @@ static int search_impl(nm_index *idx, const float *queries, uint32_t nq, uint32_
         CUDA_TRY(cudaEventRecord(ws.ev0, ws.stream));
         if (sh.rows == 0) {
             CUDA_TRY(cudaMemsetAsync(ws.d_hits, 0, (size_t)nq * k * sizeof(nm::ShardHit), ws.stream));
+        } else if (tc_usable(idx, sh, nq, k, metric, nullptr)) {
+            tc_shard[s] = true;
+            any_tc = true;
+            rc = scan_queries_tc_hits_enqueue(idx, sh, ws, ws.d_query, nq, k, metric, sh.row_base,
+                                              ws.d_hits, ws.stream);
+            if (rc) return rc;
+            continue;  // finished below, once every shard has its work in flight
         } else {
             rc = scan_queries(idx, sh, ws, ws.d_query, nq, k, metric, sh.row_base, nullptr, nullptr,
                               nullptr, ws.d_hits, ws.stream);
@@ -378,6 +397,19 @@ static int search_impl(nm_index *idx, const float *queries, uint32_t nq, uint32_
         CUDA_TRY(cudaMemcpyAsync(ws.h_hits, ws.d_hits, (size_t)nq * k * sizeof(nm::ShardHit),
                                  cudaMemcpyDeviceToHost, ws.stream));
     }
+    for (size_t s = 0; s < G; ++s) {
+        if (!tc_shard[s]) continue;
+        Shard &sh = *idx->shards[s];
+        Workspace &ws = *wss[s];
+        CUDA_TRY(cudaSetDevice(sh.device));
+        rc = scan_queries_tc_hits_finish(idx, sh, ws, ws.d_query, nq, k, metric, sh.row_base,
+                                         ws.d_hits, ws.stream);
+        if (rc) return rc;
+        CUDA_TRY(cudaEventRecord(ws.ev1, ws.stream));
+        CUDA_TRY(cudaMemcpyAsync(ws.h_hits, ws.d_hits, (size_t)nq * k * sizeof(nm::ShardHit),
+                                 cudaMemcpyDeviceToHost, ws.stream));
+    }
+    if (any_tc) idx->tc_queries += nq;
     float max_ms = 0.f;
     for (size_t s = 0; s < G; ++s) {
         CUDA_TRY(cudaSetDevice(idx->shards[s]->device));
@@ -525,7 +557,7 @@ int nm_debug_tc_dots(nm_index *idx, const float *queries, uint32_t nq, int32_t *
                              cudaMemcpyHostToDevice, ws->stream));
     int *d_dots = nullptr;
     CUDA_TRY(cudaMalloc(&d_dots, (size_t)nq * sh.rows * 4));
-    rc = scan_queries_tc(idx, sh, *ws, ws->d_query, nq, k, NM_DOT_PRODUCT,
+    rc = scan_queries_tc(idx, sh, *ws, ws->d_query, nq, k, NM_DOT_PRODUCT, sh.row_base,
                          reinterpret_cast<uint64_t *>(ws->d_result + l.rows_off),
                          reinterpret_cast<float *>(ws->d_result + l.scores_off),
                          reinterpret_cast<uint32_t *>(ws->d_result + l.counts_off), ws->stream,

@@ -16,8 +16,11 @@
 //                               K-major SWIZZLE_128B boxes staged by TMA; accumulators
 //                               [128 lanes x 256 columns] s32 in TMEM, double buffered (512
 //                               columns) so the epilogue of tile t overlaps the MMAs of t+1.
-//                               Warp roles: 0 = TMA producer, 1 = MMA issuer (one thread),
-//                               2..5 = epilogue (one TMEM lane quarter each).
+//                               Launched in CTA pairs (cta_group::2: each CTA stages its 128
+//                               corpus rows and half of the queries, one M = 256 UMMA reads
+//                               both) or, NM_TC_PAIR=0, one CTA per tile.  Warp roles: 0 = TMA
+//                               producer, 1 = MMA issuer (one thread), 2..17 = epilogue (four
+//                               warps per TMEM lane quarter, splitting the query columns).
 //                               The epilogue never writes the score matrix.  Each exact
 //                               integer dot product gives a rigorous interval [lb, ub] for
 //                               the reference score (same error model as the 1-query
@@ -1379,6 +1382,28 @@ __global__ void __launch_bounds__(kRowsPerBlock) tc_select_kernel(const TcRescor
     }
     __syncthreads();
     tc_select_query(p, q, min(p.kept_n[q], kTcKeptCap), buf, &thr_s, &cnt_s, hist, t);
+}
+
+// sharded indexes: a shard's result as ShardHit[nq, k] for the cross-shard merge
+__global__ void __launch_bounds__(256)
+tc_pack_hits_kernel(const uint64_t *__restrict__ rows, const float *__restrict__ scores,
+                    const uint32_t *__restrict__ counts, uint32_t k, ShardHit *hits) {
+    const uint32_t q = blockIdx.x, n = counts[q];
+    for (uint32_t i = threadIdx.x; i < k; i += 256u) {
+        ShardHit h;
+        h.global_row = 0ull;
+        h.ord = 0u;
+        h.score_bits = 0u;
+        if (i < n) {
+            const uint32_t sb = __float_as_uint(scores[(size_t)q * k + i]);
+            h.global_row = rows[(size_t)q * k + i];
+            h.ord = score_to_ord(sb);
+            h.score_bits = sb;
+            // an empty slot is {0,0,0}; a NaN hit has ord 0 but non-zero score bits (as
+            // write_outputs encodes it)
+        }
+        hits[(size_t)q * k + i] = h;
+    }
 }
 
 #endif  // __CUDACC__

@@ -35,6 +35,28 @@ def test_in_process_two_device_shards(metric):
     idx.close()
 
 
+@pytest.mark.parametrize("metric", ["cosine", "euclidean"])
+def test_in_process_two_device_shards_tensor_core(metric):
+    """Batches on a pre-filtered two-device index: each shard's hits come from the tensor-core
+    pre-filter, the host merges them (merge_top_k semantics); identical to the oracle."""
+    _need(2)
+    n, d, k = 150_001, 72, 20
+    rows = o.fill_synthetic(n, d, 0x5EED0001)
+    rows[5] = rows[140_000]  # tie across shards
+    idx = DeviceIndex(d, devices=[0, 1])
+    idx.load(rows)
+    idx.set_prefilter(1)
+    qs = np.concatenate([rows[140_000:140_001], o.fill_synthetic(6, d, 3)])
+    s0 = idx.stats()
+    res = idx.search(qs, k, metric)
+    assert idx.stats().tc_queries - s0.tc_queries == len(qs)
+    for i in range(len(qs)):
+        er, es = o.search(rows, qs[i], k, metric, threads=4)
+        assert np.array_equal(res[i][0], er), (metric, i)
+        assert np.array_equal(res[i][1].view(np.uint32), es.view(np.uint32))
+    idx.close()
+
+
 def _free_port():
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
@@ -74,6 +96,17 @@ def _nccl_worker(rank, world, port, q):
             assert np.array_equal(res[i][0], er), ("batched", i)
             assert np.array_equal(res[i][1].view(np.uint32), es.view(np.uint32))
         assert idx.stats().merge_launches == (1 if fused else 10)
+        # the same batch with the pre-filter on: shards of >= 65536 rows compute their hits with
+        # the tensor-core pre-filter (a rank-local choice), same all-gather + merge
+        idx.set_prefilter(1)
+        t0 = idx.stats().tc_queries
+        res = idx.search(qb, k, "euclidean")
+        for i in range(9):
+            er, es = o.search(rows, qb[i], k, "euclidean", threads=4)
+            assert np.array_equal(res[i][0], er), ("tensor core", i)
+            assert np.array_equal(res[i][1].view(np.uint32), es.view(np.uint32))
+        assert (idx.stats().tc_queries - t0 == 9) == (hi - lo >= 65536)
+        idx.set_prefilter(0)
         # k larger than a shard (and than the fast limit): chained passes + NCCL path
         res = idx.search(qs[:1], 1500, "cosine")
         er, es = o.search(rows, qs[0], 1500, "cosine", threads=4)
