@@ -445,7 +445,8 @@ constexpr uint32_t kTcMinRows = 65536;  // below this the exact kernels are chea
 bool tc_usable(const nm_index *idx, const Shard &sh, uint32_t nq, uint32_t k, int metric,
                const uint64_t *row_mask) {
     (void)metric;
-    if (!idx->prefilter.load() || !idx->tensor_core.load() || row_mask) return false;
+    if (!idx->prefilter.load() || !idx->tensor_core.load() || !idx->batching.load() || row_mask)
+        return false;
     if (nq < 2 || !sh.tmap8_valid || sh.q8_rows != sh.rows) return false;
     if (sh.rows < kTcMinRows || k > (uint32_t)nm::kMaxFastK) return false;
     if ((uint64_t)idx->dim * 16129ull >= 0x7fffffffull) return false;   // s32 accumulators
