@@ -145,19 +145,25 @@ int q8_refresh(nm_index *idx, Shard &sh, uint64_t first, uint64_t n) {
         uint64_t cap = std::max<uint64_t>(sh.rows, sh.capacity);
         int8_t *nq = nullptr;
         nm::RowMeta *nmeta = nullptr;
+        float2 *nnorms = nullptr;
         CUDA_TRY(cudaMalloc(&nq, cap * pitch8));
         CUDA_TRY(cudaMalloc(&nmeta, cap * sizeof(nm::RowMeta)));
+        CUDA_TRY(cudaMalloc(&nnorms, cap * sizeof(float2)));
         if (sh.d_q8 && sh.q8_rows) {
             CUDA_TRY(cudaMemcpyAsync(nq, sh.d_q8, sh.q8_rows * pitch8, cudaMemcpyDeviceToDevice,
                                      sh.copy_stream));
             CUDA_TRY(cudaMemcpyAsync(nmeta, sh.d_meta, sh.q8_rows * sizeof(nm::RowMeta),
                                      cudaMemcpyDeviceToDevice, sh.copy_stream));
+            CUDA_TRY(cudaMemcpyAsync(nnorms, sh.d_norms, sh.q8_rows * sizeof(float2),
+                                     cudaMemcpyDeviceToDevice, sh.copy_stream));
             CUDA_TRY(cudaStreamSynchronize(sh.copy_stream));
         }
         if (sh.d_q8) CUDA_TRY(cudaFree(sh.d_q8));
         if (sh.d_meta) CUDA_TRY(cudaFree(sh.d_meta));
+        if (sh.d_norms) CUDA_TRY(cudaFree(sh.d_norms));
         sh.d_q8 = nq;
         sh.d_meta = nmeta;
+        sh.d_norms = nnorms;
         sh.q8_capacity = cap;
     }
     if (!sh.d_q8_flag) {
@@ -172,7 +178,7 @@ int q8_refresh(nm_index *idx, Shard &sh, uint64_t first, uint64_t n) {
     if (first + n > sh.rows) n = sh.rows > first ? sh.rows - first : 0;
     if (n) {
         int rc = launch_quantize(sh, sh.d_rows, idx->pitch, idx->dim, first, n, sh.d_q8, pitch8,
-                                 sh.d_meta, sh.d_q8_flag, sh.copy_stream);
+                                 sh.d_meta, sh.d_norms, sh.d_q8_flag, sh.copy_stream);
         if (rc) return rc;
         CUDA_TRY(cudaStreamSynchronize(sh.copy_stream));
     }
@@ -322,6 +328,7 @@ void nm_index_destroy(nm_index *idx) {
         if (sh->d_rows) cudaFree(sh->d_rows);
         if (sh->d_q8) cudaFree(sh->d_q8);
         if (sh->d_meta) cudaFree(sh->d_meta);
+        if (sh->d_norms) cudaFree(sh->d_norms);
         if (sh->d_q8_flag) cudaFree(sh->d_q8_flag);
         for (int b = 0; b < 2; ++b) {
             if (sh->staging[b]) cudaFreeHost(sh->staging[b]);
@@ -513,8 +520,10 @@ int nm_index_set_prefilter(nm_index *idx, int mode) {
         if (mode == 0) {
             if (sh.d_q8) CUDA_TRY(cudaFree(sh.d_q8));
             if (sh.d_meta) CUDA_TRY(cudaFree(sh.d_meta));
+            if (sh.d_norms) CUDA_TRY(cudaFree(sh.d_norms));
             sh.d_q8 = nullptr;
             sh.d_meta = nullptr;
+            sh.d_norms = nullptr;
             sh.q8_capacity = sh.q8_rows = 0;
             sh.tmap8_valid = false;
         } else {

@@ -172,6 +172,7 @@ struct Shard {
     // int8 pre-filter copy (prefilter_kernels.cuh): [capacity8, pitch8] bytes + 16 B per row
     int8_t *d_q8 = nullptr;
     nm::RowMeta *d_meta = nullptr;
+    float2 *d_norms = nullptr;  // [capacity8] per-row L2 norms for the batch pre-filter's bound
     uint32_t *d_q8_flag = nullptr;
     uint64_t q8_capacity = 0;
     uint64_t q8_rows = 0;  // rows [0, q8_rows) are quantised and current
@@ -320,8 +321,8 @@ int launch_exchange_empty(const nm::PeerXchg &x, uint32_t k, uint64_t *scratch, 
 int launch_fill_synthetic(const Shard &sh, float *rows, uint64_t n, uint32_t dim, uint32_t pitch,
                           uint64_t seed, uint64_t global_row0, cudaStream_t stream);
 int launch_quantize(const Shard &sh, const float *rows, uint32_t pitch, uint32_t dim, uint64_t first,
-                    uint64_t n, int8_t *q8, uint32_t pitch8, nm::RowMeta *meta, uint32_t *flag,
-                    cudaStream_t stream);
+                    uint64_t n, int8_t *q8, uint32_t pitch8, nm::RowMeta *meta, float2 *norms,
+                    uint32_t *flag, cudaStream_t stream);
 
 // ---- nm_comm.cu ----
 nm::PeerXchg make_xchg(const nm_index *idx, uint32_t seq);

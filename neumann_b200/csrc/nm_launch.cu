@@ -571,6 +571,7 @@ int scan_queries_tc(nm_index *idx, const Shard &sh, Workspace &ws, const float *
         nm::TcGemmParams gp;
         memset(&gp, 0, sizeof(gp));
         gp.meta = sh.d_meta;
+        gp.norms = sh.d_norms;
         gp.qmeta = qmeta + q0;
         gp.coef = coef + q0;
         gp.kept = kept;
@@ -803,11 +804,11 @@ int launch_fill_synthetic(const Shard &sh, float *rows, uint64_t n, uint32_t dim
 }
 
 int launch_quantize(const Shard &sh, const float *rows, uint32_t pitch, uint32_t dim, uint64_t first,
-                    uint64_t n, int8_t *q8, uint32_t pitch8, nm::RowMeta *meta, uint32_t *flag,
-                    cudaStream_t stream) {
+                    uint64_t n, int8_t *q8, uint32_t pitch8, nm::RowMeta *meta, float2 *norms,
+                    uint32_t *flag, cudaStream_t stream) {
     uint32_t blocks = (uint32_t)std::min<uint64_t>((n + 7) / 8, (uint64_t)sh.sm_count * 16);
     nm::quantize_rows_kernel<<<blocks, 256, 0, stream>>>(rows, pitch, dim, first, n, q8, pitch8, meta,
-                                                         flag);
+                                                         norms, flag);
     CUDA_TRY(cudaGetLastError());
     return NM_OK;
 }

@@ -64,9 +64,11 @@ __device__ __forceinline__ float exact_score_row(const float *__restrict__ q,
 // ---------------------------------------------------------------------------------------
 // quantise rows [first, first + n): one warp per row
 // ---------------------------------------------------------------------------------------
+// norms[r] = (>= ||xt||_2, >= ||x / s_r - xt||_2): the Cauchy-Schwarz inputs of the batch
+// pre-filter's error bound (tc_prefilter_kernels.cuh); +inf for rows the analysis skips.
 __global__ void quantize_rows_kernel(const float *__restrict__ rows, uint32_t pitch, uint32_t dim,
                                      uint64_t first, uint64_t n, int8_t *q8, uint32_t pitch8,
-                                     RowMeta *meta, uint32_t *nonfinite_flag) {
+                                     RowMeta *meta, float2 *norms, uint32_t *nonfinite_flag) {
     const uint32_t lane = threadIdx.x & 31u;
     const uint64_t warp = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
     const uint64_t n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
@@ -91,7 +93,8 @@ __global__ void quantize_rows_kernel(const float *__restrict__ rows, uint32_t pi
             bad = true;
             scale = 0.0f;
         }
-        uint32_t x1 = 0;
+        uint32_t x1 = 0, x2 = 0;  // sum |xt|, sum xt^2 (exact: 127^2 dim < 2^32)
+        float dd = 0.0f;          // sum (x / s - xt)^2, every step rounded up
         int8_t *out = q8 + r * pitch8;
         for (uint32_t w = lane; w * 4u < pitch8; w += 32u) {
             uint32_t packed = 0;
@@ -100,16 +103,24 @@ __global__ void quantize_rows_kernel(const float *__restrict__ rows, uint32_t pi
                 const uint32_t i = w * 4u + b;
                 int v = 0;
                 if (i < dim && scale > 0.0f) {
-                    v = __float2int_rn(__fdiv_rn(x[i], scale));
+                    const float q = __fdiv_rn(x[i], scale);
+                    v = __float2int_rn(q);
                     v = max(-127, min(127, v));
+                    const float d = __fsub_rn(q, (float)v);  // exact (Sterbenz / small integers)
+                    dd = __fmaf_ru(d, d, dd);
                 }
                 x1 += (uint32_t)abs(v);
+                x2 += (uint32_t)(v * v);
                 packed |= ((uint32_t)(uint8_t)(int8_t)v) << (8 * b);
             }
             reinterpret_cast<uint32_t *>(out)[w] = packed;
         }
 #pragma unroll
-        for (int o = 16; o; o >>= 1) x1 += __shfl_xor_sync(0xffffffffu, x1, o);
+        for (int o = 16; o; o >>= 1) {
+            x1 += __shfl_xor_sync(0xffffffffu, x1, o);
+            x2 += __shfl_xor_sync(0xffffffffu, x2, o);
+            dd = __fadd_ru(dd, __shfl_xor_sync(0xffffffffu, dd, o));
+        }
         // reference-arithmetic magnitude: lanes 0..7 are the f32x8 lanes
         float acc = 0.0f;
         const uint32_t chunks = dim / 8u;
@@ -129,6 +140,12 @@ __global__ void quantize_rows_kernel(const float *__restrict__ rows, uint32_t pi
             m.rmag = __fsqrt_rn(ssq);
             m.flags = bad ? 1u : 0u;
             meta[r] = m;
+            if (norms) {
+                // the f32 quotient x / s is off by <= 127.01 * 2^-24 per element
+                const float dn = __fadd_ru(__fsqrt_ru(dd), __fmul_ru(7.7e-6f, __fsqrt_ru((float)dim)));
+                norms[r] = bad ? make_float2(INFINITY, INFINITY)
+                               : make_float2(__fsqrt_ru(__uint2float_ru(x2)), dn);
+            }
             if (bad) atomicOr(nonfinite_flag, 1u);
         }
     }

@@ -67,7 +67,7 @@ constexpr uint32_t kTcThreads = 32 * (kTcRoleWarps + kTcEpilogueWarps);
 constexpr uint32_t kTcKeptCap = 32768;                     // kept entries per query
 constexpr uint32_t kTcPhase0Rows = 2048;                   // first phase: keep everything (>= k)
 constexpr uint32_t kTcTmemCols = 512;                      // 2 accumulators x 256 columns
-constexpr uint32_t kTcPendCap = 48;                        // parked entries per epilogue warp
+constexpr uint32_t kTcPendCap = 40;                        // parked entries per epilogue warp
 constexpr uint32_t kTcPendDrain = 20;                      // drained once this many are parked
 
 constexpr uint32_t kTcFlagUnusable = 1u;   // query not finite / zero / denormal scale
@@ -85,8 +85,10 @@ struct alignas(16) TcQueryMeta {
     float qmag;          // reference lane-tree |q|
     uint32_t q1;         // sum |qt_i|
     uint32_t flags;      // kTcFlag*
+    float qnorm;         // >= ||qt||_2            (Cauchy-Schwarz form of the error bound)
+    float enorm;         // >= ||q / s_q - qt||_2
     uint32_t tau_ord;    // k-th best lower bound so far (0 = none yet)
-    uint32_t pad[3];
+    uint32_t pad;
 };
 
 // Phase control of one pass, device resident: the refine kernel sizes the next row range from
@@ -101,19 +103,12 @@ struct TcCtl {
     uint32_t pad[3];
 };
 
-// what the rigorous evaluation needs of a query: the first 32 bytes of TcQueryMeta, staged in
-// shared memory by the GEMM kernel
-struct alignas(16) TcQm {
-    double c_lo, c_hi;
-    float s_q;
-    float qmag;
-    uint32_t q1;
-    uint32_t flags;
-};
+// the GEMM kernel stages the whole records in shared memory for the rigorous evaluation
+using TcQm = TcQueryMeta;
 
 inline size_t tc_gemm_smem_bytes() {
     return 1024 + (size_t)kTcRingBytes + (size_t)kTcMaxQ * 16 + 256 +
-           (size_t)kTcEpilogueWarps * (kTcPendCap * 24 + 4) + (size_t)kTcMaxQ * 32 + 256;
+           (size_t)kTcEpilogueWarps * (kTcPendCap * 24 + 4) + (size_t)kTcMaxQ * 48 + 256;
 }
 
 #ifdef __CUDACC__
@@ -285,14 +280,21 @@ __device__ __forceinline__ void tc_row_sq_bounds(const RowMeta &m, uint32_t dim,
 
 // Rigorous interval of the reference score of (row, query) from the exact integer dot I.
 // wild == the analysis does not apply (non-finite data, possible overflow): always a candidate.
+// nr = (>= ||xt||_2, >= ||x / s_r - xt||_2) of the row (quantize_rows_kernel).  Each of the three
+// cross terms of  q.x = s_q s_r (I + qt.d + xt.e + e.d)  is bounded by the smaller of its
+// Hoelder (L1 x Linf) and Cauchy-Schwarz (L2 x L2) bounds; BL is the L1-only bound the epilogue
+// screen is built on (B <= BL, so everything kept here also passes the screen).
 template <class QM>
-__device__ __forceinline__ void tc_interval(int metric, int I, const RowMeta &m,
+__device__ __forceinline__ void tc_interval(int metric, int I, const RowMeta &m, const float2 nr,
                                             const QM &qm, uint32_t dim, uint32_t &lb_ord,
                                             uint32_t &ub_ord) {
     bool wild = (m.flags & 1u) != 0u || (qm.flags & kTcFlagUnusable) != 0u;
     const double g = 2.0 * ((double)dim + 16.0) * kTcU;
     const double ss = (double)qm.s_q * (double)m.scale;
-    const double B = 0.5001 * ((double)qm.q1 + (double)m.x1) + 0.2502 * (double)dim;
+    const double BL = 0.5001 * ((double)qm.q1 + (double)m.x1) + 0.2502 * (double)dim;
+    const double B = fmin(0.5001 * (double)qm.q1, (double)qm.qnorm * (double)nr.y) +
+                     fmin(0.5001 * (double)m.x1, (double)nr.x * (double)qm.enorm) +
+                     fmin(0.2502 * (double)dim, (double)qm.enorm * (double)nr.y);
     const double Dt = ss * (double)I;
     float lb, ub;
     if (metric == kEuclidean) {
@@ -312,7 +314,7 @@ __device__ __forceinline__ void tc_interval(int metric, int I, const RowMeta &m,
         ub = tc_l2_score(slo);
         lb = tc_l2_score(shi);
     } else {
-        const double S = 127.51 * (double)m.x1 + B;
+        const double S = 127.51 * (double)m.x1 + BL;
         const double E = (ss * (B + g * S)) * 1.000001 + 1e-37;
         const float lo = __double2float_rd(Dt - E), hi = __double2float_ru(Dt + E);
         if (!(ss * S < 1e37) || !(fabs(Dt) + E < 1e37)) wild = true;
@@ -458,6 +460,7 @@ tc_prepare_queries_kernel(const float *__restrict__ queries, uint32_t nq, uint32
     __shared__ float red_f[8];
     __shared__ uint32_t red_u[8];
     __shared__ double red_d[8];
+    __shared__ double red_e[8];
     __shared__ float qmag_s;
     const uint32_t q = blockIdx.x, t = threadIdx.x, lane = t & 31u, warp = t >> 5;
     uint32_t *out = reinterpret_cast<uint32_t *>(q8 + (size_t)q * pitch8);
@@ -510,6 +513,7 @@ tc_prepare_queries_kernel(const float *__restrict__ queries, uint32_t nq, uint32
     if (!(s_q >= 1e-15f)) bad = true;  // zero / tiny scale: the exact path decides
     __syncthreads();
     uint32_t q1 = 0;
+    double qq = 0.0, ee = 0.0;  // sum qt^2, sum (q / s_q - qt)^2
     for (uint32_t w = t; w * 4u < pitch8; w += 256u) {
         uint32_t packed = 0;
 #pragma unroll
@@ -517,13 +521,27 @@ tc_prepare_queries_kernel(const float *__restrict__ queries, uint32_t nq, uint32
             const uint32_t i = w * 4u + b;
             int x = 0;
             if (i < dim && !bad) {
-                x = __float2int_rn(__fdiv_rn(__ldg(v + i), s_q));
+                const float r = __fdiv_rn(__ldg(v + i), s_q);
+                x = __float2int_rn(r);
                 x = max(-127, min(127, x));
+                const double e = (double)r - (double)x;
+                qq += (double)(x * x);
+                ee += e * e;
             }
             q1 += (uint32_t)abs(x);
             packed |= ((uint32_t)(uint8_t)(int8_t)x) << (8 * b);
         }
         out[w] = packed;
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        qq += __shfl_xor_sync(0xffffffffu, qq, o);
+        ee += __shfl_xor_sync(0xffffffffu, ee, o);
+    }
+    __syncthreads();  // red_d is reused
+    if (lane == 0) {
+        red_d[warp] = qq;
+        red_e[warp] = ee;
     }
 #pragma unroll
     for (int o = 16; o; o >>= 1) q1 += __shfl_xor_sync(0xffffffffu, q1, o);
@@ -562,7 +580,17 @@ tc_prepare_queries_kernel(const float *__restrict__ queries, uint32_t nq, uint32
         m.q1 = q1;
         m.flags = bad ? kTcFlagUnusable : 0u;
         m.tau_ord = 0u;
-        m.pad[0] = m.pad[1] = m.pad[2] = 0u;
+        m.pad = 0u;
+        // ||qt||_2 exactly (integers), ||e||_2 with the f32 rounding of q / s_q (|r| <= 127.01,
+        // so each e_i is off by at most 7.6e-6) folded in; both rounded up
+        double qq2 = 0.0, ee2 = 0.0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) {
+            qq2 += red_d[w];
+            ee2 += red_e[w];
+        }
+        m.qnorm = __double2float_ru(sqrt(qq2) * (1.0 + 1e-9));
+        m.enorm = __double2float_ru((sqrt(ee2) + 7.7e-6 * sqrt((double)dim)) * (1.0 + 1e-9));
         qmeta[q] = m;
         coef[q] = bad ? tc_pass_none() : tc_pass_all(0u);
         kept_n[q] = bad ? 0u : min(n_rows, kTcPhase0Rows);  // phase 0 fills slots [0, rows)
@@ -575,6 +603,7 @@ tc_prepare_queries_kernel(const float *__restrict__ queries, uint32_t nq, uint32
 // ---------------------------------------------------------------------------------------
 struct TcGemmParams {
     const RowMeta *meta;        // [rows]
+    const float2 *norms;        // [rows] (||xt||_2, ||x / s_r - xt||_2), rounded up
     const TcQueryMeta *qmeta;   // [nq]
     const float4 *coef;         // [nq] screen coefficients of this phase
     TcKept *kept;               // [nq][kTcKeptCap]
@@ -611,8 +640,9 @@ __device__ __noinline__ void tc_keep_entry(const TcGemmParams &p, const TcQm *qm
                                            bool phase0) {
     const TcQm &qm = qm_s[q];
     if (qm.flags & kTcFlagUnusable) return;
+    const float2 nr = __ldg(p.norms + row);
     uint32_t lb_ord, ub_ord;
-    tc_interval(p.metric, I, m, qm, p.dim, lb_ord, ub_ord);
+    tc_interval(p.metric, I, m, nr, qm, p.dim, lb_ord, ub_ord);
     if (ub_ord < tau_ord) return;
     // the first phase keeps every row of [0, kTcPhase0Rows): slot == row, the list length was
     // set by the prepare kernel, no reservation needed
@@ -702,9 +732,8 @@ tc_gemm_filter_kernel(const __grid_constant__ CUtensorMap tmap_a,
             coef_s[i] = c;
         }
         if (tid < kTcEpilogueWarps) pend_cnt_s[tid] = 0u;
-        for (uint32_t i = tid; i < p.nq * 2u; i += kTcThreads)  // first 32 bytes of each record
-            reinterpret_cast<uint4 *>(qm_s)[i] =
-                reinterpret_cast<const uint4 *>(p.qmeta + (i >> 1))[i & 1u];
+        for (uint32_t i = tid; i < p.nq * 3u; i += kTcThreads)  // 48-byte records
+            reinterpret_cast<uint4 *>(qm_s)[i] = reinterpret_cast<const uint4 *>(p.qmeta)[i];
     }
     __syncthreads();
     if (tid < kTcMaxQ / 16u) {

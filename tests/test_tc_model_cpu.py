@@ -26,7 +26,14 @@ def quantise_rows(x):
         xt = np.where(scale[:, None] > 0, np.rint((x / scale[:, None]).astype(f32)), 0.0)
     xt = np.clip(np.nan_to_num(xt), -127, 127).astype(np.int64)
     rmag = np.array([o.magnitude(r) for r in x], f32)
-    return xt, scale, np.abs(xt).sum(axis=1), rmag, bad
+    # (>= ||xt||_2, >= ||x / s - xt||_2) as the kernel stores them: f32 quotient, slack for its
+    # rounding, rounded up
+    with np.errstate(divide="ignore", invalid="ignore"):
+        qf = np.where(scale[:, None] > 0, (x / scale[:, None]).astype(f32), 0.0).astype(np.float64)
+    d = np.nan_to_num(qf - xt)
+    xnorm = np.sqrt((xt.astype(np.float64) ** 2).sum(axis=1)) * (1 + 1e-7)
+    dnorm = (np.sqrt((d ** 2).sum(axis=1)) + 7.7e-6 * np.sqrt(x.shape[1])) * (1 + 1e-6)
+    return xt, scale, np.abs(xt).sum(axis=1), rmag, bad, xnorm, dnorm
 
 
 def quantise_query(q):
@@ -35,8 +42,11 @@ def quantise_query(q):
     bad = (not np.isfinite(q).all()) or not (s >= f32(1e-15))
     qt = np.zeros(q.shape, np.int64) if bad else np.clip(np.rint((q / s).astype(f32)), -127, 127).astype(np.int64)
     c = float(np.sum(q.astype(np.float64) ** 2))
+    e = np.zeros(q.shape) if bad else (q / s).astype(f32).astype(np.float64) - qt
+    qnorm = float(np.sqrt((qt.astype(np.float64) ** 2).sum())) * (1 + 1e-9)
+    enorm = (float(np.sqrt((e ** 2).sum())) + 7.7e-6 * np.sqrt(q.size)) * (1 + 1e-9)
     return qt, (f32(0) if bad else s), int(np.abs(qt).sum()), o.magnitude(q), bad, \
-        max(c * (1 - 1e-12) - 1e-40, 0.0), c * (1 + 1e-12) + 1e-40
+        max(c * (1 - 1e-12) - 1e-40, 0.0), c * (1 + 1e-12) + 1e-40, qnorm, enorm
 
 
 def rd(x):
@@ -58,12 +68,15 @@ def l2_score(s):
         return f32(1.0) / (f32(1.0) + np.sqrt(f32(s)))
 
 
-def interval(metric, I, scale, x1, rmag, bad_row, s_q, q1, qmag, c_lo, c_hi, dim):
+def interval(metric, I, scale, x1, rmag, bad_row, s_q, q1, qmag, c_lo, c_hi, dim, xnorm, dnorm,
+             qnorm, enorm):
     """-> (lb, ub, wild) as in tc_interval; wild == always a candidate."""
     wild = bool(bad_row)
     g = 2.0 * (dim + 16.0) * U
     ss = float(s_q) * float(scale)
-    B = 0.5001 * (q1 + x1) + 0.2502 * dim
+    BL = 0.5001 * (q1 + x1) + 0.2502 * dim
+    B = min(0.5001 * q1, qnorm * dnorm) + min(0.5001 * x1, xnorm * enorm) + \
+        min(0.2502 * dim, enorm * dnorm)
     Dt = ss * float(I)
     if metric == "euclidean":
         E = ss * B * 1.000001 + 1e-37
@@ -78,7 +91,7 @@ def interval(metric, I, scale, x1, rmag, bad_row, s_q, q1, qmag, c_lo, c_hi, dim
         slo = rd(lo) if lo > 0 else f32(0)
         shi = ru(hi) if hi > 0 else f32(0)
         return l2_score(shi), l2_score(slo), wild
-    S = 127.51 * x1 + B
+    S = 127.51 * x1 + BL
     E = ss * (B + g * S) * 1.000001 + 1e-37
     if not (ss * S < 1e37) or not (abs(Dt) + E < 1e37):
         return f32(0), f32(0), True
@@ -95,17 +108,17 @@ def interval(metric, I, scale, x1, rmag, bad_row, s_q, q1, qmag, c_lo, c_hi, dim
 
 def check(rows, queries, metric):
     n, dim = rows.shape
-    xt, scale, x1, rmag, bad = quantise_rows(rows)
+    xt, scale, x1, rmag, bad, xnorm, dnorm = quantise_rows(rows)
     width = []
     for q in queries:
-        qt, s_q, q1, qmag, qbad, c_lo, c_hi = quantise_query(q)
+        qt, s_q, q1, qmag, qbad, c_lo, c_hi, qnorm, enorm = quantise_query(q)
         if qbad:
             continue                      # such queries are redone by the exact path
         exact = o.score_rows(rows, q, metric)
         dots = xt @ qt
         for r in range(n):
             lb, ub, wild = interval(metric, int(dots[r]), scale[r], int(x1[r]), rmag[r], bad[r],
-                                    s_q, q1, qmag, c_lo, c_hi, dim)
+                                    s_q, q1, qmag, c_lo, c_hi, dim, xnorm[r], dnorm[r], qnorm, enorm)
             if wild:
                 continue
             e = exact[r]
