@@ -767,7 +767,7 @@ tc_gemm_filter_kernel(const __grid_constant__ CUtensorMap tmap_a,
             for (uint32_t t = unit; t < n_tiles; t += n_units) {
                 const int32_t row0 = (int32_t)(row_begin + t * kTileRows + cr * kTcM);
                 for (uint32_t kb = 0; kb < n_kb; ++kb) {
-                    mbar_wait_wd<96>(&empty_bar[stage], phase ^ 1u);
+                    mbar_wait_wd<20>(&empty_bar[stage], phase ^ 1u);
                     uint8_t *sa = ring + stage * kStageBytes;
                     if (CTAS == 2) {
                         if (cr == 0u) mbar_arrive_expect_tx(&full_bar[stage], tx);
