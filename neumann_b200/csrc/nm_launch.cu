@@ -439,7 +439,7 @@ int launch_prefiltered(nm_index *idx, const Shard &sh, Workspace &ws, const floa
 }
 
 // ---- tensor-core batch pre-filter (tc_prefilter_kernels.cuh) ------------------------------
-constexpr uint32_t kTcSortBuckets = 65536;  // row buckets of the re-score ordering
+constexpr uint32_t kTcSortBuckets = 8192;  // row buckets of the re-score ordering
 constexpr uint32_t kTcMinRows = 65536;  // below this the exact kernels are cheaper
 
 bool tc_usable(const nm_index *idx, const Shard &sh, uint32_t nq, uint32_t k, int metric,
