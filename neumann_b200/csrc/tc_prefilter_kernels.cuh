@@ -55,8 +55,15 @@ constexpr uint32_t kTcMaxQ = 256;                          // queries per pass =
 // cluster each stage their own 128 corpus rows and HALF of the queries (16 + 16 KiB, 6 stages)
 // and one UMMA of M = 256 reads both halves, so the query bytes each SM pulls from L2 halve
 // and more k-blocks are in flight: the loop is bound by bytes in flight / memory latency.
+// The loop is bound by SHARED-MEMORY bandwidth, not by HBM or the tensor pipe: every operand
+// byte is written once by TMA and read once by the UMMA (s8 x s8 at N = 256 reads 96 B/clk,
+// restaging the queries for every corpus tile writes another 64-96 B/clk, the SM moves
+// 128 B/clk).  So whenever this CTA's share of the int8 queries fits beside >= 5 corpus stages
+// it is staged ONCE per launch ("resident": 256 queries x dim <= 896 on a pair, any dim for
+// small batches) and the ring carries only corpus tiles (16 KiB stages, up to 10).
 constexpr uint32_t kTcStages1 = 4;
 constexpr uint32_t kTcStages2 = 6;
+constexpr uint32_t kTcMaxStages = 10;
 constexpr uint32_t kTcRingBytes = 192u * 1024u;
 constexpr uint32_t kTcABytes = kTcM * kTcKBytes;           // 16 KiB
 constexpr uint32_t kTcBBytesMax = kTcMaxQ * kTcKBytes;     // 32 KiB
@@ -663,8 +670,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
 tc_gemm_filter_kernel(const __grid_constant__ CUtensorMap tmap_a,
                       const __grid_constant__ CUtensorMap tmap_q,
                       const __grid_constant__ TcGemmParams p) {
-    constexpr uint32_t kStages = CTAS == 2 ? kTcStages2 : kTcStages1;
-    constexpr uint32_t kStageBytes = kTcRingBytes / kStages;       // 48 KiB / 32 KiB
+    constexpr uint32_t kStagesStream = CTAS == 2 ? kTcStages2 : kTcStages1;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t *ring = smem;                                          // stage: [A 16 KiB][B ...]
@@ -674,10 +680,11 @@ tc_gemm_filter_kernel(const __grid_constant__ CUtensorMap tmap_a,
     uint32_t *pend_cnt_s = reinterpret_cast<uint32_t *>(pend_s + kTcEpilogueWarps * kTcPendCap);
     TcQm *qm_s = reinterpret_cast<TcQm *>(pend_cnt_s + kTcEpilogueWarps);  // [256]
     uint64_t *full_bar = reinterpret_cast<uint64_t *>(qm_s + kTcMaxQ);
-    uint64_t *empty_bar = full_bar + kTcStages2;
-    uint64_t *tfull_bar = empty_bar + kTcStages2;  // [2] accumulator ready
-    uint64_t *tempty_bar = tfull_bar + 2;          // [2] accumulator drained
-    uint32_t *tmem_base_s = reinterpret_cast<uint32_t *>(tempty_bar + 2);
+    uint64_t *empty_bar = full_bar + kTcMaxStages;
+    uint64_t *tfull_bar = empty_bar + kTcMaxStages;  // [2] accumulator ready
+    uint64_t *tempty_bar = tfull_bar + 2;            // [2] accumulator drained
+    uint64_t *bfull_bar = tempty_bar + 2;            // resident queries staged
+    uint32_t *tmem_base_s = reinterpret_cast<uint32_t *>(bfull_bar + 1);
 
     const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31u;
     const uint32_t row_begin = p.ctl->row_begin, row_end = min(p.ctl->row_end, p.n_rows);
@@ -688,12 +695,19 @@ tc_gemm_filter_kernel(const __grid_constant__ CUtensorMap tmap_a,
     const uint32_t n_tiles = (row_end - row_begin + kTileRows - 1) / kTileRows;
     const uint32_t n_kb = (p.dim + kTcKBytes - 1) / kTcKBytes;
     const uint32_t n_b = p.n_pad / CTAS;           // query rows this CTA stages per k-block
+    const uint32_t b_bytes = (n_b * kTcKBytes + 1023u) & ~1023u;
+    const bool resident = n_kb * b_bytes + 5u * kTcABytes <= kTcRingBytes;
+    const uint32_t kStages =
+        resident ? min(kTcMaxStages, (kTcRingBytes - n_kb * b_bytes) / kTcABytes) : kStagesStream;
+    const uint32_t kStageBytes = resident ? kTcABytes : kTcRingBytes / kStagesStream;
+    uint8_t *ring_a = ring + (resident ? n_kb * b_bytes : 0u);  // resident queries come first
 
     if (tid == 0) {
-        for (uint32_t s = 0; s < kStages; ++s) {
+        for (uint32_t s = 0; s < kTcMaxStages; ++s) {
             mbar_init(&full_bar[s], 1);
             mbar_init(&empty_bar[s], 1);
         }
+        mbar_init(bfull_bar, 1);
         for (uint32_t a = 0; a < 2; ++a) {
             mbar_init(&tfull_bar[a], 1);
             // 1 CTA: one arrive per epilogue warp.  Pair: one per CTA on the leader's barrier (a
@@ -762,25 +776,39 @@ tc_gemm_filter_kernel(const __grid_constant__ CUtensorMap tmap_a,
         if (lane == 0) {
             const uint64_t pol_a = p.evict_first ? policy_evict_first() : policy_evict_normal();
             const uint64_t pol_q = policy_evict_normal();
-            const uint32_t tx = (kTcABytes + n_b * kTcKBytes) * CTAS;  // both CTAs' bytes
+            const uint32_t tx = (kTcABytes + (resident ? 0u : n_b * kTcKBytes)) * CTAS;  // pair: both
+            const uint32_t lead_bfull = CTAS == 2 ? mapa_shared(smem_u32(bfull_bar), 0u) : 0u;
+            if (resident) {  // this CTA's share of the queries, once
+                if (cr == 0u) mbar_arrive_expect_tx(bfull_bar, n_kb * n_b * kTcKBytes * CTAS);
+                for (uint32_t kb = 0; kb < n_kb; ++kb) {
+                    if (CTAS == 2)
+                        tma_load_2d_pair(ring + kb * b_bytes, &tmap_q, (int32_t)(kb * kTcKBytes),
+                                         (int32_t)(cr * n_b), lead_bfull, pol_q);
+                    else
+                        tma_load_2d(ring + kb * b_bytes, &tmap_q, (int32_t)(kb * kTcKBytes), 0,
+                                    bfull_bar, pol_q);
+                }
+            }
             uint32_t stage = 0, phase = 0;
             for (uint32_t t = unit; t < n_tiles; t += n_units) {
                 const int32_t row0 = (int32_t)(row_begin + t * kTileRows + cr * kTcM);
                 for (uint32_t kb = 0; kb < n_kb; ++kb) {
                     mbar_wait_wd<20>(&empty_bar[stage], phase ^ 1u);
-                    uint8_t *sa = ring + stage * kStageBytes;
+                    uint8_t *sa = ring_a + stage * kStageBytes;
                     if (CTAS == 2) {
                         if (cr == 0u) mbar_arrive_expect_tx(&full_bar[stage], tx);
                         const uint32_t fb = lead_full0 + stage * 8u;
                         tma_load_2d_pair(sa, &tmap_a, (int32_t)(kb * kTcKBytes), row0, fb, pol_a);
-                        tma_load_2d_pair(sa + kTcABytes, &tmap_q, (int32_t)(kb * kTcKBytes),
-                                         (int32_t)(cr * n_b), fb, pol_q);
+                        if (!resident)
+                            tma_load_2d_pair(sa + kTcABytes, &tmap_q, (int32_t)(kb * kTcKBytes),
+                                             (int32_t)(cr * n_b), fb, pol_q);
                     } else {
                         mbar_arrive_expect_tx(&full_bar[stage], tx);
                         tma_load_2d(sa, &tmap_a, (int32_t)(kb * kTcKBytes), row0, &full_bar[stage],
                                     pol_a);
-                        tma_load_2d(sa + kTcABytes, &tmap_q, (int32_t)(kb * kTcKBytes), 0,
-                                    &full_bar[stage], pol_q);
+                        if (!resident)
+                            tma_load_2d(sa + kTcABytes, &tmap_q, (int32_t)(kb * kTcKBytes), 0,
+                                        &full_bar[stage], pol_q);
                     }
                     if (++stage == kStages) {
                         stage = 0;
@@ -794,6 +822,7 @@ tc_gemm_filter_kernel(const __grid_constant__ CUtensorMap tmap_a,
         // ===== MMA issuer: one thread (of the leader CTA) =====
         if (lane == 0 && cr == 0u) {
             const uint32_t idesc = tc_idesc_i8(kTcM * CTAS, p.n_pad);
+            if (resident) mbar_wait_wd<0>(bfull_bar, 0u);
             uint32_t stage = 0, phase = 0, it = 0;
             for (uint32_t t = unit; t < n_tiles; t += n_units, ++it) {
                 const uint32_t acc = it & 1u, aph = (it >> 1) & 1u;
@@ -803,9 +832,10 @@ tc_gemm_filter_kernel(const __grid_constant__ CUtensorMap tmap_a,
                 for (uint32_t kb = 0; kb < n_kb; ++kb) {
                     mbar_wait_wd<0>(&full_bar[stage], phase);
                     tc_fence_after();
-                    const uint32_t sa = smem_u32(ring + stage * kStageBytes);
+                    const uint32_t sa = smem_u32(ring_a + stage * kStageBytes);
                     const uint64_t adesc = tc_smem_desc(sa);
-                    const uint64_t bdesc = tc_smem_desc(sa + kTcABytes);
+                    const uint64_t bdesc =
+                        tc_smem_desc(resident ? smem_u32(ring + kb * b_bytes) : sa + kTcABytes);
 #pragma unroll
                     for (uint32_t ks = 0; ks < kTcKBytes / 32u; ++ks) {  // UMMA K = 32 int8 = 32 B
                         if (CTAS == 2)
