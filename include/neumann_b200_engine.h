@@ -28,6 +28,8 @@ typedef struct nm_engine_config {
     int64_t search_timeout_ms;   /* < 0 = None */
     int n_devices;               /* 0 = current device */
     int devices[8];
+    int device_prefilter;        /* 1 = int8 copy of every mirror: dp4a / tensor-core pre-filters
+                                    (bit-identical results; device-side addition, default 0) */
 } nm_engine_config;
 
 void nm_engine_config_default(nm_engine_config *cfg);
@@ -46,6 +48,11 @@ int nm_engine_search_similar(nm_engine *e, const float *query, size_t n, size_t 
                              nm_results **out);
 int nm_engine_search_similar_with_metric(nm_engine *e, const float *query, size_t n, size_t top_k,
                                          int metric, nm_results **out);
+/* Batch form (no reference counterpart: there a batch is nq calls): queries [nq, n] row-major,
+ * out[i] = what nm_engine_search_similar_with_metric returns for query i.  out must hold nq
+ * pointers; free each with nm_results_free. */
+int nm_engine_search_similar_batch(nm_engine *e, const float *queries, size_t nq, size_t n,
+                                   size_t top_k, int metric, nm_results **out);
 int nm_engine_compute_similarity(const float *a, size_t na, const float *b, size_t nb,
                                  float *out);
 

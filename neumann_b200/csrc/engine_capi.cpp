@@ -76,6 +76,7 @@ int nm_engine_create(const nm_engine_config *cfg, nm_engine **out) {
         if (cfg->search_timeout_ms >= 0)
             c.search_timeout = std::chrono::milliseconds(cfg->search_timeout_ms);
         for (int i = 0; i < cfg->n_devices && i < 8; ++i) c.devices.push_back(cfg->devices[i]);
+        c.device_prefilter = cfg->device_prefilter != 0;
     }
     auto r = VectorEngine::with_config(std::move(c));
     if (r.is_err()) return fail(r.error());
@@ -127,6 +128,24 @@ int nm_engine_search_similar_with_metric(nm_engine *e, const float *query, size_
     if (metric < 0 || metric > 2) return fail(NM_ERR_INVALID_ARGUMENT, "unknown metric");
     std::vector<float> q(query, query + (query ? n : 0));
     return give(e->engine->search_similar_with_metric(q, top_k, (DistanceMetric)metric), out);
+}
+
+int nm_engine_search_similar_batch(nm_engine *e, const float *queries, size_t nq, size_t n,
+                                   size_t top_k, int metric, nm_results **out) {
+    if (!e || !out) return fail(NM_ERR_INVALID_ARGUMENT, "null argument");
+    if (metric < 0 || metric > 2) return fail(NM_ERR_INVALID_ARGUMENT, "unknown metric");
+    for (size_t i = 0; i < nq; ++i) out[i] = nullptr;
+    std::vector<std::vector<float>> qs(nq);
+    for (size_t i = 0; i < nq; ++i)
+        qs[i].assign(queries + i * n, queries + (queries ? (i + 1) * n : i * n));
+    auto r = e->engine->search_similar_batch(qs, top_k, (DistanceMetric)metric);
+    if (r.is_err()) return fail(r.error());
+    for (size_t i = 0; i < nq; ++i) {
+        auto *res = new nm_results();
+        res->hits = std::move(r.value()[i]);
+        out[i] = res;
+    }
+    return NM_OK;
 }
 
 int nm_engine_compute_similarity(const float *a, size_t na, const float *b, size_t nb,

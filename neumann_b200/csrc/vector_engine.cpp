@@ -286,6 +286,10 @@ Result<std::vector<SearchResult>> VectorEngine::scan_space(
             const int *devs = config_.devices.empty() ? nullptr : config_.devices.data();
             int rc = nm_index_create(b.dim, devs, (int)config_.devices.size(), &b.mirror);
             if (rc) return storage_from_nm(rc);
+            if (config_.device_prefilter) {
+                rc = nm_index_set_prefilter(b.mirror, 1);
+                if (rc) return storage_from_nm(rc);
+            }
         }
         if (b.synced_rows < b.keys.size()) {
             int rc = nm_index_append(b.mirror, &b.rows[b.synced_rows * (size_t)b.dim],
@@ -314,6 +318,61 @@ Result<std::vector<SearchResult>> VectorEngine::scan_space(
     std::vector<SearchResult> out;
     out.reserve(count);
     for (uint32_t i = 0; i < count; ++i) out.push_back(SearchResult{b.keys[rows[i]], scores[i]});
+    return out;
+}
+
+Result<std::vector<std::vector<SearchResult>>> VectorEngine::scan_space_batch(
+    const Space &sp, const float *queries, size_t nq, size_t dim, size_t top_k,
+    DistanceMetric metric, const char *operation,
+    std::chrono::steady_clock::time_point start) const {
+    auto expired = [&]() {
+        if (!config_.search_timeout) return false;
+        return std::chrono::steady_clock::now() - start >= *config_.search_timeout;
+    };
+    auto timeout_err = [&]() {
+        VectorError e;
+        e.kind = ErrorKind::SearchTimeout;
+        e.operation = operation;
+        e.timeout_ms = (uint64_t)config_.search_timeout->count();
+        return e;
+    };
+    std::vector<std::vector<SearchResult>> out(nq);
+    std::shared_lock<std::shared_mutex> g(sp.mu);
+    auto bit = sp.buckets.find((uint32_t)dim);
+    if (expired()) return timeout_err();
+    if (bit == sp.buckets.end() || bit->second->keys.empty()) return out;
+    Bucket &b = *bit->second;
+    {
+        std::lock_guard<std::mutex> sg(b.sync_mu);
+        if (!b.mirror) {
+            const int *devs = config_.devices.empty() ? nullptr : config_.devices.data();
+            int rc = nm_index_create(b.dim, devs, (int)config_.devices.size(), &b.mirror);
+            if (rc) return storage_from_nm(rc);
+            if (config_.device_prefilter) {
+                rc = nm_index_set_prefilter(b.mirror, 1);
+                if (rc) return storage_from_nm(rc);
+            }
+        }
+        if (b.synced_rows < b.keys.size()) {
+            int rc = nm_index_append(b.mirror, &b.rows[b.synced_rows * (size_t)b.dim],
+                                     b.keys.size() - b.synced_rows);
+            if (rc) return storage_from_nm(rc);
+            b.synced_rows = b.keys.size();
+        }
+    }
+    const size_t k = std::min<size_t>(top_k, b.keys.size());
+    std::vector<uint64_t> rows(nq * k);
+    std::vector<float> scores(nq * k);
+    std::vector<uint32_t> counts(nq, 0);
+    int rc = nm_search(b.mirror, queries, (uint32_t)nq, (uint32_t)k, (int)metric, rows.data(),
+                       scores.data(), counts.data());
+    if (rc) return storage_from_nm(rc);
+    if (expired()) return timeout_err();
+    for (size_t q = 0; q < nq; ++q) {
+        out[q].reserve(counts[q]);
+        for (uint32_t i = 0; i < counts[q]; ++i)
+            out[q].push_back(SearchResult{b.keys[rows[q * k + i]], scores[q * k + i]});
+    }
     return out;
 }
 
@@ -392,6 +451,37 @@ Result<std::vector<SearchResult>> VectorEngine::search_similar_with_metric(
     if (qmag == 0.0f && metric != DistanceMetric::Euclidean)  // lib.rs:2066
         return std::vector<SearchResult>{};
     return scan_space(*default_space_, query, top_k, metric, "search_similar_with_metric", start);
+}
+
+Result<std::vector<std::vector<SearchResult>>> VectorEngine::search_similar_batch(
+    const std::vector<std::vector<float>> &queries, size_t top_k, DistanceMetric metric) const {
+    auto start = std::chrono::steady_clock::now();
+    // the checks of search_similar_with_metric, in call order (lib.rs:2049-2066)
+    for (auto &q : queries) {
+        if (q.empty()) return err(ErrorKind::EmptyVector);
+        if (top_k == 0) return err(ErrorKind::InvalidTopK);
+    }
+    std::vector<std::vector<SearchResult>> out(queries.size());
+    // queries of one dimension share a device call; zero-magnitude queries short-circuit
+    std::map<size_t, std::vector<size_t>> by_dim;
+    for (size_t i = 0; i < queries.size(); ++i) {
+        const auto &q = queries[i];
+        if (metric != DistanceMetric::Euclidean && simd::magnitude(q.data(), q.size()) == 0.0f)
+            continue;
+        by_dim[q.size()].push_back(i);
+    }
+    for (auto &kv : by_dim) {
+        const size_t dim = kv.first, nq = kv.second.size();
+        std::vector<float> flat(nq * dim);
+        for (size_t j = 0; j < nq; ++j)
+            std::copy(queries[kv.second[j]].begin(), queries[kv.second[j]].end(),
+                      flat.begin() + j * dim);
+        auto r = scan_space_batch(*default_space_, flat.data(), nq, dim, top_k, metric,
+                                  "search_similar_batch", start);
+        if (r.is_err()) return r.error();
+        for (size_t j = 0; j < nq; ++j) out[kv.second[j]] = std::move(r.value()[j]);
+    }
+    return out;
 }
 
 Result<float> VectorEngine::compute_similarity(const std::vector<float> &a,

@@ -85,6 +85,10 @@ struct VectorEngineConfig {
     size_t batch_parallel_threshold = 100;
     std::optional<std::chrono::milliseconds> search_timeout;
     std::vector<int> devices;  // empty = current device
+    // Device-side addition: keep an int8 copy of every mirror (nm_index_set_prefilter) so that
+    // single queries use the dp4a pre-filter and batches / coalesced concurrent callers the
+    // tensor-core pre-filter.  Results are bit-identical either way; costs +1 byte per element.
+    bool device_prefilter = false;
     Result<Unit> validate() const;  // lib.rs:771-826
 };
 
@@ -132,6 +136,13 @@ class VectorEngine {
     Result<std::vector<SearchResult>> search_similar_with_metric(const std::vector<float> &query,
                                                                  size_t top_k,
                                                                  DistanceMetric metric) const;
+    // Batch form of search_similar_with_metric (no reference counterpart: there a batch is N
+    // calls, e.g. the gRPC PointsService loop, neumann_server/src/service/points.rs:410-480).
+    // Element i is exactly what search_similar_with_metric(queries[i], top_k, metric) returns;
+    // an invalid query fails the whole call with the error that call would give.  Queries of
+    // one dimension share device passes (batched kernels / tensor-core pre-filter).
+    Result<std::vector<std::vector<SearchResult>>> search_similar_batch(
+        const std::vector<std::vector<float>> &queries, size_t top_k, DistanceMetric metric) const;
     // metadata + filtered search: lib.rs:2930-3010 (store/get metadata), :3429-3557
     // (search_similar_filtered, pre/post filter), :1698-1829 (search_filtered_in_collection),
     // :3690-3735 (selectivity / count / list).  Pre-filter = device scan under a row bitmask.
@@ -227,6 +238,11 @@ class VectorEngine {
                                                  const char *operation,
                                                  std::chrono::steady_clock::time_point start,
                                                  const FilterCondition *pre_filter = nullptr) const;
+    // nq queries of one dimension (row-major) over one space: one nm_search call
+    Result<std::vector<std::vector<SearchResult>>> scan_space_batch(
+        const Space &sp, const float *queries, size_t nq, size_t dim, size_t top_k,
+        DistanceMetric metric, const char *operation,
+        std::chrono::steady_clock::time_point start) const;
 };
 
 }  // namespace neumann

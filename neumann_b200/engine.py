@@ -39,6 +39,7 @@ class NmEngineConfig(C.Structure):
         ("parallel_threshold", C.c_uint64), ("default_metric", C.c_int),
         ("max_dimension", C.c_uint64), ("search_timeout_ms", C.c_int64),
         ("n_devices", C.c_int), ("devices", C.c_int * 8),
+        ("device_prefilter", C.c_int),
     ]
 
 
@@ -56,6 +57,7 @@ ENGINE_SIGNATURES = {
     "nm_engine_count": (_u64, [_vp]),
     "nm_engine_search_similar": (C.c_int, [_vp, _vp, _sz, _sz, _pvp]),
     "nm_engine_search_similar_with_metric": (C.c_int, [_vp, _vp, _sz, _sz, C.c_int, _pvp]),
+    "nm_engine_search_similar_batch": (C.c_int, [_vp, _vp, _sz, _sz, _sz, C.c_int, _pvp]),
     "nm_engine_compute_similarity": (C.c_int, [_vp, _sz, _vp, _sz, C.POINTER(C.c_float)]),
     "nm_engine_create_collection": (C.c_int, [_vp, _cp, _u64, C.c_int]),
     "nm_engine_delete_collection": (C.c_int, [_vp, _cp]),
@@ -141,10 +143,11 @@ def _take(handle: C.c_void_p) -> list[SearchResult]:
 class VectorEngine:
     def __init__(self, *, sparse_threshold: float | None = None, parallel_threshold: int | None = None,
                  max_dimension: int | None = None, search_timeout_ms: int | None = None,
-                 devices: list[int] | None = None):
+                 devices: list[int] | None = None, device_prefilter: bool = False):
         l = _lib()
         cfg = NmEngineConfig()
         l.nm_engine_config_default(C.byref(cfg))
+        cfg.device_prefilter = 1 if device_prefilter else 0
         if sparse_threshold is not None:
             cfg.sparse_threshold = sparse_threshold
         if parallel_threshold is not None:
@@ -193,6 +196,17 @@ class VectorEngine:
         return int(_lib().nm_engine_count(self._h))
 
     # ---- search side ----
+    def search_similar_batch(self, queries, top_k: int, metric: int = 0) -> list[list[SearchResult]]:
+        """queries: [nq, dim]; element i == search_similar_with_metric(queries[i], top_k, metric)."""
+        q = np.ascontiguousarray(np.asarray(queries, dtype=np.float32))
+        if q.ndim != 2:
+            raise ValueError("queries must be [nq, dim]")
+        nq = q.shape[0]
+        hs = (C.c_void_p * max(nq, 1))()
+        _check(_lib().nm_engine_search_similar_batch(self._h, q.ctypes.data, nq, q.shape[1], top_k,
+                                                     int(metric), hs))
+        return [_take(C.c_void_p(hs[i])) for i in range(nq)]
+
     def search_similar(self, query, top_k: int) -> list[SearchResult]:
         q = _f32(query)
         h = C.c_void_p()

@@ -142,6 +142,16 @@ def test_engine_validation_order_and_short_circuits():
     assert e.search_similar_with_metric([0.0, 0.0], 5, eng.DOT_PRODUCT) == []
     # no rows of the query's dimension: empty result, no device work
     assert e.search_similar([1.0, 0.0, 0.0], 5) == []
+    # the batch form applies the same checks per query, in the same order
+    assert e.search_similar_batch(np.zeros((3, 2), np.float32), 5, eng.COSINE) == [[], [], []]
+    assert e.search_similar_batch(np.ones((2, 3), np.float32), 5, eng.EUCLIDEAN) == [[], []]
+    assert e.search_similar_batch(np.zeros((0, 2), np.float32), 5, eng.COSINE) == []
+    with pytest.raises(eng.VectorError) as ei:
+        e.search_similar_batch(np.ones((2, 2), np.float32), 0, eng.COSINE)
+    assert ei.value.kind == "InvalidTopK"
+    with pytest.raises(eng.VectorError) as ei:
+        e.search_similar_batch(np.zeros((2, 0), np.float32), 3, eng.COSINE)
+    assert ei.value.kind == "EmptyVector"
 
 
 def test_engine_config_validation():

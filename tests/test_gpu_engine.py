@@ -111,6 +111,33 @@ def test_engine_results_match_oracle_order_and_bits():
         assert [np.float32(r.score).view(np.uint32) for r in res] == list(es.view(np.uint32))
 
 
+def test_search_similar_batch_matches_single_calls_and_oracle():
+    """search_similar_batch[i] == search_similar_with_metric(queries[i]): through the exact batched
+    kernels by default, through the dp4a / tensor-core pre-filters with device_prefilter=True."""
+    n, d, k = 70_000, 40, 9
+    rows = o.fill_synthetic(n, d, 12)
+    qs = o.fill_synthetic(7, d, 13)
+    qs[3] = 0.0                                   # zero query: empty for cosine / dot
+    for pre in (False, True):
+        e = eng.VectorEngine(device_prefilter=pre)
+        for i in range(n):
+            e.store_embedding(f"k{i}", rows[i])
+        for name, mid in METRIC_ID.items():
+            res = e.search_similar_batch(qs, k, mid)
+            assert len(res) == 7
+            for i in range(7):
+                single = e.search_similar_with_metric(qs[i], k, mid)
+                assert [(r.key, np.float32(r.score).view(np.uint32)) for r in res[i]] == \
+                       [(r.key, np.float32(r.score).view(np.uint32)) for r in single], (pre, name, i)
+                if i == 3 and name != "euclidean":
+                    assert res[i] == []
+                    continue
+                er, es = o.search(rows, qs[i], k, name, threads=8)
+                assert [r.key for r in res[i]] == [f"k{int(j)}" for j in er], (pre, name, i)
+                assert [np.float32(r.score).view(np.uint32) for r in res[i]] == list(es.view(np.uint32))
+        e.close()
+
+
 def test_collections_on_gpu():
     e = eng.VectorEngine()
     e.create_collection("euc", dimension=2, metric=eng.EUCLIDEAN)
