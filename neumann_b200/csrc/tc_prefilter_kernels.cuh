@@ -26,22 +26,33 @@
 //                               the reference score (same error model as the 1-query
 //                               pre-filter, extended to the scalar L2 chain); an entry is kept
 //                               only if ub can still reach the query's running threshold tau
-//                               (k-th best lb so far).  A 5-instruction f32 test with provable
-//                               slack screens every (row, query); the few that pass are
-//                               re-evaluated rigorously in double and appended to the query's
+//                               (a score that k rows seen so far reach).  A coarse test per
+//                               16-query chunk and a 6-instruction f32 test with provable
+//                               slack screen every (row, query); the few that pass are parked
+//                               in shared memory and, once the accumulator has been released,
+//                               evaluated rigorously in double and appended to the query's
 //                               kept list.
-//   tc_refine_kernel            per query: radix-select the k-th best lb of the kept list ->
-//                               new tau, compact the list to ub >= tau, derive the screen
-//                               coefficients for the next phase.
-//   tc_rescore_kernel           per query: survivors are re-scored from the f32 mirror with
-//                               the reference arithmetic and selected exactly like the f32
-//                               scan (same keys, same tie rule).
+//   tc_refine_kernel            per query: radix-select the k-th best lb of the kept list,
+//                               re-score the k entries with the best lower bounds exactly and
+//                               take the k-th best exact score as tau, compact the list to
+//                               ub >= tau, derive the screen coefficients and the row range of
+//                               the next phase (control block in device memory).
+//   tc_sort_* / tc_score_sorted_kernel / tc_select_kernel
+//                               survivors of all queries bucket-sorted by row and re-scored
+//                               from the f32 mirror in corpus order with the reference
+//                               arithmetic (a scattered gather is bound by address
+//                               translation: 1.2 vs 4.3 TB/s), then selected per query exactly
+//                               like the f32 scan (same keys, same tie rule).
+//                               (tc_rescore_kernel: the per-query form, for dim % 4 != 0.)
+//   tc_pack_hits_kernel         sharded indexes: a shard's result as ShardHit[nq, k].
 //
-// The corpus is walked in phases of geometrically growing row ranges (first 16 Ki rows: keep
-// everything; then x4..x16 each) with a refine step between phases, so tau tightens while only
-// ~k..16k entries per query and phase are kept.  Every row of the exact top-k has
-// ub >= score >= tau, so the result is bit-identical to the f32 scan; a query whose list
-// overflows or that is not finite is flagged and redone by the exact path.
+// The corpus is walked in phases of geometrically growing row ranges (first 2048 rows: keep
+// everything; then x4..x15 each, sized on the device from the pass rate just observed) with a
+// refine step between phases, so tau tightens while only ~k..16k entries per query and phase
+// are kept.  Every row of the exact top-k has ub >= score >= tau, so the result is
+// bit-identical to the f32 scan; a query whose list overflows or that is not finite is flagged
+// and redone by the exact path.  tests/test_tc_model_cpu.py and tests/test_tc_screen_cpu.py
+// restate the interval and the screen in numpy; keep their constants in step with this file.
 #pragma once
 #include "prefilter_kernels.cuh"
 
