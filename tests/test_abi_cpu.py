@@ -70,6 +70,33 @@ def test_product_sass_uses_tma_and_no_fma_in_lane_arithmetic():
         assert c.count("FFMA") < 40  # sqrt/div expansions only
 
 
+def test_product_sass_tensor_core_prefilter():
+    """Static evidence for the batch pre-filter: the GEMM is tcgen05 (UTCIMMA = kind::i8) on CTA
+    pairs with TMA-staged operands, TMEM reads in the epilogue and multicast commits; the exact
+    re-score kernels accumulate with separate FMUL/FADD like the scan."""
+    import shutil, subprocess
+    if not shutil.which("cuobjdump"):
+        pytest.skip("cuobjdump not on PATH")
+    so = ROOT / "neumann_b200" / "libneumann_b200.so"
+    sass = subprocess.run(["cuobjdump", "-sass", str(so)], capture_output=True, text=True).stdout
+    chunks = sass.split("Function : ")
+    gemm = [c for c in chunks if "tc_gemm_filter_kernel" in c.split("\n", 1)[0]]
+    assert len(gemm) == 2                                   # <1> and <2>
+    pair = [c for c in gemm if "UTCIMMA.2CTA" in c]
+    assert len(pair) == 1
+    for mnemonic in ("UTCIMMA.2CTA", "UTMALDG.2D.2CTA", "UTCBAR.2CTA.MULTICAST", "LDTM.x16",
+                     "UCGABAR_ARV"):
+        assert mnemonic in pair[0], mnemonic
+    single = [c for c in gemm if c is not pair[0]][0]
+    assert "UTCIMMA" in single and "UTMALDG.2D" in single and "LDTM.x16" in single
+    for name in ("tc_score_sorted_kernel", "tc_refine_kernel"):
+        ks = [c for c in chunks if name in c.split("\n", 1)[0]]
+        assert len(ks) == 1
+        assert ks[0].count("FMUL") > 30 and ks[0].count("FADD") > 30
+        assert "HMMA" not in ks[0]
+    assert "HMMA" not in sass and "HGMMA" not in sass      # no legacy tensor path anywhere
+
+
 @pytest.mark.skipif(_ffi.lib().nm_device_count() > 0, reason="CPU-only behaviour")
 def test_no_gpu_fails_loudly():
     lib = _ffi.lib()
