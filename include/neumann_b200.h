@@ -91,6 +91,10 @@ int nm_index_swap_remove(nm_index *idx, uint64_t row, uint64_t *moved_from);
 int nm_index_clear(nm_index *idx);
 /* Copy row `row` back to host (diagnostics / tests). */
 int nm_index_get_row(nm_index *idx, uint64_t row, float *out_vec);
+/* Copy rows [first, first + n) back to host as a dense [n, dim] array (pinned or pageable).
+ * Diagnostics: bench.py and the parity tests hand exactly the bytes the GPU scanned to the CPU
+ * oracle this way. */
+int nm_index_get_rows(nm_index *idx, uint64_t first, uint64_t n, float *out_rows);
 
 uint64_t nm_index_rows(const nm_index *idx);
 uint32_t nm_index_dim(const nm_index *idx);

@@ -57,6 +57,7 @@ SIGNATURES = {
     "nm_index_swap_remove": (C.c_int, [_vp, C.c_uint64, _u64p]),
     "nm_index_clear": (C.c_int, [_vp]),
     "nm_index_get_row": (C.c_int, [_vp, C.c_uint64, _vp]),
+    "nm_index_get_rows": (C.c_int, [_vp, C.c_uint64, C.c_uint64, _vp]),
     "nm_index_rows": (C.c_uint64, [_vp]),
     "nm_index_dim": (C.c_uint32, [_vp]),
     "nm_index_device_count": (C.c_int, [_vp]),

@@ -473,6 +473,25 @@ int nm_index_get_row(nm_index *idx, uint64_t row, float *out_vec) {
     return NM_OK;
 }
 
+int nm_index_get_rows(nm_index *idx, uint64_t first, uint64_t n, float *out_rows) {
+    if (!idx || (n && !out_rows)) return fail(NM_ERR_INVALID_ARGUMENT, "null argument");
+    std::shared_lock<std::shared_mutex> g(idx->mu);
+    if (first + n < first || first + n > idx->total_rows())
+        return fail(NM_ERR_INVALID_ARGUMENT, "rows [%llu, %llu) out of range",
+                    (unsigned long long)first, (unsigned long long)(first + n));
+    const size_t row_bytes = (size_t)idx->dim * 4, pitch_bytes = (size_t)idx->pitch * 4;
+    for (auto &sh : idx->shards) {
+        const uint64_t lo = std::max(first, sh->row_base);
+        const uint64_t hi = std::min(first + n, sh->row_base + sh->rows);
+        if (lo >= hi) continue;
+        CUDA_TRY(cudaSetDevice(sh->device));
+        CUDA_TRY(cudaMemcpy2D(out_rows + (lo - first) * idx->dim, row_bytes,
+                              sh->d_rows + (lo - sh->row_base) * idx->pitch, pitch_bytes, row_bytes,
+                              hi - lo, cudaMemcpyDeviceToHost));
+    }
+    return NM_OK;
+}
+
 uint64_t nm_index_rows(const nm_index *idx) {
     if (!idx) return 0;
     std::shared_lock<std::shared_mutex> g(idx->mu);

@@ -82,6 +82,14 @@ class DeviceIndex:
         check(_ffi.lib().nm_index_get_row(self._h, row, out.ctypes.data))
         return out
 
+    def get_rows(self, first: int, n: int, out: np.ndarray | None = None) -> np.ndarray:
+        """Rows [first, first+n) as a dense float32 [n, dim] host array (into `out` if given)."""
+        if out is None:
+            out = np.empty((n, self.dim), np.float32)
+        assert out.dtype == np.float32 and out.flags.c_contiguous and out.size >= n * self.dim
+        check(_ffi.lib().nm_index_get_rows(self._h, first, n, out.ctypes.data))
+        return out.reshape(-1)[:n * self.dim].reshape(n, self.dim)
+
     def fill_synthetic(self, n: int, seed: int, row_offset: int = 0) -> None:
         check(_ffi.lib().nm_index_fill_synthetic(self._h, n, seed, row_offset))
 

@@ -515,3 +515,74 @@ def test_config4_batch_256_queries_full_size():
     assert np.array_equal(single[0], res[200][0])
     assert np.array_equal(single[1].view(np.uint32), res[200][1].view(np.uint32))
     idx.close()
+
+
+# ---- full-corpus oracle at the BASELINE sizes (chunked: 1M-row chunks -> per-chunk top-k ->
+#      nmo_merge_top_k, the reference's merge_top_k, distributed.rs:413-433) ------------------
+def _chunked_oracle(n, d, queries, k, metric, seed=0x5EED0001, chunk=1_000_000, threads=16,
+                    index=None):
+    """Per query the exact top-k of the WHOLE synthetic corpus, every row scored by the oracle.
+    Chunks come from the host generator; when `index` is given each chunk is also compared bit for
+    bit with the rows read back from the device mirror (nm_index_get_rows)."""
+    lists = [([], []) for _ in queries]
+    for c0 in range(0, n, chunk):
+        m = min(chunk, n - c0)
+        rows = o.fill_synthetic(m, d, seed, row_offset=c0, threads=threads)
+        if index is not None:
+            assert np.array_equal(index.get_rows(c0, m).view(np.uint32), rows.view(np.uint32))
+        for qi, q in enumerate(queries):
+            r, s = o.search(rows, q, k, metric, threads=threads)
+            lists[qi][0].append(r + np.uint64(c0))
+            lists[qi][1].append(s)
+    return [o.merge_top_k(lr, ls, k) for lr, ls in lists]
+
+
+def test_get_rows_matches_generator_and_get_row():
+    idx, rows = synth_index(70_001, 131)
+    got = idx.get_rows(0, 70_001)
+    assert np.array_equal(got.view(np.uint32), rows.view(np.uint32))
+    part = idx.get_rows(65_000, 1_234)
+    assert np.array_equal(part, rows[65_000:66_234])
+    assert np.array_equal(idx.get_row(66_000), part[1_000])
+    with pytest.raises(NmError):
+        idx.get_rows(70_000, 2)
+    idx.close()
+
+
+def test_config3_full_oracle():
+    """BASELINE config 3 (headline): 10M x 768 cosine TOP 10, 4 queries, EVERY row scored by the
+    oracle — identical ids in identical order and bit-identical scores (VE:2013-2034)."""
+    n, d, k = 10_000_000, 768, 10
+    idx = DeviceIndex(d)
+    idx.fill_synthetic(n, 0x5EED0001)
+    qs = o.fill_synthetic(4, d, 0x5EED1001)
+    exp = _chunked_oracle(n, d, qs, k, "cosine", index=idx)
+    idx.set_batching(False)
+    for qi in range(4):
+        (got,) = idx.search(qs[qi], k, "cosine")
+        assert_same(got, exp[qi], f"config 3 query {qi}")
+    idx.set_batching(True)
+    for qi, got in enumerate(idx.search(qs, k, "cosine")):      # the same 4 as one batch
+        assert_same(got, exp[qi], f"config 3 batched query {qi}")
+    idx.close()
+
+
+def test_config4_full_oracle():
+    """BASELINE config 4: 10M x 1536 Euclidean TOP 100, a batch of 256 queries; queries 0, 100 and
+    255 of the batch are checked against the oracle over EVERY row, through the default batch path
+    and through the exact batched kernels."""
+    n, d, k, nq = 10_000_000, 1536, 100, 256
+    idx = DeviceIndex(d)
+    idx.fill_synthetic(n, 0x5EED0001)
+    qs = o.fill_synthetic(nq, d, 0x5EED2001)
+    pick = [0, 100, 255]
+    exp = _chunked_oracle(n, d, qs[pick], k, "euclidean")
+    res = idx.search(qs, k, "euclidean")                       # default path
+    for j, qi in enumerate(pick):
+        assert_same(res[qi], exp[j], f"config 4 default path, query {qi}")
+    idx.set_tensor_core(False)                                  # exact batched kernels
+    res64 = idx.search(qs[64:128], k, "euclidean")
+    assert_same(res64[100 - 64], exp[1], "config 4 exact batched kernels, query 100")
+    for qi in range(64, 128):                                   # and the two paths agree on all 64
+        assert_same(res64[qi - 64], res[qi], f"default vs exact batched, query {qi}")
+    idx.close()
