@@ -179,16 +179,24 @@ int nm_index_stats(nm_index *idx, nm_stats *out);
  * and accumulates profiled_scan_ms / profiled_scans.  Used by bench.py for the roofline. */
 int nm_index_set_profiling(nm_index *idx, int enable);
 /* SURVEY 8f row 4 — quantised pre-filter with EXACT re-score (precedent:
- * ScalarQuantizedVector, tensor_store/src/hnsw.rs:308-356).  mode 1 keeps an int8 copy of the
- * mirror (+1 byte per element, +16 bytes per row); nm_search on a single-device index then
- * scans the int8 copy with dp4a (4x fewer HBM bytes), brackets every row's reference score in
- * a rigorous interval, and re-scores only the rows whose interval reaches the k-th best lower
- * bound with the exact f32 arithmetic.  Results are bit-identical to mode 0 (tested); cosine
- * and dot product, k <= 1024, single-query calls; anything else, a non-finite
- * query or an overflowing candidate list falls back to the f32 scan.  It changes the bytes
- * read per row, so it is OFF by default and benchmarked separately from the f32 roofline. */
+ * ScalarQuantizedVector, tensor_store/src/hnsw.rs:308-356).  An int8 copy of the mirror (+1 byte
+ * per element, +24 bytes per row) lets a pass read 4x fewer HBM bytes; every row's reference
+ * score is bracketed in a rigorous interval and only rows whose interval reaches the k-th best
+ * lower bound are re-scored with the exact f32 arithmetic, so results are bit-identical to the
+ * f32 scan (tested).  Modes:
+ *   2 (default, "auto")  BATCHES (nq >= 2, and coalesced rounds of concurrent single queries)
+ *      use the tensor-core pre-filter below.  The copy is built by the first eligible batch —
+ *      provided it leaves max(4 GiB, 1/16 of the device) of HBM free; otherwise batches stay on
+ *      the exact kernels — and is kept up to date by every mutation from then on.  Single
+ *      queries stay on the f32 scan (the headline path).
+ *   1  the copy is built now and single queries use it too: dp4a scan + exact re-score
+ *      (cosine and dot product, k <= 1024; anything else, a non-finite query or an
+ *      overflowing candidate list falls back to the f32 scan).  Changes the bytes read per
+ *      row, so it is benchmarked separately from the f32 roofline.
+ *   0  no copy (frees it); every search runs on the exact f32 kernels. */
 int nm_index_set_prefilter(nm_index *idx, int mode);
-/* Batches (nq >= 2) on an index with the pre-filter ON go through the tensor-core pre-filter
+/* Batches (nq >= 2) on an index whose int8 copy exists (modes 1 and 2 above) go through the
+ * tensor-core pre-filter
  * (tc_prefilter_kernels.cuh): ONE pass over the int8 copy serves up to 256 queries as an exact
  * s8 x s8 -> s32 GEMM on the tcgen05 tensor cores (accumulators in TMEM); every integer dot
  * product is turned into a rigorous score interval (cosine, dot product AND the reference's

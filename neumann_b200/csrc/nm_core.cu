@@ -138,8 +138,10 @@ int encode_tmap_u8(CUtensorMap *out, void *base, uint64_t inner, uint64_t rows, 
 
 // Bring the int8 copy of rows [first, first+n) up to date (call with the index write lock held,
 // after the f32 mirror holds the new data).  No-op while the pre-filter is off.
-int q8_refresh(nm_index *idx, Shard &sh, uint64_t first, uint64_t n) {
-    if (!idx->prefilter.load()) return NM_OK;
+int q8_refresh(nm_index *idx, Shard &sh, uint64_t first, uint64_t n, bool build) {
+    const int mode = idx->prefilter.load();
+    if (mode == 0) return NM_OK;
+    if (mode == 2 && !build && !sh.d_q8) return NM_OK;  // auto: nothing to keep up to date yet
     const uint32_t pitch8 = q8_pitch(idx->dim);
     if (sh.rows > sh.q8_capacity) {
         uint64_t cap = std::max<uint64_t>(sh.rows, sh.capacity);
@@ -184,6 +186,46 @@ int q8_refresh(nm_index *idx, Shard &sh, uint64_t first, uint64_t n) {
     }
     sh.q8_rows = sh.rows;
     return build_tmap8(idx, sh);
+}
+
+// Auto mode (nm_index_set_prefilter(idx, 2), the default): the first batch that the
+// tensor-core pre-filter can serve builds the int8 copy, provided it leaves a comfortable
+// margin of free HBM (results are bit-identical either way, so this is purely a memory
+// decision).  Called WITHOUT the index lock; takes the write lock for the build.
+int q8_auto_prepare(nm_index *idx, uint32_t nq, uint32_t k) {
+    if (idx->prefilter.load() != 2 || !idx->tensor_core.load() || !idx->batching.load()) return NM_OK;
+    {
+        std::shared_lock<std::shared_mutex> g(idx->mu);
+        bool wanted = false;
+        for (auto &sh : idx->shards)
+            if (tc_shape_ok(idx, sh->rows, nq, k) && !(sh->tmap8_valid && sh->q8_rows == sh->rows))
+                wanted = true;
+        if (!wanted || idx->q8_auto_declined_rows.load() == idx->total_rows()) return NM_OK;
+    }
+    std::unique_lock<std::shared_mutex> g(idx->mu);
+    if (idx->prefilter.load() != 2) return NM_OK;
+    const uint32_t pitch8 = q8_pitch(idx->dim);
+    for (auto &shp : idx->shards) {
+        Shard &sh = *shp;
+        if (!tc_shape_ok(idx, sh.rows, nq, k) || (sh.tmap8_valid && sh.q8_rows == sh.rows)) continue;
+        CUDA_TRY(cudaSetDevice(sh.device));
+        // async searches on caller streams never read the copy, but they may be reading memory
+        // the allocator is about to hand out: nothing to wait for here (fresh allocations only)
+        size_t free_b = 0, total_b = 0;
+        CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
+        const uint64_t cap = std::max<uint64_t>(sh.rows, sh.capacity);
+        const uint64_t need = sh.q8_capacity >= sh.rows
+                                  ? 0
+                                  : cap * (pitch8 + sizeof(nm::RowMeta) + sizeof(float2));
+        const uint64_t margin = std::max<uint64_t>(4ull << 30, total_b / 16);
+        if (need + margin > free_b) {
+            idx->q8_auto_declined_rows = idx->total_rows();
+            return NM_OK;  // not an error: batches stay on the exact kernels
+        }
+        int rc = q8_refresh(idx, sh, 0, sh.rows, true);
+        if (rc) return rc;
+    }
+    return NM_OK;
 }
 
 }  // namespace nmi
@@ -530,9 +572,10 @@ int nm_index_fill_synthetic(nm_index *idx, uint64_t n, uint64_t seed, uint64_t r
 
 int nm_index_set_prefilter(nm_index *idx, int mode) {
     if (!idx) return fail(NM_ERR_INVALID_ARGUMENT, "null index");
-    if (mode != 0 && mode != 1) return fail(NM_ERR_INVALID_ARGUMENT, "unknown pre-filter mode %d", mode);
+    if (mode < 0 || mode > 2) return fail(NM_ERR_INVALID_ARGUMENT, "unknown pre-filter mode %d", mode);
     std::unique_lock<std::shared_mutex> g(idx->mu);
     idx->prefilter = mode;
+    idx->q8_auto_declined_rows = ~0ull;
     for (auto &shp : idx->shards) {
         Shard &sh = *shp;
         CUDA_TRY(cudaSetDevice(sh.device));
@@ -545,11 +588,11 @@ int nm_index_set_prefilter(nm_index *idx, int mode) {
             sh.d_norms = nullptr;
             sh.q8_capacity = sh.q8_rows = 0;
             sh.tmap8_valid = false;
-        } else {
+        } else if (mode == 1) {
             sh.q8_rows = 0;
             int rc = q8_refresh(idx, sh, 0, sh.rows);
             if (rc) return rc;
-        }
+        }  // mode 2 keeps an existing copy and otherwise builds it at the first eligible batch
     }
     return NM_OK;
 }

@@ -212,7 +212,11 @@ struct nm_index {
         merge_launches{0}, h2d_bytes{0}, d2h_bytes{0};
     std::atomic<double> last_scan_ms{0.0};
     std::atomic<int> profiling{0};
-    std::atomic<int> prefilter{0};  // nm_index_set_prefilter: 1 = exact int8 pre-filter
+    // nm_index_set_prefilter: 0 = never, 1 = int8 copy always (single queries through the dp4a
+    // pre-filter, batches through the tensor-core pre-filter), 2 = auto (default): the copy is
+    // built at the first eligible batch when it fits in free HBM and serves batches only
+    std::atomic<int> prefilter{2};
+    std::atomic<uint64_t> q8_auto_declined_rows{~0ull};  // auto build refused at this row count
     std::atomic<int> tensor_core{1};  // nm_index_set_tensor_core: batches of a pre-filtered index
                                       // go through the tcgen05 int8 GEMM pre-filter
     std::atomic<uint64_t> tc_queries{0}, tc_fallbacks{0}, tc_survivors{0};
@@ -270,7 +274,10 @@ inline uint32_t pow2_ceil(uint32_t v) {
 
 // ---- nm_core.cu ----
 int build_tmap(nm_index *idx, Shard &sh);
-int q8_refresh(nm_index *idx, Shard &sh, uint64_t first, uint64_t n);
+int q8_refresh(nm_index *idx, Shard &sh, uint64_t first, uint64_t n, bool build = false);
+// auto mode: build the int8 copy now if a batch of nq queries would use it and it fits
+int q8_auto_prepare(nm_index *idx, uint32_t nq, uint32_t k);
+bool tc_shape_ok(const nm_index *idx, uint64_t shard_rows, uint32_t nq, uint32_t k);
 int encode_tmap_u8(CUtensorMap *out, void *base, uint64_t inner, uint64_t rows, uint64_t pitch_bytes,
                    uint32_t box_inner, uint32_t box_rows);
 uint32_t q8_pitch(uint32_t dim);

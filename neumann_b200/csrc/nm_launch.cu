@@ -356,7 +356,7 @@ size_t prefilter_smem_bytes(uint32_t n_stages, uint32_t q_words) {
 
 bool prefilter_usable(const nm_index *idx, const Shard &sh, uint32_t nq, uint32_t k, int metric,
                       const uint64_t *row_mask) {
-    if (!idx->prefilter.load() || row_mask || metric == NM_EUCLIDEAN) return false;
+    if (idx->prefilter.load() != 1 || row_mask || metric == NM_EUCLIDEAN) return false;
     if (!sh.tmap8_valid || sh.q8_rows != sh.rows || sh.rows == 0) return false;
     if (k > (uint32_t)nm::kMaxFastK || k > sh.rows) return false;
     if (idx->batching.load() && nq >= kBatchMinQueries && (idx->dim % 8u) == 0) return false;
@@ -442,18 +442,21 @@ int launch_prefiltered(nm_index *idx, const Shard &sh, Workspace &ws, const floa
 constexpr uint32_t kTcSortBuckets = 8192;  // row buckets of the re-score ordering
 constexpr uint32_t kTcMinRows = 65536;  // below this the exact kernels are cheaper
 
+// shape part of tc_usable: would a batch of nq queries over a shard of this size take the path?
+bool tc_shape_ok(const nm_index *idx, uint64_t shard_rows, uint32_t nq, uint32_t k) {
+    if (nq < 2 || shard_rows < kTcMinRows || k > (uint32_t)nm::kMaxFastK) return false;
+    if ((uint64_t)idx->dim * 16129ull >= 0x7fffffffull) return false;   // s32 accumulators
+    if ((size_t)idx->dim * 4 > 160 * 1024) return false;                // rescore keeps q in smem
+    return true;
+}
+
 bool tc_usable(const nm_index *idx, const Shard &sh, uint32_t nq, uint32_t k, int metric,
                const uint64_t *row_mask) {
     (void)metric;
     if (!idx->prefilter.load() || !idx->tensor_core.load() || !idx->batching.load() || row_mask)
         return false;
-    if (nq < 2 || !sh.tmap8_valid || sh.q8_rows != sh.rows) return false;
-    if (sh.rows < kTcMinRows || k > (uint32_t)nm::kMaxFastK) return false;
-    if ((uint64_t)idx->dim * 16129ull >= 0x7fffffffull) return false;   // s32 accumulators
-    // dim % 4 != 0: the re-score keeps the (then unaligned) query in shared memory
-    if ((idx->dim % 4u) != 0u && (size_t)idx->dim * 4 > 160 * 1024) return false;
-    if ((size_t)idx->dim * 4 > 160 * 1024) return false;                // rescore keeps q in smem
-    return true;
+    if (!sh.tmap8_valid || sh.q8_rows != sh.rows) return false;
+    return tc_shape_ok(idx, sh.rows, nq, k);
 }
 
 // auxiliary words of the tensor-core path: [cap kept_n][cap kept_prev][4 stats][passes x TcCtl]

@@ -125,6 +125,10 @@ static int search_impl(nm_index *idx, const float *queries, uint32_t nq, uint32_
                        uint32_t *out_counts) {
     int rc = validate_search(idx, queries, nq, k, metric, out_rows, out_scores, out_counts);
     if (rc) return rc;
+    if (nq >= 2 && !row_mask) {
+        rc = q8_auto_prepare(idx, nq, k);  // auto mode: first eligible batch builds the int8 copy
+        if (rc) return rc;
+    }
     std::shared_lock<std::shared_mutex> g(idx->mu);
     const size_t G = idx->shards.size();
     const uint32_t dim = idx->dim;

@@ -85,9 +85,11 @@ struct VectorEngineConfig {
     size_t batch_parallel_threshold = 100;
     std::optional<std::chrono::milliseconds> search_timeout;
     std::vector<int> devices;  // empty = current device
-    // Device-side addition: keep an int8 copy of every mirror (nm_index_set_prefilter) so that
-    // single queries use the dp4a pre-filter and batches / coalesced concurrent callers the
-    // tensor-core pre-filter.  Results are bit-identical either way; costs +1 byte per element.
+    // Device-side addition.  false (default): nm_index_set_prefilter mode 2 — batches and
+    // coalesced concurrent callers use the tensor-core pre-filter (the int8 copy is built by the
+    // first eligible batch when it fits), single queries the f32 scan.  true: mode 1 — the copy is
+    // built eagerly and single queries use the dp4a pre-filter too.  Results are bit-identical
+    // either way; the copy costs +1 byte per element.
     bool device_prefilter = false;
     Result<Unit> validate() const;  // lib.rs:771-826
 };

@@ -141,7 +141,8 @@ class DeviceIndex:
         check(_ffi.lib().nm_index_detach_comm(self._h))
 
     def set_prefilter(self, mode: int) -> None:
-        """0 = off (default), 1 = exact int8 pre-filter (see include/neumann_b200.h)."""
+        """0 = off, 1 = int8 copy for single queries and batches, 2 = auto (default): batches only,
+        copy built by the first eligible batch (see include/neumann_b200.h)."""
         check(_ffi.lib().nm_index_set_prefilter(self._h, int(mode)))
 
     def set_tensor_core(self, enable: bool) -> None:

@@ -112,8 +112,9 @@ def test_engine_results_match_oracle_order_and_bits():
 
 
 def test_search_similar_batch_matches_single_calls_and_oracle():
-    """search_similar_batch[i] == search_similar_with_metric(queries[i]): through the exact batched
-    kernels by default, through the dp4a / tensor-core pre-filters with device_prefilter=True."""
+    """search_similar_batch[i] == search_similar_with_metric(queries[i]): by default batches go
+    through the tensor-core pre-filter (auto mode) and single calls through the f32 scan; with
+    device_prefilter=True single calls use the dp4a pre-filter too."""
     n, d, k = 70_000, 40, 9
     rows = o.fill_synthetic(n, d, 12)
     qs = o.fill_synthetic(7, d, 13)

@@ -235,7 +235,8 @@ def test_batched_queries_share_one_pass(metric, n, dim, nq, k):
     rows = base.copy()
     rows[n // 2:n // 2 + n // 10] = base[:n // 10]      # exact ties
     idx = DeviceIndex(dim)
-    idx.load(rows)
+    idx.set_prefilter(0)    # this test is about the exact batched kernels (70000 rows would
+    idx.load(rows)          # otherwise take the tensor-core pre-filter, tests/test_gpu_tc.py)
     qs = o.fill_synthetic(nq, dim, 0xBEEF)
     qs[1] = rows[7]                                      # a query equal to a stored row
     if metric != "euclidean" and nq > 2:
@@ -405,21 +406,25 @@ def test_stats_counters():
     idx.close()
 
 
+@pytest.mark.parametrize("mode", [2, 0])
 @pytest.mark.parametrize("metric", METRICS)
-def test_parity_gate_1000_queries_with_tie_stress(metric):
+def test_parity_gate_1000_queries_with_tie_stress(metric, mode):
     """SURVEY 8d parity gate: >= 1000 queries per metric on a corpus with 1 % duplicated rows
-    (exact ties); ids position by position, scores bit for bit.  1000 queries ride the batched
-    kernels, the first 40 are repeated through single-query scans."""
+    (exact ties); ids position by position, scores bit for bit.  The 1000 queries go through the
+    default batch path (mode 2: tensor-core pre-filter, copy built by the first batch) and through
+    the exact batched kernels (mode 0); the first 40 are repeated through single-query scans."""
     n, d, k = 120_000, 128, 10
     rows = o.fill_synthetic(n, d, 0x5EED0001)
     rng = np.random.default_rng(11)
     dup = rng.choice(n, n // 100, replace=False)
     rows[dup] = rows[(dup * 7 + 13) % n]
     idx = DeviceIndex(d)
+    idx.set_prefilter(mode)
     idx.load(rows)
     qs = o.fill_synthetic(1000, d, 0x5EED1001)
     qs[::50] = rows[dup[:20]]            # 20 queries that hit a tie group exactly
     res = idx.search(qs, k, metric)
+    assert (idx.stats().tc_queries == 1000) == (mode == 2)
     for i in range(1000):
         assert_same(res[i], o.search(rows, qs[i], k, metric, threads=16), f"{metric} q{i}")
     idx.set_batching(False)
@@ -492,6 +497,7 @@ def test_config4_batch_256_queries_full_size():
     import np_ref
     n, d, k, nq = 10_000_000, 1536, 100, 256
     idx = DeviceIndex(d)
+    idx.set_prefilter(0)                                # the exact batched kernels
     idx.fill_synthetic(n, 0x5EED0001)
     qs = o.fill_synthetic(nq, d, 0x5EED1001)
     res = idx.search(qs, k, "euclidean")
@@ -562,8 +568,12 @@ def test_config3_full_oracle():
         (got,) = idx.search(qs[qi], k, "cosine")
         assert_same(got, exp[qi], f"config 3 query {qi}")
     idx.set_batching(True)
-    for qi, got in enumerate(idx.search(qs, k, "cosine")):      # the same 4 as one batch
-        assert_same(got, exp[qi], f"config 3 batched query {qi}")
+    for qi, got in enumerate(idx.search(qs, k, "cosine")):      # the same 4 as one batch (default:
+        assert_same(got, exp[qi], f"config 3 batched query {qi}")  # tensor-core pre-filter)
+    assert idx.stats().tc_queries == 4
+    idx.set_prefilter(0)
+    for qi, got in enumerate(idx.search(qs, k, "cosine")):      # and through the exact batched kernels
+        assert_same(got, exp[qi], f"config 3 exact batched query {qi}")
     idx.close()
 
 
@@ -577,7 +587,8 @@ def test_config4_full_oracle():
     qs = o.fill_synthetic(nq, d, 0x5EED2001)
     pick = [0, 100, 255]
     exp = _chunked_oracle(n, d, qs[pick], k, "euclidean")
-    res = idx.search(qs, k, "euclidean")                       # default path
+    res = idx.search(qs, k, "euclidean")                       # default path: tensor-core pre-filter
+    assert idx.stats().tc_queries == nq
     for j, qi in enumerate(pick):
         assert_same(res[qi], exp[j], f"config 4 default path, query {qi}")
     idx.set_tensor_core(False)                                  # exact batched kernels
