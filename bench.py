@@ -362,7 +362,7 @@ class Env:
     pass
 
 
-def time_single_query(E, idx, q_host, k, metric, steps, warmup, profile=True):
+def time_single_query(E, idx, q_host, k, metric, steps, warmup, profile=True, pipelined=True):
     """Device-resident steps on E.stream (CUDA events, max over ranks) + the same steps through
     nm_search with host buffers.  Returns a dict with both, the scan-kernel time from the
     library-side events, launches, and the GPU results of every distinct query on both paths."""
@@ -382,33 +382,46 @@ def time_single_query(E, idx, q_host, k, metric, steps, warmup, profile=True):
         idx.search_device(q_dev[j].data_ptr(), 1, k, metric, d_rows[j].data_ptr(),
                           d_scores[j].data_ptr(), d_counts[j].data_ptr(), stream.cuda_stream)
 
+    def timed_loop():
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        E.barrier()
+        ev[0].record(stream)
+        for i in range(steps):
+            step_device(i)
+        ev[1].record(stream)
+        E.barrier()
+        return nd.max_over_ranks(ev[0].elapsed_time(ev[1]), dev)
+
+    # ---- value: K asynchronous calls back to back on one stream; consecutive queries overlap
+    #      (nm_index_set_pipelining: programmatic dependent launch) ----
+    idx.set_pipelining(pipelined)
     for i in range(warmup):
         step_device(i)
     E.barrier()
     s0 = idx.stats()
-    if profile:
-        idx.set_profiling(True)
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
-    E.barrier()
-    ev[0].record(stream)
-    for i in range(steps):
-        step_device(i)
-    ev[1].record(stream)
-    E.barrier()
-    total_ms = ev[0].elapsed_time(ev[1])
-    if profile:
-        idx.set_profiling(False)
+    total_ms = timed_loop()
     s1 = idx.stats()
-    total_ms = nd.max_over_ranks(total_ms, dev)
-    out = {"ms_per_step": total_ms / steps, "value": 1e3 * steps / total_ms,
+    out = {"ms_per_step": total_ms / steps, "value": 1e3 * steps / total_ms, "pipelined": bool(pipelined),
            "launches": int((s1.scan_launches - s0.scan_launches) + (s1.merge_launches - s0.merge_launches))}
+    idx.set_pipelining(False)
     if profile:
+        # ---- roofline: the same K steps strictly serial, every scan launch bracketed by
+        #      library-side CUDA events on the launching stream ----
+        for i in range(min(warmup, 3)):
+            step_device(i)
+        E.barrier()
+        s0 = idx.stats()
+        idx.set_profiling(True)
+        serial_ms = timed_loop()
+        idx.set_profiling(False)
+        s1 = idx.stats()
         n_prof = int(s1.profiled_scans - s0.profiled_scans)
         if n_prof != steps:
             raise RuntimeError(f"profiled {n_prof} scan launches, expected {steps}")
         out["scan_ms"] = nd.max_over_ranks((s1.profiled_scan_ms - s0.profiled_scan_ms) / n_prof, dev)
+        out["serial_ms_per_step"] = serial_ms / steps
 
-    # single-step device times (extra, not the metric)
+    # single-step device times (extra, not the metric): events between the steps keep them serial
     n_pct = min(steps, 100)
     pe = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
           for _ in range(n_pct)]
@@ -494,6 +507,7 @@ def bench_cfg_small(E, a, rows, dim, k, metric, steps, warmup, label, flush_l2):
     out = {"workload": workload_name(rows, dim, metric, k), "rows": rows, "dim": dim, "k": k,
            "metric": metric, "steps": steps, "warmup": warmup,
            "device_us_per_query": m["ms_per_step"] * 1e3, "value": m["value"], "unit": "queries/s",
+           "device_us_per_query_serial": m["serial_ms_per_step"] * 1e3,
            "e2e_us_per_query": m["e2e_ms_per_step"] * 1e3, "e2e_value": m["e2e_value"],
            "step_ms_percentiles": m["pct"], "gpu_launches": m["launches"],
            "roofline": roofline_obj(algo, m["scan_ms"], E.hbm_peak, E.peak_src, "nm::scan_topk_kernel")}
@@ -725,6 +739,7 @@ def run_ours(a):
             weak = {"workload": workload_name(w_total, a.dim, a.metric, k), "scaling": "weak",
                     "rows": w_total, "rows_per_gpu": whi - wlo, "n_gpus": world,
                     "value": wm["value"], "unit": "queries/s", "ms_per_step": wm["ms_per_step"],
+                    "serial_ms_per_step": wm["serial_ms_per_step"],
                     "e2e_value": wm["e2e_value"], "steps": a.steps, "warmup": a.warmup,
                     "step_ms_percentiles": wm["pct"],
                     "roofline": roofline_obj(w_algo, wm["scan_ms"], E.hbm_peak, E.peak_src,
@@ -782,6 +797,10 @@ def run_ours(a):
                            if os.environ.get("NM_DISABLE_PEER_EXCHANGE") == "1" else ""),
             "l2": f"input {algo_bytes / 1e9:.2f} GB per GPU per step >> 126 MB L2: no flush needed",
             "generator": "u24(splitmix64(splitmix64(seed)^(r*dim+c)))*2^-23-1, on device",
+            "pipelining": "value: K asynchronous nm_search_device calls back to back on one stream with "
+                          "nm_index_set_pipelining(1) — query i+1 starts streaming on SMs query i has left "
+                          "while its last CTA merges/exchanges (programmatic dependent launch); "
+                          "serial_ms_per_step / roofline.kernel_ms / step_ms_percentiles: strictly serial",
         },
         "roofline": roofline_obj(algo_bytes, m["scan_ms"], E.hbm_peak, E.peak_src,
                                  "nm::scan_topk_kernel"),
@@ -789,6 +808,7 @@ def run_ours(a):
                 "d2h_bytes_per_step": 16 + k * 12,
                 "note": "nm_search() with host query and host result buffers; corpus resident in HBM"},
         "gpu_launches": m["launches"],
+        "serial_ms_per_step": m.get("serial_ms_per_step"),
         "step_ms_percentiles": m["pct"],
         "clocks": sampler.summary(),
     }

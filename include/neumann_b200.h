@@ -130,10 +130,27 @@ int nm_search_masked(nm_index *idx, const float *queries, uint32_t nq, uint32_t 
  * device and the work enqueued on `stream` (a cudaStream_t).  With a caller stream the call
  * is fully ASYNCHRONOUS: it returns after enqueueing and the outputs are valid once the
  * stream reaches that point.  NULL = library stream, and the call then synchronises before
- * returning.  Single-device indexes only. */
+ * returning.  Single-device indexes only.  Mutations (load / append / update / swap_remove /
+ * clear) wait for every asynchronous search issued before them, whatever the stream.  The
+ * library keeps a scratch workspace per caller stream: call nm_index_release_stream before
+ * destroying a stream that was used here.  Collective indexes: asynchronous searches are ordered
+ * by ONE stream at a time; switching streams synchronises the previous one. */
 int nm_search_device(nm_index *idx, const float *d_queries, uint32_t nq, uint32_t k,
                      int metric, uint64_t *d_out_rows, float *d_out_scores,
                      uint32_t *d_out_counts, void *stream);
+
+/* Forget (and free the scratch of) a caller stream used with nm_search_device; synchronises it. */
+int nm_index_release_stream(nm_index *idx, void *stream);
+/* enable = 1: consecutive asynchronous single-query nm_search_device calls on one caller stream
+ * OVERLAP (programmatic dependent launch): the next query's CTAs start streaming on the SMs the
+ * current query has already left, while its last CTA still merges the per-SM candidates and
+ * exchanges hits with the other shards; outputs and completion stay in call order.  The price
+ * is a rule for the caller, which is why it is opt-in: the query of call i+1 is read while call
+ * i is still running, so it must not be produced by a KERNEL enqueued on that stream after call
+ * i-1 (copies — cudaMemcpyAsync — and anything enqueued earlier are fine).  Ignored (calls run
+ * back to back) while profiling is on, for k > 1024, and for batches that share a corpus pass.
+ * Default 0. */
+int nm_index_set_pipelining(nm_index *idx, int enable);
 
 /* ---- row-range sharding across processes (one process per GPU; replaces
  *      QueryRouter::execute_scatter_gather + ResultMerger::merge_top_k,

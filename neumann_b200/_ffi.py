@@ -71,6 +71,8 @@ SIGNATURES = {
     "nm_index_stats": (C.c_int, [_vp, C.POINTER(NmStats)]),
     "nm_index_set_profiling": (C.c_int, [_vp, C.c_int]),
     "nm_index_set_batching": (C.c_int, [_vp, C.c_int]),
+    "nm_index_set_pipelining": (C.c_int, [_vp, C.c_int]),
+    "nm_index_release_stream": (C.c_int, [_vp, _vp]),
     "nm_index_set_prefilter": (C.c_int, [_vp, C.c_int]),
     "nm_index_set_coalescing": (C.c_int, [_vp, C.c_int]),
     "nm_index_set_tensor_core": (C.c_int, [_vp, C.c_int]),

@@ -384,6 +384,7 @@ void nm_index_destroy(nm_index *idx) {
 int nm_index_clear(nm_index *idx) {
     if (!idx) return fail(NM_ERR_INVALID_ARGUMENT, "null index");
     std::unique_lock<std::shared_mutex> g(idx->mu);
+    if (int wrc = wait_async_searches(idx)) return wrc;  // never tear an in-flight async scan
     for (auto &sh : idx->shards) {
         sh->rows = 0;
         sh->row_base = 0;
@@ -398,6 +399,7 @@ int nm_index_load(nm_index *idx, const float *rows, uint64_t n) {
     if (!idx) return fail(NM_ERR_INVALID_ARGUMENT, "null index");
     if (n && !rows) return fail(NM_ERR_INVALID_ARGUMENT, "null rows");
     std::unique_lock<std::shared_mutex> g(idx->mu);
+    if (int wrc = wait_async_searches(idx)) return wrc;  // never tear an in-flight async scan
     const uint64_t G = idx->shards.size();
     for (uint64_t s = 0; s < G; ++s) {
         Shard &sh = *idx->shards[s];
@@ -424,6 +426,7 @@ int nm_index_append(nm_index *idx, const float *rows, uint64_t n) {
     if (n == 0) return NM_OK;
     if (!rows) return fail(NM_ERR_INVALID_ARGUMENT, "null rows");
     std::unique_lock<std::shared_mutex> g(idx->mu);
+    if (int wrc = wait_async_searches(idx)) return wrc;  // never tear an in-flight async scan
     Shard &sh = *idx->shards.back();
     CUDA_TRY(cudaSetDevice(sh.device));
     int rc = shard_reserve(idx, sh, sh.rows + n, true);
@@ -450,6 +453,7 @@ static int locate_row(nm_index *idx, uint64_t row, Shard **out, uint64_t *local)
 int nm_index_update(nm_index *idx, uint64_t row, const float *vec) {
     if (!idx || !vec) return fail(NM_ERR_INVALID_ARGUMENT, "null argument");
     std::unique_lock<std::shared_mutex> g(idx->mu);
+    if (int wrc = wait_async_searches(idx)) return wrc;  // never tear an in-flight async scan
     Shard *sh = nullptr;
     uint64_t local = 0;
     int rc = locate_row(idx, row, &sh, &local);
@@ -463,6 +467,7 @@ int nm_index_update(nm_index *idx, uint64_t row, const float *vec) {
 int nm_index_swap_remove(nm_index *idx, uint64_t row, uint64_t *moved_from) {
     if (!idx) return fail(NM_ERR_INVALID_ARGUMENT, "null index");
     std::unique_lock<std::shared_mutex> g(idx->mu);
+    if (int wrc = wait_async_searches(idx)) return wrc;  // never tear an in-flight async scan
     Shard *sh = nullptr;
     uint64_t local = 0;
     int rc = locate_row(idx, row, &sh, &local);
@@ -545,6 +550,7 @@ int nm_index_device_count(const nm_index *idx) { return idx ? (int)idx->shards.s
 int nm_index_fill_synthetic(nm_index *idx, uint64_t n, uint64_t seed, uint64_t row_offset) {
     if (!idx) return fail(NM_ERR_INVALID_ARGUMENT, "null index");
     std::unique_lock<std::shared_mutex> g(idx->mu);
+    if (int wrc = wait_async_searches(idx)) return wrc;  // never tear an in-flight async scan
     const uint64_t G = idx->shards.size();
     for (uint64_t s = 0; s < G; ++s) {
         Shard &sh = *idx->shards[s];
@@ -574,6 +580,7 @@ int nm_index_set_prefilter(nm_index *idx, int mode) {
     if (!idx) return fail(NM_ERR_INVALID_ARGUMENT, "null index");
     if (mode < 0 || mode > 2) return fail(NM_ERR_INVALID_ARGUMENT, "unknown pre-filter mode %d", mode);
     std::unique_lock<std::shared_mutex> g(idx->mu);
+    if (int wrc = wait_async_searches(idx)) return wrc;  // never tear an in-flight async scan
     idx->prefilter = mode;
     idx->q8_auto_declined_rows = ~0ull;
     for (auto &shp : idx->shards) {

@@ -69,7 +69,13 @@ struct Workspace {
     size_t query_cap = 0;      // floats
     uint64_t *d_cand = nullptr;
     size_t cand_cap = 0;  // keys
+    // [0..1] ticket + row-block cursor, [2..3] the same for odd pipelined scans, [4] highest
+    // finished pipelined sequence number (kWsCounterWords words)
     uint32_t *d_counter = nullptr;
+    uint32_t pipe_seq = 0;          // pipelined scans issued on this (stream-bound) workspace
+    bool pipeline_next = false;     // set by nm_search_device: the next launch_scan may overlap
+    cudaEvent_t async_done = nullptr;  // recorded after every non-pipelined asynchronous call
+    bool async_pending = false;
     uint32_t *d_mask = nullptr;       // row bitmask of a pre-filtered search, padded to row blocks
     size_t mask_cap = 0;              // u32 words
     uint64_t *d_pass_keys = nullptr;  // [k] merged keys of the chained passes (k > 1024)
@@ -152,6 +158,7 @@ struct Workspace {
         if (d_gather) cudaFree(d_gather);
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
+        if (async_done) cudaEventDestroy(async_done);
         for (auto &pe : prof_events) {
             cudaEventDestroy(pe.first);
             cudaEventDestroy(pe.second);
@@ -222,6 +229,8 @@ struct nm_index {
     std::atomic<uint64_t> tc_queries{0}, tc_fallbacks{0}, tc_survivors{0};
     std::atomic<uint64_t> pf_queries{0}, pf_fallbacks{0}, pf_kept{0};
     std::atomic<int> batching{1};  // nm_index_set_batching: 0 forces one scan per query
+    std::atomic<int> pipelining{0};  // nm_index_set_pipelining: async single-query scans overlap
+    cudaStream_t xchg_async_stream = nullptr;  // last caller stream of an async collective search
     // Coalescing of concurrent single-query nm_search calls (nm_index_set_coalescing): while
     // one batch is on the GPU, calls from other host threads queue up and ride the next corpus
     // pass together (batched kernels).  No timers: an idle index serves a lone call at once.
@@ -253,6 +262,7 @@ struct nm_index {
 
 namespace nmi {
 
+constexpr uint32_t kWsCounterWords = 8;
 constexpr uint32_t kBatchMinQueries = 2;  // from 2 queries on, sharing the corpus pass pays
 
 struct ResultLayout {
@@ -284,6 +294,9 @@ uint32_t q8_pitch(uint32_t dim);
 
 // ---- nm_launch.cu: workspaces + every kernel launch ----
 int ws_acquire(Shard &sh, std::unique_ptr<Workspace> &out);
+// wait until every asynchronous nm_search_device call issued so far on this index has finished
+// (mutations call it under the write lock, so they never tear an in-flight scan)
+int wait_async_searches(nm_index *idx);
 void ws_release(Shard &sh, std::unique_ptr<Workspace> &ws);
 int ws_ensure(Workspace &ws, const Shard &sh, uint32_t dim, uint32_t nq, uint32_t k, bool need_query,
               bool need_result, bool need_hits, int gather_ranks);

@@ -6,6 +6,9 @@
 #include "prefilter_kernels.cuh"
 #include "tc_prefilter_kernels.cuh"
 
+#include <chrono>
+#include <thread>
+
 namespace nmi {
 
 size_t scan_smem_bytes(uint32_t n_stages, uint32_t q_floats) {
@@ -27,8 +30,8 @@ int ws_acquire(Shard &sh, std::unique_ptr<Workspace> &out) {
     CUDA_TRY(cudaStreamCreateWithFlags(&ws->stream, cudaStreamNonBlocking));
     CUDA_TRY(cudaEventCreate(&ws->ev0));
     CUDA_TRY(cudaEventCreate(&ws->ev1));
-    CUDA_TRY(cudaMalloc(&ws->d_counter, 2 * sizeof(uint32_t)));
-    CUDA_TRY(cudaMemsetAsync(ws->d_counter, 0, 2 * sizeof(uint32_t), ws->stream));
+    CUDA_TRY(cudaMalloc(&ws->d_counter, kWsCounterWords * sizeof(uint32_t)));
+    CUDA_TRY(cudaMemsetAsync(ws->d_counter, 0, kWsCounterWords * sizeof(uint32_t), ws->stream));
     out = std::move(ws);
     return NM_OK;
 }
@@ -37,6 +40,32 @@ void ws_release(Shard &sh, std::unique_ptr<Workspace> &ws) {
     if (!ws) return;
     std::lock_guard<std::mutex> g(sh.pool_mu);
     sh.pool.push_back(std::move(ws));
+}
+
+int wait_async_searches(nm_index *idx) {
+    for (auto &shp : idx->shards) {
+        Shard &sh = *shp;
+        std::lock_guard<std::mutex> pg(sh.pool_mu);
+        if (sh.stream_ws.empty()) continue;
+        CUDA_TRY(cudaSetDevice(sh.device));
+        for (auto &e : sh.stream_ws) {
+            Workspace &ws = *e.second;
+            if (ws.async_pending) {
+                CUDA_TRY(cudaEventSynchronize(ws.async_done));
+                ws.async_pending = false;
+            }
+            // pipelined scans record no event (it would sit between two launches and undo the
+            // overlap); their last CTA publishes the finished sequence number instead
+            for (uint32_t done = 0; ws.pipe_seq != 0;) {
+                CUDA_TRY(cudaMemcpyAsync(&done, ws.d_counter + 4, sizeof(done), cudaMemcpyDeviceToHost,
+                                         sh.copy_stream));
+                CUDA_TRY(cudaStreamSynchronize(sh.copy_stream));
+                if ((int32_t)(done - ws.pipe_seq) >= 0) break;
+                std::this_thread::sleep_for(std::chrono::microseconds(50));
+            }
+        }
+    }
+    return NM_OK;
 }
 
 int ws_ensure(Workspace &ws, const Shard &sh, uint32_t dim, uint32_t nq, uint32_t k,
@@ -50,11 +79,12 @@ int ws_ensure(Workspace &ws, const Shard &sh, uint32_t dim, uint32_t nq, uint32_
         CUDA_TRY(cudaMallocHost(&ws.h_query, qf * 4));
         ws.query_cap = qf;
     }
+    // two sets of per-CTA candidate lists: pipelined scans alternate between them
     size_t cand = (size_t)sh.sm_count * std::min<uint32_t>(k, nm::kMaxFastK);
     if (ws.cand_cap < cand) {
         if (ws.d_cand) CUDA_TRY(cudaFree(ws.d_cand));
         ws.cand_cap = 0;
-        CUDA_TRY(cudaMalloc(&ws.d_cand, cand * 8));
+        CUDA_TRY(cudaMalloc(&ws.d_cand, 2 * cand * 8));
         ws.cand_cap = cand;
     }
     if (need_result) {
@@ -106,6 +136,22 @@ int launch_scan_t(const Shard &sh, const nm::ScanParams &p, size_t smem, cudaStr
     }
     uint32_t n_rb = (p.n_rows + nm::kRowsPerBlock - 1) / nm::kRowsPerBlock;
     uint32_t grid = std::min<uint32_t>((uint32_t)sh.sm_count, n_rb);
+    if (p.pdl_seq) {
+        // programmatic dependent launch: this scan may start while the previous kernel on the
+        // stream (the previous pipelined scan) is still finishing
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(grid);
+        cfg.blockDim = dim3(nm::kScanThreads);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, sh.tmap, p));
+        return NM_OK;
+    }
     kern<<<grid, nm::kScanThreads, smem, stream>>>(sh.tmap, p);
     CUDA_TRY(cudaGetLastError());
     return NM_OK;
@@ -140,6 +186,15 @@ int launch_scan(nm_index *idx, const Shard &sh, Workspace &ws, const float *d_qu
     p.n_stages = stages;
     size_t smem = scan_smem_bytes(stages, p.q_floats);
     const bool chained = k > (uint32_t)nm::kMaxFastK;
+    const bool pipelined = ws.pipeline_next && !chained && !d_row_mask;
+    if (pipelined) {
+        p.pdl_seq = ++ws.pipe_seq;
+        p.pdl_done = ws.d_counter + 4;
+        if (p.pdl_seq & 1u) {
+            p.cand = ws.d_cand + ws.cand_cap;
+            p.done_counter = ws.d_counter + 2;
+        }
+    }
     if (chained) {
         if (ws.pass_keys_cap < k) {
             if (ws.d_pass_keys) {

@@ -307,6 +307,10 @@ static int search_impl(nm_index *idx, const float *queries, uint32_t nq, uint32_
         Shard &sh = *idx->shards[0];
         CUDA_TRY(cudaSetDevice(sh.device));
         std::lock_guard<std::mutex> cg(idx->comm_mu);
+        if (idx->xchg_async_stream) {  // asynchronous collective searches come first
+            CUDA_TRY(cudaStreamSynchronize(idx->xchg_async_stream));
+            idx->xchg_async_stream = nullptr;
+        }
         std::unique_ptr<Workspace> ws;
         rc = ws_acquire(sh, ws);
         if (rc) return rc;
@@ -617,8 +621,9 @@ int nm_search_device(nm_index *idx, const float *d_queries, uint32_t nq, uint32_
         if (!ws) {
             std::unique_ptr<Workspace> nw(new Workspace());
             nw->device = sh.device;
-            CUDA_TRY(cudaMalloc(&nw->d_counter, 2 * sizeof(uint32_t)));
-            CUDA_TRY(cudaMemsetAsync(nw->d_counter, 0, 2 * sizeof(uint32_t), stream));
+            CUDA_TRY(cudaMalloc(&nw->d_counter, kWsCounterWords * sizeof(uint32_t)));
+            CUDA_TRY(cudaMemsetAsync(nw->d_counter, 0, kWsCounterWords * sizeof(uint32_t), stream));
+            CUDA_TRY(cudaEventCreateWithFlags(&nw->async_done, cudaEventDisableTiming));
             ws = nw.get();
             sh.stream_ws.emplace_back(stream, std::move(nw));
         }
@@ -644,6 +649,22 @@ int nm_search_device(nm_index *idx, const float *d_queries, uint32_t nq, uint32_
     }
     rc = ws_ensure(*ws, sh, dim, nq, k, false, false, collective, collective ? idx->n_ranks : 0);
     if (rc) return rc;
+    // nm_index_set_pipelining: single-query scans of consecutive asynchronous calls overlap
+    // (programmatic dependent launch); profiling events between the launches would undo that
+    const bool pipelined = stream_v && idx->pipelining.load() && !idx->profiling.load();
+    ws->pipeline_next = pipelined;
+    struct PipeReset {
+        Workspace *w;
+        ~PipeReset() { w->pipeline_next = false; }
+    } pipe_reset{ws};
+    if (collective && stream_v) {
+        // the peer exchange and NCCL order collective searches by one stream: when the caller
+        // switches streams, the earlier stream's searches have to be finished first
+        std::lock_guard<std::mutex> cg(idx->comm_mu);
+        if (idx->xchg_async_stream && idx->xchg_async_stream != stream)
+            CUDA_TRY(cudaStreamSynchronize(idx->xchg_async_stream));
+        idx->xchg_async_stream = stream;
+    }
     std::pair<cudaEvent_t, cudaEvent_t> *prof = nullptr;
     if (idx->profiling.load() && sh.rows) {
         if (ws->prof_used == ws->prof_events.size()) {
@@ -688,10 +709,49 @@ int nm_search_device(nm_index *idx, const float *d_queries, uint32_t nq, uint32_
                                  stream);
         if (rc) return rc;
     }
-    if (!stream_v) CUDA_TRY(cudaStreamSynchronize(stream));
+    if (!stream_v) {
+        CUDA_TRY(cudaStreamSynchronize(stream));
+    } else if (!pipelined) {
+        // lets mutations wait for this call (wait_async_searches)
+        std::lock_guard<std::mutex> pg(sh.pool_mu);
+        CUDA_TRY(cudaEventRecord(ws->async_done, stream));
+        ws->async_pending = true;
+    }
     idx->searches += nq;
     idx->rows_scanned += (uint64_t)nq * sh.rows;
     idx->bytes_streamed += (uint64_t)nq * sh.rows * dim * 4;
+    return NM_OK;
+}
+
+int nm_index_set_pipelining(nm_index *idx, int enable) {
+    if (!idx) return fail(NM_ERR_INVALID_ARGUMENT, "null index");
+    idx->pipelining = enable ? 1 : 0;
+    return NM_OK;
+}
+
+int nm_index_release_stream(nm_index *idx, void *stream_v) {
+    if (!idx) return fail(NM_ERR_INVALID_ARGUMENT, "null index");
+    std::unique_lock<std::shared_mutex> g(idx->mu);
+    cudaStream_t stream = (cudaStream_t)stream_v;
+    for (auto &shp : idx->shards) {
+        Shard &sh = *shp;
+        CUDA_TRY(cudaSetDevice(sh.device));
+        std::unique_ptr<Workspace> victim;
+        {
+            std::lock_guard<std::mutex> pg(sh.pool_mu);
+            for (auto it = sh.stream_ws.begin(); it != sh.stream_ws.end(); ++it)
+                if (it->first == stream) {
+                    victim = std::move(it->second);
+                    sh.stream_ws.erase(it);
+                    break;
+                }
+        }
+        if (victim) CUDA_TRY(cudaStreamSynchronize(stream));  // its scratch may still be in use
+    }
+    {
+        std::lock_guard<std::mutex> cg(idx->comm_mu);
+        if (idx->xchg_async_stream == stream) idx->xchg_async_stream = nullptr;
+    }
     return NM_OK;
 }
 

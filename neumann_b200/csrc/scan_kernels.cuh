@@ -138,6 +138,23 @@ __device__ __forceinline__ uint32_t consumer_sync_popc(bool pred) {
     return total;
 }
 
+// Programmatic dependent launch (PDL): consecutive scans on one stream overlap — the next
+// query's CTAs start streaming on SMs this query has already left while its last CTA is still
+// merging / exchanging.
+__device__ __forceinline__ void pdl_launch_dependents() {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+__device__ __forceinline__ void pdl_wait_prior_grids() {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+__device__ __forceinline__ void st_release_gpu(uint32_t *p, uint32_t v) {
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t *p) {
+    uint32_t v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
 __device__ __forceinline__ void st_release_sys(uint32_t *p, uint32_t v) {
     asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
@@ -572,6 +589,13 @@ struct ScanParams {
     // set = row r takes part.  Padded to whole row blocks (8 words each).  Row blocks whose 8
     // words are all zero are never loaded.
     const uint32_t *row_mask;
+    // Pipelined launches (nm_index_set_pipelining; launched with the programmatic stream
+    // serialization attribute): pdl_seq >= 1 numbers the pipelined scans of one workspace,
+    // *pdl_done is the highest sequence number whose last CTA has finished.  `cand` and
+    // `done_counter` alternate between two sets by sequence parity, and a scan only starts
+    // once scan pdl_seq - 2 — the previous user of its set — is done.
+    uint32_t pdl_seq;
+    uint32_t *pdl_done;
 };
 
 // Read element `col` (0..31) of row t in a swizzled stage.
@@ -614,8 +638,14 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
         *thr_s = 0ull;
         *cnt_s = 0u;
         fence_mbar_init();
+        if (p.pdl_seq) {
+            // the scan two launches back used the same candidate lists and counters
+            while ((int32_t)(ld_acquire_gpu(p.pdl_done) + 2u - p.pdl_seq) < 0) __nanosleep(200);
+        }
     }
     __syncthreads();
+    // from here on the next pipelined scan may be scheduled onto SMs as they become free
+    if (p.pdl_seq) pdl_launch_dependents();
 
     if (warp == kConsumerWarps) {
         // ===================== TMA producer =====================
@@ -666,7 +696,7 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
     const uint32_t lane = t & 31u;
     // query -> shared (zero padded to a multiple of 32 floats)
     for (uint32_t i = t; i < p.q_floats; i += kRowsPerBlock)
-        q_s[i] = (i < p.dim) ? __ldg(p.query + i) : 0.0f;
+        q_s[i] = (i < p.dim) ? __ldcg(p.query + i) : 0.0f;  // L2: never a stale L1 line
     consumer_sync();
     float qmag = 0.0f;
     if (METRIC == kCosine) {
@@ -819,14 +849,22 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
     st.cap = kCandCap;
     consumer_sync();
     merge_published(st, t, p.cand, gridDim.x * p.k, p.k, ms);
+    // Pipelined: everything above overlapped with the previous scan's tail.  Its outputs, its
+    // turn in the peer exchange and its completion come first.
+    if (p.pdl_seq) pdl_wait_prior_grids();
     if (p.xchg.n_ranks > 1) {
         // p.cand has room for gridDim.x * k >= n_ranks * k merge keys only if the grid is
         // at least n_ranks CTAs; the host guarantees a scratch of max(grid, n_ranks) * k
         exchange_and_merge(st, t, p.xchg, p.row_base, p.cand, ms, p.out_rows, p.out_scores,
                            p.out_count);
+        consumer_sync();
         if (t == 0) {
             p.done_counter[0] = 0u;
             p.done_counter[1] = 0u;
+            if (p.pdl_seq) {
+                __threadfence();
+                st_release_gpu(p.pdl_done, p.pdl_seq);
+            }
         }
         return;
     }
@@ -839,10 +877,15 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
     o.row_base = p.row_base;
     o.accumulate_count = p.accumulate_count;
     write_outputs(st, t, p.k, o);
+    consumer_sync();
     if (t == 0) {
         // every CTA took its ticket after its producer's last cursor fetch: safe to reset
         p.done_counter[0] = 0u;
         p.done_counter[1] = 0u;
+        if (p.pdl_seq) {
+            __threadfence();
+            st_release_gpu(p.pdl_done, p.pdl_seq);
+        }
     }
 }
 

@@ -169,6 +169,13 @@ class DeviceIndex:
     def set_batching(self, enable: bool) -> None:
         check(_ffi.lib().nm_index_set_batching(self._h, 1 if enable else 0))
 
+    def set_pipelining(self, enable: bool) -> None:
+        """Consecutive async single-query search_device calls on one stream overlap (see header)."""
+        check(_ffi.lib().nm_index_set_pipelining(self._h, 1 if enable else 0))
+
+    def release_stream(self, stream_ptr: int) -> None:
+        check(_ffi.lib().nm_index_release_stream(self._h, stream_ptr))
+
     def set_profiling(self, enable: bool) -> None:
         check(_ffi.lib().nm_index_set_profiling(self._h, 1 if enable else 0))
 

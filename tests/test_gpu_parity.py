@@ -356,6 +356,74 @@ def test_search_device_resident_buffers():
     idx.close()
 
 
+@pytest.mark.parametrize("n,dim,k", [(300_000, 128, 10), (20_000, 96, 100), (700, 64, 5), (2_000_000, 64, 1)])
+def test_pipelined_device_searches_overlap_and_match(n, dim, k):
+    """nm_index_set_pipelining(1): consecutive asynchronous single-query calls on one caller stream
+    overlap (programmatic dependent launch, alternating scratch sets).  Every result must equal
+    the strictly serial call; outputs written into ONE shared buffer must end up holding the last
+    query's result; a mutation issued right behind the searches must wait for all of them."""
+    import torch
+    idx, rows = synth_index(n, dim)
+    nq = 40
+    q = o.fill_synthetic(nq, dim, 0x77)
+    dq = torch.from_numpy(q).cuda()
+    stream = torch.cuda.Stream()
+    d_rows = torch.zeros((nq, k), dtype=torch.int64, device="cuda")
+    d_scores = torch.zeros((nq, k), dtype=torch.float32, device="cuda")
+    d_counts = torch.zeros(nq, dtype=torch.int32, device="cuda")
+    torch.cuda.synchronize()
+
+    def run(metric, into_one=False):
+        for i in range(nq):
+            j = 0 if into_one else i
+            idx.search_device(dq[i].data_ptr(), 1, k, metric, d_rows[j].data_ptr(),
+                              d_scores[j].data_ptr(), d_counts[j].data_ptr(), stream.cuda_stream)
+
+    for metric in METRICS:
+        idx.set_pipelining(False)
+        run(metric)
+        torch.cuda.synchronize()
+        ref = (d_rows.cpu().numpy().copy(), d_scores.cpu().numpy().copy(), d_counts.cpu().numpy().copy())
+        d_rows.zero_(); d_scores.zero_(); d_counts.zero_()
+        torch.cuda.synchronize()
+        idx.set_pipelining(True)
+        s0 = idx.stats().scan_launches
+        run(metric)
+        run(metric, into_one=True)
+        assert idx.stats().scan_launches - s0 == 2 * nq
+        torch.cuda.synchronize()
+        got = (d_rows.cpu().numpy(), d_scores.cpu().numpy(), d_counts.cpu().numpy())
+        assert np.array_equal(got[2][1:], ref[2][1:])
+        assert np.array_equal(got[0][1:], ref[0][1:]), metric
+        assert np.array_equal(got[1][1:].view(np.uint32), ref[1][1:].view(np.uint32)), metric
+        # slot 0 was overwritten by every query of the second run, in call order: last one wins
+        assert np.array_equal(got[0][0], ref[0][nq - 1]) and got[2][0] == ref[2][nq - 1]
+        for i in (1, nq - 1):
+            er, es = o.search(rows, q[i], k, metric, threads=8)
+            m = int(ref[2][i])
+            assert np.array_equal(ref[0][i][:m].astype(np.uint64), er)
+            assert np.array_equal(ref[1][i][:m].view(np.uint32), es.view(np.uint32))
+    # a mutation right behind a burst of pipelined searches waits for them (no torn scan): the
+    # query itself is planted as the last row while 40 searches are in flight; all 40 must still
+    # report the corpus as it was
+    idx.set_pipelining(False)
+    run("cosine")
+    torch.cuda.synchronize()
+    before = d_rows.cpu().numpy().copy()
+    d_rows.zero_()
+    torch.cuda.synchronize()
+    idx.set_pipelining(True)
+    run("cosine")
+    idx.update(n - 1, q[3])
+    torch.cuda.synchronize()
+    assert np.array_equal(d_rows.cpu().numpy(), before)
+    (after,) = idx.search(q[3], k, "cosine")
+    assert o.compute_score(q[3], q[3], "cosine").view(np.uint32) == after[1][0].view(np.uint32)
+    assert n - 1 in after[0]
+    idx.release_stream(stream.cuda_stream)
+    idx.close()
+
+
 def test_concurrent_single_queries_are_coalesced():
     """16 host threads issue single-query nm_search calls at once (the reference's serving
     pattern): calls queue behind the running scan and share corpus passes; every result must
