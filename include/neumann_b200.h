@@ -80,7 +80,12 @@ void nm_index_destroy(nm_index *idx);
  * pageable).  Rows are split into contiguous ranges [g*n/G, (g+1)*n/G) over the devices.  */
 int nm_index_load(nm_index *idx, const float *rows, uint64_t n);
 /* Append `n` rows after the current last row (store_embedding of new keys, lib.rs:1840-1868).
- * Appended rows go to the last device shard. */
+ * The mirror grows IN PLACE: more physical memory is mapped behind the existing rows (CUDA
+ * virtual memory management; the reference's own precedent is the chunked EmbeddingSlab,
+ * tensor_store/src/embedding_slab.rs:27, 92-124), nothing is copied, so a mirror can grow up to
+ * the free memory of the device.  On an in-process multi-device index the rows land on the last
+ * shard (the end of the global row order); once that shard holds more than twice its share the
+ * rows are re-split into equal contiguous ranges — global row ids never change. */
 int nm_index_append(nm_index *idx, const float *rows, uint64_t n);
 /* Overwrite one row in place (store_embedding of an existing key). */
 int nm_index_update(nm_index *idx, uint64_t row, const float *vec);
@@ -99,6 +104,20 @@ int nm_index_get_rows(nm_index *idx, uint64_t first, uint64_t n, float *out_rows
 uint64_t nm_index_rows(const nm_index *idx);
 uint32_t nm_index_dim(const nm_index *idx);
 int nm_index_device_count(const nm_index *idx);
+/* Diagnostics: where shard `shard` (0 .. nm_index_device_count-1) stands. */
+typedef struct nm_shard_info {
+    int device;
+    uint64_t rows;            /* rows held                                                 */
+    uint64_t row_base;        /* global id of its first row                                 */
+    uint64_t capacity_rows;   /* rows the mapped part of the mirror can hold                */
+    uint64_t mapped_bytes;    /* physical memory behind the f32 mirror                      */
+    uint64_t reserved_bytes;  /* virtual address range reserved for it                      */
+    uint64_t chunks;          /* physical allocations mapped into the range                 */
+    uint64_t remaps;          /* times the range was replaced by a larger one (no copy)     */
+    uint64_t q8_rows;         /* rows of the int8 copy that are current (0 = no copy)       */
+    int grows_in_place;       /* 1 = virtual memory management, 0 = realloc-and-copy fallback */
+} nm_shard_info;
+int nm_index_shard_info(nm_index *idx, int shard, nm_shard_info *out);
 
 /* Fill the mirror ON DEVICE with the synthetic corpus of SURVEY 8d:
  *   x[r,c] = u24(splitmix64(splitmix64(seed) ^ ((row_offset + r)*dim + c))) * 2^-23 - 1

@@ -39,6 +39,15 @@ class NmStats(C.Structure):
     ]
 
 
+class NmShardInfo(C.Structure):
+    _fields_ = [
+        ("device", C.c_int), ("rows", C.c_uint64), ("row_base", C.c_uint64),
+        ("capacity_rows", C.c_uint64), ("mapped_bytes", C.c_uint64), ("reserved_bytes", C.c_uint64),
+        ("chunks", C.c_uint64), ("remaps", C.c_uint64), ("q8_rows", C.c_uint64),
+        ("grows_in_place", C.c_int),
+    ]
+
+
 _f32p = C.POINTER(C.c_float)
 _u64p = C.POINTER(C.c_uint64)
 _u32p = C.POINTER(C.c_uint32)
@@ -61,6 +70,7 @@ SIGNATURES = {
     "nm_index_rows": (C.c_uint64, [_vp]),
     "nm_index_dim": (C.c_uint32, [_vp]),
     "nm_index_device_count": (C.c_int, [_vp]),
+    "nm_index_shard_info": (C.c_int, [_vp, C.c_int, C.POINTER(NmShardInfo)]),
     "nm_index_fill_synthetic": (C.c_int, [_vp, C.c_uint64, C.c_uint64, C.c_uint64]),
     "nm_search": (C.c_int, [_vp, _vp, C.c_uint32, C.c_uint32, C.c_int, _vp, _vp, _vp]),
     "nm_search_masked": (C.c_int, [_vp, _vp, C.c_uint32, C.c_uint32, C.c_int, _vp, _vp, _vp, _vp]),

@@ -144,29 +144,28 @@ int q8_refresh(nm_index *idx, Shard &sh, uint64_t first, uint64_t n, bool build)
     if (mode == 2 && !build && !sh.d_q8) return NM_OK;  // auto: nothing to keep up to date yet
     const uint32_t pitch8 = q8_pitch(idx->dim);
     if (sh.rows > sh.q8_capacity) {
-        uint64_t cap = std::max<uint64_t>(sh.rows, sh.capacity);
-        int8_t *nq = nullptr;
-        nm::RowMeta *nmeta = nullptr;
-        float2 *nnorms = nullptr;
-        CUDA_TRY(cudaMalloc(&nq, cap * pitch8));
-        CUDA_TRY(cudaMalloc(&nmeta, cap * sizeof(nm::RowMeta)));
-        CUDA_TRY(cudaMalloc(&nnorms, cap * sizeof(float2)));
-        if (sh.d_q8 && sh.q8_rows) {
-            CUDA_TRY(cudaMemcpyAsync(nq, sh.d_q8, sh.q8_rows * pitch8, cudaMemcpyDeviceToDevice,
-                                     sh.copy_stream));
-            CUDA_TRY(cudaMemcpyAsync(nmeta, sh.d_meta, sh.q8_rows * sizeof(nm::RowMeta),
-                                     cudaMemcpyDeviceToDevice, sh.copy_stream));
-            CUDA_TRY(cudaMemcpyAsync(nnorms, sh.d_norms, sh.q8_rows * sizeof(float2),
-                                     cudaMemcpyDeviceToDevice, sh.copy_stream));
-            CUDA_TRY(cudaStreamSynchronize(sh.copy_stream));
+        // grows in place like the f32 mirror: rows already quantised keep their bytes
+        const bool exact = sh.q8_rows == 0;
+        int rc = sh.q8_buf.ensure(sh.device, sh.rows * (size_t)pitch8, exact);
+        if (!rc) rc = sh.meta_buf.ensure(sh.device, sh.rows * sizeof(nm::RowMeta), exact);
+        if (!rc) rc = sh.norms_buf.ensure(sh.device, sh.rows * sizeof(float2), exact);
+        if (rc) {
+            sh.q8_buf.release();
+            sh.meta_buf.release();
+            sh.norms_buf.release();
+            sh.d_q8 = nullptr;
+            sh.d_meta = nullptr;
+            sh.d_norms = nullptr;
+            sh.q8_capacity = sh.q8_rows = 0;
+            sh.tmap8_valid = false;
+            return rc;
         }
-        if (sh.d_q8) CUDA_TRY(cudaFree(sh.d_q8));
-        if (sh.d_meta) CUDA_TRY(cudaFree(sh.d_meta));
-        if (sh.d_norms) CUDA_TRY(cudaFree(sh.d_norms));
-        sh.d_q8 = nq;
-        sh.d_meta = nmeta;
-        sh.d_norms = nnorms;
-        sh.q8_capacity = cap;
+        sh.d_q8 = static_cast<int8_t *>(sh.q8_buf.ptr());
+        sh.d_meta = static_cast<nm::RowMeta *>(sh.meta_buf.ptr());
+        sh.d_norms = static_cast<float2 *>(sh.norms_buf.ptr());
+        sh.q8_capacity = std::min<uint64_t>({sh.q8_buf.mapped() / pitch8,
+                                             sh.meta_buf.mapped() / sizeof(nm::RowMeta),
+                                             sh.norms_buf.mapped() / sizeof(float2)});
     }
     if (!sh.d_q8_flag) {
         CUDA_TRY(cudaMalloc(&sh.d_q8_flag, sizeof(uint32_t)));
@@ -237,18 +236,13 @@ int shard_reserve(nm_index *idx, Shard &sh, uint64_t rows, bool keep) {
     if (rows > nm::kMaxLocalRows)
         return fail(NM_ERR_INVALID_ARGUMENT, "shard would hold %llu rows; limit is %u per device",
                     (unsigned long long)rows, nm::kMaxLocalRows);
-    uint64_t cap = rows;
-    if (keep && sh.capacity) cap = std::max<uint64_t>(rows, sh.capacity + sh.capacity / 2);
-    float *p = nullptr;
-    CUDA_TRY(cudaMalloc(&p, cap * idx->pitch * sizeof(float)));
-    if (keep && sh.rows) {
-        CUDA_TRY(cudaMemcpyAsync(p, sh.d_rows, sh.rows * idx->pitch * sizeof(float),
-                                 cudaMemcpyDeviceToDevice, sh.copy_stream));
-        CUDA_TRY(cudaStreamSynchronize(sh.copy_stream));
-    }
-    if (sh.d_rows) CUDA_TRY(cudaFree(sh.d_rows));
-    sh.d_rows = p;
-    sh.capacity = cap;
+    // keep == appending: grow geometrically, IN PLACE (more physical chunks mapped behind the
+    // existing rows; see nm_vmm.hpp).  !keep == bulk load: map exactly what the load needs.
+    const size_t row_bytes = (size_t)idx->pitch * sizeof(float);
+    int rc = sh.rows_buf.ensure(sh.device, rows * row_bytes, !keep);
+    if (rc) return rc;
+    sh.d_rows = static_cast<float *>(sh.rows_buf.ptr());
+    sh.capacity = sh.rows_buf.mapped() / row_bytes;
     return NM_OK;
 }
 
@@ -367,10 +361,10 @@ void nm_index_destroy(nm_index *idx) {
         cudaDeviceSynchronize();  // asynchronous nm_search_device work may still be in flight
         sh->pool.clear();
         sh->stream_ws.clear();
-        if (sh->d_rows) cudaFree(sh->d_rows);
-        if (sh->d_q8) cudaFree(sh->d_q8);
-        if (sh->d_meta) cudaFree(sh->d_meta);
-        if (sh->d_norms) cudaFree(sh->d_norms);
+        sh->rows_buf.release();
+        sh->q8_buf.release();
+        sh->meta_buf.release();
+        sh->norms_buf.release();
         if (sh->d_q8_flag) cudaFree(sh->d_q8_flag);
         for (int b = 0; b < 2; ++b) {
             if (sh->staging[b]) cudaFreeHost(sh->staging[b]);
@@ -421,6 +415,102 @@ int nm_index_load(nm_index *idx, const float *rows, uint64_t n) {
     return NM_OK;
 }
 
+// Global row ids are positions in the concatenation of the shards: keep every shard's base the
+// prefix sum of the shards before it (appends and swap-removes change the last shards' sizes).
+static void recompute_row_bases(nm_index *idx) {
+    uint64_t base = 0;
+    for (auto &sh : idx->shards) {
+        sh->row_base = base;
+        base += sh->rows;
+    }
+}
+
+// Device-to-device copy of `n` mirror rows between two shards; different devices go through the
+// source shard's pinned staging buffer (works with or without peer access).
+static int copy_rows_between(nm_index *idx, Shard &src, uint64_t src_row, Shard &dst, float *dst_base,
+                             uint64_t dst_row, uint64_t n) {
+    const size_t row_bytes = (size_t)idx->pitch * 4;
+    if (n == 0) return NM_OK;
+    if (src.device == dst.device) {
+        CUDA_TRY(cudaSetDevice(src.device));
+        CUDA_TRY(cudaMemcpyAsync(dst_base + dst_row * idx->pitch, src.d_rows + src_row * idx->pitch,
+                                 n * row_bytes, cudaMemcpyDeviceToDevice, src.copy_stream));
+        CUDA_TRY(cudaStreamSynchronize(src.copy_stream));
+        return NM_OK;
+    }
+    CUDA_TRY(cudaSetDevice(src.device));
+    if (!src.staging[0]) {
+        for (int b = 0; b < 2; ++b) {
+            CUDA_TRY(cudaMallocHost(&src.staging[b], kStagingBytes));
+            CUDA_TRY(cudaEventCreateWithFlags(&src.staging_done[b], cudaEventDisableTiming));
+        }
+    }
+    const uint64_t per = std::max<uint64_t>(1, kStagingBytes / row_bytes);
+    if (row_bytes > kStagingBytes)
+        return fail(NM_ERR_DIMENSION_MISMATCH, "dimension %u too large for staging", idx->dim);
+    for (uint64_t r = 0; r < n; r += per) {
+        const uint64_t m = std::min(per, n - r);
+        CUDA_TRY(cudaSetDevice(src.device));
+        CUDA_TRY(cudaMemcpyAsync(src.staging[0], src.d_rows + (src_row + r) * idx->pitch,
+                                 m * row_bytes, cudaMemcpyDeviceToHost, src.copy_stream));
+        CUDA_TRY(cudaStreamSynchronize(src.copy_stream));
+        CUDA_TRY(cudaSetDevice(dst.device));
+        CUDA_TRY(cudaMemcpyAsync(dst_base + (dst_row + r) * idx->pitch, src.staging[0], m * row_bytes,
+                                 cudaMemcpyHostToDevice, dst.copy_stream));
+        CUDA_TRY(cudaStreamSynchronize(dst.copy_stream));
+    }
+    return NM_OK;
+}
+
+// In-process multi-device indexes: appends land on the last shard (the end of the global row
+// order).  Once it holds more than twice its share, the rows are re-split into equal contiguous
+// ranges [s*N/G, (s+1)*N/G) — global row ids do not change, so the caller's key table stays
+// valid.  Each shard is rebuilt in a fresh buffer (old + new coexist per device while it runs).
+static int rebalance_shards(nm_index *idx, bool force) {
+    const uint64_t G = idx->shards.size();
+    if (G < 2) return NM_OK;
+    const uint64_t N = idx->total_rows();
+    uint64_t mx = 0;
+    for (auto &sh : idx->shards) mx = std::max(mx, sh->rows);
+    if (!force && mx <= 2 * ((N + G - 1) / G) + 4096) return NM_OK;
+    std::vector<GrowBuf> nb(G);  // (default-constructed in place: GrowBuf is not copyable)
+    const size_t row_bytes = (size_t)idx->pitch * 4;
+    for (uint64_t s = 0; s < G; ++s) {
+        Shard &dst = *idx->shards[s];
+        const uint64_t lo = N * s / G, hi = N * (s + 1) / G;
+        if (hi == lo) continue;
+        CUDA_TRY(cudaSetDevice(dst.device));
+        int rc = nb[s].ensure(dst.device, (hi - lo) * row_bytes, true);
+        if (rc) return rc;
+        float *base = static_cast<float *>(nb[s].ptr());
+        for (auto &tp : idx->shards) {
+            Shard &src = *tp;
+            const uint64_t a = std::max(lo, src.row_base), b = std::min(hi, src.row_base + src.rows);
+            if (a >= b) continue;
+            rc = copy_rows_between(idx, src, a - src.row_base, dst, base, a - lo, b - a);
+            if (rc) return rc;
+        }
+    }
+    for (uint64_t s = 0; s < G; ++s) {
+        Shard &sh = *idx->shards[s];
+        const uint64_t lo = N * s / G, hi = N * (s + 1) / G;
+        CUDA_TRY(cudaSetDevice(sh.device));
+        sh.rows_buf.swap(nb[s]);
+        nb[s].release();
+        sh.d_rows = static_cast<float *>(sh.rows_buf.ptr());
+        sh.capacity = sh.rows_buf.mapped() / row_bytes;
+        sh.rows = hi - lo;
+        sh.row_base = lo;
+        int rc = build_tmap(idx, sh);
+        if (rc) return rc;
+        sh.q8_rows = 0;
+        sh.tmap8_valid = false;
+        rc = q8_refresh(idx, sh, 0, sh.rows);
+        if (rc) return rc;
+    }
+    return NM_OK;
+}
+
 int nm_index_append(nm_index *idx, const float *rows, uint64_t n) {
     if (!idx) return fail(NM_ERR_INVALID_ARGUMENT, "null index");
     if (n == 0) return NM_OK;
@@ -434,9 +524,12 @@ int nm_index_append(nm_index *idx, const float *rows, uint64_t n) {
     rc = shard_upload(idx, sh, sh.rows, rows, n);
     if (rc) return rc;
     sh.rows += n;
+    recompute_row_bases(idx);
     rc = build_tmap(idx, sh);
     if (rc) return rc;
-    return q8_refresh(idx, sh, sh.rows - n, n);
+    rc = q8_refresh(idx, sh, sh.rows - n, n);
+    if (rc) return rc;
+    return rebalance_shards(idx, false);
 }
 
 static int locate_row(nm_index *idx, uint64_t row, Shard **out, uint64_t *local) {
@@ -482,18 +575,11 @@ int nm_index_swap_remove(nm_index *idx, uint64_t row, uint64_t *moved_from) {
     uint64_t last_global = last->row_base + last->rows - 1;
     if (moved_from) *moved_from = last_global;
     if (last_global != row) {
-        const size_t bytes = (size_t)idx->pitch * 4;
-        const float *src = last->d_rows + (last->rows - 1) * idx->pitch;
-        float *dst = sh->d_rows + local * idx->pitch;
-        CUDA_TRY(cudaSetDevice(sh->device));
-        if (last->device == sh->device)
-            CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, sh->copy_stream));
-        else
-            CUDA_TRY(cudaMemcpyPeerAsync(dst, sh->device, src, last->device, bytes,
-                                         sh->copy_stream));
-        CUDA_TRY(cudaStreamSynchronize(sh->copy_stream));
+        rc = copy_rows_between(idx, *last, last->rows - 1, *sh, sh->d_rows, local, 1);
+        if (rc) return rc;
     }
     last->rows -= 1;
+    recompute_row_bases(idx);
     CUDA_TRY(cudaSetDevice(last->device));
     rc = build_tmap(idx, *last);
     if (rc) return rc;
@@ -547,6 +633,25 @@ uint64_t nm_index_rows(const nm_index *idx) {
 uint32_t nm_index_dim(const nm_index *idx) { return idx ? idx->dim : 0; }
 int nm_index_device_count(const nm_index *idx) { return idx ? (int)idx->shards.size() : 0; }
 
+int nm_index_shard_info(nm_index *idx, int shard, nm_shard_info *out) {
+    if (!idx || !out) return fail(NM_ERR_INVALID_ARGUMENT, "null argument");
+    std::shared_lock<std::shared_mutex> g(idx->mu);
+    if (shard < 0 || shard >= (int)idx->shards.size())
+        return fail(NM_ERR_INVALID_ARGUMENT, "shard %d out of range", shard);
+    const Shard &sh = *idx->shards[shard];
+    out->device = sh.device;
+    out->rows = sh.rows;
+    out->row_base = sh.row_base;
+    out->capacity_rows = sh.capacity;
+    out->mapped_bytes = sh.rows_buf.mapped();
+    out->reserved_bytes = sh.rows_buf.reserved();
+    out->chunks = sh.rows_buf.chunks();
+    out->remaps = sh.rows_buf.remaps();
+    out->q8_rows = sh.d_q8 ? sh.q8_rows : 0;
+    out->grows_in_place = sh.rows_buf.vmm() ? 1 : 0;
+    return NM_OK;
+}
+
 int nm_index_fill_synthetic(nm_index *idx, uint64_t n, uint64_t seed, uint64_t row_offset) {
     if (!idx) return fail(NM_ERR_INVALID_ARGUMENT, "null index");
     std::unique_lock<std::shared_mutex> g(idx->mu);
@@ -587,9 +692,9 @@ int nm_index_set_prefilter(nm_index *idx, int mode) {
         Shard &sh = *shp;
         CUDA_TRY(cudaSetDevice(sh.device));
         if (mode == 0) {
-            if (sh.d_q8) CUDA_TRY(cudaFree(sh.d_q8));
-            if (sh.d_meta) CUDA_TRY(cudaFree(sh.d_meta));
-            if (sh.d_norms) CUDA_TRY(cudaFree(sh.d_norms));
+            sh.q8_buf.release();
+            sh.meta_buf.release();
+            sh.norms_buf.release();
             sh.d_q8 = nullptr;
             sh.d_meta = nullptr;
             sh.d_norms = nullptr;

@@ -6,6 +6,7 @@
 #pragma once
 #include "../../include/neumann_b200.h"
 #include "nm_types.hpp"
+#include "nm_vmm.hpp"
 
 #include <cuda.h>
 #include <cuda_runtime.h>
@@ -170,9 +171,12 @@ struct Workspace {
 struct Shard {
     int device = 0;
     int sm_count = 0;
-    float *d_rows = nullptr;
+    // The mirror and its int8 copy live in buffers that grow in place (nm_vmm.hpp): appends map
+    // more physical chunks behind the existing rows, nothing is ever copied to grow.
+    GrowBuf rows_buf, q8_buf, meta_buf, norms_buf;
+    float *d_rows = nullptr;  // == rows_buf.ptr()
     uint64_t rows = 0;      // local rows
-    uint64_t capacity = 0;  // local rows allocated
+    uint64_t capacity = 0;  // local rows the mapped part of rows_buf holds
     uint64_t row_base = 0;  // global index of local row 0 (within this process)
     CUtensorMap tmap;
     bool tmap_valid = false;

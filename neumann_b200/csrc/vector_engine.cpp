@@ -500,20 +500,22 @@ Result<float> VectorEngine::compute_similarity(const std::vector<float> &a,
 // ---- collections ----
 struct VectorEngine::CollectionEntry {
     std::optional<VectorCollectionConfig> config;
-    std::unique_ptr<Space> space{new Space()};
+    std::shared_ptr<Space> space{new Space()};
 };
 
-VectorEngine::Space &VectorEngine::collection_space(const std::string &name) {
+std::shared_ptr<VectorEngine::Space> VectorEngine::collection_space(const std::string &name) {
     std::unique_lock<std::shared_mutex> g(collections_mu_);
     auto &e = collections_[name];
     if (!e) e.reset(new CollectionEntry());
-    return *e->space;
+    return e->space;
 }
 
-const VectorEngine::Space *VectorEngine::find_collection_space(const std::string &name) const {
+std::shared_ptr<const VectorEngine::Space> VectorEngine::find_collection_space(
+    const std::string &name) const {
     std::shared_lock<std::shared_mutex> g(collections_mu_);
     auto it = collections_.find(name);
-    return it == collections_.end() ? nullptr : it->second->space.get();
+    if (it == collections_.end()) return nullptr;
+    return it->second->space;
 }
 
 Result<Unit> VectorEngine::create_collection(const std::string &name,
@@ -531,7 +533,9 @@ Result<Unit> VectorEngine::delete_collection(const std::string &name) {
     auto it = collections_.find(name);
     if (it == collections_.end() || !it->second->config)
         return err(ErrorKind::CollectionNotFound, name);
-    collections_.erase(it);  // drops the rows and the device mirror with it
+    // drops the map's reference; operations still running on the collection hold their own, the
+    // last one out destroys the rows and the device mirror
+    collections_.erase(it);
     return Unit{};
 }
 
@@ -562,12 +566,13 @@ Result<Unit> VectorEngine::store_in_collection(const std::string &collection,
     }
     if (config_.max_dimension && vector.size() > *config_.max_dimension)
         return dim_mismatch(*config_.max_dimension, vector.size());
-    return store_in_space(collection_space(collection), key, std::move(vector));
+    std::shared_ptr<Space> sp = collection_space(collection);
+    return store_in_space(*sp, key, std::move(vector));
 }
 
 Result<std::vector<float>> VectorEngine::get_from_collection(const std::string &collection,
                                                              const std::string &key) const {
-    const Space *sp = find_collection_space(collection);
+    std::shared_ptr<const Space> sp = find_collection_space(collection);
     if (!sp) return err(ErrorKind::NotFound, collection + ":" + key);
     auto r = get_in_space(*sp, key);
     if (r.is_err()) return err(ErrorKind::NotFound, collection + ":" + key);
@@ -576,15 +581,15 @@ Result<std::vector<float>> VectorEngine::get_from_collection(const std::string &
 
 Result<Unit> VectorEngine::delete_from_collection(const std::string &collection,
                                                   const std::string &key) {
-    const Space *sp = find_collection_space(collection);
+    std::shared_ptr<const Space> sp = find_collection_space(collection);
     if (!sp) return err(ErrorKind::NotFound, collection + ":" + key);
-    auto r = delete_in_space(*const_cast<Space *>(sp), key);
+    auto r = delete_in_space(*const_cast<Space *>(sp.get()), key);
     if (r.is_err()) return err(ErrorKind::NotFound, collection + ":" + key);
     return r;
 }
 
 size_t VectorEngine::collection_count(const std::string &collection) const {
-    const Space *sp = find_collection_space(collection);
+    std::shared_ptr<const Space> sp = find_collection_space(collection);
     if (!sp) return 0;
     std::shared_lock<std::shared_mutex> g(sp->mu);
     return sp->where.size();
@@ -597,7 +602,7 @@ Result<std::vector<SearchResult>> VectorEngine::search_in_collection(
     if (query.empty()) return err(ErrorKind::EmptyVector);
     if (top_k == 0) return err(ErrorKind::InvalidTopK);
     DistanceMetric metric = DistanceMetric::Cosine;
-    const Space *sp = nullptr;
+    std::shared_ptr<const Space> sp;  // keeps the collection alive across a concurrent delete
     {
         std::shared_lock<std::shared_mutex> g(collections_mu_);
         auto it = collections_.find(collection);
@@ -608,7 +613,7 @@ Result<std::vector<SearchResult>> VectorEngine::search_in_collection(
                     return dim_mismatch(*it->second->config->dimension, query.size());
                 metric = it->second->config->distance_metric;
             }
-            sp = it->second->space.get();
+            sp = it->second->space;
         }
     }
     float qmag = simd::magnitude(query.data(), query.size());
@@ -650,7 +655,8 @@ Result<Unit> VectorEngine::store_in_collection_with_metadata(const std::string &
     }
     if (config_.max_dimension && vector.size() > *config_.max_dimension)
         return dim_mismatch(*config_.max_dimension, vector.size());
-    return store_in_space(collection_space(collection), key, std::move(vector), &metadata);
+    std::shared_ptr<Space> sp = collection_space(collection);
+    return store_in_space(*sp, key, std::move(vector), &metadata);
 }
 
 namespace {
@@ -735,7 +741,7 @@ Result<std::vector<SearchResult>> VectorEngine::search_filtered_in_collection(
     if (query.empty()) return err(ErrorKind::EmptyVector);
     if (top_k == 0) return err(ErrorKind::InvalidTopK);
     DistanceMetric metric = DistanceMetric::Cosine;
-    const Space *sp = nullptr;
+    std::shared_ptr<const Space> sp;  // keeps the collection alive across a concurrent delete
     {
         std::shared_lock<std::shared_mutex> g(collections_mu_);
         auto it = collections_.find(collection);
@@ -746,12 +752,12 @@ Result<std::vector<SearchResult>> VectorEngine::search_filtered_in_collection(
                     return dim_mismatch(*it->second->config->dimension, query.size());
                 metric = it->second->config->distance_metric;
             }
-            sp = it->second->space.get();
+            sp = it->second->space;
         }
     }
     // zero query -> empty for every metric on this path (lib.rs:1729-1732)
     if (simd::magnitude(query.data(), query.size()) == 0.0f) return std::vector<SearchResult>{};
-    return filtered_in_space(sp, query, top_k, metric, filter,
+    return filtered_in_space(sp.get(), query, top_k, metric, filter,
                              config.value_or(FilteredSearchConfig{}),
                              "search_filtered_in_collection", start);
 }

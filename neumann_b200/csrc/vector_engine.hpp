@@ -223,8 +223,12 @@ class VectorEngine {
     // create_collection, lib.rs:1445-1500); `config` is set by create_collection only.
     struct CollectionEntry;
     std::map<std::string, std::unique_ptr<CollectionEntry>> collections_;
-    Space &collection_space(const std::string &name);              // creates on demand
-    const Space *find_collection_space(const std::string &name) const;
+    // Collection spaces are handed out as shared_ptr copies taken under collections_mu_: a
+    // concurrent delete_collection only drops the map's reference, the last running operation
+    // destroys the rows and the device mirrors (the reference's VectorEngine is Send + Sync and
+    // its delete_collection is safe against concurrent searches, lib.rs:1127-1131).
+    std::shared_ptr<Space> collection_space(const std::string &name);  // creates on demand
+    std::shared_ptr<const Space> find_collection_space(const std::string &name) const;
 
     bool should_use_sparse(const std::vector<float> &v) const;  // lib.rs:1871-1886
     Result<Unit> store_in_space(Space &sp, const std::string &key, std::vector<float> vector,

@@ -90,6 +90,15 @@ class DeviceIndex:
         check(_ffi.lib().nm_index_get_rows(self._h, first, n, out.ctypes.data))
         return out.reshape(-1)[:n * self.dim].reshape(n, self.dim)
 
+    def shard_info(self, shard: int = 0) -> "_ffi.NmShardInfo":
+        info = _ffi.NmShardInfo()
+        check(_ffi.lib().nm_index_shard_info(self._h, shard, C.byref(info)))
+        return info
+
+    @property
+    def n_shards(self) -> int:
+        return int(_ffi.lib().nm_index_device_count(self._h))
+
     def fill_synthetic(self, n: int, seed: int, row_offset: int = 0) -> None:
         check(_ffi.lib().nm_index_fill_synthetic(self._h, n, seed, row_offset))
 

@@ -301,3 +301,63 @@ def test_search_entities_on_gpu():
     assert [np.float32(r.score).view(np.uint32) for r in res] == list(es.view(np.uint32))
     e.remove_entity_embedding("user:77")
     assert e.search_entities(q, 1)[0].key != "user:77"
+
+
+def test_delete_collection_is_safe_against_concurrent_searches_and_stores():
+    """Advisor finding (round 1): delete_collection used to free a Space (rows + device mirror)
+    that concurrent search_in_collection / store_in_collection calls were still using.  Spaces are
+    shared_ptr-held now: hammer one collection name with searches, stores and delete/recreate
+    cycles from several threads; nothing may crash and every result must be well formed."""
+    import threading
+    e = eng.VectorEngine()
+    d = 32
+    rows = o.fill_synthetic(600, d, 91)
+    stop = threading.Event()
+    errors = []
+
+    def fill():
+        for i in range(300):
+            e.store_in_collection("hot", f"k{i}", rows[i])
+
+    e.create_collection("hot", dimension=d)
+    fill()
+
+    def searcher():
+        try:
+            while not stop.is_set():
+                res = e.search_in_collection("hot", rows[7], 5)
+                assert len(res) <= 5 and all(r.key.startswith("k") for r in res)
+                scores = [r.score for r in res]
+                assert scores == sorted(scores, reverse=True)
+        except Exception as ex:  # noqa: BLE001
+            errors.append(repr(ex))
+
+    def storer():
+        try:
+            i = 300
+            while not stop.is_set():
+                e.store_in_collection("hot", f"k{i % 600}", rows[i % 600])
+                i += 1
+        except Exception as ex:  # noqa: BLE001
+            errors.append(repr(ex))
+
+    ts = [threading.Thread(target=searcher) for _ in range(3)] + [threading.Thread(target=storer)]
+    for t in ts:
+        t.start()
+    for _ in range(25):
+        try:
+            e.delete_collection("hot")
+        except eng.VectorError:
+            pass                      # the storer may have re-created the rows without a config
+        try:
+            e.create_collection("hot", dimension=d)
+        except eng.VectorError:
+            pass
+        fill()
+    stop.set()
+    for t in ts:
+        t.join()
+    assert not errors, errors[:2]
+    res = e.search_in_collection("hot", rows[7], 1)
+    assert res and res[0].key == "k7"
+    e.close()

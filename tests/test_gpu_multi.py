@@ -57,6 +57,63 @@ def test_in_process_two_device_shards_tensor_core(metric):
     idx.close()
 
 
+def test_two_device_mutations_keep_row_ids_dense():
+    """Advisor finding (round 1): after swap-removes across the shard boundary an append must not
+    leave a gap in the global row ids.  Load 4 rows on 2 devices, remove rows 3, 2 and 0, append:
+    the new row is row 1 of 2, every id a search returns is < rows, and update/get_row find it."""
+    _need(2)
+    d = 8
+    rows = o.fill_synthetic(6, d, 77)
+    idx = DeviceIndex(d, devices=[0, 1])
+    idx.load(rows[:4])
+    assert idx.swap_remove(3) == 3
+    assert idx.swap_remove(2) == 2
+    assert idx.swap_remove(0) == 1          # row 1 moved into slot 0
+    assert idx.rows == 1
+    idx.append(rows[4:5])
+    assert idx.rows == 2
+    host = np.stack([rows[1], rows[4]])
+    assert np.array_equal(idx.get_row(1), rows[4])
+    for metric in ("cosine", "euclidean", "dot"):
+        ((r, s),) = idx.search(rows[4], 5, metric)
+        er, es = o.search(host, rows[4], 5, metric)
+        assert np.array_equal(r, er) and np.array_equal(s.view(np.uint32), es.view(np.uint32))
+        assert all(int(x) < idx.rows for x in r)
+    idx.update(1, rows[5])
+    assert np.array_equal(idx.get_row(1), rows[5])
+    bases = [idx.shard_info(i).row_base for i in range(2)]
+    sizes = [idx.shard_info(i).rows for i in range(2)]
+    assert bases[0] == 0 and bases[1] == sizes[0] and sum(sizes) == 2
+    idx.close()
+
+
+def test_two_device_appends_are_rebalanced():
+    """Appends land on the last shard; once it holds more than twice its share the rows are re-split
+    into equal contiguous ranges.  Global row ids (== the caller's key table) never change."""
+    _need(2)
+    d, n0, step = 48, 10_000, 9_000
+    rows = o.fill_synthetic(n0 + 6 * step, d, 0x5EED0001)
+    idx = DeviceIndex(d, devices=[0, 1])
+    idx.load(rows[:n0])
+    n = n0
+    q = o.fill_synthetic(1, d, 3)[0]
+    for i in range(6):
+        idx.append(rows[n:n + step])
+        n += step
+        sizes = [idx.shard_info(s).rows for s in range(2)]
+        assert sum(sizes) == n and max(sizes) <= 2 * ((n + 1) // 2) + 4096
+        assert idx.shard_info(1).row_base == sizes[0]
+        ((r, s),) = idx.search(q, 25, "cosine")
+        er, es = o.search(rows[:n], q, 25, "cosine", threads=4)
+        assert np.array_equal(r, er) and np.array_equal(s.view(np.uint32), es.view(np.uint32))
+    sizes = [idx.shard_info(s).rows for s in range(2)]
+    assert min(sizes) > n // 4, sizes                       # re-split happened at least once
+    probe = [0, sizes[0] - 1, sizes[0], n - 1]
+    for g in probe:
+        assert np.array_equal(idx.get_row(g), rows[g])
+    idx.close()
+
+
 def _free_port():
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
@@ -74,6 +131,7 @@ def _nccl_worker(rank, world, port, q):
     try:
         n, d, k = 200_003, 96, 16
         idx = DeviceIndex(d, devices=[rank])
+        idx.set_prefilter(0)      # exact kernels first; the tensor-core pass is switched on below
         lo, hi = nd.attach_index(idx, n)
         idx.fill_synthetic(hi - lo, 0x5EED0001, row_offset=lo)
         qs = o.fill_synthetic(3, d, 0x5EED1001)
