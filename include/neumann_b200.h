@@ -84,7 +84,7 @@ int nm_index_load(nm_index *idx, const float *rows, uint64_t n);
  * virtual memory management; the reference's own precedent is the chunked EmbeddingSlab,
  * tensor_store/src/embedding_slab.rs:27, 92-124), nothing is copied, so a mirror can grow up to
  * the free memory of the device.  On an in-process multi-device index the rows land on the last
- * shard (the end of the global row order); once that shard holds more than twice its share the
+ * shard (the end of the global row order); once a shard holds more than 1.5x its share the
  * rows are re-split into equal contiguous ranges — global row ids never change. */
 int nm_index_append(nm_index *idx, const float *rows, uint64_t n);
 /* Overwrite one row in place (store_embedding of an existing key). */
@@ -140,10 +140,68 @@ int nm_search(nm_index *idx, const float *queries, uint32_t nq, uint32_t k, int 
  * "filter first, then search the subset").  row_mask is a host bitmask over the mirror's rows,
  * bit (r % 64) of word r / 64 set = row r is eligible; ceil(rows / 64) words.  Ineligible rows
  * never rank, and 256-row blocks without any eligible row are not even read from HBM.
- * Single-device indexes without a communicator. */
+ * In-process multi-device indexes take their slices of the mask; on a collective index the mask
+ * covers THIS process's rows (local row r = bit r). */
 int nm_search_masked(nm_index *idx, const float *queries, uint32_t nq, uint32_t k, int metric,
                      const uint64_t *row_mask, uint64_t *out_rows, float *out_scores,
                      uint32_t *out_counts);
+
+/* ---- metadata columns + device-side filter evaluation (finishes search_with_pre_filter,
+ *      vector_engine/src/lib.rs:3514-3557, and search_filtered_in_collection :1698-1829: the
+ *      FilterCondition tree is evaluated ON THE DEVICE into the row bitmask of the scan, with
+ *      the type rules of evaluate_filter / compare_tensor_value_to_filter, lib.rs:3592-3684) ---- */
+typedef enum nm_value_tag {
+    NM_V_MISSING = 0, /* the row has no such field                                   */
+    NM_V_NULL = 1,
+    NM_V_BOOL = 2,    /* value 0 / 1                                                  */
+    NM_V_INT = 3,     /* value = the int64                                            */
+    NM_V_FLOAT = 4,   /* value = the bits of the double                               */
+    NM_V_STRING = 5   /* value = code of the string in the CALLER's dictionary of that column */
+} nm_value_tag;
+/* Set the metadata of rows [first_row, first_row + n) in column `column` (one column per field;
+ * ids are the caller's).  Rows never set read as NM_V_MISSING; appended rows start missing;
+ * swap_remove moves the column entries with the row; load / clear / fill_synthetic drop all
+ * columns.  Works on single-device, in-process multi-device and collective indexes (rows are
+ * this process's rows). */
+int nm_index_column_set(nm_index *idx, uint32_t column, uint64_t first_row, uint64_t n,
+                        const uint8_t *tags, const uint64_t *values);
+typedef enum nm_filter_kind {
+    NM_F_TRUE = 0, NM_F_FALSE = 1,
+    NM_F_AND = 2, NM_F_OR = 3,     /* pop two, push one                                        */
+    NM_F_EXISTS = 4,               /* the row has the field                                     */
+    NM_F_CMP = 5,                  /* field <cmp> literal; literal NULL / BOOL / INT / FLOAT    */
+    NM_F_STR_TABLE = 6             /* the row holds a string whose code has its bit set in the
+                                      table: the caller evaluated the string predicate (=, <,
+                                      CONTAINS, STARTS_WITH, IN ...) once per DISTINCT string   */
+} nm_filter_kind;
+typedef enum nm_filter_cmp { NM_C_EQ = 0, NM_C_NE, NM_C_LT, NM_C_LE, NM_C_GT, NM_C_GE } nm_filter_cmp;
+/* One op of a filter in POSTFIX order (<= 128 ops, stack depth <= 64).  A missing field or an
+ * incomparable pair of types makes every comparison false, `!=` included (lib.rs:3642-3656). */
+typedef struct nm_filter_op {
+    uint8_t kind;         /* nm_filter_kind                                     */
+    uint8_t cmp;          /* nm_filter_cmp (NM_F_CMP)                           */
+    uint8_t lit_tag;      /* nm_value_tag of the literal (NM_F_CMP)             */
+    uint8_t reserved;
+    uint32_t column;      /* leaves                                             */
+    uint64_t lit;         /* NM_F_CMP: int64 / double bits / bool               */
+    uint32_t table_off;   /* NM_F_STR_TABLE: first u32 word of its bit table in `tables` */
+    uint32_t table_bits;  /* NM_F_STR_TABLE: number of dictionary codes covered */
+} nm_filter_op;
+/* nm_search over the rows that pass the filter.  The mask is computed on the device (one small
+ * kernel, HBM-bound on 9 bytes per row and referenced column), cached per filter until the next
+ * mutation, and applied inside the scan: ineligible rows never rank and 256-row blocks without
+ * an eligible row are not read.  Single-device, in-process multi-device and collective indexes
+ * (every rank passes the same program; each shard evaluates its own rows). */
+int nm_search_filtered(nm_index *idx, const float *queries, uint32_t nq, uint32_t k, int metric,
+                       const nm_filter_op *program, uint32_t n_ops, const uint32_t *tables,
+                       uint32_t n_table_words, uint64_t *out_rows, float *out_scores,
+                       uint32_t *out_counts);
+/* Diagnostics / count_matching: evaluate the filter only.  out_mask (may be NULL): bit (r % 64)
+ * of word r / 64 = row r passes, ceil(rows / 64) words over this process's rows;
+ * *out_eligible (may be NULL) = number of passing rows. */
+int nm_index_filter_mask(nm_index *idx, const nm_filter_op *program, uint32_t n_ops,
+                         const uint32_t *tables, uint32_t n_table_words, uint64_t *out_mask,
+                         uint64_t *out_eligible);
 
 /* Same scan with the query and the outputs resident in DEVICE memory of the index's first
  * device and the work enqueued on `stream` (a cudaStream_t).  With a caller stream the call
@@ -208,6 +266,8 @@ typedef struct nm_stats {
     uint64_t tc_queries;          /* queries served through the tensor-core batch pre-filter */
     uint64_t tc_fallbacks;        /* of those, redone by the exact path                     */
     uint64_t tc_survivors;        /* (row, query) pairs re-scored exactly                    */
+    uint64_t filter_masks_built;  /* filter programs evaluated on the device (per shard)     */
+    uint64_t filter_mask_hits;    /* filtered searches served from the per-filter mask cache */
 } nm_stats;
 int nm_index_stats(nm_index *idx, nm_stats *out);
 /* When enabled, every asynchronous nm_search_device call brackets its scan launches (not the

@@ -36,6 +36,7 @@ class NmStats(C.Structure):
         ("prefilter_kept", C.c_uint64),
         ("coalesced_batches", C.c_uint64), ("coalesced_queries", C.c_uint64),
         ("tc_queries", C.c_uint64), ("tc_fallbacks", C.c_uint64), ("tc_survivors", C.c_uint64),
+        ("filter_masks_built", C.c_uint64), ("filter_mask_hits", C.c_uint64),
     ]
 
 
@@ -47,6 +48,17 @@ class NmShardInfo(C.Structure):
         ("grows_in_place", C.c_int),
     ]
 
+
+class NmFilterOp(C.Structure):
+    _fields_ = [
+        ("kind", C.c_uint8), ("cmp", C.c_uint8), ("lit_tag", C.c_uint8), ("reserved", C.c_uint8),
+        ("column", C.c_uint32), ("lit", C.c_uint64), ("table_off", C.c_uint32), ("table_bits", C.c_uint32),
+    ]
+
+
+NM_V_MISSING, NM_V_NULL, NM_V_BOOL, NM_V_INT, NM_V_FLOAT, NM_V_STRING = range(6)
+NM_F_TRUE, NM_F_FALSE, NM_F_AND, NM_F_OR, NM_F_EXISTS, NM_F_CMP, NM_F_STR_TABLE = range(7)
+NM_C_EQ, NM_C_NE, NM_C_LT, NM_C_LE, NM_C_GT, NM_C_GE = range(6)
 
 _f32p = C.POINTER(C.c_float)
 _u64p = C.POINTER(C.c_uint64)
@@ -75,6 +87,10 @@ SIGNATURES = {
     "nm_search": (C.c_int, [_vp, _vp, C.c_uint32, C.c_uint32, C.c_int, _vp, _vp, _vp]),
     "nm_search_masked": (C.c_int, [_vp, _vp, C.c_uint32, C.c_uint32, C.c_int, _vp, _vp, _vp, _vp]),
     "nm_search_device": (C.c_int, [_vp, _vp, C.c_uint32, C.c_uint32, C.c_int, _vp, _vp, _vp, _vp]),
+    "nm_index_column_set": (C.c_int, [_vp, C.c_uint32, C.c_uint64, C.c_uint64, _vp, _vp]),
+    "nm_search_filtered": (C.c_int, [_vp, _vp, C.c_uint32, C.c_uint32, C.c_int, _vp, C.c_uint32, _vp,
+                                     C.c_uint32, _vp, _vp, _vp]),
+    "nm_index_filter_mask": (C.c_int, [_vp, _vp, C.c_uint32, _vp, C.c_uint32, _vp, _u64p]),
     "nm_comm_create_id": (C.c_int, [_vp]),
     "nm_index_attach_comm": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_uint64]),
     "nm_index_detach_comm": (C.c_int, [_vp]),

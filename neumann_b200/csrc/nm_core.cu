@@ -385,7 +385,9 @@ int nm_index_clear(nm_index *idx) {
         sh->tmap_valid = false;
         sh->q8_rows = 0;
         sh->tmap8_valid = false;
+        columns_drop(*sh);
     }
+    idx->mutation_epoch++;
     return NM_OK;
 }
 
@@ -400,6 +402,8 @@ int nm_index_load(nm_index *idx, const float *rows, uint64_t n) {
         uint64_t lo = n * s / G, hi = n * (s + 1) / G;
         CUDA_TRY(cudaSetDevice(sh.device));
         sh.rows = 0;
+        columns_drop(sh);
+        idx->mutation_epoch++;
         int rc = shard_reserve(idx, sh, hi - lo, false);
         if (rc) return rc;
         rc = shard_upload(idx, sh, 0, rows + lo * idx->dim, hi - lo);
@@ -463,7 +467,7 @@ static int copy_rows_between(nm_index *idx, Shard &src, uint64_t src_row, Shard 
 }
 
 // In-process multi-device indexes: appends land on the last shard (the end of the global row
-// order).  Once it holds more than twice its share, the rows are re-split into equal contiguous
+// order).  Once a shard holds more than 1.5x its share, the rows are re-split into equal contiguous
 // ranges [s*N/G, (s+1)*N/G) — global row ids do not change, so the caller's key table stays
 // valid.  Each shard is rebuilt in a fresh buffer (old + new coexist per device while it runs).
 static int rebalance_shards(nm_index *idx, bool force) {
@@ -472,7 +476,14 @@ static int rebalance_shards(nm_index *idx, bool force) {
     const uint64_t N = idx->total_rows();
     uint64_t mx = 0;
     for (auto &sh : idx->shards) mx = std::max(mx, sh->rows);
-    if (!force && mx <= 2 * ((N + G - 1) / G) + 4096) return NM_OK;
+    const uint64_t share = (N + G - 1) / G;
+    if (!force && mx <= share + share / 2 + 4096) return NM_OK;
+    std::shared_ptr<ColumnsSnapshot> cols;
+    {
+        int rc = columns_gather(idx, &cols);  // metadata columns follow the rows
+        if (rc) return rc;
+    }
+    idx->mutation_epoch++;
     std::vector<GrowBuf> nb(G);  // (default-constructed in place: GrowBuf is not copyable)
     const size_t row_bytes = (size_t)idx->pitch * 4;
     for (uint64_t s = 0; s < G; ++s) {
@@ -508,7 +519,7 @@ static int rebalance_shards(nm_index *idx, bool force) {
         rc = q8_refresh(idx, sh, 0, sh.rows);
         if (rc) return rc;
     }
-    return NM_OK;
+    return columns_scatter(idx, *cols);
 }
 
 int nm_index_append(nm_index *idx, const float *rows, uint64_t n) {
@@ -524,8 +535,11 @@ int nm_index_append(nm_index *idx, const float *rows, uint64_t n) {
     rc = shard_upload(idx, sh, sh.rows, rows, n);
     if (rc) return rc;
     sh.rows += n;
+    idx->mutation_epoch++;
     recompute_row_bases(idx);
     rc = build_tmap(idx, sh);
+    if (rc) return rc;
+    rc = columns_after_resize(idx, sh);  // the new rows read as "missing" in every column
     if (rc) return rc;
     rc = q8_refresh(idx, sh, sh.rows - n, n);
     if (rc) return rc;
@@ -577,8 +591,13 @@ int nm_index_swap_remove(nm_index *idx, uint64_t row, uint64_t *moved_from) {
     if (last_global != row) {
         rc = copy_rows_between(idx, *last, last->rows - 1, *sh, sh->d_rows, local, 1);
         if (rc) return rc;
+        rc = columns_swap_remove(idx, *sh, local, *last, last->rows - 1);
+        if (rc) return rc;
     }
     last->rows -= 1;
+    idx->mutation_epoch++;
+    rc = columns_after_resize(idx, *last);
+    if (rc) return rc;
     recompute_row_bases(idx);
     CUDA_TRY(cudaSetDevice(last->device));
     rc = build_tmap(idx, *last);
@@ -662,6 +681,8 @@ int nm_index_fill_synthetic(nm_index *idx, uint64_t n, uint64_t seed, uint64_t r
         uint64_t lo = n * s / G, hi = n * (s + 1) / G;
         CUDA_TRY(cudaSetDevice(sh.device));
         sh.rows = 0;
+        columns_drop(sh);
+        idx->mutation_epoch++;
         int rc = shard_reserve(idx, sh, hi - lo, false);
         if (rc) return rc;
         if (hi > lo) {
@@ -760,6 +781,8 @@ int nm_index_stats(nm_index *idx, nm_stats *out) {
     out->tc_survivors = idx->tc_survivors;
     out->coalesced_batches = idx->co_batches;
     out->coalesced_queries = idx->co_queries;
+    out->filter_masks_built = idx->filter_masks_built;
+    out->filter_mask_hits = idx->filter_mask_hits;
     {
         // fold finished profiling event pairs into the totals (waits for the streams)
         std::unique_lock<std::shared_mutex> g(idx->mu);

@@ -17,6 +17,7 @@
 #include <condition_variable>
 #include <cstdint>
 #include <cstring>
+#include <map>
 #include <memory>
 #include <mutex>
 #include <shared_mutex>
@@ -168,6 +169,42 @@ struct Workspace {
     }
 };
 
+// One metadata field of the rows of a shard (filter_kernels.cuh).  Both arrays cover the
+// shard's rows [0, init_rows) (zero = missing beyond what was ever set) and grow in place.
+struct Column {
+    GrowBuf tags_buf, vals_buf;
+    uint8_t *d_tags = nullptr;
+    uint64_t *d_vals = nullptr;
+    uint64_t init_rows = 0;
+};
+
+// A computed row mask, shared between the cache and the searches using it.
+struct MaskEntry {
+    int device = 0;
+    std::vector<uint8_t> key;   // program bytes + table words
+    uint64_t epoch = 0;         // nm_index::mutation_epoch it was computed at
+    uint32_t *d_mask = nullptr; // [words] u32, padded to whole row blocks
+    size_t words = 0;
+    void *d_prog = nullptr;     // FilterOpDev[] followed by the string tables
+    cudaEvent_t ready = nullptr;
+    ~MaskEntry() {
+        cudaSetDevice(device);
+        if (d_mask) cudaFree(d_mask);
+        if (d_prog) cudaFree(d_prog);
+        if (ready) cudaEventDestroy(ready);
+    }
+};
+
+// What restricts a search to a subset of the rows: a host bitmask or a filter program.
+struct MaskSpec {
+    const uint64_t *host_mask = nullptr;
+    const nm_filter_op *prog = nullptr;
+    uint32_t n_ops = 0;
+    const uint32_t *tables = nullptr;
+    uint32_t n_table_words = 0;
+    bool any() const { return host_mask || prog; }
+};
+
 struct Shard {
     int device = 0;
     int sm_count = 0;
@@ -190,6 +227,11 @@ struct Shard {
     CUtensorMap tmap8;
     CUtensorMap tmap8_tc;  // same copy, [128 rows x 128 B] boxes (tensor-core batch pre-filter)
     bool tmap8_valid = false;
+    // metadata columns (nm_index_column_set): typed per-row values next to the mirror, and the
+    // row masks of recently used filters (valid until the next mutation)
+    std::map<uint32_t, std::unique_ptr<Column>> columns;
+    std::mutex mask_mu;
+    std::vector<std::shared_ptr<MaskEntry>> mask_cache;
     cudaStream_t copy_stream = nullptr;
     float *staging[2] = {nullptr, nullptr};
     cudaEvent_t staging_done[2] = {nullptr, nullptr};
@@ -255,6 +297,8 @@ struct nm_index {
     std::vector<PendingSearch *> co_pending;
     bool co_leader = false;
     std::atomic<uint64_t> co_batches{0}, co_queries{0};
+    std::atomic<uint64_t> filter_masks_built{0}, filter_mask_hits{0};
+    std::atomic<uint64_t> mutation_epoch{0};  // bumped by everything that invalidates row masks
     double profiled_scan_ms = 0.0;  // guarded by mu (exclusive) in nm_index_stats
     uint64_t profiled_scans = 0;
     uint64_t total_rows() const {
@@ -308,7 +352,7 @@ int ws_ensure_prefilter(Workspace &ws, uint32_t nq);
 uint32_t single_query_stages(uint32_t dim);
 bool batch_eligible(const nm_index *idx, const Shard &sh, uint32_t nq, uint32_t k, int metric);
 bool prefilter_usable(const nm_index *idx, const Shard &sh, uint32_t nq, uint32_t k, int metric,
-                      const uint64_t *row_mask);
+                      bool masked);
 int launch_scan(nm_index *idx, const Shard &sh, Workspace &ws, const float *d_query, uint32_t k,
                 int metric, uint64_t row_base, uint64_t *out_rows, float *out_scores,
                 uint32_t *out_count, nm::ShardHit *out_hits, cudaStream_t stream,
@@ -320,7 +364,7 @@ int launch_prefiltered(nm_index *idx, const Shard &sh, Workspace &ws, const floa
                        uint32_t q, uint32_t k, int metric, uint64_t *out_rows, float *out_scores,
                        uint32_t *out_count, cudaStream_t stream);
 bool tc_usable(const nm_index *idx, const Shard &sh, uint32_t nq, uint32_t k, int metric,
-               const uint64_t *row_mask);
+               bool masked);
 // nq queries through the tensor-core pre-filter; h_flags[q] != 0 afterwards (once the stream has
 // been waited for) means query q must be redone by the exact path.  *h_flags_out points into
 // pinned memory owned by the workspace.
@@ -347,6 +391,25 @@ int launch_fill_synthetic(const Shard &sh, float *rows, uint64_t n, uint32_t dim
 int launch_quantize(const Shard &sh, const float *rows, uint32_t pitch, uint32_t dim, uint64_t first,
                     uint64_t n, int8_t *q8, uint32_t pitch8, nm::RowMeta *meta, float2 *norms,
                     uint32_t *flag, cudaStream_t stream);
+
+int launch_filter_mask(const Shard &sh, const nm::FilterOpDev *d_ops, uint32_t n_ops, uint64_t n_rows,
+                       uint32_t *d_mask, uint64_t n_words, cudaStream_t stream);
+int launch_column_move(uint8_t *tags, uint64_t *vals, uint64_t dst, uint64_t src, cudaStream_t stream);
+
+// ---- nm_columns.cu: metadata columns, filter -> row mask ----
+// (all but shard_mask are called with the index write lock held)
+int columns_after_resize(nm_index *idx, Shard &sh);  // rows appended: new rows read as missing
+void columns_drop(Shard &sh);                        // load / clear: rows replaced
+int columns_swap_remove(nm_index *idx, Shard &dst, uint64_t dst_local, Shard &src, uint64_t src_local);
+struct ColumnsSnapshot;                               // all columns of all shards, on the host
+int columns_gather(nm_index *idx, std::shared_ptr<ColumnsSnapshot> *out);
+int columns_scatter(nm_index *idx, const ColumnsSnapshot &snap);
+int validate_filter_program(const nm_filter_op *prog, uint32_t n_ops, const uint32_t *tables,
+                            uint32_t n_table_words);
+// The device mask of `spec` for this shard on `stream` (shared lock held).  `first_row` = global
+// index (within spec.host_mask) of the shard's row 0.  *hold keeps a cached mask alive.
+int shard_mask(nm_index *idx, Shard &sh, Workspace &ws, const MaskSpec &spec, uint64_t first_row,
+               cudaStream_t stream, const uint32_t **d_mask, std::shared_ptr<MaskEntry> *hold);
 
 // ---- nm_comm.cu ----
 nm::PeerXchg make_xchg(const nm_index *idx, uint32_t seq);

@@ -5,6 +5,7 @@
 #include "batch_kernels.cuh"
 #include "prefilter_kernels.cuh"
 #include "tc_prefilter_kernels.cuh"
+#include "filter_kernels.cuh"
 
 #include <chrono>
 #include <thread>
@@ -410,8 +411,8 @@ size_t prefilter_smem_bytes(uint32_t n_stages, uint32_t q_words) {
 }
 
 bool prefilter_usable(const nm_index *idx, const Shard &sh, uint32_t nq, uint32_t k, int metric,
-                      const uint64_t *row_mask) {
-    if (idx->prefilter.load() != 1 || row_mask || metric == NM_EUCLIDEAN) return false;
+                      bool masked) {
+    if (idx->prefilter.load() != 1 || masked || metric == NM_EUCLIDEAN) return false;
     if (!sh.tmap8_valid || sh.q8_rows != sh.rows || sh.rows == 0) return false;
     if (k > (uint32_t)nm::kMaxFastK || k > sh.rows) return false;
     if (idx->batching.load() && nq >= kBatchMinQueries && (idx->dim % 8u) == 0) return false;
@@ -506,9 +507,9 @@ bool tc_shape_ok(const nm_index *idx, uint64_t shard_rows, uint32_t nq, uint32_t
 }
 
 bool tc_usable(const nm_index *idx, const Shard &sh, uint32_t nq, uint32_t k, int metric,
-               const uint64_t *row_mask) {
+               bool masked) {
     (void)metric;
-    if (!idx->prefilter.load() || !idx->tensor_core.load() || !idx->batching.load() || row_mask)
+    if (!idx->prefilter.load() || !idx->tensor_core.load() || !idx->batching.load() || masked)
         return false;
     if (!sh.tmap8_valid || sh.q8_rows != sh.rows) return false;
     return tc_shape_ok(idx, sh.rows, nq, k);
@@ -849,6 +850,21 @@ int launch_exchange_empty(const nm::PeerXchg &x, uint32_t k, uint64_t *scratch, 
                           float *out_scores, uint32_t *out_count, cudaStream_t stream) {
     nm::exchange_empty_shard_kernel<<<1, nm::kRowsPerBlock, 0, stream>>>(x, k, scratch, out_rows,
                                                                          out_scores, out_count);
+    CUDA_TRY(cudaGetLastError());
+    return NM_OK;
+}
+
+int launch_filter_mask(const Shard &sh, const nm::FilterOpDev *d_ops, uint32_t n_ops, uint64_t n_rows,
+                       uint32_t *d_mask, uint64_t n_words, cudaStream_t stream) {
+    const uint64_t padded = n_words * 32ull;
+    const uint32_t blocks = (uint32_t)std::min<uint64_t>((padded + 255) / 256, (uint64_t)sh.sm_count * 8);
+    nm::filter_mask_kernel<<<blocks, 256, 0, stream>>>(d_ops, n_ops, n_rows, d_mask, n_words);
+    CUDA_TRY(cudaGetLastError());
+    return NM_OK;
+}
+
+int launch_column_move(uint8_t *tags, uint64_t *vals, uint64_t dst, uint64_t src, cudaStream_t stream) {
+    nm::column_move_kernel<<<1, 1, 0, stream>>>(tags, vals, dst, src);
     CUDA_TRY(cudaGetLastError());
     return NM_OK;
 }

@@ -86,8 +86,10 @@ int download_results(nm_index *idx, const Shard &sh, Workspace &ws, const Result
 }
 
 // Rank-independent routing decision for collective searches (every rank must agree).
-bool collective_uses_fused_exchange(const nm_index *idx, uint32_t nq, uint32_t k, int metric) {
+bool collective_uses_fused_exchange(const nm_index *idx, uint32_t nq, uint32_t k, int metric,
+                                    bool masked = false) {
     if (!idx->xchg_ok || k > (uint32_t)nm::kMaxFastK) return false;
+    if (masked) return true;  // masked searches always scan query by query
     const bool long_rows = single_query_stages(idx->dim) < 4;
     const bool would_batch = (idx->batching.load() || single_query_stages(idx->dim) < 2) &&
                              (nq >= kBatchMinQueries || long_rows) &&
@@ -98,7 +100,7 @@ bool collective_uses_fused_exchange(const nm_index *idx, uint32_t nq, uint32_t k
 // One fused launch per query: scan + peer-memory exchange + merge, results written in place.
 int collective_fused(nm_index *idx, const Shard &sh, Workspace &ws, const float *d_queries,
                      uint32_t nq, uint32_t k, int metric, uint64_t *out_rows, float *out_scores,
-                     uint32_t *out_counts, cudaStream_t stream) {
+                     uint32_t *out_counts, cudaStream_t stream, const uint32_t *d_mask = nullptr) {
     for (uint32_t q = 0; q < nq; ++q) {
         nm::PeerXchg x = make_xchg(idx, ++idx->xchg_seq);
         if (sh.rows == 0) {
@@ -109,7 +111,7 @@ int collective_fused(nm_index *idx, const Shard &sh, Workspace &ws, const float 
         } else {
             int rc = launch_scan(idx, sh, ws, d_queries + (size_t)q * idx->dim, k, metric,
                                  idx->comm_row_base, out_rows + (size_t)q * k,
-                                 out_scores + (size_t)q * k, out_counts + q, nullptr, stream, &x);
+                                 out_scores + (size_t)q * k, out_counts + q, nullptr, stream, &x, d_mask);
             if (rc) return rc;
         }
     }
@@ -120,12 +122,25 @@ int collective_fused(nm_index *idx, const Shard &sh, Workspace &ws, const float 
 
 extern "C" {
 
+// one masked scan per query into this shard's hit list (masked searches do not batch)
+static int masked_hits(nm_index *idx, const Shard &sh, Workspace &ws, const float *d_queries, uint32_t nq,
+                       uint32_t k, int metric, uint64_t row_base, nm::ShardHit *out_hits,
+                       cudaStream_t stream, const uint32_t *d_mask) {
+    for (uint32_t q = 0; q < nq; ++q) {
+        int rc = launch_scan(idx, sh, ws, d_queries + (size_t)q * idx->dim, k, metric, row_base, nullptr,
+                             nullptr, nullptr, out_hits + (size_t)q * k, stream, nullptr, d_mask);
+        if (rc) return rc;
+    }
+    return NM_OK;
+}
+
 static int search_impl(nm_index *idx, const float *queries, uint32_t nq, uint32_t k, int metric,
-                       const uint64_t *row_mask, uint64_t *out_rows, float *out_scores,
+                       const MaskSpec &mspec, uint64_t *out_rows, float *out_scores,
                        uint32_t *out_counts) {
     int rc = validate_search(idx, queries, nq, k, metric, out_rows, out_scores, out_counts);
     if (rc) return rc;
-    if (nq >= 2 && !row_mask) {
+    const bool masked = mspec.any();
+    if (nq >= 2 && !masked) {
         rc = q8_auto_prepare(idx, nq, k);  // auto mode: first eligible batch builds the int8 copy
         if (rc) return rc;
     }
@@ -135,9 +150,7 @@ static int search_impl(nm_index *idx, const float *queries, uint32_t nq, uint32_
     const bool collective = idx->comm != nullptr;
     if (collective && G != 1)
         return fail(NM_ERR_CONFIGURATION, "a communicator needs a single-device index per rank");
-    if (row_mask && (collective || G != 1))
-        return fail(NM_ERR_CONFIGURATION,
-                    "nm_search_masked needs a single-device index without a communicator");
+    std::vector<std::shared_ptr<MaskEntry>> mask_holds(G);  // cached masks stay alive until the sync
 
     // ---- fast path: one device, no communicator: the kernel writes the final result ----
     if (G == 1 && !collective) {
@@ -164,31 +177,18 @@ static int search_impl(nm_index *idx, const float *queries, uint32_t nq, uint32_
         uint64_t *r_rows = reinterpret_cast<uint64_t *>(ws->d_result + l.rows_off);
         float *r_scores = reinterpret_cast<float *>(ws->d_result + l.scores_off);
         uint32_t *r_counts = reinterpret_cast<uint32_t *>(ws->d_result + l.counts_off);
-        if (row_mask) {
-            // stage the bitmask (bit r of word r/64 == bit r%32 of u32 word r/32 on little
-            // endian hosts), padded with zeros to whole row blocks
-            const size_t words = (((size_t)sh.rows + 255) / 256) * 8;
-            const size_t src_bytes = (((size_t)sh.rows + 63) / 64) * 8;
-            if (ws->mask_cap < words) {
-                if (ws->d_mask) CUDA_TRY(cudaFree(ws->d_mask));
-                ws->mask_cap = 0;
-                CUDA_TRY(cudaMalloc(&ws->d_mask, words * 4));
-                ws->mask_cap = words;
-            }
-            CUDA_TRY(cudaMemsetAsync(ws->d_mask, 0, words * 4, ws->stream));
-            CUDA_TRY(cudaMemcpyAsync(ws->d_mask, row_mask, src_bytes, cudaMemcpyHostToDevice,
-                                     ws->stream));
-            idx->h2d_bytes += src_bytes;
-        }
+        const uint32_t *d_mask = nullptr;
+        rc = shard_mask(idx, sh, *ws, mspec, sh.row_base, ws->stream, &d_mask, &mask_holds[0]);
+        if (rc) return rc;
         CUDA_TRY(cudaEventRecord(ws->ev0, ws->stream));
-        if (row_mask) {
+        if (masked) {
             for (uint32_t q = 0; q < nq; ++q) {
                 rc = launch_scan(idx, sh, *ws, ws->d_query + (size_t)q * dim, k, metric, sh.row_base,
                                  r_rows + (size_t)q * k, r_scores + (size_t)q * k, r_counts + q,
-                                 nullptr, ws->stream, nullptr, ws->d_mask);
+                                 nullptr, ws->stream, nullptr, d_mask);
                 if (rc) return rc;
             }
-        } else if (tc_usable(idx, sh, nq, k, metric, row_mask)) {
+        } else if (tc_usable(idx, sh, nq, k, metric, masked)) {
             // tensor-core pre-filter: one int8 GEMM pass per 256 queries + exact re-score; the
             // per-query flags come back with the results, flagged queries are redone exactly
             rc = scan_queries_tc(idx, sh, *ws, ws->d_query, nq, k, metric, sh.row_base, r_rows,
@@ -241,7 +241,7 @@ static int search_impl(nm_index *idx, const float *queries, uint32_t nq, uint32_
                 idx->d2h_bytes += l.total + (uint64_t)nq * 48;
                 return NM_OK;
             }
-        } else if (prefilter_usable(idx, sh, nq, k, metric, row_mask)) {
+        } else if (prefilter_usable(idx, sh, nq, k, metric, masked)) {
             rc = ws_ensure_prefilter(*ws, nq);
             if (rc) return rc;
             for (uint32_t q = 0; q < nq; ++q) {
@@ -328,17 +328,25 @@ static int search_impl(nm_index *idx, const float *queries, uint32_t nq, uint32_
         memcpy(ws->h_query, queries, (size_t)nq * dim * 4);
         CUDA_TRY(cudaMemcpyAsync(ws->d_query, ws->h_query, (size_t)nq * dim * 4,
                                  cudaMemcpyHostToDevice, ws->stream));
+        // masks of a collective index cover this rank's own rows (local row r = bit r)
+        const uint32_t *d_mask = nullptr;
+        rc = shard_mask(idx, sh, *ws, mspec, 0, ws->stream, &d_mask, &mask_holds[0]);
+        if (rc) return rc;
         CUDA_TRY(cudaEventRecord(ws->ev0, ws->stream));
-        if (collective_uses_fused_exchange(idx, nq, k, metric)) {
+        if (collective_uses_fused_exchange(idx, nq, k, metric, masked)) {
             rc = collective_fused(idx, sh, *ws, ws->d_query, nq, k, metric, r_rows, r_scores,
-                                  r_counts, ws->stream);
+                                  r_counts, ws->stream, d_mask);
             if (rc) return rc;
             CUDA_TRY(cudaEventRecord(ws->ev1, ws->stream));
         } else {
             if (sh.rows == 0) {
                 CUDA_TRY(cudaMemsetAsync(ws->d_hits, 0, (size_t)nq * k * sizeof(nm::ShardHit),
                                          ws->stream));
-            } else if (tc_usable(idx, sh, nq, k, metric, nullptr)) {
+            } else if (masked) {
+                rc = masked_hits(idx, sh, *ws, ws->d_query, nq, k, metric, idx->comm_row_base,
+                                 ws->d_hits, ws->stream, d_mask);
+                if (rc) return rc;
+            } else if (tc_usable(idx, sh, nq, k, metric, false)) {
                 // this shard's hits through the tensor-core pre-filter (a rank-local choice:
                 // the exchange format is the same)
                 rc = scan_queries_tc_hits_enqueue(idx, sh, *ws, ws->d_query, nq, k, metric,
@@ -386,10 +394,17 @@ static int search_impl(nm_index *idx, const float *queries, uint32_t nq, uint32_
         memcpy(ws.h_query, queries, (size_t)nq * dim * 4);
         CUDA_TRY(cudaMemcpyAsync(ws.d_query, ws.h_query, (size_t)nq * dim * 4,
                                  cudaMemcpyHostToDevice, ws.stream));
+        const uint32_t *d_mask = nullptr;
+        rc = shard_mask(idx, sh, ws, mspec, sh.row_base, ws.stream, &d_mask, &mask_holds[s]);
+        if (rc) return rc;
         CUDA_TRY(cudaEventRecord(ws.ev0, ws.stream));
         if (sh.rows == 0) {
             CUDA_TRY(cudaMemsetAsync(ws.d_hits, 0, (size_t)nq * k * sizeof(nm::ShardHit), ws.stream));
-        } else if (tc_usable(idx, sh, nq, k, metric, nullptr)) {
+        } else if (masked) {
+            rc = masked_hits(idx, sh, ws, ws.d_query, nq, k, metric, sh.row_base, ws.d_hits, ws.stream,
+                             d_mask);
+            if (rc) return rc;
+        } else if (tc_usable(idx, sh, nq, k, metric, false)) {
             tc_shard[s] = true;
             any_tc = true;
             rc = scan_queries_tc_hits_enqueue(idx, sh, ws, ws.d_query, nq, k, metric, sh.row_base,
@@ -495,7 +510,7 @@ static int search_coalesced(nm_index *idx, const float *query, uint32_t k, int m
         const uint32_t dim = idx->dim;
         int rc;
         if (nb == 1) {
-            rc = search_impl(idx, batch[0]->query, 1, k, metric, nullptr, batch[0]->out_rows,
+            rc = search_impl(idx, batch[0]->query, 1, k, metric, MaskSpec(), batch[0]->out_rows,
                              batch[0]->out_scores, batch[0]->out_count);
         } else {
             std::vector<float> qs((size_t)nb * dim);
@@ -504,7 +519,7 @@ static int search_coalesced(nm_index *idx, const float *query, uint32_t k, int m
             std::vector<uint32_t> counts(nb);
             for (uint32_t i = 0; i < nb; ++i)
                 memcpy(&qs[(size_t)i * dim], batch[i]->query, (size_t)dim * 4);
-            rc = search_impl(idx, qs.data(), nb, k, metric, nullptr, rows.data(), scores.data(),
+            rc = search_impl(idx, qs.data(), nb, k, metric, MaskSpec(), rows.data(), scores.data(),
                              counts.data());
             if (rc == NM_OK)
                 for (uint32_t i = 0; i < nb; ++i) {
@@ -535,7 +550,7 @@ int nm_search(nm_index *idx, const float *queries, uint32_t nq, uint32_t k, int 
     if (idx && nq == 1 && idx->coalesce_max.load() > 1 && queries && out_rows && out_scores &&
         out_counts && k > 0 && metric >= 0 && metric <= 2 && idx->comm == nullptr)
         return search_coalesced(idx, queries, k, metric, out_rows, out_scores, out_counts);
-    return search_impl(idx, queries, nq, k, metric, nullptr, out_rows, out_scores, out_counts);
+    return search_impl(idx, queries, nq, k, metric, MaskSpec(), out_rows, out_scores, out_counts);
 }
 
 int nm_debug_tc_dots(nm_index *idx, const float *queries, uint32_t nq, int32_t *out) {
@@ -593,7 +608,23 @@ int nm_search_masked(nm_index *idx, const float *queries, uint32_t nq, uint32_t 
                      const uint64_t *row_mask, uint64_t *out_rows, float *out_scores,
                      uint32_t *out_counts) {
     if (!row_mask) return fail(NM_ERR_INVALID_ARGUMENT, "null row mask");
-    return search_impl(idx, queries, nq, k, metric, row_mask, out_rows, out_scores, out_counts);
+    MaskSpec spec;
+    spec.host_mask = row_mask;
+    return search_impl(idx, queries, nq, k, metric, spec, out_rows, out_scores, out_counts);
+}
+
+int nm_search_filtered(nm_index *idx, const float *queries, uint32_t nq, uint32_t k, int metric,
+                       const nm_filter_op *program, uint32_t n_ops, const uint32_t *tables,
+                       uint32_t n_table_words, uint64_t *out_rows, float *out_scores,
+                       uint32_t *out_counts) {
+    int rc = validate_filter_program(program, n_ops, tables, n_table_words);
+    if (rc) return rc;
+    MaskSpec spec;
+    spec.prog = program;
+    spec.n_ops = n_ops;
+    spec.tables = tables;
+    spec.n_table_words = n_table_words;
+    return search_impl(idx, queries, nq, k, metric, spec, out_rows, out_scores, out_counts);
 }
 
 int nm_search_device(nm_index *idx, const float *d_queries, uint32_t nq, uint32_t k, int metric,

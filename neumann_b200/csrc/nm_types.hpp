@@ -46,6 +46,23 @@ struct alignas(16) RowMeta {
     uint32_t flags;   // bit 0: row has a non-finite element
 };
 
+// ---- device-side metadata filter (filter_kernels.cuh) ----
+enum FilterKind : uint8_t {
+    kFilterTrue = 0, kFilterFalse = 1, kFilterAnd = 2, kFilterOr = 3, kFilterExists = 4,
+    kFilterCmp = 5, kFilterStrTable = 6
+};
+enum FilterCmp : uint8_t { kFilterEq = 0, kFilterNe, kFilterLt, kFilterLe, kFilterGt, kFilterGe };
+enum ValueTag : uint8_t { kTagMissing = 0, kTagNull, kTagBool, kTagInt, kTagFloat, kTagString };
+constexpr uint32_t kFilterMaxOps = 128;
+struct FilterOpDev {         // one postfix op with this shard's column pointers resolved
+    const uint8_t *tags;     // null = the shard has no such column: every row is "missing"
+    const uint64_t *vals;
+    const uint32_t *table;   // kFilterStrTable: bit c = the predicate holds for dictionary code c
+    uint64_t lit;            // kFilterCmp: i64 / f64 bits / bool
+    uint32_t table_bits;
+    uint8_t kind, cmp, lit_tag, pad;
+};
+
 constexpr uint32_t kTcTileRows = 128;  // corpus rows per tensor-core tile (tc_prefilter_kernels.cuh)
 
 constexpr uint32_t kKeptCap = 1u << 20;  // kept (row, ub) entries per query before fallback

@@ -124,6 +124,17 @@ struct VectorEngine::Bucket {
     nm_index *mirror = nullptr;     // device mirror, created at the first search
     uint64_t synced_rows = 0;       // rows [0, synced_rows) are on the device
     std::mutex sync_mu;             // serialises lazy appends issued by concurrent searches
+    // Columnar copy of `meta` on the device (nm_index_column_set): one column per field name,
+    // strings dictionary-encoded per column.  Filled lazily by the first pre-filtered search and
+    // kept up to date incrementally; filters are then evaluated on the device.
+    struct ColumnInfo {
+        uint32_t id = 0;
+        std::unordered_map<std::string, uint32_t> dict;
+        std::vector<std::string> strings;
+    };
+    std::unordered_map<std::string, ColumnInfo> columns;
+    uint64_t cols_synced_rows = 0;      // rows [0, cols_synced_rows) have their columns on the device
+    std::vector<uint64_t> meta_dirty;   // ... except these (metadata replaced / row moved since)
     ~Bucket() {
         if (mirror) nm_index_destroy(mirror);
     }
@@ -185,6 +196,7 @@ Result<Unit> VectorEngine::store_in_space(Space &sp, const std::string &key,
         std::memcpy(&b.rows[row * dim], vector.data(), (size_t)dim * 4);
         // store.put replaces the whole TensorData: metadata of the old value is gone
         b.meta[row] = metadata ? *metadata : Metadata{};
+        if (row < b.cols_synced_rows) b.meta_dirty.push_back(row);
         if (b.mirror && row < b.synced_rows) {
             int rc = nm_index_update(b.mirror, row, vector.data());
             if (rc) return storage_from_nm(rc);
@@ -219,6 +231,10 @@ Result<Unit> VectorEngine::delete_in_space(Space &sp, const std::string &key) {
         int rc = nm_index_swap_remove(b.mirror, row, &moved);
         if (rc) return storage_from_nm(rc);
         b.synced_rows -= 1;
+        // the device moved the last row's column entries along; they are only right if that row's
+        // columns had been pushed already — re-push the slot at the next filtered search
+        if (row < b.cols_synced_rows && row != last) b.meta_dirty.push_back(row);
+        b.cols_synced_rows = std::min(b.cols_synced_rows, b.synced_rows);
     }
     if (row != last) {
         std::memcpy(&b.rows[row * dim], &b.rows[last * dim], (size_t)dim * 4);
@@ -244,6 +260,174 @@ Result<std::vector<float>> VectorEngine::get_in_space(const Space &sp,
     return std::vector<float>(p, p + b.dim);
 }
 
+// ---- device-side filters: columnar metadata + FilterCondition -> postfix program ----------
+namespace {
+
+// compare_tensor_value_to_filter restricted to two strings (lib.rs:3658-3684)
+bool string_cmp_holds(const std::string &a, const std::string &b, FilterCondition::Op op) {
+    const int c = a.compare(b);
+    switch (op) {
+    case FilterCondition::Op::Eq: return c == 0;
+    case FilterCondition::Op::Ne: return c != 0;
+    case FilterCondition::Op::Lt: return c < 0;
+    case FilterCondition::Op::Le: return c <= 0;
+    case FilterCondition::Op::Gt: return c > 0;
+    default: return c >= 0;
+    }
+}
+
+struct FilterProgram {
+    std::vector<nm_filter_op> ops;
+    std::vector<uint32_t> tables;
+    bool ok = true;  // false: too large for the device evaluator
+    void push(nm_filter_op op) { ops.push_back(op); }
+    void constant(bool v) {
+        nm_filter_op op{};
+        op.kind = v ? NM_F_TRUE : NM_F_FALSE;
+        push(op);
+    }
+};
+
+// Appends the postfix code of `f`.  Everything that needs the bytes of a string is evaluated
+// here once per DISTINCT string of the column into a bit table.
+template <class BucketT>
+void compile_filter(const BucketT &b, const FilterCondition &f, FilterProgram &out) {
+    using Op = FilterCondition::Op;
+    using T = MetadataValue::Type;
+    if (f.op == Op::True) return out.constant(true);
+    if (f.op == Op::And || f.op == Op::Or) {
+        compile_filter(b, *f.lhs, out);
+        compile_filter(b, *f.rhs, out);
+        nm_filter_op op{};
+        op.kind = f.op == Op::And ? NM_F_AND : NM_F_OR;
+        return out.push(op);
+    }
+    auto cit = b.columns.find(f.field);
+    if (cit == b.columns.end()) return out.constant(false);  // no row has the field
+    const auto &col = cit->second;
+    auto table_leaf = [&](auto pred) {
+        nm_filter_op op{};
+        op.kind = NM_F_STR_TABLE;
+        op.column = col.id;
+        op.table_off = (uint32_t)out.tables.size();
+        op.table_bits = (uint32_t)col.strings.size();
+        out.tables.resize(out.tables.size() + (col.strings.size() + 31) / 32, 0u);
+        for (size_t c = 0; c < col.strings.size(); ++c)
+            if (pred(col.strings[c])) out.tables[op.table_off + c / 32] |= 1u << (c % 32);
+        out.push(op);
+    };
+    auto cmp_leaf = [&](const FilterValue &v, Op o) {
+        if (v.type == T::String) return table_leaf([&](const std::string &s) { return string_cmp_holds(s, v.s, o); });
+        nm_filter_op op{};
+        op.kind = NM_F_CMP;
+        op.column = col.id;
+        op.cmp = o == Op::Eq ? NM_C_EQ : o == Op::Ne ? NM_C_NE : o == Op::Lt ? NM_C_LT
+                 : o == Op::Le ? NM_C_LE : o == Op::Gt ? NM_C_GT : NM_C_GE;
+        switch (v.type) {
+        case T::Null: op.lit_tag = NM_V_NULL; break;
+        case T::Bool: op.lit_tag = NM_V_BOOL; op.lit = v.b ? 1 : 0; break;
+        case T::Int: op.lit_tag = NM_V_INT; op.lit = (uint64_t)v.i; break;
+        default: op.lit_tag = NM_V_FLOAT; std::memcpy(&op.lit, &v.f, 8); break;
+        }
+        out.push(op);
+    };
+    switch (f.op) {
+    case Op::Exists: {
+        nm_filter_op op{};
+        op.kind = NM_F_EXISTS;
+        op.column = col.id;
+        return out.push(op);
+    }
+    case Op::Contains:
+        return table_leaf([&](const std::string &s) { return s.find(f.value.s) != std::string::npos; });
+    case Op::StartsWith:
+        return table_leaf([&](const std::string &s) { return s.compare(0, f.value.s.size(), f.value.s) == 0; });
+    case Op::In: {
+        if (f.values.empty()) return out.constant(false);
+        size_t pushed = 0;
+        bool any_string = false;
+        for (auto &v : f.values) any_string |= v.type == T::String;
+        if (any_string) {
+            table_leaf([&](const std::string &s) {
+                for (auto &v : f.values)
+                    if (v.type == T::String && v.s == s) return true;
+                return false;
+            });
+            ++pushed;
+        }
+        for (auto &v : f.values) {
+            if (v.type == T::String) continue;
+            cmp_leaf(v, Op::Eq);
+            if (++pushed > 1) {
+                nm_filter_op op{};
+                op.kind = NM_F_OR;
+                out.push(op);
+            }
+        }
+        return;
+    }
+    default: return cmp_leaf(f.value, f.op);
+    }
+}
+
+// Push the column entries of rows [first, first + n) to the device: one pass over the rows'
+// metadata maps per 1M-row chunk, one nm_index_column_set per column that occurs in the chunk.
+template <class BucketT>
+int push_columns(BucketT &b, uint64_t first, uint64_t n) {
+    const bool repush = first < b.cols_synced_rows;  // overwrite: absent fields must become "missing"
+    constexpr uint64_t kChunk = 1u << 20;
+    struct Staged {
+        std::vector<uint8_t> tags;
+        std::vector<uint64_t> vals;
+    };
+    for (uint64_t c0 = first; c0 < first + n; c0 += kChunk) {
+        const uint64_t m = std::min(kChunk, first + n - c0);
+        std::unordered_map<uint32_t, Staged> staged;
+        if (repush)
+            for (auto &ckv : b.columns) {
+                Staged &st = staged[ckv.second.id];
+                st.tags.assign(m, NM_V_MISSING);
+                st.vals.assign(m, 0);
+            }
+        for (uint64_t i = 0; i < m; ++i)
+            for (auto &kv : b.meta[c0 + i]) {
+                auto ins = b.columns.try_emplace(kv.first);
+                auto &col = ins.first->second;
+                if (ins.second) col.id = (uint32_t)b.columns.size();  // ids 1, 2, ...
+                Staged &st = staged[col.id];
+                if (st.tags.empty()) {
+                    st.tags.assign(m, NM_V_MISSING);
+                    st.vals.assign(m, 0);
+                }
+                const MetadataValue &v = kv.second;
+                switch (v.type) {
+                case MetadataValue::Type::Null: st.tags[i] = NM_V_NULL; break;
+                case MetadataValue::Type::Bool: st.tags[i] = NM_V_BOOL; st.vals[i] = v.b ? 1 : 0; break;
+                case MetadataValue::Type::Int: st.tags[i] = NM_V_INT; st.vals[i] = (uint64_t)v.i; break;
+                case MetadataValue::Type::Float:
+                    st.tags[i] = NM_V_FLOAT;
+                    std::memcpy(&st.vals[i], &v.f, 8);
+                    break;
+                case MetadataValue::Type::String: {
+                    auto d = col.dict.try_emplace(v.s, (uint32_t)col.strings.size());
+                    if (d.second) col.strings.push_back(v.s);
+                    st.tags[i] = NM_V_STRING;
+                    st.vals[i] = d.first->second;
+                    break;
+                }
+                }
+            }
+        for (auto &kv : staged) {
+            int rc = nm_index_column_set(b.mirror, kv.first, c0, m, kv.second.tags.data(),
+                                         kv.second.vals.data());
+            if (rc) return rc;
+        }
+    }
+    return 0;
+}
+
+}  // namespace
+
 // The seam of SURVEY 8b: "store.scan -> search_* -> sort_by -> truncate" becomes one nm_search.
 Result<std::vector<SearchResult>> VectorEngine::scan_space(
     const Space &sp, const std::vector<float> &query, size_t top_k, DistanceMetric metric,
@@ -267,19 +451,12 @@ Result<std::vector<SearchResult>> VectorEngine::scan_space(
     if (bit == sp.buckets.end() || bit->second->keys.empty())
         return std::vector<SearchResult>{};  // rows of other dimensions are skipped
     Bucket &b = *bit->second;
-    // "filter first, then search the subset" (lib.rs:3514-3557): the subset is a row bitmask;
-    // an empty subset never reaches the device
+    // "filter first, then search the subset" (lib.rs:3514-3557): the filter is compiled to a
+    // postfix program and evaluated ON THE DEVICE over the columnar copy of the metadata
+    // (nm_search_filtered); only a program too large for the device evaluator falls back to a
+    // host-built bitmask.
+    FilterProgram prog;
     std::vector<uint64_t> mask;
-    if (pre_filter) {
-        mask.assign((b.keys.size() + 63) / 64, 0ull);
-        size_t eligible = 0;
-        for (size_t r = 0; r < b.keys.size(); ++r)
-            if (evaluate_filter(b.meta[r], *pre_filter)) {
-                mask[r >> 6] |= 1ull << (r & 63);
-                ++eligible;
-            }
-        if (eligible == 0) return std::vector<SearchResult>{};
-    }
     {
         std::lock_guard<std::mutex> sg(b.sync_mu);
         if (!b.mirror) {
@@ -297,6 +474,37 @@ Result<std::vector<SearchResult>> VectorEngine::scan_space(
             if (rc) return storage_from_nm(rc);
             b.synced_rows = b.keys.size();
         }
+        if (pre_filter) {
+            // metadata columns: rows not pushed yet, then rows whose metadata changed since
+            int rc = push_columns(b, b.cols_synced_rows, b.keys.size() - b.cols_synced_rows);
+            if (rc) return storage_from_nm(rc);
+            std::sort(b.meta_dirty.begin(), b.meta_dirty.end());
+            b.meta_dirty.erase(std::unique(b.meta_dirty.begin(), b.meta_dirty.end()), b.meta_dirty.end());
+            for (uint64_t r : b.meta_dirty)
+                if (r < b.cols_synced_rows) {
+                    rc = push_columns(b, r, 1);
+                    if (rc) return storage_from_nm(rc);
+                }
+            b.meta_dirty.clear();
+            b.cols_synced_rows = b.keys.size();
+            compile_filter(b, *pre_filter, prog);
+            int depth = 0, max_depth = 0;
+            for (auto &op : prog.ops) {
+                depth += (op.kind == NM_F_AND || op.kind == NM_F_OR) ? -1 : 1;
+                max_depth = std::max(max_depth, depth);
+            }
+            prog.ok = prog.ops.size() <= 128 && max_depth <= 64;
+        }
+    }
+    if (pre_filter && !prog.ok) {
+        mask.assign((b.keys.size() + 63) / 64, 0ull);
+        size_t eligible = 0;
+        for (size_t r = 0; r < b.keys.size(); ++r)
+            if (evaluate_filter(b.meta[r], *pre_filter)) {
+                mask[r >> 6] |= 1ull << (r & 63);
+                ++eligible;
+            }
+        if (eligible == 0) return std::vector<SearchResult>{};
     }
     // The device path serves k <= NM_TOPK_FAST_MAX per call; clamp to the row count first
     // (truncate(top_k) on fewer rows returns them all, lib.rs:2034).
@@ -305,7 +513,11 @@ Result<std::vector<SearchResult>> VectorEngine::scan_space(
     std::vector<float> scores(k);
     uint32_t count = 0;
     int rc;
-    if (pre_filter) {
+    if (pre_filter && prog.ok) {
+        rc = nm_search_filtered(b.mirror, query.data(), 1, (uint32_t)k, (int)metric, prog.ops.data(),
+                                (uint32_t)prog.ops.size(), prog.tables.empty() ? nullptr : prog.tables.data(),
+                                (uint32_t)prog.tables.size(), rows.data(), scores.data(), &count);
+    } else if (pre_filter) {
         rc = nm_search_masked(b.mirror, query.data(), 1, (uint32_t)k, (int)metric, mask.data(),
                               rows.data(), scores.data(), &count);
     } else {

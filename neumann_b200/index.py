@@ -137,6 +137,48 @@ class DeviceIndex:
                                           counts.ctypes.data))
         return [(rows[i, :counts[i]].copy(), scores[i, :counts[i]].copy()) for i in range(nq)]
 
+    # ---- metadata columns + device-side filters (include/neumann_b200.h) ----
+    def column_set(self, column: int, first_row: int, tags, values) -> None:
+        t = np.ascontiguousarray(tags, dtype=np.uint8)
+        v = np.ascontiguousarray(values, dtype=np.uint64)
+        assert t.shape == v.shape and t.ndim == 1
+        check(_ffi.lib().nm_index_column_set(self._h, column, first_row, t.size, t.ctypes.data,
+                                             v.ctypes.data))
+
+    @staticmethod
+    def _program(ops, tables):
+        arr = (_ffi.NmFilterOp * len(ops))(*ops)
+        tab = np.ascontiguousarray(tables if tables is not None else np.zeros(0), dtype=np.uint32)
+        return arr, tab
+
+    def search_filtered(self, queries: np.ndarray, k: int, metric, ops, tables=None):
+        """ops: list of _ffi.NmFilterOp in postfix order; tables: uint32 words.  -> like search()."""
+        q = np.ascontiguousarray(queries, dtype=np.float32)
+        if q.ndim == 1:
+            q = q.reshape(1, -1)
+        nq = q.shape[0]
+        arr, tab = self._program(ops, tables)
+        kk = max(int(k), 1)
+        rows = np.zeros((nq, kk), np.uint64)
+        scores = np.zeros((nq, kk), np.float32)
+        counts = np.zeros(nq, np.uint32)
+        check(_ffi.lib().nm_search_filtered(self._h, q.ctypes.data, nq, int(k), _metric(metric), arr,
+                                            len(ops), tab.ctypes.data if tab.size else None, tab.size,
+                                            rows.ctypes.data, scores.ctypes.data, counts.ctypes.data))
+        return [(rows[i, :counts[i]].copy(), scores[i, :counts[i]].copy()) for i in range(nq)]
+
+    def filter_mask(self, ops, tables=None) -> np.ndarray:
+        """Evaluate a filter program on the device: bool array over this process's rows."""
+        arr, tab = self._program(ops, tables)
+        n = self.rows
+        words = np.zeros((n + 63) // 64 + 1, np.uint64)
+        elig = C.c_uint64()
+        check(_ffi.lib().nm_index_filter_mask(self._h, arr, len(ops), tab.ctypes.data if tab.size else None,
+                                              tab.size, words.ctypes.data, C.byref(elig)))
+        bits = np.unpackbits(words.view(np.uint8), bitorder="little")[:n].astype(bool)
+        assert int(bits.sum()) == int(elig.value)
+        return bits
+
     def search_device(self, d_queries_ptr: int, nq: int, k: int, metric, d_rows_ptr: int,
                       d_scores_ptr: int, d_counts_ptr: int, stream_ptr: int = 0) -> None:
         check(_ffi.lib().nm_search_device(self._h, d_queries_ptr, nq, k, _metric(metric),

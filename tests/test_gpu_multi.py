@@ -88,7 +88,7 @@ def test_two_device_mutations_keep_row_ids_dense():
 
 
 def test_two_device_appends_are_rebalanced():
-    """Appends land on the last shard; once it holds more than twice its share the rows are re-split
+    """Appends land on the last shard; once it holds more than 1.5x its share the rows are re-split
     into equal contiguous ranges.  Global row ids (== the caller's key table) never change."""
     _need(2)
     d, n0, step = 48, 10_000, 9_000
@@ -101,7 +101,7 @@ def test_two_device_appends_are_rebalanced():
         idx.append(rows[n:n + step])
         n += step
         sizes = [idx.shard_info(s).rows for s in range(2)]
-        assert sum(sizes) == n and max(sizes) <= 2 * ((n + 1) // 2) + 4096
+        assert sum(sizes) == n and max(sizes) <= 1.5 * ((n + 1) // 2) + 4096
         assert idx.shard_info(1).row_base == sizes[0]
         ((r, s),) = idx.search(q, 25, "cosine")
         er, es = o.search(rows[:n], q, 25, "cosine", threads=4)
@@ -112,6 +112,92 @@ def test_two_device_appends_are_rebalanced():
     for g in probe:
         assert np.array_equal(idx.get_row(g), rows[g])
     idx.close()
+
+
+def test_two_device_filtered_and_masked_search():
+    """Filtered (device-evaluated program) and masked (host bitmask) searches on an in-process
+    two-device index: each shard evaluates / takes its own slice; results equal the oracle on the
+    eligible subset, with global row ids."""
+    _need(2)
+    from neumann_b200._ffi import NM_C_LT, NM_F_CMP, NM_V_INT, NmFilterOp
+    n, d, k = 50_003, 40, 9
+    rows = o.fill_synthetic(n, d, 0x5EED0001)
+    idx = DeviceIndex(d, devices=[0, 1])
+    idx.load(rows)
+    bucket = (np.arange(n) * 7919 % 101).astype(np.uint64)
+    idx.column_set(3, 0, np.full(n, 3, np.uint8), bucket)            # NM_V_INT
+    prog = [NmFilterOp(kind=NM_F_CMP, cmp=NM_C_LT, lit_tag=NM_V_INT, column=3, lit=4)]
+    keep = bucket < 4
+    assert np.array_equal(idx.filter_mask(prog), keep)
+    sub = np.nonzero(keep)[0]
+    qs = o.fill_synthetic(2, d, 3)
+    for metric in ("cosine", "euclidean"):
+        res = idx.search_filtered(qs, k, metric, prog)
+        resm = idx.search_masked(qs, k, metric, keep)
+        for i in range(2):
+            er, es = o.search(rows[sub], qs[i], k, metric, threads=4)
+            want = sub[er.astype(np.int64)].astype(np.uint64)
+            for got in (res[i], resm[i]):
+                assert np.array_equal(got[0], want), (metric, i)
+                assert np.array_equal(got[1].view(np.uint32), es.view(np.uint32))
+    # rows move between the shards when they are re-split: the columns follow
+    idx.append(np.tile(rows[:1], (60_000, 1)))
+    sizes = [idx.shard_info(s).rows for s in range(2)]
+    assert abs(sizes[0] - sizes[1]) <= 1
+    m = idx.filter_mask(prog)
+    assert np.array_equal(m[:n], keep) and not m[n:].any()
+    idx.close()
+
+
+def _filtered_collective_worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+    from neumann_b200 import dist as nd
+    from neumann_b200._ffi import NM_C_GE, NM_F_CMP, NM_V_INT, NmFilterOp
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank),
+                      WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        n, d, k = 120_001, 64, 10
+        idx = DeviceIndex(d, devices=[rank])
+        lo, hi = nd.attach_index(idx, n)
+        idx.fill_synthetic(hi - lo, 0x5EED0001, row_offset=lo)
+        rows = o.fill_synthetic(n, d, 0x5EED0001)
+        bucket = (np.arange(n) * 31 % 53).astype(np.uint64)
+        idx.column_set(1, 0, np.full(hi - lo, 3, np.uint8), bucket[lo:hi])   # this rank's rows
+        prog = [NmFilterOp(kind=NM_F_CMP, cmp=NM_C_GE, lit_tag=NM_V_INT, column=1, lit=50)]
+        keep = bucket >= 50
+        sub = np.nonzero(keep)[0]
+        qs = o.fill_synthetic(3, d, 0x5EED1001)
+        for metric in ("cosine", "dot"):
+            res = idx.search_filtered(qs, k, metric, prog)            # fused exchange, masked
+            resm = idx.search_masked(qs, k, metric, keep[lo:hi])      # local slice of the mask
+            for i in range(3):
+                er, es = o.search(rows[sub], qs[i], k, metric, threads=4)
+                want = sub[er.astype(np.int64)].astype(np.uint64)
+                for got in (res[i], resm[i]):
+                    assert np.array_equal(got[0], want), (metric, i, got[0], want)
+                    assert np.array_equal(got[1].view(np.uint32), es.view(np.uint32))
+        idx.detach_comm()
+        idx.close()
+        q.put((rank, "ok"))
+    except Exception:  # noqa: BLE001
+        import traceback
+        q.put((rank, traceback.format_exc()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_collective_filtered_and_masked_search():
+    _need(2)
+    _spawn(_filtered_collective_worker, 2)
+
+
+def test_collective_filtered_search_nccl_fallback(monkeypatch):
+    _need(2)
+    monkeypatch.setenv("NM_DISABLE_PEER_EXCHANGE", "1")
+    _spawn(_filtered_collective_worker, 2)
 
 
 def _free_port():
