@@ -910,6 +910,45 @@ def run_ours(a):
         except Exception as e:  # noqa: BLE001
             line["prefilter_int8"] = {"error": repr(e)}
 
+    # ---- filtered SIMILAR (search_with_pre_filter, lib.rs:3514-3557): the filter is evaluated on
+    #      the device over a metadata column, the scan applies the row mask (extra, N=1) ----
+    if world == 1 and not a.no_configs:
+        try:
+            from neumann_b200._ffi import NM_C_LT, NM_F_CMP, NM_V_INT, NmFilterOp
+            bucket = (np.arange(local_rows, dtype=np.uint64) * np.uint64(2654435761)) % np.uint64(100)
+            t0 = time.perf_counter()
+            idx.column_set(1, 0, np.full(local_rows, NM_V_INT, np.uint8), bucket)
+            t_cols = time.perf_counter() - t0
+            filt = {"column_upload_s": t_cols, "e2e_unfiltered_value": e2e_qps,
+                    "note": "nm_search_filtered through the C ABI with host buffers; `first` = first call "
+                            "with a new filter (device mask kernel + scan), `cached` = the same filter again "
+                            "(mask reused until the next mutation); 256-row blocks without an eligible row "
+                            "are not read, so selective filters stream less than the corpus"}
+            q_np = q_host.numpy()
+            for name, lim in (("sel_50pct", 50), ("sel_1pct", 1)):
+                prog = [NmFilterOp(kind=NM_F_CMP, cmp=NM_C_LT, lit_tag=NM_V_INT, column=1, lit=lim)]
+                t_first = []
+                for rep in range(3):
+                    idx.column_set(1, 0, np.full(1, NM_V_INT, np.uint8), bucket[:1])   # invalidates the mask cache
+                    t0 = time.perf_counter()
+                    got = idx.search_filtered(q_np[rep], k, a.metric, prog)
+                    t_first.append(time.perf_counter() - t0)
+                ts = []
+                for i in range(a.steps):
+                    t0 = time.perf_counter()
+                    got = idx.search_filtered(q_np[i % nq], k, a.metric, prog)
+                    ts.append(time.perf_counter() - t0)
+                t_c = float(np.mean(ts))
+                keep = np.nonzero(bucket < lim)[0]
+                filt[name] = {"eligible_rows": int(keep.size),
+                              "first_call_ms": sorted(t_first)[1] * 1e3, "cached_ms": t_c * 1e3,
+                              "first_call_vs_unfiltered_e2e": sorted(t_first)[1] * e2e_qps,
+                              "cached_vs_unfiltered_e2e": t_c * e2e_qps,
+                              "all_hits_eligible": bool(np.all(bucket[got[0][0].astype(np.int64)] < lim))}
+            line["filtered"] = filt
+        except Exception as e:  # noqa: BLE001
+            line["filtered"] = {"error": repr(e)}
+
     # ---- cpu_baseline (N=1): the oracle pass of the parity check IS a full-corpus measurement ----
     if world == 1 and not a.no_cpu_baseline and parity is not None:
         t_q = parity["oracle_search_s"] / parity["queries"]
