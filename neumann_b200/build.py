@@ -7,6 +7,7 @@ parts).  The built .so stays in-tree (git-ignored) so it travels to the GPU box.
 """
 from __future__ import annotations
 
+import hashlib
 import os
 import subprocess
 import sys
@@ -34,17 +35,35 @@ def sources() -> list[Path]:
     return sorted(CSRC.glob("*.cu")) + sorted(CSRC.glob("*.cpp"))
 
 
-def _stale(target: Path, deps: list[Path]) -> bool:
-    if not target.exists():
-        return True
-    t = target.stat().st_mtime
-    return any(d.stat().st_mtime > t for d in deps)
+def _content_hash(deps: list[Path], flags: list[str]) -> str:
+    """sha256 over the build recipe and every source byte: the .so is git-ignored but ships to the
+    GPU box, so "is it current" must not depend on mtimes (a checkout resets them)."""
+    h = hashlib.sha256()
+    h.update("\0".join(flags).encode())
+    for d in sorted(deps):
+        h.update(str(d.relative_to(ROOT)).encode() + b"\0")
+        h.update(d.read_bytes())
+        h.update(b"\0")
+    return h.hexdigest()
+
+
+def _stale(target: Path, digest: str) -> bool:
+    side = target.with_name(target.name + ".srchash")
+    return not target.exists() or not side.exists() or side.read_text().strip() != digest
+
+
+def library_deps() -> list[Path]:
+    return sources() + sorted(CSRC.glob("*.cuh")) + sorted(CSRC.glob("*.hpp")) + \
+        sorted((ROOT / "include").glob("*.h"))
+
+
+def library_is_current() -> bool:
+    return not _stale(LIB, _content_hash(library_deps(), NVCC_FLAGS))
 
 
 def build_library(force: bool = False, verbose: bool = False) -> Path:
-    deps = sources() + sorted(CSRC.glob("*.cuh")) + sorted(CSRC.glob("*.hpp")) + \
-        sorted((ROOT / "include").glob("*.h")) + [Path(__file__)]
-    if not force and not _stale(LIB, deps):
+    digest = _content_hash(library_deps(), NVCC_FLAGS)
+    if not force and not _stale(LIB, digest):
         return LIB
     cmd = [NVCC, *NVCC_FLAGS, "-I", str(ROOT / "include"), "-o", str(LIB),
            *[str(s) for s in sources()], "-ldl", "-lpthread"]
@@ -56,6 +75,7 @@ def build_library(force: bool = False, verbose: bool = False) -> Path:
         sys.stderr.write(r.stdout + r.stderr)
     if r.returncode != 0:
         raise RuntimeError("nvcc failed building libneumann_b200.so")
+    LIB.with_name(LIB.name + ".srchash").write_text(digest + "\n")
     return LIB
 
 
@@ -63,8 +83,10 @@ def build_oracle(force: bool = False) -> Path:
     """Test infrastructure only (see oracle/nm_oracle.c)."""
     odir = ROOT / "oracle"
     lib = odir / "libnm_oracle.so"
-    if force or _stale(lib, [odir / "nm_oracle.c", odir / "Makefile"]):
+    digest = _content_hash([odir / "nm_oracle.c", odir / "Makefile"], [])
+    if force or _stale(lib, digest):
         subprocess.run(["make", "-C", str(odir), "-B"], check=True, capture_output=True)
+        lib.with_name(lib.name + ".srchash").write_text(digest + "\n")
     return lib
 
 

@@ -831,14 +831,18 @@ int scan_queries(nm_index *idx, const Shard &sh, Workspace &ws, const float *d_q
 int launch_merge_shards(nm_index *idx, const nm::ShardHit *d_gather, uint32_t nq, uint32_t k,
                         uint64_t *out_rows, float *out_scores, uint32_t *out_counts,
                         cudaStream_t stream) {
-    const uint32_t total = (uint32_t)idx->n_ranks * k;
-    const uint32_t n_sort = pow2_ceil(total);
+    const uint64_t total = (uint64_t)idx->n_ranks * k;
+    if (total > 4096) {
+        // large gathers (k up to the corpus size): rank-based merge of the sorted shard lists
+        const dim3 grid((uint32_t)((total + nm::kMergeThreads - 1) / nm::kMergeThreads), nq);
+        nm::merge_shards_rank_kernel<<<grid, nm::kMergeThreads, 0, stream>>>(
+            d_gather, (uint32_t)idx->n_ranks, k, nq * k, out_rows, out_scores, out_counts);
+        CUDA_TRY(cudaGetLastError());
+        idx->merge_launches++;
+        return NM_OK;
+    }
+    const uint32_t n_sort = pow2_ceil((uint32_t)total);
     const size_t msmem = (size_t)n_sort * 8;
-    if (msmem > 200 * 1024)
-        return fail(NM_ERR_INVALID_TOP_K, "n_ranks*k = %u too large for the merge kernel", total);
-    if (msmem > 48 * 1024)
-        CUDA_TRY(cudaFuncSetAttribute(nm::merge_shards_kernel,
-                                      cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     nm::merge_shards_kernel<<<nq, nm::kMergeThreads, msmem, stream>>>(
         d_gather, (uint32_t)idx->n_ranks, k, nq * k, n_sort, out_rows, out_scores, out_counts);
     CUDA_TRY(cudaGetLastError());

@@ -494,9 +494,10 @@ static int search_coalesced(nm_index *idx, const float *query, uint32_t k, int m
             continue;
         }
         // become the leader for one round: everything queued with my (k, metric)
-        idx->co_leader = true;
         std::vector<nm_index::PendingSearch *> batch;
         const size_t cap = (size_t)std::max(1, idx->coalesce_max.load());
+        batch.reserve(std::min(cap, idx->co_pending.size()));  // (may throw: not the leader yet)
+        idx->co_leader = true;
         for (auto it = idx->co_pending.begin(); it != idx->co_pending.end() && batch.size() < cap;) {
             if ((*it)->k == me.k && (*it)->metric == me.metric) {
                 batch.push_back(*it);
@@ -509,24 +510,32 @@ static int search_coalesced(nm_index *idx, const float *query, uint32_t k, int m
         const uint32_t nb = (uint32_t)batch.size();
         const uint32_t dim = idx->dim;
         int rc;
-        if (nb == 1) {
-            rc = search_impl(idx, batch[0]->query, 1, k, metric, MaskSpec(), batch[0]->out_rows,
-                             batch[0]->out_scores, batch[0]->out_count);
-        } else {
-            std::vector<float> qs((size_t)nb * dim);
-            std::vector<uint64_t> rows((size_t)nb * k);
-            std::vector<float> scores((size_t)nb * k);
-            std::vector<uint32_t> counts(nb);
-            for (uint32_t i = 0; i < nb; ++i)
-                memcpy(&qs[(size_t)i * dim], batch[i]->query, (size_t)dim * 4);
-            rc = search_impl(idx, qs.data(), nb, k, metric, MaskSpec(), rows.data(), scores.data(),
-                             counts.data());
-            if (rc == NM_OK)
-                for (uint32_t i = 0; i < nb; ++i) {
-                    *batch[i]->out_count = counts[i];
-                    memcpy(batch[i]->out_rows, &rows[(size_t)i * k], (size_t)counts[i] * 8);
-                    memcpy(batch[i]->out_scores, &scores[(size_t)i * k], (size_t)counts[i] * 4);
-                }
+        // nothing may leave this block by exception: co_leader has to be handed back, and the C
+        // ABI never throws (std::bad_alloc from the staging vectors becomes NM_ERR_STORAGE)
+        try {
+            if (nb == 1) {
+                rc = search_impl(idx, batch[0]->query, 1, k, metric, MaskSpec(), batch[0]->out_rows,
+                                 batch[0]->out_scores, batch[0]->out_count);
+            } else {
+                std::vector<float> qs((size_t)nb * dim);
+                std::vector<uint64_t> rows((size_t)nb * k);
+                std::vector<float> scores((size_t)nb * k);
+                std::vector<uint32_t> counts(nb);
+                for (uint32_t i = 0; i < nb; ++i)
+                    memcpy(&qs[(size_t)i * dim], batch[i]->query, (size_t)dim * 4);
+                rc = search_impl(idx, qs.data(), nb, k, metric, MaskSpec(), rows.data(), scores.data(),
+                                 counts.data());
+                if (rc == NM_OK)
+                    for (uint32_t i = 0; i < nb; ++i) {
+                        *batch[i]->out_count = counts[i];
+                        memcpy(batch[i]->out_rows, &rows[(size_t)i * k], (size_t)counts[i] * 8);
+                        memcpy(batch[i]->out_scores, &scores[(size_t)i * k], (size_t)counts[i] * 4);
+                    }
+            }
+        } catch (const std::exception &e) {
+            rc = fail(NM_ERR_STORAGE, "coalesced search failed: %s", e.what());
+        } catch (...) {
+            rc = fail(NM_ERR_STORAGE, "coalesced search failed");
         }
         const std::string err = rc ? std::string(nmi::last_error()) : std::string();
         idx->co_batches++;

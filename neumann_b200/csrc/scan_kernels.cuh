@@ -980,6 +980,58 @@ merge_shards_kernel(const ShardHit *hits, uint32_t n_shards, uint32_t k, uint32_
     }
 }
 
+// The same merge for gathers that do not fit the shared-memory sort (n_shards * k > 4096, e.g.
+// k = 100 000 over 8 shards): every shard list is already sorted, so each hit computes its final
+// rank directly — its position in its own list plus, for every other list, the number of hits
+// that precede it in the total order (binary search; on equal scores the earlier shard wins,
+// which is exactly the stable sort of the concatenation).  No size limit, no scratch.
+__global__ void __launch_bounds__(kMergeThreads)
+merge_shards_rank_kernel(const ShardHit *hits, uint32_t n_shards, uint32_t k, uint32_t hits_stride_q,
+                         uint64_t *out_rows, float *out_scores, uint32_t *out_counts) {
+    const uint32_t q = blockIdx.y;
+    const uint32_t pos = blockIdx.x * kMergeThreads + threadIdx.x;
+    auto list = [&](uint32_t s) { return hits + (uint64_t)s * hits_stride_q + (uint64_t)q * k; };
+    auto valid_count = [&](const ShardHit *l) {  // valid hits come first, empty slots {0,0,0} last
+        uint32_t lo = 0, hi = k;
+        while (lo < hi) {
+            const uint32_t mid = (lo + hi) >> 1;
+            const ShardHit h = l[mid];
+            if (h.ord != 0u || h.score_bits != 0u) lo = mid + 1;
+            else hi = mid;
+        }
+        return lo;
+    };
+    if (pos == 0) {
+        uint64_t total = 0;
+        for (uint32_t s = 0; s < n_shards; ++s) total += valid_count(list(s));
+        out_counts[q] = (uint32_t)(total < k ? total : k);
+    }
+    if (pos >= n_shards * k) return;
+    const uint32_t s = pos / k, i = pos - s * k;
+    const ShardHit h = list(s)[i];
+    if (h.ord == 0u && h.score_bits == 0u) return;
+    uint64_t rank = i;
+    for (uint32_t t = 0; t < n_shards && rank < k; ++t) {
+        if (t == s) continue;
+        const ShardHit *l = list(t);
+        const uint32_t nv = valid_count(l);
+        // hits of list t that precede h: ord > h.ord, or ord == h.ord when t is an earlier shard
+        uint32_t lo = 0, hi = nv;
+        while (lo < hi) {
+            const uint32_t mid = (lo + hi) >> 1;
+            const uint32_t o = l[mid].ord;
+            const bool before = (o > h.ord) || (o == h.ord && t < s);
+            if (before) lo = mid + 1;
+            else hi = mid;
+        }
+        rank += lo;
+    }
+    if (rank < k) {
+        out_rows[(uint64_t)q * k + rank] = h.global_row;
+        out_scores[(uint64_t)q * k + rank] = __uint_as_float(h.score_bits);
+    }
+}
+
 // ---------------------------------------------------------------------------------------
 // synthetic corpus: bit-identical to oracle nmo_fill_synthetic
 // ---------------------------------------------------------------------------------------

@@ -332,7 +332,8 @@ def test_engine_pre_filter_runs_on_the_device_and_matches_the_reference_rules():
     e.store_embedding_with_metadata("k0007", rows[7], metas[7])
     metas[8] = {}
     e.store_embedding("k0008", rows[8])                       # plain store drops the metadata
-    for victim in (5, 1234, n - 1):
+    for victim in (5, 1234, -1):
+        victim = victim % len(keys)                             # -1: the last row itself
         e.delete_embedding(keys[victim])
         last = len(keys) - 1
         keys[victim], vecs[victim], metas[victim] = keys[last], vecs[last], metas[last]

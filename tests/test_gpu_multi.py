@@ -141,7 +141,7 @@ def test_two_device_filtered_and_masked_search():
                 assert np.array_equal(got[0], want), (metric, i)
                 assert np.array_equal(got[1].view(np.uint32), es.view(np.uint32))
     # rows move between the shards when they are re-split: the columns follow
-    idx.append(np.tile(rows[:1], (60_000, 1)))
+    idx.append(np.tile(rows[:1], (90_000, 1)))          # last shard > 1.5x its share -> re-split
     sizes = [idx.shard_info(s).rows for s in range(2)]
     assert abs(sizes[0] - sizes[1]) <= 1
     m = idx.filter_mask(prog)
@@ -255,6 +255,13 @@ def _nccl_worker(rank, world, port, q):
         res = idx.search(qs[:1], 1500, "cosine")
         er, es = o.search(rows, qs[0], 1500, "cosine", threads=4)
         assert np.array_equal(res[0][0], er) and np.array_equal(res[0][1].view(np.uint32), es.view(np.uint32))
+        # gathers too large for the shared-memory sort (ranks x k > 4096): rank-based merge kernel,
+        # two queries at once, with exact ties across the shard boundary
+        res = idx.search(qs[:2], 5000, "dot")
+        for i in range(2):
+            er, es = o.search(rows, qs[i], 5000, "dot", threads=4)
+            assert np.array_equal(res[i][0], er), ("rank merge", i)
+            assert np.array_equal(res[i][1].view(np.uint32), es.view(np.uint32))
         idx.detach_comm()
         idx.close()
         q.put((rank, "ok"))
