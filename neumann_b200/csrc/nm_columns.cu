@@ -3,6 +3,7 @@
 // metadata map per filtered query (reference: search_with_pre_filter,
 // vector_engine/src/lib.rs:3514-3557 collects the matching keys first; evaluate_filter :3592).
 #include "nm_internal.hpp"
+#include "nm_trace.hpp"
 
 using namespace nmi;
 
@@ -304,6 +305,7 @@ extern "C" {
 
 int nm_index_column_set(nm_index *idx, uint32_t column, uint64_t first_row, uint64_t n,
                         const uint8_t *tags, const uint64_t *values) {
+    NM_TRACE("nm_index_column_set");
     if (!idx) return fail(NM_ERR_INVALID_ARGUMENT, "null index");
     if (n == 0) return NM_OK;
     if (!tags || !values) return fail(NM_ERR_INVALID_ARGUMENT, "null column data");

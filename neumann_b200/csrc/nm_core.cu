@@ -3,6 +3,7 @@
 // int8 copy, statistics.  Row-major f32, pitch = dim rounded up to 4 floats so every row is
 // 16-byte aligned for TMA.  There is deliberately no CPU code path for the scan.
 #include "nm_internal.hpp"
+#include "nm_trace.hpp"
 
 #include <cstdarg>
 #include <cstdio>
@@ -140,6 +141,8 @@ int encode_tmap_u8(CUtensorMap *out, void *base, uint64_t inner, uint64_t rows, 
 // after the f32 mirror holds the new data).  No-op while the pre-filter is off.
 int q8_refresh(nm_index *idx, Shard &sh, uint64_t first, uint64_t n, bool build) {
     const int mode = idx->prefilter.load();
+    if (mode == 0) return NM_OK;
+    NM_TRACE("q8_refresh");
     if (mode == 0) return NM_OK;
     if (mode == 2 && !build && !sh.d_q8) return NM_OK;  // auto: nothing to keep up to date yet
     const uint32_t pitch8 = q8_pitch(idx->dim);
@@ -392,6 +395,7 @@ int nm_index_clear(nm_index *idx) {
 }
 
 int nm_index_load(nm_index *idx, const float *rows, uint64_t n) {
+    NM_TRACE("nm_index_load");
     if (!idx) return fail(NM_ERR_INVALID_ARGUMENT, "null index");
     if (n && !rows) return fail(NM_ERR_INVALID_ARGUMENT, "null rows");
     std::unique_lock<std::shared_mutex> g(idx->mu);
@@ -523,6 +527,7 @@ static int rebalance_shards(nm_index *idx, bool force) {
 }
 
 int nm_index_append(nm_index *idx, const float *rows, uint64_t n) {
+    NM_TRACE("nm_index_append");
     if (!idx) return fail(NM_ERR_INVALID_ARGUMENT, "null index");
     if (n == 0) return NM_OK;
     if (!rows) return fail(NM_ERR_INVALID_ARGUMENT, "null rows");
@@ -558,6 +563,7 @@ static int locate_row(nm_index *idx, uint64_t row, Shard **out, uint64_t *local)
 }
 
 int nm_index_update(nm_index *idx, uint64_t row, const float *vec) {
+    NM_TRACE("nm_index_update");
     if (!idx || !vec) return fail(NM_ERR_INVALID_ARGUMENT, "null argument");
     std::unique_lock<std::shared_mutex> g(idx->mu);
     if (int wrc = wait_async_searches(idx)) return wrc;  // never tear an in-flight async scan
@@ -572,6 +578,7 @@ int nm_index_update(nm_index *idx, uint64_t row, const float *vec) {
 }
 
 int nm_index_swap_remove(nm_index *idx, uint64_t row, uint64_t *moved_from) {
+    NM_TRACE("nm_index_swap_remove");
     if (!idx) return fail(NM_ERR_INVALID_ARGUMENT, "null index");
     std::unique_lock<std::shared_mutex> g(idx->mu);
     if (int wrc = wait_async_searches(idx)) return wrc;  // never tear an in-flight async scan
@@ -672,6 +679,7 @@ int nm_index_shard_info(nm_index *idx, int shard, nm_shard_info *out) {
 }
 
 int nm_index_fill_synthetic(nm_index *idx, uint64_t n, uint64_t seed, uint64_t row_offset) {
+    NM_TRACE("nm_index_fill_synthetic");
     if (!idx) return fail(NM_ERR_INVALID_ARGUMENT, "null index");
     std::unique_lock<std::shared_mutex> g(idx->mu);
     if (int wrc = wait_async_searches(idx)) return wrc;  // never tear an in-flight async scan

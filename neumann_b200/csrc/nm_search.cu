@@ -2,6 +2,7 @@
 // the single-query scan, the batched kernels, the int8 pre-filter, the fused peer exchange and
 // the NCCL all-gather path, and the host-side merge of in-process multi-device indexes.
 #include "nm_internal.hpp"
+#include "nm_trace.hpp"
 
 #include <cstdlib>
 
@@ -59,6 +60,7 @@ int validate_search(const nm_index *idx, const void *queries, uint32_t nq, uint3
 int download_results(nm_index *idx, const Shard &sh, Workspace &ws, const ResultLayout &l,
                      uint32_t nq, uint32_t k, uint64_t *out_rows, float *out_scores,
                      uint32_t *out_counts) {
+    NM_TRACE("wait_download");
     CUDA_TRY(cudaMemcpyAsync(ws.h_result, ws.d_result, l.total, cudaMemcpyDeviceToHost, ws.stream));
     {
         int wrc = wait_stream(ws.stream);
@@ -137,6 +139,7 @@ static int masked_hits(nm_index *idx, const Shard &sh, Workspace &ws, const floa
 static int search_impl(nm_index *idx, const float *queries, uint32_t nq, uint32_t k, int metric,
                        const MaskSpec &mspec, uint64_t *out_rows, float *out_scores,
                        uint32_t *out_counts) {
+    NM_TRACE(mspec.prog ? "nm_search_filtered" : (mspec.host_mask ? "nm_search_masked" : "nm_search"));
     int rc = validate_search(idx, queries, nq, k, metric, out_rows, out_scores, out_counts);
     if (rc) return rc;
     const bool masked = mspec.any();
@@ -171,15 +174,22 @@ static int search_impl(nm_index *idx, const float *queries, uint32_t nq, uint32_
         rc = ws_ensure(*ws, sh, dim, nq, k, true, true, false, 0);
         if (rc) return rc;
         ResultLayout l = result_layout(nq, k);
-        memcpy(ws->h_query, queries, (size_t)nq * dim * 4);
-        CUDA_TRY(cudaMemcpyAsync(ws->d_query, ws->h_query, (size_t)nq * dim * 4,
-                                 cudaMemcpyHostToDevice, ws->stream));
+        {
+            NM_TRACE("stage_query");
+            memcpy(ws->h_query, queries, (size_t)nq * dim * 4);
+            CUDA_TRY(cudaMemcpyAsync(ws->d_query, ws->h_query, (size_t)nq * dim * 4,
+                                     cudaMemcpyHostToDevice, ws->stream));
+        }
         uint64_t *r_rows = reinterpret_cast<uint64_t *>(ws->d_result + l.rows_off);
         float *r_scores = reinterpret_cast<float *>(ws->d_result + l.scores_off);
         uint32_t *r_counts = reinterpret_cast<uint32_t *>(ws->d_result + l.counts_off);
         const uint32_t *d_mask = nullptr;
-        rc = shard_mask(idx, sh, *ws, mspec, sh.row_base, ws->stream, &d_mask, &mask_holds[0]);
-        if (rc) return rc;
+        if (masked) {
+            NM_TRACE("filter_mask");
+            rc = shard_mask(idx, sh, *ws, mspec, sh.row_base, ws->stream, &d_mask, &mask_holds[0]);
+            if (rc) return rc;
+        }
+        NM_TRACE("scan");
         CUDA_TRY(cudaEventRecord(ws->ev0, ws->stream));
         if (masked) {
             for (uint32_t q = 0; q < nq; ++q) {
@@ -362,6 +372,7 @@ static int search_impl(nm_index *idx, const float *queries, uint32_t nq, uint32_
                 if (rc) return rc;
             }
             CUDA_TRY(cudaEventRecord(ws->ev1, ws->stream));
+            NM_TRACE("exchange_merge");
             NCCL_TRY(nccl().AllGather(ws->d_hits, ws->d_gather,
                                       (size_t)nq * k * sizeof(nm::ShardHit), ncclChar, idx->comm,
                                       ws->stream));
@@ -639,6 +650,7 @@ int nm_search_filtered(nm_index *idx, const float *queries, uint32_t nq, uint32_
 int nm_search_device(nm_index *idx, const float *d_queries, uint32_t nq, uint32_t k, int metric,
                      uint64_t *d_out_rows, float *d_out_scores, uint32_t *d_out_counts,
                      void *stream_v) {
+    NM_TRACE("nm_search_device");
     int rc = validate_search(idx, d_queries, nq, k, metric, d_out_rows, d_out_scores, d_out_counts);
     if (rc) return rc;
     std::shared_lock<std::shared_mutex> g(idx->mu);

@@ -85,8 +85,8 @@ constexpr uint32_t kTcThreads = 32 * (kTcRoleWarps + kTcEpilogueWarps);
 constexpr uint32_t kTcKeptCap = 32768;                     // kept entries per query
 constexpr uint32_t kTcPhase0Rows = 2048;                   // first phase: keep everything (>= k)
 constexpr uint32_t kTcTmemCols = 512;                      // 2 accumulators x 256 columns
-constexpr uint32_t kTcPendCap = 40;                        // parked entries per epilogue warp
-constexpr uint32_t kTcPendDrain = 20;                      // drained once this many are parked
+constexpr uint32_t kTcPendCap = 64;                        // parked entries per epilogue warp
+constexpr uint32_t kTcPendDrain = 24;                      // drained once this many are parked
 
 constexpr uint32_t kTcFlagUnusable = 1u;   // query not finite / zero / denormal scale
 constexpr uint32_t kTcFlagOverflow = 2u;   // kept list overflowed
@@ -126,7 +126,7 @@ using TcQm = TcQueryMeta;
 
 inline size_t tc_gemm_smem_bytes() {
     return 1024 + (size_t)kTcRingBytes + (size_t)kTcMaxQ * 16 + 256 +
-           (size_t)kTcEpilogueWarps * (kTcPendCap * 24 + 4) + (size_t)kTcMaxQ * 48 + 256;
+           (size_t)kTcEpilogueWarps * (kTcPendCap * 12 + 4) + (size_t)kTcMaxQ * 48 + 256;
 }
 
 #ifdef __CUDACC__
@@ -642,13 +642,10 @@ struct TcGemmParams {
 // An entry that passed the screen, parked until the accumulator has been handed back to the MMA
 // issuer: the rigorous evaluation (double precision, a list reservation in global memory) must
 // not sit between the TMEM reads of a tile and the release of its accumulator.
-struct TcPend {
+struct TcPend {         // the row's constants are re-read (L2) when the entry is evaluated
     int I;
-    uint32_t q_flags;   // query | row flags << 16
+    uint32_t q;
     uint32_t row;
-    float scale;
-    uint32_t x1;
-    float rmag;
 };
 // rigorous re-evaluation + append of ONE (row, query) entry that passed the screen.  Called
 // divergently: every lane walks its own hits, so the latencies of the list reservations of a
@@ -886,18 +883,18 @@ tc_gemm_filter_kernel(const __grid_constant__ CUtensorMap tmap_a,
             if (ok) raw = __ldg(reinterpret_cast<const float4 *>(p.meta + r));
             return raw;
         };
-        auto drain = [&]() {  // warp-uniform
+        auto drain = [&]() {  // warp-uniform: one parked entry per lane and round
             __syncwarp();
             const uint32_t n_pend = min(*pcnt, kTcPendCap);
             for (uint32_t e = lane; e < n_pend; e += 32u) {
                 const TcPend pe = pq[e];
+                const float4 raw = __ldg(reinterpret_cast<const float4 *>(p.meta + pe.row));
                 RowMeta rm;
-                rm.scale = pe.scale;
-                rm.x1 = pe.x1;
-                rm.rmag = pe.rmag;
-                rm.flags = pe.q_flags >> 16;
-                const uint32_t qq = pe.q_flags & 0xffffu;
-                tc_keep_entry(p, qm_s, qq, pe.I, pe.row, rm, __float_as_uint(coef_s[qq].w), phase0);
+                rm.scale = raw.x;
+                rm.x1 = __float_as_uint(raw.y);
+                rm.rmag = raw.z;
+                rm.flags = __float_as_uint(raw.w);
+                tc_keep_entry(p, qm_s, pe.q, pe.I, pe.row, rm, __float_as_uint(coef_s[pe.q].w), phase0);
             }
             __syncwarp();
             if (lane == 0) *pcnt = 0u;
@@ -947,45 +944,48 @@ tc_gemm_filter_kernel(const __grid_constant__ CUtensorMap tmap_a,
                 const float rhs_c = fmaf(alpha, cm.x, fmaf(beta, cm.y, cm.z));
                 if (!__any_sync(0xffffffffu, valid && !(lhs_c < rhs_c))) return;
                 // fine: every column against its own threshold
-                bool hit = false;
+                uint32_t mask = 0u;
 #pragma unroll
                 for (uint32_t j = 0; j < 16u; ++j) {
                     const float4 cq = coef_s[c0 + j];
                     const float lhs = __int_as_float((v[j] >> sh) + add_r);
                     const float rhs = fmaf(alpha, cq.x, fmaf(beta, cq.y, cq.z));
-                    hit |= !(lhs < rhs);
+                    if (!(lhs < rhs)) mask |= 1u << j;
                 }
-                if (hit && valid) {  // rare: rigorous evaluation of this lane's hits
-                    uint32_t mask = 0u;
-                    int tmp[16];
-#pragma unroll
-                    for (uint32_t j = 0; j < 16u; ++j) {
-                        const float4 cq = coef_s[c0 + j];
-                        const float lhs = __int_as_float((v[j] >> sh) + add_r);
-                        const float rhs = fmaf(alpha, cq.x, fmaf(beta, cq.y, cq.z));
-                        if (!(lhs < rhs)) mask |= 1u << j;
-                        tmp[j] = v[j];
-                    }
+                {
                     const uint32_t left = p.nq - c0;  // c0 < nq
                     mask &= left >= 16u ? 0xffffu : ((1u << left) - 1u);
-                    while (mask) {
+                    if (!valid) mask = 0u;
+                }
+                // Park the hits.  The reservation is warp-cooperative (one entry per lane and
+                // round, slots handed out by ballot) and a full queue is drained by the WHOLE warp
+                // right here: in the early phases, where a few per cent of all entries pass, the
+                // rigorous evaluation then still runs 32 lanes wide instead of lane by lane.
+                uint32_t any = __ballot_sync(0xffffffffu, mask != 0u);
+                while (any) {
+                    const uint32_t n_new = __popc(any);
+                    uint32_t cnt = *pcnt;
+                    if (cnt + n_new > kTcPendCap) {
+                        drain();
+                        cnt = 0u;
+                    }
+                    if (mask) {
                         const uint32_t j = __ffs(mask) - 1u;
                         mask &= mask - 1u;
-                        const uint32_t slot = atomicAdd(pcnt, 1u);
-                        if (slot < kTcPendCap) {
-                            TcPend e;
-                            e.I = tmp[j];
-                            e.q_flags = (c0 + j) | (m.flags << 16);
-                            e.row = row;
-                            e.scale = m.scale;
-                            e.x1 = m.x1;
-                            e.rmag = m.rmag;
-                            pq[slot] = e;
-                        } else {  // queue full (early phases keep most entries): evaluate now
-                            tc_keep_entry(p, qm_s, c0 + j, tmp[j], row, m,
-                                          __float_as_uint(coef_s[c0 + j].w), phase0);
-                        }
+                        int I = 0;
+#pragma unroll
+                        for (uint32_t jj = 0; jj < 16u; ++jj)
+                            if (jj == j) I = v[jj];
+                        TcPend e;
+                        e.I = I;
+                        e.q = c0 + j;
+                        e.row = row;
+                        pq[cnt + __popc(any & ((1u << lane) - 1u))] = e;
                     }
+                    __syncwarp();
+                    if (lane == 0) *pcnt = cnt + n_new;
+                    __syncwarp();
+                    any = __ballot_sync(0xffffffffu, mask != 0u);
                 }
             };
             if (p.dump) {  // diagnostics only (nm_debug_tc_dots)
@@ -1115,7 +1115,7 @@ __device__ __forceinline__ uint32_t tc_radix_kth(F val, uint32_t n, uint32_t k, 
 // are fetched as 8 independent float4 loads, the next block is in flight while the current one
 // is folded (the rows are scattered, so the loop is bound by HBM latency otherwise); the query
 // comes from shared memory as broadcast float4.  Same element order as scan_topk_kernel.
-template <int METRIC>
+template <int METRIC, uint32_t BLK = 8>
 __device__ __forceinline__ float tc_score_row(const float *q_s, const float *__restrict__ x,
                                               uint32_t dim, float qmag) {
     RowAcc<METRIC> acc;
@@ -1124,7 +1124,6 @@ __device__ __forceinline__ float tc_score_row(const float *q_s, const float *__r
     const uint32_t n4 = full / 4u;
     const float4 *xv = reinterpret_cast<const float4 *>(x);
     const float4 *qv = reinterpret_cast<const float4 *>(q_s);
-    constexpr uint32_t BLK = 8;
     float4 cur[BLK], nxt[BLK];
 #pragma unroll
     for (uint32_t j = 0; j < BLK; ++j)
@@ -1170,7 +1169,7 @@ __global__ void __launch_bounds__(256) tc_refine_kernel(const TcRefineParams p) 
     __shared__ uint32_t warp_cnt[8];
     __shared__ uint32_t out_pos_s, top_n;
     __shared__ uint32_t top_idx[kTcTopCap];
-    __shared__ uint32_t top_ord[kTcTopCap];
+    __shared__ uint32_t top_ord[kTcTopCap];   // first the rows (for the prefetch), then the exact ords
     const uint32_t q = blockIdx.x, t = threadIdx.x, lane = t & 31u, warp = t >> 5;
     const uint32_t row_begin = p.ctl->row_begin, row_end = min(p.ctl->row_end, p.n_rows);
     if (row_begin >= row_end) return;  // no phase ran before this launch
@@ -1188,14 +1187,31 @@ __global__ void __launch_bounds__(256) tc_refine_kernel(const TcRefineParams p) 
         for (uint32_t i = t; i < p.dim; i += 256u) q_s[i] = __ldg(qv + i);
         __syncthreads();
         for (uint32_t i = t; i < n; i += 256u) {
-            if (list[i].lb_ord >= sel) {
+            const TcKept e = list[i];
+            if (e.lb_ord >= sel) {
                 const uint32_t pos = atomicAdd(&top_n, 1u);
-                if (pos < kTcTopCap) top_idx[pos] = i;
+                if (pos < kTcTopCap) {
+                    top_idx[pos] = i;
+                    top_ord[pos] = (e.lb_ord != e.ub_ord) ? e.row : 0xffffffffu;  // exact already
+                }
             }
         }
         __syncthreads();
         const uint32_t cnt = top_n;
         if (cnt <= kTcTopCap) {
+            // The k threads below each walk one scattered row as a chain of dependent 128-byte
+            // steps: pull all of those rows into L2 first, with every thread of the CTA issuing
+            // prefetches, so the walk pays L2 instead of HBM latency per step.
+            {
+                const uint32_t lines = (p.dim * 4u + 127u) / 128u;
+                for (uint32_t w = t; w < cnt * lines; w += 256u) {
+                    const uint32_t j = w / lines, seg = w - j * lines;
+                    const uint32_t row = top_ord[j];
+                    if (row != 0xffffffffu)
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(p.rows + (size_t)row * p.pitch + seg * 32u));
+                }
+            }
+            __syncthreads();
             const float qmag = p.qmeta[q].qmag;
             for (uint32_t j = t; j < cnt; j += 256u) {
                 const uint32_t i = top_idx[j];
