@@ -43,7 +43,9 @@ __device__ __forceinline__ void bulk_load_1d(void *dst, const void *src, uint32_
 // prepare: queries [nq_pass, dim] (row-major) -> qt [n_kc][32][QB] (+ zero padding), qmag[QB]
 // ---------------------------------------------------------------------------------------
 __global__ void prepare_batch_kernel(const float *queries, uint32_t nq_pass, uint32_t dim,
-                                     uint32_t qb, uint32_t n_kc, float *qt, float *qmag) {
+                                     uint32_t qb, uint32_t n_kc, float *qt, float *qmag,
+                                     const uint32_t *gate) {
+    if (!gate_open(gate, nq_pass)) return;  // conditional pass: no query of it was flagged
     const uint32_t total = n_kc * 32u * qb;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total;
          i += gridDim.x * blockDim.x) {
@@ -94,6 +96,8 @@ struct BatchScoreParams {
     uint32_t dim;
     uint32_t n_stages;
     uint32_t evict_first;
+    const uint32_t *gate;    // conditional pass: runs only if any of gate[0..gate_n) is set
+    uint32_t gate_n;
 };
 
 // Stage stride: corpus box + query chunk, rounded up to 1 KiB because the next stage's corpus
@@ -124,6 +128,7 @@ score_batch_kernel(const __grid_constant__ CUtensorMap tmap, const BatchScorePar
 
     const uint32_t tid = threadIdx.x;
     const uint32_t warp = tid >> 5;
+    if (!gate_open(p.gate, p.gate_n)) return;
     const uint32_t n_stages = p.n_stages;
     const uint32_t n_rb = (p.n_rows + kRowsPerBlock - 1) / kRowsPerBlock;
     const uint32_t n_kc = (p.dim + kChunkFloats - 1) / kChunkFloats;
@@ -321,6 +326,8 @@ struct BatchSelectParams {
     uint32_t out_stride;     // slots per query in the outputs (the caller's k)
     uint32_t n_rows;
     uint32_t k;              // <= kMaxFastK
+    const uint32_t *gate;    // conditional pass (see BatchScoreParams)
+    uint32_t gate_n;
 };
 
 __global__ void __launch_bounds__(kRowsPerBlock)
@@ -332,6 +339,7 @@ select_batch_kernel(const BatchSelectParams p) {
     const uint32_t t = threadIdx.x;
     const uint32_t q = blockIdx.y;
     const uint32_t n_cta = gridDim.x;
+    if (!gate_open(p.gate, p.gate_n)) return;
     if (t == 0) {
         thr_s = 0ull;
         cnt_s = 0u;

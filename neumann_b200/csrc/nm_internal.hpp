@@ -109,6 +109,7 @@ struct Workspace {
     uint64_t *d_tc_keys = nullptr;  // [256][kTcKeptCap]
     uint8_t *d_tc_out = nullptr;      // scratch result block of a sharded tensor-core pass
     size_t tc_out_cap = 0;
+    uint32_t *d_tc_redo = nullptr;    // [tc_nq_cap] device-side redo flags (asynchronous searches)
     uint32_t *d_tc_bucket = nullptr;  // row-bucket counters / cursors of the re-score ordering
     void *d_tc_sorted = nullptr;      // [256 * kTcKeptCap] uint2 {row, query << 16 | slot}
     // batched-query path (batch_kernels.cuh)
@@ -146,6 +147,7 @@ struct Workspace {
         if (d_tc_kept) cudaFree(d_tc_kept);
         if (d_tc_keys) cudaFree(d_tc_keys);
         if (d_tc_out) cudaFree(d_tc_out);
+        if (d_tc_redo) cudaFree(d_tc_redo);
         if (d_tc_bucket) cudaFree(d_tc_bucket);
         if (d_tc_sorted) cudaFree(d_tc_sorted);
         if (d_qt) cudaFree(d_qt);
@@ -356,10 +358,16 @@ bool prefilter_usable(const nm_index *idx, const Shard &sh, uint32_t nq, uint32_
 int launch_scan(nm_index *idx, const Shard &sh, Workspace &ws, const float *d_query, uint32_t k,
                 int metric, uint64_t row_base, uint64_t *out_rows, float *out_scores,
                 uint32_t *out_count, nm::ShardHit *out_hits, cudaStream_t stream,
-                const nm::PeerXchg *xchg = nullptr, const uint32_t *d_row_mask = nullptr);
+                const nm::PeerXchg *xchg = nullptr, const uint32_t *d_row_mask = nullptr,
+                const uint32_t *d_gate = nullptr);
+// d_gate (device, [nq], may be null): conditional execution — a query (or the pass of the batched
+// kernels it belongs to) is only computed if its gate word is non-zero
 int scan_queries(nm_index *idx, const Shard &sh, Workspace &ws, const float *d_queries, uint32_t nq,
                  uint32_t k, int metric, uint64_t row_base, uint64_t *out_rows, float *out_scores,
-                 uint32_t *out_counts, nm::ShardHit *out_hits, cudaStream_t stream);
+                 uint32_t *out_counts, nm::ShardHit *out_hits, cudaStream_t stream,
+                 const uint32_t *d_gate = nullptr);
+// after scan_queries_tc on the same stream: per-query redo flags, computed on the device
+int tc_redo_flags(const Workspace &ws, uint32_t nq, uint32_t rows, uint32_t **d_redo, cudaStream_t stream);
 int launch_prefiltered(nm_index *idx, const Shard &sh, Workspace &ws, const float *d_query,
                        uint32_t q, uint32_t k, int metric, uint64_t *out_rows, float *out_scores,
                        uint32_t *out_count, cudaStream_t stream);

@@ -163,11 +163,12 @@ int launch_scan_t(const Shard &sh, const nm::ScanParams &p, size_t smem, cudaStr
 int launch_scan(nm_index *idx, const Shard &sh, Workspace &ws, const float *d_query, uint32_t k,
                 int metric, uint64_t row_base, uint64_t *out_rows, float *out_scores,
                 uint32_t *out_count, nm::ShardHit *out_hits, cudaStream_t stream,
-                const nm::PeerXchg *xchg, const uint32_t *d_row_mask) {
+                const nm::PeerXchg *xchg, const uint32_t *d_row_mask, const uint32_t *d_gate) {
     nm::ScanParams p;
     memset(&p, 0, sizeof(p));
     if (xchg) p.xchg = *xchg;
     p.row_mask = d_row_mask;
+    p.gate = d_gate;
     p.query = d_query;
     p.cand = ws.d_cand;
     p.done_counter = ws.d_counter;
@@ -187,7 +188,7 @@ int launch_scan(nm_index *idx, const Shard &sh, Workspace &ws, const float *d_qu
     p.n_stages = stages;
     size_t smem = scan_smem_bytes(stages, p.q_floats);
     const bool chained = k > (uint32_t)nm::kMaxFastK;
-    const bool pipelined = ws.pipeline_next && !chained && !d_row_mask;
+    const bool pipelined = ws.pipeline_next && !chained && !d_row_mask && !d_gate;
     if (pipelined) {
         p.pdl_seq = ++ws.pipe_seq;
         p.pdl_done = ws.d_counter + 4;
@@ -294,7 +295,7 @@ bool batch_eligible(const nm_index *idx, const Shard &sh, uint32_t nq, uint32_t 
 int scan_queries_batched(nm_index *idx, const Shard &sh, Workspace &ws, const float *d_queries,
                          uint32_t nq, uint32_t k, int metric, uint64_t row_base,
                          uint64_t *out_rows, float *out_scores, uint32_t *out_counts,
-                         nm::ShardHit *out_hits, cudaStream_t stream) {
+                         nm::ShardHit *out_hits, cudaStream_t stream, const uint32_t *d_gate) {
     const uint32_t dim = idx->dim;
     const uint32_t n_kc = (dim + 31u) / 32u;
     const uint32_t k_eff = (uint32_t)std::min<uint64_t>(k, sh.rows);
@@ -337,14 +338,15 @@ int scan_queries_batched(nm_index *idx, const Shard &sh, Workspace &ws, const fl
         CUDA_TRY(cudaMalloc(&ws.d_bcand, need_cand * 8));
         ws.bcand_cap = need_cand;
     }
-    if (out_hits && k_eff < k)
+    if (out_hits && k_eff < k && !d_gate)
         CUDA_TRY(cudaMemsetAsync(out_hits, 0, (size_t)nq * k * sizeof(nm::ShardHit), stream));
 
     for (uint32_t q0 = 0; q0 < nq; q0 += qb_max) {
         const uint32_t nqp = std::min<uint32_t>(qb_max, nq - q0);
         const uint32_t qb = nqp > 16u ? 64u : round_qb(nqp);
         nm::prepare_batch_kernel<<<std::max<uint32_t>(8u, (n_kc * 32u * qb + 255u) / 256u), 256, 0, stream>>>(
-            d_queries + (size_t)q0 * dim, nqp, dim, qb, n_kc, ws.d_qt, ws.d_qmag);
+            d_queries + (size_t)q0 * dim, nqp, dim, qb, n_kc, ws.d_qt, ws.d_qmag,
+            d_gate ? d_gate + q0 : nullptr);
         CUDA_TRY(cudaGetLastError());
         nm::BatchScoreParams sp;
         memset(&sp, 0, sizeof(sp));
@@ -357,6 +359,8 @@ int scan_queries_batched(nm_index *idx, const Shard &sh, Workspace &ws, const fl
         sp.n_rows = (uint32_t)sh.rows;
         sp.dim = dim;
         sp.evict_first = (sh.rows * idx->pitch * 4ull > (64ull << 20)) ? 1u : 0u;
+        sp.gate = d_gate ? d_gate + q0 : nullptr;
+        sp.gate_n = nqp;
         int rc;
 #define NM_SCORE_BATCH(METRIC_, QB_)                                          \
     do {                                                                      \
@@ -394,6 +398,8 @@ int scan_queries_batched(nm_index *idx, const Shard &sh, Workspace &ws, const fl
         bp.out_stride = k;
         bp.n_rows = (uint32_t)sh.rows;
         bp.k = k_eff;
+        bp.gate = sp.gate;
+        bp.gate_n = nqp;
         dim3 grid(ctas_per_q, nqp);
         nm::select_batch_kernel<<<grid, nm::kRowsPerBlock, 0, stream>>>(bp);
         CUDA_TRY(cudaGetLastError());
@@ -548,14 +554,17 @@ static int ws_ensure_tc(Workspace &ws, uint32_t dim, uint32_t nq, cudaStream_t s
         if (ws.h_tc_qmeta) CUDA_TRY(cudaFreeHost(ws.h_tc_qmeta));
         if (ws.d_tc_coef) CUDA_TRY(cudaFree(ws.d_tc_coef));
         if (ws.d_tc_kept_n) CUDA_TRY(cudaFree(ws.d_tc_kept_n));
+        if (ws.d_tc_redo) CUDA_TRY(cudaFree(ws.d_tc_redo));
         ws.tc_nq_cap = 0;
         ws.d_tc_qmeta = ws.h_tc_qmeta = ws.d_tc_coef = nullptr;
         ws.d_tc_kept_n = nullptr;
+        ws.d_tc_redo = nullptr;
         const size_t tail = 8 * sizeof(uint32_t) + (cap / nm::kTcMaxQ + 1) * sizeof(nm::TcCtl);
         CUDA_TRY(cudaMalloc(&ws.d_tc_qmeta, cap * sizeof(nm::TcQueryMeta)));
         CUDA_TRY(cudaMallocHost(&ws.h_tc_qmeta, cap * sizeof(nm::TcQueryMeta) + tail));
         CUDA_TRY(cudaMalloc(&ws.d_tc_coef, cap * sizeof(float4)));
         CUDA_TRY(cudaMalloc(&ws.d_tc_kept_n, 2 * cap * sizeof(uint32_t) + tail));
+        CUDA_TRY(cudaMalloc(&ws.d_tc_redo, cap * sizeof(uint32_t)));
         ws.tc_nq_cap = cap;
     }
     if (!ws.d_tc_kept) {
@@ -808,11 +817,11 @@ int scan_queries_tc_hits_finish(nm_index *idx, const Shard &sh, Workspace &ws,
 int scan_queries(nm_index *idx, const Shard &sh, Workspace &ws, const float *d_queries,
                  uint32_t nq, uint32_t k, int metric, uint64_t row_base, uint64_t *out_rows,
                  float *out_scores, uint32_t *out_counts, nm::ShardHit *out_hits,
-                 cudaStream_t stream) {
+                 cudaStream_t stream, const uint32_t *d_gate) {
     if ((idx->batching.load() || single_query_stages(idx->dim) < 2) &&
         batch_eligible(idx, sh, nq, k, metric)) {
         int rc = scan_queries_batched(idx, sh, ws, d_queries, nq, k, metric, row_base, out_rows,
-                                      out_scores, out_counts, out_hits, stream);
+                                      out_scores, out_counts, out_hits, stream, d_gate);
         if (rc != -1) return rc;
     }
     for (uint32_t q = 0; q < nq; ++q) {
@@ -820,9 +829,19 @@ int scan_queries(nm_index *idx, const Shard &sh, Workspace &ws, const float *d_q
                              out_rows ? out_rows + (size_t)q * k : nullptr,
                              out_scores ? out_scores + (size_t)q * k : nullptr,
                              out_counts ? out_counts + q : nullptr,
-                             out_hits ? out_hits + (size_t)q * k : nullptr, stream);
+                             out_hits ? out_hits + (size_t)q * k : nullptr, stream, nullptr, nullptr,
+                             d_gate ? d_gate + q : nullptr);
         if (rc) return rc;
     }
+    return NM_OK;
+}
+
+int tc_redo_flags(const Workspace &ws, uint32_t nq, uint32_t rows, uint32_t **d_redo, cudaStream_t stream) {
+    const TcAux aux = tc_aux(ws);
+    nm::tc_redo_flags_kernel<<<(nq + 255u) / 256u, 256, 0, stream>>>(
+        static_cast<const nm::TcQueryMeta *>(ws.d_tc_qmeta), aux.ctl, nq, rows, ws.d_tc_redo);
+    CUDA_TRY(cudaGetLastError());
+    *d_redo = ws.d_tc_redo;
     return NM_OK;
 }
 

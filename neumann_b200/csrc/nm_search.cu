@@ -653,6 +653,10 @@ int nm_search_device(nm_index *idx, const float *d_queries, uint32_t nq, uint32_
     NM_TRACE("nm_search_device");
     int rc = validate_search(idx, d_queries, nq, k, metric, d_out_rows, d_out_scores, d_out_counts);
     if (rc) return rc;
+    if (nq >= 2 && idx->comm == nullptr) {
+        rc = q8_auto_prepare(idx, nq, k);  // auto mode: first eligible batch builds the int8 copy
+        if (rc) return rc;
+    }
     std::shared_lock<std::shared_mutex> g(idx->mu);
     if (idx->shards.size() != 1)
         return fail(NM_ERR_CONFIGURATION, "nm_search_device needs a single-device index");
@@ -731,6 +735,19 @@ int nm_search_device(nm_index *idx, const float *d_queries, uint32_t nq, uint32_
     if (!collective) {
         if (sh.rows == 0) {
             CUDA_TRY(cudaMemsetAsync(d_out_counts, 0, (size_t)nq * 4, stream));
+        } else if (tc_usable(idx, sh, nq, k, metric, false)) {
+            // batches: tensor-core pre-filter, then the exact kernels as CONDITIONAL launches that
+            // only run for queries the device flagged (nothing is read back to the host here)
+            rc = scan_queries_tc(idx, sh, *ws, d_queries, nq, k, metric, sh.row_base, d_out_rows,
+                                 d_out_scores, d_out_counts, stream);
+            if (rc) return rc;
+            uint32_t *d_redo = nullptr;
+            rc = tc_redo_flags(*ws, nq, (uint32_t)sh.rows, &d_redo, stream);
+            if (rc) return rc;
+            rc = scan_queries(idx, sh, *ws, d_queries, nq, k, metric, sh.row_base, d_out_rows,
+                              d_out_scores, d_out_counts, nullptr, stream, d_redo);
+            if (rc) return rc;
+            idx->tc_queries += nq;
         } else {
             rc = scan_queries(idx, sh, *ws, d_queries, nq, k, metric, sh.row_base, d_out_rows,
                               d_out_scores, d_out_counts, nullptr, stream);

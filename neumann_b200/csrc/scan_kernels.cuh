@@ -596,7 +596,20 @@ struct ScanParams {
     // once scan pdl_seq - 2 — the previous user of its set — is done.
     uint32_t pdl_seq;
     uint32_t *pdl_done;
+    // Conditional launch: when set, the kernel runs only if *gate != 0 (the exact redo of a
+    // query the tensor-core pre-filter flagged, decided on the device: asynchronous searches
+    // never read flags back to the host).
+    const uint32_t *gate;
 };
+
+// Uniform "is this conditional launch needed?": true when any of gate[0..n) is non-zero, or
+// when there is no gate.  Contains a barrier: call with all threads of the CTA.
+__device__ __forceinline__ bool gate_open(const uint32_t *gate, uint32_t n) {
+    if (!gate) return true;
+    uint32_t any = 0u;
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) any |= __ldcg(gate + i);
+    return __syncthreads_or((int)any) != 0;
+}
 
 // Read element `col` (0..31) of row t in a swizzled stage.
 __device__ __forceinline__ float stage_elem(const uint8_t *stage, uint32_t t, uint32_t col) {
@@ -624,6 +637,7 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
 
     const uint32_t tid = threadIdx.x;
     const uint32_t warp = tid >> 5;
+    if (!gate_open(p.gate, 1u)) return;
     const uint32_t n_stages = p.n_stages;
     const uint32_t n_rb = (p.n_rows + kRowsPerBlock - 1) / kRowsPerBlock;
     const uint32_t n_kc_full = p.dim / kChunkFloats;

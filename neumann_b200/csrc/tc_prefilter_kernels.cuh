@@ -1470,6 +1470,18 @@ __global__ void __launch_bounds__(kRowsPerBlock) tc_select_kernel(const TcRescor
     tc_select_query(p, q, min(p.kept_n[q], kTcKeptCap), buf, &thr_s, &cnt_s, hist, t);
 }
 
+// Which queries of a call must be redone by the exact path, decided ON THE DEVICE (asynchronous
+// searches): the query was unusable / its list overflowed, or the phases of its pass did not
+// reach the end of the corpus.  Same rule as the host's tc_query_flags.
+__global__ void tc_redo_flags_kernel(const TcQueryMeta *qmeta, const TcCtl *ctl, uint32_t nq,
+                                     uint32_t n_rows, uint32_t *redo) {
+    for (uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < nq; q += gridDim.x * blockDim.x) {
+        uint32_t f = qmeta[q].flags;
+        if (ctl[q / kTcMaxQ].row_begin < n_rows) f |= 4u;
+        redo[q] = f;
+    }
+}
+
 // sharded indexes: a shard's result as ShardHit[nq, k] for the cross-shard merge
 __global__ void __launch_bounds__(256)
 tc_pack_hits_kernel(const uint64_t *__restrict__ rows, const float *__restrict__ scores,

@@ -330,3 +330,50 @@ def test_config4_full_size_properties(n, dim, nq, k, metric):
     for i in range(4):
         assert_same(res[i], exact[i], f"config 4 q{i}")
     idx.close()
+
+
+@pytest.mark.parametrize("metric", METRICS)
+def test_tc_device_resident_batches_with_conditional_redo(metric):
+    """nm_search_device (query + outputs in HBM, asynchronous on a caller stream) takes the
+    tensor-core pre-filter for batches too.  Nothing is read back to the host there: the queries
+    the device flags (zero / non-finite / overflowing lists) are redone by CONDITIONAL launches of
+    the exact kernels that check the flags on the device.  Results must equal nm_search."""
+    import torch
+    n, d, k = 90_000, 64, 12
+    rows = o.fill_synthetic(n, d, 0x5EED0001)
+    rows[500:900] = rows[7]                      # ties
+    idx = DeviceIndex(d)
+    idx.load(rows)
+    qs = o.fill_synthetic(70, d, 0x5EED1001)
+    qs[3] = 0.0                                   # unusable for the int8 path
+    qs[40, 5] = np.inf                            # not finite
+    qs[69] *= np.float32(1e-30)                   # tiny scale
+    want = idx.search(qs, k, metric)              # host path (auto mode: tensor cores + host-side redo)
+    assert idx.stats().tc_queries == 70
+    stream = torch.cuda.Stream()
+    dq = torch.from_numpy(qs).cuda()
+    d_rows = torch.zeros((70, k), dtype=torch.int64, device="cuda")
+    d_scores = torch.zeros((70, k), dtype=torch.float32, device="cuda")
+    d_counts = torch.zeros(70, dtype=torch.int32, device="cuda")
+    torch.cuda.synchronize()
+    for _ in range(2):                            # twice: scratch and flags are reused correctly
+        idx.search_device(dq.data_ptr(), 70, k, metric, d_rows.data_ptr(), d_scores.data_ptr(),
+                          d_counts.data_ptr(), stream.cuda_stream)
+    assert idx.stats().tc_queries == 3 * 70
+    torch.cuda.synchronize()
+    gr, gs, gc = d_rows.cpu().numpy().astype(np.uint64), d_scores.cpu().numpy(), d_counts.cpu().numpy()
+    for i in range(70):
+        assert_same((gr[i, :gc[i]], gs[i, :gc[i]]), want[i], f"device batch {metric} q{i}")
+    for i in (0, 3, 40, 69):
+        assert_same(want[i], o.search(rows, qs[i], k, metric, threads=8), f"oracle {metric} q{i}")
+    # all-identical rows: every list overflows, every query is redone on the device
+    idx.load(np.ones((100_000, d), np.float32))
+    q1 = np.ones((3, d), np.float32)
+    dq1 = torch.from_numpy(q1).cuda()
+    torch.cuda.synchronize()
+    idx.search_device(dq1.data_ptr(), 3, k, metric, d_rows.data_ptr(), d_scores.data_ptr(),
+                      d_counts.data_ptr(), stream.cuda_stream)
+    torch.cuda.synchronize()
+    assert np.array_equal(d_rows[:3].cpu().numpy(), np.tile(np.arange(k), (3, 1)))
+    idx.release_stream(stream.cuda_stream)
+    idx.close()
