@@ -412,16 +412,18 @@ int scan_queries_batched(nm_index *idx, const Shard &sh, Workspace &ws, const fl
 // ---- exact int8 pre-filter path (single shard, host-synchronous nm_search only) -----------
 size_t prefilter_smem_bytes(uint32_t n_stages, uint32_t q_words) {
     return 1024 + (size_t)n_stages * nm::kStageBytes + (size_t)nm::kCandCap * 8 +
-           (size_t)q_words * 4 + 2 * nm::kMaxStages * 8 + 256 +
+           (size_t)q_words * 4 + 2 * nm::kMaxStages * 8 + 256 + 64 +
            (size_t)nm::kKeptStage * sizeof(nm::KeptEntry);
 }
 
 bool prefilter_usable(const nm_index *idx, const Shard &sh, uint32_t nq, uint32_t k, int metric,
                       bool masked) {
-    if (idx->prefilter.load() != 1 || masked || metric == NM_EUCLIDEAN) return false;
+    if (idx->prefilter.load() != 1 || masked) return false;
     if (!sh.tmap8_valid || sh.q8_rows != sh.rows || sh.rows == 0) return false;
     if (k > (uint32_t)nm::kMaxFastK || k > sh.rows) return false;
-    if (idx->batching.load() && nq >= kBatchMinQueries && (idx->dim % 8u) == 0) return false;
+    if (idx->batching.load() && nq >= kBatchMinQueries &&
+        (metric == NM_EUCLIDEAN || (idx->dim % 8u) == 0))
+        return false;  // batches share a corpus pass in the batched kernels instead
     uint32_t q_words = ((idx->dim + 127u) / 128u) * 32u;
     return prefilter_smem_bytes(3, q_words) <= 227 * 1024;
 }
@@ -470,7 +472,7 @@ int launch_prefiltered(nm_index *idx, const Shard &sh, Workspace &ws, const floa
     p.dim = idx->dim;
     p.k = k;
     p.q_words = ((idx->dim + 127u) / 128u) * 32u;
-    p.metric = metric == NM_COSINE ? nm::kCosine : nm::kDot;
+    p.metric = metric == NM_COSINE ? nm::kCosine : (metric == NM_EUCLIDEAN ? nm::kEuclidean : nm::kDot);
     uint32_t stages = nm::kMaxStages;
     while (stages > 3 && prefilter_smem_bytes(stages, p.q_words) > 227 * 1024) --stages;
     p.n_stages = stages;

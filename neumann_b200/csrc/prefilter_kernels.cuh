@@ -151,6 +151,27 @@ __global__ void quantize_rows_kernel(const float *__restrict__ rows, uint32_t pi
     }
 }
 
+#ifdef __CUDACC__
+// score of the reference's Euclidean metric from the f32 chain sum (lib.rs:2244, 2249-2253)
+__device__ __forceinline__ float tc_l2_score(float s) {
+    return __fdiv_rn(1.0f, __fadd_rn(1.0f, __fsqrt_rn(s)));
+}
+constexpr double kTcU = 5.9604644775390625e-08;  // 2^-24
+
+// bounds on the real |x|^2 of a row from its reference-arithmetic magnitude: rmag =
+// fl(sqrt(lane tree)), every term non-negative, so the tree is within (dim/8 + 16) u relative
+// and the sqrt / re-squaring add ~2u; 1e-37 covers products that underflowed.
+__device__ __forceinline__ void tc_row_sq_bounds(const RowMeta &m, uint32_t dim, double &a_lo,
+                                                 double &a_hi) {
+    const double a = (double)m.rmag * (double)m.rmag;
+    const double rel = ((double)(dim / 8u) + 24.0) * kTcU * 1.01;
+    a_lo = a * (1.0 - rel) - 1e-37;
+    a_hi = a * (1.0 + rel) + 1e-37;
+    if (a_lo < 0.0) a_lo = 0.0;
+}
+
+#endif  // __CUDACC__
+
 // ---------------------------------------------------------------------------------------
 // pre-filter scan
 // ---------------------------------------------------------------------------------------
@@ -166,7 +187,7 @@ struct PrefilterParams {
     uint32_t k;
     uint32_t n_stages;
     uint32_t q_words;         // int8 query words in smem (multiple of 32)
-    int metric;               // kCosine or kDot
+    int metric;               // kCosine, kDot or kEuclidean
 };
 
 // status bits
@@ -219,6 +240,7 @@ prefilter_scan_kernel(const __grid_constant__ CUtensorMap tmap8, const Prefilter
     float *qs_s = reinterpret_cast<float *>(red_u + 8);              // [0] s_q [1] qmag [2] Q1
     uint32_t *kept_cnt_s = reinterpret_cast<uint32_t *>(qs_s + 4);   // [0] count [1] flush base
     KeptEntry *kept_s = reinterpret_cast<KeptEntry *>(kept_cnt_s + 2);  // kKeptStage entries
+    double *red_d = reinterpret_cast<double *>(kept_s + kKeptStage);    // 8 doubles
 
     const uint32_t tid = threadIdx.x;
     const uint32_t warp = tid >> 5;
@@ -272,28 +294,36 @@ prefilter_scan_kernel(const __grid_constant__ CUtensorMap tmap8, const Prefilter
     // query statistics: max |q|, finiteness
     float mx = 0.0f;
     bool bad = false;
+    double qsq = 0.0;  // real |q|^2 (Euclidean: d^2 = |x|^2 + |q|^2 - 2 q.x)
     for (uint32_t i = t; i < p.dim; i += kRowsPerBlock) {
         float v = __ldg(p.query + i);
         bad |= !(fabsf(v) <= 3.4028234e38f);
         mx = fmaxf(mx, fabsf(v));
+        qsq += (double)v * (double)v;
     }
 #pragma unroll
     for (int o = 16; o; o >>= 1) {
         mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
         bad |= __shfl_xor_sync(0xffffffffu, (int)bad, o) != 0;
+        qsq += __shfl_xor_sync(0xffffffffu, qsq, o);
     }
     if (lane == 0) {
         red_f[warp] = mx;
         red_u[warp] = bad ? 1u : 0u;
+        red_d[warp] = qsq;
     }
     consumer_sync();
     mx = 0.0f;
     bad = false;
+    qsq = 0.0;
 #pragma unroll
     for (int w = 0; w < kConsumerWarps; ++w) {
         mx = fmaxf(mx, red_f[w]);
         bad |= red_u[w] != 0u;
+        qsq += red_d[w];
     }
+    double c_lo = qsq * (1.0 - 1e-12) - 1e-40, c_hi = qsq * (1.0 + 1e-12) + 1e-40;
+    if (c_lo < 0.0) c_lo = 0.0;
     const float s_q = __fdiv_rn(mx, 127.0f);
     if (mx > 0.0f && s_q < 1.17549435e-38f) bad = true;  // denormal scale: let the f32 scan decide
     consumer_sync();
@@ -407,9 +437,25 @@ prefilter_scan_kernel(const __grid_constant__ CUtensorMap tmap8, const Prefilter
             float lo = __double2float_rd(Dt - E), hi = __double2float_ru(Dt + E);
             // S bounds every partial sum of the reference's f32 arithmetic: below 1e37 nothing
             // can overflow there, so the interval analysis applies; otherwise "unknown"
-            const bool wild = !(ss * S < 1e37) || !(fabs(Dt) + E < 1e37);
+            bool wild = !(ss * S < 1e37) || !(fabs(Dt) + E < 1e37);
             float lb, ub;
-            if (p.metric == kCosine) {
+            if (p.metric == kEuclidean) {
+                // the same interval as the tensor-core batch pre-filter (tc_interval): the real dot
+                // lies within ss*B of ss*I, the real d^2 = |x|^2 + |q|^2 - 2 dot, and the f32 chain
+                // of non-negative terms is within (dim + 4) u relative of the real d^2; the score
+                // 1 / (1 + sqrt(.)) is monotone and correctly rounded
+                const double Ed = ss * B * 1.000001 + 1e-37;
+                double a_lo, a_hi;
+                tc_row_sq_bounds(m, p.dim, a_lo, a_hi);
+                const double gc = ((double)p.dim + 4.0) * kTcU * 1.01;
+                double dlo = a_lo + c_lo - 2.0 * (Dt + Ed);
+                double dhi = a_hi + c_hi - 2.0 * (Dt - Ed);
+                dlo = dlo * (1.0 - gc) * (1.0 - 1e-12) - 1e-36;
+                dhi = dhi * (1.0 + gc) * (1.0 + 1e-12) + 1e-36;
+                wild = !(dhi < 1e37) || !(a_hi < 1e37) || !(c_hi < 1e37);
+                ub = tc_l2_score((dlo > 0.0) ? __double2float_rd(dlo) : 0.0f);
+                lb = tc_l2_score((dhi > 0.0) ? __double2float_ru(dhi) : 0.0f);
+            } else if (p.metric == kCosine) {
                 if (qmag == 0.0f || m.rmag == 0.0f) {
                     lb = ub = 0.0f;
                 } else {

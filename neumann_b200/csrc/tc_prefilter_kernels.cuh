@@ -278,23 +278,8 @@ __device__ __forceinline__ void tc_ld_wait(int (&v)[16]) {
 // ---------------------------------------------------------------------------------------
 // error model
 // ---------------------------------------------------------------------------------------
-// score of the reference's Euclidean metric from the f32 chain sum (lib.rs:2244, 2249-2253)
-__device__ __forceinline__ float tc_l2_score(float s) {
-    return __fdiv_rn(1.0f, __fadd_rn(1.0f, __fsqrt_rn(s)));
-}
-constexpr double kTcU = 5.9604644775390625e-08;  // 2^-24
-
-// bounds on the real |x|^2 of a row from its reference-arithmetic magnitude: rmag =
-// fl(sqrt(lane tree)), every term non-negative, so the tree is within (dim/8 + 16) u relative
-// and the sqrt / re-squaring add ~2u; 1e-37 covers products that underflowed.
-__device__ __forceinline__ void tc_row_sq_bounds(const RowMeta &m, uint32_t dim, double &a_lo,
-                                                 double &a_hi) {
-    const double a = (double)m.rmag * (double)m.rmag;
-    const double rel = ((double)(dim / 8u) + 24.0) * kTcU * 1.01;
-    a_lo = a * (1.0 - rel) - 1e-37;
-    a_hi = a * (1.0 + rel) + 1e-37;
-    if (a_lo < 0.0) a_lo = 0.0;
-}
+// (tc_l2_score, kTcU and tc_row_sq_bounds live in prefilter_kernels.cuh: the single-query
+// pre-filter uses the same Euclidean interval)
 
 // Rigorous interval of the reference score of (row, query) from the exact integer dot I.
 // wild == the analysis does not apply (non-finite data, possible overflow): always a candidate.

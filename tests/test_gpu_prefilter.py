@@ -27,7 +27,7 @@ def check(idx, rows, queries, k, metric, ctx=""):
         s1.prefilter_kept - s0.prefilter_kept
 
 
-@pytest.mark.parametrize("metric", ["cosine", "dot"])
+@pytest.mark.parametrize("metric", ["cosine", "dot", "euclidean"])
 @pytest.mark.parametrize("n,dim,k", [(50_000, 128, 10), (20_000, 768, 10), (30_000, 100, 100),
                                      (9_000, 1536, 1), (70_000, 64, 1000), (3_000, 13, 5),
                                      (400, 8, 7), (5_000, 4096, 3)])
@@ -43,7 +43,7 @@ def test_prefilter_equals_exact_scan_synthetic(metric, n, dim, k):
     idx.close()
 
 
-@pytest.mark.parametrize("metric", ["cosine", "dot"])
+@pytest.mark.parametrize("metric", ["cosine", "dot", "euclidean"])
 def test_prefilter_adversarial_data(metric):
     """Near-duplicates inside the quantisation error, exact duplicates, outlier elements (coarse
     int8 scale), tiny and huge magnitudes, zero rows, negative copies."""
@@ -95,7 +95,7 @@ def test_prefilter_rows_with_nonfinite_values_stay_exact():
     idx = DeviceIndex(d)
     idx.load(rows)
     idx.set_prefilter(1)
-    for metric in ("cosine", "dot"):
+    for metric in ("cosine", "dot", "euclidean"):
         check(idx, rows, [o.fill_synthetic(1, d, 10)[0]], 1000, metric, "nonfinite rows")
     idx.close()
 
