@@ -379,7 +379,7 @@ bool tc_usable(const nm_index *idx, const Shard &sh, uint32_t nq, uint32_t k, in
 int scan_queries_tc(nm_index *idx, const Shard &sh, Workspace &ws, const float *d_queries,
                     uint32_t nq, uint32_t k, int metric, uint64_t row_base, uint64_t *out_rows,
                     float *out_scores, uint32_t *out_counts, cudaStream_t stream,
-                    int *debug_dots = nullptr);
+                    int *debug_dots = nullptr, const uint32_t *d_row_mask = nullptr);
 int scan_queries_tc_hits_enqueue(nm_index *idx, const Shard &sh, Workspace &ws,
                                  const float *d_queries, uint32_t nq, uint32_t k, int metric,
                                  uint64_t row_base, nm::ShardHit *out_hits, cudaStream_t stream);

@@ -585,7 +585,8 @@ constexpr uint32_t kTcMaxPhases = 12;
 
 int scan_queries_tc(nm_index *idx, const Shard &sh, Workspace &ws, const float *d_queries,
                     uint32_t nq, uint32_t k, int metric, uint64_t row_base, uint64_t *out_rows,
-                    float *out_scores, uint32_t *out_counts, cudaStream_t stream, int *debug_dots) {
+                    float *out_scores, uint32_t *out_counts, cudaStream_t stream, int *debug_dots,
+                    const uint32_t *d_row_mask) {
     static std::mutex mu;
     static bool configured[64] = {false};
     {
@@ -633,7 +634,7 @@ int scan_queries_tc(nm_index *idx, const Shard &sh, Workspace &ws, const float *
         nm::TcCtl *ctl = aux.ctl + pass;
         nm::tc_prepare_queries_kernel<<<n_pad, 256, 0, stream>>>(
             d_queries + (size_t)q0 * dim, nqp, dim, pitch8, ws.d_tc_q8, qmeta + q0, coef + q0,
-            aux.kept_n + q0, aux.kept_prev + q0, ctl, rows);
+            aux.kept_n + q0, aux.kept_prev + q0, ctl, rows, d_row_mask ? 1u : 0u);
         CUDA_TRY(cudaGetLastError());
         CUtensorMap tmap_q;
         rc = encode_tmap_u8(&tmap_q, ws.d_tc_q8, dim, n_pad, pitch8, 128, n_pad / ctas);
@@ -658,6 +659,7 @@ int scan_queries_tc(nm_index *idx, const Shard &sh, Workspace &ws, const float *
         gp.shift = 0;
         while (((16300ull * dim) >> gp.shift) >= (1ull << 22) - 64) ++gp.shift;
         gp.metric = kmetric;
+        gp.row_mask = d_row_mask;
         nm::TcRefineParams rp;
         memset(&rp, 0, sizeof(rp));
         rp.kept = kept;

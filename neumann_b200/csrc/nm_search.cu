@@ -143,7 +143,7 @@ static int search_impl(nm_index *idx, const float *queries, uint32_t nq, uint32_
     int rc = validate_search(idx, queries, nq, k, metric, out_rows, out_scores, out_counts);
     if (rc) return rc;
     const bool masked = mspec.any();
-    if (nq >= 2 && !masked) {
+    if (nq >= 2) {
         rc = q8_auto_prepare(idx, nq, k);  // auto mode: first eligible batch builds the int8 copy
         if (rc) return rc;
     }
@@ -191,18 +191,20 @@ static int search_impl(nm_index *idx, const float *queries, uint32_t nq, uint32_
         }
         NM_TRACE("scan");
         CUDA_TRY(cudaEventRecord(ws->ev0, ws->stream));
-        if (masked) {
+        const bool tc_path = tc_usable(idx, sh, nq, k, metric, false);
+        if (masked && !tc_path) {
             for (uint32_t q = 0; q < nq; ++q) {
                 rc = launch_scan(idx, sh, *ws, ws->d_query + (size_t)q * dim, k, metric, sh.row_base,
                                  r_rows + (size_t)q * k, r_scores + (size_t)q * k, r_counts + q,
                                  nullptr, ws->stream, nullptr, d_mask);
                 if (rc) return rc;
             }
-        } else if (tc_usable(idx, sh, nq, k, metric, masked)) {
+        } else if (tc_path) {
             // tensor-core pre-filter: one int8 GEMM pass per 256 queries + exact re-score; the
-            // per-query flags come back with the results, flagged queries are redone exactly
+            // per-query flags come back with the results, flagged queries are redone exactly.
+            // Masked batches too: ineligible rows never enter the kept lists.
             rc = scan_queries_tc(idx, sh, *ws, ws->d_query, nq, k, metric, sh.row_base, r_rows,
-                                 r_scores, r_counts, ws->stream);
+                                 r_scores, r_counts, ws->stream, nullptr, d_mask);
             if (rc) return rc;
             CUDA_TRY(cudaEventRecord(ws->ev1, ws->stream));
             CUDA_TRY(cudaMemcpyAsync(ws->h_result, ws->d_result, l.total, cudaMemcpyDeviceToHost,
@@ -216,7 +218,7 @@ static int search_impl(nm_index *idx, const float *queries, uint32_t nq, uint32_
                 if (tc_query_flags(*ws, q, (uint32_t)sh.rows) != 0) ++n_redo;
             idx->tc_fallbacks += n_redo;
             const bool redo = n_redo != 0;
-            if (n_redo * 2 > nq) {
+            if (n_redo * 2 > nq && !masked) {
                 // most of the batch (e.g. a corpus ordered against the running threshold): the
                 // exact batched kernels redo all of it in shared corpus passes
                 rc = scan_queries(idx, sh, *ws, ws->d_query, nq, k, metric, sh.row_base, r_rows,
@@ -227,7 +229,7 @@ static int search_impl(nm_index *idx, const float *queries, uint32_t nq, uint32_
                     if (tc_query_flags(*ws, q, (uint32_t)sh.rows) == 0) continue;
                     rc = launch_scan(idx, sh, *ws, ws->d_query + (size_t)q * dim, k, metric,
                                      sh.row_base, r_rows + (size_t)q * k, r_scores + (size_t)q * k,
-                                     r_counts + q, nullptr, ws->stream);
+                                     r_counts + q, nullptr, ws->stream, nullptr, d_mask);
                     if (rc) return rc;
                 }
             }

@@ -459,7 +459,8 @@ __device__ __forceinline__ void tc_row_coef(int metric, const RowMeta &m, const 
 __global__ void __launch_bounds__(256)
 tc_prepare_queries_kernel(const float *__restrict__ queries, uint32_t nq, uint32_t dim,
                           uint32_t pitch8, int8_t *q8, TcQueryMeta *qmeta, float4 *coef,
-                          uint32_t *kept_n, uint32_t *kept_prev, TcCtl *ctl, uint32_t n_rows) {
+                          uint32_t *kept_n, uint32_t *kept_prev, TcCtl *ctl, uint32_t n_rows,
+                          uint32_t masked) {
     __shared__ float red_f[8];
     __shared__ uint32_t red_u[8];
     __shared__ double red_d[8];
@@ -596,7 +597,8 @@ tc_prepare_queries_kernel(const float *__restrict__ queries, uint32_t nq, uint32
         m.enorm = __double2float_ru((sqrt(ee2) + 7.7e-6 * sqrt((double)dim)) * (1.0 + 1e-9));
         qmeta[q] = m;
         coef[q] = bad ? tc_pass_none() : tc_pass_all(0u);
-        kept_n[q] = bad ? 0u : min(n_rows, kTcPhase0Rows);  // phase 0 fills slots [0, rows)
+        // phase 0 fills slots [0, rows) directly; with a row mask it appends like every other phase
+        kept_n[q] = (bad || masked) ? 0u : min(n_rows, kTcPhase0Rows);
         kept_prev[q] = 0u;
     }
 }
@@ -622,6 +624,7 @@ struct TcGemmParams {
     uint32_t screen;            // 0: skip the f32 screen (every entry evaluated rigorously; tests)
     uint32_t shift;             // the screen works on I >> shift (|I >> shift| < 2^22)
     int metric;
+    const uint32_t *row_mask;   // optional pre-filter: bit r set = row r takes part (may be null)
 };
 
 // An entry that passed the screen, parked until the accumulator has been handed back to the MMA
@@ -859,7 +862,7 @@ tc_gemm_filter_kernel(const __grid_constant__ CUtensorMap tmap_a,
         const uint32_t n_chunks = (p.nq + 15u) / 16u;
         const float sc = __uint_as_float((127u - p.shift) << 23);
         const int sh = (int)p.shift;
-        const bool phase0 = row_begin == 0u;
+        const bool phase0 = row_begin == 0u && p.row_mask == nullptr;
         const TcRowConsts rcst = tc_row_consts(p.metric, p.dim);
         TcPend *pq = pend_s + (warp - kTcRoleWarps) * kTcPendCap;
         uint32_t *pcnt = pend_cnt_s + (warp - kTcRoleWarps);
@@ -894,7 +897,8 @@ tc_gemm_filter_kernel(const __grid_constant__ CUtensorMap tmap_a,
         for (uint32_t t = unit; t < n_tiles; t += n_units, ++it) {
             const uint32_t acc = it & 1u, aph = (it >> 1) & 1u;
             const uint32_t row = row_begin + t * kTileRows + cr * kTcM + qd * 32u + lane;
-            const bool valid = row < row_end;
+            bool valid = row < row_end;
+            if (valid && p.row_mask) valid = ((__ldg(p.row_mask + (row >> 5)) >> (row & 31u)) & 1u) != 0u;
             const float4 raw = raw_next;
             {   // next tile's row constants: in flight while this tile is screened
                 const uint32_t tn = t + n_units;
@@ -1071,9 +1075,21 @@ __device__ __forceinline__ uint32_t tc_radix_kth(F val, uint32_t n, uint32_t k, 
         hist[t] = 0u;
         __syncthreads();
         const uint32_t prefix = sel_s[0], need = sel_s[1];
-        for (uint32_t i = t; i < n; i += 256u) {
-            const uint32_t o = val(i);
-            if (shift == 24 || (o >> (shift + 8)) == prefix) atomicAdd(&hist[(o >> shift) & 255u], 1u);
+        // four independent loads per thread and round: the lists live in L2 / HBM and the loop is
+        // latency-, not bandwidth-bound
+        for (uint32_t base = 0; base < n; base += 1024u) {
+            uint32_t o[4];
+#pragma unroll
+            for (uint32_t j = 0; j < 4u; ++j) {
+                const uint32_t i = base + j * 256u + t;
+                o[j] = i < n ? val(i) : 0u;
+            }
+#pragma unroll
+            for (uint32_t j = 0; j < 4u; ++j) {
+                const uint32_t i = base + j * 256u + t;
+                if (i < n && (shift == 24 || (o[j] >> (shift + 8)) == prefix))
+                    atomicAdd(&hist[(o[j] >> shift) & 255u], 1u);
+            }
         }
         __syncthreads();
         const uint32_t mine = hist[t];
@@ -1171,13 +1187,23 @@ __global__ void __launch_bounds__(256) tc_refine_kernel(const TcRefineParams p) 
         const float *qv = p.queries + (size_t)q * p.dim;
         for (uint32_t i = t; i < p.dim; i += 256u) q_s[i] = __ldg(qv + i);
         __syncthreads();
-        for (uint32_t i = t; i < n; i += 256u) {
-            const TcKept e = list[i];
-            if (e.lb_ord >= sel) {
-                const uint32_t pos = atomicAdd(&top_n, 1u);
-                if (pos < kTcTopCap) {
-                    top_idx[pos] = i;
-                    top_ord[pos] = (e.lb_ord != e.ub_ord) ? e.row : 0xffffffffu;  // exact already
+        for (uint32_t base = 0; base < n; base += 1024u) {
+            TcKept e[4];
+#pragma unroll
+            for (uint32_t j = 0; j < 4u; ++j) {
+                const uint32_t i = base + j * 256u + t;
+                e[j].row = e[j].lb_ord = e[j].ub_ord = 0u;
+                if (i < n) e[j] = list[i];
+            }
+#pragma unroll
+            for (uint32_t j = 0; j < 4u; ++j) {
+                const uint32_t i = base + j * 256u + t;
+                if (i < n && e[j].lb_ord >= sel) {
+                    const uint32_t pos = atomicAdd(&top_n, 1u);
+                    if (pos < kTcTopCap) {
+                        top_idx[pos] = i;
+                        top_ord[pos] = (e[j].lb_ord != e[j].ub_ord) ? e[j].row : 0xffffffffu;  // exact already
+                    }
                 }
             }
         }
@@ -1218,21 +1244,36 @@ __global__ void __launch_bounds__(256) tc_refine_kernel(const TcRefineParams p) 
             tau = max(tau, ex);
         }
     }
-    // in-place stable compaction (writes never pass the chunk being read)
+    // in-place stable compaction, 1024 entries per round (four independent loads per thread; the
+    // writes of a round never pass the entries it has read)
     if (t == 0) out_pos_s = 0u;
     __syncthreads();
-    for (uint32_t base = 0; base < n; base += 256u) {
-        const uint32_t i = base + t;
-        TcKept e;
-        e.row = e.lb_ord = e.ub_ord = 0u;
-        if (i < n) e = list[i];
-        const bool keep = i < n && e.ub_ord >= tau;
-        const uint32_t ballot = __ballot_sync(0xffffffffu, keep);
-        if (lane == 0) warp_cnt[warp] = __popc(ballot);
-        __syncthreads();
-        uint32_t off = out_pos_s;
+    for (uint32_t base = 0; base < n; base += 1024u) {
+        TcKept e[4];
+        bool keep[4];
+        uint32_t mine = 0;
+#pragma unroll
+        for (uint32_t j = 0; j < 4u; ++j) {
+            const uint32_t i = base + t * 4u + j;  // thread t owns 4 consecutive entries: order kept
+            e[j].row = e[j].lb_ord = e[j].ub_ord = 0u;
+            if (i < n) e[j] = list[i];
+            keep[j] = i < n && e[j].ub_ord >= tau;
+            mine += keep[j] ? 1u : 0u;
+        }
+        // exclusive prefix of `mine` over the 256 threads
+        uint32_t incl = mine;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const uint32_t v = __shfl_up_sync(0xffffffffu, incl, off);
+            if (lane >= (uint32_t)off) incl += v;
+        }
+        if (lane == 31u) warp_cnt[warp] = incl;
+        __syncthreads();  // (also: every thread has read its entries before anyone writes)
+        uint32_t off = out_pos_s + incl - mine;
         for (uint32_t w = 0; w < warp; ++w) off += warp_cnt[w];
-        if (keep) list[off + __popc(ballot & ((1u << lane) - 1u))] = e;
+#pragma unroll
+        for (uint32_t j = 0; j < 4u; ++j)
+            if (keep[j]) list[off++] = e[j];
         __syncthreads();
         if (t == 0) {
             uint32_t tot = 0;

@@ -377,3 +377,39 @@ def test_tc_device_resident_batches_with_conditional_redo(metric):
     assert np.array_equal(d_rows[:3].cpu().numpy(), np.tile(np.arange(k), (3, 1)))
     idx.release_stream(stream.cuda_stream)
     idx.close()
+
+
+@pytest.mark.parametrize("metric", METRICS)
+def test_tc_masked_and_filtered_batches(metric):
+    """Batches with a row mask (host bitmask or device-evaluated filter) take the tensor-core
+    pre-filter too: ineligible rows never enter the kept lists; the result is the oracle's on the
+    eligible subset, bit for bit."""
+    from neumann_b200._ffi import NM_C_LT, NM_F_CMP, NM_V_INT, NmFilterOp
+    n, d, k, nq = 120_000, 72, 15, 9
+    rows = o.fill_synthetic(n, d, 0x5EED0001)
+    idx = DeviceIndex(d)
+    idx.load(rows)
+    bucket = (np.arange(n) * 2654435761 % 10).astype(np.uint64)
+    idx.column_set(1, 0, np.full(n, 3, np.uint8), bucket)
+    qs = o.fill_synthetic(nq, d, 0x5EED1001)
+    for lim in (3, 1):                                       # 30 % and 10 % of the rows eligible
+        keep = bucket < lim
+        sub = np.nonzero(keep)[0]
+        prog = [NmFilterOp(kind=NM_F_CMP, cmp=NM_C_LT, lit_tag=NM_V_INT, column=1, lit=lim)]
+        s0 = idx.stats().tc_queries
+        res_f = idx.search_filtered(qs, k, metric, prog)
+        res_m = idx.search_masked(qs, k, metric, keep)
+        assert idx.stats().tc_queries - s0 == 2 * nq
+        for i in range(nq):
+            er, es = o.search(rows[sub], qs[i], k, metric, threads=8)
+            want = (sub[er.astype(np.int64)].astype(np.uint64), es)
+            assert_same(res_f[i], want, f"filtered batch {metric} lim={lim} q{i}")
+            assert_same(res_m[i], want, f"masked batch {metric} lim={lim} q{i}")
+    # fewer eligible rows than k: everything eligible comes back, in order
+    keep = np.zeros(n, bool)
+    keep[[5, 70_000, 119_999]] = True
+    res = idx.search_masked(qs[:2], k, metric, keep)
+    for i in range(2):
+        er, es = o.search(rows[keep], qs[i], k, metric)
+        assert_same(res[i], (np.nonzero(keep)[0][er.astype(np.int64)].astype(np.uint64), es), "tiny subset")
+    idx.close()
