@@ -751,6 +751,10 @@ def run_ours(a):
         widx.close()
 
     if rank != 0:
+        # every rank tears its shard down (ncclCommDestroy is collective in effect: rank 0 does the
+        # same right before ITS barrier below — closing on one side only deadlocks)
+        if idx is not None:
+            idx.close()
         if world > 1:
             dist.barrier()
             dist.destroy_process_group()

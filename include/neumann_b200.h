@@ -243,6 +243,9 @@ int nm_comm_create_id(void *out_id /* NM_COMM_ID_BYTES */);
  * The exchange is ONE ncclAllGather of nq*k 16-byte candidates per rank. */
 int nm_index_attach_comm(nm_index *idx, const void *id, int n_ranks, int rank,
                          uint64_t row_base);
+/* Detaching (and nm_index_destroy of an attached index) tears the communicator down: like
+ * ncclCommDestroy it must be called by EVERY rank; a rank that destroys its shard while the others
+ * wait for it elsewhere deadlocks. */
 int nm_index_detach_comm(nm_index *idx);
 
 /* ---- instrumentation (counters the reference keeps in ShardAccessTracker,
