@@ -180,8 +180,10 @@ def oracle_shard_topk(idx, n_local, global_lo, queries, k, metric, threads, seed
     o = _oracle()
     nq, dim = queries.shape
     chunk_rows = max(1, min(chunk_rows, n_local))
-    buf = torch.empty((chunk_rows, dim), dtype=torch.float32).pin_memory().numpy() \
-        if n_local else np.zeros((0, dim), np.float32)
+    buf = torch.empty((chunk_rows, dim), dtype=torch.float32)
+    if torch.cuda.is_available():
+        buf = buf.pin_memory()
+    buf = buf.numpy() if n_local else np.zeros((0, dim), np.float32)
     per_q_rows = [[] for _ in range(nq)]
     per_q_scores = [[] for _ in range(nq)]
     t_search = 0.0

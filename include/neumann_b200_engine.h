@@ -86,6 +86,12 @@ int nm_engine_search_filtered_in_collection(nm_engine *e, const char *collection
                                             const char *where_expr, int strategy,
                                             size_t oversample_factor, nm_results **out);
 int nm_engine_count_matching(nm_engine *e, const char *where_expr, uint64_t *out);
+/* Tests / diagnostics (no device involved): the metadata columns the rows of dimension `dim` of
+ * the default space are pushed to the device as, the postfix nm_filter_op program `where_expr`
+ * compiles to, and the host's evaluate_filter verdict per row, as JSON text.  *out_len receives
+ * the full length; `out` (may be NULL) receives at most out_cap - 1 bytes + NUL. */
+int nm_engine_debug_filter_program(nm_engine *e, uint32_t dim, const char *where_expr, char *out,
+                                   size_t out_cap, size_t *out_len);
 /* PointsService::query post-processing (neumann_server/src/service/points.rs:449-485);
  * score_threshold is ignored when has_threshold == 0. */
 int nm_engine_query_points(nm_engine *e, const char *collection, const float *vector, size_t n,

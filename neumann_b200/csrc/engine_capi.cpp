@@ -281,6 +281,21 @@ int nm_engine_count_matching(nm_engine *e, const char *where_expr, uint64_t *out
     return NM_OK;
 }
 
+int nm_engine_debug_filter_program(nm_engine *e, uint32_t dim, const char *where_expr, char *out,
+                                   size_t out_cap, size_t *out_len) {
+    if (!e || !out_len) return fail(NM_ERR_INVALID_ARGUMENT, "null argument");
+    FilterCondition f;
+    if (!parse_filter_arg(where_expr, &f)) return NM_ERR_INVALID_ARGUMENT;
+    const std::string js = e->engine->debug_filter_program(dim, f);
+    *out_len = js.size();
+    if (out && out_cap) {
+        const size_t m = std::min(out_cap - 1, js.size());
+        std::memcpy(out, js.data(), m);
+        out[m] = 0;
+    }
+    return NM_OK;
+}
+
 int nm_engine_query_points(nm_engine *e, const char *collection, const float *vector, size_t n,
                            size_t limit, size_t offset, int has_threshold, float score_threshold,
                            nm_results **out) {

@@ -370,11 +370,12 @@ void compile_filter(const BucketT &b, const FilterCondition &f, FilterProgram &o
     }
 }
 
-// Push the column entries of rows [first, first + n) to the device: one pass over the rows'
-// metadata maps per 1M-row chunk, one nm_index_column_set per column that occurs in the chunk.
-template <class BucketT>
-int push_columns(BucketT &b, uint64_t first, uint64_t n) {
-    const bool repush = first < b.cols_synced_rows;  // overwrite: absent fields must become "missing"
+// Column entries of rows [first, first + n): one pass over the rows' metadata maps per 1M-row
+// chunk, `sink(column id, first row, rows, tags, vals)` once per column that occurs in the chunk
+// (every known column when `all_columns`: rows being re-pushed must overwrite absent fields with
+// "missing").  Registers new field names and new distinct strings on the way.
+template <class BucketT, class Sink>
+int stage_columns(BucketT &b, uint64_t first, uint64_t n, bool all_columns, Sink sink) {
     constexpr uint64_t kChunk = 1u << 20;
     struct Staged {
         std::vector<uint8_t> tags;
@@ -383,7 +384,7 @@ int push_columns(BucketT &b, uint64_t first, uint64_t n) {
     for (uint64_t c0 = first; c0 < first + n; c0 += kChunk) {
         const uint64_t m = std::min(kChunk, first + n - c0);
         std::unordered_map<uint32_t, Staged> staged;
-        if (repush)
+        if (all_columns)
             for (auto &ckv : b.columns) {
                 Staged &st = staged[ckv.second.id];
                 st.tags.assign(m, NM_V_MISSING);
@@ -418,12 +419,22 @@ int push_columns(BucketT &b, uint64_t first, uint64_t n) {
                 }
             }
         for (auto &kv : staged) {
-            int rc = nm_index_column_set(b.mirror, kv.first, c0, m, kv.second.tags.data(),
-                                         kv.second.vals.data());
+            int rc = sink(kv.first, c0, m, kv.second.tags, kv.second.vals);
             if (rc) return rc;
         }
     }
     return 0;
+}
+
+// Push the column entries of rows [first, first + n) to the device.
+template <class BucketT>
+int push_columns(BucketT &b, uint64_t first, uint64_t n) {
+    const bool repush = first < b.cols_synced_rows;
+    return stage_columns(b, first, n, repush,
+                         [&](uint32_t col, uint64_t row0, uint64_t m, const std::vector<uint8_t> &tags,
+                             const std::vector<uint64_t> &vals) {
+                             return nm_index_column_set(b.mirror, col, row0, m, tags.data(), vals.data());
+                         });
 }
 
 }  // namespace
@@ -1057,6 +1068,49 @@ std::vector<VectorEngine::MirrorInfo> VectorEngine::mirror_info() const {
     for (auto &kv : default_space_->buckets)
         out.push_back(MirrorInfo{kv.first, (uint64_t)kv.second->keys.size(),
                                  kv.second->mirror ? nm_index_rows(kv.second->mirror) : 0});
+    return out;
+}
+
+// Host-only view of the device-side filter path (tests): the columns the rows of dimension `dim`
+// of the default space would be pushed as, the postfix program `filter` compiles to, and what
+// evaluate_filter says per row.  JSON, no device involved.
+std::string VectorEngine::debug_filter_program(uint32_t dim, const FilterCondition &filter) const {
+    Space &sp = *default_space_;
+    std::unique_lock<std::shared_mutex> g(sp.mu);
+    std::string out = "{";
+    auto bit = sp.buckets.find(dim);
+    if (bit == sp.buckets.end()) return "{\"rows\": 0}";
+    Bucket &b = *bit->second;
+    std::lock_guard<std::mutex> sg(b.sync_mu);
+    const uint64_t n = b.keys.size();
+    out += "\"rows\": " + std::to_string(n) + ", \"columns\": {";
+    bool first_col = true;
+    stage_columns(b, 0, n, true,
+                  [&](uint32_t col, uint64_t row0, uint64_t m, const std::vector<uint8_t> &tags,
+                      const std::vector<uint64_t> &vals) {
+                      (void)row0;  // n <= one chunk in tests
+                      out += std::string(first_col ? "" : ", ") + "\"" + std::to_string(col) + "\": {\"tags\": [";
+                      first_col = false;
+                      for (uint64_t i = 0; i < m; ++i) out += (i ? "," : "") + std::to_string(tags[i]);
+                      out += "], \"vals\": [";
+                      for (uint64_t i = 0; i < m; ++i) out += (i ? "," : "") + std::to_string(vals[i]);
+                      out += "]}";
+                      return 0;
+                  });
+    out += "}, \"ops\": [";
+    FilterProgram prog;
+    compile_filter(b, filter, prog);
+    for (size_t i = 0; i < prog.ops.size(); ++i) {
+        const nm_filter_op &op = prog.ops[i];
+        out += std::string(i ? ", " : "") + "[" + std::to_string(op.kind) + "," + std::to_string(op.cmp) + "," +
+               std::to_string(op.lit_tag) + "," + std::to_string(op.column) + "," + std::to_string(op.lit) +
+               "," + std::to_string(op.table_off) + "," + std::to_string(op.table_bits) + "]";
+    }
+    out += "], \"tables\": [";
+    for (size_t i = 0; i < prog.tables.size(); ++i) out += (i ? "," : "") + std::to_string(prog.tables[i]);
+    out += "], \"host\": [";
+    for (uint64_t r = 0; r < n; ++r) out += std::string(r ? "," : "") + (evaluate_filter(b.meta[r], filter) ? "1" : "0");
+    out += "]}";
     return out;
 }
 

@@ -211,6 +211,9 @@ class VectorEngine {
         uint64_t host_rows, device_rows;
     };
     std::vector<MirrorInfo> mirror_info() const;
+    // Tests: columns + compiled postfix program + host evaluation for the rows of one dimension
+    // of the default space, as JSON (no device involved).
+    std::string debug_filter_program(uint32_t dim, const FilterCondition &filter) const;
 
   private:
     struct Bucket;

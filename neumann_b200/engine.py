@@ -71,6 +71,7 @@ ENGINE_SIGNATURES = {
     "nm_engine_search_similar_filtered": (C.c_int, [_vp, _vp, _sz, _sz, _cp, C.c_int, _sz, _pvp]),
     "nm_engine_search_filtered_in_collection": (C.c_int, [_vp, _cp, _vp, _sz, _sz, _cp, C.c_int, _sz, _pvp]),
     "nm_engine_count_matching": (C.c_int, [_vp, _cp, C.POINTER(_u64)]),
+    "nm_engine_debug_filter_program": (C.c_int, [_vp, C.c_uint32, _cp, _vp, _sz, C.POINTER(_sz)]),
     "nm_engine_query_points": (C.c_int, [_vp, _cp, _vp, _sz, _sz, _sz, C.c_int, C.c_float, _pvp]),
     "nm_engine_set_entity_embedding": (C.c_int, [_vp, _cp, _vp, _sz]),
     "nm_engine_remove_entity_embedding": (C.c_int, [_vp, _cp]),
@@ -284,6 +285,15 @@ class VectorEngine:
             self._h, collection.encode(), q.ctypes.data, q.size, top_k, where.encode(), strategy,
             oversample_factor, C.byref(h)))
         return _take(h)
+
+    def debug_filter_program(self, dim: int, where: str) -> dict:
+        """Columns + compiled postfix program + host verdict per row (JSON; no device involved)."""
+        import json
+        n = _sz(0)
+        _check(_lib().nm_engine_debug_filter_program(self._h, dim, where.encode(), None, 0, C.byref(n)))
+        buf = C.create_string_buffer(n.value + 1)
+        _check(_lib().nm_engine_debug_filter_program(self._h, dim, where.encode(), buf, n.value + 1, C.byref(n)))
+        return json.loads(buf.value.decode())
 
     def count_matching(self, where: str) -> int:
         n = C.c_uint64()
