@@ -322,20 +322,9 @@ int nm_index_column_set(nm_index *idx, uint32_t column, uint64_t first_row, uint
         const uint64_t lo = std::max(first_row, sh.row_base), hi = std::min(first_row + n, sh.row_base + sh.rows);
         if (lo >= hi) continue;
         CUDA_TRY(cudaSetDevice(sh.device));
-        auto &slot = sh.columns[column];
-        if (!slot) slot.reset(new Column());
-        Column &c = *slot;
+        Column &c = column_of(sh, column);
         if (c.init_rows > sh.rows) c.init_rows = sh.rows;
-        if (c.init_rows < sh.rows) {
-            int rc = c.tags_buf.ensure(sh.device, sh.rows, false);
-            if (!rc) rc = c.vals_buf.ensure(sh.device, sh.rows * sizeof(uint64_t), false);
-            if (rc) return rc;
-            c.d_tags = static_cast<uint8_t *>(c.tags_buf.ptr());
-            c.d_vals = static_cast<uint64_t *>(c.vals_buf.ptr());
-            CUDA_TRY(cudaMemsetAsync(c.d_tags + c.init_rows, 0, sh.rows - c.init_rows, sh.copy_stream));
-            CUDA_TRY(cudaMemsetAsync(c.d_vals + c.init_rows, 0, (sh.rows - c.init_rows) * 8, sh.copy_stream));
-            c.init_rows = sh.rows;
-        }
+        if (int rc = column_reserve(sh, c, sh.rows)) return rc;  // rows never set read as "missing"
         CUDA_TRY(cudaMemcpyAsync(c.d_tags + (lo - sh.row_base), tags + (lo - first_row), hi - lo,
                                  cudaMemcpyHostToDevice, sh.copy_stream));
         CUDA_TRY(cudaMemcpyAsync(c.d_vals + (lo - sh.row_base), values + (lo - first_row), (hi - lo) * 8,
