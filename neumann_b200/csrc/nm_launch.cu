@@ -600,9 +600,6 @@ int scan_queries_tc(nm_index *idx, const Shard &sh, Workspace &ws, const float *
                                           cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
             CUDA_TRY(cudaFuncSetAttribute(nm::tc_refine_kernel,
                                           cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-            CUDA_TRY(cudaFuncSetAttribute(nm::tc_score_sorted_staged_kernel,
-                                          cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          (int)nm::tc_rescore_staged_smem()));
             if (sh.device < 64) configured[sh.device] = true;
         }
     }
@@ -738,17 +735,8 @@ int scan_queries_tc(nm_index *idx, const Shard &sh, Workspace &ws, const float *
             CUDA_TRY(cudaGetLastError());
             nm::tc_sort_scatter_kernel<<<nqp, 256, 0, stream>>>(so);
             CUDA_TRY(cudaGetLastError());
-            static const bool staged = [] {
-                const char *e = getenv("NM_TC_RESCORE_STAGED");
-                return !(e && e[0] == '0');
-            }();
-            if (staged)   // rows staged through shared memory, 512 contiguous bytes per request
-                nm::tc_score_sorted_staged_kernel<<<(uint32_t)sh.sm_count, 32 * nm::kTcRsWarps,
-                                                    nm::tc_rescore_staged_smem(), stream>>>(sp, so.sorted,
-                                                                                            so.total);
-            else
-                nm::tc_score_sorted_kernel<<<(uint32_t)sh.sm_count * 8u, 256, 0, stream>>>(sp, so.sorted,
-                                                                                          so.total);
+            nm::tc_score_sorted_kernel<<<(uint32_t)sh.sm_count * 8u, 256, 0, stream>>>(sp, so.sorted,
+                                                                                      so.total);
             CUDA_TRY(cudaGetLastError());
             nm::tc_select_kernel<<<nqp, nm::kRowsPerBlock, 0, stream>>>(sp);
             CUDA_TRY(cudaGetLastError());

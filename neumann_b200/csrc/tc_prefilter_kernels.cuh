@@ -1482,137 +1482,6 @@ __global__ void __launch_bounds__(256) tc_score_sorted_kernel(const TcRescorePar
     }
 }
 
-// The same re-score with the rows staged through shared memory (r02).  One thread per entry
-// reading its row 128 bytes at a time makes every warp-wide load touch 32 different DRAM pages:
-// the gather ran at 1.9 TB/s.  Here a WARP owns 32 row-sorted entries; its lanes fetch each of
-// the 32 rows 512 contiguous bytes at a time (cp.async, double buffered) into a padded tile, then
-// every lane walks ITS row's 128 floats from shared memory in the reference's element order
-// (row stride 528 B: the LDS.128 of a quarter warp hit 8 distinct bank groups).
-constexpr uint32_t kTcRsWarps = 4;                     // warps per CTA
-constexpr uint32_t kTcRsChunk = 128;                   // floats per row and stage
-constexpr uint32_t kTcRsRowBytes = kTcRsChunk * 4 + 16;
-constexpr uint32_t kTcRsStageBytes = 32 * kTcRsRowBytes;
-inline size_t tc_rescore_staged_smem() { return (size_t)kTcRsWarps * 2 * kTcRsStageBytes; }
-
-__device__ __forceinline__ void cp_async_16(uint32_t saddr, const void *gptr) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(saddr), "l"(gptr) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() {
-    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
-}
-
-template <int METRIC>
-__device__ __forceinline__ void tc_score_group_staged(const TcRescoreParams &p, const uint2 *sorted,
-                                                      uint32_t base, uint32_t n, uint8_t *tile,
-                                                      uint32_t lane) {
-    // this lane's entry (lanes past the end shadow the last one and do not store)
-    const uint32_t e = min(base + lane, n - 1u);
-    const bool live = base + lane < n;
-    const uint2 ent = sorted[e];
-    const uint32_t row = ent.x, q = ent.y >> 16, slot = ent.y & 0xffffu;
-    const float *qv = p.queries + (size_t)q * p.dim;
-    const float qmag = p.qmeta[q].qmag;
-    const uint32_t dim = p.dim, full = (dim / 8u) * 8u;
-    const uint32_t n_ch = (dim + kTcRsChunk - 1u) / kTcRsChunk;
-    const uint32_t tile_s = smem_u32(tile);
-    auto issue = [&](uint32_t c) {   // rows of all 32 lanes, 512 B each (one row per instruction)
-        const uint32_t col0 = c * kTcRsChunk;
-        const uint32_t cols = min(kTcRsChunk, dim - col0);            // multiple of 4
-        const uint32_t buf = tile_s + (c & 1u) * kTcRsStageBytes;
-#pragma unroll 4
-        for (uint32_t r = 0; r < 32u; ++r) {
-            const uint32_t rr = __shfl_sync(0xffffffffu, row, r);
-            if (lane * 4u < cols)
-                cp_async_16(buf + r * kTcRsRowBytes + lane * 16u,
-                            p.rows + (size_t)rr * p.pitch + col0 + lane * 4u);
-        }
-        cp_async_commit();
-    };
-    RowAcc<METRIC> acc;
-    acc.reset();
-    float l2 = 0.0f, dot = 0.0f, ssq = 0.0f;
-    bool folded = false;
-    issue(0);
-    for (uint32_t c = 0; c < n_ch; ++c) {
-        if (c + 1u < n_ch) {
-            issue(c + 1u);
-            cp_async_wait<1>();
-        } else {
-            cp_async_wait<0>();
-        }
-        __syncwarp();
-        const uint32_t col0 = c * kTcRsChunk;
-        const uint32_t cols = min(kTcRsChunk, dim - col0);
-        const float4 *xs = reinterpret_cast<const float4 *>(tile + (c & 1u) * kTcRsStageBytes +
-                                                            lane * kTcRsRowBytes);
-        const float4 *qq = reinterpret_cast<const float4 *>(qv + col0);
-        const uint32_t n4_full = (min(col0 + cols, full) - min(col0, full)) / 4u;  // float4s in whole f32x8 groups
-#pragma unroll 4
-        for (uint32_t j = 0; j < n4_full; j += 2u) {
-            acc.template step<0>(xs[j], __ldg(qq + j));
-            acc.template step<1>(xs[j + 1u], __ldg(qq + j + 1u));
-        }
-        if (col0 + cols > full) {
-            // the dim % 8 tail (4 elements: dim % 4 == 0 here) comes after the lane fold
-            if (METRIC == kEuclidean) {
-                l2 = acc.d[0];
-            } else {
-                dot = fold_lanes(acc.d);
-                if (METRIC == kCosine) ssq = fold_lanes(acc.s);
-            }
-            folded = true;
-            const float *xt = reinterpret_cast<const float *>(xs) + (full - col0);
-            const float *qt = qv + full;
-            for (uint32_t i = 0; i < dim - full; ++i) {
-                const float xi = xt[i];
-                if (METRIC == kEuclidean) {
-                    const float df = __fsub_rn(__ldg(qt + i), xi);
-                    l2 = __fadd_rn(l2, __fmul_rn(df, df));
-                } else {
-                    dot = __fadd_rn(dot, __fmul_rn(__ldg(qt + i), xi));
-                    if (METRIC == kCosine) ssq = __fadd_rn(ssq, __fmul_rn(xi, xi));
-                }
-            }
-        }
-        __syncwarp();  // the buffer is refilled two iterations later
-    }
-    if (!folded) {
-        if (METRIC == kEuclidean) {
-            l2 = acc.d[0];
-        } else {
-            dot = fold_lanes(acc.d);
-            if (METRIC == kCosine) ssq = fold_lanes(acc.s);
-        }
-    }
-    float sc;
-    if (METRIC == kEuclidean) {
-        sc = tc_l2_score(l2);
-    } else if (METRIC == kDot) {
-        sc = dot;
-    } else {
-        const float rmag = __fsqrt_rn(ssq);
-        sc = (qmag == 0.0f || rmag == 0.0f) ? 0.0f : __fdiv_rn(dot, __fmul_rn(qmag, rmag));
-    }
-    if (live) p.exact_keys[(size_t)q * kTcKeptCap + slot] = make_key(__float_as_uint(sc), row);
-}
-
-__global__ void __launch_bounds__(32 * kTcRsWarps)
-tc_score_sorted_staged_kernel(const TcRescoreParams p, const uint2 *__restrict__ sorted,
-                              const uint32_t *__restrict__ total) {
-    extern __shared__ __align__(16) uint8_t rs_smem[];
-    const uint32_t n = *total;
-    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    uint8_t *tile = rs_smem + (size_t)warp * 2u * kTcRsStageBytes;
-    const uint32_t n_groups = (n + 31u) / 32u;
-    for (uint32_t g = blockIdx.x * kTcRsWarps + warp; g < n_groups; g += gridDim.x * kTcRsWarps) {
-        if (p.metric == kEuclidean) tc_score_group_staged<kEuclidean>(p, sorted, g * 32u, n, tile, lane);
-        else if (p.metric == kCosine) tc_score_group_staged<kCosine>(p, sorted, g * 32u, n, tile, lane);
-        else tc_score_group_staged<kDot>(p, sorted, g * 32u, n, tile, lane);
-    }
-}
-
 __global__ void __launch_bounds__(kRowsPerBlock) tc_select_kernel(const TcRescoreParams p) {
     __shared__ __align__(16) uint64_t buf[kCandCap];
     __shared__ uint64_t thr_s;
