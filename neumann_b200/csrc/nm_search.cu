@@ -715,14 +715,16 @@ int nm_search_device(nm_index *idx, const float *d_queries, uint32_t nq, uint32_
         Workspace *w;
         ~PipeReset() { w->pipeline_next = false; }
     } pipe_reset{ws};
-    if (collective && stream_v) {
-        // the peer exchange and NCCL order collective searches by one stream: when the caller
-        // switches streams, the earlier stream's searches have to be finished first
-        std::lock_guard<std::mutex> cg(idx->comm_mu);
+    // The peer exchange and NCCL order collective searches by ONE stream: when the caller
+    // switches streams, the earlier stream's searches are finished first (called with comm_mu
+    // held, in the same critical section that enqueues the search).
+    auto adopt_stream = [&]() -> int {
+        if (!stream_v) return NM_OK;
         if (idx->xchg_async_stream && idx->xchg_async_stream != stream)
             CUDA_TRY(cudaStreamSynchronize(idx->xchg_async_stream));
         idx->xchg_async_stream = stream;
-    }
+        return NM_OK;
+    };
     std::pair<cudaEvent_t, cudaEvent_t> *prof = nullptr;
     if (idx->profiling.load() && sh.rows) {
         if (ws->prof_used == ws->prof_events.size()) {
@@ -759,12 +761,16 @@ int nm_search_device(nm_index *idx, const float *d_queries, uint32_t nq, uint32_
     } else if (collective_uses_fused_exchange(idx, nq, k, metric)) {
         // (collective calls on one index must be issued in the same order on every rank)
         std::lock_guard<std::mutex> cg(idx->comm_mu);
+        rc = adopt_stream();
+        if (rc) return rc;
         rc = collective_fused(idx, sh, *ws, d_queries, nq, k, metric, d_out_rows, d_out_scores,
                               d_out_counts, stream);
         if (rc) return rc;
         if (prof) CUDA_TRY(cudaEventRecord(prof->second, stream));
     } else {
         std::lock_guard<std::mutex> cg(idx->comm_mu);
+        rc = adopt_stream();
+        if (rc) return rc;
         if (sh.rows == 0) {
             CUDA_TRY(cudaMemsetAsync(ws->d_hits, 0, (size_t)nq * k * sizeof(nm::ShardHit), stream));
         } else {
