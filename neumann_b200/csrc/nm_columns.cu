@@ -226,10 +226,15 @@ int shard_mask(nm_index *idx, Shard &sh, Workspace &ws, const MaskSpec &spec, ui
         memcpy(key.data() + (size_t)spec.n_ops * sizeof(nm_filter_op), spec.tables,
                (size_t)spec.n_table_words * 4);
     const uint64_t epoch = idx->mutation_epoch.load();
+    const size_t ops_bytes = (size_t)spec.n_ops * sizeof(nm::FilterOpDev);
+    const size_t tab_bytes = (size_t)spec.n_table_words * 4;
+    std::shared_ptr<MaskEntry> e;
     {
         std::lock_guard<std::mutex> g(sh.mask_mu);
         for (auto it = sh.mask_cache.begin(); it != sh.mask_cache.end();) {
             if ((*it)->epoch != epoch) {
+                // stale: keep its buffers for the next new filter unless a search still holds it
+                if (it->use_count() == 1 && sh.mask_free.size() < 4) sh.mask_free.push_back(*it);
                 it = sh.mask_cache.erase(it);
                 continue;
             }
@@ -239,6 +244,13 @@ int shard_mask(nm_index *idx, Shard &sh, Workspace &ws, const MaskSpec &spec, ui
             }
             ++it;
         }
+        if (!*hold)
+            for (auto it = sh.mask_free.begin(); it != sh.mask_free.end(); ++it)
+                if ((*it)->words_cap >= words && (*it)->prog_cap >= ops_bytes + tab_bytes + 16) {
+                    e = *it;
+                    sh.mask_free.erase(it);
+                    break;
+                }
     }
     if (*hold) {
         idx->filter_mask_hits++;
@@ -246,15 +258,19 @@ int shard_mask(nm_index *idx, Shard &sh, Workspace &ws, const MaskSpec &spec, ui
         *d_mask = (*hold)->d_mask;
         return NM_OK;
     }
-    std::shared_ptr<MaskEntry> e(new MaskEntry());
-    e->device = sh.device;
+    if (!e) {
+        e.reset(new MaskEntry());
+        e->device = sh.device;
+        // sized for the shard's capacity and a full-size program: recycled across filters
+        e->words_cap = (((size_t)std::max<uint64_t>(sh.capacity, sh.rows) + 255) / 256) * 8;
+        e->prog_cap = std::max<size_t>(ops_bytes + tab_bytes + 16,
+                                       nm::kFilterMaxOps * sizeof(nm::FilterOpDev) + 4096);
+        CUDA_TRY(cudaMalloc(&e->d_mask, e->words_cap * 4));
+        CUDA_TRY(cudaMalloc(&e->d_prog, e->prog_cap));
+        CUDA_TRY(cudaEventCreateWithFlags(&e->ready, cudaEventDisableTiming));
+    }
     e->epoch = epoch;
     e->words = words;
-    const size_t ops_bytes = (size_t)spec.n_ops * sizeof(nm::FilterOpDev);
-    const size_t tab_bytes = (size_t)spec.n_table_words * 4;
-    CUDA_TRY(cudaMalloc(&e->d_mask, words * 4));
-    CUDA_TRY(cudaMalloc(&e->d_prog, ops_bytes + tab_bytes + 16));
-    CUDA_TRY(cudaEventCreateWithFlags(&e->ready, cudaEventDisableTiming));
     const uint32_t *d_tables = reinterpret_cast<const uint32_t *>(static_cast<uint8_t *>(e->d_prog) + ops_bytes);
     std::vector<nm::FilterOpDev> ops(spec.n_ops);
     for (uint32_t i = 0; i < spec.n_ops; ++i) {
@@ -291,7 +307,11 @@ int shard_mask(nm_index *idx, Shard &sh, Workspace &ws, const MaskSpec &spec, ui
     e->key.swap(key);
     {
         std::lock_guard<std::mutex> g(sh.mask_mu);
-        if (sh.mask_cache.size() >= 8) sh.mask_cache.erase(sh.mask_cache.begin());
+        if (sh.mask_cache.size() >= 8) {
+            if (sh.mask_cache.front().use_count() == 1 && sh.mask_free.size() < 4)
+                sh.mask_free.push_back(sh.mask_cache.front());
+            sh.mask_cache.erase(sh.mask_cache.begin());
+        }
         sh.mask_cache.push_back(e);
     }
     *hold = e;

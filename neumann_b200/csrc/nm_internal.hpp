@@ -187,6 +187,8 @@ struct MaskEntry {
     uint64_t epoch = 0;         // nm_index::mutation_epoch it was computed at
     uint32_t *d_mask = nullptr; // [words] u32, padded to whole row blocks
     size_t words = 0;
+    size_t words_cap = 0;       // allocation sizes: stale entries are recycled, not freed (a
+    size_t prog_cap = 0;        // cudaMalloc / cudaFree pair per new filter cost ~5 ms at 10M rows)
     void *d_prog = nullptr;     // FilterOpDev[] followed by the string tables
     cudaEvent_t ready = nullptr;
     ~MaskEntry() {
@@ -234,6 +236,7 @@ struct Shard {
     std::map<uint32_t, std::unique_ptr<Column>> columns;
     std::mutex mask_mu;
     std::vector<std::shared_ptr<MaskEntry>> mask_cache;
+    std::vector<std::shared_ptr<MaskEntry>> mask_free;  // buffers of stale masks, for reuse
     cudaStream_t copy_stream = nullptr;
     float *staging[2] = {nullptr, nullptr};
     cudaEvent_t staging_done[2] = {nullptr, nullptr};

@@ -675,6 +675,16 @@ int scan_queries_tc(nm_index *idx, const Shard &sh, Workspace &ws, const float *
         rp.dim = dim;
         rp.k = k_eff;
         rp.metric = kmetric;
+        static const uint32_t grow0 = [] {
+            const char *e = getenv("NM_TC_GROW0");
+            return e ? (uint32_t)std::max(1, atoi(e)) : 4u;
+        }();
+        static const uint32_t allow_mul = [] {
+            const char *e = getenv("NM_TC_ALLOW");
+            return e ? (uint32_t)std::max(1, atoi(e)) : 1u;
+        }();
+        rp.grow0 = grow0;
+        rp.allow_mul = allow_mul;
         for (uint32_t ph = 0; ph < kTcMaxPhases; ++ph) {
             if (pair) {
                 cudaLaunchConfig_t cfg = {};

@@ -1055,6 +1055,8 @@ struct TcRefineParams {
     uint32_t dim;
     uint32_t k;
     int metric;
+    uint32_t grow0;      // row-range growth after the first phase (its pass rate says nothing)
+    uint32_t allow_mul;  // the pass rate is assumed to drop at least this much from phase to phase
 };
 
 constexpr uint32_t kTcTopCap = 2048;  // >= kMaxFastK; entries re-scored per refine at most
@@ -1297,7 +1299,7 @@ __global__ void __launch_bounds__(256) tc_refine_kernel(const TcRefineParams p) 
         if (!(qm.flags & (kTcFlagUnusable | kTcFlagOverflow))) {
             const uint64_t added = n > prev ? n - prev : 1u;
             const uint64_t room = (kTcKeptCap - m) / 2u;
-            const uint64_t allowed = room * (uint64_t)(row_end - row_begin) / added;
+            const uint64_t allowed = (uint64_t)p.allow_mul * room * (uint64_t)(row_end - row_begin) / added;
             atomicMin(&p.ctl->next_rows, allowed < 0xfffffff0ull ? (uint32_t)allowed : 0xfffffff0u);
         }
         __threadfence();
@@ -1306,7 +1308,7 @@ __global__ void __launch_bounds__(256) tc_refine_kernel(const TcRefineParams p) 
             unsigned long long span = *reinterpret_cast<volatile uint32_t *>(&p.ctl->next_rows);
             // the first phase keeps everything, so its pass rate says nothing: grow 4x;
             // afterwards at least 8 Ki rows and at most 15x what has been seen so far
-            if (row_begin == 0u) span = 4ull * row_end;
+            if (row_begin == 0u) span = (unsigned long long)p.grow0 * row_end;
             if (span < 8192ull) span = 8192ull;
             if (span > 15ull * row_end) span = 15ull * row_end;
             const unsigned long long nb = row_end;
