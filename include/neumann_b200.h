@@ -309,7 +309,8 @@ int nm_index_set_prefilter(nm_index *idx, int mode);
 int nm_index_set_tensor_core(nm_index *idx, int enable);
 /* Diagnostics: the exact integer dot products the tensor-core pass computes,
  * out[q * rows + r] = sum_i int8(row r)[i] * int8(query q)[i], for the first min(nq, 256)
- * queries (host buffers).  Needs the pre-filter ON and a single-device index. */
+ * queries (host buffers).  Needs the int8 copy (pre-filter mode 1, or mode 2 after a first
+ * eligible batch) and a single-device index. */
 int nm_debug_tc_dots(nm_index *idx, const float *queries, uint32_t nq, int32_t *out);
 /* Diagnostics: the int8 copy of row `row` and its scale (x ~ scale * int8). */
 int nm_debug_q8_row(nm_index *idx, uint64_t row, int8_t *out_q8, float *out_scale);

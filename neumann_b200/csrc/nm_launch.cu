@@ -579,7 +579,7 @@ static int ws_ensure_tc(Workspace &ws, uint32_t dim, uint32_t nq, cudaStream_t s
 }
 
 // One pass per 256 queries: prepare, then kTcMaxPhases (gemm, refine) pairs whose row ranges
-// are chosen ON DEVICE (first 16 Ki rows keep everything; each refine sizes the next range
+// are chosen ON DEVICE (the first 2048 rows keep everything; each refine sizes the next range
 // from the pass rate it saw; pairs past the end exit at once), then the exact re-score.
 constexpr uint32_t kTcMaxPhases = 12;
 

@@ -583,7 +583,7 @@ int nm_debug_tc_dots(nm_index *idx, const float *queries, uint32_t nq, int32_t *
     Shard &sh = *idx->shards[0];
     nq = std::min<uint32_t>(nq, 256u);
     if (!sh.tmap8_valid || sh.q8_rows != sh.rows || sh.rows == 0)
-        return fail(NM_ERR_CONFIGURATION, "nm_debug_tc_dots needs the pre-filter on");
+        return fail(NM_ERR_CONFIGURATION, "nm_debug_tc_dots needs the int8 copy (nm_index_set_prefilter(idx, 1))");
     CUDA_TRY(cudaSetDevice(sh.device));
     std::unique_ptr<Workspace> ws;
     int rc = ws_acquire(sh, ws);
