@@ -128,3 +128,40 @@ def test_search_during_growth():
         got = [int(x) for x in r]
         assert any(got == topk_of[m] for m in topk_of if m >= n_before), (n_before, got)
     idx.close()
+
+
+def test_realloc_fallback_without_vmm():
+    """NM_NO_VMM=1 (or a driver without virtual memory management) keeps the r01 growth strategy —
+    a larger cudaMalloc and one copy.  Same results; shard_info says which strategy is active."""
+    import subprocess
+    import sys
+    from pathlib import Path
+    root = Path(__file__).resolve().parent.parent
+    code = r'''
+import sys
+sys.path.insert(0, "ROOT"); sys.path.insert(0, "ROOT/tests")
+import numpy as np
+import oracle_ffi as o
+from neumann_b200 import DeviceIndex
+d = 40
+rows = o.fill_synthetic(90_000, d, 7)
+idx = DeviceIndex(d)
+idx.load(rows[:10])
+n = 10
+for step in (1, 500, 20_000, 69_489):
+    idx.append(rows[n:n + step]); n += step
+info = idx.shard_info()
+assert info.grows_in_place == 0 and info.rows == n == 90_000, (info.grows_in_place, info.rows)
+idx.column_set(2, 0, np.full(n, 3, np.uint8), np.arange(n, dtype=np.uint64))
+q = o.fill_synthetic(1, d, 8)[0]
+for metric in ("cosine", "euclidean", "dot"):
+    ((r, s),) = idx.search(q, 10, metric)
+    er, es = o.search(rows, q, 10, metric, threads=4)
+    assert np.array_equal(r, er) and np.array_equal(s.view(np.uint32), es.view(np.uint32)), metric
+res = idx.search(rows[:4], 5, "euclidean")          # a batch: int8 copy in plain buffers too
+assert all(int(res[i][0][0]) == i for i in range(4))
+print("FALLBACK_OK")
+'''.replace("ROOT", str(root))
+    env = dict(__import__("os").environ, NM_NO_VMM="1")
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "FALLBACK_OK" in r.stdout, (r.stdout[-400:], r.stderr[-800:])
