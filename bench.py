@@ -214,6 +214,20 @@ def oracle_shard_topk(idx, n_local, global_lo, queries, k, metric, threads, seed
 
 def parity_check(idx, n_local, global_lo, total_rows, queries, k, metric, gpu_results, seed,
                  world, rank, label):
+    """parity_check_core, with infrastructure failures (host RAM for the chunk buffer, a broken
+    oracle build ...) reported as {"ok": false, "error": ...} instead of losing the whole line."""
+    try:
+        return parity_check_core(idx, n_local, global_lo, total_rows, queries, k, metric, gpu_results,
+                                 seed, world, rank, label)
+    except Exception as e:  # noqa: BLE001
+        if world > 1:
+            raise        # the other ranks are inside a collective: fail loudly rather than hang
+        return {"ok": False, "ids_equal": False, "score_bits_equal": False, "queries": int(len(queries)),
+                "oracle_rows": 0, "error": repr(e), "what": label}
+
+
+def parity_check_core(idx, n_local, global_lo, total_rows, queries, k, metric, gpu_results, seed,
+                      world, rank, label):
     """gpu_results: {name: list over queries of (rows u64[], scores f32[])} as seen on this rank
     (every rank holds the merged result).  Returns the parity object on rank 0, None elsewhere."""
     import numpy as np
