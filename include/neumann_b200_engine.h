@@ -30,6 +30,7 @@ typedef struct nm_engine_config {
     int devices[8];
     int device_prefilter;        /* 1 = int8 copy of every mirror: dp4a / tensor-core pre-filters
                                     (bit-identical results; device-side addition, default 0) */
+    uint64_t max_keys_per_scan;  /* 0 = None (lib.rs:638): bounds list_keys / clear */
 } nm_engine_config;
 
 void nm_engine_config_default(nm_engine_config *cfg);
@@ -92,6 +93,22 @@ int nm_engine_count_matching(nm_engine *e, const char *where_expr, uint64_t *out
  * the full length; `out` (may be NULL) receives at most out_cap - 1 bytes + NUL. */
 int nm_engine_debug_filter_program(nm_engine *e, uint32_t dim, const char *where_expr, char *out,
                                    size_t out_cap, size_t *out_len);
+/* Metadata maintenance (vector_engine/src/lib.rs:3346-3420); `metadata_wire` as for
+ * nm_engine_store_embedding_with_metadata.  The device-side metadata columns follow at the next
+ * filtered search. */
+int nm_engine_update_metadata(nm_engine *e, const char *key, const char *metadata_wire);
+int nm_engine_remove_metadata_field(nm_engine *e, const char *key, const char *field);
+int nm_engine_has_metadata_field(nm_engine *e, const char *key, const char *field);
+/* lib.rs:2340-2354, 2924-2940: *out = embeddings deleted (clear: at most max_keys_per_scan per
+ * call).  keys_wire = keys separated by 0x1f. */
+int nm_engine_clear(nm_engine *e, uint64_t *out);
+int nm_engine_batch_delete_embeddings(nm_engine *e, const char *keys_wire, uint64_t *out);
+/* lib.rs:2988-3058: search_similar / search_entities (entities != 0) with pagination.  limit < 0 =
+ * no limit.  *total_count receives the number of ranked hits when count_total != 0 (else
+ * UINT64_MAX); *has_more as the reference computes it. */
+int nm_engine_search_paginated(nm_engine *e, int entities, const float *query, size_t n, size_t top_k,
+                               size_t skip, int64_t limit, int count_total, nm_results **out,
+                               uint64_t *total_count, int *has_more);
 /* PointsService::query post-processing (neumann_server/src/service/points.rs:449-485);
  * score_threshold is ignored when has_threshold == 0. */
 int nm_engine_query_points(nm_engine *e, const char *collection, const float *vector, size_t n,

@@ -77,6 +77,7 @@ int nm_engine_create(const nm_engine_config *cfg, nm_engine **out) {
             c.search_timeout = std::chrono::milliseconds(cfg->search_timeout_ms);
         for (int i = 0; i < cfg->n_devices && i < 8; ++i) c.devices.push_back(cfg->devices[i]);
         c.device_prefilter = cfg->device_prefilter != 0;
+        if (cfg->max_keys_per_scan) c.max_keys_per_scan = (size_t)cfg->max_keys_per_scan;
     }
     auto r = VectorEngine::with_config(std::move(c));
     if (r.is_err()) return fail(r.error());
@@ -278,6 +279,74 @@ int nm_engine_count_matching(nm_engine *e, const char *where_expr, uint64_t *out
     FilterCondition f;
     if (!parse_filter_arg(where_expr, &f)) return NM_ERR_INVALID_ARGUMENT;
     *out = e->engine->count_matching(f);
+    return NM_OK;
+}
+
+int nm_engine_update_metadata(nm_engine *e, const char *key, const char *metadata_wire) {
+    if (!e || !key) return fail(NM_ERR_INVALID_ARGUMENT, "null argument");
+    Metadata m;
+    std::string perr;
+    if (!parse_metadata_wire(metadata_wire ? metadata_wire : "", &m, &perr))
+        return fail(NM_ERR_INVALID_ARGUMENT, perr);
+    auto r = e->engine->update_metadata(key, m);
+    return r.is_err() ? fail(r.error()) : NM_OK;
+}
+
+int nm_engine_remove_metadata_field(nm_engine *e, const char *key, const char *field) {
+    if (!e || !key || !field) return fail(NM_ERR_INVALID_ARGUMENT, "null argument");
+    auto r = e->engine->remove_metadata_field(key, field);
+    return r.is_err() ? fail(r.error()) : NM_OK;
+}
+
+int nm_engine_has_metadata_field(nm_engine *e, const char *key, const char *field) {
+    return e && key && field && e->engine->has_metadata_field(key, field);
+}
+
+int nm_engine_clear(nm_engine *e, uint64_t *out) {
+    if (!e) return fail(NM_ERR_INVALID_ARGUMENT, "null argument");
+    auto r = e->engine->clear();
+    if (r.is_err()) return fail(r.error());
+    if (out) *out = r.value();
+    return NM_OK;
+}
+
+int nm_engine_batch_delete_embeddings(nm_engine *e, const char *keys_wire, uint64_t *out) {
+    if (!e || !keys_wire) return fail(NM_ERR_INVALID_ARGUMENT, "null argument");
+    std::vector<std::string> keys;
+    std::string w(keys_wire);
+    size_t pos = 0;
+    while (pos <= w.size()) {
+        size_t end = w.find('\x1f', pos);
+        if (end == std::string::npos) end = w.size();
+        if (end > pos) keys.push_back(w.substr(pos, end - pos));
+        pos = end + 1;
+    }
+    auto r = e->engine->batch_delete_embeddings(keys);
+    if (r.is_err()) return fail(r.error());
+    if (out) *out = r.value();
+    return NM_OK;
+}
+
+int nm_engine_search_paginated(nm_engine *e, int entities, const float *query, size_t n, size_t top_k,
+                               size_t skip, int64_t limit, int count_total, nm_results **out,
+                               uint64_t *total_count, int *has_more) {
+    if (!e) return fail(NM_ERR_INVALID_ARGUMENT, "null argument");
+    if (out) *out = nullptr;
+    std::vector<float> q(query, query + (query ? n : 0));
+    VectorEngine::Pagination pg;
+    pg.skip = skip;
+    if (limit >= 0) pg.limit = (size_t)limit;
+    pg.count_total = count_total != 0;
+    auto r = entities ? e->engine->search_entities_paginated(q, top_k, pg)
+                      : e->engine->search_similar_paginated(q, top_k, pg);
+    if (r.is_err()) return fail(r.error());
+    if (total_count) *total_count = r.value().total_count ? (uint64_t)*r.value().total_count : UINT64_MAX;
+    if (has_more) *has_more = r.value().has_more ? 1 : 0;
+    if (out) {
+        auto *res = new nm_results();
+        res->hits = std::move(r.value().items);
+        *out = res;
+    }
     return NM_OK;
 }
 

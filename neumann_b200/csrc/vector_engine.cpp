@@ -864,6 +864,154 @@ Result<Metadata> VectorEngine::get_metadata(const std::string &key) const {
     return sp.buckets.at(it->second.first)->meta[it->second.second];
 }
 
+Result<Unit> VectorEngine::update_metadata(const std::string &key, const Metadata &metadata) {
+    Space &sp = *default_space_;
+    std::unique_lock<std::shared_mutex> g(sp.mu);
+    auto it = sp.where.find(key);
+    if (it == sp.where.end()) return err(ErrorKind::NotFound, key);
+    Bucket &b = *sp.buckets.at(it->second.first);
+    const uint64_t row = it->second.second;
+    for (auto &kv : metadata) b.meta[row][kv.first] = kv.second;
+    if (row < b.cols_synced_rows) b.meta_dirty.push_back(row);
+    return Unit{};
+}
+
+Result<Unit> VectorEngine::remove_metadata_field(const std::string &key, const std::string &field) {
+    Space &sp = *default_space_;
+    std::unique_lock<std::shared_mutex> g(sp.mu);
+    auto it = sp.where.find(key);
+    if (it == sp.where.end()) return err(ErrorKind::NotFound, key);
+    Bucket &b = *sp.buckets.at(it->second.first);
+    const uint64_t row = it->second.second;
+    if (b.meta[row].erase(field) && row < b.cols_synced_rows) b.meta_dirty.push_back(row);
+    return Unit{};
+}
+
+bool VectorEngine::has_metadata_field(const std::string &key, const std::string &field) const {
+    const Space &sp = *default_space_;
+    std::shared_lock<std::shared_mutex> g(sp.mu);
+    auto it = sp.where.find(key);
+    if (it == sp.where.end()) return false;
+    return sp.buckets.at(it->second.first)->meta[it->second.second].count(field) != 0;
+}
+
+Result<std::optional<MetadataValue>> VectorEngine::get_metadata_field(const std::string &key,
+                                                                      const std::string &field) const {
+    const Space &sp = *default_space_;
+    std::shared_lock<std::shared_mutex> g(sp.mu);
+    auto it = sp.where.find(key);
+    if (it == sp.where.end()) return err(ErrorKind::NotFound, key);
+    const Metadata &m = sp.buckets.at(it->second.first)->meta[it->second.second];
+    auto f = m.find(field);
+    if (f == m.end()) return std::optional<MetadataValue>{};
+    return std::optional<MetadataValue>{f->second};
+}
+
+// lib.rs:2312-2354.  The reference lists keys in HashSet order; here: bucket by bucket, row order.
+std::vector<std::string> VectorEngine::list_keys() const { return list_keys_bounded(); }
+
+std::vector<std::string> VectorEngine::list_keys_bounded() const {
+    const size_t limit = config_.max_keys_per_scan.value_or(SIZE_MAX);
+    std::vector<std::string> out;
+    std::shared_lock<std::shared_mutex> g(default_space_->mu);
+    for (auto &kv : default_space_->buckets)
+        for (auto &k : kv.second->keys) {
+            if (out.size() >= limit) return out;
+            out.push_back(k);
+        }
+    return out;
+}
+
+Result<size_t> VectorEngine::clear() {
+    // up to max_keys_per_scan embeddings per call (lib.rs:2340-2354): call again until 0 comes back
+    {
+        Space &sp = *default_space_;
+        std::unique_lock<std::shared_mutex> g(sp.mu);
+        const size_t total = sp.where.size();
+        if (total <= config_.max_keys_per_scan.value_or(SIZE_MAX)) {
+            sp.buckets.clear();  // everything goes: drop the buckets and their device mirrors wholesale
+            sp.where.clear();
+            return total;
+        }
+    }
+    std::vector<std::string> keys = list_keys_bounded();
+    for (auto &k : keys) {
+        auto r = delete_in_space(*default_space_, k);
+        if (r.is_err() && r.error().kind != ErrorKind::NotFound) return r.error();
+    }
+    return keys.size();
+}
+
+Result<size_t> VectorEngine::batch_delete_embeddings(const std::vector<std::string> &keys) {
+    size_t deleted = 0;
+    for (auto &k : keys)
+        if (delete_in_space(*default_space_, k).is_ok()) ++deleted;  // missing keys are skipped
+    return deleted;
+}
+
+namespace {
+// lib.rs:2994-3020 / 3033-3058, shared by the two paginated searches
+template <class Paged, class Pag>
+Paged paginate_hits(std::vector<SearchResult> results, const Pag &pg) {
+    Paged out;
+    if (pg.count_total) out.total_count = results.size();
+    for (size_t i = pg.skip; i < results.size(); ++i) {
+        if (pg.limit && out.items.size() >= *pg.limit) break;
+        out.items.push_back(std::move(results[i]));
+    }
+    out.has_more = false;
+    if (pg.limit && out.total_count) {
+        size_t end = pg.skip + out.items.size();
+        if (end < pg.skip) end = SIZE_MAX;  // saturating_add
+        out.has_more = end < *out.total_count;
+    }
+    return out;
+}
+size_t paginated_fetch(size_t top_k, size_t skip, const std::optional<size_t> &limit) {
+    size_t need = skip + limit.value_or(top_k);
+    if (need < skip) need = SIZE_MAX;  // saturating_add
+    return std::min(need, top_k);
+}
+}  // namespace
+
+Result<VectorEngine::PagedResult<SearchResult>> VectorEngine::search_similar_paginated(
+    const std::vector<float> &query, size_t top_k, Pagination pagination) const {
+    auto r = search_similar(query, paginated_fetch(top_k, pagination.skip, pagination.limit));
+    if (r.is_err()) return r.error();
+    return paginate_hits<PagedResult<SearchResult>>(std::move(r.value()), pagination);
+}
+
+Result<VectorEngine::PagedResult<SearchResult>> VectorEngine::search_entities_paginated(
+    const std::vector<float> &query, size_t top_k, Pagination pagination) const {
+    auto r = search_entities(query, paginated_fetch(top_k, pagination.skip, pagination.limit));
+    if (r.is_err()) return r.error();
+    return paginate_hits<PagedResult<SearchResult>>(std::move(r.value()), pagination);
+}
+
+bool VectorEngine::exists_in_collection(const std::string &collection, const std::string &key) const {
+    std::shared_ptr<const Space> sp = find_collection_space(collection);
+    if (!sp) return false;
+    std::shared_lock<std::shared_mutex> g(sp->mu);
+    return sp->where.count(key) != 0;
+}
+
+std::vector<std::string> VectorEngine::list_collection_keys(const std::string &collection) const {
+    std::vector<std::string> out;
+    std::shared_ptr<const Space> sp = find_collection_space(collection);
+    if (!sp) return out;
+    std::shared_lock<std::shared_mutex> g(sp->mu);
+    for (auto &kv : sp->buckets)
+        for (auto &k : kv.second->keys) out.push_back(k);
+    return out;
+}
+
+std::optional<VectorCollectionConfig> VectorEngine::get_collection_config(const std::string &name) const {
+    std::shared_lock<std::shared_mutex> g(collections_mu_);
+    auto it = collections_.find(name);
+    if (it == collections_.end()) return std::nullopt;
+    return it->second->config;
+}
+
 Result<Unit> VectorEngine::store_in_collection_with_metadata(const std::string &collection,
                                                              const std::string &key,
                                                              std::vector<float> vector,

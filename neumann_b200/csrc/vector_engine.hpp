@@ -128,6 +128,12 @@ class VectorEngine {
     bool exists(const std::string &key) const;
     size_t count() const;
     std::optional<size_t> dimension() const;
+    // lib.rs:2312-2354, 2924-2940: key listing, clear and batch delete (respecting
+    // max_keys_per_scan like the reference); deletes maintain the device mirror by swap-remove.
+    std::vector<std::string> list_keys() const;
+    std::vector<std::string> list_keys_bounded() const;
+    Result<size_t> clear();
+    Result<size_t> batch_delete_embeddings(const std::vector<std::string> &keys);
     // lib.rs:2865-2913 (validation first, then stores; returns number stored)
     Result<size_t> batch_store_embeddings(
         const std::vector<std::pair<std::string, std::vector<float>>> &items);
@@ -151,6 +157,13 @@ class VectorEngine {
     Result<Unit> store_embedding_with_metadata(const std::string &key, std::vector<float> vector,
                                                Metadata metadata);
     Result<Metadata> get_metadata(const std::string &key) const;
+    // lib.rs:3346-3420: merge fields into / remove a field from an embedding's metadata.  The
+    // device-side metadata columns follow at the next filtered search.
+    Result<Unit> update_metadata(const std::string &key, const Metadata &metadata);
+    Result<Unit> remove_metadata_field(const std::string &key, const std::string &field);
+    bool has_metadata_field(const std::string &key, const std::string &field) const;
+    Result<std::optional<MetadataValue>> get_metadata_field(const std::string &key,
+                                                            const std::string &field) const;
     Result<std::vector<SearchResult>> search_similar_filtered(
         const std::vector<float> &query, size_t top_k, const FilterCondition &filter,
         std::optional<FilteredSearchConfig> config = std::nullopt) const;
@@ -171,6 +184,22 @@ class VectorEngine {
     Result<std::vector<float>> get_entity_embedding(const std::string &entity_key) const;
     bool entity_has_embedding(const std::string &entity_key) const;
     Result<Unit> remove_entity_embedding(const std::string &entity_key);
+    // lib.rs:1052-1121, 2988-3058: pagination over the ranked hits
+    struct Pagination {
+        size_t skip = 0;
+        std::optional<size_t> limit;
+        bool count_total = false;
+    };
+    template <class T>
+    struct PagedResult {
+        std::vector<T> items;
+        std::optional<size_t> total_count;
+        bool has_more = false;
+    };
+    Result<PagedResult<SearchResult>> search_similar_paginated(const std::vector<float> &query,
+                                                              size_t top_k, Pagination pagination) const;
+    Result<PagedResult<SearchResult>> search_entities_paginated(const std::vector<float> &query,
+                                                               size_t top_k, Pagination pagination) const;
     Result<std::vector<SearchResult>> search_entities(const std::vector<float> &query,
                                                       size_t top_k) const;
 
@@ -201,6 +230,9 @@ class VectorEngine {
                                                    const std::string &key) const;
     Result<Unit> delete_from_collection(const std::string &collection, const std::string &key);
     size_t collection_count(const std::string &collection) const;
+    bool exists_in_collection(const std::string &collection, const std::string &key) const;   // lib.rs:1537
+    std::vector<std::string> list_collection_keys(const std::string &collection) const;       // lib.rs:1543
+    std::optional<VectorCollectionConfig> get_collection_config(const std::string &name) const;  // lib.rs:1412
     Result<std::vector<SearchResult>> search_in_collection(const std::string &collection,
                                                            const std::vector<float> &query,
                                                            size_t top_k) const;

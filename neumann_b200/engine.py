@@ -39,7 +39,7 @@ class NmEngineConfig(C.Structure):
         ("parallel_threshold", C.c_uint64), ("default_metric", C.c_int),
         ("max_dimension", C.c_uint64), ("search_timeout_ms", C.c_int64),
         ("n_devices", C.c_int), ("devices", C.c_int * 8),
-        ("device_prefilter", C.c_int),
+        ("device_prefilter", C.c_int), ("max_keys_per_scan", C.c_uint64),
     ]
 
 
@@ -71,6 +71,13 @@ ENGINE_SIGNATURES = {
     "nm_engine_search_similar_filtered": (C.c_int, [_vp, _vp, _sz, _sz, _cp, C.c_int, _sz, _pvp]),
     "nm_engine_search_filtered_in_collection": (C.c_int, [_vp, _cp, _vp, _sz, _sz, _cp, C.c_int, _sz, _pvp]),
     "nm_engine_count_matching": (C.c_int, [_vp, _cp, C.POINTER(_u64)]),
+    "nm_engine_update_metadata": (C.c_int, [_vp, _cp, _cp]),
+    "nm_engine_remove_metadata_field": (C.c_int, [_vp, _cp, _cp]),
+    "nm_engine_has_metadata_field": (C.c_int, [_vp, _cp, _cp]),
+    "nm_engine_clear": (C.c_int, [_vp, C.POINTER(_u64)]),
+    "nm_engine_batch_delete_embeddings": (C.c_int, [_vp, _cp, C.POINTER(_u64)]),
+    "nm_engine_search_paginated": (C.c_int, [_vp, C.c_int, _vp, _sz, _sz, _sz, C.c_int64, C.c_int, _pvp,
+                                             C.POINTER(_u64), C.POINTER(C.c_int)]),
     "nm_engine_debug_filter_program": (C.c_int, [_vp, C.c_uint32, _cp, _vp, _sz, C.POINTER(_sz)]),
     "nm_engine_query_points": (C.c_int, [_vp, _cp, _vp, _sz, _sz, _sz, C.c_int, C.c_float, _pvp]),
     "nm_engine_set_entity_embedding": (C.c_int, [_vp, _cp, _vp, _sz]),
@@ -144,7 +151,8 @@ def _take(handle: C.c_void_p) -> list[SearchResult]:
 class VectorEngine:
     def __init__(self, *, sparse_threshold: float | None = None, parallel_threshold: int | None = None,
                  max_dimension: int | None = None, search_timeout_ms: int | None = None,
-                 devices: list[int] | None = None, device_prefilter: bool = False):
+                 devices: list[int] | None = None, device_prefilter: bool = False,
+                 max_keys_per_scan: int | None = None):
         l = _lib()
         cfg = NmEngineConfig()
         l.nm_engine_config_default(C.byref(cfg))
@@ -155,6 +163,8 @@ class VectorEngine:
             cfg.parallel_threshold = parallel_threshold
         if max_dimension is not None:
             cfg.max_dimension = max_dimension
+        if max_keys_per_scan is not None:
+            cfg.max_keys_per_scan = max_keys_per_scan
         if search_timeout_ms is not None:
             cfg.search_timeout_ms = search_timeout_ms
         if devices:
@@ -285,6 +295,38 @@ class VectorEngine:
             self._h, collection.encode(), q.ctypes.data, q.size, top_k, where.encode(), strategy,
             oversample_factor, C.byref(h)))
         return _take(h)
+
+    def update_metadata(self, key: str, metadata: dict) -> None:
+        _check(_lib().nm_engine_update_metadata(self._h, key.encode(), encode_metadata(metadata)))
+
+    def remove_metadata_field(self, key: str, field: str) -> None:
+        _check(_lib().nm_engine_remove_metadata_field(self._h, key.encode(), field.encode()))
+
+    def has_metadata_field(self, key: str, field: str) -> bool:
+        return bool(_lib().nm_engine_has_metadata_field(self._h, key.encode(), field.encode()))
+
+    def clear(self) -> int:
+        n = _u64(0)
+        _check(_lib().nm_engine_clear(self._h, C.byref(n)))
+        return int(n.value)
+
+    def batch_delete_embeddings(self, keys) -> int:
+        n = _u64(0)
+        _check(_lib().nm_engine_batch_delete_embeddings(self._h, "\x1f".join(keys).encode(), C.byref(n)))
+        return int(n.value)
+
+    def search_paginated(self, query, top_k: int, skip: int = 0, limit: int | None = None,
+                         count_total: bool = False, entities: bool = False):
+        """-> (items, total_count or None, has_more): search_similar_paginated / search_entities_paginated."""
+        q = _f32(query)
+        h = C.c_void_p()
+        total = _u64(0)
+        more = C.c_int(0)
+        _check(_lib().nm_engine_search_paginated(self._h, 1 if entities else 0, q.ctypes.data, q.size, top_k,
+                                                 skip, -1 if limit is None else limit, 1 if count_total else 0,
+                                                 C.byref(h), C.byref(total), C.byref(more)))
+        items = _take(h)
+        return items, (None if total.value == 0xFFFFFFFFFFFFFFFF else int(total.value)), bool(more.value)
 
     def debug_filter_program(self, dim: int, where: str) -> dict:
         """Columns + compiled postfix program + host verdict per row (JSON; no device involved)."""

@@ -290,3 +290,43 @@ def test_entity_embeddings_host_side():
     with pytest.raises(eng.VectorError) as ei:
         e.search_entities([1.0, 0.0], 0)
     assert ei.value.kind == "InvalidTopK"
+
+
+def test_metadata_maintenance_clear_and_batch_delete_host_side():
+    """vector_engine/src/lib.rs:3346-3420 (update_metadata / remove_metadata_field /
+    has_metadata_field), :2340-2354 (clear, bounded by max_keys_per_scan), :2924-2940
+    (batch_delete_embeddings); reference KATs :5253-5283, :6700-6745.  Host logic only."""
+    e = eng.VectorEngine()
+    e.store_embedding_with_metadata("item", [1.0, 2.0], {"color": "red"})
+    e.update_metadata("item", {"size": "large", "color": "blue"})            # :6700-6736
+    assert e.count_matching("color = 'blue' AND size = 'large'") == 1
+    assert e.count_matching("color = 'red'") == 0
+    assert e.has_metadata_field("item", "size") and not e.has_metadata_field("item", "weight")
+    assert not e.has_metadata_field("nobody", "size")
+    with pytest.raises(eng.VectorError) as ei:
+        e.update_metadata("nonexistent", {})                                  # :6739-6745
+    assert ei.value.kind == "NotFound"
+    e.remove_metadata_field("item", "size")
+    assert not e.has_metadata_field("item", "size") and e.count_matching("EXISTS(size)") == 0
+    with pytest.raises(eng.VectorError) as ei:
+        e.remove_metadata_field("nonexistent", "size")
+    assert ei.value.kind == "NotFound"
+    # batch delete: missing keys are skipped (:5253-5283)
+    for k, v in (("a", [1.0]), ("b", [2.0]), ("c", [3.0])):
+        e.store_embedding(k, v)
+    assert e.batch_delete_embeddings(["a", "b"]) == 2
+    assert e.count() == 2 and e.exists("c") and e.exists("item")
+    assert e.batch_delete_embeddings([]) == 0
+    assert e.batch_delete_embeddings(["c", "nonexistent"]) == 1
+    # clear: everything at once without a bound ...
+    for i in range(7):
+        e.store_embedding(f"k{i}", [float(i), 1.0])
+    assert e.clear() == 8 and e.count() == 0 and e.clear() == 0
+    e.close()
+    # ... and at most max_keys_per_scan per call with one ("call again until 0 is returned")
+    e = eng.VectorEngine(max_keys_per_scan=3)
+    for i in range(8):
+        e.store_embedding(f"k{i}", [float(i), 1.0])
+    assert [e.clear(), e.clear(), e.clear(), e.clear()] == [3, 3, 2, 0]
+    assert e.count() == 0
+    e.close()

@@ -361,3 +361,53 @@ def test_delete_collection_is_safe_against_concurrent_searches_and_stores():
     res = e.search_in_collection("hot", rows[7], 1)
     assert res and res[0].key == "k7"
     e.close()
+
+
+def test_paginated_searches_and_metadata_updates_on_gpu():
+    """search_similar_paginated / search_entities_paginated (vector_engine/src/lib.rs:2988-3058,
+    KATs :5367-5397, :9232-9250) slice the ranked hits of the device scan; update_metadata /
+    remove_metadata_field (:3346-3384) reach the device-side metadata columns before the next
+    filtered search; clear / batch_delete keep the mirror in step."""
+    e = eng.VectorEngine()
+    for i in range(10):
+        e.store_embedding(f"v{i}", [float(i), 0.5])
+    full = e.search_similar([5.0, 0.5], 10)
+    items, total, more = e.search_paginated([5.0, 0.5], 10, skip=0, limit=3, count_total=True)
+    assert [x.key for x in items] == [x.key for x in full[:3]] and total == 3 and not more
+    # (the reference fetches min(skip + limit, top_k) hits and counts THOSE: total == 3, :2994-3003)
+    items, total, more = e.search_paginated([5.0, 0.5], 10, skip=2, limit=3, count_total=True)
+    assert [x.key for x in items] == [x.key for x in full[2:5]] and total == 5 and not more
+    items, total, more = e.search_paginated([5.0, 0.5], 10, skip=4)          # skip only: top_k hits
+    assert [x.key for x in items] == [x.key for x in full[4:]] and total is None and not more
+    items, total, more = e.search_paginated([5.0, 0.5], 4, skip=1, limit=10, count_total=True)
+    assert [x.key for x in items] == [x.key for x in full[1:4]] and total == 4 and not more
+    with pytest.raises(eng.VectorError):
+        e.search_paginated([], 10, limit=3)
+    for i in range(5):
+        e.set_entity_embedding(f"entity:{i}", [float(i), 0.0])
+    items, total, more = e.search_paginated([2.0, 0.0], 5, limit=3, entities=True)   # :9232-9250
+    assert len(items) == 3 and total is None and not more
+    # metadata updates reach the device columns
+    rows = o.fill_synthetic(400, 16, 5)
+    for i in range(400):
+        e.store_embedding_with_metadata(f"m{i}", rows[i], {"grp": i % 4, "tag": "old"})
+    q = rows[7]
+    assert [x.key for x in e.search_similar_filtered(q, 3, "grp = 3", eng.PRE_FILTER)][0] == "m7"
+    e.update_metadata("m7", {"grp": 9, "tag": "new"})
+    hits = e.search_similar_filtered(q, 3, "grp = 3", eng.PRE_FILTER)
+    assert "m7" not in [x.key for x in hits] and all(int(x.key[1:]) % 4 == 3 for x in hits)
+    assert [x.key for x in e.search_similar_filtered(q, 3, "grp = 9 AND tag = 'new'", eng.PRE_FILTER)] == ["m7"]
+    e.remove_metadata_field("m7", "grp")
+    assert e.search_similar_filtered(q, 3, "grp = 9", eng.PRE_FILTER) == []
+    assert [x.key for x in e.search_similar_filtered(q, 3, "tag = 'new'", eng.PRE_FILTER)] == ["m7"]
+    # batch delete + clear keep host and device in step
+    assert e.batch_delete_embeddings([f"m{i}" for i in range(0, 400, 2)] + ["nope"]) == 200
+    hits = e.search_similar(rows[8], 400)
+    assert len(hits) == 200 and all(int(x.key[1:]) % 2 == 1 for x in hits)
+    er, es = o.search(rows[1::2], rows[8], 5, "cosine")
+    assert [x.key for x in hits[:5]] == [f"m{2 * int(i) + 1}" for i in er]
+    assert e.clear() == 210 and e.count() == 0
+    assert e.search_similar(rows[8], 5) == []
+    e.store_embedding("again", rows[3])
+    assert [x.key for x in e.search_similar(rows[3], 5)] == ["again"]
+    e.close()
