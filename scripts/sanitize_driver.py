@@ -28,8 +28,44 @@ for (n, d) in [(3000, 100), (1500, 64), (700, 13)]:
         sub = np.nonzero(mask)[0]
         er, es = o.search(rows[sub], qs[1], 5, m)
         ok &= np.array_equal(g[0], sub[er.astype(np.int64)].astype(np.uint64))
+    # r02: device-evaluated filter over metadata columns, column moves on swap-remove
+    from neumann_b200._ffi import NM_C_GE, NM_C_LT, NM_F_AND, NM_F_CMP, NM_F_EXISTS, NM_F_OR, NM_V_FLOAT, NM_V_INT, NmFilterOp
+    import struct
+    vals = (np.arange(n) * 7 % 11).astype(np.uint64)
+    tags = np.where(np.arange(n) % 5 == 0, 0, 3).astype(np.uint8)          # every 5th row: field missing
+    idx.column_set(1, 0, tags, vals)
+    prog = [NmFilterOp(kind=NM_F_CMP, cmp=NM_C_LT, lit_tag=NM_V_INT, column=1, lit=4),
+            NmFilterOp(kind=NM_F_CMP, cmp=NM_C_GE, lit_tag=NM_V_FLOAT, column=1,
+                       lit=struct.unpack("<Q", struct.pack("<d", 9.5))[0]),
+            NmFilterOp(kind=NM_F_OR), NmFilterOp(kind=NM_F_EXISTS, column=1), NmFilterOp(kind=NM_F_AND)]
+    keep = (tags == 3) & ((vals < 4) | (vals >= 10))
+    ok &= np.array_equal(idx.filter_mask(prog), keep)
+    sub = np.nonzero(keep)[0]
+    for m in ("cosine", "euclidean"):
+        res = idx.search_filtered(qs[:2], 6, m, prog)
+        for i in range(2):
+            er, es = o.search(rows[sub], qs[i], 6, m)
+            ok &= np.array_equal(res[i][0], sub[er.astype(np.int64)].astype(np.uint64))
+    # r02: pipelined asynchronous device-resident searches (programmatic dependent launch)
+    import torch
+    stream = torch.cuda.Stream()
+    dq = torch.from_numpy(qs).cuda()
+    d_r = torch.zeros((9, 5), dtype=torch.int64, device="cuda")
+    d_s = torch.zeros((9, 5), dtype=torch.float32, device="cuda")
+    d_c = torch.zeros(9, dtype=torch.int32, device="cuda")
+    torch.cuda.synchronize()
+    idx.set_pipelining(True)
+    for i in range(9):
+        idx.search_device(dq[i].data_ptr(), 1, 5, "cosine", d_r[i].data_ptr(), d_s[i].data_ptr(),
+                          d_c[i].data_ptr(), stream.cuda_stream)
+    torch.cuda.synchronize()
+    idx.set_pipelining(False)
+    for i in range(9):
+        er, es = o.search(rows, qs[i], 5, "cosine")
+        ok &= np.array_equal(d_r[i].cpu().numpy().astype(np.uint64), er)
+    idx.release_stream(stream.cuda_stream)
     idx.set_prefilter(1)                                   # int8 pre-filter kernels
-    for m in ("cosine", "dot"):
+    for m in ("cosine", "dot", "euclidean"):
         (g,) = idx.search(qs[4], 10, m)
         ok &= same(g, o.search(rows, qs[4], 10, m))
     idx.set_prefilter(0)
