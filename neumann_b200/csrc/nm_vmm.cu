@@ -120,22 +120,37 @@ int GrowBuf::ensure(int device, size_t bytes, bool exact) {
         if (r != CUDA_SUCCESS)
             return fail(NM_ERR_STORAGE, "cuMemAddressReserve(%zu) failed with CUresult %d", want, (int)r);
         if (base_) {
-            size_t off = 0;
+            // Map every chunk into the new range FIRST (one physical allocation may be mapped at
+            // several addresses), switch over only when all of it worked: a failure half way
+            // leaves the old mapping — and the mirror — untouched.
+            size_t off = 0, done = 0;
             for (const Chunk &c : chunks_) {
-                r = api.Unmap(base_ + off, c.size);
-                if (r == CUDA_SUCCESS) r = api.Map(nb + off, c.size, 0, c.h, 0);
-                if (r != CUDA_SUCCESS)
-                    return fail(NM_ERR_STORAGE, "re-mapping a mirror chunk failed with CUresult %d", (int)r);
+                r = api.Map(nb + off, c.size, 0, c.h, 0);
+                if (r != CUDA_SUCCESS) break;
                 off += c.size;
+                ++done;
             }
-            if (mapped_) {
+            if (r == CUDA_SUCCESS && mapped_) {
                 CUmemAccessDesc acc;
                 acc.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
                 acc.location.id = device_;
                 acc.flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
                 r = api.SetAccess(nb, mapped_, &acc, 1);
-                if (r != CUDA_SUCCESS)
-                    return fail(NM_ERR_STORAGE, "cuMemSetAccess failed with CUresult %d", (int)r);
+            }
+            if (r != CUDA_SUCCESS) {
+                off = 0;
+                for (size_t i = 0; i < done; ++i) {
+                    api.Unmap(nb + off, chunks_[i].size);
+                    off += chunks_[i].size;
+                }
+                api.AddressFree(nb, want);
+                return fail(NM_ERR_STORAGE, "re-mapping the mirror into a larger range failed with CUresult %d",
+                            (int)r);
+            }
+            off = 0;
+            for (const Chunk &c : chunks_) {
+                api.Unmap(base_ + off, c.size);
+                off += c.size;
             }
             api.AddressFree(base_, va_size_);
             ++remaps_;
