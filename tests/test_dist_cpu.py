@@ -69,3 +69,63 @@ def test_two_rank_gloo_shard_and_merge():
     for p in procs:
         p.join(timeout=60)
     assert sorted(res) == [(0, "ok"), (1, "ok")], res
+
+
+# ---- merge_shards_rank_kernel (scan_kernels.cuh) restated in numpy -----------------------------
+def _rank_merge(lists, k):
+    """What merge_shards_rank_kernel computes: every shard list is sorted (score desc, row asc) with
+    empty slots last; a hit's final rank is its position in its own list plus, per other list, the
+    number of hits that precede it — strictly better score, or equal score in an EARLIER shard
+    (binary search).  Hits with rank < k land at out[rank]."""
+    import np_ref
+    ords = [np_ref.orderable(np.asarray(s, np.float32)).astype(np.int64) for _, s in lists]
+    out_r = np.zeros(k, np.uint64)
+    out_s = np.zeros(k, np.float32)
+    written = np.zeros(k, bool)
+    for s, (rows, scores) in enumerate(lists):
+        for i in range(len(rows)):
+            o_i = ords[s][i]
+            rank = i
+            for t in range(len(lists)):
+                if t == s:
+                    continue
+                lo, hi = 0, len(ords[t])                 # first index that does NOT precede the hit
+                while lo < hi:
+                    mid = (lo + hi) // 2
+                    before = ords[t][mid] > o_i or (ords[t][mid] == o_i and t < s)
+                    lo, hi = (mid + 1, hi) if before else (lo, mid)
+                rank += lo
+            if rank < k:
+                assert not written[rank]                  # ranks are a permutation: no collisions
+                out_r[rank], out_s[rank], written[rank] = rows[i], scores[i], True
+    n = int(min(k, sum(len(r) for r, _ in lists)))
+    assert written[:n].all() and not written[n:].any()
+    return out_r[:n], out_s[:n]
+
+
+def test_rank_based_merge_equals_merge_top_k():
+    """The large-gather merge kernel's algorithm against the oracle's merge_top_k
+    (distributed.rs:413-433: concatenate in shard order, stable sort, truncate) on tie-heavy shard
+    lists of ragged lengths, with NaN scores (rank last) and -0.0 / +0.0 (tie)."""
+    rng = np.random.default_rng(7)
+    for trial in range(60):
+        n_shards = int(rng.integers(1, 9))
+        k = int(rng.integers(1, 40))
+        pool = np.array([0.5, 0.25, -0.0, 0.0, 1.0, -1.0, np.nan, 0.125, 3.0], np.float32)
+        lists, base = [], 0
+        for s in range(n_shards):
+            m = int(rng.integers(0, k + 1))              # a shard returns at most k hits
+            scores = rng.choice(pool, m) if trial % 2 else rng.normal(0, 1, m).astype(np.float32)
+            rows = base + np.sort(rng.choice(1000, m, replace=False)).astype(np.uint64)
+            # each shard list arrives sorted by (score desc, NaN last, row asc): the scan's order
+            import np_ref
+            order = np.lexsort((rows, -np_ref.orderable(scores).astype(np.int64)))
+            lists.append((rows[order], np.asarray(scores, np.float32)[order]))
+            base += 1000
+        er, es = o.merge_top_k([r for r, _ in lists], [s for _, s in lists], k) if sum(len(r) for r, _ in lists) \
+            else (np.zeros(0, np.uint64), np.zeros(0, np.float32))
+        gr, gs = _rank_merge(lists, k)
+        assert np.array_equal(gr, er), (trial, gr, er)
+        nan = np.isnan(es)
+        assert np.array_equal(np.isnan(gs), nan)
+        assert np.array_equal(gs.view(np.uint32)[~nan], es.view(np.uint32)[~nan])
