@@ -385,10 +385,12 @@ int scan_queries_tc(nm_index *idx, const Shard &sh, Workspace &ws, const float *
                     int *debug_dots = nullptr, const uint32_t *d_row_mask = nullptr);
 int scan_queries_tc_hits_enqueue(nm_index *idx, const Shard &sh, Workspace &ws,
                                  const float *d_queries, uint32_t nq, uint32_t k, int metric,
-                                 uint64_t row_base, nm::ShardHit *out_hits, cudaStream_t stream);
+                                 uint64_t row_base, nm::ShardHit *out_hits, cudaStream_t stream,
+                                 const uint32_t *d_row_mask = nullptr);
 int scan_queries_tc_hits_finish(nm_index *idx, const Shard &sh, Workspace &ws,
                                 const float *d_queries, uint32_t nq, uint32_t k, int metric,
-                                uint64_t row_base, nm::ShardHit *out_hits, cudaStream_t stream);
+                                uint64_t row_base, nm::ShardHit *out_hits, cudaStream_t stream,
+                                const uint32_t *d_row_mask = nullptr);
 uint32_t tc_query_flags(const Workspace &ws, uint32_t q, uint32_t rows);
 uint32_t tc_phases(const Workspace &ws);
 uint32_t tc_survivors(const Workspace &ws);

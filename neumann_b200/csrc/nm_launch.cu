@@ -792,7 +792,8 @@ uint32_t tc_phases(const Workspace &ws) {
 // caller has other shards in flight): wait, redo flagged queries with the exact scan.
 int scan_queries_tc_hits_enqueue(nm_index *idx, const Shard &sh, Workspace &ws,
                                  const float *d_queries, uint32_t nq, uint32_t k, int metric,
-                                 uint64_t row_base, nm::ShardHit *out_hits, cudaStream_t stream) {
+                                 uint64_t row_base, nm::ShardHit *out_hits, cudaStream_t stream,
+                                 const uint32_t *d_row_mask) {
     const ResultLayout l = result_layout(nq, k);
     if (ws.tc_out_cap < l.total) {
         CUDA_TRY(cudaStreamSynchronize(stream));
@@ -805,7 +806,7 @@ int scan_queries_tc_hits_enqueue(nm_index *idx, const Shard &sh, Workspace &ws,
     float *t_scores = reinterpret_cast<float *>(ws.d_tc_out + l.scores_off);
     uint32_t *t_counts = reinterpret_cast<uint32_t *>(ws.d_tc_out + l.counts_off);
     int rc = scan_queries_tc(idx, sh, ws, d_queries, nq, k, metric, row_base, t_rows, t_scores,
-                             t_counts, stream);
+                             t_counts, stream, nullptr, d_row_mask);
     if (rc) return rc;
     nm::tc_pack_hits_kernel<<<nq, 256, 0, stream>>>(t_rows, t_scores, t_counts, k, out_hits);
     CUDA_TRY(cudaGetLastError());
@@ -814,14 +815,16 @@ int scan_queries_tc_hits_enqueue(nm_index *idx, const Shard &sh, Workspace &ws,
 
 int scan_queries_tc_hits_finish(nm_index *idx, const Shard &sh, Workspace &ws,
                                 const float *d_queries, uint32_t nq, uint32_t k, int metric,
-                                uint64_t row_base, nm::ShardHit *out_hits, cudaStream_t stream) {
+                                uint64_t row_base, nm::ShardHit *out_hits, cudaStream_t stream,
+                                const uint32_t *d_row_mask) {
     CUDA_TRY(cudaStreamSynchronize(stream));
     idx->tc_survivors += tc_survivors(ws);
     for (uint32_t q = 0; q < nq; ++q) {
         if (tc_query_flags(ws, q, (uint32_t)sh.rows) == 0) continue;
         idx->tc_fallbacks++;
         int rc = launch_scan(idx, sh, ws, d_queries + (size_t)q * idx->dim, k, metric, row_base,
-                             nullptr, nullptr, nullptr, out_hits + (size_t)q * k, stream);
+                             nullptr, nullptr, nullptr, out_hits + (size_t)q * k, stream, nullptr,
+                             d_row_mask);
         if (rc) return rc;
     }
     return NM_OK;

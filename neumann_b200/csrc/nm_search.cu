@@ -91,7 +91,9 @@ int download_results(nm_index *idx, const Shard &sh, Workspace &ws, const Result
 bool collective_uses_fused_exchange(const nm_index *idx, uint32_t nq, uint32_t k, int metric,
                                     bool masked = false) {
     if (!idx->xchg_ok || k > (uint32_t)nm::kMaxFastK) return false;
-    if (masked) return true;  // masked searches always scan query by query
+    // masked single queries: fused scan + exchange; masked batches: per-shard hit lists (tensor-core
+    // pre-filter where a shard can, else query by query) + ONE all-gather
+    if (masked) return nq < kBatchMinQueries;
     const bool long_rows = single_query_stages(idx->dim) < 4;
     const bool would_batch = (idx->batching.load() || single_query_stages(idx->dim) < 2) &&
                              (nq >= kBatchMinQueries || long_rows) &&
@@ -354,20 +356,20 @@ static int search_impl(nm_index *idx, const float *queries, uint32_t nq, uint32_
             if (sh.rows == 0) {
                 CUDA_TRY(cudaMemsetAsync(ws->d_hits, 0, (size_t)nq * k * sizeof(nm::ShardHit),
                                          ws->stream));
+            } else if (tc_usable(idx, sh, nq, k, metric, false)) {
+                // this shard's hits through the tensor-core pre-filter (a rank-local choice:
+                // the exchange format is the same); masked / filtered batches too
+                rc = scan_queries_tc_hits_enqueue(idx, sh, *ws, ws->d_query, nq, k, metric,
+                                                  idx->comm_row_base, ws->d_hits, ws->stream, d_mask);
+                if (rc) return rc;
+                rc = scan_queries_tc_hits_finish(idx, sh, *ws, ws->d_query, nq, k, metric,
+                                                 idx->comm_row_base, ws->d_hits, ws->stream, d_mask);
+                if (rc) return rc;
+                idx->tc_queries += nq;
             } else if (masked) {
                 rc = masked_hits(idx, sh, *ws, ws->d_query, nq, k, metric, idx->comm_row_base,
                                  ws->d_hits, ws->stream, d_mask);
                 if (rc) return rc;
-            } else if (tc_usable(idx, sh, nq, k, metric, false)) {
-                // this shard's hits through the tensor-core pre-filter (a rank-local choice:
-                // the exchange format is the same)
-                rc = scan_queries_tc_hits_enqueue(idx, sh, *ws, ws->d_query, nq, k, metric,
-                                                  idx->comm_row_base, ws->d_hits, ws->stream);
-                if (rc) return rc;
-                rc = scan_queries_tc_hits_finish(idx, sh, *ws, ws->d_query, nq, k, metric,
-                                                 idx->comm_row_base, ws->d_hits, ws->stream);
-                if (rc) return rc;
-                idx->tc_queries += nq;
             } else {
                 rc = scan_queries(idx, sh, *ws, ws->d_query, nq, k, metric, idx->comm_row_base,
                                   nullptr, nullptr, nullptr, ws->d_hits, ws->stream);
@@ -388,6 +390,7 @@ static int search_impl(nm_index *idx, const float *queries, uint32_t nq, uint32_
     //      the host (G*k hits), exactly ResultMerger::merge_top_k -------------------------
     std::vector<std::unique_ptr<Workspace>> wss(G);
     std::vector<char> tc_shard(G, 0);
+    std::vector<const uint32_t *> d_masks(G, nullptr);
     bool any_tc = false;
     struct ReleaseAll {
         nm_index *idx;
@@ -410,20 +413,21 @@ static int search_impl(nm_index *idx, const float *queries, uint32_t nq, uint32_
         const uint32_t *d_mask = nullptr;
         rc = shard_mask(idx, sh, ws, mspec, sh.row_base, ws.stream, &d_mask, &mask_holds[s]);
         if (rc) return rc;
+        d_masks[s] = d_mask;
         CUDA_TRY(cudaEventRecord(ws.ev0, ws.stream));
         if (sh.rows == 0) {
             CUDA_TRY(cudaMemsetAsync(ws.d_hits, 0, (size_t)nq * k * sizeof(nm::ShardHit), ws.stream));
-        } else if (masked) {
-            rc = masked_hits(idx, sh, ws, ws.d_query, nq, k, metric, sh.row_base, ws.d_hits, ws.stream,
-                             d_mask);
-            if (rc) return rc;
         } else if (tc_usable(idx, sh, nq, k, metric, false)) {
             tc_shard[s] = true;
             any_tc = true;
             rc = scan_queries_tc_hits_enqueue(idx, sh, ws, ws.d_query, nq, k, metric, sh.row_base,
-                                              ws.d_hits, ws.stream);
+                                              ws.d_hits, ws.stream, d_mask);
             if (rc) return rc;
             continue;  // finished below, once every shard has its work in flight
+        } else if (masked) {
+            rc = masked_hits(idx, sh, ws, ws.d_query, nq, k, metric, sh.row_base, ws.d_hits, ws.stream,
+                             d_mask);
+            if (rc) return rc;
         } else {
             rc = scan_queries(idx, sh, ws, ws.d_query, nq, k, metric, sh.row_base, nullptr, nullptr,
                               nullptr, ws.d_hits, ws.stream);
@@ -439,7 +443,7 @@ static int search_impl(nm_index *idx, const float *queries, uint32_t nq, uint32_
         Workspace &ws = *wss[s];
         CUDA_TRY(cudaSetDevice(sh.device));
         rc = scan_queries_tc_hits_finish(idx, sh, ws, ws.d_query, nq, k, metric, sh.row_base,
-                                         ws.d_hits, ws.stream);
+                                         ws.d_hits, ws.stream, d_masks[s]);
         if (rc) return rc;
         CUDA_TRY(cudaEventRecord(ws.ev1, ws.stream));
         CUDA_TRY(cudaMemcpyAsync(ws.h_hits, ws.d_hits, (size_t)nq * k * sizeof(nm::ShardHit),

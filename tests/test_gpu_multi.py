@@ -120,7 +120,7 @@ def test_two_device_filtered_and_masked_search():
     eligible subset, with global row ids."""
     _need(2)
     from neumann_b200._ffi import NM_C_LT, NM_F_CMP, NM_V_INT, NmFilterOp
-    n, d, k = 50_003, 40, 9
+    n, d, k = 150_003, 40, 9               # 75k rows per shard: batches take the tensor cores
     rows = o.fill_synthetic(n, d, 0x5EED0001)
     idx = DeviceIndex(d, devices=[0, 1])
     idx.load(rows)
@@ -132,16 +132,19 @@ def test_two_device_filtered_and_masked_search():
     sub = np.nonzero(keep)[0]
     qs = o.fill_synthetic(2, d, 3)
     for metric in ("cosine", "euclidean"):
-        res = idx.search_filtered(qs, k, metric, prog)
-        resm = idx.search_masked(qs, k, metric, keep)
+        t0 = idx.stats().tc_queries
+        res = idx.search_filtered(qs, k, metric, prog)              # a batch of 2: tensor-core
+        resm = idx.search_masked(qs, k, metric, keep)               # pre-filter per shard, masked
+        assert idx.stats().tc_queries - t0 == 4
+        single = idx.search_filtered(qs[0], k, metric, prog)        # one query: masked f32 scans
         for i in range(2):
             er, es = o.search(rows[sub], qs[i], k, metric, threads=4)
             want = sub[er.astype(np.int64)].astype(np.uint64)
-            for got in (res[i], resm[i]):
+            for got in (res[i], resm[i]) + ((single[0],) if i == 0 else ()):
                 assert np.array_equal(got[0], want), (metric, i)
                 assert np.array_equal(got[1].view(np.uint32), es.view(np.uint32))
     # rows move between the shards when they are re-split: the columns follow
-    idx.append(np.tile(rows[:1], (90_000, 1)))          # last shard > 1.5x its share -> re-split
+    idx.append(np.tile(rows[:1], (250_000, 1)))         # last shard > 1.5x its share -> re-split
     sizes = [idx.shard_info(s).rows for s in range(2)]
     assert abs(sizes[0] - sizes[1]) <= 1
     m = idx.filter_mask(prog)
@@ -159,7 +162,7 @@ def _filtered_collective_worker(rank, world, port, q):
     torch.cuda.set_device(rank)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
-        n, d, k = 120_001, 64, 10
+        n, d, k = 140_001, 64, 10               # 70k rows per rank: batches take the tensor cores
         idx = DeviceIndex(d, devices=[rank])
         lo, hi = nd.attach_index(idx, n)
         idx.fill_synthetic(hi - lo, 0x5EED0001, row_offset=lo)
@@ -171,12 +174,15 @@ def _filtered_collective_worker(rank, world, port, q):
         sub = np.nonzero(keep)[0]
         qs = o.fill_synthetic(3, d, 0x5EED1001)
         for metric in ("cosine", "dot"):
-            res = idx.search_filtered(qs, k, metric, prog)            # fused exchange, masked
-            resm = idx.search_masked(qs, k, metric, keep[lo:hi])      # local slice of the mask
+            t0 = idx.stats().tc_queries
+            res = idx.search_filtered(qs, k, metric, prog)            # batch: per-shard tensor-core
+            resm = idx.search_masked(qs, k, metric, keep[lo:hi])      # pre-filter + ONE all-gather
+            assert idx.stats().tc_queries - t0 == 6
+            one = idx.search_filtered(qs[1], k, metric, prog)         # single: fused exchange, masked
             for i in range(3):
                 er, es = o.search(rows[sub], qs[i], k, metric, threads=4)
                 want = sub[er.astype(np.int64)].astype(np.uint64)
-                for got in (res[i], resm[i]):
+                for got in (res[i], resm[i]) + ((one[0],) if i == 1 else ()):
                     assert np.array_equal(got[0], want), (metric, i, got[0], want)
                     assert np.array_equal(got[1].view(np.uint32), es.view(np.uint32))
         idx.detach_comm()
