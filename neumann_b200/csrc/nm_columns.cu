@@ -41,8 +41,49 @@ struct ColumnsSnapshot {
     uint64_t rows = 0;
 };
 
+namespace {
+constexpr size_t kMaskCacheEntries = 8;   // masks kept per shard (distinct filters between mutations)
+constexpr size_t kMaskPoolEntries = 12;   // + masks still held by searches in flight
+
+size_t shard_mask_words_cap(const Shard &sh) {
+    return (((size_t)std::max<uint64_t>(sh.capacity, sh.rows) + 255) / 256) * 8;
+}
+
+int mask_entry_alloc(const Shard &sh, size_t prog_bytes, std::shared_ptr<MaskEntry> *out) {
+    std::shared_ptr<MaskEntry> e(new MaskEntry());
+    e->device = sh.device;
+    // sized for the shard's capacity and a full-size program: recycled across filters
+    e->words_cap = shard_mask_words_cap(sh);
+    e->prog_cap = std::max<size_t>(prog_bytes, nm::kFilterMaxOps * sizeof(nm::FilterOpDev) + 4096);
+    CUDA_TRY(cudaMalloc(&e->d_mask, e->words_cap * 4));
+    CUDA_TRY(cudaMalloc(&e->d_prog, e->prog_cap));
+    CUDA_TRY(cudaEventCreateWithFlags(&e->ready, cudaEventDisableTiming));
+    *out = e;
+    return NM_OK;
+}
+}  // namespace
+
+// Device allocation does not belong on the search path (a cudaMalloc next to a 30 GB mirror was
+// measured at 0.2 - 100 ms): the mask buffers a shard's filters will need are allocated when its
+// metadata arrives or its capacity changes, and recycled from then on.
+int mask_pool_prepare(Shard &sh) {
+    CUDA_TRY(cudaSetDevice(sh.device));
+    const size_t cap = shard_mask_words_cap(sh);
+    std::lock_guard<std::mutex> g(sh.mask_mu);
+    for (auto it = sh.mask_free.begin(); it != sh.mask_free.end();)
+        it = (*it)->words_cap < cap ? sh.mask_free.erase(it) : it + 1;
+    while (sh.mask_cache.size() + sh.mask_free.size() < kMaskPoolEntries) {
+        std::shared_ptr<MaskEntry> e;
+        if (int rc = mask_entry_alloc(sh, 0, &e)) return rc;
+        sh.mask_free.push_back(e);
+    }
+    return NM_OK;
+}
+
 int columns_after_resize(nm_index *idx, Shard &sh) {
     (void)idx;
+    if (!sh.columns.empty())
+        if (int rc = mask_pool_prepare(sh)) return rc;
     for (auto &kv : sh.columns) {
         Column &c = *kv.second;
         if (c.init_rows > sh.rows) c.init_rows = sh.rows;  // rows were removed: re-zero on regrowth
@@ -234,7 +275,7 @@ int shard_mask(nm_index *idx, Shard &sh, Workspace &ws, const MaskSpec &spec, ui
         for (auto it = sh.mask_cache.begin(); it != sh.mask_cache.end();) {
             if ((*it)->epoch != epoch) {
                 // stale: keep its buffers for the next new filter unless a search still holds it
-                if (it->use_count() == 1 && sh.mask_free.size() < 4) sh.mask_free.push_back(*it);
+                if (it->use_count() == 1 && sh.mask_free.size() < kMaskPoolEntries) sh.mask_free.push_back(*it);
                 it = sh.mask_cache.erase(it);
                 continue;
             }
@@ -258,17 +299,8 @@ int shard_mask(nm_index *idx, Shard &sh, Workspace &ws, const MaskSpec &spec, ui
         *d_mask = (*hold)->d_mask;
         return NM_OK;
     }
-    if (!e) {
-        e.reset(new MaskEntry());
-        e->device = sh.device;
-        // sized for the shard's capacity and a full-size program: recycled across filters
-        e->words_cap = (((size_t)std::max<uint64_t>(sh.capacity, sh.rows) + 255) / 256) * 8;
-        e->prog_cap = std::max<size_t>(ops_bytes + tab_bytes + 16,
-                                       nm::kFilterMaxOps * sizeof(nm::FilterOpDev) + 4096);
-        CUDA_TRY(cudaMalloc(&e->d_mask, e->words_cap * 4));
-        CUDA_TRY(cudaMalloc(&e->d_prog, e->prog_cap));
-        CUDA_TRY(cudaEventCreateWithFlags(&e->ready, cudaEventDisableTiming));
-    }
+    if (!e)  // pool exhausted (every entry held by a search in flight) or an oversized string table
+        if (int rc = mask_entry_alloc(sh, ops_bytes + tab_bytes + 16, &e)) return rc;
     e->epoch = epoch;
     e->words = words;
     const uint32_t *d_tables = reinterpret_cast<const uint32_t *>(static_cast<uint8_t *>(e->d_prog) + ops_bytes);
@@ -298,7 +330,12 @@ int shard_mask(nm_index *idx, Shard &sh, Workspace &ws, const MaskSpec &spec, ui
         CUDA_TRY(cudaMemcpyAsync(static_cast<uint8_t *>(e->d_prog) + ops_bytes, spec.tables, tab_bytes,
                                  cudaMemcpyHostToDevice, stream));
     // (pageable sources: both copies have been staged when the calls return)
-    int rc = launch_filter_mask(sh, static_cast<const nm::FilterOpDev *>(e->d_prog), spec.n_ops, sh.rows,
+    uint32_t depth = 0, max_depth = 0;  // validated: never underflows, ends at 1
+    for (uint32_t i = 0; i < spec.n_ops; ++i) {
+        if (spec.prog[i].kind == NM_F_AND || spec.prog[i].kind == NM_F_OR) --depth;
+        else max_depth = std::max(max_depth, ++depth);
+    }
+    int rc = launch_filter_mask(sh, static_cast<const nm::FilterOpDev *>(e->d_prog), spec.n_ops, max_depth, sh.rows,
                                 e->d_mask, words, stream);
     if (rc) return rc;
     CUDA_TRY(cudaEventRecord(e->ready, stream));
@@ -307,8 +344,8 @@ int shard_mask(nm_index *idx, Shard &sh, Workspace &ws, const MaskSpec &spec, ui
     e->key.swap(key);
     {
         std::lock_guard<std::mutex> g(sh.mask_mu);
-        if (sh.mask_cache.size() >= 8) {
-            if (sh.mask_cache.front().use_count() == 1 && sh.mask_free.size() < 4)
+        if (sh.mask_cache.size() >= kMaskCacheEntries) {
+            if (sh.mask_cache.front().use_count() == 1 && sh.mask_free.size() < kMaskPoolEntries)
                 sh.mask_free.push_back(sh.mask_cache.front());
             sh.mask_cache.erase(sh.mask_cache.begin());
         }
@@ -345,6 +382,7 @@ int nm_index_column_set(nm_index *idx, uint32_t column, uint64_t first_row, uint
         Column &c = column_of(sh, column);
         if (c.init_rows > sh.rows) c.init_rows = sh.rows;
         if (int rc = column_reserve(sh, c, sh.rows)) return rc;  // rows never set read as "missing"
+        if (int rc = mask_pool_prepare(sh)) return rc;           // filters will follow: no cudaMalloc then
         CUDA_TRY(cudaMemcpyAsync(c.d_tags + (lo - sh.row_base), tags + (lo - first_row), hi - lo,
                                  cudaMemcpyHostToDevice, sh.copy_stream));
         CUDA_TRY(cudaMemcpyAsync(c.d_vals + (lo - sh.row_base), values + (lo - first_row), (hi - lo) * 8,

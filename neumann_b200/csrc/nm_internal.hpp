@@ -405,7 +405,8 @@ int launch_quantize(const Shard &sh, const float *rows, uint32_t pitch, uint32_t
                     uint64_t n, int8_t *q8, uint32_t pitch8, nm::RowMeta *meta, float2 *norms,
                     uint32_t *flag, cudaStream_t stream);
 
-int launch_filter_mask(const Shard &sh, const nm::FilterOpDev *d_ops, uint32_t n_ops, uint64_t n_rows,
+int launch_filter_mask(const Shard &sh, const nm::FilterOpDev *d_ops, uint32_t n_ops, uint32_t max_depth,
+                       uint64_t n_rows,
                        uint32_t *d_mask, uint64_t n_words, cudaStream_t stream);
 int launch_column_move(uint8_t *tags, uint64_t *vals, uint64_t dst, uint64_t src, cudaStream_t stream);
 

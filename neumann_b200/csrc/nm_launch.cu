@@ -894,11 +894,15 @@ int launch_exchange_empty(const nm::PeerXchg &x, uint32_t k, uint64_t *scratch, 
     return NM_OK;
 }
 
-int launch_filter_mask(const Shard &sh, const nm::FilterOpDev *d_ops, uint32_t n_ops, uint64_t n_rows,
-                       uint32_t *d_mask, uint64_t n_words, cudaStream_t stream) {
-    const uint64_t padded = n_words * 32ull;
-    const uint32_t blocks = (uint32_t)std::min<uint64_t>((padded + 255) / 256, (uint64_t)sh.sm_count * 8);
-    nm::filter_mask_kernel<<<blocks, 256, 0, stream>>>(d_ops, n_ops, n_rows, d_mask, n_words);
+int launch_filter_mask(const Shard &sh, const nm::FilterOpDev *d_ops, uint32_t n_ops, uint32_t max_depth,
+                       uint64_t n_rows, uint32_t *d_mask, uint64_t n_words, cudaStream_t stream) {
+    // one warp per 256-row block of the mask, 8 warps per CTA; giant shards loop
+    if (n_words == 0) return NM_OK;
+    const uint32_t blocks = (uint32_t)std::min<uint64_t>((n_words / 8 + 7) / 8, (uint64_t)sh.sm_count * 64);
+    if (max_depth <= 32)
+        nm::filter_mask_kernel<uint32_t><<<blocks, 256, 0, stream>>>(d_ops, n_ops, n_rows, d_mask, n_words);
+    else
+        nm::filter_mask_kernel<uint64_t><<<blocks, 256, 0, stream>>>(d_ops, n_ops, n_rows, d_mask, n_words);
     CUDA_TRY(cudaGetLastError());
     return NM_OK;
 }

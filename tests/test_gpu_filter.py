@@ -179,6 +179,30 @@ def test_filter_program_follows_the_reference_type_rules():
     idx.close()
 
 
+@pytest.mark.parametrize("n", [1, 31, 32, 255, 256, 257, 511, 512, 2048, 8193])
+def test_filter_mask_at_the_edges_of_a_mask_block(n):
+    """A warp evaluates one 256-row block of the mask (8 words); whole blocks take the unguarded
+    loads, the last partial one the guarded ones; TRUE must not leak past the last row."""
+    idx = DeviceIndex(8)
+    idx.fill_synthetic(n, 11)
+    rng = np.random.default_rng(n)
+    a = rng.integers(-20, 20, n)
+    tags = np.where(rng.integers(0, 7, n) == 0, NM_V_MISSING, NM_V_INT).astype(np.uint8)
+    idx.column_set(3, 0, tags, a.astype(np.int64).view(np.uint64))
+    have = tags == NM_V_INT
+    cases = [([NmFilterOp(kind=NM_F_TRUE)], np.ones(n, bool)),
+             ([cmp_op(3, NM_C_LT, 5)], have & (a < 5)),
+             ([cmp_op(3, NM_C_NE, 0)], have & (a != 0)),
+             ([cmp_op(3, NM_C_GE, -3), NmFilterOp(kind=NM_F_EXISTS, column=3), NmFilterOp(kind=NM_F_AND),
+               NmFilterOp(kind=NM_F_FALSE), NmFilterOp(kind=NM_F_OR)], have & (a >= -3))]
+    # a right-leaning chain 64 deep: every leaf is pushed before the first AND pops anything
+    deep = [cmp_op(3, NM_C_GT, -20 + (j % 3)) for j in range(64)] + [NmFilterOp(kind=NM_F_AND)] * 63
+    cases.append((deep, have & (a > -18)))
+    for prog, want in cases:
+        assert np.array_equal(idx.filter_mask(prog, None), want)
+    idx.close()
+
+
 @pytest.mark.parametrize("metric", ["cosine", "euclidean", "dot"])
 def test_search_filtered_equals_the_oracle_on_the_subset(metric):
     n, d, k = 90_000, 48, 12
