@@ -40,6 +40,10 @@ for (n, d) in [(3000, 100), (1500, 64), (700, 13)]:
             NmFilterOp(kind=NM_F_OR), NmFilterOp(kind=NM_F_EXISTS, column=1), NmFilterOp(kind=NM_F_AND)]
     keep = (tags == 3) & ((vals < 4) | (vals >= 10))
     ok &= np.array_equal(idx.filter_mask(prog), keep)
+    # a stack 40 deep takes the 64-bit-stack instance of the kernel
+    deep = [NmFilterOp(kind=NM_F_CMP, cmp=NM_C_LT, lit_tag=NM_V_INT, column=1, lit=9 - (j % 2)) for j in range(40)] \
+        + [NmFilterOp(kind=NM_F_AND)] * 39
+    ok &= np.array_equal(idx.filter_mask(deep), (tags == 3) & (vals < 8))
     sub = np.nonzero(keep)[0]
     for m in ("cosine", "euclidean"):
         res = idx.search_filtered(qs[:2], 6, m, prog)
