@@ -36,6 +36,19 @@ int wait_stream(cudaStream_t stream) {
     }
 }
 
+// Small result blocks are written by the kernels straight into the pinned host block (mapped
+// into the device's address space under UVA): no device-to-host copy operation between the last
+// kernel and the caller — its engine hand-over costs more than 136 bytes of posted PCIe writes.
+// Stream completion makes the writes visible to the host.  NM_ZERO_COPY_RESULTS=0 switches it off.
+constexpr size_t kZeroCopyResultBytes = 4096;
+bool zero_copy_results(size_t total) {
+    static const bool on = [] {
+        const char *m = getenv("NM_ZERO_COPY_RESULTS");
+        return !(m && m[0] == '0');
+    }();
+    return on && total <= kZeroCopyResultBytes;
+}
+
 struct HostHit {
     uint32_t ord;
     uint32_t score_bits;
@@ -59,9 +72,10 @@ int validate_search(const nm_index *idx, const void *queries, uint32_t nq, uint3
 // Packed result block device -> pinned host -> caller buffers; one D2H copy, one sync.
 int download_results(nm_index *idx, const Shard &sh, Workspace &ws, const ResultLayout &l,
                      uint32_t nq, uint32_t k, uint64_t *out_rows, float *out_scores,
-                     uint32_t *out_counts) {
+                     uint32_t *out_counts, bool on_host = false) {
     NM_TRACE("wait_download");
-    CUDA_TRY(cudaMemcpyAsync(ws.h_result, ws.d_result, l.total, cudaMemcpyDeviceToHost, ws.stream));
+    if (!on_host)  // else: the kernels wrote into ws.h_result themselves
+        CUDA_TRY(cudaMemcpyAsync(ws.h_result, ws.d_result, l.total, cudaMemcpyDeviceToHost, ws.stream));
     {
         int wrc = wait_stream(ws.stream);
         if (wrc) return wrc;
@@ -83,7 +97,7 @@ int download_results(nm_index *idx, const Shard &sh, Workspace &ws, const Result
     idx->rows_scanned += (uint64_t)nq * sh.rows;
     idx->bytes_streamed += (uint64_t)nq * sh.rows * idx->dim * 4;
     idx->h2d_bytes += (uint64_t)nq * idx->dim * 4;
-    idx->d2h_bytes += l.total;
+    idx->d2h_bytes += l.total;  // zero-copy or copied: the same bytes cross the bus
     return NM_OK;
 }
 
@@ -182,9 +196,15 @@ static int search_impl(nm_index *idx, const float *queries, uint32_t nq, uint32_
             CUDA_TRY(cudaMemcpyAsync(ws->d_query, ws->h_query, (size_t)nq * dim * 4,
                                      cudaMemcpyHostToDevice, ws->stream));
         }
-        uint64_t *r_rows = reinterpret_cast<uint64_t *>(ws->d_result + l.rows_off);
-        float *r_scores = reinterpret_cast<float *>(ws->d_result + l.scores_off);
-        uint32_t *r_counts = reinterpret_cast<uint32_t *>(ws->d_result + l.counts_off);
+        const bool tc_path = tc_usable(idx, sh, nq, k, metric, false);
+        // the pre-filter paths copy their status words back with the results and may redo queries
+        // in place: they keep the device-side block
+        const bool host_block = zero_copy_results(l.total) && !tc_path &&
+                                !prefilter_usable(idx, sh, nq, k, metric, masked);
+        uint8_t *r_base = host_block ? ws->h_result : ws->d_result;
+        uint64_t *r_rows = reinterpret_cast<uint64_t *>(r_base + l.rows_off);
+        float *r_scores = reinterpret_cast<float *>(r_base + l.scores_off);
+        uint32_t *r_counts = reinterpret_cast<uint32_t *>(r_base + l.counts_off);
         const uint32_t *d_mask = nullptr;
         if (masked) {
             NM_TRACE("filter_mask");
@@ -193,7 +213,6 @@ static int search_impl(nm_index *idx, const float *queries, uint32_t nq, uint32_
         }
         NM_TRACE("scan");
         CUDA_TRY(cudaEventRecord(ws->ev0, ws->stream));
-        const bool tc_path = tc_usable(idx, sh, nq, k, metric, false);
         if (masked && !tc_path) {
             for (uint32_t q = 0; q < nq; ++q) {
                 rc = launch_scan(idx, sh, *ws, ws->d_query + (size_t)q * dim, k, metric, sh.row_base,
@@ -311,7 +330,7 @@ static int search_impl(nm_index *idx, const float *queries, uint32_t nq, uint32_
             if (rc) return rc;
         }
         CUDA_TRY(cudaEventRecord(ws->ev1, ws->stream));
-        return download_results(idx, sh, *ws, l, nq, k, out_rows, out_scores, out_counts);
+        return download_results(idx, sh, *ws, l, nq, k, out_rows, out_scores, out_counts, host_block);
     }
 
     // ---- collective path: one shard per process.  Single queries: ONE fused launch (scan +
@@ -336,9 +355,11 @@ static int search_impl(nm_index *idx, const float *queries, uint32_t nq, uint32_
         rc = ws_ensure(*ws, sh, dim, nq, k, true, true, true, idx->n_ranks);
         if (rc) return rc;
         ResultLayout l = result_layout(nq, k);
-        uint64_t *r_rows = reinterpret_cast<uint64_t *>(ws->d_result + l.rows_off);
-        float *r_scores = reinterpret_cast<float *>(ws->d_result + l.scores_off);
-        uint32_t *r_counts = reinterpret_cast<uint32_t *>(ws->d_result + l.counts_off);
+        const bool host_block = zero_copy_results(l.total);  // (rank-local choice)
+        uint8_t *r_base = host_block ? ws->h_result : ws->d_result;
+        uint64_t *r_rows = reinterpret_cast<uint64_t *>(r_base + l.rows_off);
+        float *r_scores = reinterpret_cast<float *>(r_base + l.scores_off);
+        uint32_t *r_counts = reinterpret_cast<uint32_t *>(r_base + l.counts_off);
         memcpy(ws->h_query, queries, (size_t)nq * dim * 4);
         CUDA_TRY(cudaMemcpyAsync(ws->d_query, ws->h_query, (size_t)nq * dim * 4,
                                  cudaMemcpyHostToDevice, ws->stream));
@@ -383,7 +404,7 @@ static int search_impl(nm_index *idx, const float *queries, uint32_t nq, uint32_
             rc = launch_merge_shards(idx, ws->d_gather, nq, k, r_rows, r_scores, r_counts, ws->stream);
             if (rc) return rc;
         }
-        return download_results(idx, sh, *ws, l, nq, k, out_rows, out_scores, out_counts);
+        return download_results(idx, sh, *ws, l, nq, k, out_rows, out_scores, out_counts, host_block);
     }
 
     // ---- several devices in this process: scan each shard, merge the per-shard top-k on
