@@ -589,6 +589,7 @@ def bench_cfg4(E, a):
     rows, dim, k, nq, metric = a.cfg4_rows, 1536, 100, 256, "euclidean"
     idx = DeviceIndex(dim, devices=[E.local_rank])
     idx.fill_synthetic(rows, SEED_ROWS)
+    idx.set_profiling(True)  # last_scan_ms (device time per call); ~8 us of events per 5 ms call
     qb = synth_rows(nq, dim, SEED_BATCH)
     out = {"workload": workload_name(rows, dim, metric, k, nq), "rows": rows, "dim": dim, "k": k,
            "metric": metric, "batch": nq}
@@ -897,11 +898,13 @@ def run_ours(a):
                 idx.search(qb, a.k, a.metric)
                 b0 = idx.stats()
                 ts = []
+                idx.set_profiling(True)  # device time of the last call -> last_scan_ms
                 for _ in range(10):
                     t0 = time.perf_counter()
                     got = idx.search(qb, a.k, a.metric)
                     ts.append(time.perf_counter() - t0)
                 b1 = idx.stats()
+                idx.set_profiling(False)
                 t_b = sorted(ts)[len(ts) // 2]
                 nb = int(b1.tc_queries - b0.tc_queries)
                 same = all(np.array_equal(g[0], e[0]) and _bits_equal(g[1], e[1])

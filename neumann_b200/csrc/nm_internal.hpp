@@ -66,6 +66,7 @@ struct Workspace {
     int device = -1;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool timed = false;  // ev0 / ev1 were recorded for the call in flight (profiling on)
     float *d_query = nullptr;
     float *h_query = nullptr;  // pinned
     size_t query_cap = 0;      // floats

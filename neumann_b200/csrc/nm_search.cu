@@ -49,6 +49,24 @@ bool zero_copy_results(size_t total) {
     return on && total <= kZeroCopyResultBytes;
 }
 
+// Device-time bracket of a synchronous search (nm_stats.last_scan_ms).  Two timing events cost
+// ~8 us of a 36 us call on a small corpus (each makes the front end drain and write a timestamp),
+// so they are recorded only while nm_index_set_profiling is on; otherwise last_scan_ms reads 0.
+static inline int time_begin(nm_index *idx, Workspace &ws) {
+    ws.timed = idx->profiling.load() != 0;
+    if (ws.timed) CUDA_TRY(cudaEventRecord(ws.ev0, ws.stream));
+    return NM_OK;
+}
+static inline int time_end(Workspace &ws) {
+    if (ws.timed) CUDA_TRY(cudaEventRecord(ws.ev1, ws.stream));
+    return NM_OK;
+}
+static inline int time_read(Workspace &ws, float *ms) {
+    *ms = 0.f;
+    if (ws.timed) CUDA_TRY(cudaEventElapsedTime(ms, ws.ev0, ws.ev1));
+    return NM_OK;
+}
+
 struct HostHit {
     uint32_t ord;
     uint32_t score_bits;
@@ -81,7 +99,7 @@ int download_results(nm_index *idx, const Shard &sh, Workspace &ws, const Result
         if (wrc) return wrc;
     }
     float ms = 0.f;
-    CUDA_TRY(cudaEventElapsedTime(&ms, ws.ev0, ws.ev1));
+    if (int trc = time_read(ws, &ms)) return trc;
     idx->last_scan_ms = ms;
     const uint32_t *hc = reinterpret_cast<const uint32_t *>(ws.h_result + l.counts_off);
     const uint64_t *hr = reinterpret_cast<const uint64_t *>(ws.h_result + l.rows_off);
@@ -212,7 +230,7 @@ static int search_impl(nm_index *idx, const float *queries, uint32_t nq, uint32_
             if (rc) return rc;
         }
         NM_TRACE("scan");
-        CUDA_TRY(cudaEventRecord(ws->ev0, ws->stream));
+        if (int trc = time_begin(idx, *ws)) return trc;
         if (masked && !tc_path) {
             for (uint32_t q = 0; q < nq; ++q) {
                 rc = launch_scan(idx, sh, *ws, ws->d_query + (size_t)q * dim, k, metric, sh.row_base,
@@ -227,7 +245,7 @@ static int search_impl(nm_index *idx, const float *queries, uint32_t nq, uint32_
             rc = scan_queries_tc(idx, sh, *ws, ws->d_query, nq, k, metric, sh.row_base, r_rows,
                                  r_scores, r_counts, ws->stream, nullptr, d_mask);
             if (rc) return rc;
-            CUDA_TRY(cudaEventRecord(ws->ev1, ws->stream));
+            if (int trc = time_end(*ws)) return trc;
             CUDA_TRY(cudaMemcpyAsync(ws->h_result, ws->d_result, l.total, cudaMemcpyDeviceToHost,
                                      ws->stream));
             rc = wait_stream(ws->stream);
@@ -256,7 +274,7 @@ static int search_impl(nm_index *idx, const float *queries, uint32_t nq, uint32_
             }
             if (!redo) {
                 float ms = 0.f;
-                CUDA_TRY(cudaEventElapsedTime(&ms, ws->ev0, ws->ev1));
+                if (int trc = time_read(*ws, &ms)) return trc;
                 idx->last_scan_ms = ms;
                 const uint32_t *hc = reinterpret_cast<const uint32_t *>(ws->h_result + l.counts_off);
                 const uint64_t *hr = reinterpret_cast<const uint64_t *>(ws->h_result + l.rows_off);
@@ -287,7 +305,7 @@ static int search_impl(nm_index *idx, const float *queries, uint32_t nq, uint32_
             // overflowed (or whose query is not finite) are redone with the exact f32 scan
             CUDA_TRY(cudaMemcpyAsync(ws->h_pf_ctl, ws->d_pf_ctl, (size_t)nq * 8 * sizeof(uint32_t),
                                      cudaMemcpyDeviceToHost, ws->stream));
-            CUDA_TRY(cudaEventRecord(ws->ev1, ws->stream));
+            if (int trc = time_end(*ws)) return trc;
             CUDA_TRY(cudaMemcpyAsync(ws->h_result, ws->d_result, l.total, cudaMemcpyDeviceToHost,
                                      ws->stream));
             rc = wait_stream(ws->stream);
@@ -307,7 +325,7 @@ static int search_impl(nm_index *idx, const float *queries, uint32_t nq, uint32_
             if (!redo) {
                 // results are already on the host: finish without a second copy
                 float ms = 0.f;
-                CUDA_TRY(cudaEventElapsedTime(&ms, ws->ev0, ws->ev1));
+                if (int trc = time_read(*ws, &ms)) return trc;
                 idx->last_scan_ms = ms;
                 const uint32_t *hc = reinterpret_cast<const uint32_t *>(ws->h_result + l.counts_off);
                 const uint64_t *hr = reinterpret_cast<const uint64_t *>(ws->h_result + l.rows_off);
@@ -329,7 +347,7 @@ static int search_impl(nm_index *idx, const float *queries, uint32_t nq, uint32_
                               r_counts, nullptr, ws->stream);
             if (rc) return rc;
         }
-        CUDA_TRY(cudaEventRecord(ws->ev1, ws->stream));
+        if (int trc = time_end(*ws)) return trc;
         return download_results(idx, sh, *ws, l, nq, k, out_rows, out_scores, out_counts, host_block);
     }
 
@@ -367,12 +385,12 @@ static int search_impl(nm_index *idx, const float *queries, uint32_t nq, uint32_
         const uint32_t *d_mask = nullptr;
         rc = shard_mask(idx, sh, *ws, mspec, 0, ws->stream, &d_mask, &mask_holds[0]);
         if (rc) return rc;
-        CUDA_TRY(cudaEventRecord(ws->ev0, ws->stream));
+        if (int trc = time_begin(idx, *ws)) return trc;
         if (collective_uses_fused_exchange(idx, nq, k, metric, masked)) {
             rc = collective_fused(idx, sh, *ws, ws->d_query, nq, k, metric, r_rows, r_scores,
                                   r_counts, ws->stream, d_mask);
             if (rc) return rc;
-            CUDA_TRY(cudaEventRecord(ws->ev1, ws->stream));
+            if (int trc = time_end(*ws)) return trc;
         } else {
             if (sh.rows == 0) {
                 CUDA_TRY(cudaMemsetAsync(ws->d_hits, 0, (size_t)nq * k * sizeof(nm::ShardHit),
@@ -396,7 +414,7 @@ static int search_impl(nm_index *idx, const float *queries, uint32_t nq, uint32_
                                   nullptr, nullptr, nullptr, ws->d_hits, ws->stream);
                 if (rc) return rc;
             }
-            CUDA_TRY(cudaEventRecord(ws->ev1, ws->stream));
+            if (int trc = time_end(*ws)) return trc;
             NM_TRACE("exchange_merge");
             NCCL_TRY(nccl().AllGather(ws->d_hits, ws->d_gather,
                                       (size_t)nq * k * sizeof(nm::ShardHit), ncclChar, idx->comm,
@@ -435,7 +453,7 @@ static int search_impl(nm_index *idx, const float *queries, uint32_t nq, uint32_
         rc = shard_mask(idx, sh, ws, mspec, sh.row_base, ws.stream, &d_mask, &mask_holds[s]);
         if (rc) return rc;
         d_masks[s] = d_mask;
-        CUDA_TRY(cudaEventRecord(ws.ev0, ws.stream));
+        if (int trc = time_begin(idx, ws)) return trc;
         if (sh.rows == 0) {
             CUDA_TRY(cudaMemsetAsync(ws.d_hits, 0, (size_t)nq * k * sizeof(nm::ShardHit), ws.stream));
         } else if (tc_usable(idx, sh, nq, k, metric, false)) {
@@ -454,7 +472,7 @@ static int search_impl(nm_index *idx, const float *queries, uint32_t nq, uint32_
                               nullptr, ws.d_hits, ws.stream);
             if (rc) return rc;
         }
-        CUDA_TRY(cudaEventRecord(ws.ev1, ws.stream));
+        if (int trc = time_end(ws)) return trc;
         CUDA_TRY(cudaMemcpyAsync(ws.h_hits, ws.d_hits, (size_t)nq * k * sizeof(nm::ShardHit),
                                  cudaMemcpyDeviceToHost, ws.stream));
     }
@@ -466,7 +484,7 @@ static int search_impl(nm_index *idx, const float *queries, uint32_t nq, uint32_
         rc = scan_queries_tc_hits_finish(idx, sh, ws, ws.d_query, nq, k, metric, sh.row_base,
                                          ws.d_hits, ws.stream, d_masks[s]);
         if (rc) return rc;
-        CUDA_TRY(cudaEventRecord(ws.ev1, ws.stream));
+        if (int trc = time_end(ws)) return trc;
         CUDA_TRY(cudaMemcpyAsync(ws.h_hits, ws.d_hits, (size_t)nq * k * sizeof(nm::ShardHit),
                                  cudaMemcpyDeviceToHost, ws.stream));
     }
@@ -477,7 +495,7 @@ static int search_impl(nm_index *idx, const float *queries, uint32_t nq, uint32_
         rc = wait_stream(wss[s]->stream);
         if (rc) return rc;
         float ms = 0.f;
-        CUDA_TRY(cudaEventElapsedTime(&ms, wss[s]->ev0, wss[s]->ev1));
+        if (int trc = time_read(*wss[s], &ms)) return trc;
         max_ms = std::max(max_ms, ms);
     }
     idx->last_scan_ms = max_ms;

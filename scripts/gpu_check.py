@@ -41,7 +41,7 @@ print("ALL PARITY", "OK" if ok else "FAIL", flush=True)
 for (n, d, k, metric) in [(1_000_000, 768, 10, "cosine"), (10_000_000, 768, 10, "cosine"),
                           (10_000_000, 768, 10, "euclidean"), (10_000_000, 768, 10, "dot"),
                           (5_000_000, 1536, 100, "euclidean")]:
-    idx = DeviceIndex(d)
+    idx = DeviceIndex(d); idx.set_profiling(True)   # last_scan_ms
     t0 = time.time(); idx.fill_synthetic(n, 0x5EED0001); t1 = time.time()
     q = o.fill_synthetic(1, d, 0x5EED1001)[0]
     for _ in range(3): idx.search(q, k, metric)

@@ -10,7 +10,7 @@ from neumann_b200.synth import synth_rows
 n, d, nq, k = (int(x) for x in sys.argv[1:5])
 metric = sys.argv[5]
 steps = int(sys.argv[6]) if len(sys.argv) > 6 else 5
-idx = DeviceIndex(d); idx.fill_synthetic(n, 0x5EED0001); idx.set_prefilter(1)
+idx = DeviceIndex(d); idx.fill_synthetic(n, 0x5EED0001); idx.set_prefilter(1); idx.set_profiling(True)
 qs = synth_rows(nq, d, 0x5EED1001)
 idx.search(qs, k, metric)
 s0 = idx.stats()

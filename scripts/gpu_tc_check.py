@@ -16,7 +16,7 @@ def quantise(q):
 
 
 def check_dots(n, d, nq):
-    idx = DeviceIndex(d); idx.fill_synthetic(n, 0x5EED0001); idx.set_prefilter(1)
+    idx = DeviceIndex(d); idx.fill_synthetic(n, 0x5EED0001); idx.set_prefilter(1); idx.set_profiling(True)
     qs = synth_rows(nq, d, 0x5EED1001)
     dots = idx.debug_tc_dots(qs)
     rows = sorted(set([0, 1, 31, 32, 127, 128, 129, n - 1, n - 2, n // 2] +

@@ -470,7 +470,13 @@ def test_stats_counters():
     s = idx.stats()
     assert s.searches == 2 and s.scan_launches == 2
     assert s.rows_scanned == 2000 and s.bytes_streamed == 2 * 1000 * 64 * 4
-    assert s.last_scan_ms > 0
+    assert s.last_scan_ms == 0           # timing events are recorded only while profiling is on
+    idx.set_profiling(True)
+    idx.search(q, 3, "dot")
+    assert idx.stats().last_scan_ms > 0
+    idx.set_profiling(False)
+    idx.search(q, 3, "dot")
+    assert idx.stats().last_scan_ms == 0
     idx.close()
 
 
