@@ -188,8 +188,8 @@ struct MaskEntry {
     uint64_t epoch = 0;         // nm_index::mutation_epoch it was computed at
     uint32_t *d_mask = nullptr; // [words] u32, padded to whole row blocks
     size_t words = 0;
-    size_t words_cap = 0;       // allocation sizes: stale entries are recycled, not freed (a
-    size_t prog_cap = 0;        // cudaMalloc / cudaFree pair per new filter cost ~5 ms at 10M rows)
+    size_t words_cap = 0;       // allocation sizes: entries come from a per-shard pool filled when
+    size_t prog_cap = 0;        // metadata arrives and go back to it (no cudaMalloc while searching)
     void *d_prog = nullptr;     // FilterOpDev[] followed by the string tables
     cudaEvent_t ready = nullptr;
     ~MaskEntry() {
