@@ -55,6 +55,21 @@ struct FilteredSearchConfig {
     FilterStrategy strategy = FilterStrategy::Auto;
     float selectivity_threshold = 0.1f;
     size_t oversample_factor = 3;
+    static FilteredSearchConfig pre_filter() {
+        FilteredSearchConfig c;
+        c.strategy = FilterStrategy::PreFilter;
+        return c;
+    }
+    static FilteredSearchConfig post_filter() {
+        FilteredSearchConfig c;
+        c.strategy = FilterStrategy::PostFilter;
+        return c;
+    }
+    FilteredSearchConfig with_oversample(size_t factor) const {
+        FilteredSearchConfig c = *this;
+        c.oversample_factor = factor;
+        return c;
+    }
 };
 
 // Parses `field op literal [AND|OR ...]` with parentheses (AND binds tighter than OR), the

@@ -43,6 +43,10 @@ std::string VectorError::to_string() const {
     case ErrorKind::CollectionNotFound: return "Collection not found: " + message;
     case ErrorKind::SearchTimeout:
         return "search timeout: " + operation + " exceeded " + std::to_string(timeout_ms) + "ms";
+    case ErrorKind::BatchValidationError:
+        return "Batch validation error at index " + std::to_string(index) + ": " + message;
+    case ErrorKind::BatchOperationError:
+        return "Batch operation error at index " + std::to_string(index) + ": " + message;
     default: return "Invalid argument: " + message;
     }
 }
@@ -158,13 +162,17 @@ Result<std::unique_ptr<VectorEngine>> VectorEngine::with_config(VectorEngineConf
 }
 
 // lib.rs:1876-1885
-bool VectorEngine::should_use_sparse(const std::vector<float> &v) const {
+bool VectorEngine::should_use_sparse_with_threshold(const std::vector<float> &v, float threshold) {
     if (v.empty()) return false;
     size_t nnz = 0;
     for (float x : v)
         if (std::fabs(x) > 1e-6f) ++nnz;
     float zero_ratio = 1.0f - ((float)nnz / (float)v.size());
-    return zero_ratio >= config_.sparse_threshold;
+    return zero_ratio >= threshold;
+}
+
+bool VectorEngine::should_use_sparse(const std::vector<float> &v) const {
+    return should_use_sparse_with_threshold(v, config_.sparse_threshold);
 }
 
 Result<Unit> VectorEngine::store_in_space(Space &sp, const std::string &key,
@@ -633,23 +641,27 @@ std::optional<size_t> VectorEngine::dimension() const {
     return (size_t)default_space_->buckets.begin()->first;
 }
 
-Result<size_t> VectorEngine::batch_store_embeddings(
-    const std::vector<std::pair<std::string, std::vector<float>>> &items) {
-    for (size_t i = 0; i < items.size(); ++i) {
-        if (items[i].second.empty()) {
-            VectorError e = err(ErrorKind::InvalidArgument,
-                                "batch validation failed at index " + std::to_string(i) +
-                                    ": empty vector");
+Result<VectorEngine::BatchResult> VectorEngine::batch_store_embeddings(
+    const std::vector<EmbeddingInput> &inputs) {
+    BatchResult out;
+    for (size_t i = 0; i < inputs.size(); ++i)
+        if (inputs[i].vector.empty()) {
+            VectorError e = err(ErrorKind::BatchValidationError, "Empty vector provided");
+            e.index = i;
             return e;
         }
-        if (config_.max_dimension && items[i].second.size() > *config_.max_dimension)
-            return dim_mismatch(*config_.max_dimension, items[i].second.size());
+    out.stored_keys.reserve(inputs.size());
+    for (size_t i = 0; i < inputs.size(); ++i) {
+        auto r = store_embedding(inputs[i].key, inputs[i].vector);
+        if (r.is_err()) {
+            VectorError e = err(ErrorKind::BatchOperationError, r.error().to_string());
+            e.index = i;
+            return e;
+        }
+        out.stored_keys.push_back(inputs[i].key);
     }
-    for (auto &kv : items) {
-        auto r = store_embedding(kv.first, kv.second);
-        if (r.is_err()) return r.error();
-    }
-    return items.size();
+    out.count = out.stored_keys.size();
+    return out;
 }
 
 Result<std::vector<SearchResult>> VectorEngine::search_similar(const std::vector<float> &query,
@@ -864,6 +876,16 @@ Result<Metadata> VectorEngine::get_metadata(const std::string &key) const {
     return sp.buckets.at(it->second.first)->meta[it->second.second];
 }
 
+Result<Metadata> VectorEngine::get_collection_metadata(const std::string &collection,
+                                                       const std::string &key) const {
+    std::shared_ptr<const Space> sp = find_collection_space(collection);
+    if (!sp) return err(ErrorKind::NotFound, key);
+    std::shared_lock<std::shared_mutex> g(sp->mu);
+    auto it = sp->where.find(key);
+    if (it == sp->where.end()) return err(ErrorKind::NotFound, key);
+    return sp->buckets.at(it->second.first)->meta[it->second.second];
+}
+
 Result<Unit> VectorEngine::update_metadata(const std::string &key, const Metadata &metadata) {
     Space &sp = *default_space_;
     std::unique_lock<std::shared_mutex> g(sp.mu);
@@ -919,6 +941,36 @@ std::vector<std::string> VectorEngine::list_keys_bounded() const {
             if (out.size() >= limit) return out;
             out.push_back(k);
         }
+    return out;
+}
+
+VectorEngine::PagedResult<std::string> VectorEngine::list_keys_paginated(Pagination pagination) const {
+    const size_t max_scan = config_.max_keys_per_scan.value_or(SIZE_MAX);
+    const size_t want = pagination.limit.value_or(max_scan);
+    const size_t fetch_limit =
+        std::min(pagination.skip > SIZE_MAX - want ? SIZE_MAX : pagination.skip + want, max_scan);
+    PagedResult<std::string> out;
+    size_t total = 0;
+    {
+        std::shared_lock<std::shared_mutex> g(default_space_->mu);
+        size_t seen = 0;
+        for (auto &kv : default_space_->buckets) {
+            for (auto &k : kv.second->keys) {
+                if (seen >= fetch_limit) break;
+                if (seen >= pagination.skip && out.items.size() < pagination.limit.value_or(SIZE_MAX))
+                    out.items.push_back(k);
+                ++seen;
+            }
+        }
+        total = default_space_->where.size();
+    }
+    if (pagination.count_total) {
+        out.total_count = total;
+        out.has_more = (pagination.skip > SIZE_MAX - out.items.size() ? SIZE_MAX
+                                                                        : pagination.skip + out.items.size()) < total;
+    } else {
+        out.has_more = out.items.size() == pagination.limit.value_or(0);
+    }
     return out;
 }
 
@@ -1172,6 +1224,22 @@ bool VectorEngine::entity_has_embedding(const std::string &entity_key) const {
 
 Result<Unit> VectorEngine::remove_entity_embedding(const std::string &entity_key) {
     return delete_in_space(*entity_space_, entity_key);
+}
+
+std::vector<std::string> VectorEngine::scan_entities_with_embeddings() const {
+    const size_t limit = config_.max_keys_per_scan.value_or(SIZE_MAX);
+    std::vector<std::string> out;
+    std::shared_lock<std::shared_mutex> g(entity_space_->mu);
+    for (auto &kv : entity_space_->buckets)
+        for (auto &k : kv.second->keys) {
+            if (out.size() >= limit) return out;
+            out.push_back(k);
+        }
+    return out;
+}
+
+size_t VectorEngine::count_entities_with_embeddings() const {
+    return scan_entities_with_embeddings().size();
 }
 
 Result<std::vector<SearchResult>> VectorEngine::search_entities(const std::vector<float> &query,

@@ -4,8 +4,8 @@
 // to the device through the nm_* C ABI (include/neumann_b200.h).  There is no CPU scan here:
 // without a CUDA device the search methods return StorageError.
 //
-// Not mirrored (out of scope): HNSW/IVF wrappers, metadata filters, pagination,
-// persistence, entity embeddings.
+// Not mirrored (out of scope): HNSW / IVF / PQ wrappers and persistence.
+// tests/cpp/reference_suite.cpp replays the reference's own unit tests against this class.
 #pragma once
 #include <chrono>
 #include <cstdint>
@@ -45,12 +45,15 @@ enum class ErrorKind : int {
     CollectionNotFound,
     SearchTimeout,
     InvalidArgument,
+    BatchValidationError,  // { index, cause } — cause in `message`
+    BatchOperationError,   // { index, cause }
 };
 
 struct VectorError {
     ErrorKind kind = ErrorKind::StorageError;
     std::string message;       // NotFound(key) / StorageError(msg) / ConfigurationError(msg) / ...
     size_t expected = 0, got = 0;  // DimensionMismatch
+    size_t index = 0;          // BatchValidationError / BatchOperationError
     std::string operation;     // SearchTimeout
     uint64_t timeout_ms = 0;   // SearchTimeout
     int status() const;        // nm_status code
@@ -92,6 +95,27 @@ struct VectorEngineConfig {
     // either way; the copy costs +1 byte per element.
     bool device_prefilter = false;
     Result<Unit> validate() const;  // lib.rs:771-826
+    // presets, lib.rs:666-700 (the index-file limits of the reference belong to persistence)
+    static VectorEngineConfig high_throughput() {
+        VectorEngineConfig c;
+        c.parallel_threshold = 1000;
+        return c;
+    }
+    VectorEngineConfig with_search_timeout(std::chrono::nanoseconds t) const {  // lib.rs:1000
+        VectorEngineConfig c = *this;
+        // milliseconds, like Deadline::timeout_ms: a sub-millisecond timeout (the 1 ns of the
+        // reference's tests) is 0 ms = expired at the first check
+        c.search_timeout = std::chrono::duration_cast<std::chrono::milliseconds>(t);
+        return c;
+    }
+    static VectorEngineConfig low_memory() {
+        VectorEngineConfig c;
+        c.sparse_threshold = 0.3f;
+        c.max_dimension = 4096;
+        c.max_keys_per_scan = 10000;
+        c.search_timeout = std::chrono::milliseconds(30000);
+        return c;
+    }
 };
 
 // vector_engine/src/lib.rs:455-499
@@ -100,6 +124,22 @@ struct VectorCollectionConfig {
     DistanceMetric distance_metric = DistanceMetric::Cosine;
     bool auto_index = false;          // kept for API parity (HNSW is out of scope)
     size_t auto_index_threshold = 1000;
+    VectorCollectionConfig with_dimension(size_t dim) const {
+        VectorCollectionConfig c = *this;
+        c.dimension = dim;
+        return c;
+    }
+    VectorCollectionConfig with_metric(DistanceMetric m) const {
+        VectorCollectionConfig c = *this;
+        c.distance_metric = m;
+        return c;
+    }
+    VectorCollectionConfig with_auto_index(size_t threshold) const {
+        VectorCollectionConfig c = *this;
+        c.auto_index = true;
+        c.auto_index_threshold = threshold;
+        return c;
+    }
 };
 
 // The reference's f32 helpers this layer needs on the host (zero-query short-circuit,
@@ -134,9 +174,17 @@ class VectorEngine {
     std::vector<std::string> list_keys_bounded() const;
     Result<size_t> clear();
     Result<size_t> batch_delete_embeddings(const std::vector<std::string> &keys);
-    // lib.rs:2865-2913 (validation first, then stores; returns number stored)
-    Result<size_t> batch_store_embeddings(
-        const std::vector<std::pair<std::string, std::vector<float>>> &items);
+    // lib.rs:1005-1046, 2858-2913: every input is validated first (BatchValidationError { index }),
+    // then stored in order; a store that fails reports BatchOperationError { index, cause }.
+    struct EmbeddingInput {
+        std::string key;
+        std::vector<float> vector;
+    };
+    struct BatchResult {
+        std::vector<std::string> stored_keys;
+        size_t count = 0;
+    };
+    Result<BatchResult> batch_store_embeddings(const std::vector<EmbeddingInput> &inputs);
 
     // lib.rs:1950-2037, 2049-2101
     Result<std::vector<SearchResult>> search_similar(const std::vector<float> &query,
@@ -184,18 +232,43 @@ class VectorEngine {
     Result<std::vector<float>> get_entity_embedding(const std::string &entity_key) const;
     bool entity_has_embedding(const std::string &entity_key) const;
     Result<Unit> remove_entity_embedding(const std::string &entity_key);
+    // lib.rs:3224-3237 (at most max_keys_per_scan entities are visited, as there)
+    std::vector<std::string> scan_entities_with_embeddings() const;
+    size_t count_entities_with_embeddings() const;
     // lib.rs:1052-1121, 2988-3058: pagination over the ranked hits
     struct Pagination {
         size_t skip = 0;
         std::optional<size_t> limit;
         bool count_total = false;
+        static Pagination with(size_t skip, size_t limit) {  // Pagination::new
+            Pagination p;
+            p.skip = skip;
+            p.limit = limit;
+            return p;
+        }
+        static Pagination skip_only(size_t skip) {
+            Pagination p;
+            p.skip = skip;
+            return p;
+        }
+        Pagination with_total() const {
+            Pagination p = *this;
+            p.count_total = true;
+            return p;
+        }
     };
     template <class T>
     struct PagedResult {
         std::vector<T> items;
         std::optional<size_t> total_count;
         bool has_more = false;
+        static PagedResult empty() {
+            PagedResult r;
+            r.total_count = 0;
+            return r;
+        }
     };
+    PagedResult<std::string> list_keys_paginated(Pagination pagination) const;  // lib.rs:2946-2981
     Result<PagedResult<SearchResult>> search_similar_paginated(const std::vector<float> &query,
                                                               size_t top_k, Pagination pagination) const;
     Result<PagedResult<SearchResult>> search_entities_paginated(const std::vector<float> &query,
@@ -233,6 +306,8 @@ class VectorEngine {
     bool exists_in_collection(const std::string &collection, const std::string &key) const;   // lib.rs:1537
     std::vector<std::string> list_collection_keys(const std::string &collection) const;       // lib.rs:1543
     std::optional<VectorCollectionConfig> get_collection_config(const std::string &name) const;  // lib.rs:1412
+    Result<Metadata> get_collection_metadata(const std::string &collection,
+                                             const std::string &key) const;                   // lib.rs:1557
     Result<std::vector<SearchResult>> search_in_collection(const std::string &collection,
                                                            const std::vector<float> &query,
                                                            size_t top_k) const;
@@ -266,6 +341,9 @@ class VectorEngine {
     std::shared_ptr<const Space> find_collection_space(const std::string &name) const;
 
     bool should_use_sparse(const std::vector<float> &v) const;  // lib.rs:1871-1886
+  public:
+    static bool should_use_sparse_with_threshold(const std::vector<float> &v, float threshold);  // lib.rs:1876
+  private:
     Result<Unit> store_in_space(Space &sp, const std::string &key, std::vector<float> vector,
                                 const Metadata *metadata = nullptr);
     Result<std::vector<SearchResult>> filtered_in_space(

@@ -1,0 +1,47 @@
+"""tests/cpp/reference_suite.cpp: the reference's own vector_engine unit tests (218 of them: store /
+get / delete, search_similar*, metrics, sparse storage, entities, pagination, batch operations,
+metadata, filtered search, collections, timeouts, concurrency, edge values) restated against the
+C++ host mirror, each under the reference test's name with its lib.rs line.  The tests that never
+search run here on the CPU; the whole suite (searches on the device) runs under -m gpu."""
+import re
+import subprocess
+from pathlib import Path
+
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def _build(tmp_path) -> Path:
+    from neumann_b200 import build as nb
+    nb.build_library()  # no-op when the in-tree library matches the sources
+    exe = tmp_path / "reference_suite"
+    cmd = ["g++", "-std=c++17", "-O1", "-Wall", "-Wextra", "-Wno-unused-function",
+           str(ROOT / "tests" / "cpp" / "reference_suite.cpp"),
+           "-I", str(ROOT / "neumann_b200" / "csrc"), "-I", str(ROOT / "include"),
+           "-L", str(ROOT / "neumann_b200"), "-lneumann_b200", "-pthread",
+           "-Wl,-rpath," + str(ROOT / "neumann_b200"), "-o", str(exe)]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    return exe
+
+
+def _summary(stdout: str):
+    m = re.search(r"reference_suite: (\d+) tests run, (\d+) skipped \(need a device\), (\d+) failed", stdout)
+    assert m, stdout
+    return tuple(int(x) for x in m.groups())
+
+
+def test_reference_suite_host_side(tmp_path):
+    r = subprocess.run([str(_build(tmp_path)), "--host"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, (r.stdout, r.stderr)
+    ran, skipped, failed = _summary(r.stdout)
+    assert failed == 0 and ran >= 149 and ran + skipped >= 218
+
+
+@pytest.mark.gpu
+def test_reference_suite_on_the_device(tmp_path):
+    r = subprocess.run([str(_build(tmp_path))], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, (r.stdout, r.stderr)
+    ran, skipped, failed = _summary(r.stdout)
+    assert failed == 0 and skipped == 0 and ran >= 218
