@@ -123,7 +123,8 @@ int nm_engine_search_entities(nm_engine *e, const float *query, size_t n, size_t
                               nm_results **out);
 
 /* QueryRouter::execute (legacy string path) / execute_parsed (AST path), SIMILAR + EMBED only.
- * *out is NULL for QueryResult::Empty. */
+ * *out is NULL for every result that is not QueryResult::Similar (Empty; the Value of EMBED GET
+ * and the Count of EMBED DELETE / BATCH are available through the C++ API only). */
 int nm_engine_execute(nm_engine *e, const char *command, nm_results **out);
 int nm_engine_execute_parsed(nm_engine *e, const char *command, nm_results **out);
 

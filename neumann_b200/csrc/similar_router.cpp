@@ -4,6 +4,8 @@
 #include <algorithm>
 #include <cctype>
 #include <cerrno>
+#include <charconv>
+#include <cmath>
 #include <cstdlib>
 
 namespace neumann {
@@ -41,6 +43,49 @@ RouterOutcome ok_similar(const std::vector<SearchResult> &rs) {
     o.result.kind = QueryResult::Kind::Similar;
     for (auto &r : rs) o.result.similar.push_back(SimilarResult{r.key, r.score});
     return o;
+}
+
+RouterOutcome ok_value(std::string v) {
+    RouterOutcome o;
+    o.ok = true;
+    o.result.kind = QueryResult::Kind::Value;
+    o.result.value = std::move(v);
+    return o;
+}
+RouterOutcome ok_count(size_t n) {
+    RouterOutcome o;
+    o.ok = true;
+    o.result.kind = QueryResult::Kind::Count;
+    o.result.count = n;
+    return o;
+}
+
+// One f32 the way Rust's `{:?}` prints it: the shortest digits that round-trip, plain decimals
+// with at least one fractional digit for 1e-4 <= |x| < 1e16, `1e30` / `1e-18` outside.
+std::string rust_debug_f32(float x) {
+    if (std::isnan(x)) return "NaN";
+    if (std::isinf(x)) return x < 0 ? "-inf" : "inf";
+    char buf[64];
+    const float ax = std::fabs(x);
+    if (x == 0.0f || (ax >= 1e-4f && ax < 1e16f)) {
+        auto r = std::to_chars(buf, buf + sizeof buf, x, std::chars_format::fixed);
+        std::string s(buf, r.ptr);
+        if (s.find('.') == std::string::npos) s += ".0";
+        return s;
+    }
+    auto r = std::to_chars(buf, buf + sizeof buf, x, std::chars_format::scientific);
+    std::string s(buf, r.ptr);  // d.ddde+XX
+    const size_t e = s.find('e');
+    std::string mant = s.substr(0, e), ex = s.substr(e + 1);
+    const bool neg = !ex.empty() && ex[0] == '-';
+    if (!ex.empty() && (ex[0] == '+' || ex[0] == '-')) ex.erase(ex.begin());
+    while (ex.size() > 1 && ex[0] == '0') ex.erase(ex.begin());
+    return mant + "e" + (neg ? "-" : "") + ex;
+}
+std::string rust_debug_vec(const std::vector<float> &v) {
+    std::string s = "[";
+    for (size_t i = 0; i < v.size(); ++i) s += (i ? ", " : "") + rust_debug_f32(v[i]);
+    return s + "]";
 }
 
 // QR:6884-6901 parse_vector: strip brackets, split on ',', Rust f32::from_str per item.
@@ -89,19 +134,48 @@ bool parse_usize(const std::string &tok, size_t *out) {
     *out = (size_t)v;
     return true;
 }
-std::string strip_quotes(const std::string &s) {
-    std::string t = trim(s);
-    if (t.size() >= 2 && ((t.front() == '"' && t.back() == '"') ||
-                          (t.front() == '\'' && t.back() == '\'')))
-        return t.substr(1, t.size() - 2);
-    return t;
-}
 // split "<first-word> <rest>" on the first whitespace run
 void split_first(const std::string &s, std::string *first, std::string *rest) {
     size_t i = 0;
     while (i < s.size() && !std::isspace((unsigned char)s[i])) ++i;
     *first = s.substr(0, i);
     *rest = i < s.size() ? trim(s.substr(i)) : std::string();
+}
+
+// A key expression of the AST grammar at the front of *s: 'string', "string" or identifier.
+// Consumes it; anything else (a number, a bracket) is not a key (QR expr_to_string).
+bool take_key_expr(std::string *s, std::string *key) {
+    *s = trim(*s);
+    if (s->empty()) return false;
+    const char c = (*s)[0];
+    if (c == '\'' || c == '"') {
+        const size_t e = s->find(c, 1);
+        if (e == std::string::npos) return false;
+        *key = s->substr(1, e - 1);
+        *s = trim(s->substr(e + 1));
+        return true;
+    }
+    if (!(std::isalpha((unsigned char)c) || c == '_')) return false;
+    size_t i = 0;
+    while (i < s->size() && (std::isalnum((unsigned char)(*s)[i]) || (*s)[i] == '_' || (*s)[i] == ':' ||
+                             (*s)[i] == '.' || (*s)[i] == '-'))
+        ++i;
+    *key = s->substr(0, i);
+    *s = trim(s->substr(i));
+    return true;
+}
+// Optional `INTO ident` at the front of *s.  false = malformed (INTO without a name).
+bool take_into(std::string *s, std::string *collection, bool *has) {
+    *has = false;
+    std::string kw, rest;
+    split_first(trim(*s), &kw, &rest);
+    if (upper(kw) != "INTO") return true;
+    std::string name;
+    split_first(rest, &name, s);
+    if (name.empty()) return false;
+    *collection = name;
+    *has = true;
+    return true;
 }
 
 }  // namespace
@@ -167,29 +241,83 @@ RouterOutcome QueryRouter::execute_parsed(const std::string &command_in) {
     const std::string op = upper(word);
 
     if (op == "EMBED") {
-        // `EMBED STORE 'key' [..] [INTO coll]` (parser.rs EmbedOp::Store) or the legacy form
+        // parser.rs:1777-1851 + exec_embed QR:5228-5311; a bare `EMBED key [..]` is the legacy form
         std::string w2, r2;
         split_first(rest, &w2, &r2);
-        if (upper(w2) != "STORE") return execute(command);
-        size_t lb = r2.find('['), rb = r2.rfind(']');
-        if (lb == std::string::npos || rb == std::string::npos || rb < lb)
+        const std::string sub = upper(w2);
+        std::string collection;
+        bool has_collection = false;
+        if (sub == "GET" || sub == "DELETE") {
+            std::string key;
+            if (!take_key_expr(&r2, &key)) return fail(RouterError::Kind::ParseError, "expected a key after EMBED " + sub);
+            if (!take_into(&r2, &collection, &has_collection))
+                return fail(RouterError::Kind::ParseError, "expected collection name after INTO");
+            if (sub == "GET") {
+                auto g = has_collection ? vector_.get_from_collection(collection, key) : vector_.get_embedding(key);
+                if (g.is_err()) return from_vector_error(g.error());
+                return ok_value(rust_debug_vec(g.value()));
+            }
+            auto d = has_collection ? vector_.delete_from_collection(collection, key) : vector_.delete_embedding(key);
+            if (d.is_err()) return from_vector_error(d.error());
+            return ok_count(1);
+        }
+        if (sub == "BATCH") {
+            // EMBED BATCH [('key', [v, ...]), ...] [INTO coll]: items are stored in order, the
+            // first failure ends the statement (what was stored stays stored, as in the reference)
+            std::string t = trim(r2);
+            if (t.empty() || t[0] != '[') return fail(RouterError::Kind::ParseError, "expected [ after EMBED BATCH");
+            t = trim(t.substr(1));
+            std::vector<std::pair<std::string, std::vector<float>>> items;
+            while (!t.empty() && t[0] != ']') {
+                if (t[0] != '(') return fail(RouterError::Kind::ParseError, "expected ( in EMBED BATCH");
+                t = t.substr(1);
+                std::string key;
+                if (!take_key_expr(&t, &key)) return fail(RouterError::Kind::ParseError, "expected a key in EMBED BATCH");
+                if (t.empty() || t[0] != ',') return fail(RouterError::Kind::ParseError, "expected , after the key");
+                t = trim(t.substr(1));
+                const size_t rb = t.find(']');
+                if (t.empty() || t[0] != '[' || rb == std::string::npos)
+                    return fail(RouterError::Kind::ParseError, "expected [vector] in EMBED BATCH");
+                std::vector<float> v;
+                std::string why;
+                if (trim(t.substr(1, rb - 1)).empty()) v.clear();
+                else if (!parse_vector(t.substr(0, rb + 1), &v, &why))
+                    return fail(RouterError::Kind::InvalidArgument, why);
+                t = trim(t.substr(rb + 1));
+                if (t.empty() || t[0] != ')') return fail(RouterError::Kind::ParseError, "expected ) in EMBED BATCH");
+                t = trim(t.substr(1));
+                items.emplace_back(std::move(key), std::move(v));
+                if (!t.empty() && t[0] == ',') t = trim(t.substr(1));
+                else break;
+            }
+            if (t.empty() || t[0] != ']') return fail(RouterError::Kind::ParseError, "expected ] after EMBED BATCH items");
+            t = trim(t.substr(1));
+            if (!take_into(&t, &collection, &has_collection))
+                return fail(RouterError::Kind::ParseError, "expected collection name after INTO");
+            size_t count = 0;
+            for (auto &kv : items) {
+                auto r = has_collection ? vector_.store_in_collection(collection, kv.first, std::move(kv.second))
+                                        : vector_.store_embedding(kv.first, std::move(kv.second));
+                if (r.is_err()) return from_vector_error(r.error());
+                ++count;
+            }
+            return ok_count(count);
+        }
+        if (sub != "STORE") return execute(command);
+        std::string key;
+        if (!take_key_expr(&r2, &key)) return fail(RouterError::Kind::ParseError, "expected a key after EMBED STORE");
+        const size_t rb = r2.find(']');
+        if (r2.empty() || r2[0] != '[' || rb == std::string::npos)
             return fail(RouterError::Kind::ParseError, "expected [vector]");
-        std::string key = strip_quotes(r2.substr(0, lb));
         std::vector<float> v;
         std::string why;
-        if (!parse_vector(r2.substr(lb, rb - lb + 1), &v, &why))
+        if (!parse_vector(r2.substr(0, rb + 1), &v, &why))
             return fail(RouterError::Kind::InvalidArgument, why);
         std::string tail = trim(r2.substr(rb + 1));
-        Result<Unit> r = Unit{};
-        if (!tail.empty()) {
-            std::string kw, coll;
-            split_first(tail, &kw, &coll);
-            if (upper(kw) != "INTO" || coll.empty())
-                return fail(RouterError::Kind::ParseError, "unexpected tokens: " + tail);
-            r = vector_.store_in_collection(coll, key, std::move(v));
-        } else {
-            r = vector_.store_embedding(key, std::move(v));
-        }
+        if (!take_into(&tail, &collection, &has_collection))
+            return fail(RouterError::Kind::ParseError, "expected collection name after INTO");
+        Result<Unit> r = has_collection ? vector_.store_in_collection(collection, key, std::move(v))
+                                        : vector_.store_embedding(key, std::move(v));
         if (r.is_err()) return from_vector_error(r.error());
         return ok_empty();
     }
@@ -263,7 +391,7 @@ RouterOutcome QueryRouter::execute_parsed(const std::string &command_in) {
             has_collection = true;
             stage = 3;
         } else {
-            return fail(RouterError::Kind::ParseError, "unexpected token: " + kw);
+            break;  // not part of this statement: parser::parse never looks at what follows it
         }
     }
 

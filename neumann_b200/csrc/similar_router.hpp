@@ -20,10 +20,12 @@ struct SimilarResult {
     float score;
 };
 
-// QueryResult (QR:265-266) restricted to what this operator returns.
+// QueryResult (QR:265-266) restricted to what SIMILAR and EMBED return.
 struct QueryResult {
-    enum class Kind { Empty, Similar } kind = Kind::Empty;
+    enum class Kind { Empty, Similar, Value, Count } kind = Kind::Empty;
     std::vector<SimilarResult> similar;
+    std::string value;  // Value: EMBED GET prints the vector as Rust's {:?} would
+    size_t count = 0;   // Count: EMBED DELETE (1) / EMBED BATCH (embeddings stored)
 };
 
 struct RouterError {
@@ -45,8 +47,13 @@ class QueryRouter {
     VectorEngine &vector() { return vector_; }
     // Legacy string commands: `EMBED <key> [v, ...]`, `SIMILAR <key|[v, ...]> [TOP k]`.
     RouterOutcome execute(const std::string &command);
-    // AST grammar: `SIMILAR <'key'|ident|[v, ...]> [LIMIT k] [COSINE|EUCLIDEAN|DOT_PRODUCT]
-    // [INTO collection]`; `EMBED STORE 'key' [v, ...] [INTO collection]` and the legacy EMBED.
+    // AST grammar (neumann_parser/src/parser.rs:1777-1919): `SIMILAR <'key'|ident|[v, ...]>
+    // [LIMIT k] [COSINE|EUCLIDEAN|DOT_PRODUCT] [INTO collection] [WHERE expr]` — the clauses in THIS
+    // order; `EMBED STORE 'key' [v, ...]`, `EMBED GET key`, `EMBED DELETE key`,
+    // `EMBED BATCH [('k', [v, ...]), ...]`, each with an optional `INTO collection`.  Like the
+    // reference's `parser::parse`, which reads ONE statement and never looks at what follows it,
+    // tokens after the last clause that fits the grammar are ignored (`SIMILAR [1, 0] COSINE
+    // LIMIT 3` is a cosine search with the default limit of 10: QR's own tests rely on it).
     RouterOutcome execute_parsed(const std::string &command);
 
   private:

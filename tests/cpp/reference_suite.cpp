@@ -5,6 +5,9 @@
 // reference's assertions.  Tests of subsystems outside SURVEY §8 (HNSW / IVF / PQ wrappers,
 // persistence, TensorStore plumbing) are not here.
 //
+// The last section does the same for the SIMILAR / EMBED tests of query_router/src/lib.rs against
+// neumann::QueryRouter (similar_router.hpp).
+//
 // Test infrastructure: built and run by tests/test_cpp_reference_suite.py
 //   g++ -std=c++17 tests/cpp/reference_suite.cpp -Ineumann_b200/csrc -Iinclude -Lneumann_b200 -lneumann_b200
 //   ./reference_suite            every test (needs a CUDA device: searches run on the GPU)
@@ -19,6 +22,7 @@
 #include <thread>
 #include <vector>
 
+#include "similar_router.hpp"
 #include "vector_engine.hpp"
 
 using namespace neumann;
@@ -1710,6 +1714,253 @@ TEST_HOST(clear_all_embeddings, "lib.rs:9548") {
 TEST_HOST(clear_empty_engine, "lib.rs:9565") {
     VectorEngine engine;
     REQUIRE(engine.clear().value() == 0);
+}
+
+// ---------------------------------------------------------------------------------------------
+// query_router: the SIMILAR operator and the EMBED command that feeds it
+// (query_router/src/lib.rs tests; "QR" below).  Router = QueryRouter::new() + its own VectorEngine.
+// ---------------------------------------------------------------------------------------------
+struct Router {
+    VectorEngine engine;
+    QueryRouter router{engine};
+    RouterOutcome execute(const std::string &c) { return router.execute(c); }
+    RouterOutcome execute_parsed(const std::string &c) { return router.execute_parsed(c); }
+};
+#define REQUIRE_KIND(o, k) REQUIRE((o).ok && (o).result.kind == QueryResult::Kind::k)
+
+TEST_HOST(routes_embed_to_vector, "QR:7656") {
+    Router r;
+    auto o = r.execute("EMBED doc1 [1.0, 0.0, 0.0]");
+    REQUIRE_KIND(o, Empty);
+    REQUIRE(r.engine.exists("doc1"));
+}
+TEST_GPU(routes_similar_to_vector, "QR:7669") {
+    Router r;
+    REQUIRE(r.execute("EMBED doc1 [1.0, 0.0, 0.0]").ok);
+    REQUIRE(r.execute("EMBED doc2 [0.0, 1.0, 0.0]").ok);
+    REQUIRE(r.execute("EMBED doc3 [0.9, 0.1, 0.0]").ok);
+    auto o = r.execute("SIMILAR doc1 TOP 2");
+    REQUIRE_KIND(o, Similar);
+    REQUIRE(o.result.similar.size() == 2);
+    REQUIRE(o.result.similar[0].key == "doc1");
+}
+TEST_HOST(handles_embedding_not_found, "QR:7815") {
+    Router r;
+    auto o = r.execute("SIMILAR nonexistent TOP 5");
+    REQUIRE(!o.ok && o.error.kind == RouterError::Kind::VectorError);
+}
+TEST_GPU(embed_and_similar_inline, "QR:8051") {
+    Router r;
+    REQUIRE(r.execute("EMBED v1 [1.0, 0.0]").ok);
+    REQUIRE(r.execute("EMBED v2 [0.0, 1.0]").ok);
+    auto o = r.execute("SIMILAR [1.0, 0.0] TOP 1");
+    REQUIRE_KIND(o, Similar);
+    REQUIRE(o.result.similar.size() == 1 && o.result.similar[0].key == "v1");
+}
+TEST_GPU(similar_with_inline_vector, "QR:8467") {
+    Router r;
+    REQUIRE(r.execute("EMBED v1 [1.0, 0.0, 0.0]").ok);
+    auto o = r.execute("SIMILAR [0.9, 0.1, 0.0] TOP 1");
+    REQUIRE_KIND(o, Similar);
+    REQUIRE(o.result.similar.size() == 1);
+}
+TEST_HOST(missing_embed_args, "QR:8537") {
+    Router r;
+    REQUIRE(!r.execute("EMBED").ok);
+}
+TEST_HOST(missing_similar_args, "QR:8544") {
+    Router r;
+    REQUIRE(!r.execute("SIMILAR").ok);
+}
+TEST_HOST(embed_with_empty_brackets, "QR:8858") {
+    Router r;
+    REQUIRE(!r.execute("EMBED emptykey []").ok);
+}
+TEST_HOST(similar_no_results, "QR:8948") {
+    Router r;
+    REQUIRE(!r.execute("SIMILAR nonexistent TOP 5").ok);
+}
+TEST_HOST(parsed_embed_store, "QR:9361") {
+    Router r;
+    REQUIRE_KIND(r.execute_parsed("EMBED STORE 'key1' [1.0, 2.0, 3.0]"), Empty);
+}
+TEST_HOST(parsed_embed_get, "QR:9370") {
+    Router r;
+    REQUIRE(r.execute("EMBED vec1 [1.0, 2.0, 3.0]").ok);
+    auto o = r.execute_parsed("EMBED GET 'vec1'");
+    REQUIRE_KIND(o, Value);
+    REQUIRE(o.result.value == "[1.0, 2.0, 3.0]");  // format!("{vec:?}"); the reference asserts contains("1")
+}
+TEST_HOST(parsed_embed_delete, "QR:9382") {
+    Router r;
+    REQUIRE(r.execute("EMBED todelete [1.0, 2.0]").ok);
+    auto o = r.execute_parsed("EMBED DELETE 'todelete'");
+    REQUIRE_KIND(o, Count);
+    REQUIRE(o.result.count == 1);
+}
+TEST_GPU(parsed_similar_by_key, "QR:9394") {
+    Router r;
+    REQUIRE(r.execute("EMBED item1 [1.0, 0.0, 0.0]").ok);
+    REQUIRE(r.execute("EMBED item2 [0.9, 0.1, 0.0]").ok);
+    auto o = r.execute_parsed("SIMILAR 'item1' LIMIT 5");
+    REQUIRE_KIND(o, Similar);
+    REQUIRE(!o.result.similar.empty());
+}
+TEST_GPU(parsed_similar_by_vector, "QR:9407") {
+    Router r;
+    REQUIRE(r.execute("EMBED vec1 [1.0, 0.0, 0.0]").ok);
+    REQUIRE(r.execute("EMBED vec2 [0.0, 1.0, 0.0]").ok);
+    auto o = r.execute_parsed("SIMILAR [1.0, 0.0, 0.0] LIMIT 5");
+    REQUIRE_KIND(o, Similar);
+    REQUIRE(!o.result.similar.empty());
+}
+TEST_GPU(parsed_similar_cosine_metric, "QR:9436") {
+    Router r;
+    REQUIRE(r.execute("EMBED cos_a [1.0, 0.0]").ok);
+    REQUIRE(r.execute("EMBED cos_b [0.0, 1.0]").ok);
+    REQUIRE(r.execute("EMBED cos_c [0.707, 0.707]").ok);
+    // the metric comes AFTER the limit in the grammar: here `LIMIT 3` follows the statement and
+    // is never read (parser::parse reads one statement) — the default limit of 10 applies
+    auto o = r.execute_parsed("SIMILAR [1.0, 0.0] COSINE LIMIT 3");
+    REQUIRE_KIND(o, Similar);
+    REQUIRE(o.result.similar.size() == 3);
+    REQUIRE(o.result.similar[0].key == "cos_a");
+}
+TEST_GPU(parsed_similar_euclidean_metric, "QR:9457") {
+    Router r;
+    REQUIRE(r.execute("EMBED euc_a [1.0, 0.0]").ok);
+    REQUIRE(r.execute("EMBED euc_b [2.0, 0.0]").ok);
+    REQUIRE(r.execute("EMBED euc_c [10.0, 0.0]").ok);
+    auto o = r.execute_parsed("SIMILAR [1.0, 0.0] EUCLIDEAN LIMIT 3");
+    REQUIRE_KIND(o, Similar);
+    REQUIRE(o.result.similar.size() == 3);
+    REQUIRE(o.result.similar[0].key == "euc_a");
+}
+TEST_GPU(parsed_similar_euclidean_zero_query, "QR:9478") {
+    Router r;
+    REQUIRE(r.execute("EMBED zero_origin [0.0, 0.0]").ok);
+    REQUIRE(r.execute("EMBED zero_unit [1.0, 0.0]").ok);
+    REQUIRE(r.execute("EMBED zero_far [10.0, 0.0]").ok);
+    auto o = r.execute_parsed("SIMILAR [0.0, 0.0] EUCLIDEAN LIMIT 3");
+    REQUIRE_KIND(o, Similar);
+    REQUIRE(o.result.similar.size() == 3);
+    REQUIRE(o.result.similar[0].key == "zero_origin");
+    REQUIRE(std::fabs(o.result.similar[0].score - 1.0f) < 0.01f);
+}
+TEST_GPU(parsed_similar_dot_product_metric, "QR:9505") {
+    Router r;
+    REQUIRE(r.execute("EMBED dot_a [1.0, 0.0]").ok);
+    REQUIRE(r.execute("EMBED dot_b [2.0, 0.0]").ok);
+    REQUIRE(r.execute("EMBED dot_c [0.5, 0.0]").ok);
+    auto o = r.execute_parsed("SIMILAR [1.0, 0.0] DOT_PRODUCT LIMIT 3");
+    REQUIRE_KIND(o, Similar);
+    REQUIRE(o.result.similar.size() == 3);
+    REQUIRE(o.result.similar[0].key == "dot_b");
+}
+TEST_GPU(parsed_similar_with_limit_expr, "QR:10526") {
+    Router r;
+    REQUIRE(r.execute("EMBED v1 [1.0, 0.0]").ok);
+    REQUIRE(r.execute("EMBED v2 [0.0, 1.0]").ok);
+    REQUIRE_KIND(r.execute_parsed("SIMILAR 'v1' LIMIT 10"), Similar);
+}
+TEST_HOST(parsed_embed_store_with_list, "QR:10537") {
+    Router r;
+    REQUIRE(r.execute_parsed("EMBED STORE 'stored_vec' [1.0, 2.0, 3.0]").ok);
+    REQUIRE_KIND(r.execute_parsed("EMBED GET 'stored_vec'"), Value);
+}
+TEST_HOST(parsed_embed_with_int_values, "QR:10635") {
+    Router r;
+    REQUIRE(r.execute_parsed("EMBED STORE 'intvec' [1, 2, 3]").ok);
+    REQUIRE(r.engine.get_embedding("intvec").value() == (Vec{1.0f, 2.0f, 3.0f}));
+}
+TEST_HOST(parsed_similar_limit_not_integer, "QR:10709") {
+    Router r;
+    REQUIRE(r.execute("EMBED v [1.0, 2.0]").ok);
+    REQUIRE(!r.execute_parsed("SIMILAR 'v' LIMIT 'ten'").ok);
+}
+TEST_HOST(parsed_embed_get_with_ident_key, "QR:10757") {
+    Router r;
+    REQUIRE(r.execute("EMBED mykey [1.0, 2.0]").ok);
+    REQUIRE_KIND(r.execute_parsed("EMBED GET mykey"), Value);
+}
+TEST_GPU(parsed_similar_with_ident_key, "QR:10766") {
+    Router r;
+    REQUIRE(r.execute("EMBED vec1 [1.0, 0.0]").ok);
+    REQUIRE_KIND(r.execute_parsed("SIMILAR vec1 LIMIT 5"), Similar);
+}
+TEST_HOST(parsed_embed_delete_nonexistent, "QR:10815") {
+    Router r;
+    REQUIRE(!r.execute_parsed("EMBED DELETE 'nonexistent'").ok);
+}
+TEST_HOST(parsed_embed_non_number_vector, "QR:10887") {
+    Router r;
+    REQUIRE(!r.execute_parsed("EMBED STORE 'k' ['a', 'b']").ok);
+}
+TEST_HOST(parsed_embed_batch_basic, "QR:12916") {
+    Router r;
+    auto o = r.execute_parsed("EMBED BATCH [('doc1', [1.0, 0.0]), ('doc2', [0.0, 1.0]), ('doc3', [0.5, 0.5])]");
+    REQUIRE_KIND(o, Count);
+    REQUIRE(o.result.count == 3);
+    REQUIRE(r.execute_parsed("EMBED GET 'doc1'").ok);
+}
+TEST_HOST(parsed_embed_batch_empty, "QR:12935") {
+    Router r;
+    auto o = r.execute_parsed("EMBED BATCH []");
+    REQUIRE_KIND(o, Count);
+    REQUIRE(o.result.count == 0);
+}
+TEST_HOST(parsed_embed_store_into_collection, "QR:16287") {
+    Router r;
+    REQUIRE(r.execute_parsed("EMBED STORE 'doc1' [1.0, 2.0, 3.0] INTO my_collection").ok);
+    REQUIRE_KIND(r.execute_parsed("EMBED GET 'doc1' INTO my_collection"), Value);
+    REQUIRE(!r.engine.exists("doc1"));  // the default space is a different namespace
+}
+TEST_HOST(parsed_embed_delete_from_collection, "QR:16303") {
+    Router r;
+    REQUIRE(r.execute_parsed("EMBED STORE 'to_delete' [1.0, 2.0] INTO test_coll").ok);
+    auto o = r.execute_parsed("EMBED DELETE 'to_delete' INTO test_coll");
+    REQUIRE_KIND(o, Count);
+    REQUIRE(o.result.count == 1);
+    REQUIRE(!r.execute_parsed("EMBED GET 'to_delete' INTO test_coll").ok);
+}
+TEST_GPU(parsed_similar_into_collection, "QR:16323") {
+    Router r;
+    REQUIRE(r.execute_parsed("EMBED STORE 'vec_a' [1.0, 0.0, 0.0] INTO vectors").ok);
+    REQUIRE(r.execute_parsed("EMBED STORE 'vec_b' [0.9, 0.1, 0.0] INTO vectors").ok);
+    REQUIRE(r.execute_parsed("EMBED STORE 'vec_c' [0.0, 1.0, 0.0] INTO vectors").ok);
+    auto o = r.execute_parsed("SIMILAR [1.0, 0.0, 0.0] LIMIT 3 INTO vectors");
+    REQUIRE_KIND(o, Similar);
+    REQUIRE(o.result.similar.size() == 3);
+    REQUIRE(o.result.similar[0].key == "vec_a");
+}
+TEST_GPU(parsed_similar_with_where_clause, "QR:16378") {
+    Router r;
+    REQUIRE_OK(r.engine.store_embedding_with_metadata("item_a", {1.0f, 0.0f}, meta({{"category", S("science")}})));
+    REQUIRE_OK(r.engine.store_embedding_with_metadata("item_b", {0.9f, 0.1f}, meta({{"category", S("tech")}})));
+    REQUIRE_OK(r.engine.store_embedding_with_metadata("item_c", {0.8f, 0.2f}, meta({{"category", S("science")}})));
+    auto o = r.execute_parsed("SIMILAR [1.0, 0.0] LIMIT 10 WHERE category = 'science'");
+    REQUIRE_KIND(o, Similar);
+    REQUIRE(o.result.similar.size() == 2);
+    for (const auto &x : o.result.similar) REQUIRE(x.key == "item_a" || x.key == "item_c");
+}
+TEST_HOST(parsed_embed_batch_into_collection, "QR:16432") {
+    Router r;
+    auto o = r.execute_parsed("EMBED BATCH [('b1', [1.0, 2.0]), ('b2', [3.0, 4.0])] INTO batch_test");
+    REQUIRE_KIND(o, Count);
+    REQUIRE(o.result.count == 2);
+    REQUIRE(r.execute_parsed("EMBED GET 'b1' INTO batch_test").ok);
+    REQUIRE(r.execute_parsed("EMBED GET 'b2' INTO batch_test").ok);
+}
+TEST_GPU(test_similar_in_collection, "QR:19912") {
+    // `COLLECTION 'grp'` and `TOP 2` are not part of either statement's grammar: the parser stops
+    // after the vector, so c1 / c2 land in the default space and the search runs there
+    Router r;
+    REQUIRE(r.execute_parsed("EMBED STORE 'c1' [1.0, 0.0] COLLECTION 'grp'").ok);
+    REQUIRE(r.execute_parsed("EMBED STORE 'c2' [0.9, 0.1] COLLECTION 'grp'").ok);
+    auto o = r.execute_parsed("SIMILAR [1.0, 0.0] TOP 2 COLLECTION 'grp'");
+    REQUIRE_KIND(o, Similar);
+    REQUIRE(!o.result.similar.empty());
+    REQUIRE(r.engine.exists("c1") && !r.engine.collection_exists("grp"));
 }
 
 }  // namespace
