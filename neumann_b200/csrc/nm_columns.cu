@@ -72,6 +72,8 @@ int mask_pool_prepare(Shard &sh) {
     std::lock_guard<std::mutex> g(sh.mask_mu);
     for (auto it = sh.mask_free.begin(); it != sh.mask_free.end();)
         it = (*it)->words_cap < cap ? sh.mask_free.erase(it) : it + 1;
+    for (auto it = sh.mask_cache.begin(); it != sh.mask_cache.end();)  // (stale as well: the shard grew)
+        it = (*it)->words_cap < cap ? sh.mask_cache.erase(it) : it + 1;
     while (sh.mask_cache.size() + sh.mask_free.size() < kMaskPoolEntries) {
         std::shared_ptr<MaskEntry> e;
         if (int rc = mask_entry_alloc(sh, 0, &e)) return rc;
@@ -275,7 +277,10 @@ int shard_mask(nm_index *idx, Shard &sh, Workspace &ws, const MaskSpec &spec, ui
         for (auto it = sh.mask_cache.begin(); it != sh.mask_cache.end();) {
             if ((*it)->epoch != epoch) {
                 // stale: keep its buffers for the next new filter unless a search still holds it
-                if (it->use_count() == 1 && sh.mask_free.size() < kMaskPoolEntries) sh.mask_free.push_back(*it);
+                // (buffers sized for a smaller capacity are of no use any more: let them go)
+                if (it->use_count() == 1 && sh.mask_free.size() < kMaskPoolEntries &&
+                    (*it)->words_cap >= shard_mask_words_cap(sh))
+                    sh.mask_free.push_back(*it);
                 it = sh.mask_cache.erase(it);
                 continue;
             }
@@ -345,7 +350,8 @@ int shard_mask(nm_index *idx, Shard &sh, Workspace &ws, const MaskSpec &spec, ui
     {
         std::lock_guard<std::mutex> g(sh.mask_mu);
         if (sh.mask_cache.size() >= kMaskCacheEntries) {
-            if (sh.mask_cache.front().use_count() == 1 && sh.mask_free.size() < kMaskPoolEntries)
+            if (sh.mask_cache.front().use_count() == 1 && sh.mask_free.size() < kMaskPoolEntries &&
+                sh.mask_cache.front()->words_cap >= shard_mask_words_cap(sh))
                 sh.mask_free.push_back(sh.mask_cache.front());
             sh.mask_cache.erase(sh.mask_cache.begin());
         }

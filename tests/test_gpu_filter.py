@@ -203,6 +203,30 @@ def test_filter_mask_at_the_edges_of_a_mask_block(n):
     idx.close()
 
 
+def test_filter_masks_survive_growth_of_the_shard():
+    """The mask buffers come from a per-shard pool sized for the shard's capacity: after appends
+    that grow the mirror, many more distinct filters than the pool holds must still evaluate
+    correctly (undersized buffers are dropped, not recycled)."""
+    d = 8
+    idx = DeviceIndex(d)
+    rows = o.fill_synthetic(40_000, d, 21)
+    idx.load(rows[:1000])
+    a = (np.arange(40_000) * 7919) % 1000
+    idx.column_set(1, 0, np.full(1000, NM_V_INT, np.uint8), a[:1000].astype(np.uint64))
+    for lim in (10, 500, 900):
+        assert np.array_equal(idx.filter_mask([cmp_op(1, NM_C_LT, lim)], None), a[:1000] < lim)
+    idx.append(rows[1000:])                                   # 40x: the mirror and every column grow
+    idx.column_set(1, 1000, np.full(39_000, NM_V_INT, np.uint8), a[1000:].astype(np.uint64))
+    built0 = idx.stats().filter_masks_built
+    for j in range(30):                                       # > 12 pool entries, > 8 cached masks
+        lim = 17 + 31 * j
+        assert np.array_equal(idx.filter_mask([cmp_op(1, NM_C_LT, lim)], None), a < lim), lim
+    assert idx.stats().filter_masks_built - built0 == 30
+    (g,) = idx.search_filtered(rows[5], 3, "cosine", [cmp_op(1, NM_C_EQ, int(a[5]))])
+    assert g[0][0] == 5
+    idx.close()
+
+
 @pytest.mark.parametrize("metric", ["cosine", "euclidean", "dot"])
 def test_search_filtered_equals_the_oracle_on_the_subset(metric):
     n, d, k = 90_000, 48, 12
