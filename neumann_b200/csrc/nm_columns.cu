@@ -173,6 +173,8 @@ int columns_scatter(nm_index *idx, const ColumnsSnapshot &snap) {
             sh.mask_cache.clear();
         }
         if (!sh.rows) continue;
+        if (!snap.cols.empty())
+            if (int rc = mask_pool_prepare(sh)) return rc;  // the shard's capacity may have changed
         for (auto &kv : snap.cols) {
             Column &c = column_of(sh, kv.first);
             int rc = column_reserve(sh, c, sh.rows);
