@@ -4,8 +4,9 @@
 //                         parse_similar_args QR:6903-6929, execute_embed QR:6617-6630
 //   execute_parsed     -> AST path             exec_similar QR:5316-5451 with the grammar of
 //                         neumann_parser/src/parser.rs:1853-1919
-// Everything else the router dispatches (SQL, graph, vault, blob, chain, CONNECTED TO, WHERE
-// filters) is out of scope and reported as an error, not silently ignored.
+// Everything else the router dispatches (SQL, graph, vault, blob, chain, SIMILAR ... CONNECTED TO)
+// is out of scope and reported as an error, not silently ignored.  tests/cpp/reference_suite.cpp
+// replays the reference's SIMILAR / EMBED router tests against this class.
 #pragma once
 #include <string>
 #include <vector>
