@@ -5,8 +5,9 @@
 // reference's assertions.  Tests of subsystems outside SURVEY §8 (HNSW / IVF / PQ wrappers,
 // persistence, TensorStore plumbing) are not here.
 //
-// The last section does the same for the SIMILAR / EMBED tests of query_router/src/lib.rs against
-// neumann::QueryRouter (similar_router.hpp).
+// The last sections do the same for the SIMILAR / EMBED tests of query_router/src/lib.rs against
+// neumann::QueryRouter (similar_router.hpp) and for the PointsService::query cases of
+// neumann_server/tests/grpc_vector_points.rs against VectorEngine::query_points.
 //
 // Test infrastructure: built and run by tests/test_cpp_reference_suite.py
 //   g++ -std=c++17 tests/cpp/reference_suite.cpp -Ineumann_b200/csrc -Iinclude -Lneumann_b200 -lneumann_b200
@@ -1961,6 +1962,98 @@ TEST_GPU(test_similar_in_collection, "QR:19912") {
     REQUIRE_KIND(o, Similar);
     REQUIRE(!o.result.similar.empty());
     REQUIRE(r.engine.exists("c1") && !r.engine.collection_exists("grp"));
+}
+
+// ---------------------------------------------------------------------------------------------
+// gRPC PointsService::query (neumann_server/tests/grpc_vector_points.rs; "GP" below): the
+// post-processing of points.rs:449-485 is VectorEngine::query_points here, the transport is not.
+// ---------------------------------------------------------------------------------------------
+static void setup_test_collection(VectorEngine &e, const std::string &name, size_t dimension) {  // GP:75-88
+    e.create_collection(name, VectorCollectionConfig{}.with_dimension(dimension));
+}
+static void upsert_test_points(VectorEngine &e, const std::string &collection, size_t count, size_t dimension) {  // GP:91-112
+    for (size_t i = 0; i < count; ++i) {
+        Vec v(dimension);
+        for (size_t j = 0; j < dimension; ++j) v[j] = (float)(i * 10 + j) / 10.0f;
+        e.store_in_collection(collection, key_of("point_", i), v);
+    }
+}
+TEST_GPU(test_points_query_basic, "GP:336") {
+    VectorEngine engine;
+    setup_test_collection(engine, "test_query", 3);
+    upsert_test_points(engine, "test_query", 10, 3);
+    auto r = engine.query_points("test_query", {0.5f, 1.0f, 1.5f}, 5, 0, std::nullopt, false);
+    REQUIRE_OK(r);
+    REQUIRE(r.value().size() <= 5 && !r.value().empty());
+    for (size_t i = 1; i < r.value().size(); ++i) REQUIRE(r.value()[i - 1].score >= r.value()[i].score);
+}
+TEST_GPU(test_points_query_with_offset, "GP:371") {
+    VectorEngine engine;
+    setup_test_collection(engine, "test_query_offset", 3);
+    upsert_test_points(engine, "test_query_offset", 10, 3);
+    auto r = engine.query_points("test_query_offset", {0.0f, 0.0f, 0.0f}, 3, 2, std::nullopt, false);
+    REQUIRE_OK(r);
+    REQUIRE(r.value().size() <= 3);
+    // with a query that has a direction: the page is ranks [2, 5) of the unpaged search
+    auto full = engine.search_in_collection("test_query_offset", {0.5f, 1.0f, 1.5f}, 10);
+    auto page = engine.query_points("test_query_offset", {0.5f, 1.0f, 1.5f}, 3, 2, std::nullopt, false);
+    REQUIRE_OK(full);
+    REQUIRE_OK(page);
+    REQUIRE(page.value().size() == 3);
+    for (size_t i = 0; i < 3; ++i) REQUIRE(page.value()[i].id == full.value()[i + 2].key);
+}
+TEST_GPU(test_points_query_with_score_threshold, "GP:402") {
+    VectorEngine engine;
+    setup_test_collection(engine, "test_query_threshold", 3);
+    upsert_test_points(engine, "test_query_threshold", 10, 3);
+    auto r = engine.query_points("test_query_threshold", {0.0f, 0.0f, 0.0f}, 10, 0, 0.8f, false);
+    REQUIRE_OK(r);
+    for (const auto &p : r.value()) REQUIRE(p.score >= 0.8f);
+    // (a query with a direction: cos = 0.956, 0.951, 0.940, ... for point_0, point_1, point_2, ...)
+    r = engine.query_points("test_query_threshold", {0.5f, 1.0f, 1.5f}, 10, 0, 0.945f, true);
+    REQUIRE_OK(r);
+    REQUIRE(r.value().size() == 2);
+    for (const auto &p : r.value()) REQUIRE(p.score >= 0.945f && p.vector.size() == 3);
+}
+TEST_HOST(test_points_query_empty_collection, "GP:436") {
+    VectorEngine engine;
+    setup_test_collection(engine, "test_query_empty", 3);
+    auto r = engine.query_points("test_query_empty", {1.0f, 2.0f, 3.0f}, 5, 0, std::nullopt, false);
+    REQUIRE_OK(r);
+    REQUIRE(r.value().empty());
+}
+TEST_HOST(test_points_query_missing_collection, "GP:604") {
+    VectorEngine engine;
+    auto r = engine.query_points("nonexistent_collection", {1.0f, 2.0f, 3.0f}, 5, 0, std::nullopt, false);
+    REQUIRE_OK(r);  // "VectorEngine returns Ok with empty results for non-existent collections"
+    REQUIRE(r.value().empty());
+}
+TEST_GPU(test_points_operation_after_collection_delete, "GP:629") {
+    VectorEngine engine;
+    setup_test_collection(engine, "test_deleted", 3);
+    upsert_test_points(engine, "test_deleted", 5, 3);
+    auto before = engine.query_points("test_deleted", {1.0f, 2.0f, 3.0f}, 5, 0, std::nullopt, false);
+    REQUIRE_OK(before);
+    REQUIRE(!before.value().empty());
+    REQUIRE_OK(engine.delete_collection("test_deleted"));
+    auto after = engine.query_points("test_deleted", {1.0f, 2.0f, 3.0f}, 5, 0, std::nullopt, false);
+    REQUIRE_OK(after);
+    REQUIRE(after.value().empty());
+}
+TEST_GPU(test_points_concurrent_query, "GP:901") {
+    VectorEngine engine;
+    setup_test_collection(engine, "test_concurrent_query", 3);
+    upsert_test_points(engine, "test_concurrent_query", 20, 3);
+    std::atomic<int> ok{0};
+    std::vector<std::thread> ts;
+    for (int i = 0; i < 5; ++i)
+        ts.emplace_back([&, i] {
+            auto r = engine.query_points("test_concurrent_query", {(float)i, (float)i + 1.0f, (float)i + 2.0f}, 5, 0,
+                                         std::nullopt, false);
+            if (r.is_ok() && r.value().size() == 5) ++ok;
+        });
+    for (auto &t : ts) t.join();
+    REQUIRE(ok == 5);
 }
 
 }  // namespace
