@@ -2056,6 +2056,19 @@ TEST_GPU(test_points_concurrent_query, "GP:901") {
     REQUIRE(ok == 5);
 }
 
+// ---------------------------------------------------------------------------------------------
+// tensor_store::hnsw::simd — the host restatement the zero-query short-circuit and
+// compute_similarity use (tensor_store/src/hnsw.rs tests; "TS" below)
+// ---------------------------------------------------------------------------------------------
+TEST_HOST(test_simd_dot_product, "TS/hnsw.rs:2801") {
+    const float a[4] = {1.0f, 2.0f, 3.0f, 4.0f}, b[4] = {1.0f, 1.0f, 1.0f, 1.0f};
+    REQUIRE(std::fabs(simd::dot_product(a, b, 4) - 10.0f) < 1e-6f);
+}
+TEST_HOST(test_simd_magnitude, "TS/hnsw.rs:2809") {
+    const float v[2] = {3.0f, 4.0f};
+    REQUIRE(std::fabs(simd::magnitude(v, 2) - 5.0f) < 1e-6f);
+}
+
 }  // namespace
 
 int main(int argc, char **argv) {
