@@ -31,6 +31,26 @@ def test_reference_arm_scores_the_full_corpus_in_both_modes():
     assert res["last_result_rows"] == chk["last_result_rows"]
 
 
+def test_reference_arm_under_torchrun_prints_one_line_from_rank_0():
+    """The driver launches the reference arm like the GPU arm — for N > 1 through torchrun.  Rank 0
+    alone runs it and prints ONE JSON line (n_gpus as asked); the other ranks exit 0 without work."""
+    import socket
+    with socket.socket() as sk:
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+           "--master-addr", "127.0.0.1", "--master-port", str(port), str(ROOT / "bench.py"),
+           "--impl", "reference", "--gpus", "2", "--rows", "40000", "--dim", "64", "--steps", "2", "--warmup", "1"]
+    r = subprocess.run(cmd, env=dict(os.environ, NM_BENCH_REF_MODE="resident"), capture_output=True, text=True,
+                       timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1, r.stdout
+    line = json.loads(lines[0])
+    assert line["impl"] == "reference" and line["n_gpus"] == 2 and line["gpu_launches"] == 0
+    assert line["config"]["rows"] == 40000 and line["value"] > 0 and line["e2e"]["value"] == line["value"]
+
+
 # ---- the parity machinery of the GPU arm, on CPU: chunked oracle per shard + merge over ranks ----
 class _FakeShard:
     """Stands in for a DeviceIndex shard: get_rows() serves the synthetic corpus from the host."""
