@@ -806,7 +806,7 @@ TEST_HOST(pagination_default, "lib.rs:6163") {
     REQUIRE(p.skip == 0 && !p.limit.has_value() && !p.count_total);
 }
 static void store_ten(VectorEngine &engine) {
-    char buf[8];
+    char buf[16];
     for (int i = 0; i < 10; ++i) {
         std::snprintf(buf, sizeof buf, "v%02d", i);
         engine.store_embedding(buf, {(float)i});
